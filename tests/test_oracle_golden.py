@@ -1,0 +1,241 @@
+"""Pin the CPU oracle (oracle/*.c) against the reference's golden vectors.
+
+CPU-only.  Sources of truth:
+  * ref_pickles_{f8,f4}.npz : the reference's own pickled golden vectors
+    (pisa/stages/osc/prob3numba/numba_osc_tests.py:263-318, data dir :326)
+  * ref_prob3/layers/hist    : outputs of the unmodified reference run in the build
+    container by tests/golden/make_golden.py
+Tolerances are the reference's own AC_KW (numba_osc_tests.py:82).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from conftest import AC_KW_F4, AC_KW_F8, load_golden
+
+CASES = [
+    "nufit32_no", "nufit32_no_nubar", "nufit32_no_E1TeV", "nufit32_no_blearth", "nufit32_io",
+    "nufit32_std_nsi_no", "nufit32_vac_nsi_no", "nufit32_std_decay_no", "nufit32_lri_std_mat",
+    "nufit32_mass_of_earth_no", "nufit32_mass_of_core_w_constrain_no",
+    "nufit32_mass_of_core_wo_constrain_no",
+]  # nufit32_std_decay (decay_flag=1 -> eigvals branch) is out of scope
+
+
+def _tag(dtype):
+    return ("f8", AC_KW_F8) if dtype == np.float64 else ("f4", AC_KW_F4)
+
+
+@pytest.mark.parametrize("dtype", [np.float64])
+@pytest.mark.parametrize("case", CASES)
+def test_propagate_scalar_pickles(case, dtype):
+    tag, kw = _tag(dtype)
+    g = load_golden("ref_pickles_%s.npz" % tag)
+    p = "propagate_scalar/%s/" % case
+    out = oracle.propagate_array(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], g[p + "decay_flag"],
+                                 g[p + "mat_decay"], g[p + "lri_pot"], g[p + "nubar"],
+                                 g[p + "energy"], g[p + "densities"][None], g[p + "distances"][None],
+                                 dtype=dtype)[0]
+    assert np.allclose(out, g[p + "probability"], **kw), np.abs(out - g[p + "probability"]).max()
+    # unitarity (numba_osc_tests.py:457-470)
+    assert np.allclose(out.sum(axis=0), 1, **kw) and np.allclose(out.sum(axis=1), 1, **kw)
+
+
+@pytest.mark.parametrize("dtype", [np.float64])
+@pytest.mark.parametrize("case", CASES)
+def test_subfunction_pickles(case, dtype):
+    tag, kw = _tag(dtype)
+    g = load_golden("ref_pickles_%s.npz" % tag)
+    p = "get_H_vac_hostfunc/%s/" % case
+    out = oracle.get_H_vac(g[p + "mix_nubar"], g[p + "mix_nubar_conj_transp"], g[p + "dm_vac_vac"], dtype)
+    assert np.allclose(out, g[p + "H_vac"], **kw)
+    p = "get_H_mat_hostfunc/%s/" % case
+    out = oracle.get_H_mat(g[p + "rho"], g[p + "mat_pot"], g[p + "nubar"], dtype)
+    assert np.allclose(out, g[p + "H_mat"], **kw)
+    p = "get_dms_hostfunc/%s/" % case
+    if p + "H_full" in g.files:
+        dmm, dmat = oracle.get_dms(g[p + "energy"], g[p + "H_full"], g[p + "dm_vac_vac"], dtype)
+        assert np.allclose(dmm, g[p + "dm_mat_mat"], **kw)
+        assert np.allclose(dmat, g[p + "dm_mat"], **kw)
+    p = "product_hostfunc/%s/" % case
+    out = oracle.get_product(g[p + "energy"], g[p + "dm_mat"], g[p + "dm_mat_mat"],
+                             g[p + "H_full_mass_eigenstate_basis"], dtype)
+    assert np.allclose(out, g[p + "product"], **kw)
+    p = "get_transition_matrix_massbasis_hostfunc/%s/" % case
+    out = oracle.get_transition_matrix_massbasis(g[p + "baseline"], g[p + "energy"], g[p + "dm_mat"],
+                                                 g[p + "dm_mat_mat"],
+                                                 g[p + "H_full_mass_eigenstate_basis"], dtype)
+    assert np.allclose(out, g[p + "transition_matrix"], **kw)
+    p = "get_transition_matrix_hostfunc/%s/" % case
+    out = oracle.get_transition_matrix(g[p + "nubar"], g[p + "energy"], g[p + "rho"], g[p + "baseline"],
+                                       g[p + "mix_nubar"], g[p + "mix_nubar_conj_transp"],
+                                       g[p + "mat_pot"], g[p + "H_vac"], g[p + "decay_flag"],
+                                       g[p + "H_decay"], g[p + "lri_pot"], g[p + "dm"], dtype)
+    assert np.allclose(out, g[p + "transition_matrix"], **kw)
+    # |T|^2 unitarity (numba_osc_tests.py:498-517)
+    t2 = np.abs(out) ** 2
+    assert np.allclose(t2.sum(axis=0), 1, **kw) and np.allclose(t2.sum(axis=1), 1, **kw)
+
+
+def _layers_cases(g):
+    return sorted({k.rsplit("/", 1)[0] for k in g.files})
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_layers_vs_reference(dtype):
+    tag, _ = _tag(dtype)
+    g = load_golden("ref_layers_%s.npz" % tag)
+    for key in _layers_cases(g):
+        model = key.split("/")[0]
+        depth, height, yei, yeo, yem = g[key + "/params"]
+        prem = np.loadtxt("pisa_b200/resources/osc/%s.dat" % model) if False else None
+        import os
+        from conftest import ROOT
+        prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", model + ".dat"))
+        L = oracle.OracleLayers(prem, depth, height, dtype=dtype)
+        L.setElecFrac(yei, yeo, yem)
+        assert np.array_equal(L.radii, g[key + "/radii"])
+        assert np.array_equal(L.rhos, g[key + "/rhos"])
+        assert np.array_equal(L.coszen_limit, g[key + "/coszen_limit"])
+        assert L.max_layers == int(g[key + "/max_layers"])
+        # cz EXACTLY equal to a tangent direction is excluded: there the reference's masks say
+        # "not crossed" while its un-masked large root sqrt(+7e-9) > 0 survives the `> 0`
+        # filter (layers.py:115,128), so it emits an unsorted path with a negative segment
+        # (e.g. -2947 km).  Measure-zero reference defect, kept out of parity sets.
+        cz = g[key + "/cz"]
+        tangents = L.coszen_limit[(L.coszen_limit > -1) & (L.coszen_limit < 1)]
+        ok = ~np.isin(cz, tangents)
+        assert ok.sum() >= len(cz) - 3 * len(tangents)  # f4: the +-1ulp(f8) neighbours collapse
+        n, den, dis = L.calcLayers(cz[ok])
+        assert np.array_equal(n, g[key + "/n_layers"][ok]), key
+        assert np.array_equal(den, g[key + "/density"][ok]), key
+        # bit-exact: same IEEE operations in the same order
+        ref = g[key + "/distance"][ok]
+        if dtype == np.float64:
+            assert np.array_equal(dis, ref), (key, np.abs(dis - ref).max())
+        else:
+            # numba's float32/float64 promotion inside extCalcLayers is only modelled
+            # approximately: allow 2 float32 ulps on the stored distances
+            assert np.allclose(dis, ref, rtol=2.5e-7, atol=1e-6), (key, np.abs(dis - ref).max())
+
+
+def test_layers_closed_form():
+    """Numbers asserted by the reference's own test_layers_2/3 (layers.py:552-554, 566-575,
+    617-665), at its ALLCLOSE_KW (rtol 1e-12, atol eps)."""
+    import os
+    from conftest import ROOT
+    kw = dict(rtol=1e-12, atol=2.220446049250313e-16)
+    prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_4layer.dat"))
+    L = oracle.OracleLayers(prem, 1.0, 20.0)
+    ref = np.array([1., 1., -0.4461133826191877, -0.8375825182106081, -0.9814881717430358, -1.])
+    assert np.allclose(L.coszen_limit, ref, **kw)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    # test_layers_2: total vacuum path for 8 zenith angles == sum of the segments
+    cz = np.cos(np.array([0., 36. * np.pi / 180., 63. * np.pi / 180., np.pi / 2., 105. * np.pi / 180.,
+                          125. * np.pi / 180., 170 * np.pi / 180., np.pi]))
+    correct_length = np.array([21., 25.934954968613056, 45.9673929915939, 517.6688130455607,
+                               3376.716060094899, 7343.854310588515, 12567.773643090592, 12761.])
+    _, _, dis = L.calcLayers(cz)
+    assert np.allclose(dis.sum(axis=1), correct_length, rtol=1e-12)
+    # test_layers_3: per-layer segments for cz = 1, 0, first tangent, -1
+    _, den, dis = L.calcLayers(np.array([1., 0, -0.4461133826191877, -1.]))
+    z = [0.0] * 10
+    assert np.allclose(dis[0], [20., 1.] + z, **kw)
+    assert np.allclose(dis[1], [404.79277484435556, 112.87603820120549] + z, **kw)
+    assert np.allclose(dis[2], [44.525143211129944, 5685.725369597015] + z, **kw)
+    assert np.allclose(dis[3], [20., 670., 2221., 2260., 2440., 2260., 2221., 669., 0, 0, 0, 0], **kw)
+    # setElecFrac idempotence (test_layers_4, layers.py:669-772)
+    rhos = L.rhos.copy()
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    assert np.array_equal(rhos, L.rhos)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_f4_pickles_vs_f64_oracle(case):
+    """The reference's FP32 golden vectors against the FP64 oracle on the same (float32-valued)
+    inputs.  The prob3 oracle is FP64 only (prob3_oracle.c header); this documents how far the
+    reference's own mixed-precision FP32 path is from FP64 on its golden cases."""
+    g = load_golden("ref_pickles_f4.npz")
+    p = "propagate_scalar/%s/" % case
+    out = oracle.propagate_array(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], g[p + "decay_flag"],
+                                 g[p + "mat_decay"], g[p + "lri_pot"], g[p + "nubar"],
+                                 g[p + "energy"], g[p + "densities"][None], g[p + "distances"][None])[0]
+    err = np.abs(out - g[p + "probability"]).max()
+    # nufit32_no_blearth uses a 1.3e7 km baseline (phases ~1e5 rad): float32 inputs alone move it
+    assert err < (5e-3 if case == "nufit32_no_blearth" else 1e-4), err
+
+
+@pytest.mark.parametrize("dtype", [np.float64])
+def test_propagate_array_vs_reference(dtype):
+    tag, kw = _tag(dtype)
+    g = load_golden("ref_prob3_%s.npz" % tag)
+    import os
+    from conftest import ROOT
+    prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat"))
+    depth, height, yei, yeo, yem = g["earth"]
+    L = oracle.OracleLayers(prem, depth, height, dtype=dtype)
+    L.setElecFrac(yei, yeo, yem)
+    _, den, dis = L.calcLayers(g["coszen"])
+    assert np.array_equal(den[:64], g["densities"]) and np.array_equal(dis[:64], g["distances"])
+    keys = sorted({k.rsplit("/", 1)[0] for k in g.files if k.count("/") == 2})
+    assert len(keys) == 13
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    for key in keys:
+        out = oracle.propagate_array(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], -1, zero,
+                                     g[key + "/lri_pot"], g[key + "/nubar"], g["energy"], den, dis,
+                                     dtype=dtype, n_threads=4)
+        ref = g[key + "/probability"]
+        if dtype == np.float64:
+            assert np.allclose(out, ref, **kw), (key, np.abs(out - ref).max())
+        else:
+            # the FP32 reference amplifies libm/rounding differences (its own
+            # f4-vs-f8 distance is 7e-5); require the bulk to agree at the reference tolerance
+            err = np.abs(out - ref)
+            assert np.percentile(err, 99) < 1e-4 and err.max() < 2e-3, (key, err.max())
+
+
+def test_find_index_and_lookup_vs_reference():
+    g = load_golden("ref_hist_f8.npz")
+    for name in ("lin", "log", "irr", "one", "inf"):
+        idx = oracle.find_index(g["find_index/%s/vals" % name], g["find_index/%s/edges" % name])
+        assert np.array_equal(idx, g["find_index/%s/idx" % name]), name
+    x, y, z = g["lookup/x"], g["lookup/y"], g["lookup/z"]
+    x0, x1, nx, y0, y1, ny, z0, z1, nz = g["lookup/binning"]
+    i1, _ = oracle.regular_index([x], [x0], [x1], [nx])
+    i2, _ = oracle.regular_index([x, y], [x0, y0], [x1, y1], [nx, ny])
+    i3, _ = oracle.regular_index([x, y, z], [x0, y0, z0], [x1, y1, z1], [nx, ny, nz])
+    # Events whose raw index rounds up to n (x < hi but (x-lo)*norm == n): the reference's
+    # lookup_regular_* then reads flat_hist out of bounds (the fixture holds a denormal
+    # garbage value for y = nextafter(1, 0)); the oracle folds them into the last bin.
+    # They are excluded here and counted (DESIGN.md "parity-unpinned edge cases").
+    def rounds_up(v, lo, hi, n):
+        return (v >= lo) & (v < hi) & (((v - lo) * (n / (hi - lo))).astype(np.int64) >= n)
+    bad = rounds_up(x, x0, x1, nx) | rounds_up(y, y0, y1, ny) | rounds_up(z, z0, z1, nz)
+    assert 1 <= bad.sum() <= 3
+    ok = ~bad
+    assert np.array_equal(oracle.lookup(i1, g["lookup/h1"])[ok], g["lookup/o1"][ok])
+    assert np.array_equal(oracle.lookup(i2, g["lookup/h2"])[ok], g["lookup/o2"][ok])
+    assert np.array_equal(oracle.lookup(i3, g["lookup/h3"])[ok], g["lookup/o3"][ok])
+    assert np.array_equal(oracle.lookup(i2, g["lookup/h2a"])[ok], g["lookup/o2a"][ok])
+
+
+def test_histogram_vs_numpy_histogramdd():
+    """translation.py:779-818 test_histogram: histogram() == np.histogramdd (rtol 1e-12)."""
+    g = load_golden("ref_hist_f8.npz")
+    s, w = g["histdd/sample"], g["histdd/weights"]
+    for d, nb in ((1, (10,)), (2, (10, 7)), (3, (10, 7, 5))):
+        coords = [s[:, i] for i in range(d)]
+        hw = oracle.histogram_regular(coords, w, [0.0] * d, [1.0] * d, nb)
+        hc = oracle.histogram_regular(coords, None, [0.0] * d, [1.0] * d, nb)
+        assert np.allclose(hw, g["histdd/%dd/weighted" % d].ravel(), rtol=1e-12, atol=2.2e-16)
+        assert np.array_equal(hc, g["histdd/%dd/counts" % d].ravel())
+
+
+def test_digitize_irregular_matches_numpy():
+    rng = np.random.default_rng(3)
+    edges = np.array([5.62341325, 7.49894209, 10.0, 13.33521432, 17.7827941, 23.71373706,
+                      31.6227766, 42.16965034, 56.23413252])
+    x = np.concatenate([edges, np.nextafter(edges, 0), np.nextafter(edges, 100), rng.uniform(1, 80, 1000),
+                        [np.nan, np.inf, -np.inf]])
+    ref = np.searchsorted(edges, x, side="right") - 1
+    ref[x == edges[-1]] -= 1
+    assert np.array_equal(oracle.digitize_irregular(x, edges), ref)
