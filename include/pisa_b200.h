@@ -1,0 +1,216 @@
+/*
+ * pisa_b200.h -- C ABI of the B200-native oscillation-reweighting + histogramming path.
+ *
+ * Drop-in boundary for the hot path of icecube/pisa (reference citations are
+ * relative to the reference repository root):
+ *
+ *   osc.prob3 / prob3numba   pisa/stages/osc/prob3.py:329-622,
+ *                            pisa/stages/osc/prob3numba/numba_osc_hostfuncs.py:60-70,206-221,
+ *                            pisa/stages/osc/prob3numba/numba_osc_kernels.py:121-872
+ *   Earth layers             pisa/stages/osc/layers.py:38-169,308-335
+ *   utils.hist / histogram   pisa/stages/utils/hist.py:62-218,
+ *                            pisa/core/translation.py:90-223 (histogram),
+ *                            :228-501 (lookup), :503-597 (find_index)
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller (the Python
+ *     Stage classes hold them as torch tensors); struct pointers are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream).  Calls only
+ *     enqueue work; nothing synchronises unless stated.
+ *   - return value 0 = ok; non-zero = PISAB_ERR_*; pisab_last_error() gives the text
+ *     (thread-local).  There is no CPU fallback anywhere behind this interface.
+ *   - *_f64 / *_f32 select the storage type of event arrays (PISA_FTYPE,
+ *     pisa/__init__.py:152-179).  Parameter structs are always double.
+ */
+#ifndef PISA_B200_H
+#define PISA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PISAB_MAX_RADII 64   /* PREM_59layer + atmosphere = 61 shells                     */
+#define PISAB_MAX_LAYERS 120 /* hard cap of the reference, numba_osc_kernels.py:173-177,227 */
+#define PISAB_MAX_DIMS 4
+
+enum {
+    PISAB_OK = 0,
+    PISAB_ERR_ARG = 1,         /* bad argument (null pointer, negative size, ...)             */
+    PISAB_ERR_CUDA = 2,        /* CUDA runtime error; text in pisab_last_error()              */
+    PISAB_ERR_UNSUPPORTED = 3, /* branch of the reference that is out of scope (decay_flag=1, */
+                               /* non-Hermitian potential, Earth geometry the reference       */
+                               /* itself cannot process)                                      */
+    PISAB_ERR_WORKSPACE = 4    /* caller-provided workspace too small                         */
+};
+
+/* Argument list of `propagate_array` (numba_osc_hostfuncs.py:60-70), host side.
+ * Complex matrices are row-major [3][3][2] = (re, im). */
+typedef struct pisab_osc_consts {
+    double dm[9];         /* dm[i][j] = m_i^2 - m_j^2 (eV^2), OscParams.dm_matrix            */
+    double mix[18];       /* PMNS matrix (un-conjugated; nubar handling is internal)         */
+    double mat_pot[18];   /* generalised matter potential / a, diag(1|1.02,0,0) + eps        */
+    double mat_decay[18]; /* accepted for signature parity; only read when decay_flag == 1    */
+    double lri_pot[9];    /* long-range-interaction potential (eV), real symmetric            */
+    int64_t decay_flag;   /* -1 = standard oscillations (supported); +1 = decay (rejected)    */
+} pisab_osc_consts_t;
+
+/* What `Layers` holds after __init__/setElecFrac (layers.py:216-289,308-335):
+ * shells ordered surface (atmosphere shell) first. */
+typedef struct pisab_earth {
+    int32_t n_radii;
+    int32_t max_layers;                    /* 2 * n_radii (layers.py:244)                     */
+    double r_detector;                     /* r_earth - detector_depth (km)                   */
+    double radii[PISAB_MAX_RADII];         /* km, decreasing                                  */
+    double rho_e[PISAB_MAX_RADII];         /* electron-fraction weighted densities            */
+    double coszen_limit[PISAB_MAX_RADII];  /* tangent direction per shell (1 if r >= r_det)   */
+} pisab_earth_t;
+
+/* Regularised output binning as utils.hist builds it (hist.py:86-127): every
+ * dimension is either linear-regular in x, linear-regular in log(x), or given by
+ * explicit edges (irregular -> searchsorted).  Flat index is row-major. */
+enum { PISAB_DIM_LIN = 0, PISAB_DIM_LOG = 1, PISAB_DIM_EDGES = 2 };
+typedef struct pisab_binning {
+    int32_t n_dims;
+    int32_t kind[PISAB_MAX_DIMS];
+    int32_t n_bins[PISAB_MAX_DIMS];
+    double lo[PISAB_MAX_DIMS];             /* LIN: domain; LOG: log(domain) (hist.py:118-120) */
+    double hi[PISAB_MAX_DIMS];
+    const double *d_edges[PISAB_MAX_DIMS]; /* EDGES: device pointer to n_bins+1 edges         */
+} pisab_binning_t;
+
+/* ---- library ------------------------------------------------------------------------ */
+const char *pisab_last_error(void);
+const char *pisab_version(void);
+/* sm count / compute capability of the current device; fails without a CUDA device. */
+int pisab_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+
+/* ---- Earth layers: Layers.calcLayers / extCalcLayers (layers.py:38-169,339-363) ------- */
+/* d_densities, d_distances: [n, earth->max_layers], zero padded, ordered from the
+ * production point to the detector; bit-identical to the reference in FP64. */
+int pisab_layers_calc_f64(const pisab_earth_t *earth, const double *d_coszen, int64_t n,
+                          double *d_densities, double *d_distances, int32_t *d_n_layers,
+                          void *stream);
+int pisab_layers_calc_f32(const pisab_earth_t *earth, const float *d_coszen, int64_t n,
+                          float *d_densities, float *d_distances, int32_t *d_n_layers,
+                          void *stream);
+
+/* ---- propagate_array (numba_osc_hostfuncs.py:60-70) ------------------------------------ */
+/* Explicit layer arrays, exactly the gufunc's inputs.  nubar: scalar when d_nubar == NULL
+ * (aux scalar of a container, prob3.py:582), else per event (+1 / -1, int32).
+ * d_probability: [n,3,3], out[i][j] = P(nu_i -> nu_j). */
+int pisab_prob3_propagate_layers_f64(const pisab_osc_consts_t *consts, int32_t nubar,
+                                     const int32_t *d_nubar, const double *d_energy,
+                                     const double *d_densities, const double *d_distances,
+                                     int64_t n, int32_t n_layers, double *d_probability,
+                                     void *stream);
+int pisab_prob3_propagate_layers_f32(const pisab_osc_consts_t *consts, int32_t nubar,
+                                     const int32_t *d_nubar, const float *d_energy,
+                                     const float *d_densities, const float *d_distances,
+                                     int64_t n, int32_t n_layers, float *d_probability,
+                                     void *stream);
+
+/* Layers evaluated in-kernel from coszen (prob3.setup_function + compute_function fused,
+ * prob3.py:406-409,581-605).  Any of d_probability ([n,3,3]) or (d_prob_e, d_prob_mu)
+ * ([n] each, = fill_probs(probability, 0|1, flav), numba_osc_hostfuncs.py:206-221) may be
+ * NULL.  flav: scalar when d_flav == NULL. */
+int pisab_prob3_propagate_earth_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                    int32_t nubar, const int32_t *d_nubar, int32_t flav,
+                                    const int32_t *d_flav, const double *d_energy,
+                                    const double *d_coszen, int64_t n, double *d_probability,
+                                    double *d_prob_e, double *d_prob_mu, void *stream);
+int pisab_prob3_propagate_earth_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                    int32_t nubar, const int32_t *d_nubar, int32_t flav,
+                                    const int32_t *d_flav, const float *d_energy,
+                                    const float *d_coszen, int64_t n, float *d_probability,
+                                    float *d_prob_e, float *d_prob_mu, void *stream);
+
+/* fill_probs (numba_osc_hostfuncs.py:206-221): out[n] = probability[n, initial_flav, flav] */
+int pisab_fill_probs_f64(const double *d_probability, int32_t initial_flav, int32_t flav,
+                         int64_t n, double *d_out, void *stream);
+int pisab_fill_probs_f32(const float *d_probability, int32_t initial_flav, int32_t flav,
+                         int64_t n, float *d_out, void *stream);
+
+/* prob3.apply_function (prob3.py:621-622):
+ * weights *= nu_flux[:,0]*prob_e + nu_flux[:,1]*prob_mu ; d_nu_flux is [n,2]. */
+int pisab_apply_osc_weights_f64(const double *d_nu_flux, const double *d_prob_e,
+                                const double *d_prob_mu, int64_t n, double *d_weights,
+                                void *stream);
+int pisab_apply_osc_weights_f32(const float *d_nu_flux, const float *d_prob_e,
+                                const float *d_prob_mu, int64_t n, float *d_weights, void *stream);
+
+/* ---- histogramming (hist.py:129-218, translation.py:90-223,417-597) -------------------- */
+/* Flat row-major bin index per event, -1 when outside in any dimension.  d_coords[d] are
+ * device pointers to the n RAW sample values of dimension d (LOG dims are logged
+ * internally exactly like Container.translate, container.py:845-850). Bit-exact vs the
+ * reference rule `lo <= x < hi ; (int)((x-lo) * n/(hi-lo))` / searchsorted(right)-1. */
+int pisab_hist_index_f64(const pisab_binning_t *binning, const double *const *d_coords,
+                         int64_t n, int32_t *d_index, void *stream);
+int pisab_hist_index_f32(const pisab_binning_t *binning, const float *const *d_coords, int64_t n,
+                         int32_t *d_index, void *stream);
+
+/* Workspace (bytes) the accumulate / fused calls need for n events into n_bins bins. */
+int64_t pisab_hist_workspace_bytes(int64_t n, int32_t n_bins);
+
+/* hist[b] = sum w, hist_w2[b] = sum w^2 over events with index b (d_hist_w2 may be NULL).
+ * d_weights may be NULL (unweighted counts, hist.py:179-185).  Deterministic: fixed
+ * per-warp accumulation order and a fixed-order two-stage reduction (no float atomics)
+ * whenever n_bins <= PISAB_DET_MAX_BINS. Output is overwritten, always double. */
+#define PISAB_DET_MAX_BINS 1024
+int pisab_hist_accumulate_f64(const int32_t *d_index, const double *d_weights, int64_t n,
+                              int32_t n_bins, double *d_hist, double *d_hist_w2,
+                              void *d_workspace, int64_t workspace_bytes, void *stream);
+int pisab_hist_accumulate_f32(const int32_t *d_index, const float *d_weights, int64_t n,
+                              int32_t n_bins, double *d_hist, double *d_hist_w2,
+                              void *d_workspace, int64_t workspace_bytes, void *stream);
+
+/* lookup / Container.binned_to_array (translation.py:417-501, container.py:981-1012):
+ * out[n, width] = flat_hist[index[n], width], 0 outside. */
+int pisab_lookup_f64(const int32_t *d_index, const double *d_flat_hist, int64_t n, int32_t width,
+                     double *d_out, void *stream);
+int pisab_lookup_f32(const int32_t *d_index, const float *d_flat_hist, int64_t n, int32_t width,
+                     float *d_out, void *stream);
+
+/* ---- fused template evaluation (prob3 compute+apply and hist in one pass) -- */
+/* For every event: probabilities through the Earth (as *_propagate_earth), then
+ *   w = weights_in * (nu_flux[0]*prob_e + nu_flux[1]*prob_mu)       (prob3.py:621-622)
+ * and hist[index] += w, hist_w2[index] += w*w (hist.py:198-209, error_method 'sumw2').
+ * d_weights_out / d_prob_e / d_prob_mu are optional per-event outputs. */
+int pisab_reweight_hist_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                            int32_t nubar, const int32_t *d_nubar, int32_t flav,
+                            const int32_t *d_flav, const double *d_energy, const double *d_coszen,
+                            const double *d_nu_flux, const double *d_weights_in,
+                            const int32_t *d_index, int64_t n, int32_t n_bins, double *d_hist,
+                            double *d_hist_w2, double *d_weights_out, double *d_prob_e,
+                            double *d_prob_mu, void *d_workspace, int64_t workspace_bytes,
+                            void *stream);
+int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                            int32_t nubar, const int32_t *d_nubar, int32_t flav,
+                            const int32_t *d_flav, const float *d_energy, const float *d_coszen,
+                            const float *d_nu_flux, const float *d_weights_in,
+                            const int32_t *d_index, int64_t n, int32_t n_bins, double *d_hist,
+                            double *d_hist_w2, float *d_weights_out, float *d_prob_e,
+                            float *d_prob_mu, void *d_workspace, int64_t workspace_bytes,
+                            void *stream);
+
+/* mod_chi2 (pisa/utils/stats.py:651-695) on device for the scan driver:
+ * sum_b (obs-exp)^2 / (sigma^2 + max(exp,1e-10)); result is one double on the device. */
+int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const double *d_observed,
+                   int32_t n_bins, double *d_out, void *stream);
+
+/* ---- measurement helpers (bench.py) ---------------------------------------------------- */
+/* Dependent-chain-free DFMA microbenchmark: runs `iters` x 8 independent FMAs per thread
+ * on a full grid and returns achieved FP64 FLOP/s (synchronises). Roofline denominator. */
+int pisab_fp64_peak_probe(int32_t iters, double *flops_per_s, double *elapsed_ms);
+/* Kernels launched by this library since load / last reset (bench.py's gpu_launches). */
+int64_t pisab_launch_count(int32_t reset);
+/* Time of the most recent propagation-class kernel measured with CUDA events on its own
+ * stream when profiling is enabled (pisab_set_profiling(1)); ms, or negative if none. */
+int pisab_set_profiling(int32_t on);
+double pisab_last_kernel_ms(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PISA_B200_H */

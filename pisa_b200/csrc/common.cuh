@@ -1,0 +1,70 @@
+// common.cuh -- error handling, launch bookkeeping and device tables shared by the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pisa_b200.h"
+
+namespace pisab {
+
+// ---- host-side error text (thread local) -------------------------------------------------
+void set_error(const char *fmt, ...);
+int cuda_fail(cudaError_t e, const char *what);
+
+#define PISAB_CUDA_CHECK(expr)                                   \
+    do {                                                         \
+        cudaError_t _e = (expr);                                 \
+        if (_e != cudaSuccess) return ::pisab::cuda_fail(_e, #expr); \
+    } while (0)
+
+// ---- launch bookkeeping -----------------------------------------------------------------
+// Every kernel launch goes through note_launch() so bench.py can report `gpu_launches`, and
+// (when profiling is on) through LaunchTimer so the dominant kernel is timed with CUDA
+// events on the stream it was launched on.
+void note_launch(int n = 1);
+struct LaunchTimer {
+    cudaStream_t stream;
+    bool active;
+    explicit LaunchTimer(cudaStream_t s);
+    ~LaunchTimer();
+};
+
+// number of SMs of the current device (cached); 0 on failure
+int sm_count();
+
+// ---- device-side parameter tables (passed by value as kernel arguments) -------------------
+// Hermitian 3x3 in packed form: diagonal (real) + upper triangle (re, im).
+struct Herm3 {
+    double d0, d1, d2;
+    double r01, i01, r02, i02, r12, i12;
+};
+
+// Per-launch constants of the propagation (built on the host from pisab_osc_consts_t).
+// The Hamiltonian of one layer is, for neutrinos,
+//     H = hv * (1/E) + rho * vm + lr          (eV^2/GeV)
+// with hv = 0.5 * U diag(0, dm21, dm31) U^dagger, vm = 0.5*1.52588e-4 * mat_pot,
+// lr = 1e9 * lri_pot.  For antineutrinos the reference uses conj(U), -a*conj(V), -lri
+// (numba_osc_kernels.py:208-217,435-440,650-653), i.e. H_bar = conj(hv/E - rho*vm - lr);
+// since |conj(z)| = |z| and conj(exp(-iXt)) = exp(+i conj(X) t), the probabilities are those
+// of H' = -hv/E + rho*vm + lr propagated with the same code, so only `hv` changes sign.
+struct OscTable {
+    Herm3 hv[2]; // [0] = nu, [1] = nubar (sign flipped)
+    Herm3 vm;
+    Herm3 lr;
+};
+
+struct EarthTable {
+    int n_radii;
+    int idx_first_inner; // first shell with radius < r_detector (layers.py:91)
+    double r_det;        // r_detector
+    double rd2;          // r_detector * r_detector (rounded once, as the reference does)
+    double rj2[PISAB_MAX_RADII];   // radii**2
+    double rho[PISAB_MAX_RADII];   // electron-weighted densities
+    double limit[PISAB_MAX_RADII]; // coszen_limit
+};
+
+int build_osc_table(const pisab_osc_consts_t *c, OscTable *out);
+int build_earth_table(const pisab_earth_t *e, EarthTable *out);
+
+} // namespace pisab

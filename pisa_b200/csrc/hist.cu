@@ -1,0 +1,393 @@
+// hist.cu -- bin indexing, weighted histogram accumulation, lookup, small element-wise ops.
+#include <math.h>
+
+#include "hist_device.cuh"
+
+namespace pisab {
+
+// ---------------------------------------------------------------------------------------------
+// bin index (translation.py:417-455 rule; hist.py:93-113 for irregular dims)
+// ---------------------------------------------------------------------------------------------
+struct BinningTable {
+    int n_dims;
+    int kind[PISAB_MAX_DIMS];
+    int n_bins[PISAB_MAX_DIMS];
+    double lo[PISAB_MAX_DIMS], hi[PISAB_MAX_DIMS], norm[PISAB_MAX_DIMS];
+    const double *edges[PISAB_MAX_DIMS];
+};
+
+template <typename IO>
+struct CoordPtrs {
+    const IO *p[PISAB_MAX_DIMS];
+};
+
+// np.searchsorted(edges, x, side='right') - 1, with x == last edge folded into the last bin
+__device__ __forceinline__ int digitize_right(const double *__restrict__ edges, int n_edges, double v) {
+    if (v != v) return n_edges - 1; // nan sorts last: searchsorted returns n_edges
+    int lo = 0, hi = n_edges;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(edges + mid) <= v) lo = mid + 1;
+        else hi = mid;
+    }
+    int idx = lo - 1;
+    if (v == __ldg(edges + n_edges - 1)) idx -= 1;
+    return idx;
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+hist_index_kernel(const __grid_constant__ BinningTable B, const __grid_constant__ CoordPtrs<IO> C,
+                  int64_t n, int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int flat = 0;
+        bool ok = true;
+#pragma unroll
+        for (int d = 0; d < PISAB_MAX_DIMS; ++d) {
+            if (d >= B.n_dims) break;
+            // arithmetic is double in both storage modes (numba promotes float32 op float64;
+            // fast_histogram converts to double)
+            double x = (double)__ldg(C.p[d] + i);
+            int id;
+            if (B.kind[d] == PISAB_DIM_EDGES) {
+                id = digitize_right(B.edges[d], B.n_bins[d] + 1, x);
+                ok = ok && id >= 0 && id < B.n_bins[d];
+            } else {
+                // Container.translate: np.log on the FTYPE array (container.py:845-850)
+                if (B.kind[d] == PISAB_DIM_LOG) x = sizeof(IO) == 4 ? (double)logf((float)x) : log(x);
+                const bool in = x >= B.lo[d] && x < B.hi[d];
+                // (int)((x - lo) * norm): no FMA contraction
+                id = in ? (int)__dmul_rn(__dsub_rn(x, B.lo[d]), B.norm[d]) : 0;
+                // x < hi whose product rounds up to n: out-of-bounds access in the reference,
+                // folded into the last bin here and in the oracle
+                if (id >= B.n_bins[d]) id = B.n_bins[d] - 1;
+                ok = ok && in;
+            }
+            flat = flat * B.n_bins[d] + id;
+        }
+        out[i] = ok ? flat : -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// accumulation
+// ---------------------------------------------------------------------------------------------
+template <typename IO>
+__global__ void __launch_bounds__(kHistBlock)
+hist_accumulate_kernel(const int32_t *__restrict__ index, const IO *__restrict__ weights, int64_t n,
+                       int n_bins, double *__restrict__ partials) {
+    extern __shared__ double s_hist[];
+    WarpHist wh(s_hist, n_bins);
+    wh.clear();
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t warp_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    // 4 warp-steps per iteration so that 8 loads are in flight per lane
+    int64_t base = warp_first;
+    for (; base + 3 * stride < n; base += 4 * stride) {
+        int b[4];
+        double w[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = base + u * stride + lane;
+            const bool ok = i < n;
+            b[u] = ok ? __ldg(index + i) : -1;
+            w[u] = ok ? (weights ? (double)__ldg(weights + i) : 1.0) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) wh.add(b[u], w[u]);
+    }
+    for (; base < n; base += stride) {
+        const int64_t i = base + lane;
+        const bool ok = i < n;
+        const int b = ok ? __ldg(index + i) : -1;
+        const double w = ok ? (weights ? (double)__ldg(weights + i) : 1.0) : 0.0;
+        wh.add(b, w);
+    }
+    wh.flush(partials + (size_t)blockIdx.x * 2 * n_bins);
+}
+
+// large binnings: global atomics (not run-to-run bit-reproducible; documented in DESIGN.md)
+template <typename IO>
+__global__ void __launch_bounds__(256)
+hist_accumulate_atomic_kernel(const int32_t *__restrict__ index, const IO *__restrict__ weights,
+                              int64_t n, int n_bins, double *__restrict__ hist,
+                              double *__restrict__ hist_w2) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int b = __ldg(index + i);
+        if (b < 0 || b >= n_bins) continue;
+        const double w = weights ? (double)__ldg(weights + i) : 1.0;
+        atomicAdd(hist + b, w);
+        if (hist_w2) atomicAdd(hist_w2 + b, w * w);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+hist_reduce_kernel(const double *__restrict__ partials, int n_blocks, int n_bins,
+                   double *__restrict__ hist, double *__restrict__ hist_w2) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= 2 * n_bins) return;
+    double s = 0.0;
+    for (int k = 0; k < n_blocks; ++k) s += partials[(size_t)k * 2 * n_bins + b];
+    if (b < n_bins) hist[b] = s;
+    else if (hist_w2) hist_w2[b - n_bins] = s;
+}
+
+int hist_grid(int64_t n) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + kHistBlock - 1) / kHistBlock;
+    if (want < 1) want = 1;
+    const int64_t cap = (int64_t)sms * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+int hist_reduce_partials(const double *d_partials, int n_blocks, int n_bins, double *d_hist,
+                         double *d_hist_w2, cudaStream_t s) {
+    hist_reduce_kernel<<<(2 * n_bins + 255) / 256, 256, 0, s>>>(d_partials, n_blocks, n_bins, d_hist, d_hist_w2);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lookup, fill_probs, apply weights, mod_chi2
+// ---------------------------------------------------------------------------------------------
+template <typename IO>
+__global__ void __launch_bounds__(256)
+lookup_kernel(const int32_t *__restrict__ index, const IO *__restrict__ flat_hist, int64_t n,
+              int width, IO *__restrict__ out) {
+    const int64_t total = n * width;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        const int64_t i = k / width;
+        const int w = (int)(k - i * width);
+        const int b = __ldg(index + i);
+        out[k] = b >= 0 ? __ldg(flat_hist + (int64_t)b * width + w) : (IO)0;
+    }
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+fill_probs_kernel(const IO *__restrict__ probability, int offset, int64_t n, IO *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        out[i] = __ldg(probability + i * 9 + offset);
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+apply_osc_weights_kernel(const IO *__restrict__ nu_flux, const IO *__restrict__ prob_e,
+                         const IO *__restrict__ prob_mu, int64_t n, IO *__restrict__ weights) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        // prob3.py:622, evaluated in FTYPE without contraction like numpy
+        const IO a = nu_flux[2 * i] * prob_e[i];
+        const IO b = nu_flux[2 * i + 1] * prob_mu[i];
+        if (sizeof(IO) == 8) weights[i] = (IO)__dmul_rn((double)weights[i], __dadd_rn((double)a, (double)b));
+        else weights[i] = (IO)__fmul_rn((float)weights[i], __fadd_rn((float)a, (float)b));
+    }
+}
+
+// stats.py:651-695 mod_chi2 = sum (N_obs - N_exp)^2 / (sigma^2 + N_exp), N_exp clipped at 1e-10
+__global__ void __launch_bounds__(256)
+mod_chi2_kernel(const double *__restrict__ expected, const double *__restrict__ expected_w2,
+                const double *__restrict__ observed, int n_bins, double *__restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        const double e = fmax(expected[b], 1e-10);
+        const double sig2 = expected_w2 ? expected_w2[b] : 0.0;
+        const double d = observed[b] - e;
+        acc += d * d / (sig2 + e);
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
+static int ew_grid(int64_t n) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + 255) / 256;
+    if (want < 1) want = 1;
+    const int64_t cap = (int64_t)sms * 8;
+    return (int)(want < cap ? want : cap);
+}
+
+template <typename IO>
+static int hist_index_impl(const pisab_binning_t *binning, const IO *const *d_coords, int64_t n,
+                           int32_t *d_index, void *stream) {
+    if (!binning || !d_coords || n < 0 || (n > 0 && !d_index)) { set_error("bad arguments"); return PISAB_ERR_ARG; }
+    if (binning->n_dims < 1 || binning->n_dims > PISAB_MAX_DIMS) { set_error("n_dims outside [1,%d]", PISAB_MAX_DIMS); return PISAB_ERR_ARG; }
+    BinningTable B = {};
+    CoordPtrs<IO> C = {};
+    B.n_dims = binning->n_dims;
+    int64_t total = 1;
+    for (int d = 0; d < B.n_dims; ++d) {
+        B.kind[d] = binning->kind[d];
+        B.n_bins[d] = binning->n_bins[d];
+        if (B.n_bins[d] < 1) { set_error("dimension %d has no bins", d); return PISAB_ERR_ARG; }
+        total *= B.n_bins[d];
+        B.lo[d] = binning->lo[d];
+        B.hi[d] = binning->hi[d];
+        // norm = n / (hi - lo)  (translation.py:419,429-430)
+        B.norm[d] = (double)B.n_bins[d] / (B.hi[d] - B.lo[d]);
+        B.edges[d] = binning->d_edges[d];
+        if (B.kind[d] == PISAB_DIM_EDGES && !B.edges[d]) { set_error("dimension %d: edges missing", d); return PISAB_ERR_ARG; }
+        if (B.kind[d] != PISAB_DIM_EDGES && !(B.hi[d] > B.lo[d])) { set_error("dimension %d: empty range", d); return PISAB_ERR_ARG; }
+        C.p[d] = d_coords[d];
+        if (!C.p[d]) { set_error("dimension %d: null sample", d); return PISAB_ERR_ARG; }
+    }
+    if (total > 2147483647LL) { set_error("too many bins"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    hist_index_kernel<IO><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+template <typename IO>
+static int hist_accumulate_impl(const int32_t *d_index, const IO *d_weights, int64_t n, int32_t n_bins,
+                                double *d_hist, double *d_hist_w2, void *d_workspace,
+                                int64_t workspace_bytes, void *stream) {
+    if (n < 0 || n_bins < 1 || !d_hist || (n > 0 && !d_index)) { set_error("bad arguments"); return PISAB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (n_bins > PISAB_DET_MAX_BINS) {
+        PISAB_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(double) * n_bins, s));
+        if (d_hist_w2) PISAB_CUDA_CHECK(cudaMemsetAsync(d_hist_w2, 0, sizeof(double) * n_bins, s));
+        if (n > 0) {
+            LaunchTimer t(s);
+            hist_accumulate_atomic_kernel<IO><<<ew_grid(n), 256, 0, s>>>(d_index, d_weights, n, n_bins, d_hist, d_hist_w2);
+            note_launch();
+        }
+        PISAB_CUDA_CHECK(cudaGetLastError());
+        return PISAB_OK;
+    }
+    if (!d_workspace || workspace_bytes < pisab_hist_workspace_bytes(n, n_bins)) {
+        set_error("workspace too small: need %lld bytes", (long long)pisab_hist_workspace_bytes(n, n_bins));
+        return PISAB_ERR_WORKSPACE;
+    }
+    const int grid = hist_grid(n);
+    const size_t smem = WarpHist::smem_bytes(kHistBlock, n_bins);
+    if (smem > 48 * 1024)
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(hist_accumulate_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        LaunchTimer t(s);
+        hist_accumulate_kernel<IO><<<grid, kHistBlock, smem, s>>>(d_index, d_weights, n, n_bins, (double *)d_workspace);
+        note_launch();
+    }
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return hist_reduce_partials((const double *)d_workspace, grid, n_bins, d_hist, d_hist_w2, s);
+}
+
+} // namespace pisab
+
+using namespace pisab;
+
+extern "C" {
+
+int64_t pisab_hist_workspace_bytes(int64_t n, int32_t n_bins) {
+    (void)n;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    return (int64_t)sms * 8 * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
+}
+
+int pisab_hist_index_f64(const pisab_binning_t *binning, const double *const *d_coords, int64_t n,
+                         int32_t *d_index, void *stream) {
+    return hist_index_impl<double>(binning, d_coords, n, d_index, stream);
+}
+int pisab_hist_index_f32(const pisab_binning_t *binning, const float *const *d_coords, int64_t n,
+                         int32_t *d_index, void *stream) {
+    return hist_index_impl<float>(binning, d_coords, n, d_index, stream);
+}
+int pisab_hist_accumulate_f64(const int32_t *d_index, const double *d_weights, int64_t n, int32_t n_bins,
+                              double *d_hist, double *d_hist_w2, void *d_workspace,
+                              int64_t workspace_bytes, void *stream) {
+    return hist_accumulate_impl<double>(d_index, d_weights, n, n_bins, d_hist, d_hist_w2, d_workspace,
+                                        workspace_bytes, stream);
+}
+int pisab_hist_accumulate_f32(const int32_t *d_index, const float *d_weights, int64_t n, int32_t n_bins,
+                              double *d_hist, double *d_hist_w2, void *d_workspace,
+                              int64_t workspace_bytes, void *stream) {
+    return hist_accumulate_impl<float>(d_index, d_weights, n, n_bins, d_hist, d_hist_w2, d_workspace,
+                                       workspace_bytes, stream);
+}
+
+#define PISAB_EW_CHECK(cond)                         \
+    if (!(cond)) {                                   \
+        set_error("bad arguments: " #cond);          \
+        return PISAB_ERR_ARG;                        \
+    }
+
+int pisab_lookup_f64(const int32_t *d_index, const double *d_flat_hist, int64_t n, int32_t width,
+                     double *d_out, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && width >= 1 && (n == 0 || (d_index && d_flat_hist && d_out)));
+    if (n == 0) return PISAB_OK;
+    lookup_kernel<double><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+int pisab_lookup_f32(const int32_t *d_index, const float *d_flat_hist, int64_t n, int32_t width,
+                     float *d_out, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && width >= 1 && (n == 0 || (d_index && d_flat_hist && d_out)));
+    if (n == 0) return PISAB_OK;
+    lookup_kernel<float><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_fill_probs_f64(const double *d_probability, int32_t initial_flav, int32_t flav, int64_t n,
+                         double *d_out, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && initial_flav >= 0 && initial_flav < 3 && flav >= 0 && flav < 3 && (n == 0 || (d_probability && d_out)));
+    if (n == 0) return PISAB_OK;
+    fill_probs_kernel<double><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_probability, initial_flav * 3 + flav, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+int pisab_fill_probs_f32(const float *d_probability, int32_t initial_flav, int32_t flav, int64_t n,
+                         float *d_out, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && initial_flav >= 0 && initial_flav < 3 && flav >= 0 && flav < 3 && (n == 0 || (d_probability && d_out)));
+    if (n == 0) return PISAB_OK;
+    fill_probs_kernel<float><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_probability, initial_flav * 3 + flav, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_apply_osc_weights_f64(const double *d_nu_flux, const double *d_prob_e, const double *d_prob_mu,
+                                int64_t n, double *d_weights, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && (n == 0 || (d_nu_flux && d_prob_e && d_prob_mu && d_weights)));
+    if (n == 0) return PISAB_OK;
+    apply_osc_weights_kernel<double><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_nu_flux, d_prob_e, d_prob_mu, n, d_weights);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+int pisab_apply_osc_weights_f32(const float *d_nu_flux, const float *d_prob_e, const float *d_prob_mu,
+                                int64_t n, float *d_weights, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && (n == 0 || (d_nu_flux && d_prob_e && d_prob_mu && d_weights)));
+    if (n == 0) return PISAB_OK;
+    apply_osc_weights_kernel<float><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_nu_flux, d_prob_e, d_prob_mu, n, d_weights);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const double *d_observed,
+                   int32_t n_bins, double *d_out, void *stream) {
+    PISAB_EW_CHECK(n_bins >= 1 && d_expected && d_observed && d_out);
+    mod_chi2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_expected, d_expected_w2, d_observed, n_bins, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,111 @@
+// layers.cu -- Layers.calcLayers / extCalcLayers (layers.py:38-169) as a stand-alone kernel.
+// Parity / API path: the propagation kernels evaluate the same geometry in registers and never
+// materialise these [n, max_layers] arrays.
+#include "prob3_device.cuh"
+
+namespace pisab {
+
+template <typename IO>
+__global__ void __launch_bounds__(128)
+layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO *__restrict__ coszen,
+              int64_t n, IO *__restrict__ densities, IO *__restrict__ distances,
+              int32_t *__restrict__ n_layers) {
+    __shared__ EarthTable E;
+    {
+        const int *src = reinterpret_cast<const int *>(&earth);
+        int *dst = reinterpret_cast<int *>(&E);
+        for (int i = threadIdx.x; i < (int)(sizeof(EarthTable) / 4); i += blockDim.x) dst[i] = src[i];
+        __syncthreads();
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const IO czs = __ldg(coszen + i);
+        const double cz = (double)czs;
+        IO *den = densities + i * max_layers;
+        IO *dis = distances + i * max_layers;
+        const int idx = E.idx_first_inner;
+        const double base = __dmul_rn(-E.r_det, cz);
+        int count = 0, slot = 0;
+        if (!(cz < E.limit[idx])) {
+            // layers.py:94-103 (`coszen**2.` is float64 in both FTYPE modes)
+            const double cz2 = __dmul_rn(cz, cz);
+            double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0]));
+            for (int j = 0; j < idx; ++j) {
+                const double l_next = (j + 1 < idx) ? __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1])) : 0.0;
+                const double seg = __dsub_rn(l_cur, l_next);
+                l_cur = l_next;
+                den[slot] = seg > 0.0 ? (IO)E.rho[j] : (IO)0;
+                dis[slot] = (IO)seg;
+                count += seg > 0.0;
+                ++slot;
+            }
+            for (; slot < E.n_radii && slot < max_layers; ++slot) { den[slot] = (IO)0; dis[slot] = (IO)0; }
+        } else {
+            // layers.py:105-159; `coszen**2` (int exponent) stays in FTYPE under numba's typing
+            const double cz2 = sizeof(IO) == 4 ? (double)__fmul_rn((float)czs, (float)czs) : __dmul_rn(cz, cz);
+            int K = idx; // number of crossed shells
+            while (K < E.n_radii && E.limit[K] > cz) ++K;
+            // inbound: shells 0 .. K-1
+            double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0]));
+            for (int j = 0; j < K; ++j) {
+                double seg;
+                if (j + 1 < K) {
+                    const double l_next = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1]));
+                    seg = __dsub_rn(l_cur, l_next);
+                    l_cur = l_next;
+                } else {
+                    const double s_j = __dsub_rn(base, shell_root(E.rd2, cz2, E.rj2[j]));
+                    seg = __dsub_rn(l_cur, s_j);
+                }
+                den[slot] = seg > 0.0 ? (IO)E.rho[j] : (IO)0;
+                dis[slot] = (IO)seg;
+                count += seg > 0.0;
+                ++slot;
+            }
+            // outbound: shells K-2 .. 1, segments s_{j+1} - s_j (s_idx-1 := 0)
+            for (int j = K - 2; j >= 1; --j) {
+                const double s_hi = __dsub_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1]));
+                const double s_lo = j >= idx ? __dsub_rn(base, shell_root(E.rd2, cz2, E.rj2[j])) : 0.0;
+                const double seg = __dsub_rn(s_hi, s_lo);
+                den[slot] = seg > 0.0 ? (IO)E.rho[j] : (IO)0;
+                dis[slot] = (IO)seg;
+                count += seg > 0.0;
+                ++slot;
+            }
+        }
+        for (; slot < max_layers; ++slot) { den[slot] = (IO)0; dis[slot] = (IO)0; }
+        if (n_layers) n_layers[i] = count;
+    }
+}
+
+template <typename IO>
+static int layers_impl(const pisab_earth_t *earth, const IO *d_coszen, int64_t n, IO *d_densities,
+                       IO *d_distances, int32_t *d_n_layers, void *stream) {
+    if (n < 0 || (n > 0 && (!d_coszen || !d_densities || !d_distances))) { set_error("bad arguments"); return PISAB_ERR_ARG; }
+    EarthTable et;
+    int rc = build_earth_table(earth, &et);
+    if (rc) return rc;
+    if (earth->max_layers < 2 * earth->n_radii - 2) { set_error("max_layers too small"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + 127) / 128;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    layers_kernel<IO><<<grid, 128, 0, (cudaStream_t)stream>>>(et, earth->max_layers, d_coszen, n, d_densities,
+                                                             d_distances, d_n_layers);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+} // namespace pisab
+
+extern "C" {
+int pisab_layers_calc_f64(const pisab_earth_t *earth, const double *d_coszen, int64_t n,
+                          double *d_densities, double *d_distances, int32_t *d_n_layers, void *stream) {
+    return pisab::layers_impl<double>(earth, d_coszen, n, d_densities, d_distances, d_n_layers, stream);
+}
+int pisab_layers_calc_f32(const pisab_earth_t *earth, const float *d_coszen, int64_t n, float *d_densities,
+                          float *d_distances, int32_t *d_n_layers, void *stream) {
+    return pisab::layers_impl<float>(earth, d_coszen, n, d_densities, d_distances, d_n_layers, stream);
+}
+}

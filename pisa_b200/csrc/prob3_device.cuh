@@ -1,0 +1,303 @@
+// prob3_device.cuh -- per-event three-flavour propagation through constant-density layers.
+//
+// What the reference computes (numba_osc_kernels.py:121-345,348-531,687-872): for every layer
+// with distance > 0 the transition matrix T = exp(-i H t) (H the 3x3 Hermitian Hamiltonian in
+// matter, t = 2 * 2.534 * distance), obtained from the eigenvalues of H (closed-form roots of
+// the characteristic cubic, get_dms :687-831) and Lagrange's / Sylvester's formula
+// (get_product :834-872, get_transition_matrix_massbasis :481-531); the ordered product of the
+// layer matrices, rotated to the flavour basis, gives P(i->j) = |A_ji|^2.
+//
+// B200 formulation (same mathematics, far fewer FP64 operations, no local-memory arrays):
+//   * work in the FLAVOUR basis throughout: H = hv/E + rho*vm + lr with per-launch constants,
+//     so the two mass-basis rotations per layer (:466-467) and the final rotation (:327-328)
+//     disappear;
+//   * eigenvalues: the reference's own cubic coefficients c2, c1, c0 and its cancellation-safe
+//     discriminant (:716-782), atan2 + ONE sincos (cos(theta +- 2pi/3) by rotation);
+//   * exp(-iHt) = a0*1 + a1*H + a2*H^2 (Cayley-Hamilton form of the same Lagrange sum): the
+//     27 complex divisions and the 3x3x3 product tensor collapse into one reciprocal, H^2
+//     (Hermitian: 9 reals) and three complex coefficients; a global phase is dropped;
+//   * Earth symmetry: shell j is crossed on the way in and on the way out with the same
+//     (rho, length); T_j is built once and applied to both sides of the running product
+//     (what the reference's 1e-5 layer cache achieves with a 17 KiB local array, :224-249);
+//   * when only prob_e / prob_mu of one final flavour are needed (fill_probs), a row vector
+//     and two column vectors are propagated instead of 3x3 matrices.
+#pragma once
+#include "common.cuh"
+
+namespace pisab {
+
+struct Cplx {
+    double re, im;
+};
+
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) {
+    return Cplx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ Cplx cfma(Cplx a, Cplx b, Cplx c) { // a*b + c
+    Cplx r;
+    r.re = fma(a.re, b.re, fma(-a.im, b.im, c.re));
+    r.im = fma(a.re, b.im, fma(a.im, b.re, c.im));
+    return r;
+}
+
+typedef Cplx Mat3[3][3];
+
+// H = hv * inv_e + lr   (per event), then + rho * vm per layer
+__device__ __forceinline__ Herm3 herm_axpy(double a, const Herm3 &x, const Herm3 &y) {
+    Herm3 r;
+    r.d0 = fma(a, x.d0, y.d0);
+    r.d1 = fma(a, x.d1, y.d1);
+    r.d2 = fma(a, x.d2, y.d2);
+    r.r01 = fma(a, x.r01, y.r01);
+    r.i01 = fma(a, x.i01, y.i01);
+    r.r02 = fma(a, x.r02, y.r02);
+    r.i02 = fma(a, x.i02, y.i02);
+    r.r12 = fma(a, x.r12, y.r12);
+    r.i12 = fma(a, x.i12, y.i12);
+    return r;
+}
+
+// T = exp(-i h t) up to a global phase.  `h` in eV^2/GeV, t = 2 * 2.534 * distance[km].
+__device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3 T) {
+    // ---- characteristic polynomial x^3 + c2 x^2 + c1 x + c0 (numba_osc_kernels.py:716-752)
+    const double n01 = fma(h.r01, h.r01, h.i01 * h.i01);
+    const double n02 = fma(h.r02, h.r02, h.i02 * h.i02);
+    const double n12 = fma(h.r12, h.r12, h.i12 * h.i12);
+    const double ur = fma(h.r01, h.r12, -h.i01 * h.i12); // h01*h12
+    const double ui = fma(h.r01, h.i12, h.i01 * h.r12);
+    const double rpa = fma(ur, h.r02, ui * h.i02);       // Re(h01 h12 h20)
+    const double c2 = -(h.d0 + h.d1 + h.d2);
+    const double c1 = fma(h.d0, h.d1 + h.d2, h.d1 * h.d2) - n01 - n12 - n02;
+    const double c0 = fma(h.d0, n12, fma(h.d1, n02, h.d2 * n01)) - 2.0 * rpa - h.d0 * h.d1 * h.d2;
+
+    // ---- roots (:766-814): p, q and the cancellation-safe p^3 - q^2
+    double p = fma(c2, c2, -3.0 * c1);
+    p = fmax(p, 0.0);
+    const double q = fma(4.5 * c1, c2, fma(-13.5, c0, -c2 * c2 * c2));
+    double disc = 27.0 * fma(0.25 * c1 * c1, p - c1, c0 * fma(6.75, c0, q));
+    disc = fmax(disc, 0.0);
+    const double theta = atan2(sqrt(disc), q) * (1.0 / 3.0);
+    const double b = (2.0 / 3.0) * sqrt(p);
+    const double base = c2 * (-1.0 / 3.0);
+    double st, ct;
+    sincos(theta, &st, &ct); // theta in [0, pi/3]
+    const double kh = 0.5, ks = 0.86602540378443864676; // cos, sin of pi/3
+    // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
+    const double l0 = fma(b, -kh * ct - ks * st, base);
+    const double l1 = fma(b, -kh * ct + ks * st, base);
+    const double l2 = fma(b, ct, base);
+
+    // ---- Lagrange weights with the global phase exp(-i l2 t) dropped
+    const double g01 = l0 - l1, g02 = l0 - l2, g12 = l1 - l2;
+    const double inv_g = 1.0 / (g01 * g02 * g12);
+    const double id0 = g12 * inv_g;  // 1/((l0-l1)(l0-l2))
+    const double id1 = -g02 * inv_g; // 1/((l1-l0)(l1-l2))
+    const double id2 = g01 * inv_g;  // 1/((l2-l0)(l2-l1))
+    double s0, k0, s1, k1;
+    sincos(-g02 * t, &s0, &k0); // exp(-i (l0-l2) t)
+    sincos(-g12 * t, &s1, &k1); // exp(-i (l1-l2) t)
+    const Cplx w0{k0 * id0, s0 * id0};
+    const Cplx w1{k1 * id1, s1 * id1};
+    const double w2 = id2;
+    // exp(-iHt) = a0 + a1 H + a2 H^2
+    const double m12 = l1 + l2, m02 = l0 + l2, m01 = l0 + l1;
+    const double p12 = l1 * l2, p02 = l0 * l2, p01 = l0 * l1;
+    const Cplx a2{w0.re + w1.re + w2, w0.im + w1.im};
+    const Cplx a1{-fma(w0.re, m12, fma(w1.re, m02, w2 * m01)), -fma(w0.im, m12, w1.im * m02)};
+    const Cplx a0{fma(w0.re, p12, fma(w1.re, p02, w2 * p01)), fma(w0.im, p12, w1.im * p02)};
+
+    // ---- H^2 (Hermitian)
+    const double q0 = fma(h.d0, h.d0, n01 + n02);
+    const double q1 = fma(h.d1, h.d1, n01 + n12);
+    const double q2 = fma(h.d2, h.d2, n02 + n12);
+    const double t01 = h.d0 + h.d1, t02 = h.d0 + h.d2, t12 = h.d1 + h.d2;
+    const double s01r = fma(h.r01, t01, fma(h.r02, h.r12, h.i02 * h.i12));
+    const double s01i = fma(h.i01, t01, fma(h.i02, h.r12, -h.r02 * h.i12));
+    const double s02r = fma(h.r02, t02, ur);
+    const double s02i = fma(h.i02, t02, ui);
+    const double s12r = fma(h.r12, t12, fma(h.r01, h.r02, h.i01 * h.i02));
+    const double s12i = fma(h.i12, t12, fma(h.r01, h.i02, -h.i01 * h.r02));
+
+    // ---- assemble T
+    T[0][0] = Cplx{fma(a2.re, q0, fma(a1.re, h.d0, a0.re)), fma(a2.im, q0, fma(a1.im, h.d0, a0.im))};
+    T[1][1] = Cplx{fma(a2.re, q1, fma(a1.re, h.d1, a0.re)), fma(a2.im, q1, fma(a1.im, h.d1, a0.im))};
+    T[2][2] = Cplx{fma(a2.re, q2, fma(a1.re, h.d2, a0.re)), fma(a2.im, q2, fma(a1.im, h.d2, a0.im))};
+#define PISAB_OFFDIAG(I, J, RE, IM, SR, SI)                                   \
+    {                                                                         \
+        const double xr = fma(a2.re, SR, a1.re * RE), xi = fma(a2.im, SR, a1.im * RE); \
+        const double yr = fma(a2.re, SI, a1.re * IM), yi = fma(a2.im, SI, a1.im * IM); \
+        T[I][J] = Cplx{xr - yi, xi + yr};                                     \
+        T[J][I] = Cplx{xr + yi, xi - yr};                                     \
+    }
+    PISAB_OFFDIAG(0, 1, h.r01, h.i01, s01r, s01i)
+    PISAB_OFFDIAG(0, 2, h.r02, h.i02, s02r, s02i)
+    PISAB_OFFDIAG(1, 2, h.r12, h.i12, s12r, s12i)
+#undef PISAB_OFFDIAG
+}
+
+// ---- small dense helpers on NR x 3 / 3 x NC blocks ----------------------------------------
+// L (NR x 3) <- L . T
+template <int NR>
+__device__ __forceinline__ void left_times(Cplx (*L)[3], const Mat3 T) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+        Cplx o[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            Cplx acc = cmul(L[r][0], T[0][c]);
+            acc = cfma(L[r][1], T[1][c], acc);
+            acc = cfma(L[r][2], T[2][c], acc);
+            o[c] = acc;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) L[r][c] = o[c];
+    }
+}
+// R (3 x NC, stored as R[c][k] = column c, component k) <- T . R
+template <int NC>
+__device__ __forceinline__ void times_right(const Mat3 T, Cplx (*R)[3]) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        Cplx o[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            Cplx acc = cmul(T[k][0], R[c][0]);
+            acc = cfma(T[k][1], R[c][1], acc);
+            acc = cfma(T[k][2], R[c][2], acc);
+            o[k] = acc;
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) R[c][k] = o[k];
+    }
+}
+
+// ---- Earth geometry (layers.py:38-169) with the reference's operation order ----------------
+// sqrt argument r_det^2*cz^2 - r_det^2 + r_j^2, evaluated without FMA contraction so that the
+// distances are bit-identical to numpy's.
+__device__ __forceinline__ double shell_root(double rd2, double cz2, double rj2) {
+    return __dsqrt_rn(__dadd_rn(__dsub_rn(__dmul_rn(rd2, cz2), rd2), rj2));
+}
+
+// Propagation state: L is NR x 3 (rows of the product on the detector side), R holds NC
+// columns of the product on the production side.
+//   MODE_FULL: NR = 3, NC = 3  -> probability[3][3]
+//   MODE_ROW : NR = 1, NC = 2  -> prob_e, prob_mu of final flavour `flav`
+template <int NR, int NC>
+struct Propagator {
+    Cplx L[NR][3];
+    Cplx R[NC][3];
+
+    __device__ __forceinline__ void init_right(const Mat3 T) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) R[c][k] = T[k][c];
+    }
+    __device__ __forceinline__ void init_left(const Mat3 T, int flav) {
+        if (NR == 3) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) L[r][c] = T[r][c];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Cplx v = T[0][c];
+                if (flav == 1) v = T[1][c];
+                if (flav == 2) v = T[2][c];
+                L[0][c] = v;
+            }
+        }
+    }
+    // amplitude A[r][c] = sum_k L[r][k] R[c][k]; returns |A|^2
+    __device__ __forceinline__ double prob(int r, int c) const {
+        Cplx acc = cmul(L[r][0], R[c][0]);
+        acc = cfma(L[r][1], R[c][1], acc);
+        acc = cfma(L[r][2], R[c][2], acc);
+        return fma(acc.re, acc.re, acc.im * acc.im);
+    }
+};
+
+// Per-event propagation through the Earth.  h0 = hv/E + lr (per event), vm scales with rho.
+// Returns false for a direction the reference cannot process either (never for idx == 2).
+//   out_full != nullptr (NR=NC=3): out_full[i*3+j] = P(i -> j)
+//   NR=1: pe = P(e -> flav), pmu = P(mu -> flav)
+template <int NR, int NC>
+__device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm,
+                                                const EarthTable &E, double cz, int flav,
+                                                Propagator<NR, NC> &P) {
+    const double T_SCALE = 2.0 * 2.534; // (1/2)(1/hbar c) in GeV/(eV^2 km), :524, times 2 (M = 2E lambda)
+    const double cz2 = __dmul_rn(cz, cz);
+    const double base = __dmul_rn(-E.r_det, cz);
+    const int idx = E.idx_first_inner;
+    Mat3 T;
+
+    // shells outside the detector (j < idx): always crossed once, far side
+    double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0]));
+    if (!(cz < E.limit[idx])) {
+        // ---- no tangent (layers.py:94-103): segments l_j - l_{j+1}, last one l_{idx-1} - 0.
+        // Segments of length <= 0 are skipped like in the reference (:233,285).
+        bool have_r = false, have_l = false;
+        for (int j = 0; j < idx; ++j) {
+            const double l_next = (j + 1 < idx) ? __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1])) : 0.0;
+            const double seg = __dsub_rn(l_cur, l_next);
+            l_cur = l_next;
+            if (seg > 0.0) {
+                transition_matrix(herm_axpy(E.rho[j], vm, h0), T_SCALE * seg, T);
+                if (j + 1 == idx) { P.init_left(T, flav); have_l = true; }
+                else if (!have_r) { P.init_right(T); have_r = true; }
+                else times_right<NC>(T, P.R);
+            }
+        }
+        if (!have_r || !have_l) {
+            Mat3 I = {{{1, 0}, {0, 0}, {0, 0}}, {{0, 0}, {1, 0}, {0, 0}}, {{0, 0}, {0, 0}, {1, 0}}};
+            if (!have_r) P.init_right(I);
+            if (!have_l) P.init_left(I, flav);
+        }
+        return;
+    }
+
+    // ---- two-root branch (layers.py:105-159), idx == 2 (checked on the host)
+    // far side, production -> detector: shells 0 and 1 once each
+    {
+        const double l1 = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[1]));
+        transition_matrix(herm_axpy(E.rho[0], vm, h0), T_SCALE * __dsub_rn(l_cur, l1), T);
+        P.init_right(T);
+        l_cur = l1;
+    }
+    const double sq2 = shell_root(E.rd2, cz2, E.rj2[2]);
+    {
+        const double l2 = __dadd_rn(base, sq2);
+        const Herm3 h = herm_axpy(E.rho[1], vm, h0);
+        transition_matrix(h, T_SCALE * __dsub_rn(l_cur, l2), T);
+        times_right<NC>(T, P.R);
+        // near side: detector shell again, length s_2 - 0 (small root of shell 2)
+        transition_matrix(h, T_SCALE * __dsub_rn(base, sq2), T);
+        P.init_left(T, flav);
+        l_cur = l2;
+    }
+    // inner shells j = 2 .. K-1; shell j is the innermost one iff shell j+1 is not crossed
+    double sq_cur = sq2;
+    for (int j = 2; j < E.n_radii; ++j) {
+        const bool innermost = !(j + 1 < E.n_radii && E.limit[j + 1] > cz);
+        const Herm3 h = herm_axpy(E.rho[j], vm, h0);
+        if (innermost) {
+            // l_j - s_j (:128-133): chord through the innermost shell
+            const double s_j = __dsub_rn(base, sq_cur);
+            transition_matrix(h, T_SCALE * __dsub_rn(l_cur, s_j), T);
+            times_right<NC>(T, P.R);
+            break;
+        }
+        const double sq_next = shell_root(E.rd2, cz2, E.rj2[j + 1]);
+        const double l_next = __dadd_rn(base, sq_next);
+        // inbound segment l_j - l_{j+1}; the outbound twin s_{j+1} - s_j differs by rounding only
+        // and hits the reference's layer cache (:236-249), i.e. reuses this matrix
+        transition_matrix(h, T_SCALE * __dsub_rn(l_cur, l_next), T);
+        times_right<NC>(T, P.R);
+        left_times<NR>(P.L, T);
+        l_cur = l_next;
+        sq_cur = sq_next;
+    }
+}
+
+} // namespace pisab

@@ -1,0 +1,295 @@
+"""Device operators of the hot path: thin, typed wrappers over the C ABI (include/pisa_b200.h).
+
+All array arguments are CUDA ``torch`` tensors (torch is used for device memory and streams
+only); parameter structs are host objects.  Every call enqueues on torch's current stream.
+There is no CPU path: a non-CUDA tensor raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Binning, Earth, OscConsts  # noqa: F401  (re-exported)
+
+_FLOATS = (torch.float64, torch.float32)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, name, dtype=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return None
+        raise ValueError("%s is required" % name)
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise TypeError("%s must be a CUDA torch tensor (pisa_b200 has no CPU path)" % name)
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError("%s must have dtype %s, got %s" % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise ValueError("%s must be contiguous" % name)
+    return t
+
+
+def _ptr(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _species(val, n, name):
+    """(+1|-1 or flavour) given as python int (aux scalar of a container) or int32 tensor [n]."""
+    if isinstance(val, torch.Tensor):
+        _chk(val, name, torch.int32)
+        if val.numel() != n:
+            raise ValueError("%s must have one entry per event" % name)
+        return 0, val
+    return int(val), None
+
+
+def device_info():
+    sms, maj, mnr = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(_lib.load().pisab_device_info(ctypes.byref(sms), ctypes.byref(maj), ctypes.byref(mnr)))
+    return dict(sm_count=sms.value, cc=(maj.value, mnr.value))
+
+
+# ----------------------------------------------------------------------------- layers -----
+
+def layers_calc(earth, coszen):
+    """``Layers.calcLayers`` (layers.py:339-363): returns (n_layers[int32], densities, distances),
+    the latter two shaped [N, earth.max_layers]."""
+    _chk(coszen, "coszen")
+    if coszen.dtype not in _FLOATS:
+        raise TypeError("coszen must be float32/float64")
+    n = coszen.numel()
+    den = torch.empty((n, earth.max_layers), dtype=coszen.dtype, device=coszen.device)
+    dis = torch.empty_like(den)
+    nl = torch.empty(n, dtype=torch.int32, device=coszen.device)
+    f = _lib.fn("pisab_layers_calc", coszen.dtype)
+    _lib.check(f(ctypes.byref(earth), _ptr(coszen), n, _ptr(den), _ptr(dis), _ptr(nl), _stream()))
+    return nl, den, dis
+
+
+# ------------------------------------------------------------------------ propagation -----
+
+def propagate_layers(consts, nubar, energy, densities, distances, out=None):
+    """``propagate_array`` (numba_osc_hostfuncs.py:60-70) with explicit layer arrays.
+    Returns probability[N,3,3] with out[i,j] = P(nu_i -> nu_j)."""
+    _chk(energy, "energy")
+    dt = energy.dtype
+    n = energy.numel()
+    _chk(densities, "densities", dt)
+    _chk(distances, "distances", dt)
+    if densities.shape != distances.shape or densities.shape[0] != n:
+        raise ValueError("densities/distances must be [N, n_layers]")
+    nl = densities.shape[1]
+    nb, d_nb = _species(nubar, n, "nubar")
+    if out is None:
+        out = torch.empty((n, 3, 3), dtype=dt, device=energy.device)
+    _chk(out, "out", dt)
+    f = _lib.fn("pisab_prob3_propagate_layers", dt)
+    _lib.check(f(ctypes.byref(consts), nb, _ptr(d_nb), _ptr(energy), _ptr(densities), _ptr(distances), n, nl,
+                 _ptr(out), _stream()))
+    return out
+
+
+def propagate_earth(consts, earth, nubar, energy, coszen, flav=None, probability=None, prob_e=None,
+                    prob_mu=None, want_probability=True):
+    """Layers evaluated in-kernel from ``coszen`` (prob3.py:406-409 + :581-605 fused).
+
+    Returns (probability | None, prob_e | None, prob_mu | None).  ``flav`` (0/1/2, python int or
+    int32 tensor) selects the final flavour for prob_e / prob_mu (fill_probs)."""
+    _chk(energy, "energy")
+    dt = energy.dtype
+    _chk(coszen, "coszen", dt)
+    n = energy.numel()
+    if coszen.numel() != n:
+        raise ValueError("energy and coszen must have the same length")
+    nb, d_nb = _species(nubar, n, "nubar")
+    if want_probability and probability is None:
+        probability = torch.empty((n, 3, 3), dtype=dt, device=energy.device)
+    fl, d_fl = 0, None
+    if flav is not None:
+        fl, d_fl = _species(flav, n, "flav")
+        if prob_e is None:
+            prob_e = torch.empty(n, dtype=dt, device=energy.device)
+        if prob_mu is None:
+            prob_mu = torch.empty(n, dtype=dt, device=energy.device)
+    for t, nm in ((probability, "probability"), (prob_e, "prob_e"), (prob_mu, "prob_mu")):
+        _chk(t, nm, dt, allow_none=True)
+    f = _lib.fn("pisab_prob3_propagate_earth", dt)
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), nb, _ptr(d_nb), fl, _ptr(d_fl), _ptr(energy),
+                 _ptr(coszen), n, _ptr(probability), _ptr(prob_e), _ptr(prob_mu), _stream()))
+    return probability, prob_e, prob_mu
+
+
+def fill_probs(probability, initial_flav, flav, out=None):
+    """``fill_probs`` (numba_osc_hostfuncs.py:206-221)."""
+    _chk(probability, "probability")
+    n = probability.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=probability.dtype, device=probability.device)
+    _chk(out, "out", probability.dtype)
+    f = _lib.fn("pisab_fill_probs", probability.dtype)
+    _lib.check(f(_ptr(probability), int(initial_flav), int(flav), n, _ptr(out), _stream()))
+    return out
+
+
+def apply_osc_weights(nu_flux, prob_e, prob_mu, weights):
+    """In place ``weights *= nu_flux[:,0]*prob_e + nu_flux[:,1]*prob_mu`` (prob3.py:621-622)."""
+    _chk(weights, "weights")
+    dt = weights.dtype
+    n = weights.numel()
+    _chk(nu_flux, "nu_flux", dt)
+    _chk(prob_e, "prob_e", dt)
+    _chk(prob_mu, "prob_mu", dt)
+    if nu_flux.shape != (n, 2):
+        raise ValueError("nu_flux must be [N, 2]")
+    f = _lib.fn("pisab_apply_osc_weights", dt)
+    _lib.check(f(_ptr(nu_flux), _ptr(prob_e), _ptr(prob_mu), n, _ptr(weights), _stream()))
+    return weights
+
+
+# -------------------------------------------------------------------------- histogram -----
+
+def make_binning(dims, device):
+    """dims: list of dicts {kind: 'lin'|'log'|'edges', n_bins, lo, hi, edges}.  For 'log', lo/hi
+    are the RAW domain; log() is taken here exactly like hist.py:118-120 (np.log(domain)).
+    Returns (Binning struct, keep-alive list of edge tensors)."""
+    if not 1 <= len(dims) <= _lib.MAX_DIMS:
+        raise ValueError("1..%d dimensions supported" % _lib.MAX_DIMS)
+    b = Binning()
+    b.n_dims = len(dims)
+    keep = []
+    for i, d in enumerate(dims):
+        kind = d["kind"]
+        b.n_bins[i] = int(d["n_bins"])
+        if kind == "edges":
+            edges = torch.as_tensor(np.asarray(d["edges"], dtype=np.float64), device=device)
+            if edges.numel() != b.n_bins[i] + 1:
+                raise ValueError("edges must have n_bins + 1 entries")
+            keep.append(edges)
+            b.kind[i] = _lib.DIM_EDGES
+            b.d_edges[i] = edges.data_ptr()
+            b.lo[i], b.hi[i] = float(edges[0]), float(edges[-1])
+        elif kind == "log":
+            lo, hi = np.log(np.asarray([d["lo"], d["hi"]], dtype=np.float64))
+            b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LOG, float(lo), float(hi)
+        elif kind == "lin":
+            b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LIN, float(d["lo"]), float(d["hi"])
+        else:
+            raise ValueError("unknown dimension kind %r" % kind)
+    return b, keep
+
+
+def hist_index(binning, coords, out=None):
+    """Flat row-major bin index per event (int32, -1 outside); translation.py:417-455 rule."""
+    dt = coords[0].dtype
+    n = coords[0].numel()
+    if len(coords) != binning.n_dims:
+        raise ValueError("one sample array per binning dimension")
+    for c in coords:
+        _chk(c, "coords", dt)
+        if c.numel() != n:
+            raise ValueError("sample arrays must have equal length")
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=coords[0].device)
+    _chk(out, "out", torch.int32)
+    ptrs = (ctypes.c_void_p * len(coords))(*[c.data_ptr() for c in coords])
+    f = _lib.fn("pisab_hist_index", dt)
+    _lib.check(f(ctypes.byref(binning), ptrs, n, _ptr(out), _stream()))
+    return out
+
+
+_workspaces = {}
+
+
+def _workspace(device, n, n_bins):
+    need = int(_lib.load().pisab_hist_workspace_bytes(n, n_bins))
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def hist_accumulate(index, weights, n_bins, want_w2=True):
+    """(hist, hist_w2) as float64 tensors; ``weights`` may be None (counts, hist.py:179-185)."""
+    _chk(index, "index", torch.int32)
+    n = index.numel()
+    dt = torch.float64 if weights is None else weights.dtype
+    if weights is not None:
+        _chk(weights, "weights")
+        if weights.numel() != n:
+            raise ValueError("weights and index must have the same length")
+    hist = torch.empty(n_bins, dtype=torch.float64, device=index.device)
+    w2 = torch.empty(n_bins, dtype=torch.float64, device=index.device) if want_w2 else None
+    ws = _workspace(index.device, n, n_bins)
+    f = _lib.fn("pisab_hist_accumulate", dt)
+    _lib.check(f(_ptr(index), _ptr(weights), n, int(n_bins), _ptr(hist), _ptr(w2), _ptr(ws), ws.numel(), _stream()))
+    return hist, w2
+
+
+def lookup(index, flat_hist, out=None):
+    """``lookup`` on a regularised binning (translation.py:417-501): out = flat_hist[index], 0 outside."""
+    _chk(index, "index", torch.int32)
+    _chk(flat_hist, "flat_hist")
+    n = index.numel()
+    width = 1 if flat_hist.dim() == 1 else flat_hist.shape[1]
+    shape = (n,) if flat_hist.dim() == 1 else (n, width)
+    if out is None:
+        out = torch.empty(shape, dtype=flat_hist.dtype, device=index.device)
+    _chk(out, "out", flat_hist.dtype)
+    f = _lib.fn("pisab_lookup", flat_hist.dtype)
+    _lib.check(f(_ptr(index), _ptr(flat_hist), n, int(width), _ptr(out), _stream()))
+    return out
+
+
+def reweight_hist(consts, earth, nubar, flav, energy, coszen, nu_flux, weights_in, index, n_bins,
+                  weights_out=None, prob_e=None, prob_mu=None, hist=None, hist_w2=None):
+    """Fused template evaluation: prob3 + ``weights *= flux.prob`` + weighted histogram (w, w^2)."""
+    _chk(energy, "energy")
+    dt = energy.dtype
+    n = energy.numel()
+    for t, nm in ((coszen, "coszen"), (nu_flux, "nu_flux"), (weights_in, "weights_in")):
+        _chk(t, nm, dt)
+    _chk(index, "index", torch.int32)
+    if nu_flux.shape != (n, 2) or coszen.numel() != n or weights_in.numel() != n or index.numel() != n:
+        raise ValueError("inconsistent event array shapes")
+    for t, nm in ((weights_out, "weights_out"), (prob_e, "prob_e"), (prob_mu, "prob_mu")):
+        _chk(t, nm, dt, allow_none=True)
+    nb, d_nb = _species(nubar, n, "nubar")
+    fl, d_fl = _species(flav, n, "flav")
+    if hist is None:
+        hist = torch.empty(n_bins, dtype=torch.float64, device=energy.device)
+    if hist_w2 is None:
+        hist_w2 = torch.empty(n_bins, dtype=torch.float64, device=energy.device)
+    ws = _workspace(energy.device, n, n_bins)
+    f = _lib.fn("pisab_reweight_hist", dt)
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), nb, _ptr(d_nb), fl, _ptr(d_fl), _ptr(energy),
+                 _ptr(coszen), _ptr(nu_flux), _ptr(weights_in), _ptr(index), n, int(n_bins), _ptr(hist),
+                 _ptr(hist_w2), _ptr(weights_out), _ptr(prob_e), _ptr(prob_mu), _ptr(ws), ws.numel(), _stream()))
+    return hist, hist_w2
+
+
+def mod_chi2(expected, expected_w2, observed):
+    """``mod_chi2`` (pisa/utils/stats.py:651-695) on device; returns a 1-element float64 tensor."""
+    _chk(expected, "expected", torch.float64)
+    _chk(observed, "observed", torch.float64)
+    _chk(expected_w2, "expected_w2", torch.float64, allow_none=True)
+    out = torch.empty(1, dtype=torch.float64, device=expected.device)
+    _lib.check(_lib.load().pisab_mod_chi2(_ptr(expected), _ptr(expected_w2), _ptr(observed), expected.numel(),
+                                          _ptr(out), _stream()))
+    return out
+
+
+def fp64_peak_probe(iters=20000):
+    """Measured DFMA throughput of the device (FLOP/s): the FP64 roofline denominator."""
+    flops, ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.load().pisab_fp64_peak_probe(int(iters), ctypes.byref(flops), ctypes.byref(ms)))
+    return flops.value, ms.value
+
+
+def launch_count(reset=False):
+    return int(_lib.load().pisab_launch_count(1 if reset else 0))

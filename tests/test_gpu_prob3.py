@@ -1,0 +1,215 @@
+"""GPU parity tests of the propagation kernels against the CPU oracle (through the C ABI).
+
+Tolerance (FP64): the reference's own golden-vector criterion (numba_osc_tests.py:82)
+rtol = 1e-10, atol = 1e-14 is required of >= 99.9 % of the probabilities, and every probability
+must satisfy rtol = 1e-10 with atol = 1e-12: the reference's own unitarity noise on these inputs is
+6e-14 (tests/golden/make_golden.py log), i.e. its results carry ~1e-13 absolute rounding noise, so
+a tighter absolute bound would compare noise with noise.
+"""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from conftest import AC_KW_F8, ROOT, load_golden  # noqa: E402
+
+PREM12 = os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _earth(prem_file=PREM12, depth=2.0, height=20.0, ye=(0.4656, 0.4656, 0.4957), dtype=np.float64):
+    from pisa_b200 import ops
+    L = oracle.OracleLayers(np.loadtxt(prem_file), depth, height, dtype=dtype)
+    L.setElecFrac(*ye)
+    e = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    return L, e
+
+
+def _assert_prob(out, ref, what):
+    err = np.abs(out - ref)
+    strict = np.isclose(out, ref, **AC_KW_F8)
+    loose = np.isclose(out, ref, rtol=1e-10, atol=1e-12)
+    assert loose.all(), (what, "max abs", err.max(), "n_bad", (~loose).sum())
+    assert strict.mean() >= 0.999, (what, "fraction within (1e-10, 1e-14)", strict.mean())
+
+
+def _keys(g):
+    return sorted({k.rsplit("/", 1)[0] for k in g.files if k.count("/") == 2})
+
+
+def test_golden_pickles_through_abi():
+    """The reference's own golden vectors (explicit layers) through pisab_prob3_propagate_layers."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_pickles_f8.npz")
+    cases = sorted({k.split("/")[1] for k in g.files if k.startswith("propagate_scalar/")})
+    cases = [c for c in cases if c != "nufit32_std_decay"]
+    assert len(cases) == 12
+    for case in cases:
+        p = "propagate_scalar/%s/" % case
+        consts = ops.OscConsts.from_matrices(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], int(g[p + "decay_flag"]),
+                                             g[p + "mat_decay"], g[p + "lri_pot"])
+        e = torch.tensor([float(g[p + "energy"])], dtype=torch.float64, device=dev)
+        rho = torch.tensor(g[p + "densities"][None].astype(np.float64), device=dev)
+        dist = torch.tensor(g[p + "distances"][None].astype(np.float64), device=dev)
+        out = ops.propagate_layers(consts, int(g[p + "nubar"]), e, rho, dist).cpu().numpy()[0]
+        ref = g[p + "probability"]
+        assert np.allclose(out, ref, rtol=1e-10, atol=1e-13), (case, np.abs(out - ref).max())
+
+
+def test_decay_branch_is_rejected():
+    from pisa_b200 import ops
+    from pisa_b200._lib import PisabError
+    dev = _dev()
+    g = load_golden("ref_pickles_f8.npz")
+    p = "propagate_scalar/nufit32_std_decay/"
+    consts = ops.OscConsts.from_matrices(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], 1, g[p + "mat_decay"], g[p + "lri_pot"])
+    e = torch.ones(1, dtype=torch.float64, device=dev)
+    with pytest.raises(PisabError):
+        ops.propagate_layers(consts, 1, e, torch.ones((1, 3), dtype=torch.float64, device=dev),
+                             torch.ones((1, 3), dtype=torch.float64, device=dev))
+
+
+def test_reference_fixture_events_earth_and_layers():
+    """1200 reference events x 13 parameter sets: in-kernel layers and explicit layers, vs the
+    committed outputs of the unmodified reference."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    L, earth = _earth()
+    _, den, dis = L.calcLayers(g["coszen"])
+    e = torch.tensor(g["energy"], device=dev)
+    cz = torch.tensor(g["coszen"], device=dev)
+    rho_t, dis_t = torch.tensor(den, device=dev), torch.tensor(dis, device=dev)
+    for key in _keys(g):
+        consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], -1, None,
+                                             g[key + "/lri_pot"])
+        nubar = int(g[key + "/nubar"])
+        ref = g[key + "/probability"]
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+        _assert_prob(full.cpu().numpy(), ref, key + " earth")
+        lay = ops.propagate_layers(consts, nubar, e, rho_t, dis_t)
+        _assert_prob(lay.cpu().numpy(), ref, key + " layers")
+        for flav in (0, 1, 2):
+            _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=flav, want_probability=False)
+            _assert_prob(pe.cpu().numpy(), ref[:, 0, flav], key + " prob_e")
+            _assert_prob(pmu.cpu().numpy(), ref[:, 1, flav], key + " prob_mu")
+
+
+@pytest.mark.parametrize("nubar", [1, -1])
+def test_large_random_sample_vs_oracle(nubar):
+    """2e5 seeded events (SURVEY 8d laws) against the oracle, NSI + deltacp, plus unitarity on 2e6."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    key = "nufit20_nh_dcp306_stdnsi/nu"
+    consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"])
+    L, earth = _earth()
+    rng = np.random.default_rng(0)
+    n = 200_000
+    energy = 10 ** rng.uniform(0, 3, n)
+    coszen = rng.uniform(-1, 1, n)
+    _, den, dis = L.calcLayers(coszen)
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    ref = oracle.propagate_array(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], -1, zero, np.zeros((3, 3)),
+                                 nubar, energy, den, dis, n_threads=os.cpu_count())
+    full, _, _ = ops.propagate_earth(consts, earth, nubar, torch.tensor(energy, device=dev),
+                                     torch.tensor(coszen, device=dev))
+    _assert_prob(full.cpu().numpy(), ref, "random %d" % nubar)
+    # size-independent property at a larger size: rows and columns sum to one
+    n2 = 2_000_000
+    e2 = torch.tensor(10 ** rng.uniform(0, 3, n2), device=dev)
+    c2 = torch.tensor(rng.uniform(-1, 1, n2), device=dev)
+    p2, _, _ = ops.propagate_earth(consts, earth, nubar, e2, c2)
+    assert float((p2.sum(dim=1) - 1).abs().max()) < 5e-12
+    assert float((p2.sum(dim=2) - 1).abs().max()) < 5e-12
+
+
+def test_per_event_species_arrays():
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    L, earth = _earth()
+    e = torch.tensor(g["energy"], device=dev)
+    cz = torch.tensor(g["coszen"], device=dev)
+    n = e.numel()
+    rng = np.random.default_rng(5)
+    nubar = rng.choice([1, -1], n).astype(np.int32)
+    flav = rng.integers(0, 3, n).astype(np.int32)
+    key = "nufit20_nh_dcp306"
+    consts = ops.OscConsts.from_matrices(g[key + "/nu/dm"], g[key + "/nu/mix"], g[key + "/nu/mat_pot"])
+    ref = np.where((nubar > 0)[:, None, None], g[key + "/nu/probability"], g[key + "/nubar/probability"])
+    _, pe, pmu = ops.propagate_earth(consts, earth, torch.tensor(nubar, device=dev), e, cz,
+                                     flav=torch.tensor(flav, device=dev), want_probability=False)
+    _assert_prob(pe.cpu().numpy(), ref[np.arange(n), 0, flav], "per-event prob_e")
+    _assert_prob(pmu.cpu().numpy(), ref[np.arange(n), 1, flav], "per-event prob_mu")
+
+
+def test_fp32_mode_vs_fp64_oracle():
+    """FP32 storage mode: <= 1e-5 absolute against the FP64 oracle on the same (float32) inputs
+    (BASELINE.json north_star); the distance to the reference's own FP32 fixtures is reported."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g4 = load_golden("ref_prob3_f4.npz")
+    L, earth = _earth()
+    e32, cz32 = g4["energy"], g4["coszen"]
+    _, den, dis = L.calcLayers(cz32.astype(np.float64))
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    for key in _keys(g4):
+        nubar = int(g4[key + "/nubar"])
+        dm, mix, mp, lri = (g4[key + "/" + k].astype(np.complex128 if k in ("mix", "mat_pot") else np.float64)
+                            for k in ("dm", "mix", "mat_pot", "lri_pot"))
+        consts = ops.OscConsts.from_matrices(dm, mix, mp, -1, None, lri)
+        ref64 = oracle.propagate_array(dm, mix, mp, -1, zero, lri, nubar, e32.astype(np.float64), den, dis)
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, torch.tensor(e32, device=dev),
+                                         torch.tensor(cz32, device=dev))
+        assert full.dtype == torch.float32
+        out = full.cpu().numpy().astype(np.float64)
+        assert np.abs(out - ref64).max() <= 1e-5, (key, np.abs(out - ref64).max())
+        # informational: the reference's own FP32 path on the same inputs
+        d_ref4 = np.abs(out - g4[key + "/probability"]).max()
+        assert d_ref4 < 5e-4, (key, d_ref4)
+
+
+def test_layers_kernel_bit_exact():
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_layers_f8.npz")
+    for key in sorted({k.rsplit("/", 1)[0] for k in g.files}):
+        model = key.split("/")[0]
+        depth, height, yei, yeo, yem = g[key + "/params"]
+        L, earth = _earth(os.path.join(ROOT, "pisa_b200", "resources", "osc", model + ".dat"), depth, height,
+                          (yei, yeo, yem))
+        cz = g[key + "/cz"]
+        tangents = L.coszen_limit[(L.coszen_limit > -1) & (L.coszen_limit < 1)]
+        ok = ~np.isin(cz, tangents)  # exact tangents: reference defect, see test_oracle_golden.py
+        nl, den, dis = ops.layers_calc(earth, torch.tensor(cz[ok], device=dev))
+        assert np.array_equal(nl.cpu().numpy(), g[key + "/n_layers"][ok].astype(np.int32)), key
+        assert np.array_equal(den.cpu().numpy(), g[key + "/density"][ok]), key
+        assert np.array_equal(dis.cpu().numpy(), g[key + "/distance"][ok]), key
+
+
+def test_unsupported_geometry_and_bad_args():
+    from pisa_b200 import ops
+    from pisa_b200._lib import PisabError
+    dev = _dev()
+    # detector below the first inner PREM boundary (idx != 2): the reference itself is undefined
+    L, earth = _earth(depth=5.0)
+    cz = torch.zeros(4, dtype=torch.float64, device=dev)
+    with pytest.raises(PisabError):
+        ops.layers_calc(earth, cz)
+    with pytest.raises(TypeError):
+        ops.layers_calc(earth, torch.zeros(4, dtype=torch.float64))  # CPU tensor: no CPU path
+    # empty input is fine
+    L, earth = _earth()
+    nl, den, dis = ops.layers_calc(earth, torch.zeros(0, dtype=torch.float64, device=dev))
+    assert den.shape == (0, 28)
