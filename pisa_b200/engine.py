@@ -1,0 +1,162 @@
+"""Template-evaluation engine: the fit-loop fast path over a set of event containers.
+
+One call = one template: for every container (nue_cc ... nutaubar_nc, prob3.py:401-404) run the
+fused kernel (prob3 through the Earth -> ``weights *= flux.prob`` -> weighted histogram with
+sumw2) and return one device buffer ``[n_containers, 2, n_bins]`` (sum w, sum w^2).  With
+``torch.distributed`` initialised, events are sharded over ranks and the buffer -- the only
+thing that crosses NVLink -- is all-reduced once per template.
+
+This is what ``Pipeline.run()`` of ``osc.prob3`` + ``utils.hist`` in events mode computes
+(prob3.py:452-622, hist.py:129-218) without the intermediate HBM round trips.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+_NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
+
+EVENT_KEYS = ("true_energy", "true_coszen", "nu_flux", "weights", "index")
+
+
+class _Block:
+    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage")
+
+    def __init__(self, name, nubar, flav, n):
+        self.name, self.nubar, self.flav, self.n = name, int(nubar), int(flav), int(n)
+        self.dev, self.host, self.stage = {}, {}, None
+
+
+class ReweightEngine:
+    """Device-resident event containers + fused template evaluation."""
+
+    def __init__(self, earth, n_bins, dtype=np.float64, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pisa_b200.engine needs a CUDA device (there is no CPU path)")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        self.earth = earth
+        self.n_bins = int(n_bins)
+        self.tdtype = _NP2T[np.dtype(dtype)]
+        self.blocks = []
+        self._out = None
+        self._copy_stream = None
+        self._host_out = None
+
+    # ------------------------------------------------------------------ containers -------
+    def add_container(self, name, nubar, flav, true_energy, true_coszen, nu_flux, weights, index):
+        """Register one container.  Tensors may live on the device (resident mode) or be pinned
+        host tensors / numpy arrays (host mode, see evaluate_host)."""
+        arrays = dict(true_energy=true_energy, true_coszen=true_coszen, nu_flux=nu_flux, weights=weights,
+                      index=index)
+        n = int(arrays["true_energy"].shape[0])
+        blk = _Block(name, nubar, flav, n)
+        for k, a in arrays.items():
+            want = torch.int32 if k == "index" else self.tdtype
+            t = torch.as_tensor(a)
+            if t.dtype != want:
+                raise TypeError("%s.%s must be %s" % (name, k, want))
+            if t.is_cuda:
+                blk.dev[k] = t.contiguous()
+            else:
+                blk.host[k] = t.contiguous().pin_memory() if not t.is_pinned() else t
+        self.blocks.append(blk)
+        self._out = None
+        return blk
+
+    @property
+    def n_events(self):
+        return sum(b.n for b in self.blocks)
+
+    def _result_buffer(self):
+        if self._out is None or self._out.shape[0] != len(self.blocks):
+            self._out = torch.empty((len(self.blocks), 2, self.n_bins), dtype=torch.float64, device=self.device)
+        return self._out
+
+    # ------------------------------------------------------------------- evaluation ------
+    def _launch(self, consts, blk, arrays, out_row, weights_out=None):
+        ops.reweight_hist(consts, self.earth, blk.nubar, blk.flav, arrays["true_energy"], arrays["true_coszen"],
+                          arrays["nu_flux"], arrays["weights"], arrays["index"], self.n_bins,
+                          weights_out=weights_out, hist=out_row[0], hist_w2=out_row[1])
+
+    def evaluate(self, consts, allreduce=True, events=None):
+        """Resident mode: all event arrays already in HBM.  Returns [n_containers, 2, n_bins].
+        ``events``: optional list that receives one (start, stop) CUDA-event pair per fused
+        launch (for the roofline timing in bench.py)."""
+        out = self._result_buffer()
+        for i, blk in enumerate(self.blocks):
+            if events is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            self._launch(consts, blk, blk.dev, out[i])
+            if events is not None:
+                e1.record()
+                events.append((e0, e1))
+        if allreduce:
+            self.allreduce(out)
+        return out
+
+    def evaluate_host(self, consts, allreduce=True):
+        """Host mode: event arrays live in pinned host memory; every call copies them to the
+        device (double-buffered on a copy stream so the copy of container i+1 overlaps the
+        kernel of container i) and returns the histograms as a HOST numpy array."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        out = self._result_buffer()
+        main = torch.cuda.current_stream()
+        nmax = max(b.n for b in self.blocks)
+        stages = getattr(self, "_stages", None)
+        if stages is None or stages[0]["true_energy"].shape[0] < nmax:
+            stages = []
+            for _ in range(2):
+                stages.append(dict(
+                    true_energy=torch.empty(nmax, dtype=self.tdtype, device=self.device),
+                    true_coszen=torch.empty(nmax, dtype=self.tdtype, device=self.device),
+                    nu_flux=torch.empty((nmax, 2), dtype=self.tdtype, device=self.device),
+                    weights=torch.empty(nmax, dtype=self.tdtype, device=self.device),
+                    index=torch.empty(nmax, dtype=torch.int32, device=self.device)))
+            self._stages = stages
+            self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            for e in self._stage_free:
+                e.record(main)
+        h2d = 0
+        for i, blk in enumerate(self.blocks):
+            s = i & 1
+            st = stages[s]
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._stage_free[s])
+                views = {}
+                for k in EVENT_KEYS:
+                    src = blk.host[k]
+                    dst = st[k][:blk.n]
+                    dst.copy_(src, non_blocking=True)
+                    views[k] = dst
+                    h2d += src.numel() * src.element_size()
+                self._stage_ready[s].record(self._copy_stream)
+            main.wait_event(self._stage_ready[s])
+            self._launch(consts, blk, views, out[i])
+            self._stage_free[s].record(main)
+        if allreduce:
+            self.allreduce(out)
+        if self._host_out is None or self._host_out.shape != out.shape:
+            self._host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+        self._host_out.copy_(out, non_blocking=True)
+        main.synchronize()
+        self.last_h2d_bytes = h2d
+        self.last_d2h_bytes = out.numel() * out.element_size()
+        return self._host_out.numpy()
+
+    @staticmethod
+    def allreduce(buf):
+        """Sum the per-GPU histograms (one NCCL all-reduce per template; no-op on one rank)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return buf
+
+
+def shard_slice(n, rank, world):
+    """Contiguous slice [start, stop) of n events owned by `rank` (fixed boundaries -> reproducible)."""
+    base, rem = divmod(int(n), int(world))
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)

@@ -1,0 +1,187 @@
+"""GPU parity tests: bin indexing (bit-exact), weighted histogram, lookup, fused reweight+hist."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from conftest import ROOT, load_golden  # noqa: E402
+
+DRAGON_E_EDGES = np.array([5.62341325, 7.49894209, 10.0, 13.33521432, 17.7827941, 23.71373706,
+                           31.6227766, 42.16965034, 56.23413252])
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _sample(n, seed, dtype=np.float64):
+    """SURVEY 8d reco variables."""
+    rng = np.random.default_rng(seed)
+    true_e = 10 ** rng.uniform(0, 3, n)
+    true_cz = rng.uniform(-1, 1, n)
+    reco_e = true_e * rng.lognormal(0, 0.3, n)
+    reco_cz = true_cz + rng.normal(0, 0.2, n)
+    pid = rng.integers(0, 2, n).astype(np.float64)
+    return reco_e.astype(dtype), reco_cz.astype(dtype), pid.astype(dtype)
+
+
+def _edge_values(edges):
+    fin = edges[np.isfinite(edges)]
+    return np.concatenate([edges, np.nextafter(fin, np.inf), np.nextafter(fin, -np.inf),
+                           [-np.inf, np.inf, np.nan, fin.min() - 1, fin.max() + 1]])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_index_bit_exact_lin_log_edges(dtype):
+    from pisa_b200 import ops
+    dev = _dev()
+    n = 300_000
+    reco_e, reco_cz, pid = _sample(n, 0, dtype)
+    # edge cases in every dimension (translation.py:868-905 spirit)
+    ev = _edge_values(DRAGON_E_EDGES).astype(dtype)
+    reco_e[:len(ev)] = ev
+    cv = _edge_values(np.linspace(-1, 1, 9)).astype(dtype)
+    reco_cz[100:100 + len(cv)] = cv
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    t = [torch.tensor(a, dtype=tdt, device=dev) for a in (reco_e, reco_cz, pid)]
+
+    # (a) irregular energy edges (FP64 classification of dragon_datarelease)
+    b, keep = ops.make_binning([dict(kind="edges", n_bins=8, edges=DRAGON_E_EDGES),
+                                dict(kind="lin", n_bins=8, lo=-1.0, hi=1.0),
+                                dict(kind="lin", n_bins=2, lo=0.0, hi=2.0)], dev)
+    idx = ops.hist_index(b, t).cpu().numpy()
+    ie = oracle.digitize_irregular(reco_e, DRAGON_E_EDGES, dtype)
+    i2, _ = oracle.regular_index([reco_cz, pid], [-1.0, 0.0], [1.0, 2.0], [8, 2], dtype)
+    ref = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
+    assert np.array_equal(idx, ref.astype(np.int32))
+
+    # (b) log-regular energy axis: linear bins in log(x) (hist.py:114-121)
+    with np.errstate(all="ignore"):
+        log_e = np.log(reco_e)  # numpy log in FTYPE, like Container.translate
+    b, keep = ops.make_binning([dict(kind="log", n_bins=8, lo=5.62341325, hi=56.23413252),
+                                dict(kind="lin", n_bins=8, lo=-1.0, hi=1.0),
+                                dict(kind="lin", n_bins=2, lo=0.0, hi=2.0)], dev)
+    idx = ops.hist_index(b, t).cpu().numpy()
+    lo, hi = np.log(5.62341325), np.log(56.23413252)
+    ref, _ = oracle.regular_index([log_e, reco_cz, pid], [lo, -1.0, 0.0], [hi, 1.0, 2.0], [8, 8, 2], dtype)
+    diff = np.flatnonzero(idx != ref)
+    # device log vs numpy log can differ by 1 ulp: only events within 1 ulp of an edge may move
+    assert len(diff) <= 2, (len(diff), reco_e[diff][:5])
+
+
+def test_accumulate_vs_oracle_and_deterministic():
+    from pisa_b200 import ops
+    dev = _dev()
+    n = 1_000_003
+    rng = np.random.default_rng(2)
+    idx = rng.integers(-1, 128, n).astype(np.int32)
+    idx[rng.random(n) < 0.3] = 5  # a hot bin
+    w = rng.uniform(0, 2, n)
+    ti, tw = torch.tensor(idx, device=dev), torch.tensor(w, device=dev)
+    h, h2 = ops.hist_accumulate(ti, tw, 128)
+    ref = oracle.accumulate(idx, w, 128)
+    ref2 = oracle.accumulate(idx, w * w, 128)
+    assert np.allclose(h.cpu().numpy(), ref, rtol=1e-10, atol=0)
+    assert np.allclose(h2.cpu().numpy(), ref2, rtol=1e-10, atol=0)
+    # counts are exact
+    c, _ = ops.hist_accumulate(ti, None, 128, want_w2=False)
+    assert np.array_equal(c.cpu().numpy(), np.bincount(idx[idx >= 0], minlength=128).astype(np.float64))
+    # run-to-run bit reproducibility (fixed accumulation order, no float atomics)
+    for _ in range(3):
+        hb, hb2 = ops.hist_accumulate(ti, tw, 128)
+        assert torch.equal(hb, h) and torch.equal(hb2, h2)
+    # ragged / tiny / empty inputs
+    for m in (0, 1, 31, 33, 129):
+        hh, _ = ops.hist_accumulate(ti[:m].contiguous(), tw[:m].contiguous(), 128)
+        assert np.allclose(hh.cpu().numpy(), oracle.accumulate(idx[:m], w[:m], 128), rtol=1e-12, atol=0)
+    # float32 weights, large binning (atomic path)
+    w32 = w.astype(np.float32)
+    idx_big = rng.integers(0, 3200, n).astype(np.int32)
+    hb, _ = ops.hist_accumulate(torch.tensor(idx_big, device=dev), torch.tensor(w32, device=dev), 3200)
+    assert np.allclose(hb.cpu().numpy(), oracle.accumulate(idx_big, w32.astype(np.float64), 3200), rtol=1e-10)
+
+
+def test_lookup_exact():
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_hist_f8.npz")
+    x, y = g["lookup/x"], g["lookup/y"]
+    x0, x1, nx, y0, y1, ny, _, _, _ = g["lookup/binning"]
+    b, keep = ops.make_binning([dict(kind="lin", n_bins=int(nx), lo=x0, hi=x1),
+                                dict(kind="lin", n_bins=int(ny), lo=y0, hi=y1)], dev)
+    idx = ops.hist_index(b, [torch.tensor(x, device=dev), torch.tensor(y, device=dev)])
+    ref_idx, _ = oracle.regular_index([x, y], [x0, y0], [x1, y1], [nx, ny])
+    assert np.array_equal(idx.cpu().numpy(), ref_idx.astype(np.int32))
+    for key in ("h2", "h2a"):
+        out = ops.lookup(idx, torch.tensor(g["lookup/" + key], device=dev)).cpu().numpy()
+        assert np.array_equal(out, oracle.lookup(ref_idx, g["lookup/" + key]))
+    # and against the reference's own njit lookups, except the events it reads out of bounds
+    def rounds_up(v, lo, hi, n):
+        return (v >= lo) & (v < hi) & (((v - lo) * (n / (hi - lo))).astype(np.int64) >= n)
+    ok = ~(rounds_up(x, x0, x1, nx) | rounds_up(y, y0, y1, ny))
+    out = ops.lookup(idx, torch.tensor(g["lookup/h2"], device=dev)).cpu().numpy()
+    assert np.array_equal(out[ok], g["lookup/o2"][ok])
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_reweight_hist_vs_oracle_chain(dtype):
+    """prob3 -> fill_probs -> weights *= flux.prob -> hist(w), hist(w^2): fused kernel vs the oracle."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    key = "nufit20_nh_dcp306_stdnsi/nu"
+    dm, mix, mat_pot = g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"]
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    n = 100_000
+    rng = np.random.default_rng(1)
+    energy = (10 ** rng.uniform(0, 3, n)).astype(dtype)
+    coszen = rng.uniform(-1, 1, n).astype(dtype)
+    flux = rng.uniform(0.5, 1.5, (n, 2)).astype(dtype)
+    w0 = rng.uniform(0, 1, n).astype(dtype)
+    idx = rng.integers(-1, 128, n).astype(np.int32)
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    T = lambda a: torch.tensor(a, dtype=tdt, device=dev)  # noqa: E731
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    _, den, dis = L.calcLayers(coszen.astype(np.float64))
+    for nubar, flav in ((1, 1), (-1, 0), (1, 2)):
+        prob = oracle.propagate_array(dm, mix, mat_pot, -1, zero, np.zeros((3, 3)), nubar,
+                                      energy.astype(np.float64), den, dis, n_threads=os.cpu_count())
+        pe, pmu = oracle.fill_probs(prob, 0, flav), oracle.fill_probs(prob, 1, flav)
+        w = w0.astype(np.float64) * (flux[:, 0].astype(np.float64) * pe + flux[:, 1].astype(np.float64) * pmu)
+        ref, ref2 = oracle.accumulate(idx, w, 128), oracle.accumulate(idx, w * w, 128)
+        wout = torch.empty(n, dtype=tdt, device=dev)
+        h, h2 = ops.reweight_hist(consts, earth, nubar, flav, T(energy), T(coszen), T(flux), T(w0),
+                                  torch.tensor(idx, device=dev), 128, weights_out=wout)
+        tol = 1e-10 if dtype == np.float64 else 2e-5
+        assert np.allclose(h.cpu().numpy(), ref, rtol=tol), np.abs(h.cpu().numpy() / ref - 1).max()
+        assert np.allclose(h2.cpu().numpy(), ref2, rtol=2 * tol)
+        assert np.allclose(wout.cpu().numpy(), w, rtol=tol, atol=1e-12 if dtype == np.float64 else 1e-5)
+        # unfused path gives the same histogram (binned weights within 1e-10)
+        _, pe_t, pmu_t = ops.propagate_earth(consts, earth, nubar, T(energy), T(coszen), flav=flav,
+                                             want_probability=False)
+        w_t = ops.apply_osc_weights(T(flux), pe_t, pmu_t, T(w0).clone())
+        hu, hu2 = ops.hist_accumulate(torch.tensor(idx, device=dev), w_t, 128)
+        assert np.allclose(hu.cpu().numpy(), ref, rtol=tol)
+
+
+def test_mod_chi2():
+    from pisa_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(0)
+    exp = rng.uniform(0, 50, 128)
+    exp[3] = 0.0
+    w2 = rng.uniform(0, 5, 128)
+    obs = rng.poisson(exp).astype(np.float64)
+    e = np.clip(exp, 1e-10, np.inf)
+    ref = ((obs - e) ** 2 / (w2 + e)).sum()  # stats.py:674-695 with sigma^2 = sumw2
+    out = ops.mod_chi2(torch.tensor(exp, device=dev), torch.tensor(w2, device=dev), torch.tensor(obs, device=dev))
+    assert np.isclose(float(out), ref, rtol=1e-12)

@@ -1,0 +1,65 @@
+"""Host-side parameter builders vs matrices produced by the reference classes (CPU only)."""
+import os
+
+import numpy as np
+
+from conftest import ROOT, load_golden
+from pisa_b200.stages.osc.layers import Layers
+from pisa_b200.stages.osc.nsi_params import StdNSIParams
+from pisa_b200.stages.osc.osc_params import OscParams
+
+import sys
+sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+from make_golden import PARAM_SETS  # noqa: E402  (pure-python dict; no reference import at module level)
+
+
+def _osc(ps):
+    op = OscParams()
+    op.theta12, op.theta13, op.theta23 = (np.deg2rad(ps[k]) for k in ("t12", "t13", "t23"))
+    op.deltacp = np.deg2rad(ps["dcp"])
+    op.dm21, op.dm31 = ps["dm21"], ps["dm31"]
+    return op
+
+
+def test_mix_and_dm_matrices_bitwise():
+    g = load_golden("ref_params_f8.npz")
+    for name, ps in PARAM_SETS.items():
+        op = _osc(ps)
+        assert np.array_equal(op.mix_matrix_complex, g[name + "/mix"]), name
+        assert np.array_equal(op.mix_matrix_reparam_complex, g[name + "/mix_reparam"]), name
+        assert np.array_equal(op.dm_matrix, g[name + "/dm"]), name
+    op = OscParams()
+    assert np.array_equal(op.dm_matrix, g["degenerate/dm"])
+
+
+def test_std_nsi_eps_matrix_bitwise():
+    g = load_golden("ref_params_f8.npz")
+    ps = PARAM_SETS["nufit20_nh_dcp306_stdnsi"]["nsi"]
+    nsi = StdNSIParams()
+    nsi.eps_ee = ps["eps_ee"]
+    nsi.eps_emu = (ps["eps_emu"][0], np.deg2rad(ps["eps_emu"][1]))
+    nsi.eps_etau = (ps["eps_etau"][0], np.deg2rad(ps["eps_etau"][1]))
+    nsi.eps_mumu = ps["eps_mumu"]
+    nsi.eps_mutau = (ps["eps_mutau"][0], np.deg2rad(ps["eps_mutau"][1]))
+    nsi.eps_tautau = ps["eps_tautau"]
+    assert np.array_equal(nsi.eps_matrix, g["nufit20_nh_dcp306_stdnsi/eps"])
+    std = np.zeros((3, 3), dtype=np.complex128)
+    std[0, 0] += 1.0
+    assert np.array_equal(std + nsi.eps_matrix, g["nufit20_nh_dcp306_stdnsi/mat_pot"])
+
+
+def test_layers_host_tables_bitwise():
+    g = load_golden("ref_layers_f8.npz")
+    for key in sorted({k.rsplit("/", 1)[0] for k in g.files}):
+        model = key.split("/")[0]
+        depth, height, yei, yeo, yem = g[key + "/params"]
+        L = Layers(os.path.join(ROOT, "pisa_b200", "resources", "osc", model + ".dat"), depth, height)
+        L.setElecFrac(yei, yeo, yem)
+        assert np.array_equal(L.radii, g[key + "/radii"])
+        assert np.array_equal(L.rhos, g[key + "/rhos"])
+        assert np.array_equal(L.coszen_limit, g[key + "/coszen_limit"])
+        assert L.max_layers == int(g[key + "/max_layers"]) and L.r_detector == float(g[key + "/r_detector"])
+        # idempotence of setElecFrac (test_layers_4, layers.py:669-772)
+        rhos = L.rhos.copy()
+        L.setElecFrac(yei, yeo, yem)
+        assert np.array_equal(rhos, L.rhos)
