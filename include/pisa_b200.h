@@ -114,17 +114,31 @@ int pisab_prob3_propagate_layers_f32(const pisab_osc_consts_t *consts, int32_t n
 /* Layers evaluated in-kernel from coszen (prob3.setup_function + compute_function fused,
  * prob3.py:406-409,581-605).  Any of d_probability ([n,3,3]) or (d_prob_e, d_prob_mu)
  * ([n] each, = fill_probs(probability, 0|1, flav), numba_osc_hostfuncs.py:206-221) may be
- * NULL.  flav: scalar when d_flav == NULL. */
+ * NULL.  flav: scalar when d_flav == NULL.
+ * d_order (optional, may be NULL): a permutation of 0..n-1 giving the order in which events are
+ * assigned to threads.  Results are always written to the event's own slot, so it changes
+ * nothing but speed: pass the events grouped by pisab_layer_count() (number of crossed Earth
+ * shells) and every warp walks the same number of layers.  It depends on coszen only, i.e. it
+ * is setup-time work like the reference's calcLayers in prob3.setup_function (prob3.py:406-409). */
 int pisab_prob3_propagate_earth_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     int32_t nubar, const int32_t *d_nubar, int32_t flav,
                                     const int32_t *d_flav, const double *d_energy,
-                                    const double *d_coszen, int64_t n, double *d_probability,
-                                    double *d_prob_e, double *d_prob_mu, void *stream);
+                                    const double *d_coszen, const int32_t *d_order, int64_t n,
+                                    double *d_probability, double *d_prob_e, double *d_prob_mu,
+                                    void *stream);
 int pisab_prob3_propagate_earth_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     int32_t nubar, const int32_t *d_nubar, int32_t flav,
                                     const int32_t *d_flav, const float *d_energy,
-                                    const float *d_coszen, int64_t n, float *d_probability,
-                                    float *d_prob_e, float *d_prob_mu, void *stream);
+                                    const float *d_coszen, const int32_t *d_order, int64_t n,
+                                    float *d_probability, float *d_prob_e, float *d_prob_mu,
+                                    void *stream);
+
+/* Number of Earth shells crossed per event (count of coszen_limit[j] > coszen, layers.py:112,148):
+ * the sort key for d_order above. */
+int pisab_layer_count_f64(const pisab_earth_t *earth, const double *d_coszen, int64_t n,
+                          int32_t *d_count, void *stream);
+int pisab_layer_count_f32(const pisab_earth_t *earth, const float *d_coszen, int64_t n,
+                          int32_t *d_count, void *stream);
 
 /* fill_probs (numba_osc_hostfuncs.py:206-221): out[n] = probability[n, initial_flav, flav] */
 int pisab_fill_probs_f64(const double *d_probability, int32_t initial_flav, int32_t flav,
@@ -176,12 +190,14 @@ int pisab_lookup_f32(const int32_t *d_index, const float *d_flat_hist, int64_t n
 /* For every event: probabilities through the Earth (as *_propagate_earth), then
  *   w = weights_in * (nu_flux[0]*prob_e + nu_flux[1]*prob_mu)       (prob3.py:621-622)
  * and hist[index] += w, hist_w2[index] += w*w (hist.py:198-209, error_method 'sumw2').
- * d_weights_out / d_prob_e / d_prob_mu are optional per-event outputs. */
+ * d_weights_out / d_prob_e / d_prob_mu are optional per-event outputs; d_order as above (the
+ * histogram is summed in thread order, so a fixed d_order keeps it bit-reproducible). */
 int pisab_reweight_hist_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                             int32_t nubar, const int32_t *d_nubar, int32_t flav,
                             const int32_t *d_flav, const double *d_energy, const double *d_coszen,
                             const double *d_nu_flux, const double *d_weights_in,
-                            const int32_t *d_index, int64_t n, int32_t n_bins, double *d_hist,
+                            const int32_t *d_index, const int32_t *d_order, int64_t n,
+                            int32_t n_bins, double *d_hist,
                             double *d_hist_w2, double *d_weights_out, double *d_prob_e,
                             double *d_prob_mu, void *d_workspace, int64_t workspace_bytes,
                             void *stream);
@@ -189,7 +205,8 @@ int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_
                             int32_t nubar, const int32_t *d_nubar, int32_t flav,
                             const int32_t *d_flav, const float *d_energy, const float *d_coszen,
                             const float *d_nu_flux, const float *d_weights_in,
-                            const int32_t *d_index, int64_t n, int32_t n_bins, double *d_hist,
+                            const int32_t *d_index, const int32_t *d_order, int64_t n,
+                            int32_t n_bins, double *d_hist,
                             double *d_hist_w2, float *d_weights_out, float *d_prob_e,
                             float *d_prob_mu, void *d_workspace, int64_t workspace_bytes,
                             void *stream);

@@ -75,14 +75,15 @@ _SIGNATURES = {
     "pisab_prob3_propagate_layers": (c_i32, [ctypes.POINTER(OscConsts), c_i32, c_vp, c_vp, c_vp, c_vp, c_i64,
                                              c_i32, c_vp, c_vp]),
     "pisab_prob3_propagate_earth": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth), c_i32, c_vp, c_i32,
-                                            c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+                                            c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "pisab_layer_count": (c_i32, [ctypes.POINTER(Earth), c_vp, c_i64, c_vp, c_vp]),
     "pisab_fill_probs": (c_i32, [c_vp, c_i32, c_i32, c_i64, c_vp, c_vp]),
     "pisab_apply_osc_weights": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pisab_hist_index": (c_i32, [ctypes.POINTER(Binning), ctypes.POINTER(c_vp), c_i64, c_vp, c_vp]),
     "pisab_hist_accumulate": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_lookup": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp]),
     "pisab_reweight_hist": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth), c_i32, c_vp, c_i32, c_vp,
-                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                    c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                                     c_vp, c_i64, c_vp]),
 }
 _UNTYPED = {

@@ -79,6 +79,36 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
 }
 
 template <typename IO>
+__global__ void __launch_bounds__(256)
+layer_count_kernel(const __grid_constant__ EarthTable earth, const IO *__restrict__ coszen, int64_t n,
+                   int32_t *__restrict__ count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double cz = (double)__ldg(coszen + i);
+        int k = 0;
+        for (int j = 0; j < earth.n_radii; ++j) k += earth.limit[j] > cz;
+        count[i] = k;
+    }
+}
+
+template <typename IO>
+static int layer_count_impl(const pisab_earth_t *earth, const IO *d_coszen, int64_t n, int32_t *d_count,
+                            void *stream) {
+    if (n < 0 || (n > 0 && (!d_coszen || !d_count))) { set_error("bad arguments"); return PISAB_ERR_ARG; }
+    EarthTable et;
+    int rc = build_earth_table(earth, &et);
+    if (rc) return rc;
+    if (n == 0) return PISAB_OK;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    layer_count_kernel<IO><<<grid, 256, 0, (cudaStream_t)stream>>>(et, d_coszen, n, d_count);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+template <typename IO>
 static int layers_impl(const pisab_earth_t *earth, const IO *d_coszen, int64_t n, IO *d_densities,
                        IO *d_distances, int32_t *d_n_layers, void *stream) {
     if (n < 0 || (n > 0 && (!d_coszen || !d_densities || !d_distances))) { set_error("bad arguments"); return PISAB_ERR_ARG; }
@@ -103,6 +133,14 @@ extern "C" {
 int pisab_layers_calc_f64(const pisab_earth_t *earth, const double *d_coszen, int64_t n,
                           double *d_densities, double *d_distances, int32_t *d_n_layers, void *stream) {
     return pisab::layers_impl<double>(earth, d_coszen, n, d_densities, d_distances, d_n_layers, stream);
+}
+int pisab_layer_count_f64(const pisab_earth_t *earth, const double *d_coszen, int64_t n, int32_t *d_count,
+                          void *stream) {
+    return pisab::layer_count_impl<double>(earth, d_coszen, n, d_count, stream);
+}
+int pisab_layer_count_f32(const pisab_earth_t *earth, const float *d_coszen, int64_t n, int32_t *d_count,
+                          void *stream) {
+    return pisab::layer_count_impl<float>(earth, d_coszen, n, d_count, stream);
 }
 int pisab_layers_calc_f32(const pisab_earth_t *earth, const float *d_coszen, int64_t n, float *d_densities,
                           float *d_distances, int32_t *d_n_layers, void *stream) {

@@ -127,13 +127,16 @@ __global__ void __launch_bounds__(kBlock)
 prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                    int nubar, const int32_t *__restrict__ d_nubar, int flav,
                    const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
-                   const IO *__restrict__ coszen, int64_t n, IO *__restrict__ probability,
-                   IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
+                   const IO *__restrict__ coszen, const int32_t *__restrict__ order, int64_t n,
+                   IO *__restrict__ probability, IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
     __shared__ OscTable s_osc;
     __shared__ EarthTable s_earth;
     copy_tables(osc, earth, &s_osc, &s_earth);
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+        // `order` (optional) lists the events grouped by number of crossed shells so that the 32
+        // lanes of a warp walk the same number of layers; results go back to the event's own slot
+        const int64_t i = order ? (int64_t)__ldg(order + t) : t;
         const double e = ld(energy, i), cz = ld(coszen, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
@@ -226,7 +229,8 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
                      int nubar, const int32_t *__restrict__ d_nubar, int flav,
                      const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
                      const IO *__restrict__ coszen, const IO *__restrict__ nu_flux,
-                     const IO *__restrict__ weights_in, const int32_t *__restrict__ index, int64_t n,
+                     const IO *__restrict__ weights_in, const int32_t *__restrict__ index,
+                     const int32_t *__restrict__ order, int64_t n,
                      int n_bins, double *__restrict__ partials, IO *__restrict__ weights_out,
                      IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
     extern __shared__ double s_hist[]; // [warps][2][n_bins] private bins, then staging
@@ -240,10 +244,11 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // warp-uniform trip count so that the warp-collective histogram step is always converged
     const int64_t warp_first = first - (threadIdx.x & 31);
     for (int64_t base = warp_first; base < n; base += stride) {
-        const int64_t i = base + (threadIdx.x & 31);
+        const int64_t t = base + (threadIdx.x & 31);
         double w = 0.0;
         int bin = -1;
-        if (i < n) {
+        if (t < n) {
+            const int64_t i = order ? (int64_t)__ldg(order + t) : t;
             const double e = ld(energy, i), cz = ld(coszen, i);
             const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
             const int fl = d_flav ? __ldg(d_flav + i) : flav;
@@ -283,8 +288,8 @@ template <typename IO>
 static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                 int32_t nubar, const int32_t *d_nubar, int32_t flav,
                                 const int32_t *d_flav, const IO *d_energy, const IO *d_coszen,
-                                int64_t n, IO *d_probability, IO *d_prob_e, IO *d_prob_mu,
-                                void *stream) {
+                                const int32_t *d_order, int64_t n, IO *d_probability, IO *d_prob_e,
+                                IO *d_prob_mu, void *stream) {
     if (n < 0 || (n > 0 && (!d_energy || !d_coszen))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
     if (!d_nubar && nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
     if ((d_prob_e == nullptr) != (d_prob_mu == nullptr)) { set_error("prob_e and prob_mu go together"); return PISAB_ERR_ARG; }
@@ -300,7 +305,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     if (d_probability) {
         LaunchTimer t(s);
         prob3_earth_kernel<IO, true><<<grid_for(n, 4), kBlock, 0, s>>>(
-            ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, n, d_probability, nullptr, nullptr);
+            ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, d_probability, nullptr, nullptr);
         note_launch();
     }
     if (d_prob_e && d_probability) {
@@ -317,7 +322,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     } else if (d_prob_e) {
         LaunchTimer t(s);
         prob3_earth_kernel<IO, false><<<grid_for(n, 4), kBlock, 0, s>>>(
-            ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, n, nullptr, d_prob_e, d_prob_mu);
+            ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, nullptr, d_prob_e, d_prob_mu);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
@@ -358,7 +363,8 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
                               int32_t nubar, const int32_t *d_nubar, int32_t flav,
                               const int32_t *d_flav, const IO *d_energy, const IO *d_coszen,
                               const IO *d_nu_flux, const IO *d_weights_in, const int32_t *d_index,
-                              int64_t n, int32_t n_bins, double *d_hist, double *d_hist_w2,
+                              const int32_t *d_order, int64_t n, int32_t n_bins, double *d_hist,
+                              double *d_hist_w2,
                               IO *d_weights_out, IO *d_prob_e, IO *d_prob_mu, void *d_workspace,
                               int64_t workspace_bytes, void *stream) {
     if (n < 0 || n_bins < 1 || !d_hist) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
@@ -390,7 +396,7 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
     {
         LaunchTimer t(s);
         reweight_hist_kernel<IO><<<grid, kBlock, smem, s>>>(ot, et, nubar, d_nubar, flav, d_flav, d_energy,
-                                                            d_coszen, d_nu_flux, d_weights_in, d_index, n, n_bins,
+                                                            d_coszen, d_nu_flux, d_weights_in, d_index, d_order, n, n_bins,
                                                             (double *)d_workspace, d_weights_out, d_prob_e, d_prob_mu);
         note_launch();
     }
@@ -403,17 +409,18 @@ extern "C" {
 int pisab_prob3_propagate_earth_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     int32_t nubar, const int32_t *d_nubar, int32_t flav,
                                     const int32_t *d_flav, const double *d_energy,
-                                    const double *d_coszen, int64_t n, double *d_probability,
-                                    double *d_prob_e, double *d_prob_mu, void *stream) {
-    return propagate_earth_impl<double>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, n,
+                                    const double *d_coszen, const int32_t *d_order, int64_t n,
+                                    double *d_probability, double *d_prob_e, double *d_prob_mu,
+                                    void *stream) {
+    return propagate_earth_impl<double>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n,
                                         d_probability, d_prob_e, d_prob_mu, stream);
 }
 int pisab_prob3_propagate_earth_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     int32_t nubar, const int32_t *d_nubar, int32_t flav,
                                     const int32_t *d_flav, const float *d_energy, const float *d_coszen,
-                                    int64_t n, float *d_probability, float *d_prob_e, float *d_prob_mu,
-                                    void *stream) {
-    return propagate_earth_impl<float>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, n,
+                                    const int32_t *d_order, int64_t n, float *d_probability,
+                                    float *d_prob_e, float *d_prob_mu, void *stream) {
+    return propagate_earth_impl<float>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n,
                                        d_probability, d_prob_e, d_prob_mu, stream);
 }
 int pisab_prob3_propagate_layers_f64(const pisab_osc_consts_t *consts, int32_t nubar,
@@ -433,22 +440,24 @@ int pisab_prob3_propagate_layers_f32(const pisab_osc_consts_t *consts, int32_t n
 int pisab_reweight_hist_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                             int32_t nubar, const int32_t *d_nubar, int32_t flav, const int32_t *d_flav,
                             const double *d_energy, const double *d_coszen, const double *d_nu_flux,
-                            const double *d_weights_in, const int32_t *d_index, int64_t n,
+                            const double *d_weights_in, const int32_t *d_index,
+                            const int32_t *d_order, int64_t n,
                             int32_t n_bins, double *d_hist, double *d_hist_w2, double *d_weights_out,
                             double *d_prob_e, double *d_prob_mu, void *d_workspace,
                             int64_t workspace_bytes, void *stream) {
     return reweight_hist_impl<double>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen,
-                                      d_nu_flux, d_weights_in, d_index, n, n_bins, d_hist, d_hist_w2,
+                                      d_nu_flux, d_weights_in, d_index, d_order, n, n_bins, d_hist, d_hist_w2,
                                       d_weights_out, d_prob_e, d_prob_mu, d_workspace, workspace_bytes, stream);
 }
 int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                             int32_t nubar, const int32_t *d_nubar, int32_t flav, const int32_t *d_flav,
                             const float *d_energy, const float *d_coszen, const float *d_nu_flux,
-                            const float *d_weights_in, const int32_t *d_index, int64_t n, int32_t n_bins,
+                            const float *d_weights_in, const int32_t *d_index, const int32_t *d_order,
+                            int64_t n, int32_t n_bins,
                             double *d_hist, double *d_hist_w2, float *d_weights_out, float *d_prob_e,
                             float *d_prob_mu, void *d_workspace, int64_t workspace_bytes, void *stream) {
     return reweight_hist_impl<float>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen,
-                                     d_nu_flux, d_weights_in, d_index, n, n_bins, d_hist, d_hist_w2,
+                                     d_nu_flux, d_weights_in, d_index, d_order, n, n_bins, d_hist, d_hist_w2,
                                      d_weights_out, d_prob_e, d_prob_mu, d_workspace, workspace_bytes, stream);
 }
 

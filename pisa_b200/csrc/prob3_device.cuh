@@ -42,6 +42,34 @@ __device__ __forceinline__ Cplx cfma(Cplx a, Cplx b, Cplx c) { // a*b + c
 
 typedef Cplx Mat3[3][3];
 
+// sin/cos for |x| < ~1e5 rad (phases here are < 1e3): two-term Cody-Waite reduction with FMA and
+// the fdlibm kernel polynomials on [-pi/4, pi/4].  No Payne-Hanek slow path (keeps the code small
+// enough for the instruction cache); max error ~1 ulp, same as the CUDA fast path.
+__device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
+    const double kd = rint(x * 0.63661977236758134308); // 2/pi
+    const int k = (int)kd;
+    double r = fma(-kd, 1.5707963267948966, x);
+    r = fma(-kd, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s = fma(r * z, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+    // quadrant
+    const double ss = (k & 1) ? c : s;
+    const double cc = (k & 1) ? s : c;
+    *sn = (k & 2) ? -ss : ss;
+    *cs = ((k + 1) & 2) ? -cc : cc;
+}
+
 // H = hv * inv_e + lr   (per event), then + rho * vm per layer
 __device__ __forceinline__ Herm3 herm_axpy(double a, const Herm3 &x, const Herm3 &y) {
     Herm3 r;
@@ -80,7 +108,7 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
     const double b = (2.0 / 3.0) * sqrt(p);
     const double base = c2 * (-1.0 / 3.0);
     double st, ct;
-    sincos(theta, &st, &ct); // theta in [0, pi/3]
+    sincos_small(theta, &st, &ct); // theta in [0, pi/3]
     const double kh = 0.5, ks = 0.86602540378443864676; // cos, sin of pi/3
     // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
     const double l0 = fma(b, -kh * ct - ks * st, base);
@@ -94,8 +122,8 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
     const double id1 = -g02 * inv_g; // 1/((l1-l0)(l1-l2))
     const double id2 = g01 * inv_g;  // 1/((l2-l0)(l2-l1))
     double s0, k0, s1, k1;
-    sincos(-g02 * t, &s0, &k0); // exp(-i (l0-l2) t)
-    sincos(-g12 * t, &s1, &k1); // exp(-i (l1-l2) t)
+    sincos_small(-g02 * t, &s0, &k0); // exp(-i (l0-l2) t)
+    sincos_small(-g12 * t, &s1, &k1); // exp(-i (l1-l2) t)
     const Cplx w0{k0 * id0, s0 * id0};
     const Cplx w1{k1 * id1, s1 * id1};
     const double w2 = id2;
@@ -219,84 +247,88 @@ struct Propagator {
 };
 
 // Per-event propagation through the Earth.  h0 = hv/E + lr (per event), vm scales with rho.
-// Returns false for a direction the reference cannot process either (never for idx == 2).
-//   out_full != nullptr (NR=NC=3): out_full[i*3+j] = P(i -> j)
-//   NR=1: pe = P(e -> flav), pmu = P(mu -> flav)
+// The path is walked as a sequence of steps (shell, segment length, action) with ONE
+// transition_matrix call site, so that the kernel stays small (instruction cache) and a warp of
+// events with the same number of crossed shells executes without divergence.
+//
+//   two-root branch (layers.py:105-159, K crossed shells, first inner shell index 2):
+//     shell 0 (atmosphere)       l_0 - l_1            R  = cols(T)
+//     shell 1, far side          l_1 - l_2            R <- T R
+//     shell 1, near side         s_2 - 0              L  = rows(T)
+//     shell j = 2 .. K-2         l_j - l_{j+1}        R <- T R ; L <- L T   (in/out twin, :236-249)
+//     shell K-1 (innermost)      l_{K-1} - s_{K-1}    R <- T R
+//   no-tangent branch (layers.py:94-103): shells 0 .. idx-1 once each, last one initialises L.
+//   Segments of length <= 0 are skipped like in the reference (:233,285).
 template <int NR, int NC>
 __device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm,
                                                 const EarthTable &E, double cz, int flav,
                                                 Propagator<NR, NC> &P) {
-    const double T_SCALE = 2.0 * 2.534; // (1/2)(1/hbar c) in GeV/(eV^2 km), :524, times 2 (M = 2E lambda)
+    const double T_SCALE = 2.0 * 2.534; // (1/2)(1/hbar c) in GeV/(eV^2 km) (:524), times 2 (M = 2 E lambda)
+    enum { ACT_R = 1, ACT_L = 2 };
     const double cz2 = __dmul_rn(cz, cz);
     const double base = __dmul_rn(-E.r_det, cz);
     const int idx = E.idx_first_inner;
-    Mat3 T;
+    const bool tangent = cz < E.limit[idx];
+    bool have_r = false, have_l = false;
 
-    // shells outside the detector (j < idx): always crossed once, far side
-    double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0]));
-    if (!(cz < E.limit[idx])) {
-        // ---- no tangent (layers.py:94-103): segments l_j - l_{j+1}, last one l_{idx-1} - 0.
-        // Segments of length <= 0 are skipped like in the reference (:233,285).
-        bool have_r = false, have_l = false;
-        for (int j = 0; j < idx; ++j) {
+    double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0])); // large root of current shell
+    double sq_cur = 0.0;                                             // sqrt term of current shell
+    int j = 0;        // current shell
+    int phase = 0;    // 0: walking inwards, 1: near-side piece of the detector shell pending
+    for (;;) {
+        double seg;
+        int act;
+        bool last = false;
+        const int shell = j;
+        if (!tangent) {
             const double l_next = (j + 1 < idx) ? __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1])) : 0.0;
-            const double seg = __dsub_rn(l_cur, l_next);
+            seg = __dsub_rn(l_cur, l_next);
             l_cur = l_next;
-            if (seg > 0.0) {
-                transition_matrix(herm_axpy(E.rho[j], vm, h0), T_SCALE * seg, T);
-                if (j + 1 == idx) { P.init_left(T, flav); have_l = true; }
-                else if (!have_r) { P.init_right(T); have_r = true; }
-                else times_right<NC>(T, P.R);
+            act = (j + 1 == idx) ? ACT_L : ACT_R;
+            last = (j + 1 == idx);
+            ++j;
+        } else if (phase == 1) {
+            // near side of the detector shell: small root of shell idx minus 0
+            seg = __dsub_rn(base, sq_cur);
+            act = ACT_L;
+            phase = 0;
+            // `shell` is idx-1 here (j was already advanced to idx)
+        } else {
+            const bool innermost = !(j + 1 < E.n_radii && E.limit[j + 1] > cz);
+            if (innermost) {
+                seg = __dsub_rn(l_cur, __dsub_rn(base, sq_cur)); // l_j - s_j
+                act = ACT_R;
+                last = true;
+            } else {
+                const double sq_next = shell_root(E.rd2, cz2, E.rj2[j + 1]);
+                const double l_next = __dadd_rn(base, sq_next);
+                seg = __dsub_rn(l_cur, l_next);
+                l_cur = l_next;
+                sq_cur = sq_next;
+                act = (j >= idx) ? (ACT_R | ACT_L) : ACT_R;
+                if (j + 1 == idx) phase = 1; // after the far side of shell idx-1 do its near side
+                ++j;
             }
         }
-        if (!have_r || !have_l) {
-            Mat3 I = {{{1, 0}, {0, 0}, {0, 0}}, {{0, 0}, {1, 0}, {0, 0}}, {{0, 0}, {0, 0}, {1, 0}}};
-            if (!have_r) P.init_right(I);
-            if (!have_l) P.init_left(I, flav);
+        const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
+        if (seg > 0.0) {
+            Mat3 T;
+            transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0), T_SCALE * seg, T);
+            if (act & ACT_R) {
+                if (have_r) times_right<NC>(T, P.R);
+                else { P.init_right(T); have_r = true; }
+            }
+            if (act & ACT_L) {
+                if (have_l) left_times<NR>(P.L, T);
+                else { P.init_left(T, flav); have_l = true; }
+            }
         }
-        return;
+        if (last) break;
     }
-
-    // ---- two-root branch (layers.py:105-159), idx == 2 (checked on the host)
-    // far side, production -> detector: shells 0 and 1 once each
-    {
-        const double l1 = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[1]));
-        transition_matrix(herm_axpy(E.rho[0], vm, h0), T_SCALE * __dsub_rn(l_cur, l1), T);
-        P.init_right(T);
-        l_cur = l1;
-    }
-    const double sq2 = shell_root(E.rd2, cz2, E.rj2[2]);
-    {
-        const double l2 = __dadd_rn(base, sq2);
-        const Herm3 h = herm_axpy(E.rho[1], vm, h0);
-        transition_matrix(h, T_SCALE * __dsub_rn(l_cur, l2), T);
-        times_right<NC>(T, P.R);
-        // near side: detector shell again, length s_2 - 0 (small root of shell 2)
-        transition_matrix(h, T_SCALE * __dsub_rn(base, sq2), T);
-        P.init_left(T, flav);
-        l_cur = l2;
-    }
-    // inner shells j = 2 .. K-1; shell j is the innermost one iff shell j+1 is not crossed
-    double sq_cur = sq2;
-    for (int j = 2; j < E.n_radii; ++j) {
-        const bool innermost = !(j + 1 < E.n_radii && E.limit[j + 1] > cz);
-        const Herm3 h = herm_axpy(E.rho[j], vm, h0);
-        if (innermost) {
-            // l_j - s_j (:128-133): chord through the innermost shell
-            const double s_j = __dsub_rn(base, sq_cur);
-            transition_matrix(h, T_SCALE * __dsub_rn(l_cur, s_j), T);
-            times_right<NC>(T, P.R);
-            break;
-        }
-        const double sq_next = shell_root(E.rd2, cz2, E.rj2[j + 1]);
-        const double l_next = __dadd_rn(base, sq_next);
-        // inbound segment l_j - l_{j+1}; the outbound twin s_{j+1} - s_j differs by rounding only
-        // and hits the reference's layer cache (:236-249), i.e. reuses this matrix
-        transition_matrix(h, T_SCALE * __dsub_rn(l_cur, l_next), T);
-        times_right<NC>(T, P.R);
-        left_times<NR>(P.L, T);
-        l_cur = l_next;
-        sq_cur = sq_next;
+    if (!have_r || !have_l) {
+        Mat3 I = {{{1, 0}, {0, 0}, {0, 0}}, {{0, 0}, {1, 0}, {0, 0}}, {{0, 0}, {0, 0}, {1, 0}}};
+        if (!have_r) P.init_right(I);
+        if (!have_l) P.init_left(I, flav);
     }
 }
 

@@ -20,17 +20,17 @@ EVENT_KEYS = ("true_energy", "true_coszen", "nu_flux", "weights", "index")
 
 
 class _Block:
-    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage")
+    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage", "order")
 
     def __init__(self, name, nubar, flav, n):
         self.name, self.nubar, self.flav, self.n = name, int(nubar), int(flav), int(n)
-        self.dev, self.host, self.stage = {}, {}, None
+        self.dev, self.host, self.stage, self.order = {}, {}, None, None
 
 
 class ReweightEngine:
     """Device-resident event containers + fused template evaluation."""
 
-    def __init__(self, earth, n_bins, dtype=np.float64, device=None):
+    def __init__(self, earth, n_bins, dtype=np.float64, device=None, sort_events=True):
         if not torch.cuda.is_available():
             raise RuntimeError("pisa_b200.engine needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -38,6 +38,7 @@ class ReweightEngine:
         self.n_bins = int(n_bins)
         self.tdtype = _NP2T[np.dtype(dtype)]
         self.blocks = []
+        self.sort_events = bool(sort_events)
         self._out = None
         self._copy_stream = None
         self._host_out = None
@@ -59,6 +60,11 @@ class ReweightEngine:
                 blk.dev[k] = t.contiguous()
             else:
                 blk.host[k] = t.contiguous().pin_memory() if not t.is_pinned() else t
+        if self.sort_events:
+            # setup-time, depends on true_coszen only (like calcLayers in prob3.setup_function):
+            # thread order that groups events by the number of Earth shells they cross
+            cz = blk.dev["true_coszen"] if "true_coszen" in blk.dev else blk.host["true_coszen"].to(self.device)
+            blk.order = ops.layer_order(self.earth, cz)
         self.blocks.append(blk)
         self._out = None
         return blk
@@ -76,7 +82,7 @@ class ReweightEngine:
     def _launch(self, consts, blk, arrays, out_row, weights_out=None):
         ops.reweight_hist(consts, self.earth, blk.nubar, blk.flav, arrays["true_energy"], arrays["true_coszen"],
                           arrays["nu_flux"], arrays["weights"], arrays["index"], self.n_bins,
-                          weights_out=weights_out, hist=out_row[0], hist_w2=out_row[1])
+                          weights_out=weights_out, hist=out_row[0], hist_w2=out_row[1], order=blk.order)
 
     def evaluate(self, consts, allreduce=True, events=None):
         """Resident mode: all event arrays already in HBM.  Returns [n_containers, 2, n_bins].

@@ -37,6 +37,13 @@ def _ptr(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
 
+def _check_order(order, n):
+    if order is not None:
+        _chk(order, "order", torch.int32)
+        if order.numel() != n:
+            raise ValueError("order must be a permutation of all %d events" % n)
+
+
 def _species(val, n, name):
     """(+1|-1 or flavour) given as python int (aux scalar of a container) or int32 tensor [n]."""
     if isinstance(val, torch.Tensor):
@@ -93,8 +100,23 @@ def propagate_layers(consts, nubar, energy, densities, distances, out=None):
     return out
 
 
+def layer_order(earth, coszen):
+    """Setup-time helper: permutation (int32) listing the events grouped by the number of Earth
+    shells they cross, deepest first, stable within a group.  Passing it as ``order`` to
+    propagate_earth / reweight_hist makes every warp walk the same number of layers; it depends on
+    ``coszen`` only (the reference computes its layer arrays once in setup_function as well)."""
+    _chk(coszen, "coszen")
+    n = coszen.numel()
+    count = torch.empty(n, dtype=torch.int32, device=coszen.device)
+    f = _lib.fn("pisab_layer_count", coszen.dtype)
+    _lib.check(f(ctypes.byref(earth), _ptr(coszen), n, _ptr(count), _stream()))
+    # torch.sort is plumbing here (stable => the permutation, hence every sum, is reproducible)
+    order = torch.sort(count, descending=True, stable=True).indices
+    return order.to(torch.int32).contiguous()
+
+
 def propagate_earth(consts, earth, nubar, energy, coszen, flav=None, probability=None, prob_e=None,
-                    prob_mu=None, want_probability=True):
+                    prob_mu=None, want_probability=True, order=None):
     """Layers evaluated in-kernel from ``coszen`` (prob3.py:406-409 + :581-605 fused).
 
     Returns (probability | None, prob_e | None, prob_mu | None).  ``flav`` (0/1/2, python int or
@@ -117,9 +139,10 @@ def propagate_earth(consts, earth, nubar, energy, coszen, flav=None, probability
             prob_mu = torch.empty(n, dtype=dt, device=energy.device)
     for t, nm in ((probability, "probability"), (prob_e, "prob_e"), (prob_mu, "prob_mu")):
         _chk(t, nm, dt, allow_none=True)
+    _check_order(order, n)
     f = _lib.fn("pisab_prob3_propagate_earth", dt)
     _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), nb, _ptr(d_nb), fl, _ptr(d_fl), _ptr(energy),
-                 _ptr(coszen), n, _ptr(probability), _ptr(prob_e), _ptr(prob_mu), _stream()))
+                 _ptr(coszen), _ptr(order), n, _ptr(probability), _ptr(prob_e), _ptr(prob_mu), _stream()))
     return probability, prob_e, prob_mu
 
 
@@ -247,7 +270,7 @@ def lookup(index, flat_hist, out=None):
 
 
 def reweight_hist(consts, earth, nubar, flav, energy, coszen, nu_flux, weights_in, index, n_bins,
-                  weights_out=None, prob_e=None, prob_mu=None, hist=None, hist_w2=None):
+                  weights_out=None, prob_e=None, prob_mu=None, hist=None, hist_w2=None, order=None):
     """Fused template evaluation: prob3 + ``weights *= flux.prob`` + weighted histogram (w, w^2)."""
     _chk(energy, "energy")
     dt = energy.dtype
@@ -265,10 +288,11 @@ def reweight_hist(consts, earth, nubar, flav, energy, coszen, nu_flux, weights_i
         hist = torch.empty(n_bins, dtype=torch.float64, device=energy.device)
     if hist_w2 is None:
         hist_w2 = torch.empty(n_bins, dtype=torch.float64, device=energy.device)
+    _check_order(order, n)
     ws = _workspace(energy.device, n, n_bins)
     f = _lib.fn("pisab_reweight_hist", dt)
     _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), nb, _ptr(d_nb), fl, _ptr(d_fl), _ptr(energy),
-                 _ptr(coszen), _ptr(nu_flux), _ptr(weights_in), _ptr(index), n, int(n_bins), _ptr(hist),
+                 _ptr(coszen), _ptr(nu_flux), _ptr(weights_in), _ptr(index), _ptr(order), n, int(n_bins), _ptr(hist),
                  _ptr(hist_w2), _ptr(weights_out), _ptr(prob_e), _ptr(prob_mu), _ptr(ws), ws.numel(), _stream()))
     return hist, hist_w2
 

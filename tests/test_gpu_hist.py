@@ -164,6 +164,17 @@ def test_fused_reweight_hist_vs_oracle_chain(dtype):
         tol = 1e-10 if dtype == np.float64 else 2e-5
         assert np.allclose(h.cpu().numpy(), ref, rtol=tol), np.abs(h.cpu().numpy() / ref - 1).max()
         assert np.allclose(h2.cpu().numpy(), ref2, rtol=2 * tol)
+        # grouped thread order: same histogram within rounding, per-event weights bit-identical,
+        # and bit-reproducible run to run
+        order = ops.layer_order(earth, T(coszen))
+        wout_o = torch.empty(n, dtype=tdt, device=dev)
+        ho, ho2 = ops.reweight_hist(consts, earth, nubar, flav, T(energy), T(coszen), T(flux), T(w0),
+                                    torch.tensor(idx, device=dev), 128, weights_out=wout_o, order=order)
+        assert torch.equal(wout_o, wout)
+        assert np.allclose(ho.cpu().numpy(), ref, rtol=tol) and np.allclose(ho2.cpu().numpy(), ref2, rtol=2 * tol)
+        ho_b, _ = ops.reweight_hist(consts, earth, nubar, flav, T(energy), T(coszen), T(flux), T(w0),
+                                    torch.tensor(idx, device=dev), 128, order=order)
+        assert torch.equal(ho, ho_b)
         assert np.allclose(wout.cpu().numpy(), w, rtol=tol, atol=1e-12 if dtype == np.float64 else 1e-5)
         # unfused path gives the same histogram (binned weights within 1e-10)
         _, pe_t, pmu_t = ops.propagate_earth(consts, earth, nubar, T(energy), T(coszen), flav=flav,

@@ -213,3 +213,30 @@ def test_unsupported_geometry_and_bad_args():
     L, earth = _earth()
     nl, den, dis = ops.layers_calc(earth, torch.zeros(0, dtype=torch.float64, device=dev))
     assert den.shape == (0, 28)
+
+
+def test_event_order_changes_speed_not_results():
+    """`order` (events grouped by crossed shells) must give bit-identical per-event outputs."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    key = "nufit20_nh_dcp306_stdnsi/nu"
+    consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"])
+    L, earth = _earth()
+    rng = np.random.default_rng(11)
+    n = 100_003
+    e = torch.tensor(10 ** rng.uniform(0, 3, n), device=dev)
+    cz = torch.tensor(rng.uniform(-1, 1, n), device=dev)
+    order = ops.layer_order(earth, cz)
+    assert order.dtype == torch.int32 and np.array_equal(np.sort(order.cpu().numpy()), np.arange(n))
+    # grouped deepest-first, stable
+    k = (torch.tensor(L.coszen_limit, device=dev)[None, :] > cz[:, None]).sum(dim=1)
+    ks = k[order.long()]
+    assert bool((ks[1:] <= ks[:-1]).all())
+    p0, pe0, pm0 = ops.propagate_earth(consts, earth, -1, e, cz, flav=1)
+    p1, pe1, pm1 = ops.propagate_earth(consts, earth, -1, e, cz, flav=1, order=order)
+    assert torch.equal(p0, p1) and torch.equal(pe0, pe1) and torch.equal(pm0, pm1)
+    _, pe2, pm2 = ops.propagate_earth(consts, earth, -1, e, cz, flav=1, want_probability=False, order=order)
+    _, pe3, pm3 = ops.propagate_earth(consts, earth, -1, e, cz, flav=1, want_probability=False)
+    assert torch.equal(pe2, pe3) and torch.equal(pm2, pm3)
+    _assert_prob(pe2.cpu().numpy(), p0[:, 0, 1].cpu().numpy(), "row mode vs full mode")
