@@ -1,0 +1,209 @@
+"""``osc.prob3`` service: three-flavour oscillation probabilities through the Earth on a B200.
+
+Drop-in for pisa/stages/osc/prob3.py (reference :37-641): same constructor kwargs
+(``include_nlo, nsi_type, reparam_mix_matrix, neutrino_decay, tomography_type, lri_type``), same
+``expected_params`` (:178-191 plus the 9 ``eps_*`` for ``nsi_type='standard'`` :244-254), same
+container keys read (``true_energy, true_coszen, nubar, flav, nu_flux, weights``) and written
+(``probability, prob_e, prob_mu``; ``weights`` multiplied in ``apply_function`` :621-622), same
+linking of the flavour containers in grid mode (:398-404,415-419,456-459).
+
+What runs where: ``compute_function`` builds the PMNS / dm / matter-potential matrices on the host
+exactly like :485-567 and then makes ONE call per container into the CUDA library
+(``pisab_prob3_propagate_earth``), which evaluates the Earth layers (reference: ``Layers.calcLayers``
+at setup, :406-409) and the propagation (``propagate_array`` :439-450) in one kernel and writes
+``probability``, ``prob_e`` and ``prob_mu`` (``fill_probs`` :593-605).  The ``densities`` /
+``distances`` arrays of the reference are therefore not materialised by default
+(``store_layers=True`` restores them for inspection).
+
+Out of scope (raise at construction): neutrino decay (numpy eigvals branch), vacuum-like NSI,
+Earth tomography, long-range interactions parameter classes.
+"""
+import numpy as np
+
+from pisa_b200 import ops
+from pisa_b200.core.stage import Stage
+from pisa_b200.stages.osc.layers import Layers
+from pisa_b200.stages.osc.nsi_params import StdNSIParams
+from pisa_b200.stages.osc.osc_params import OscParams
+from pisa_b200.utils.resources import find_resource
+
+__all__ = ["prob3", "init_test", "NSI_TYPES"]
+
+NSI_TYPES = ["standard", "vacuum-like"]
+
+_NU = ["nue_cc", "numu_cc", "nutau_cc", "nue_nc", "numu_nc", "nutau_nc"]
+_NUBAR = ["nuebar_cc", "numubar_cc", "nutaubar_cc", "nuebar_nc", "numubar_nc", "nutaubar_nc"]
+
+
+class prob3(Stage):  # pylint: disable=invalid-name
+    def __init__(self, include_nlo=False, nsi_type=None, reparam_mix_matrix=False, neutrino_decay=False,
+                 tomography_type=None, lri_type=None, store_layers=False, **std_kwargs):
+        expected_params = ("detector_depth", "earth_model", "prop_height", "YeI", "YeO", "YeM", "theta12",
+                           "theta13", "theta23", "deltam21", "deltam31", "deltacp")
+        expected_container_keys = ("true_energy", "true_coszen", "nubar", "flav", "nu_flux", "weights")
+        self.include_nlo = include_nlo
+        if nsi_type is not None:
+            nsi_type = nsi_type.strip().lower()
+            if nsi_type not in NSI_TYPES:
+                raise ValueError('Chosen NSI type "%s" not available! Choose one of %s.' % (nsi_type, NSI_TYPES))
+            if nsi_type == "vacuum-like":
+                raise NotImplementedError("vacuum-like NSI is outside the scope of pisa_b200")
+        self.nsi_type = nsi_type
+        self.reparam_mix_matrix = reparam_mix_matrix
+        if neutrino_decay:
+            raise NotImplementedError("neutrino decay (numpy.linalg.eigvals branch) is outside the scope of pisa_b200")
+        if tomography_type is not None:
+            raise NotImplementedError("Earth tomography is outside the scope of pisa_b200")
+        if lri_type is not None:
+            raise NotImplementedError("long-range interactions are outside the scope of pisa_b200")
+        self.neutrino_decay, self.decay_flag = False, -1
+        self.tomography_type, self.lri_type = None, None
+        nsi_params = ()
+        if nsi_type == "standard":
+            nsi_params = ("eps_ee", "eps_emu_magn", "eps_emu_phase", "eps_etau_magn", "eps_etau_phase",
+                          "eps_mumu", "eps_mutau_magn", "eps_mutau_phase", "eps_tautau")
+        super().__init__(expected_params=expected_params + nsi_params,
+                         expected_container_keys=expected_container_keys, **std_kwargs)
+        self.store_layers = store_layers
+        self.layers = None
+        self.osc_params = None
+        self.nsi_params = None
+        self.gen_mat_pot_matrix_complex = None
+        self.decay_matrix = np.zeros((3, 3), dtype=np.complex128)
+        self.lri_pot = np.zeros((3, 3), dtype=np.float64)
+        self.YeI = self.YeO = self.YeM = None
+        self._earth = None
+        self._orders = {}
+
+    # ------------------------------------------------------------------------------------
+    def _link(self):
+        if self.is_map:
+            self.data.link_containers("nu", _NU)
+            self.data.link_containers("nubar", _NUBAR)
+
+    def _store_layers(self):
+        if not self.store_layers:
+            return
+        for container in self.data:
+            self.layers.calcLayers(container["true_coszen"])
+            container["densities"] = self.layers.density
+            container["distances"] = self.layers.distance
+
+    def setup_function(self):
+        self.osc_params = OscParams()
+        if self.nsi_type == "standard":
+            self.nsi_params = StdNSIParams()
+        earth_model = find_resource(self.params.earth_model.value)
+        self.YeI = self.params.YeI.value.m_as("dimensionless")
+        self.YeO = self.params.YeO.value.m_as("dimensionless")
+        self.YeM = self.params.YeM.value.m_as("dimensionless")
+        prop_height = self.params.prop_height.value.m_as("km")
+        detector_depth = self.params.detector_depth.value.m_as("km")
+        self.layers = Layers(earth_model, detector_depth, prop_height)
+        self.layers.setElecFrac(self.YeI, self.YeO, self.YeM)
+        self._earth = self.layers.earth_struct()
+
+        # layers do not care about flavour: link everything while touching true_coszen (:398-412)
+        if self.is_map:
+            self.data.link_containers("nu", _NU + _NUBAR)
+        self._store_layers()
+        # thread order grouping events by crossed shells: depends on true_coszen only
+        self._orders = {}
+        for container in self.data:
+            order = ops.layer_order(self._earth, container["true_coszen"])
+            for c in (container.containers if hasattr(container, "containers") else [container]):
+                self._orders[c.name] = order
+        self.data.unlink_containers()
+
+        # output arrays (:414-427)
+        self._link()
+        for container in self.data:
+            n = container.size
+            tc = container["true_coszen"]
+            container["probability"] = tc.new_empty((n, 3, 3))
+        self.data.unlink_containers()
+        for container in self.data:
+            tc = container["true_coszen"]
+            container["prob_e"] = tc.new_empty(container.size)
+            container["prob_mu"] = tc.new_empty(container.size)
+
+    def _update_matrices(self):
+        p = self.params
+        for angle in (p.theta12, p.theta13, p.theta23, p.deltacp):
+            if angle.value.units == "dimensionless":
+                raise ValueError("%s is dimensionless, but needs units rad or deg!" % angle.name)
+        o = self.osc_params
+        o.theta12 = p.theta12.value.m_as("rad")
+        o.theta13 = p.theta13.value.m_as("rad")
+        o.theta23 = p.theta23.value.m_as("rad")
+        o.dm21 = p.deltam21.value.m_as("eV**2")
+        o.dm31 = p.deltam31.value.m_as("eV**2")
+        o.deltacp = p.deltacp.value.m_as("rad")
+        std = np.zeros((3, 3), dtype=np.complex128)
+        std[0, 0] += 1.020 if self.include_nlo else 1.0   # :540-546
+        if self.nsi_type == "standard":
+            n = self.nsi_params
+            n.eps_ee = p.eps_ee.value.m_as("dimensionless")
+            n.eps_emu = (p.eps_emu_magn.value.m_as("dimensionless"), p.eps_emu_phase.value.m_as("rad"))
+            n.eps_etau = (p.eps_etau_magn.value.m_as("dimensionless"), p.eps_etau_phase.value.m_as("rad"))
+            n.eps_mumu = p.eps_mumu.value.m_as("dimensionless")
+            n.eps_mutau = (p.eps_mutau_magn.value.m_as("dimensionless"), p.eps_mutau_phase.value.m_as("rad"))
+            n.eps_tautau = p.eps_tautau.value.m_as("dimensionless")
+            self.gen_mat_pot_matrix_complex = std + n.eps_matrix
+        else:
+            self.gen_mat_pot_matrix_complex = std
+        mix = o.mix_matrix_reparam_complex if self.reparam_mix_matrix else o.mix_matrix_complex
+        return ops.OscConsts.from_matrices(o.dm_matrix, mix, self.gen_mat_pot_matrix_complex, self.decay_flag,
+                                           self.decay_matrix, self.lri_pot)
+
+    def compute_function(self):
+        YeI = self.params.YeI.value.m_as("dimensionless")
+        YeO = self.params.YeO.value.m_as("dimensionless")
+        YeM = self.params.YeM.value.m_as("dimensionless")
+        if YeI != self.YeI or YeO != self.YeO or YeM != self.YeM:   # :466-474
+            self.YeI, self.YeO, self.YeM = YeI, YeO, YeM
+            self.layers.setElecFrac(YeI, YeO, YeM)
+            self._earth = self.layers.earth_struct()
+            self._store_layers()
+        consts = self._update_matrices()
+
+        self._link()
+        for container in self.data:
+            first = container.containers[0] if hasattr(container, "containers") else container
+            ops.propagate_earth(consts, self._earth, int(container["nubar"]), container["true_energy"],
+                                container["true_coszen"], probability=container["probability"],
+                                order=self._orders.get(first.name))
+            container.mark_changed("probability")
+        self.data.unlink_containers()   # the following is flavour specific (:590-608)
+        for container in self.data:
+            flav = int(container["flav"])
+            ops.fill_probs(container["probability"], 0, flav, out=container["prob_e"])
+            ops.fill_probs(container["probability"], 1, flav, out=container["prob_mu"])
+            container.mark_changed("prob_e")
+            container.mark_changed("prob_mu")
+
+    def apply_function(self):
+        for container in self.data:
+            w = container["weights"]
+            ops.apply_osc_weights(container["nu_flux"], container["prob_e"], container["prob_mu"], w)
+            container.mark_changed("weights")
+
+
+def init_test(**param_kwargs):
+    """Initialisation example (prob3.py:625-641)."""
+    from pisa_b200.core.param import Param, ParamSet
+    from pisa_b200.utils.units import ureg
+    return prob3(include_nlo=True, params=ParamSet([
+        Param(name="detector_depth", value=10 * ureg.km, **param_kwargs),
+        Param(name="prop_height", value=18 * ureg.km, **param_kwargs),
+        Param(name="earth_model", value="osc/PREM_4layer.dat", **param_kwargs),
+        Param(name="YeI", value=0.5, **param_kwargs),
+        Param(name="YeO", value=0.5, **param_kwargs),
+        Param(name="YeM", value=0.5, **param_kwargs),
+        Param(name="theta12", value=33 * ureg.degree, **param_kwargs),
+        Param(name="theta13", value=8 * ureg.degree, **param_kwargs),
+        Param(name="theta23", value=50 * ureg.degree, **param_kwargs),
+        Param(name="deltam21", value=8e-5 * ureg.eV ** 2, **param_kwargs),
+        Param(name="deltam31", value=3e-3 * ureg.eV ** 2, **param_kwargs),
+        Param(name="deltacp", value=180 * ureg.degree, **param_kwargs),
+    ]))

@@ -1,0 +1,204 @@
+"""GPU tests of the drop-in boundary: Pipeline(cfg).run() / get_outputs() / get_mapset against the
+CPU oracle, stage caching, representation translation, and the reweighting engine."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from conftest import ROOT  # noqa: E402
+
+PREM12 = os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _oracle_layers():
+    L = oracle.OracleLayers(np.loadtxt(PREM12), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    return L
+
+
+def _matrices(stage):
+    o = stage.osc_params
+    return o.dm_matrix, o.mix_matrix_complex, stage.gen_mat_pot_matrix_complex
+
+
+def test_oscillogram_pipeline_matches_oracle_on_the_grid():
+    """BASELINE config C1: prob3 on the 200 x 200 (E x coszen) grid, nu + nubar = 80 000 evaluations
+    (README minimal example: Pipeline(cfg).run(); data.get_mapset('prob_mu'))."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    pipe = Pipeline("settings/pipeline/b200_oscillogram.cfg")
+    assert [s.service_name for s in pipe.stages] == ["toy_event_generator", "nominal", "prob3"]
+    pipe.run()
+    grid = pipe.data["output_binning"]
+    pipe.data.representation = grid
+    maps_mu = pipe.data.get_mapset("prob_mu")
+    maps_e = pipe.data.get_mapset("prob_e")
+    assert len(maps_mu) == 12 and maps_mu["numu_cc"].hist.shape == (200, 200)
+
+    # the grid points the reference evaluates: weighted bin centres, energy-major (container.py:769-773)
+    e = np.sqrt(np.logspace(0, 3, 201)[:-1] * np.logspace(0, 3, 201)[1:])
+    cz = 0.5 * (np.linspace(-1, 1, 201)[:-1] + np.linspace(-1, 1, 201)[1:])
+    E, CZ = (a.ravel() for a in np.meshgrid(e, cz, indexing="ij"))
+    L = _oracle_layers()
+    _, den, dis = L.calcLayers(CZ)
+    dm, mix, mat_pot = _matrices(pipe["prob3"])
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    for nubar, names in ((1, ["nue_cc", "numu_nc", "nutau_cc"]), (-1, ["nuebar_nc", "numubar_cc", "nutaubar_cc"])):
+        ref = oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, E, den, dis, n_threads=os.cpu_count())
+        for name in names:
+            flav = 2 if "tau" in name else (1 if "mu" in name else 0)
+            for maps, init in ((maps_e, 0), (maps_mu, 1)):
+                out = maps[name].hist.ravel()
+                assert np.allclose(out, ref[:, init, flav], rtol=1e-10, atol=1e-12), (name, init)
+    # output key `weights` = initial_weights * (0 * prob_e + 1 * prob_mu)
+    out = pipe.get_outputs()
+    assert np.allclose(out["numubar_cc"].hist, maps_mu["numubar_cc"].hist, rtol=1e-14, atol=0)
+    # unitarity of the full matrix on the grid
+    prob = pipe.data["nue_cc"]["probability"]
+    assert float((prob.sum(dim=1) - 1).abs().max()) < 5e-12
+
+
+def test_stage_cache_and_param_update():
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.utils.units import ureg
+    pipe = Pipeline("settings/pipeline/b200_oscillogram.cfg", profile=True)
+    pipe.run()
+    osc = pipe["prob3"]
+    n_calc = len(osc.calc_times)
+    first = pipe.data["numu_cc"]["prob_mu"].clone()
+    pipe.run()   # nothing changed -> compute() is skipped (stage.py:538-542)
+    assert len(osc.calc_times) == n_calc
+    pipe.params.theta23 = 50 * ureg.deg
+    pipe.run()
+    assert len(osc.calc_times) == n_calc + 1
+    assert not torch.equal(first, pipe.data["numu_cc"]["prob_mu"])
+    pipe.params.theta23 = 42 * ureg.deg
+    pipe.run()
+    assert torch.equal(first, pipe.data["numu_cc"]["prob_mu"])   # deterministic kernel
+    # mass ordering selection
+    pipe.select_params(["ih"])
+    assert pipe.params.deltam31.value.m < 0
+    pipe.run()
+    assert not torch.equal(first, pipe.data["numu_cc"]["prob_mu"])
+
+
+def test_events_pipeline_matches_oracle_chain():
+    """IceCube-3y shaped pipeline on synthetic MC: prob3 (events) -> aeff -> hist (sumw2)."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.utils import synthetic as syn
+    pipe = Pipeline("settings/pipeline/b200_events.cfg")
+    out = pipe.get_outputs()
+    assert out.names[:3] == ["nue_cc", "numu_cc", "nutau_cc"] and out["nue_cc"].hist.shape == (8, 8, 2)
+    dm, mix, mat_pot = _matrices(pipe["prob3"])
+    L = _oracle_layers()
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    livetime = 2.5 * 365 * 86400.0
+    total_bad_idx = 0
+    for c in pipe.data.containers:
+        c.representation = "events"
+        ev = {k: c[k].cpu().numpy() for k in ("true_energy", "true_coszen", "reco_energy", "reco_coszen", "pid",
+                                               "nu_flux", "weighted_aeff", "initial_weights")}
+        nubar, flav = int(c["nubar"]), int(c["flav"])
+        _, den, dis = L.calcLayers(ev["true_coszen"])
+        prob = oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, ev["true_energy"], den, dis,
+                                      n_threads=os.cpu_count())
+        w = ev["initial_weights"] * (ev["nu_flux"][:, 0] * prob[:, 0, flav] + ev["nu_flux"][:, 1] * prob[:, 1, flav])
+        w = w * (ev["weighted_aeff"] * (1.0 * livetime))
+        ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
+        i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
+        idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
+        total_bad_idx += int((c.bin_index(pipe.output_binning).cpu().numpy() != idx).sum())
+        ref = oracle.accumulate(idx, w, 128).reshape(8, 8, 2)
+        ref_err = np.sqrt(oracle.accumulate(idx, w * w, 128)).reshape(8, 8, 2)
+        assert np.allclose(out[c.name].hist, ref, rtol=1e-10, atol=0), c.name
+        assert np.allclose(out[c.name].std_devs, ref_err, rtol=1e-10, atol=0), c.name
+        # events representation of the weights stays valid after histogramming (hist.py:213)
+        c.representation = "events"
+        assert np.allclose(c["weights"].cpu().numpy(), w, rtol=1e-10, atol=0)
+    assert total_bad_idx == 0   # bin indices bit-exact
+    # a second template with a different theta23 changes the maps; going back restores them exactly
+    from pisa_b200.utils.units import ureg
+    pipe.params.theta23 = 49 * ureg.deg
+    out2 = pipe.get_outputs()
+    assert not np.allclose(out2["numu_cc"].hist, out["numu_cc"].hist, rtol=1e-6)
+    pipe.params.theta23 = 42.3 * ureg.deg
+    out3 = pipe.get_outputs()
+    assert np.array_equal(out3["numu_cc"].hist, out["numu_cc"].hist)
+
+
+def test_container_translations_roundtrip():
+    """events -> binned (average / sum) -> events, like container.py::test_container (:1043-1131)."""
+    _need_gpu()
+    from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+    from pisa_b200.core.container import Container
+    rng = np.random.default_rng(0)
+    n = 50_000
+    x, y = rng.uniform(0, 100, n), rng.uniform(1, 100, n)
+    c = Container("test")
+    c["x"], c["y"] = x, y
+    c["w"] = np.ones(n)
+    c["v"] = 2.0 * x
+    c.translation_modes["w"] = "sum"
+    b = MultiDimBinning([OneDimBinning("x", num_bins=10, is_lin=True, domain=[0, 100]),
+                         OneDimBinning("y", num_bins=10, is_log=True, domain=[1, 100])])
+    c.representation = b
+    counts = c["w"].cpu().numpy().reshape(10, 10)
+    ref_counts, _, _ = np.histogram2d(x, y, bins=[np.linspace(0, 100, 11), np.logspace(0, 2, 11)])
+    # log axis through the device log vs numpy edges: identical away from 1-ulp edge cases
+    assert np.abs(counts - ref_counts).sum() <= 2
+    avg = c["v"].cpu().numpy().reshape(10, 10)
+    assert np.allclose(avg.mean(axis=1), 2 * (np.arange(10) * 10 + 5), rtol=0.06)  # statistical
+    # binned -> events lookup of the averaged quantity
+    c["v"] = c["v"]  # mark the binned copy as the valid one
+    c.representation = "events"
+    back = c["v"].cpu().numpy()
+    ix = np.clip((x / 10).astype(int), 0, 9)
+    iy = np.clip((np.log(y) / np.log(100) * 10).astype(int), 0, 9)
+    assert np.allclose(back, avg[ix, iy], rtol=1e-12, atol=0)
+    c.representation = "log_events"
+    assert np.allclose(c["y"].cpu().numpy(), np.log(y), rtol=1e-15)
+    with pytest.raises(KeyError):
+        c["nonexistent"]
+
+
+def test_engine_host_mode_equals_resident_mode():
+    _need_gpu()
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine, shard_slice
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    dm, mix, mat_pot = syn.osc_matrices(nsi=syn.STD_NSI)
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    a = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    b = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    u = ReweightEngine(L.earth_struct(), 128, np.float64, dev, sort_events=False)
+    for i, (name, nubar, flav) in enumerate(syn.CONTAINERS[:5]):
+        ev = syn.make_events_numpy(30_000 + 7 * i, seed=i)
+        t = {k: torch.tensor(v, device=dev) for k, v in ev.items()}
+        idx = ops.hist_index(binning, [t["reco_energy"], t["reco_coszen"], t["pid"]])
+        a.add_container(name, nubar, flav, t["true_energy"], t["true_coszen"], t["nu_flux"], t["weights"], idx)
+        u.add_container(name, nubar, flav, t["true_energy"], t["true_coszen"], t["nu_flux"], t["weights"], idx)
+        b.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
+                        idx.cpu().numpy())
+    ra = a.evaluate(consts).cpu().numpy()
+    rb = b.evaluate_host(consts)
+    ru = u.evaluate(consts).cpu().numpy()
+    assert np.array_equal(ra, rb)                      # same thread order -> bit-identical sums
+    assert np.allclose(ra, ru, rtol=1e-12, atol=0)     # different thread order -> rounding only
+    assert b.last_h2d_bytes == sum(blk.n for blk in b.blocks) * 44 and b.last_d2h_bytes == 5 * 2 * 128 * 8
+    assert shard_slice(10, 0, 3) == (0, 4) and shard_slice(10, 2, 3) == (7, 10)

@@ -1,0 +1,160 @@
+"""CPU-only tests of the host-side boundary: units, params, binning, cfg parsing, Stage contract,
+and that the C-ABI library loads and exports every symbol the header declares."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+from pisa_b200.core.param import Param, ParamSelector, ParamSet
+from pisa_b200.utils.config_parser import parse_pipeline_config
+from pisa_b200.utils.units import Quantity, parse_quantity, ureg
+
+REF_RES = "/root/reference/pisa_examples/resources"
+
+
+def test_abi_library_exports_every_declared_symbol():
+    from pisa_b200 import _lib
+    lib = _lib.load()   # loading must work without a GPU
+    header = open(os.path.join(ROOT, "include", "pisa_b200.h")).read()
+    declared = sorted(set(re.findall(r"^(?:int|int64_t|double|const char \*)\s*(pisab_[a-z0-9_]+)\s*\(", header, re.M)))
+    assert len(declared) >= 29
+    exported = subprocess.check_output(["nm", "-D", "--defined-only", _lib.lib_path()]).decode()
+    for name in declared:
+        assert re.search(r"\bT %s\b" % name, exported), "symbol %s declared in the header but not exported" % name
+        assert hasattr(lib, name)
+    assert sorted(_lib.EXPORTED_SYMBOLS) == declared
+    assert b"sm_100a" in lib.pisab_version()
+    # SASS is sm_100a only (no multi-arch fat binary, no PTX fallback for other targets)
+    archs = set(re.findall(r"arch = (sm_\d+a?)", subprocess.check_output(["cuobjdump", "-lelf", _lib.lib_path()]).decode()
+                           + subprocess.run(["cuobjdump", "-sass", _lib.lib_path()], capture_output=True, text=True).stdout[:200000]))
+    assert archs <= {"sm_100a"} and archs
+
+
+def test_no_cpu_path():
+    import torch
+    from pisa_b200 import ops
+    with pytest.raises(TypeError):
+        ops.hist_accumulate(torch.zeros(4, dtype=torch.int32), torch.zeros(4, dtype=torch.float64), 8)
+    # the product never imports the oracle
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "pisa_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_units_and_quantity_parsing():
+    q, s = parse_quantity("8.5 +/- 0.205 units.deg")
+    assert q.units == "deg" and q.m == 8.5 and s == 0.205
+    assert np.isclose(q.m_as("rad"), np.deg2rad(8.5))
+    q, s = parse_quantity("2.457e-3 units.eV**2")
+    assert q.m_as("eV**2") == 2.457e-3 and np.isnan(s)
+    q, _ = parse_quantity("42. * units.degree")
+    assert q.m_as("deg") == 42.0
+    assert (2.5 * ureg.common_year).m_as("sec") == 2.5 * 365 * 86400
+    assert parse_quantity("1e4")[0].units == "dimensionless"
+    with pytest.raises(ValueError):
+        parse_quantity("osc/PREM_12layer.dat")
+    with pytest.raises(ValueError):
+        (1.0 * ureg.km).to("deg")
+    assert isinstance(np.array([0., 90.]) * ureg.degree, Quantity)
+
+
+def test_paramset_selector_and_hash():
+    a = Param("theta23", 42 * ureg.deg, is_fixed=False)
+    b = Param("deltam31", 2.457e-3 * ureg.eV ** 2)
+    bi = Param("deltam31", -2.374e-3 * ureg.eV ** 2)
+    sel = ParamSelector(regular_params=[a], selector_param_sets={"nh": [b], "ih": [bi]}, selections=["nh"])
+    ps = sel.params
+    assert ps.names == ("theta23", "deltam31") and ps.deltam31.value.m == 2.457e-3
+    h0 = ps.values_hash
+    ps.theta23.value = 45 * ureg.deg
+    assert ps.values_hash != h0 and ps.free.names == ("theta23",)
+    ps.theta23.value = 42 * ureg.deg
+    assert ps.values_hash == h0
+    sel.select_params(["ih"])
+    assert ps.deltam31.value.m == -2.374e-3     # same ParamSet object the stage holds
+    with pytest.raises(ValueError):
+        ps.theta23.value = 3 * ureg.km
+
+
+def test_binning_classification_is_ftype_dependent_rule():
+    """dragon_datarelease.reco_energy has 9-digit edges whose ratios differ by 5.5e-10,
+    so in FP64 (rtol 1e-12) it is IRREGULAR -> searchsorted on the real edges."""
+    e = OneDimBinning("reco_energy", is_log=True, bin_edges=[5.62341325, 7.49894209, 10.0, 13.33521432, 17.7827941,
+                                                             23.71373706, 31.6227766, 42.16965034, 56.23413252] * ureg.GeV)
+    assert e.is_irregular and e.is_log and e.num_bins == 8
+    t = OneDimBinning("true_energy", num_bins=200, is_log=True, domain=[1., 1000] * ureg.GeV)
+    c = OneDimBinning("true_coszen", num_bins=200, is_lin=True, domain=[-1, 1])
+    assert not t.is_irregular and not c.is_irregular
+    assert np.array_equal(t.bin_edges.m, np.logspace(0, 3, 201))
+    assert np.allclose(t.weighted_centers.m, np.sqrt(t.bin_edges.m[:-1] * t.bin_edges.m[1:]), rtol=0, atol=0)
+    m = MultiDimBinning([t, c], name="calc_grid")
+    assert m.shape == (200, 200) and m.size == 40000 and m.names == ["true_energy", "true_coszen"]
+    assert hash(m) == hash(MultiDimBinning([t, c])) and m == MultiDimBinning([t, c])
+    g = m.meshgrid("weighted_centers", attach_units=False)
+    assert g[0].shape == (200, 200) and g[0][3, 0] == g[0][3, 7] and g[1][0, 5] == g[1][9, 5]  # 'ij', row-major
+    pid = OneDimBinning("pid", bin_edges=[-np.inf, 0.55, np.inf])
+    assert pid.is_irregular
+
+
+def test_parse_own_and_reference_pipeline_cfgs():
+    d = parse_pipeline_config("settings/pipeline/b200_events.cfg")
+    assert list(d.keys())[1:] == [("data", "synthetic_mc"), ("osc", "prob3"), ("aeff", "aeff"), ("utils", "hist")]
+    assert d["pipeline"]["output_key"] == ("weights", "errors") and d["pipeline"]["output_binning"].shape == (8, 8, 2)
+    p = d[("osc", "prob3")]["params"].params
+    assert set(p.names) == {"earth_model", "YeI", "YeM", "YeO", "detector_depth", "prop_height", "theta12", "theta13",
+                            "theta23", "deltam21", "deltam31", "deltacp"}
+    assert p.theta13.value.m_as("deg") == 8.5 and p.deltam31.value.m_as("eV**2") == 2.457e-3  # nh selected
+    assert not p.theta23.is_fixed and p.theta12.is_fixed and p.earth_model.value == "osc/PREM_12layer.dat"
+    if not os.path.isdir(REF_RES):
+        pytest.skip("reference tree not present")
+    old = os.environ.get("PISA_RESOURCES")
+    os.environ["PISA_RESOURCES"] = REF_RES
+    try:
+        # byte-identical reference cfgs (README example + the IceCube 3y pipeline)
+        d = parse_pipeline_config("settings/pipeline/osc_example.cfg")
+        assert list(d.keys())[1:] == [("data", "toy_event_generator"), ("flux", "barr_simple"), ("osc", "prob3")]
+        assert d[("osc", "prob3")]["calc_mode"].shape == (200, 200)
+        p = d[("osc", "prob3")]["params"].params
+        assert p.theta23.value.m_as("deg") == 42.0 and p.deltacp.value.m_as("deg") == 0.0
+        assert np.array_equal(p.theta13.range.m, [7.85, 9.1]) and p.theta13.prior["kind"] == "gaussian"
+        d = parse_pipeline_config("settings/pipeline/IceCube_3y_neutrinos.cfg")
+        assert d[("utils", "hist")]["error_method"] == "sumw2"
+        assert d[("osc", "prob3")]["calc_mode"].shape == (200, 200) and d[("osc", "prob3")]["apply_mode"] == "events"
+        assert d[("aeff", "aeff")]["params"].params.livetime.value.m_as("common_year") == 2.5
+    finally:
+        if old is None:
+            del os.environ["PISA_RESOURCES"]
+        else:
+            os.environ["PISA_RESOURCES"] = old
+
+
+def test_stage_contract_errors():
+    from pisa_b200.stages.osc.prob3 import init_test, prob3
+    from pisa_b200.stages.utils.hist import hist
+    s = init_test()
+    assert (s.stage_name, s.service_name) == ("osc", "prob3")
+    assert s.has_setup and s.has_compute and s.has_apply and s.param_hash is None
+    good = s.params
+    with pytest.raises(ValueError, match="Missing params"):
+        prob3(params=ParamSet([p for p in good if p.name != "theta12"]))
+    with pytest.raises(ValueError, match="Excess params"):
+        prob3(params=ParamSet(list(good) + [Param("bogus", 1.0)]))
+    with pytest.raises(ValueError):
+        prob3(params=good, nsi_type="quantum")
+    with pytest.raises(NotImplementedError):
+        prob3(params=good, neutrino_decay=True)
+    with pytest.raises(ValueError, match="not supported"):
+        hist(calc_mode="log_events").setup()
+    h = hist(calc_mode="events")
+    h.data = "not a container set"
+    with pytest.raises(TypeError):
+        h.setup()
+    # nsi_type='standard' adds the nine eps_* names (prob3.py:244-254)
+    with pytest.raises(ValueError, match="eps_ee"):
+        prob3(params=good, nsi_type="standard")
