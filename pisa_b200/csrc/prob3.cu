@@ -102,7 +102,13 @@ int build_earth_table(const pisab_earth_t *e, EarthTable *out) {
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlock = 128;
+#ifndef PISAB_BLOCK
+#define PISAB_BLOCK 256
+#endif
+#ifndef PISAB_MIN_BLOCKS
+#define PISAB_MIN_BLOCKS 2
+#endif
+constexpr int kBlock = PISAB_BLOCK;
 
 template <typename IO>
 __device__ __forceinline__ double ld(const IO *p, int64_t i) { return (double)__ldg(p + i); }
@@ -123,7 +129,7 @@ __device__ __forceinline__ void copy_tables(const OscTable &osc, const EarthTabl
 // One thread per event, layers computed in-kernel from coszen.
 //   FULL: probability[n,3,3] ; otherwise prob_e / prob_mu of the event's final flavour.
 template <typename IO, bool FULL>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                    int nubar, const int32_t *__restrict__ d_nubar, int flav,
                    const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
@@ -224,7 +230,7 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 
 // Fused template evaluation: probabilities + reweighting + weighted histogram (w, w^2).
 template <typename IO>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      int nubar, const int32_t *__restrict__ d_nubar, int flav,
                      const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
@@ -284,6 +290,16 @@ static int grid_for(int64_t n, int blocks_per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
+// Persistent grid: exactly the number of blocks that are resident at once (one wave), so that the
+// grid-stride loop gives every block the same share of every layer-count class.
+template <typename K>
+static int resident_grid(K kernel, int64_t n, size_t smem) {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 2;
+    if (occ > 8) occ = 8; // workspace bound (pisab_hist_workspace_bytes)
+    return grid_for(n, occ);
+}
+
 template <typename IO>
 static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                 int32_t nubar, const int32_t *d_nubar, int32_t flav,
@@ -304,7 +320,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     cudaStream_t s = (cudaStream_t)stream;
     if (d_probability) {
         LaunchTimer t(s);
-        prob3_earth_kernel<IO, true><<<grid_for(n, 4), kBlock, 0, s>>>(
+        prob3_earth_kernel<IO, true><<<resident_grid(prob3_earth_kernel<IO, true>, n, 0), kBlock, 0, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, d_probability, nullptr, nullptr);
         note_launch();
     }
@@ -321,7 +337,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
         if (r1) return r1;
     } else if (d_prob_e) {
         LaunchTimer t(s);
-        prob3_earth_kernel<IO, false><<<grid_for(n, 4), kBlock, 0, s>>>(
+        prob3_earth_kernel<IO, false><<<resident_grid(prob3_earth_kernel<IO, false>, n, 0), kBlock, 0, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, nullptr, d_prob_e, d_prob_mu);
         note_launch();
     }
@@ -389,10 +405,10 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
     rc = build_earth_table(earth, &et);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const int grid = hist_grid(n);
     const size_t smem = WarpHist::smem_bytes(kBlock, n_bins);
     if (smem > 48 * 1024)
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(reweight_hist_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = resident_grid(reweight_hist_kernel<IO>, n, smem);
     {
         LaunchTimer t(s);
         reweight_hist_kernel<IO><<<grid, kBlock, smem, s>>>(ot, et, nubar, d_nubar, flav, d_flav, d_energy,
