@@ -146,7 +146,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         const double e = ld(energy, i), cz = ld(coszen, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
-        const Herm3 h0 = herm_axpy(1.0 / e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+        const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
         if (FULL) {
             Propagator<3, 3> P;
             propagate_earth<3, 3>(h0, s_osc.vm, s_earth, cz, 0, P);
@@ -177,12 +177,12 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
                     int n_layers, IO *__restrict__ probability) {
     __shared__ OscTable s_osc;
     copy_tables(osc, *reinterpret_cast<const EarthTable *>(&osc), &s_osc, nullptr);
-    const double T_SCALE = 2.0 * 2.534;
+    const double T_SCALE = kTab[18];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double e = ld(energy, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
-        const Herm3 h0 = herm_axpy(1.0 / e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+        const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
         const IO *rho = densities + i * n_layers;
         const IO *dist = distances + i * n_layers;
         Cplx M[3][3];
@@ -258,7 +258,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
             const double e = ld(energy, i), cz = ld(coszen, i);
             const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
             const int fl = d_flav ? __ldg(d_flav + i) : flav;
-            const Herm3 h0 = herm_axpy(1.0 / e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+            const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
             Propagator<1, 2> P;
             propagate_earth<1, 2>(h0, s_osc.vm, s_earth, cz, fl, P);
             const double pe = P.prob(0, 0), pmu = P.prob(0, 1);

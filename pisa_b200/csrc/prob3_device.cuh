@@ -42,32 +42,105 @@ __device__ __forceinline__ Cplx cfma(Cplx a, Cplx b, Cplx c) { // a*b + c
 
 typedef Cplx Mat3[3][3];
 
+// ---- numeric building blocks ------------------------------------------------------------------
+// Non-trivial double constants live in __constant__ memory: a DFMA can take a constant-bank
+// operand directly, whereas a 64-bit literal costs two extra MOV/UMOV issue slots per use (ncu on
+// the first version of this kernel: 30 % of all issued instructions were such moves).
+__constant__ double kTab[24] = {
+    /* 0 */ 0.63661977236758134308,   // 2/pi
+    /* 1 */ 1.5707963267948966,       // pi/2 hi
+    /* 2 */ 6.123233995736766e-17,    // pi/2 lo
+    /* 3.. 8: fdlibm __kernel_sin S6..S1 */
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    /* 9..14: fdlibm __kernel_cos C6..C1 */
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02,
+    /* 15 */ 0.86602540378443864676,  // sin(pi/3)
+    /* 16 */ 0.33333333333333333333,  // 1/3
+    /* 17 */ 0.66666666666666666667,  // 2/3
+    /* 18 */ 5.068,                   // 2 * 2.534  (numba_osc_kernels.py:524)
+    /* 19 */ 0.375, 0, 0, 0, 0};
+
+// 1/x and 1/sqrt(x) from the hardware approximations (MUFU.RCP64H / RSQ64H) + two Newton steps:
+// ~1 ulp, no IEEE fix-up path (the library versions cost ~20 instructions plus a slow-path call).
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double h = 0.5 * x;
+    r = r * fma(-h * r, r, 1.5);
+    r = r * fma(-h * r, r, 1.5);
+    return r;
+}
+// sqrt(x) for x >= 0 (0 allowed) to ~1 ulp
+__device__ __forceinline__ double sqrt_fast(double x) {
+    const double xs = fmax(x, 1e-290);
+    const double r = rsqrt_fast(xs);
+    double s = xs * r;
+    s = fma(fma(-s, s, xs), 0.5 * r, s); // one Newton correction of the product
+    return x > 0.0 ? s : 0.0;
+}
+
 // sin/cos for |x| < ~1e5 rad (phases here are < 1e3): two-term Cody-Waite reduction with FMA and
 // the fdlibm kernel polynomials on [-pi/4, pi/4].  No Payne-Hanek slow path (keeps the code small
 // enough for the instruction cache); max error ~1 ulp, same as the CUDA fast path.
 __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
-    const double kd = rint(x * 0.63661977236758134308); // 2/pi
+    const double kd = rint(x * kTab[0]);
     const int k = (int)kd;
-    double r = fma(-kd, 1.5707963267948966, x);
-    r = fma(-kd, 6.123233995736766e-17, r);
+    double r = fma(-kd, kTab[1], x);
+    r = fma(-kd, kTab[2], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kTab[3], kTab[4]);
+    ps = fma(z, ps, kTab[5]);
+    ps = fma(z, ps, kTab[6]);
+    ps = fma(z, ps, kTab[7]);
+    ps = fma(z, ps, kTab[8]);
     const double s = fma(r * z, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kTab[9], kTab[10]);
+    pc = fma(z, pc, kTab[11]);
+    pc = fma(z, pc, kTab[12]);
+    pc = fma(z, pc, kTab[13]);
+    pc = fma(z, pc, kTab[14]);
     const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
-    // quadrant
     const double ss = (k & 1) ? c : s;
     const double cc = (k & 1) ? s : c;
     *sn = (k & 2) ? -ss : ss;
     *cs = ((k + 1) & 2) ? -cc : cc;
+}
+
+// (cos t, sin t) with 3t = atan2(zi, zr), zi >= 0, i.e. the principal cube root of the unit complex
+// number z/|z| (replaces atan2 + sincos of numba_osc_kernels.py:794-813).  A float-precision seed
+// (atan2f + fast sincosf, ~1e-6) is normalised and refined by one third-order angle correction
+//     d = Im(z conj(w^3)) / 3 ,  w <- w (1 - d^2/2 + i d)
+// which leaves an error ~1.5 d^3 ~ 1e-18.  The conditioning of the eigenvalues sits entirely in
+// (zr, zi), not in this step.
+__device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_out, double *s_out) {
+    const double n2 = fma(zr, zr, zi * zi);
+    const bool ok = n2 > 0.0;
+    const double inv = rsqrt_fast(ok ? n2 : 1.0);
+    zr = ok ? zr * inv : 1.0;
+    zi = ok ? zi * inv : 0.0;
+    float sf, cf;
+    __sincosf(atan2f((float)zi, (float)zr) * (1.0f / 3.0f), &sf, &cf);
+    double c = (double)cf, s = (double)sf;
+    const double m = fma(c, c, fma(s, s, -1.0)); // |w|^2 - 1 ~ 1e-7
+    const double r = fma(m, fma(m, kTab[19], -0.5), 1.0);
+    c *= r;
+    s *= r;
+    const double w2r = fma(c, c, -s * s), w2i = 2.0 * c * s;
+    const double w3r = fma(w2r, c, -w2i * s), w3i = fma(w2r, s, w2i * c);
+    const double d = fma(zi, w3r, -zr * w3i) * kTab[16];
+    const double k = fma(-0.5 * d, d, 1.0);
+    *c_out = fma(c, k, -s * d);
+    *s_out = fma(s, k, c * d);
 }
 
 // H = hv * inv_e + lr   (per event), then + rho * vm per layer
@@ -104,12 +177,11 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
     const double q = fma(4.5 * c1, c2, fma(-13.5, c0, -c2 * c2 * c2));
     double disc = 27.0 * fma(0.25 * c1 * c1, p - c1, c0 * fma(6.75, c0, q));
     disc = fmax(disc, 0.0);
-    const double theta = atan2(sqrt(disc), q) * (1.0 / 3.0);
-    const double b = (2.0 / 3.0) * sqrt(p);
-    const double base = c2 * (-1.0 / 3.0);
+    const double b = kTab[17] * sqrt_fast(p);
+    const double base = -c2 * kTab[16];
     double st, ct;
-    sincos_small(theta, &st, &ct); // theta in [0, pi/3]
-    const double kh = 0.5, ks = 0.86602540378443864676; // cos, sin of pi/3
+    unit_cube_root(q, sqrt_fast(disc), &ct, &st); // theta = atan2(sqrt(disc), q) / 3 in [0, pi/3]
+    const double kh = 0.5, ks = kTab[15]; // cos, sin of pi/3
     // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
     const double l0 = fma(b, -kh * ct - ks * st, base);
     const double l1 = fma(b, -kh * ct + ks * st, base);
@@ -117,7 +189,7 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
 
     // ---- Lagrange weights with the global phase exp(-i l2 t) dropped
     const double g01 = l0 - l1, g02 = l0 - l2, g12 = l1 - l2;
-    const double inv_g = 1.0 / (g01 * g02 * g12);
+    const double inv_g = rcp_fast(g01 * g02 * g12);
     const double id0 = g12 * inv_g;  // 1/((l0-l1)(l0-l2))
     const double id1 = -g02 * inv_g; // 1/((l1-l0)(l1-l2))
     const double id2 = g01 * inv_g;  // 1/((l2-l0)(l2-l1))
@@ -263,7 +335,7 @@ template <int NR, int NC>
 __device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm,
                                                 const EarthTable &E, double cz, int flav,
                                                 Propagator<NR, NC> &P) {
-    const double T_SCALE = 2.0 * 2.534; // (1/2)(1/hbar c) in GeV/(eV^2 km) (:524), times 2 (M = 2 E lambda)
+    const double T_SCALE = kTab[18]; // 2 * 2.534: (1/2)(1/hbar c) in GeV/(eV^2 km) (:524), times 2 (M = 2 E lambda)
     enum { ACT_R = 1, ACT_L = 2 };
     const double cz2 = __dmul_rn(cz, cz);
     const double base = __dmul_rn(-E.r_det, cz);

@@ -25,9 +25,30 @@ def fast_probs(dm, mix, mat_pot, lri, nubar, E, rho, dist, variant="trig"):
         p = np.maximum(c2*c2 - 3*c1, 0)
         q = -13.5*c0 - c2**3 + 4.5*c1*c2
         tmp = np.maximum(27*(0.25*c1*c1*(p-c1) + c0*(q+6.75*c0)), 0)
-        th = np.arctan2(np.sqrt(tmp), q)/3
         b_ = (2/3)*np.sqrt(p)
-        cth, sth = np.cos(th), np.sin(th)
+        if variant == "cbrt":
+            zr, zi = q, np.sqrt(tmp)
+            n2 = zr*zr + zi*zi
+            inv = 1/np.sqrt(np.where(n2 > 0, n2, 1.0))
+            zr, zi = np.where(n2 > 0, zr*inv, 1.0), np.where(n2 > 0, zi*inv, 0.0)
+            th0 = (np.arctan2(zi.astype(np.float32), zr.astype(np.float32)) / np.float32(3)).astype(np.float32)
+            # emulate fast intrinsics: add ~5e-7 abs noise
+            cf = np.cos(th0).astype(np.float32) + np.float32(4e-7); sf = np.sin(th0).astype(np.float32) - np.float32(3e-7)
+            c, s_ = cf.astype(np.float64), sf.astype(np.float64)
+            m = c*c + s_*s_ - 1.0
+            r = 1 - 0.5*m + 0.375*m*m
+            c, s_ = c*r, s_*r
+            for _ in range(1):
+                w2r, w2i = c*c - s_*s_, 2*c*s_
+                w3r, w3i = w2r*c - w2i*s_, w2r*s_ + w2i*c
+                e_ = zi*w3r - zr*w3i
+                d_ = e_/3
+                k = 1 - 0.5*d_*d_
+                c, s_ = c*k - s_*d_, s_*k + c*d_
+            cth, sth = c, s_
+        else:
+            th = np.arctan2(np.sqrt(tmp), q)/3
+            cth, sth = np.cos(th), np.sin(th)
         c120, s120 = -0.5, np.sqrt(3)/2
         lam = np.stack([b_*cth, b_*(cth*c120 - sth*s120), b_*(cth*c120 + sth*s120)], axis=1) - (c2/3)[:,None]
         I2 = None
@@ -55,7 +76,7 @@ if __name__ == "__main__":
     keys = sorted({k.rsplit("/", 1)[0] for k in g.files if k.count("/") == 2})
     for key in keys:
         ref = g[key + "/probability"]
-        out = fast_probs(g[key+"/dm"], g[key+"/mix"], g[key+"/mat_pot"], g[key+"/lri_pot"], int(g[key+"/nubar"]), g["energy"], den, dis)
+        out = fast_probs(g[key+"/dm"], g[key+"/mix"], g[key+"/mat_pot"], g[key+"/lri_pot"], int(g[key+"/nubar"]), g["energy"], den, dis, variant=sys.argv[1] if len(sys.argv)>1 else "trig")
         err = np.abs(out - ref)
         rel = err / np.maximum(np.abs(ref), 1e-300)
         ok = np.isclose(out, ref, rtol=1e-10, atol=1e-14)
