@@ -105,7 +105,18 @@ EXPORTED_SYMBOLS = sorted(
 
 
 class PisabError(RuntimeError):
-    pass
+    """Any non-zero status of the C ABI (CUDA failure, workspace too small, ...)."""
+
+
+class PisabArgError(PisabError, ValueError):
+    """PISAB_ERR_ARG: the exception class the reference raises for bad modes / params (stage.py:360-379)."""
+
+
+class PisabUnsupportedError(PisabError, NotImplementedError):
+    """PISAB_ERR_UNSUPPORTED: a branch of the reference that is outside the hot path (e.g. neutrino decay)."""
+
+
+_ERR_CLASSES = {1: PisabArgError, 3: PisabUnsupportedError}
 
 
 def lib_path():
@@ -137,7 +148,7 @@ def load():
 
 def check(rc):
     if rc != 0:
-        raise PisabError("pisa_b200 error %d: %s" % (rc, load().pisab_last_error().decode()))
+        raise _ERR_CLASSES.get(rc, PisabError)("pisa_b200 error %d: %s" % (rc, load().pisab_last_error().decode()))
 
 
 def fn(name, dtype):

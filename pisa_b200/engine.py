@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .distributed import combine_histograms, shard_slice  # noqa: F401  (shard_slice re-exported)
 
 _NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
 
@@ -30,7 +31,7 @@ class _Block:
 class ReweightEngine:
     """Device-resident event containers + fused template evaluation."""
 
-    def __init__(self, earth, n_bins, dtype=np.float64, device=None, sort_events=True):
+    def __init__(self, earth, n_bins, dtype=np.float64, device=None, sort_events=True, deterministic=True):
         if not torch.cuda.is_available():
             raise RuntimeError("pisa_b200.engine needs a CUDA device (there is no CPU path)")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
@@ -39,6 +40,7 @@ class ReweightEngine:
         self.tdtype = _NP2T[np.dtype(dtype)]
         self.blocks = []
         self.sort_events = bool(sort_events)
+        self.deterministic = bool(deterministic)
         self._out = None
         self._copy_stream = None
         self._host_out = None
@@ -152,17 +154,6 @@ class ReweightEngine:
         self.last_d2h_bytes = out.numel() * out.element_size()
         return self._host_out.numpy()
 
-    @staticmethod
-    def allreduce(buf):
-        """Sum the per-GPU histograms (one NCCL all-reduce per template; no-op on one rank)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(buf, op=dist.ReduceOp.SUM)
-        return buf
-
-
-def shard_slice(n, rank, world):
-    """Contiguous slice [start, stop) of n events owned by `rank` (fixed boundaries -> reproducible)."""
-    base, rem = divmod(int(n), int(world))
-    start = rank * base + min(rank, rem)
-    return start, start + base + (1 if rank < rem else 0)
+    def allreduce(self, buf):
+        """Sum the per-GPU histograms: the single exchange step per template (no-op on one rank)."""
+        return combine_histograms(buf, deterministic=self.deterministic)
