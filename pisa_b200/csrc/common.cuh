@@ -1,6 +1,10 @@
 // common.cuh -- error handling, launch bookkeeping and device tables shared by the kernels.
 #pragma once
+#ifdef PISAB_HOST_EMU
+#include "../../scratch/hostemu/cuda_shim.h" // development-only: device math compiled by g++
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 #include <stdio.h>
 
@@ -52,6 +56,13 @@ struct OscTable {
     Herm3 hv[2]; // [0] = nu, [1] = nubar (sign flipped)
     Herm3 vm;
     Herm3 lr;
+    // Vacuum shortcut (shells with rho == 0, i.e. the atmosphere, when lri_pot == 0): there the
+    // eigen-decomposition is the PMNS matrix itself, exp(-iHt) = 1 + sum_k (e^{-i phi_k} - 1) P_k
+    // with the projectors P_k = u_k u_k^dagger (k = 2, 3) and phi_k = hdm[k] * t / E.
+    Herm3 pr2, pr3;
+    double hdm21, hdm31; // 0.5 * dm21, 0.5 * dm31
+    double vac_ok;       // 1.0 when the shortcut is valid (lri_pot == 0), else 0.0
+    double pad_;
 };
 
 struct EarthTable {

@@ -8,98 +8,6 @@
 namespace pisab {
 
 // ---------------------------------------------------------------------------------------------
-// host: parameter tables
-// ---------------------------------------------------------------------------------------------
-static void pack_herm(const double m[3][3][2], double scale, Herm3 *h) {
-    h->d0 = scale * m[0][0][0];
-    h->d1 = scale * m[1][1][0];
-    h->d2 = scale * m[2][2][0];
-    h->r01 = scale * m[0][1][0];
-    h->i01 = scale * m[0][1][1];
-    h->r02 = scale * m[0][2][0];
-    h->i02 = scale * m[0][2][1];
-    h->r12 = scale * m[1][2][0];
-    h->i12 = scale * m[1][2][1];
-}
-
-static bool is_hermitian(const double m[3][3][2]) {
-    double scale = 0;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) scale = fmax(scale, fmax(fabs(m[i][j][0]), fabs(m[i][j][1])));
-    const double tol = 1e-12 * scale + 1e-300;
-    for (int i = 0; i < 3; ++i) {
-        if (fabs(m[i][i][1]) > tol) return false;
-        for (int j = i + 1; j < 3; ++j)
-            if (fabs(m[i][j][0] - m[j][i][0]) > tol || fabs(m[i][j][1] + m[j][i][1]) > tol) return false;
-    }
-    return true;
-}
-
-int build_osc_table(const pisab_osc_consts_t *c, OscTable *out) {
-    if (!c || !out) { set_error("null osc consts"); return PISAB_ERR_ARG; }
-    if (c->decay_flag == 1) {
-        // numba_osc_kernels.py:445-451 -> get_dms_numerical (numpy.linalg.eigvals): out of scope
-        set_error("decay_flag == 1 (neutrino decay) is not supported by the B200 path");
-        return PISAB_ERR_UNSUPPORTED;
-    }
-    double U[3][3][2], V[3][3][2], Lr[3][3][2], Hv[3][3][2];
-    memcpy(U, c->mix, sizeof U);
-    memcpy(V, c->mat_pot, sizeof V);
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { Lr[i][j][0] = c->lri_pot[i * 3 + j]; Lr[i][j][1] = 0.0; }
-    if (!is_hermitian(V)) { set_error("mat_pot must be Hermitian"); return PISAB_ERR_UNSUPPORTED; }
-    if (!is_hermitian(Lr)) { set_error("lri_pot must be symmetric"); return PISAB_ERR_UNSUPPORTED; }
-    // H_vac = U diag(0, dm[1][0], dm[2][0]) U^dagger  (get_H_vac, numba_osc_kernels.py:534-569)
-    const double d[3] = {0.0, c->dm[1 * 3 + 0], c->dm[2 * 3 + 0]};
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double re = 0, im = 0;
-            for (int k = 0; k < 3; ++k) {
-                // U[i][k] * d[k] * conj(U[j][k])
-                const double ar = U[i][k][0], ai = U[i][k][1], br = U[j][k][0], bi = -U[j][k][1];
-                re += d[k] * (ar * br - ai * bi);
-                im += d[k] * (ar * bi + ai * br);
-            }
-            Hv[i][j][0] = re;
-            Hv[i][j][1] = im;
-        }
-    pack_herm(Hv, 0.5, &out->hv[0]);   // one_over_two_e = 0.5 / energy (:443)
-    pack_herm(Hv, -0.5, &out->hv[1]);  // antineutrinos, see common.cuh
-    pack_herm(V, 0.5 * 1.52588e-4, &out->vm); // a = 0.5 * rho * tworttwoGf (:636-637)
-    pack_herm(Lr, 1e9, &out->lr);      // eV -> eV^2/GeV (:438)
-    return PISAB_OK;
-}
-
-int build_earth_table(const pisab_earth_t *e, EarthTable *out) {
-    if (!e || !out) { set_error("null earth"); return PISAB_ERR_ARG; }
-    if (e->n_radii < 2 || e->n_radii > PISAB_MAX_RADII) {
-        set_error("n_radii = %d outside [2, %d]", e->n_radii, PISAB_MAX_RADII);
-        return PISAB_ERR_ARG;
-    }
-    memset(out, 0, sizeof *out);
-    out->n_radii = e->n_radii;
-    out->r_det = e->r_detector;
-    out->rd2 = e->r_detector * e->r_detector;
-    int idx = -1;
-    for (int j = 0; j < e->n_radii; ++j) {
-        out->rj2[j] = e->radii[j] * e->radii[j];
-        out->rho[j] = e->rho_e[j];
-        out->limit[j] = e->coszen_limit[j];
-        if (idx < 0 && e->radii[j] < e->r_detector) idx = j;
-    }
-    if (idx < 1) { set_error("no Earth shell below the detector"); return PISAB_ERR_UNSUPPORTED; }
-    if (idx != 2) {
-        // extCalcLayers pairs 2K - idx segments with 2K - 2 densities (layers.py:128-158); for
-        // idx != 2 the reference reads out of bounds for every up-going direction.
-        set_error("detector must sit inside the outermost Earth shell (first inner shell index %d != 2); "
-                  "the reference's extCalcLayers is undefined for this geometry", idx);
-        return PISAB_ERR_UNSUPPORTED;
-    }
-    out->idx_first_inner = idx;
-    return PISAB_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
 #ifndef PISAB_BLOCK
@@ -146,10 +54,11 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         const double e = ld(energy, i), cz = ld(coszen, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
-        const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+        const double inv_e = rcp_fast(e);
+        const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
         if (FULL) {
             Propagator<3, 3> P;
-            propagate_earth<3, 3>(h0, s_osc.vm, s_earth, cz, 0, P);
+            propagate_earth<3, 3>(h0, s_osc, s_earth, cz, inv_e, nb, 0, P);
             IO *o = probability + i * 9;
 #pragma unroll
             for (int a = 0; a < 3; ++a)
@@ -157,7 +66,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
                 for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a); // P(a->b) = |A[b][a]|^2
         } else {
             Propagator<1, 2> P;
-            propagate_earth<1, 2>(h0, s_osc.vm, s_earth, cz, fl, P);
+            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             prob_e[i] = (IO)P.prob(0, 0);
             prob_mu[i] = (IO)P.prob(0, 1);
         }
@@ -182,7 +91,8 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double e = ld(energy, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
-        const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+        const double inv_e = rcp_fast(e);
+        const Herm3 h0 = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
         const IO *rho = densities + i * n_layers;
         const IO *dist = distances + i * n_layers;
         Cplx M[3][3];
@@ -228,7 +138,37 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
     }
 }
 
+// dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
+template <typename IO>
+static size_t fused_smem_bytes(int n_bins) {
+    size_t doubles = 0;
+#ifndef PISAB_STATE_REGS
+    doubles += (size_t)PropagatorSmem<1, 2>::kDoubles * kBlock;
+#endif
+#ifndef PISAB_H0_REGS
+    doubles += 9 * (size_t)kBlock;
+#endif
+    return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
+}
+
+// ---- per-thread asynchronous staging (LDGSTS): global -> shared without touching registers ----
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Fused template evaluation: probabilities + reweighting + weighted histogram (w, w^2).
+//
+// Memory latency: a thread spends ~25k cycles of FP64 work per event and then needs 44 bytes of the
+// next one; with 4 warps per scheduler an exposed DRAM round trip (~1.5k cycles, twice: inputs at
+// the top, flux/weight/bin at the bottom) costs ~15 % (ncu, round 1 capture d).  So every thread
+// software-pipelines its own stream: at the top of an event it issues cp.async copies of (a) the
+// flux / weight / bin of THIS event, needed at the bottom, and (b) energy / coszen of its NEXT event
+// into its private shared-memory slots, and waits for them only after the propagation.  The index of
+// the event after next (`order` indirection) rides in a register.
 template <typename IO>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
@@ -239,18 +179,36 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
                      const int32_t *__restrict__ order, int64_t n,
                      int n_bins, double *__restrict__ partials, IO *__restrict__ weights_out,
                      IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
-    extern __shared__ double s_hist[]; // [warps][2][n_bins] private bins, then staging
+    // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 18 x block]
+    // [per-thread h0 9 x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block] (int32)
+    extern __shared__ __align__(16) double s_hist[];
     __shared__ OscTable s_osc;
     __shared__ EarthTable s_earth;
+    double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
+#ifndef PISAB_STATE_REGS
+    double(*s_state)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
+    s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
+#endif
+#ifndef PISAB_H0_REGS
+    double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
+    s_dyn += 9 * kBlock;
+#endif
+    IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
+    IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
+    int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
     WarpHist wh(s_hist, n_bins);
     wh.clear();
     copy_tables(osc, earth, &s_osc, &s_earth);
+    const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
     // warp-uniform trip count so that the warp-collective histogram step is always converged
-    const int64_t warp_first = first - (threadIdx.x & 31);
+    const int64_t warp_first = first - (tid & 31);
+    // `order` (optional) lists the events grouped by number of crossed shells; -1 = no event
+#ifdef PISAB_NO_PREFETCH
+    // plain version (kept for A/B timing in scratch/kbench.py): loads issued where they are needed
     for (int64_t base = warp_first; base < n; base += stride) {
-        const int64_t t = base + (threadIdx.x & 31);
+        const int64_t t = base + (tid & 31);
         double w = 0.0;
         int bin = -1;
         if (t < n) {
@@ -258,11 +216,11 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
             const double e = ld(energy, i), cz = ld(coszen, i);
             const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
             const int fl = d_flav ? __ldg(d_flav + i) : flav;
-            const Herm3 h0 = herm_axpy(rcp_fast(e), s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+            const double inv_e = rcp_fast(e);
+            const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
             Propagator<1, 2> P;
-            propagate_earth<1, 2>(h0, s_osc.vm, s_earth, cz, fl, P);
+            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
-            // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
             const double fe = ld(nu_flux, 2 * i), fm = ld(nu_flux, 2 * i + 1);
             w = ld(weights_in, i) * (fe * pe + fm * pmu);
             bin = __ldg(index + i);
@@ -272,6 +230,57 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
         }
         wh.add(bin, w);
     }
+#else
+    // (n < 2^31 is checked by the host wrapper: 32-bit event indices save registers)
+    auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
+    int i_cur = event_of(first), i_next = event_of(first + stride);
+    if (i_cur >= 0) { s_e[tid] = __ldg(energy + i_cur); s_cz[tid] = __ldg(coszen + i_cur); }
+    for (int64_t base = warp_first; base < n; base += stride) {
+        const int64_t t = base + (tid & 31);
+        const int i_nn = event_of(t + 2 * stride);
+        double w = 0.0;
+        int bin = -1;
+        if (i_cur >= 0) {
+            const int64_t i = i_cur;
+            const double e = (double)s_e[tid], cz = (double)s_cz[tid];
+            cp_async<2 * sizeof(IO)>(&s_flux[tid][0], nu_flux + 2 * i);
+            cp_async<sizeof(IO)>(&s_w[tid], weights_in + i);
+            cp_async<4>(&s_bin[tid], index + i);
+            if (i_next >= 0) {
+                cp_async<sizeof(IO)>(&s_e[tid], energy + i_next);
+                cp_async<sizeof(IO)>(&s_cz[tid], coszen + i_next);
+            }
+            cp_async_commit();
+            const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
+            const int fl = d_flav ? __ldg(d_flav + i) : flav;
+            const double inv_e = rcp_fast(e);
+#ifdef PISAB_H0_REGS
+            const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
+#else
+            H0Smem::store(&s_h0[0][tid], kBlock, herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr));
+            const H0Smem h0{&s_h0[0][tid], kBlock};
+#endif
+#ifdef PISAB_STATE_REGS
+            Propagator<1, 2> P;
+#else
+            PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
+#endif
+            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+            const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
+            cp_async_wait_all();
+            // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
+            const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
+            w = (double)s_w[tid] * (fe * pe + fm * pmu);
+            bin = s_bin[tid];
+            if (weights_out) weights_out[i] = (IO)w;
+            if (prob_e) prob_e[i] = (IO)pe;
+            if (prob_mu) prob_mu[i] = (IO)pmu;
+        }
+        wh.add(bin, w);
+        i_cur = i_next;
+        i_next = i_nn;
+    }
+#endif
     wh.flush(partials + (size_t)blockIdx.x * 2 * n_bins);
 }
 
@@ -388,6 +397,7 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
         set_error("bad event arrays");
         return PISAB_ERR_ARG;
     }
+    if (n > 2147483647LL) { set_error("at most 2^31-1 events per call (32-bit event indices)"); return PISAB_ERR_ARG; }
     if (n_bins > PISAB_DET_MAX_BINS) {
         set_error("fused reweight+hist supports up to %d bins; use propagate_earth + hist_accumulate", PISAB_DET_MAX_BINS);
         return PISAB_ERR_UNSUPPORTED;
@@ -405,9 +415,14 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
     rc = build_earth_table(earth, &et);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = WarpHist::smem_bytes(kBlock, n_bins);
-    if (smem > 48 * 1024)
-        PISAB_CUDA_CHECK(cudaFuncSetAttribute(reweight_hist_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem = fused_smem_bytes<IO>(n_bins);
+    {
+        // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
+        cudaFuncAttributes fa;
+        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reweight_hist_kernel<IO>));
+        if (fa.sharedSizeBytes + smem > 48 * 1024)
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(reweight_hist_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     const int grid = resident_grid(reweight_hist_kernel<IO>, n, smem);
     {
         LaunchTimer t(s);

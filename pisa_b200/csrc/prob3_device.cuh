@@ -66,7 +66,11 @@ __constant__ double kTab[24] = {
 // ~1 ulp, no IEEE fix-up path (the library versions cost ~20 instructions plus a slow-path call).
 __device__ __forceinline__ double rcp_fast(double x) {
     double r;
+#ifdef PISAB_HOST_EMU
+    r = (double)(float)(1.0 / x);
+#else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
@@ -74,7 +78,11 @@ __device__ __forceinline__ double rcp_fast(double x) {
 }
 __device__ __forceinline__ double rsqrt_fast(double x) {
     double r;
+#ifdef PISAB_HOST_EMU
+    r = (double)(float)(1.0 / sqrt(x));
+#else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#endif
     double h = 0.5 * x;
     r = r * fma(-h * r, r, 1.5);
     r = r * fma(-h * r, r, 1.5);
@@ -123,11 +131,9 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
 // which leaves an error ~1.5 d^3 ~ 1e-18.  The conditioning of the eigenvalues sits entirely in
 // (zr, zi), not in this step.
 __device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_out, double *s_out) {
-    const double n2 = fma(zr, zr, zi * zi);
-    const bool ok = n2 > 0.0;
-    const double inv = rsqrt_fast(ok ? n2 : 1.0);
-    zr = ok ? zr * inv : 1.0;
-    zi = ok ? zi * inv : 0.0;
+    // (zr, zi) is already of unit modulus (up to rounding): the caller scales by p^(-3/2), because
+    // q^2 + (p^3 - q^2) = p^3 -- no second rsqrt here.  A modulus error delta only enters the
+    // correction step as delta * d ~ 1e-23.
     float sf, cf;
     __sincosf(atan2f((float)zi, (float)zr) * (1.0f / 3.0f), &sf, &cf);
     double c = (double)cf, s = (double)sf;
@@ -177,10 +183,15 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
     const double q = fma(4.5 * c1, c2, fma(-13.5, c0, -c2 * c2 * c2));
     double disc = 27.0 * fma(0.25 * c1 * c1, p - c1, c0 * fma(6.75, c0, q));
     disc = fmax(disc, 0.0);
-    const double b = kTab[17] * sqrt_fast(p);
+    // sqrt(p) and p^(-3/2) from one rsqrt; p == 0 only for H proportional to 1 (all roots equal)
+    const bool p_ok = p > 1e-290;
+    const double rs = rsqrt_fast(p_ok ? p : 1.0);
+    const double b = p_ok ? kTab[17] * (p * rs) : 0.0;
+    const double inv = rs * rs * rs;
     const double base = -c2 * kTab[16];
     double st, ct;
-    unit_cube_root(q, sqrt_fast(disc), &ct, &st); // theta = atan2(sqrt(disc), q) / 3 in [0, pi/3]
+    // theta = atan2(sqrt(disc), q) / 3 in [0, pi/3]
+    unit_cube_root(p_ok ? q * inv : 1.0, p_ok ? sqrt_fast(disc) * inv : 0.0, &ct, &st);
     const double kh = 0.5, ks = kTab[15]; // cos, sin of pi/3
     // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
     const double l0 = fma(b, -kh * ct - ks * st, base);
@@ -282,11 +293,18 @@ __device__ __forceinline__ double shell_root(double rd2, double cz2, double rj2)
 // columns of the product on the production side.
 //   MODE_FULL: NR = 3, NC = 3  -> probability[3][3]
 //   MODE_ROW : NR = 1, NC = 2  -> prob_e, prob_mu of final flavour `flav`
+// Two storage policies with the same interface:
+//   Propagator      : registers (18 / 36 doubles live across the eigenvalue solve);
+//   PropagatorSmem  : a per-thread column of shared memory, [(v*3+k)*2+re/im][block] doubles, so that
+//                     the vectors occupy registers only while they are being multiplied -- the
+//                     eigenvalue solve + matrix assembly then fit the 128-register budget without
+//                     spills, and the loop carries no register moves for the state.
 template <int NR, int NC>
 struct Propagator {
     Cplx L[NR][3];
     Cplx R[NC][3];
 
+    __device__ __forceinline__ void set_right(int c, int k, Cplx v) { R[c][k] = v; }
     __device__ __forceinline__ void init_right(const Mat3 T) {
 #pragma unroll
         for (int c = 0; c < NC; ++c)
@@ -309,11 +327,84 @@ struct Propagator {
             }
         }
     }
+    __device__ __forceinline__ void mul_right(const Mat3 T) { times_right<NC>(T, R); }
+    __device__ __forceinline__ void mul_left(const Mat3 T) { left_times<NR>(L, T); }
     // amplitude A[r][c] = sum_k L[r][k] R[c][k]; returns |A|^2
     __device__ __forceinline__ double prob(int r, int c) const {
         Cplx acc = cmul(L[r][0], R[c][0]);
         acc = cfma(L[r][1], R[c][1], acc);
         acc = cfma(L[r][2], R[c][2], acc);
+        return fma(acc.re, acc.re, acc.im * acc.im);
+    }
+};
+
+template <int NR, int NC>
+struct PropagatorSmem {
+    double *col; // this thread's column: &state[0][threadIdx.x]
+    int pitch;   // doubles between consecutive rows (= block size)
+    static constexpr int kDoubles = (NR + NC) * 6;
+
+    __device__ __forceinline__ Cplx ld(int v, int k) const {
+        return Cplx{col[((v * 3 + k) * 2) * pitch], col[((v * 3 + k) * 2 + 1) * pitch]};
+    }
+    __device__ __forceinline__ void st(int v, int k, Cplx z) {
+        col[((v * 3 + k) * 2) * pitch] = z.re;
+        col[((v * 3 + k) * 2 + 1) * pitch] = z.im;
+    }
+    // vectors 0..NC-1 = columns of R, NC..NC+NR-1 = rows of L
+    __device__ __forceinline__ void set_right(int c, int k, Cplx v) { st(c, k, v); }
+    __device__ __forceinline__ void init_right(const Mat3 T) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) st(c, k, T[k][c]);
+    }
+    __device__ __forceinline__ void init_left(const Mat3 T, int flav) {
+        if (NR == 3) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st(NC + r, c, T[r][c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Cplx v = T[0][c];
+                if (flav == 1) v = T[1][c];
+                if (flav == 2) v = T[2][c];
+                st(NC, c, v);
+            }
+        }
+    }
+    __device__ __forceinline__ void mul_right(const Mat3 T) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const Cplx r0 = ld(c, 0), r1 = ld(c, 1), r2 = ld(c, 2);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                Cplx acc = cmul(T[k][0], r0);
+                acc = cfma(T[k][1], r1, acc);
+                acc = cfma(T[k][2], r2, acc);
+                st(c, k, acc);
+            }
+        }
+    }
+    __device__ __forceinline__ void mul_left(const Mat3 T) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const Cplx l0 = ld(NC + r, 0), l1 = ld(NC + r, 1), l2 = ld(NC + r, 2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                Cplx acc = cmul(l0, T[0][c]);
+                acc = cfma(l1, T[1][c], acc);
+                acc = cfma(l2, T[2][c], acc);
+                st(NC + r, c, acc);
+            }
+        }
+    }
+    __device__ __forceinline__ double prob(int r, int c) const {
+        Cplx acc = cmul(ld(NC + r, 0), ld(c, 0));
+        acc = cfma(ld(NC + r, 1), ld(c, 1), acc);
+        acc = cfma(ld(NC + r, 2), ld(c, 2), acc);
         return fma(acc.re, acc.re, acc.im * acc.im);
     }
 };
@@ -331,10 +422,63 @@ struct Propagator {
 //     shell K-1 (innermost)      l_{K-1} - s_{K-1}    R <- T R
 //   no-tangent branch (layers.py:94-103): shells 0 .. idx-1 once each, last one initialises L.
 //   Segments of length <= 0 are skipped like in the reference (:233,285).
-template <int NR, int NC>
-__device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm,
-                                                const EarthTable &E, double cz, int flav,
-                                                Propagator<NR, NC> &P) {
+// Columns 0..NC-1 of the vacuum transition matrix 1 + z2 P2 + z3 P3 (see OscTable), written
+// straight into R (R[c][k] = T[k][c]); ts = -/+ t / E for nu / nubar.
+template <int NC, typename PROP>
+__device__ __forceinline__ void vacuum_columns(const OscTable &o, double ts, PROP &P) {
+    double s2, c2, s3, c3;
+    sincos_small(o.hdm21 * ts, &s2, &c2);
+    sincos_small(o.hdm31 * ts, &s3, &c3);
+    const double z2r = c2 - 1.0, z2i = s2, z3r = c3 - 1.0, z3i = s3;
+    const Herm3 &A = o.pr2, &B = o.pr3;
+#define PISAB_VAC_DIAG(C, DA, DB) \
+    P.set_right(C, C, Cplx{fma(z2r, DA, fma(z3r, DB, 1.0)), fma(z2i, DA, z3i * DB)});
+#define PISAB_VAC_OFF(I, J, AR, AI, BR, BI)                                         \
+    {                                                                               \
+        const double xr = fma(z2r, AR, z3r * BR), xi = fma(z2i, AR, z3i * BR);        \
+        const double yr = fma(z2r, AI, z3r * BI), yi = fma(z2i, AI, z3i * BI);        \
+        if (J < NC) P.set_right(J, I, Cplx{xr - yi, xi + yr}); /* T[I][J] */           \
+        if (I < NC) P.set_right(I, J, Cplx{xr + yi, xi - yr}); /* T[J][I] */           \
+    }
+    PISAB_VAC_DIAG(0, A.d0, B.d0)
+    PISAB_VAC_DIAG(1, A.d1, B.d1)
+    if (NC > 2) PISAB_VAC_DIAG(2, A.d2, B.d2)
+    PISAB_VAC_OFF(0, 1, A.r01, A.i01, B.r01, B.i01)
+    PISAB_VAC_OFF(0, 2, A.r02, A.i02, B.r02, B.i02)
+    PISAB_VAC_OFF(1, 2, A.r12, A.i12, B.r12, B.i12)
+#undef PISAB_VAC_DIAG
+#undef PISAB_VAC_OFF
+}
+
+// Where the per-event part of the Hamiltonian (h0 = hv/E + lr, 9 doubles) lives between layers:
+// in registers, or in a per-thread column of shared memory (frees 18 registers for the
+// eigenvalue solve; the 9 LDS per layer are conflict-free with the [9][block] layout).
+struct H0Reg {
+    Herm3 h;
+    __device__ __forceinline__ Herm3 load() const { return h; }
+};
+struct H0Smem {
+    const double *col; // &s_h0[0][threadIdx.x]
+    int pitch;         // block size
+    __device__ __forceinline__ static void store(double *col, int pitch, const Herm3 &h) {
+        col[0] = h.d0; col[pitch] = h.d1; col[2 * pitch] = h.d2;
+        col[3 * pitch] = h.r01; col[4 * pitch] = h.i01; col[5 * pitch] = h.r02;
+        col[6 * pitch] = h.i02; col[7 * pitch] = h.r12; col[8 * pitch] = h.i12;
+    }
+    __device__ __forceinline__ Herm3 load() const {
+        Herm3 h;
+        h.d0 = col[0]; h.d1 = col[pitch]; h.d2 = col[2 * pitch];
+        h.r01 = col[3 * pitch]; h.i01 = col[4 * pitch]; h.r02 = col[5 * pitch];
+        h.i02 = col[6 * pitch]; h.r12 = col[7 * pitch]; h.i12 = col[8 * pitch];
+        return h;
+    }
+};
+
+template <int NR, int NC, typename H0, typename PROP>
+__device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &osc,
+                                                const EarthTable &E, double cz, double inv_e,
+                                                int nubar, int flav, PROP &P) {
+    const Herm3 &vm = osc.vm;
     const double T_SCALE = kTab[18]; // 2 * 2.534: (1/2)(1/hbar c) in GeV/(eV^2 km) (:524), times 2 (M = 2 E lambda)
     enum { ACT_R = 1, ACT_L = 2 };
     const double cz2 = __dmul_rn(cz, cz);
@@ -347,6 +491,23 @@ __device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm
     double sq_cur = 0.0;                                             // sqrt term of current shell
     int j = 0;        // current shell
     int phase = 0;    // 0: walking inwards, 1: near-side piece of the detector shell pending
+#ifndef PISAB_NO_VACUUM_SHORTCUT
+    // Shell 0 is the atmosphere (rho = 0, layers.py:262-275): with no long-range potential its
+    // transition matrix needs no eigenvalue solve.  Every path starts with it (both branches), so it
+    // is taken out of the loop; the loop then resumes at shell 1 in exactly the state it would have.
+    if (osc.vac_ok != 0.0 && E.rho[0] == 0.0 && idx >= 2) {
+        const double sq_next = shell_root(E.rd2, cz2, E.rj2[1]);
+        const double l_next = __dadd_rn(base, sq_next);
+        const double seg = __dsub_rn(l_cur, l_next);
+        l_cur = l_next;
+        sq_cur = sq_next;
+        j = 1;
+        if (seg > 0.0) {
+            vacuum_columns<NC>(osc, (nubar > 0 ? -T_SCALE : T_SCALE) * seg * inv_e, P);
+            have_r = true;
+        }
+    }
+#endif
     for (;;) {
         double seg;
         int act;
@@ -385,13 +546,13 @@ __device__ __forceinline__ void propagate_earth(const Herm3 &h0, const Herm3 &vm
         const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
         if (seg > 0.0) {
             Mat3 T;
-            transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0), T_SCALE * seg, T);
+            transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0.load()), T_SCALE * seg, T);
             if (act & ACT_R) {
-                if (have_r) times_right<NC>(T, P.R);
+                if (have_r) P.mul_right(T);
                 else { P.init_right(T); have_r = true; }
             }
             if (act & ACT_L) {
-                if (have_l) left_times<NR>(P.L, T);
+                if (have_l) P.mul_left(T);
                 else { P.init_left(T, flav); have_l = true; }
             }
         }

@@ -1,0 +1,51 @@
+"""Compare the host-emulated device math with the CPU oracle (development tool)."""
+import ctypes, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle
+from pisa_b200._lib import OscConsts, Earth
+from pisa_b200.utils import synthetic as syn
+
+emu = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libemu.so"))
+
+def layers_obj(model="PREM_12layer.dat", depth=2.0, height=20.0):
+    prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", model))
+    L = oracle.OracleLayers(prem, depth, height)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    return L
+
+def earth_struct(L):
+    return Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+
+def run(n=200000, nsi=False, nubar=1, lri=None, model="PREM_12layer.dat", seed=0, depth=2.0):
+    rng = np.random.default_rng(seed)
+    e = 10 ** rng.uniform(0, 3, n); cz = rng.uniform(-1, 1, n)
+    L = layers_obj(model, depth)
+    dm, mix, mp = syn.osc_matrices(nsi=syn.STD_NSI if nsi else None)
+    zc = np.zeros((3, 3), complex); lr = np.zeros((3, 3)) if lri is None else lri
+    c = OscConsts.from_matrices(dm, mix, mp, -1, zc, lr)
+    E = earth_struct(L)
+    prob = np.empty((n, 3, 3)); pe = np.empty(n); pm = np.empty(n)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    worst = 0
+    for flav in (0, 1, 2):
+        rc = emu.emu_propagate(ctypes.byref(c), ctypes.byref(E), nubar, flav, vp(e), vp(cz), ctypes.c_int64(n), vp(prob), vp(pe), vp(pm))
+        assert rc == 0
+        _, den, dis = L.calcLayers(cz)
+        ref = oracle.propagate_array(dm, mix, mp, -1, zc, lr, nubar, e, den, dis)
+        d_full = np.abs(prob - ref).max()
+        d_row = max(np.abs(pe - ref[:, 0, flav]).max(), np.abs(pm - ref[:, 1, flav]).max())
+        worst = max(worst, d_full, d_row)
+    print("n=%d nsi=%s nubar=%+d lri=%s %s: max|dP| = %.3e" % (n, nsi, nubar, lri is not None, model, worst))
+    return worst
+
+if __name__ == "__main__":
+    w = 0
+    for nubar in (1, -1):
+        for nsi in (False, True):
+            w = max(w, run(nsi=nsi, nubar=nubar))
+    w = max(w, run(lri=np.diag([1e-14, -1e-14, 0.0])))
+    w = max(w, run(model="PREM_10layer.dat", n=50000))
+    w = max(w, run(model="PREM_4layer.dat", n=50000, depth=10.0))
+    print("worst", w)

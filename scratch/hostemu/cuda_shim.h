@@ -1,0 +1,25 @@
+// Development-only: lets g++ compile the DEVICE math headers (prob3_device.cuh) so that numerics
+// changes can be checked against the oracle in this GPU-less container before spending GPU time.
+// Never part of the library (pisa_b200/build.py compiles with nvcc and without PISAB_HOST_EMU).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#define __device__
+#define __host__
+#define __global__
+#define __forceinline__ inline
+#define __constant__ static const
+#define __restrict__
+#define __launch_bounds__(...)
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+#define cudaSuccess 0
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dsub_rn(double a, double b) { volatile double r = a - b; return r; }
+static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
+template <typename T> static inline T __ldg(const T *p) { return *p; }
+using std::fma; using std::fmax; using std::fmin; using std::rint; using std::sqrt;
+static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
+#define __sincosf pisab_emu_sincosf

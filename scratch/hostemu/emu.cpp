@@ -1,0 +1,32 @@
+// Host emulation of the per-event device math (development tool, see cuda_shim.h).
+#define PISAB_HOST_EMU
+#include "../../pisa_b200/csrc/prob3_device.cuh"
+#include "../../pisa_b200/csrc/tables.cu"
+#include <stdarg.h>
+namespace pisab {
+void set_error(const char *fmt, ...) { va_list ap; va_start(ap, fmt); vfprintf(stderr, fmt, ap); va_end(ap); fputc('\n', stderr); }
+}
+using namespace pisab;
+extern "C" int emu_propagate(const pisab_osc_consts_t *c, const pisab_earth_t *e, int nubar, int flav,
+                             const double *energy, const double *coszen, int64_t n, double *probability,
+                             double *prob_e, double *prob_mu) {
+    OscTable ot; EarthTable et;
+    int rc = build_osc_table(c, &ot); if (rc) return rc;
+    rc = build_earth_table(e, &et); if (rc) return rc;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) {
+        const double inv_e = rcp_fast(energy[i]);
+        const H0Reg h0{herm_axpy(inv_e, ot.hv[nubar > 0 ? 0 : 1], ot.lr)};
+        if (probability) {
+            Propagator<3, 3> P;
+            propagate_earth<3, 3>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) probability[i * 9 + a * 3 + b] = P.prob(b, a);
+        }
+        if (prob_e) {
+            Propagator<1, 2> P;
+            propagate_earth<1, 2>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
+            prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
+        }
+    }
+    return 0;
+}

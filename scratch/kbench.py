@@ -31,22 +31,29 @@ def run(path, n=8_333_333, reps=5):
     idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
     order = ops.layer_order(earth, ev["true_coszen"])
     args = (consts, earth, 1, 1, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"], idx, 128)
-    for _ in range(3):
-        ops.reweight_hist(*args, order=order)
-    torch.cuda.synchronize()
-    ts = []
-    for _ in range(reps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); h, h2 = ops.reweight_hist(*args, order=order); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    return min(ts), float(h.sum())
+    o = order.long()
+    sargs = (consts, earth, 1, 1, ev["true_energy"][o].contiguous(), ev["true_coszen"][o].contiguous(),
+             ev["nu_flux"][o].contiguous(), ev["weights"][o].contiguous(), idx[o].contiguous(), 128)
+    out = []
+    for a, kw in ((args, dict(order=order)), (sargs, dict())):
+        for _ in range(3):
+            ops.reweight_hist(*a, **kw)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); h, h2 = ops.reweight_hist(*a, **kw); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        out.append((min(ts), float(h.sum())))
+    return out
 
 if __name__ == "__main__":
     variants = json.loads(sys.argv[1]) if len(sys.argv) > 1 else {"base": []}
     for tag, flags in variants.items():
         try:
             p = build_variant(tag, flags)
-            ms, chk = run(p)
-            print("%-28s %8.3f ms  %.3e ev/s  checksum %.10e" % (tag, ms, 8_333_333 / ms * 1e3, chk), flush=True)
+            (ms, chk), (ms2, chk2) = run(p)
+            print("%-28s order: %8.3f ms %.3e ev/s | presorted: %8.3f ms %.3e ev/s | checksums %.12e %.12e" % (
+                tag, ms, 8_333_333 / ms * 1e3, ms2, 8_333_333 / ms2 * 1e3, chk, chk2), flush=True)
         except Exception as e:
             print(tag, "FAILED", repr(e)[:300], flush=True)
