@@ -62,7 +62,7 @@ struct OscTable {
     Herm3 pr2, pr3;
     double hdm21, hdm31; // 0.5 * dm21, 0.5 * dm31
     double vac_ok;       // 1.0 when the shortcut is valid (lri_pot == 0), else 0.0
-    double pad_;
+    double std_matter;   // 1.0 when vm = diag(a, 0, 0) (no NSI): layers only move H[0][0]
 };
 
 struct EarthTable {

@@ -55,10 +55,11 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
         const double inv_e = rcp_fast(e);
-        const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
+        H0Reg h0;
+        h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
         if (FULL) {
             Propagator<3, 3> P;
-            propagate_earth<3, 3>(h0, s_osc, s_earth, cz, inv_e, nb, 0, P);
+            propagate_earth<3, 3, false>(h0, s_osc, s_earth, cz, inv_e, nb, 0, P);
             IO *o = probability + i * 9;
 #pragma unroll
             for (int a = 0; a < 3; ++a)
@@ -66,7 +67,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
                 for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a); // P(a->b) = |A[b][a]|^2
         } else {
             Propagator<1, 2> P;
-            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+            propagate_earth<1, 2, false>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             prob_e[i] = (IO)P.prob(0, 0);
             prob_mu[i] = (IO)P.prob(0, 1);
         }
@@ -146,7 +147,7 @@ static size_t fused_smem_bytes(int n_bins) {
     doubles += (size_t)PropagatorSmem<1, 2>::kDoubles * kBlock;
 #endif
 #ifndef PISAB_H0_REGS
-    doubles += 9 * (size_t)kBlock;
+    doubles += (size_t)H0Smem::kDoubles * kBlock;
 #endif
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
@@ -169,7 +170,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // flux / weight / bin of THIS event, needed at the bottom, and (b) energy / coszen of its NEXT event
 // into its private shared-memory slots, and waits for them only after the propagation.  The index of
 // the event after next (`order` indirection) rides in a register.
-template <typename IO>
+template <typename IO, bool STD>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      int nubar, const int32_t *__restrict__ d_nubar, int flav,
@@ -186,12 +187,12 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     __shared__ EarthTable s_earth;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
 #ifndef PISAB_STATE_REGS
-    double(*s_state)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
+    double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
 #endif
 #ifndef PISAB_H0_REGS
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
-    s_dyn += 9 * kBlock;
+    s_dyn += H0Smem::kDoubles * kBlock;
 #endif
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
@@ -217,9 +218,11 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
             const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
             const int fl = d_flav ? __ldg(d_flav + i) : flav;
             const double inv_e = rcp_fast(e);
-            const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
+            H0Reg h0;
+        h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+            if (STD) h0.set_poly();
             Propagator<1, 2> P;
-            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+            propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
             const double fe = ld(nu_flux, 2 * i), fm = ld(nu_flux, 2 * i + 1);
             w = ld(weights_in, i) * (fe * pe + fm * pmu);
@@ -255,17 +258,23 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
             const int fl = d_flav ? __ldg(d_flav + i) : flav;
             const double inv_e = rcp_fast(e);
 #ifdef PISAB_H0_REGS
-            const H0Reg h0{herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr)};
+            H0Reg h0;
+            h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+            if (STD) h0.set_poly();
 #else
-            H0Smem::store(&s_h0[0][tid], kBlock, herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr));
-            const H0Smem h0{&s_h0[0][tid], kBlock};
+            H0Smem h0{&s_h0[0][tid], kBlock};
+            {
+                const Herm3 hh = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+                h0.store(hh);
+                if (STD) h0.set_poly(hh);
+            }
 #endif
 #ifdef PISAB_STATE_REGS
             Propagator<1, 2> P;
 #else
             PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
 #endif
-            propagate_earth<1, 2>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+            propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
             cp_async_wait_all();
             // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
@@ -416,19 +425,25 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = fused_smem_bytes<IO>(n_bins);
+    // standard matter potential (no NSI) -> the specialised instantiation (see H0Reg)
+#ifdef PISAB_NO_STD
+    auto kernel = reweight_hist_kernel<IO, false>;
+#else
+    auto kernel = ot.std_matter != 0.0 ? reweight_hist_kernel<IO, true> : reweight_hist_kernel<IO, false>;
+#endif
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
-        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, reweight_hist_kernel<IO>));
+        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
         if (fa.sharedSizeBytes + smem > 48 * 1024)
-            PISAB_CUDA_CHECK(cudaFuncSetAttribute(reweight_hist_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = resident_grid(reweight_hist_kernel<IO>, n, smem);
+    const int grid = resident_grid(kernel, n, smem);
     {
         LaunchTimer t(s);
-        reweight_hist_kernel<IO><<<grid, kBlock, smem, s>>>(ot, et, nubar, d_nubar, flav, d_flav, d_energy,
-                                                            d_coszen, d_nu_flux, d_weights_in, d_index, d_order, n, n_bins,
-                                                            (double *)d_workspace, d_weights_out, d_prob_e, d_prob_mu);
+        kernel<<<grid, kBlock, smem, s>>>(ot, et, nubar, d_nubar, flav, d_flav, d_energy,
+                                          d_coszen, d_nu_flux, d_weights_in, d_index, d_order, n, n_bins,
+                                          (double *)d_workspace, d_weights_out, d_prob_e, d_prob_mu);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());

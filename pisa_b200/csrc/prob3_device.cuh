@@ -62,27 +62,39 @@ __constant__ double kTab[24] = {
     /* 18 */ 5.068,                   // 2 * 2.534  (numba_osc_kernels.py:524)
     /* 19 */ 0.375, 0, 0, 0, 0};
 
-// 1/x and 1/sqrt(x) from the hardware approximations (MUFU.RCP64H / RSQ64H) + two Newton steps:
-// ~1 ulp, no IEEE fix-up path (the library versions cost ~20 instructions plus a slow-path call).
-__device__ __forceinline__ double rcp_fast(double x) {
+// 1/x, 1/sqrt(x) and sqrt(x) from the hardware approximations (MUFU.RCP64H / RSQ64H, ~2^-22) refined
+// by ONE third-order step (error -> ~2^-64 before rounding, result ~1 ulp): a dependent chain of 3-4
+// FP64 instructions instead of the 5-7 of two Newton steps -- these sit on the critical path of every
+// layer (the kernel is latency-bound on its FP64 dependency chains, see profiles/).  No IEEE fix-up
+// path (the library versions cost ~20 instructions plus a slow-path call).
+__device__ __forceinline__ double rcp_seed(double x) {
     double r;
 #ifdef PISAB_HOST_EMU
     r = (double)(float)(1.0 / x);
 #else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
+    return r;
 }
-__device__ __forceinline__ double rsqrt_fast(double x) {
+__device__ __forceinline__ double rsqrt_seed(double x) {
     double r;
 #ifdef PISAB_HOST_EMU
     r = (double)(float)(1.0 / sqrt(x));
 #else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
+    return r;
+}
+#ifdef PISAB_NEWTON2
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r = rcp_seed(x);
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double r = rsqrt_seed(x);
     double h = 0.5 * x;
     r = r * fma(-h * r, r, 1.5);
     r = r * fma(-h * r, r, 1.5);
@@ -96,6 +108,29 @@ __device__ __forceinline__ double sqrt_fast(double x) {
     s = fma(fma(-s, s, xs), 0.5 * r, s); // one Newton correction of the product
     return x > 0.0 ? s : 0.0;
 }
+#else
+__device__ __forceinline__ double rcp_fast(double x) {
+    const double r = rcp_seed(x);
+    const double e = fma(-x, r, 1.0);      // 1/x = r / (1 - e) = r (1 + e + e^2 + O(e^3))
+    return fma(r * e, 1.0 + e, r);
+}
+// with e = 1 - x r^2:  x^(-1/2) = r (1 - e)^(-1/2) = r (1 + e/2 + 3 e^2/8 + O(e^3))
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    const double r = rsqrt_seed(x);
+    const double t = x * r;
+    const double e = fma(-t, r, 1.0);
+    return fma(r * e, fma(e, kTab[19], 0.5), r);
+}
+// sqrt(x) = x r (1 + e/2 + 3 e^2/8); x >= 0 (0 allowed)
+__device__ __forceinline__ double sqrt_fast(double x) {
+    const double xs = fmax(x, 1e-290);
+    const double r = rsqrt_seed(xs);
+    const double t = xs * r;
+    const double e = fma(-t, r, 1.0);
+    const double s = fma(t * e, fma(e, kTab[19], 0.5), t);
+    return x > 0.0 ? s : 0.0;
+}
+#endif
 
 // sin/cos for |x| < ~1e5 rad (phases here are < 1e3): two-term Cody-Waite reduction with FMA and
 // the fdlibm kernel polynomials on [-pi/4, pi/4].  No Payne-Hanek slow path (keeps the code small
@@ -106,6 +141,7 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
     double r = fma(-kd, kTab[1], x);
     r = fma(-kd, kTab[2], r);
     const double z = r * r;
+#ifdef PISAB_HORNER
     double ps = fma(z, kTab[3], kTab[4]);
     ps = fma(z, ps, kTab[5]);
     ps = fma(z, ps, kTab[6]);
@@ -118,6 +154,14 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
     pc = fma(z, pc, kTab[13]);
     pc = fma(z, pc, kTab[14]);
     const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
+#else
+    // Estrin evaluation: dependency depth 3 after z instead of 5 (the kernel is latency-bound)
+    const double zz = z * z;
+    const double ps = fma(zz, fma(zz, fma(z, kTab[3], kTab[4]), fma(z, kTab[5], kTab[6])), fma(z, kTab[7], kTab[8]));
+    const double s = fma(r * z, ps, r);
+    const double pc = fma(zz, fma(zz, fma(z, kTab[9], kTab[10]), fma(z, kTab[11], kTab[12])), fma(z, kTab[13], kTab[14]));
+    const double c = fma(zz, pc, fma(z, -0.5, 1.0));
+#endif
     const double ss = (k & 1) ? c : s;
     const double cc = (k & 1) ? s : c;
     *sn = (k & 2) ? -ss : ss;
@@ -136,17 +180,20 @@ __device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_o
     // correction step as delta * d ~ 1e-23.
     float sf, cf;
     __sincosf(atan2f((float)zi, (float)zr) * (1.0f / 3.0f), &sf, &cf);
-    double c = (double)cf, s = (double)sf;
-    const double m = fma(c, c, fma(s, s, -1.0)); // |w|^2 - 1 ~ 1e-7
-    const double r = fma(m, fma(m, kTab[19], -0.5), 1.0);
-    c *= r;
-    s *= r;
-    const double w2r = fma(c, c, -s * s), w2i = 2.0 * c * s;
-    const double w3r = fma(w2r, c, -w2i * s), w3i = fma(w2r, s, w2i * c);
-    const double d = fma(zi, w3r, -zr * w3i) * kTab[16];
+    const double c = (double)cf, s = (double)sf;
+    // u = (c, s) has |u|^2 = 1 + m, m ~ 1e-7.  The normalisation (1+m)^(-1/2) = rho and the angle
+    // correction are evaluated as two independent chains (depth 9 instead of 15):
+    //   d = Im(z conj(w^3)) / 3 = Im(z conj(u^3)) (1 - 3m/2) / 3 ,  w' = rho u (1 - d^2/2 + i d)
+    const double m = fma(c, c, fma(s, s, -1.0));
+    const double rho = fma(m, fma(m, kTab[19], -0.5), 1.0);
+    const double cr = c * rho, sr = s * rho;
+    const double third = fma(m, -0.5, kTab[16]); // (1 - 1.5 m) / 3
+    const double u2r = fma(c, c, -s * s), u2i = 2.0 * c * s;
+    const double u3r = fma(u2r, c, -u2i * s), u3i = fma(u2r, s, u2i * c);
+    const double d = fma(zi, u3r, -zr * u3i) * third;
     const double k = fma(-0.5 * d, d, 1.0);
-    *c_out = fma(c, k, -s * d);
-    *s_out = fma(s, k, c * d);
+    *c_out = fma(cr, k, -sr * d);
+    *s_out = fma(sr, k, cr * d);
 }
 
 // H = hv * inv_e + lr   (per event), then + rho * vm per layer
@@ -164,18 +211,28 @@ __device__ __forceinline__ Herm3 herm_axpy(double a, const Herm3 &x, const Herm3
     return r;
 }
 
-// T = exp(-i h t) up to a global phase.  `h` in eV^2/GeV, t = 2 * 2.534 * distance[km].
-__device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3 T) {
-    // ---- characteristic polynomial x^3 + c2 x^2 + c1 x + c0 (numba_osc_kernels.py:716-752)
+// Characteristic polynomial x^3 + c2 x^2 + c1 x + c0 of a Hermitian 3x3 (numba_osc_kernels.py:716-752)
+__device__ __forceinline__ void char_poly(const Herm3 &h, double &c2, double &c1, double &c0) {
     const double n01 = fma(h.r01, h.r01, h.i01 * h.i01);
     const double n02 = fma(h.r02, h.r02, h.i02 * h.i02);
     const double n12 = fma(h.r12, h.r12, h.i12 * h.i12);
     const double ur = fma(h.r01, h.r12, -h.i01 * h.i12); // h01*h12
     const double ui = fma(h.r01, h.i12, h.i01 * h.r12);
     const double rpa = fma(ur, h.r02, ui * h.i02);       // Re(h01 h12 h20)
-    const double c2 = -(h.d0 + h.d1 + h.d2);
-    const double c1 = fma(h.d0, h.d1 + h.d2, h.d1 * h.d2) - n01 - n12 - n02;
-    const double c0 = fma(h.d0, n12, fma(h.d1, n02, h.d2 * n01)) - 2.0 * rpa - h.d0 * h.d1 * h.d2;
+    c2 = -(h.d0 + h.d1 + h.d2);
+    c1 = fma(h.d0, h.d1 + h.d2, h.d1 * h.d2) - n01 - n12 - n02;
+    c0 = fma(h.d0, n12, fma(h.d1, n02, h.d2 * n01)) - 2.0 * rpa - h.d0 * h.d1 * h.d2;
+}
+
+// T = exp(-i h t) up to a global phase, given the characteristic polynomial of h.
+// `h` in eV^2/GeV, t = 2 * 2.534 * distance[km].
+__device__ __forceinline__ void transition_matrix(const Herm3 &h, double c2, double c1, double c0, double t,
+                                                  Mat3 T) {
+    const double n01 = fma(h.r01, h.r01, h.i01 * h.i01);
+    const double n02 = fma(h.r02, h.r02, h.i02 * h.i02);
+    const double n12 = fma(h.r12, h.r12, h.i12 * h.i12);
+    const double ur = fma(h.r01, h.r12, -h.i01 * h.i12); // h01*h12
+    const double ui = fma(h.r01, h.i12, h.i01 * h.r12);
 
     // ---- roots (:766-814): p, q and the cancellation-safe p^3 - q^2
     double p = fma(c2, c2, -3.0 * c1);
@@ -246,6 +303,12 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3
 #undef PISAB_OFFDIAG
 }
 
+__device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3 T) {
+    double c2, c1, c0;
+    char_poly(h, c2, c1, c0);
+    transition_matrix(h, c2, c1, c0, t, T);
+}
+
 // ---- small dense helpers on NR x 3 / 3 x NC blocks ----------------------------------------
 // L (NR x 3) <- L . T
 template <int NR>
@@ -287,6 +350,17 @@ __device__ __forceinline__ void times_right(const Mat3 T, Cplx (*R)[3]) {
 // distances are bit-identical to numpy's.
 __device__ __forceinline__ double shell_root(double rd2, double cz2, double rj2) {
     return __dsqrt_rn(__dadd_rn(__dsub_rn(__dmul_rn(rd2, cz2), rd2), rj2));
+}
+
+// Same argument, ~1 ulp square root without the IEEE fix-up path: used by the propagation kernels,
+// where a 1e-16 relative change of a segment length moves a phase by < 1e-13 (the stand-alone layers
+// kernel keeps the correctly rounded version and stays bit-identical to numpy).
+__device__ __forceinline__ double shell_root_fast(double rd2, double cz2, double rj2) {
+#ifdef PISAB_EXACT_SQRT
+    return shell_root(rd2, cz2, rj2);
+#else
+    return sqrt_fast(__dadd_rn(__dsub_rn(__dmul_rn(rd2, cz2), rd2), rj2));
+#endif
 }
 
 // Propagation state: L is NR x 3 (rows of the product on the detector side), R holds NC
@@ -340,17 +414,15 @@ struct Propagator {
 
 template <int NR, int NC>
 struct PropagatorSmem {
-    double *col; // this thread's column: &state[0][threadIdx.x]
-    int pitch;   // doubles between consecutive rows (= block size)
+    double2 *col; // this thread's column: &state[0][threadIdx.x]; one (re, im) pair per 128-bit access
+    int pitch;    // entries between consecutive rows (= block size)
     static constexpr int kDoubles = (NR + NC) * 6;
 
     __device__ __forceinline__ Cplx ld(int v, int k) const {
-        return Cplx{col[((v * 3 + k) * 2) * pitch], col[((v * 3 + k) * 2 + 1) * pitch]};
+        const double2 z = col[(v * 3 + k) * pitch];
+        return Cplx{z.x, z.y};
     }
-    __device__ __forceinline__ void st(int v, int k, Cplx z) {
-        col[((v * 3 + k) * 2) * pitch] = z.re;
-        col[((v * 3 + k) * 2 + 1) * pitch] = z.im;
-    }
+    __device__ __forceinline__ void st(int v, int k, Cplx z) { col[(v * 3 + k) * pitch] = make_double2(z.re, z.im); }
     // vectors 0..NC-1 = columns of R, NC..NC+NR-1 = rows of L
     __device__ __forceinline__ void set_right(int c, int k, Cplx v) { st(c, k, v); }
     __device__ __forceinline__ void init_right(const Mat3 T) {
@@ -453,14 +525,30 @@ __device__ __forceinline__ void vacuum_columns(const OscTable &o, double ts, PRO
 // Where the per-event part of the Hamiltonian (h0 = hv/E + lr, 9 doubles) lives between layers:
 // in registers, or in a per-thread column of shared memory (frees 18 registers for the
 // eigenvalue solve; the 9 LDS per layer are conflict-free with the [9][block] layout).
+// For the standard matter potential (vm = diag(a, 0, 0): no NSI) a layer changes only H[0][0], by
+// x = rho * a, and the characteristic polynomial is linear in x:
+//     c2 = c2_0 - x ,  c1 = c1_0 + x (d1 + d2) ,  c0 = c0_0 - x (d1 d2 - |h12|^2)
+// so the provider also keeps the 5 per-event invariants and a layer costs 3 FMAs instead of 17 + 9.
 struct H0Reg {
     Herm3 h;
+    double inv[5]; // c2_0, c1_0, c0_0, d1 + d2, d1 d2 - |h12|^2 (only set by set_poly)
     __device__ __forceinline__ Herm3 load() const { return h; }
+    __device__ __forceinline__ void set_poly() {
+        char_poly(h, inv[0], inv[1], inv[2]);
+        inv[3] = h.d1 + h.d2;
+        inv[4] = fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12));
+    }
+    __device__ __forceinline__ void poly(double x, double &c2, double &c1, double &c0) const {
+        c2 = inv[0] - x;
+        c1 = fma(x, inv[3], inv[1]);
+        c0 = fma(-x, inv[4], inv[2]);
+    }
 };
 struct H0Smem {
-    const double *col; // &s_h0[0][threadIdx.x]
-    int pitch;         // block size
-    __device__ __forceinline__ static void store(double *col, int pitch, const Herm3 &h) {
+    double *col; // &s_h0[0][threadIdx.x], 14 rows: h0 (9) + invariants (5)
+    int pitch;   // block size
+    static constexpr int kDoubles = 14;
+    __device__ __forceinline__ void store(const Herm3 &h) {
         col[0] = h.d0; col[pitch] = h.d1; col[2 * pitch] = h.d2;
         col[3 * pitch] = h.r01; col[4 * pitch] = h.i01; col[5 * pitch] = h.r02;
         col[6 * pitch] = h.i02; col[7 * pitch] = h.r12; col[8 * pitch] = h.i12;
@@ -472,9 +560,21 @@ struct H0Smem {
         h.i02 = col[6 * pitch]; h.r12 = col[7 * pitch]; h.i12 = col[8 * pitch];
         return h;
     }
+    __device__ __forceinline__ void set_poly(const Herm3 &h) {
+        double c2, c1, c0;
+        char_poly(h, c2, c1, c0);
+        col[9 * pitch] = c2; col[10 * pitch] = c1; col[11 * pitch] = c0;
+        col[12 * pitch] = h.d1 + h.d2;
+        col[13 * pitch] = fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12));
+    }
+    __device__ __forceinline__ void poly(double x, double &c2, double &c1, double &c0) const {
+        c2 = col[9 * pitch] - x;
+        c1 = fma(x, col[12 * pitch], col[10 * pitch]);
+        c0 = fma(-x, col[13 * pitch], col[11 * pitch]);
+    }
 };
 
-template <int NR, int NC, typename H0, typename PROP>
+template <int NR, int NC, bool STD, typename H0, typename PROP>
 __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &osc,
                                                 const EarthTable &E, double cz, double inv_e,
                                                 int nubar, int flav, PROP &P) {
@@ -487,7 +587,7 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
     const bool tangent = cz < E.limit[idx];
     bool have_r = false, have_l = false;
 
-    double l_cur = __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[0])); // large root of current shell
+    double l_cur = __dadd_rn(base, shell_root_fast(E.rd2, cz2, E.rj2[0])); // large root of current shell
     double sq_cur = 0.0;                                             // sqrt term of current shell
     int j = 0;        // current shell
     int phase = 0;    // 0: walking inwards, 1: near-side piece of the detector shell pending
@@ -496,7 +596,7 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
     // transition matrix needs no eigenvalue solve.  Every path starts with it (both branches), so it
     // is taken out of the loop; the loop then resumes at shell 1 in exactly the state it would have.
     if (osc.vac_ok != 0.0 && E.rho[0] == 0.0 && idx >= 2) {
-        const double sq_next = shell_root(E.rd2, cz2, E.rj2[1]);
+        const double sq_next = shell_root_fast(E.rd2, cz2, E.rj2[1]);
         const double l_next = __dadd_rn(base, sq_next);
         const double seg = __dsub_rn(l_cur, l_next);
         l_cur = l_next;
@@ -514,7 +614,7 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
         bool last = false;
         const int shell = j;
         if (!tangent) {
-            const double l_next = (j + 1 < idx) ? __dadd_rn(base, shell_root(E.rd2, cz2, E.rj2[j + 1])) : 0.0;
+            const double l_next = (j + 1 < idx) ? __dadd_rn(base, shell_root_fast(E.rd2, cz2, E.rj2[j + 1])) : 0.0;
             seg = __dsub_rn(l_cur, l_next);
             l_cur = l_next;
             act = (j + 1 == idx) ? ACT_L : ACT_R;
@@ -533,7 +633,7 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
                 act = ACT_R;
                 last = true;
             } else {
-                const double sq_next = shell_root(E.rd2, cz2, E.rj2[j + 1]);
+                const double sq_next = shell_root_fast(E.rd2, cz2, E.rj2[j + 1]);
                 const double l_next = __dadd_rn(base, sq_next);
                 seg = __dsub_rn(l_cur, l_next);
                 l_cur = l_next;
@@ -546,7 +646,17 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
         const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
         if (seg > 0.0) {
             Mat3 T;
-            transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0.load()), T_SCALE * seg, T);
+            if (STD) {
+                // standard matter: only H[0][0] moves with the density (see H0Reg)
+                const double x = E.rho[rho_shell] * vm.d0;
+                Herm3 h = h0.load();
+                h.d0 += x;
+                double c2, c1, c0;
+                h0.poly(x, c2, c1, c0);
+                transition_matrix(h, c2, c1, c0, T_SCALE * seg, T);
+            } else {
+                transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0.load()), T_SCALE * seg, T);
+            }
             if (act & ACT_R) {
                 if (have_r) P.mul_right(T);
                 else { P.init_right(T); have_r = true; }

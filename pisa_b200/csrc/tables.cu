@@ -84,7 +84,11 @@ int build_osc_table(const pisab_osc_consts_t *c, OscTable *out) {
     bool lr_zero = true;
     for (int i = 0; i < 9; ++i) lr_zero = lr_zero && c->lri_pot[i] == 0.0;
     out->vac_ok = lr_zero ? 1.0 : 0.0;
-    out->pad_ = 0.0;
+    {
+        const Herm3 &v = out->vm;
+        out->std_matter = (v.d1 == 0.0 && v.d2 == 0.0 && v.r01 == 0.0 && v.i01 == 0.0 && v.r02 == 0.0 &&
+                           v.i02 == 0.0 && v.r12 == 0.0 && v.i12 == 0.0) ? 1.0 : 0.0;
+    }
     return PISAB_OK;
 }
 

@@ -23,3 +23,5 @@ template <typename T> static inline T __ldg(const T *p) { return *p; }
 using std::fma; using std::fmax; using std::fmin; using std::rint; using std::sqrt;
 static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 #define __sincosf pisab_emu_sincosf
+struct double2 { double x, y; };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }

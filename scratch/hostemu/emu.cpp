@@ -16,15 +16,18 @@ extern "C" int emu_propagate(const pisab_osc_consts_t *c, const pisab_earth_t *e
 #pragma omp parallel for
     for (int64_t i = 0; i < n; ++i) {
         const double inv_e = rcp_fast(energy[i]);
-        const H0Reg h0{herm_axpy(inv_e, ot.hv[nubar > 0 ? 0 : 1], ot.lr)};
+        H0Reg h0;
+        h0.h = herm_axpy(inv_e, ot.hv[nubar > 0 ? 0 : 1], ot.lr);
+        h0.set_poly();
         if (probability) {
             Propagator<3, 3> P;
-            propagate_earth<3, 3>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
+            propagate_earth<3, 3, false>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
             for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) probability[i * 9 + a * 3 + b] = P.prob(b, a);
         }
         if (prob_e) {
             Propagator<1, 2> P;
-            propagate_earth<1, 2>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
+            if (ot.std_matter != 0.0) propagate_earth<1, 2, true>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
+            else propagate_earth<1, 2, false>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
             prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
         }
     }
