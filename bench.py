@@ -12,7 +12,8 @@ from the reference tree; configs[0] is the reference's CPU-sized grid case and i
 
 One "step" = one template evaluation = one pass of the hot path over all events of this rank:
 for each container the fused kernel (layers -> prob3 -> weights *= flux.prob -> histogram w, w^2),
-then ONE all-reduce of the [12, 2, 128] histogram buffer when N > 1 (weak scaling: events/GPU fixed).
+then ONE exchange of the [12, 2, 128] histogram buffer when N > 1 (weak scaling: events/GPU fixed).
+All 12 containers are evaluated by ONE launch of the fused kernel.
 
 value : events/s with the event arrays resident in HBM (inputs 4.4 GB/GPU >> 126 MB L2, so no
         L2 flush is needed between steps).
@@ -324,8 +325,10 @@ def run_native(args):
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = n_gpu * world / (ms_step * 1e-3)
-    # per-launch CUDA-event times bracket the fused kernel + its tiny partial-reduction kernel
+    # per-launch CUDA-event times bracket the fused kernel (ONE launch for all 12 containers) + its tiny
+    # partial-reduction kernel
     launch_ms = float(np.mean([a.elapsed_time(b) for a, b in kernel_events]))
+    per = n_gpu  # events per fused launch
     hist_total = float(out[:, 0].sum())
 
     # ---- FP64 roofline denominator -------------------------------------------------------------

@@ -211,6 +211,32 @@ int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_
                             float *d_prob_mu, void *d_workspace, int64_t workspace_bytes,
                             void *stream);
 
+/* One template = ALL flavour containers of a pipeline in one launch (the fit-loop entry point;
+ * SURVEY 8f.1).  Per container: the event arrays as above plus `scale`, the per-container scalar that
+ * aeff.aeff multiplies into the weights (livetime * aeff_scale * norms, pisa/stages/aeff/aeff.py:68-88):
+ *   w = weights[i] * (nu_flux[i,0]*prob_e + nu_flux[i,1]*prob_mu) * scale
+ * d_hist: [n_containers][2][n_bins] (sum w, sum w^2), overwritten.  The descriptor array is a HOST
+ * array; all pointers inside are device pointers of the storage type of the entry point. */
+#define PISAB_MAX_BATCH 16
+typedef struct pisab_container {
+    const void *d_energy, *d_coszen, *d_nu_flux, *d_weights;
+    const int32_t *d_index;   /* flat output bin per event, -1 outside                         */
+    const int32_t *d_order;   /* optional thread order (see pisab_layer_count_*), may be NULL  */
+    void *d_weights_out;      /* optional per-event output weights, may be NULL                */
+    int64_t n;
+    double scale;
+    int32_t nubar, flav;
+} pisab_container_t;
+int64_t pisab_reweight_batch_workspace_bytes(int32_t n_containers, int32_t n_bins);
+int pisab_reweight_hist_batch_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                  const pisab_container_t *containers, int32_t n_containers,
+                                  int32_t n_bins, double *d_hist, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream);
+int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                  const pisab_container_t *containers, int32_t n_containers,
+                                  int32_t n_bins, double *d_hist, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream);
+
 /* mod_chi2 (pisa/utils/stats.py:651-695) on device for the scan driver:
  * sum_b (obs-exp)^2 / (sigma^2 + max(exp,1e-10)); result is one double on the device. */
 int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const double *d_observed,

@@ -64,6 +64,15 @@ class Binning(ctypes.Structure):
                 ("lo", c_dbl * MAX_DIMS), ("hi", c_dbl * MAX_DIMS), ("d_edges", c_vp * MAX_DIMS)]
 
 
+class ContainerDesc(ctypes.Structure):
+    """pisab_container_t -- one flavour container of a batched template evaluation."""
+    _fields_ = [("d_energy", c_vp), ("d_coszen", c_vp), ("d_nu_flux", c_vp), ("d_weights", c_vp),
+                ("d_index", c_vp), ("d_order", c_vp), ("d_weights_out", c_vp), ("n", c_i64),
+                ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32)]
+
+
+MAX_BATCH = 16
+
 _lib = None
 
 _SIGNATURES = {
@@ -85,9 +94,12 @@ _SIGNATURES = {
     "pisab_reweight_hist": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth), c_i32, c_vp, c_i32, c_vp,
                                     c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp,
                                     c_vp, c_i64, c_vp]),
+    "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
+                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
 }
 _UNTYPED = {
     "pisab_hist_workspace_bytes": (c_i64, [c_i64, c_i32]),
+    "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pisab_fp64_peak_probe": (c_i32, [c_i32, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "pisab_launch_count": (c_i64, [c_i32]),

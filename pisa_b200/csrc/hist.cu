@@ -144,6 +144,32 @@ hist_reduce_kernel(const double *__restrict__ partials, int n_blocks, int n_bins
     }
 }
 
+// Batched variant for the fused template kernel: partials[container][block][2 n_bins] ->
+// out[container][2][n_bins], same fixed summation order per value.
+__global__ void __launch_bounds__(256)
+hist_reduce_batch_kernel(const double *__restrict__ partials, int n_blocks, int n_bins, int n_containers,
+                         double *__restrict__ out) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // warp-uniform: (container, value)
+    const int lane = threadIdx.x & 31;
+    if (v >= n_containers * 2 * n_bins) return;
+    const int c = v / (2 * n_bins), b = v - c * 2 * n_bins;
+    const double *src = partials + (size_t)c * n_blocks * 2 * n_bins + b;
+    double s = 0.0;
+    for (int k = lane; k < n_blocks; k += 32) s += __ldg(src + (size_t)k * 2 * n_bins);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[v] = s;
+}
+
+int hist_reduce_batch(const double *d_partials, int n_blocks, int n_bins, int n_containers, double *d_out,
+                      cudaStream_t s) {
+    const int warps = n_containers * 2 * n_bins;
+    hist_reduce_batch_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(d_partials, n_blocks, n_bins, n_containers, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
 int hist_grid(int64_t n) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + kHistBlock - 1) / kHistBlock;
@@ -304,6 +330,11 @@ int64_t pisab_hist_workspace_bytes(int64_t n, int32_t n_bins) {
     (void)n;
     const int sms = sm_count() > 0 ? sm_count() : 148;
     return (int64_t)sms * 8 * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
+}
+
+int64_t pisab_reweight_batch_workspace_bytes(int32_t n_containers, int32_t n_bins) {
+    if (n_containers < 1) n_containers = 1;
+    return (int64_t)n_containers * pisab_hist_workspace_bytes(0, n_bins);
 }
 
 int pisab_hist_index_f64(const pisab_binning_t *binning, const double *const *d_coords, int64_t n,

@@ -74,4 +74,7 @@ int hist_grid(int64_t n);
 int hist_reduce_partials(const double *d_partials, int n_blocks, int n_bins, double *d_hist,
                          double *d_hist_w2, cudaStream_t s);
 
+int hist_reduce_batch(const double *d_partials, int n_blocks, int n_bins, int n_containers, double *d_out,
+                      cudaStream_t s);
+
 } // namespace pisab

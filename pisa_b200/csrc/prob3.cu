@@ -142,13 +142,7 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
 static size_t fused_smem_bytes(int n_bins) {
-    size_t doubles = 0;
-#ifndef PISAB_STATE_REGS
-    doubles += (size_t)PropagatorSmem<1, 2>::kDoubles * kBlock;
-#endif
-#ifndef PISAB_H0_REGS
-    doubles += (size_t)H0Smem::kDoubles * kBlock;
-#endif
+    const size_t doubles = (size_t)(PropagatorSmem<1, 2>::kDoubles + H0Smem::kDoubles) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
@@ -161,136 +155,122 @@ __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Fused template evaluation: probabilities + reweighting + weighted histogram (w, w^2).
+// Fused template evaluation: probabilities + reweighting + weighted histogram (w, w^2), for up to
+// PISAB_MAX_BATCH flavour containers in ONE launch.
 //
-// Memory latency: a thread spends ~25k cycles of FP64 work per event and then needs 44 bytes of the
+// Grid: one resident wave (persistent).  Every block walks its grid-stride share of EVERY container in
+// turn (perfectly balanced whatever the container sizes), flushing its warp-private histograms to
+// partials[container][block] between containers; a second tiny kernel sums the partials in block order.
+//
+// Memory latency: a thread spends ~20k cycles of FP64 work per event and then needs 44 bytes of the
 // next one; with 4 warps per scheduler an exposed DRAM round trip (~1.5k cycles, twice: inputs at
 // the top, flux/weight/bin at the bottom) costs ~15 % (ncu, round 1 capture d).  So every thread
 // software-pipelines its own stream: at the top of an event it issues cp.async copies of (a) the
 // flux / weight / bin of THIS event, needed at the bottom, and (b) energy / coszen of its NEXT event
 // into its private shared-memory slots, and waits for them only after the propagation.  The index of
 // the event after next (`order` indirection) rides in a register.
+//
+// Registers: the propagation state (row + two column vectors) and the per-event part of the
+// Hamiltonian live in per-thread columns of shared memory, so the eigenvalue solve + matrix assembly
+// fit 128 registers (2 x 256 threads per SM) without spills or loop-carried moves.
+template <typename IO>
+struct FusedContainer {
+    const IO *energy, *coszen, *nu_flux, *weights_in;
+    const int32_t *index, *order, *d_nubar, *d_flav;
+    IO *weights_out, *prob_e, *prob_mu;
+    int64_t n;
+    double scale; // per-container factor folded into the weight (aeff.aeff: livetime * aeff_scale * norms)
+    int32_t nubar, flav;
+};
+template <typename IO>
+struct FusedBatch {
+    int32_t n_containers;
+    int32_t n_bins;
+    FusedContainer<IO> c[PISAB_MAX_BATCH];
+};
+
 template <typename IO, bool STD>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
-                     int nubar, const int32_t *__restrict__ d_nubar, int flav,
-                     const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
-                     const IO *__restrict__ coszen, const IO *__restrict__ nu_flux,
-                     const IO *__restrict__ weights_in, const int32_t *__restrict__ index,
-                     const int32_t *__restrict__ order, int64_t n,
-                     int n_bins, double *__restrict__ partials, IO *__restrict__ weights_out,
-                     IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
-    // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 18 x block]
-    // [per-thread h0 9 x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block] (int32)
+                     const __grid_constant__ FusedBatch<IO> batch, double *__restrict__ partials) {
+    // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
+    // [per-thread h0 + invariants 14 x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     extern __shared__ __align__(16) double s_hist[];
     __shared__ OscTable s_osc;
     __shared__ EarthTable s_earth;
+    const int n_bins = batch.n_bins;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
-#ifndef PISAB_STATE_REGS
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
-#endif
-#ifndef PISAB_H0_REGS
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
     s_dyn += H0Smem::kDoubles * kBlock;
-#endif
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
     WarpHist wh(s_hist, n_bins);
-    wh.clear();
     copy_tables(osc, earth, &s_osc, &s_earth);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
     // warp-uniform trip count so that the warp-collective histogram step is always converged
     const int64_t warp_first = first - (tid & 31);
-    // `order` (optional) lists the events grouped by number of crossed shells; -1 = no event
-#ifdef PISAB_NO_PREFETCH
-    // plain version (kept for A/B timing in scratch/kbench.py): loads issued where they are needed
-    for (int64_t base = warp_first; base < n; base += stride) {
-        const int64_t t = base + (tid & 31);
-        double w = 0.0;
-        int bin = -1;
-        if (t < n) {
-            const int64_t i = order ? (int64_t)__ldg(order + t) : t;
-            const double e = ld(energy, i), cz = ld(coszen, i);
-            const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
-            const int fl = d_flav ? __ldg(d_flav + i) : flav;
-            const double inv_e = rcp_fast(e);
-            H0Reg h0;
-        h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
-            if (STD) h0.set_poly();
-            Propagator<1, 2> P;
-            propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
-            const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
-            const double fe = ld(nu_flux, 2 * i), fm = ld(nu_flux, 2 * i + 1);
-            w = ld(weights_in, i) * (fe * pe + fm * pmu);
-            bin = __ldg(index + i);
-            if (weights_out) weights_out[i] = (IO)w;
-            if (prob_e) prob_e[i] = (IO)pe;
-            if (prob_mu) prob_mu[i] = (IO)pmu;
-        }
-        wh.add(bin, w);
-    }
-#else
-    // (n < 2^31 is checked by the host wrapper: 32-bit event indices save registers)
-    auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
-    int i_cur = event_of(first), i_next = event_of(first + stride);
-    if (i_cur >= 0) { s_e[tid] = __ldg(energy + i_cur); s_cz[tid] = __ldg(coszen + i_cur); }
-    for (int64_t base = warp_first; base < n; base += stride) {
-        const int64_t t = base + (tid & 31);
-        const int i_nn = event_of(t + 2 * stride);
-        double w = 0.0;
-        int bin = -1;
-        if (i_cur >= 0) {
-            const int64_t i = i_cur;
-            const double e = (double)s_e[tid], cz = (double)s_cz[tid];
-            cp_async<2 * sizeof(IO)>(&s_flux[tid][0], nu_flux + 2 * i);
-            cp_async<sizeof(IO)>(&s_w[tid], weights_in + i);
-            cp_async<4>(&s_bin[tid], index + i);
-            if (i_next >= 0) {
-                cp_async<sizeof(IO)>(&s_e[tid], energy + i_next);
-                cp_async<sizeof(IO)>(&s_cz[tid], coszen + i_next);
+
+    for (int ci = 0; ci < batch.n_containers; ++ci) {
+        const FusedContainer<IO> &C = batch.c[ci];
+        const IO *__restrict__ energy = C.energy, *__restrict__ coszen = C.coszen;
+        const IO *__restrict__ nu_flux = C.nu_flux, *__restrict__ weights_in = C.weights_in;
+        const int32_t *__restrict__ index = C.index, *__restrict__ order = C.order;
+        const int64_t n = C.n;
+        wh.clear();
+        // `order` (optional) lists the events grouped by number of crossed shells; -1 = no event
+        // (n < 2^31 is checked by the host wrapper: 32-bit event indices save registers)
+        auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
+        int i_cur = event_of(first), i_next = event_of(first + stride);
+        if (i_cur >= 0) { s_e[tid] = __ldg(energy + i_cur); s_cz[tid] = __ldg(coszen + i_cur); }
+        for (int64_t base = warp_first; base < n; base += stride) {
+            const int64_t t = base + (tid & 31);
+            const int i_nn = event_of(t + 2 * stride);
+            double w = 0.0;
+            int bin = -1;
+            if (i_cur >= 0) {
+                const int64_t i = i_cur;
+                const double e = (double)s_e[tid], cz = (double)s_cz[tid];
+                cp_async<2 * sizeof(IO)>(&s_flux[tid][0], nu_flux + 2 * i);
+                cp_async<sizeof(IO)>(&s_w[tid], weights_in + i);
+                cp_async<4>(&s_bin[tid], index + i);
+                if (i_next >= 0) {
+                    cp_async<sizeof(IO)>(&s_e[tid], energy + i_next);
+                    cp_async<sizeof(IO)>(&s_cz[tid], coszen + i_next);
+                }
+                cp_async_commit();
+                const int nb = C.d_nubar ? __ldg(C.d_nubar + i) : C.nubar;
+                const int fl = C.d_flav ? __ldg(C.d_flav + i) : C.flav;
+                const double inv_e = rcp_fast(e);
+                H0Smem h0{&s_h0[0][tid], kBlock};
+                {
+                    const Herm3 hh = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+                    h0.store(hh);
+                    if (STD) h0.set_poly(hh);
+                }
+                PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
+                propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+                const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
+                cp_async_wait_all();
+                // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
+                const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
+                w = (double)s_w[tid] * (fe * pe + fm * pmu) * C.scale;
+                bin = s_bin[tid];
+                if (C.weights_out) C.weights_out[i] = (IO)w;
+                if (C.prob_e) C.prob_e[i] = (IO)pe;
+                if (C.prob_mu) C.prob_mu[i] = (IO)pmu;
             }
-            cp_async_commit();
-            const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
-            const int fl = d_flav ? __ldg(d_flav + i) : flav;
-            const double inv_e = rcp_fast(e);
-#ifdef PISAB_H0_REGS
-            H0Reg h0;
-            h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
-            if (STD) h0.set_poly();
-#else
-            H0Smem h0{&s_h0[0][tid], kBlock};
-            {
-                const Herm3 hh = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
-                h0.store(hh);
-                if (STD) h0.set_poly(hh);
-            }
-#endif
-#ifdef PISAB_STATE_REGS
-            Propagator<1, 2> P;
-#else
-            PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
-#endif
-            propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
-            const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
-            cp_async_wait_all();
-            // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
-            const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
-            w = (double)s_w[tid] * (fe * pe + fm * pmu);
-            bin = s_bin[tid];
-            if (weights_out) weights_out[i] = (IO)w;
-            if (prob_e) prob_e[i] = (IO)pe;
-            if (prob_mu) prob_mu[i] = (IO)pmu;
+            wh.add(bin, w);
+            i_cur = i_next;
+            i_next = i_nn;
         }
-        wh.add(bin, w);
-        i_cur = i_next;
-        i_next = i_nn;
+        wh.flush(partials + ((size_t)ci * gridDim.x + blockIdx.x) * 2 * n_bins);
+        __syncthreads(); // the next container clears the bins
     }
-#endif
-    wh.flush(partials + (size_t)blockIdx.x * 2 * n_bins);
 }
 
 } // namespace pisab
@@ -393,28 +373,29 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
 }
 
 template <typename IO>
-static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
-                              int32_t nubar, const int32_t *d_nubar, int32_t flav,
-                              const int32_t *d_flav, const IO *d_energy, const IO *d_coszen,
-                              const IO *d_nu_flux, const IO *d_weights_in, const int32_t *d_index,
-                              const int32_t *d_order, int64_t n, int32_t n_bins, double *d_hist,
-                              double *d_hist_w2,
-                              IO *d_weights_out, IO *d_prob_e, IO *d_prob_mu, void *d_workspace,
-                              int64_t workspace_bytes, void *stream) {
-    if (n < 0 || n_bins < 1 || !d_hist) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
-    if (n > 0 && (!d_energy || !d_coszen || !d_nu_flux || !d_weights_in || !d_index)) {
-        set_error("bad event arrays");
-        return PISAB_ERR_ARG;
-    }
-    if (n > 2147483647LL) { set_error("at most 2^31-1 events per call (32-bit event indices)"); return PISAB_ERR_ARG; }
+static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                    const FusedBatch<IO> &batch, int64_t n_max, double *d_batch_out,
+                                    double *d_hist, double *d_hist_w2, void *d_workspace,
+                                    int64_t workspace_bytes, void *stream) {
+    const int n_bins = batch.n_bins;
+    if (n_bins < 1) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
     if (n_bins > PISAB_DET_MAX_BINS) {
         set_error("fused reweight+hist supports up to %d bins; use propagate_earth + hist_accumulate", PISAB_DET_MAX_BINS);
         return PISAB_ERR_UNSUPPORTED;
     }
-    if (!d_nubar && nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
-    if (!d_flav && (flav < 0 || flav > 2)) { set_error("flav must be 0, 1 or 2"); return PISAB_ERR_ARG; }
-    if (workspace_bytes < pisab_hist_workspace_bytes(n, n_bins) || !d_workspace) {
-        set_error("workspace too small: need %lld bytes", (long long)pisab_hist_workspace_bytes(n, n_bins));
+    for (int c = 0; c < batch.n_containers; ++c) {
+        const FusedContainer<IO> &C = batch.c[c];
+        if (C.n < 0 || (C.n > 0 && (!C.energy || !C.coszen || !C.nu_flux || !C.weights_in || !C.index))) {
+            set_error("container %d: bad event arrays", c);
+            return PISAB_ERR_ARG;
+        }
+        if (C.n > 2147483647LL) { set_error("at most 2^31-1 events per container (32-bit event indices)"); return PISAB_ERR_ARG; }
+        if (!C.d_nubar && C.nubar != 1 && C.nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
+        if (!C.d_flav && (C.flav < 0 || C.flav > 2)) { set_error("flav must be 0, 1 or 2"); return PISAB_ERR_ARG; }
+    }
+    const int64_t need = pisab_reweight_batch_workspace_bytes(batch.n_containers, n_bins);
+    if (workspace_bytes < need || !d_workspace) {
+        set_error("workspace too small: need %lld bytes", (long long)need);
         return PISAB_ERR_WORKSPACE;
     }
     OscTable ot;
@@ -426,11 +407,7 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
     cudaStream_t s = (cudaStream_t)stream;
     const size_t smem = fused_smem_bytes<IO>(n_bins);
     // standard matter potential (no NSI) -> the specialised instantiation (see H0Reg)
-#ifdef PISAB_NO_STD
-    auto kernel = reweight_hist_kernel<IO, false>;
-#else
     auto kernel = ot.std_matter != 0.0 ? reweight_hist_kernel<IO, true> : reweight_hist_kernel<IO, false>;
-#endif
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
@@ -438,16 +415,65 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
         if (fa.sharedSizeBytes + smem > 48 * 1024)
             PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = resident_grid(kernel, n, smem);
+    const int grid = resident_grid(kernel, n_max, smem);
     {
         LaunchTimer t(s);
-        kernel<<<grid, kBlock, smem, s>>>(ot, et, nubar, d_nubar, flav, d_flav, d_energy,
-                                          d_coszen, d_nu_flux, d_weights_in, d_index, d_order, n, n_bins,
-                                          (double *)d_workspace, d_weights_out, d_prob_e, d_prob_mu);
+        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, (double *)d_workspace);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
+    if (d_batch_out)
+        return hist_reduce_batch((const double *)d_workspace, grid, n_bins, batch.n_containers, d_batch_out, s);
     return hist_reduce_partials((const double *)d_workspace, grid, n_bins, d_hist, d_hist_w2, s);
+}
+
+template <typename IO>
+static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                              int32_t nubar, const int32_t *d_nubar, int32_t flav,
+                              const int32_t *d_flav, const IO *d_energy, const IO *d_coszen,
+                              const IO *d_nu_flux, const IO *d_weights_in, const int32_t *d_index,
+                              const int32_t *d_order, int64_t n, int32_t n_bins, double *d_hist,
+                              double *d_hist_w2,
+                              IO *d_weights_out, IO *d_prob_e, IO *d_prob_mu, void *d_workspace,
+                              int64_t workspace_bytes, void *stream) {
+    if (!d_hist) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
+    FusedBatch<IO> batch = {};
+    batch.n_containers = 1;
+    batch.n_bins = n_bins;
+    FusedContainer<IO> &C = batch.c[0];
+    C.energy = d_energy; C.coszen = d_coszen; C.nu_flux = d_nu_flux; C.weights_in = d_weights_in;
+    C.index = d_index; C.order = d_order; C.d_nubar = d_nubar; C.d_flav = d_flav;
+    C.weights_out = d_weights_out; C.prob_e = d_prob_e; C.prob_mu = d_prob_mu;
+    C.n = n; C.scale = 1.0; C.nubar = nubar; C.flav = flav;
+    return reweight_hist_batch_impl<IO>(consts, earth, batch, n, nullptr, d_hist, d_hist_w2, d_workspace,
+                                        workspace_bytes, stream);
+}
+
+template <typename IO>
+static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                   const pisab_container_t *containers, int32_t n_containers,
+                                   int32_t n_bins, double *d_hist, void *d_workspace,
+                                   int64_t workspace_bytes, void *stream) {
+    if (!containers || n_containers < 1 || n_containers > PISAB_MAX_BATCH || !d_hist) {
+        set_error("n_containers must be in [1, %d] and the output non-null", PISAB_MAX_BATCH);
+        return PISAB_ERR_ARG;
+    }
+    FusedBatch<IO> batch = {};
+    batch.n_containers = n_containers;
+    batch.n_bins = n_bins;
+    int64_t n_max = 0;
+    for (int c = 0; c < n_containers; ++c) {
+        const pisab_container_t &S = containers[c];
+        FusedContainer<IO> &C = batch.c[c];
+        C.energy = (const IO *)S.d_energy; C.coszen = (const IO *)S.d_coszen;
+        C.nu_flux = (const IO *)S.d_nu_flux; C.weights_in = (const IO *)S.d_weights;
+        C.index = S.d_index; C.order = S.d_order; C.d_nubar = nullptr; C.d_flav = nullptr;
+        C.weights_out = (IO *)S.d_weights_out; C.prob_e = nullptr; C.prob_mu = nullptr;
+        C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav;
+        if (S.n > n_max) n_max = S.n;
+    }
+    return reweight_hist_batch_impl<IO>(consts, earth, batch, n_max, d_hist, nullptr, nullptr, d_workspace,
+                                        workspace_bytes, stream);
 }
 
 extern "C" {
@@ -505,6 +531,21 @@ int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_
     return reweight_hist_impl<float>(consts, earth, nubar, d_nubar, flav, d_flav, d_energy, d_coszen,
                                      d_nu_flux, d_weights_in, d_index, d_order, n, n_bins, d_hist, d_hist_w2,
                                      d_weights_out, d_prob_e, d_prob_mu, d_workspace, workspace_bytes, stream);
+}
+
+int pisab_reweight_hist_batch_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                  const pisab_container_t *containers, int32_t n_containers,
+                                  int32_t n_bins, double *d_hist, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream) {
+    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                           workspace_bytes, stream);
+}
+int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                  const pisab_container_t *containers, int32_t n_containers,
+                                  int32_t n_bins, double *d_hist, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream) {
+    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                          workspace_bytes, stream);
 }
 
 } // extern "C"

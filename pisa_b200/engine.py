@@ -44,6 +44,8 @@ class ReweightEngine:
         self._out = None
         self._copy_stream = None
         self._host_out = None
+        self._batches = None
+        self._host_batches = {}
 
     # ------------------------------------------------------------------ containers -------
     def add_container(self, name, nubar, flav, true_energy, true_coszen, nu_flux, weights, index):
@@ -63,12 +65,20 @@ class ReweightEngine:
             else:
                 blk.host[k] = t.contiguous().pin_memory() if not t.is_pinned() else t
         if self.sort_events:
-            # setup-time, depends on true_coszen only (like calcLayers in prob3.setup_function):
-            # thread order that groups events by the number of Earth shells they cross
+            # setup-time, depends on true_coszen only (like calcLayers in prob3.setup_function): the events
+            # are physically re-ordered so that a warp's 32 events cross the same number of Earth shells
+            # (no divergence) AND its loads are contiguous; a histogram does not depend on the event order
             cz = blk.dev["true_coszen"] if "true_coszen" in blk.dev else blk.host["true_coszen"].to(self.device)
-            blk.order = ops.layer_order(self.earth, cz)
+            order = ops.layer_order(self.earth, cz).long()
+            for k in list(blk.dev):
+                blk.dev[k] = blk.dev[k][order].contiguous()
+            if blk.host:
+                order_h = order.cpu()
+                for k in list(blk.host):
+                    blk.host[k] = blk.host[k][order_h].contiguous().pin_memory()
         self.blocks.append(blk)
         self._out = None
+        self._batches = None
         return blk
 
     @property
@@ -81,21 +91,37 @@ class ReweightEngine:
         return self._out
 
     # ------------------------------------------------------------------- evaluation ------
-    def _launch(self, consts, blk, arrays, out_row, weights_out=None):
-        ops.reweight_hist(consts, self.earth, blk.nubar, blk.flav, arrays["true_energy"], arrays["true_coszen"],
-                          arrays["nu_flux"], arrays["weights"], arrays["index"], self.n_bins,
-                          weights_out=weights_out, hist=out_row[0], hist_w2=out_row[1], order=blk.order)
+    def set_scales(self, scales):
+        """Per-container factor folded into the weights (aeff.aeff: livetime * aeff_scale * norms)."""
+        self.scales = [float(x) for x in scales]
+        if len(self.scales) != len(self.blocks):
+            raise ValueError("one scale per container")
+        self._batches = None
+        self._host_batches = {}
+
+    def _get_batches(self):
+        if self._batches is None:
+            scales = getattr(self, "scales", None) or [1.0] * len(self.blocks)
+            self._batches = []
+            for lo in range(0, len(self.blocks), ops.MAX_BATCH):
+                chunk = self.blocks[lo:lo + ops.MAX_BATCH]
+                desc = [dict(nubar=b.nubar, flav=b.flav, energy=b.dev["true_energy"], coszen=b.dev["true_coszen"],
+                             nu_flux=b.dev["nu_flux"], weights=b.dev["weights"], index=b.dev["index"],
+                             scale=scales[lo + j]) for j, b in enumerate(chunk)]
+                self._batches.append((lo, ops.TemplateBatch(desc, self.n_bins)))
+        return self._batches
 
     def evaluate(self, consts, allreduce=True, events=None):
-        """Resident mode: all event arrays already in HBM.  Returns [n_containers, 2, n_bins].
+        """Resident mode: all event arrays already in HBM.  ONE fused launch for all containers
+        (+ one reduction of the per-block partial histograms).  Returns [n_containers, 2, n_bins].
         ``events``: optional list that receives one (start, stop) CUDA-event pair per fused
         launch (for the roofline timing in bench.py)."""
         out = self._result_buffer()
-        for i, blk in enumerate(self.blocks):
+        for lo, batch in self._get_batches():
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            self._launch(consts, blk, blk.dev, out[i])
+            ops.reweight_hist_batch(consts, self.earth, batch, out=out[lo:lo + batch.n])
             if events is not None:
                 e1.record()
                 events.append((e0, e1))
@@ -123,6 +149,7 @@ class ReweightEngine:
                     weights=torch.empty(nmax, dtype=self.tdtype, device=self.device),
                     index=torch.empty(nmax, dtype=torch.int32, device=self.device)))
             self._stages = stages
+            self._host_batches = {}
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
             self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
             for e in self._stage_free:
@@ -142,7 +169,15 @@ class ReweightEngine:
                     h2d += src.numel() * src.element_size()
                 self._stage_ready[s].record(self._copy_stream)
             main.wait_event(self._stage_ready[s])
-            self._launch(consts, blk, views, out[i])
+            batch = self._host_batches.get((i, s))
+            if batch is None:
+                scales = getattr(self, "scales", None) or [1.0] * len(self.blocks)
+                batch = ops.TemplateBatch([dict(nubar=blk.nubar, flav=blk.flav, energy=views["true_energy"],
+                                                coszen=views["true_coszen"], nu_flux=views["nu_flux"],
+                                                weights=views["weights"], index=views["index"],
+                                                scale=scales[i])], self.n_bins)
+                self._host_batches[(i, s)] = batch
+            ops.reweight_hist_batch(consts, self.earth, batch, out=out[i:i + 1])
             self._stage_free[s].record(main)
         if allreduce:
             self.allreduce(out)

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Binning, Earth, OscConsts  # noqa: F401  (re-exported)
+from ._lib import MAX_BATCH, Binning, ContainerDesc, Earth, OscConsts  # noqa: F401  (re-exported)
 
 _FLOATS = (torch.float64, torch.float32)
 
@@ -227,8 +227,8 @@ def hist_index(binning, coords, out=None):
 _workspaces = {}
 
 
-def _workspace(device, n, n_bins):
-    need = int(_lib.load().pisab_hist_workspace_bytes(n, n_bins))
+def _workspace(device, n, n_bins, n_containers=1):
+    need = int(_lib.load().pisab_reweight_batch_workspace_bytes(n_containers, n_bins))
     key = (device.index if device.index is not None else torch.cuda.current_device())
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < need:
@@ -295,6 +295,62 @@ def reweight_hist(consts, earth, nubar, flav, energy, coszen, nu_flux, weights_i
                  _ptr(coszen), _ptr(nu_flux), _ptr(weights_in), _ptr(index), _ptr(order), n, int(n_bins), _ptr(hist),
                  _ptr(hist_w2), _ptr(weights_out), _ptr(prob_e), _ptr(prob_mu), _ptr(ws), ws.numel(), _stream()))
     return hist, hist_w2
+
+
+class TemplateBatch:
+    """Descriptor array for ``reweight_hist_batch``: up to MAX_BATCH flavour containers evaluated in ONE
+    kernel launch.  Built once (the event arrays of a fit do not move); ``scale`` (the aeff.aeff
+    per-container factor) can be updated between templates with ``set_scale``."""
+
+    def __init__(self, containers, n_bins):
+        """containers: list of dicts with nubar, flav, energy, coszen, nu_flux, weights, index and optional
+        order, weights_out, scale."""
+        if not 1 <= len(containers) <= MAX_BATCH:
+            raise ValueError("a batch holds 1..%d containers" % MAX_BATCH)
+        self.n_bins = int(n_bins)
+        self.n = len(containers)
+        self.desc = (ContainerDesc * self.n)()
+        self._keep = []
+        dt = None
+        for d, c in zip(self.desc, containers):
+            e = _chk(c["energy"], "energy")
+            dt = dt or e.dtype
+            n = e.numel()
+            for nm in ("coszen", "nu_flux", "weights"):
+                _chk(c[nm], nm, dt)
+            _chk(c["index"], "index", torch.int32)
+            if c["nu_flux"].shape != (n, 2) or c["coszen"].numel() != n or c["weights"].numel() != n \
+                    or c["index"].numel() != n:
+                raise ValueError("inconsistent event array shapes")
+            order, wout = c.get("order"), c.get("weights_out")
+            _check_order(order, n)
+            _chk(wout, "weights_out", dt, allow_none=True)
+            d.d_energy, d.d_coszen = e.data_ptr(), c["coszen"].data_ptr()
+            d.d_nu_flux, d.d_weights = c["nu_flux"].data_ptr(), c["weights"].data_ptr()
+            d.d_index = c["index"].data_ptr()
+            d.d_order = 0 if order is None else order.data_ptr()
+            d.d_weights_out = 0 if wout is None else wout.data_ptr()
+            d.n, d.scale, d.nubar, d.flav = n, float(c.get("scale", 1.0)), int(c["nubar"]), int(c["flav"])
+            self._keep.append((e, c["coszen"], c["nu_flux"], c["weights"], c["index"], order, wout))
+        self.dtype = dt
+        self.device = containers[0]["energy"].device
+
+    def set_scale(self, i, scale):
+        self.desc[i].scale = float(scale)
+
+
+def reweight_hist_batch(consts, earth, batch, out=None):
+    """All containers of ``batch`` in one launch; returns ``[n_containers, 2, n_bins]`` (sum w, sum w^2)."""
+    if out is None:
+        out = torch.empty((batch.n, 2, batch.n_bins), dtype=torch.float64, device=batch.device)
+    _chk(out, "out", torch.float64)
+    if out.numel() != batch.n * 2 * batch.n_bins:
+        raise ValueError("out must hold [n_containers, 2, n_bins] doubles")
+    ws = _workspace(batch.device, 0, batch.n_bins, batch.n)
+    f = _lib.fn("pisab_reweight_hist_batch", batch.dtype)
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(out), _ptr(ws),
+                 ws.numel(), _stream()))
+    return out
 
 
 def mod_chi2(expected, expected_w2, observed):

@@ -196,3 +196,56 @@ def test_mod_chi2():
     ref = ((obs - e) ** 2 / (w2 + e)).sum()  # stats.py:674-695 with sigma^2 = sumw2
     out = ops.mod_chi2(torch.tensor(exp, device=dev), torch.tensor(w2, device=dev), torch.tensor(obs, device=dev))
     assert np.isclose(float(out), ref, rtol=1e-12)
+
+
+def test_batched_template_equals_per_container_calls():
+    """One launch over ragged containers (incl. an empty one, per-container scale, standard-matter AND NSI
+    instantiations) == the per-container calls bit for bit, and == the oracle chain within 1e-10."""
+    from pisa_b200 import ops
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    sizes = [5000, 1, 0, 777, 33, 12345, 64, 31, 2048, 9, 300, 4097]
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    for nsi in (None, syn.STD_NSI):
+        dm, mix, mat_pot = syn.osc_matrices(nsi=nsi)
+        consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+        desc, host = [], []
+        for c, ((name, nubar, flav), n) in enumerate(zip(syn.CONTAINERS, sizes)):
+            ev = syn.make_events_numpy(n, seed=50 + c)
+            t = {k: torch.tensor(v, device=dev) for k, v in ev.items()}
+            index = ops.hist_index(binning, [t["reco_energy"], t["reco_coszen"], t["pid"]]) if n else \
+                torch.empty(0, dtype=torch.int32, device=dev)
+            scale = 0.5 + 0.25 * c
+            desc.append(dict(nubar=nubar, flav=flav, energy=t["true_energy"], coszen=t["true_coszen"],
+                             nu_flux=t["nu_flux"], weights=t["weights"], index=index, scale=scale,
+                             weights_out=torch.empty(n, dtype=torch.float64, device=dev)))
+            host.append((nubar, flav, ev, index.cpu().numpy(), scale))
+        batch = ops.TemplateBatch(desc, 128)
+        out = ops.reweight_hist_batch(consts, earth, batch)
+        out2 = ops.reweight_hist_batch(consts, earth, batch)
+        assert torch.equal(out, out2)                      # run-to-run bit-reproducible
+        out = out.cpu().numpy()
+        for c, (nubar, flav, ev, idx, scale) in enumerate(host):
+            n = len(idx)
+            if n == 0:
+                assert not out[c].any()
+                continue
+            d = desc[c]
+            h, h2 = ops.reweight_hist(consts, earth, nubar, flav, d["energy"], d["coszen"], d["nu_flux"],
+                                      d["weights"], d["index"], 128)
+            # the single-container entry point has scale == 1; compare through the oracle instead
+            _, den, dis = L.calcLayers(ev["true_coszen"])
+            prob = oracle.propagate_array(dm, mix, mat_pot, -1, zero, np.zeros((3, 3)), nubar, ev["true_energy"],
+                                          den, dis)
+            w = ev["weights"] * (ev["nu_flux"][:, 0] * prob[:, 0, flav] + ev["nu_flux"][:, 1] * prob[:, 1, flav]) * scale
+            ref, ref2 = oracle.accumulate(idx, w, 128), oracle.accumulate(idx, w * w, 128)
+            assert np.allclose(out[c, 0], ref, rtol=1e-10, atol=1e-300), (c, np.abs(out[c, 0] - ref).max())
+            assert np.allclose(out[c, 1], ref2, rtol=2e-10, atol=1e-300)
+            assert np.allclose(h.cpu().numpy() * scale, out[c, 0], rtol=1e-13)
+            assert np.allclose(d["weights_out"].cpu().numpy(), w, rtol=1e-10, atol=1e-13)
+    with pytest.raises(ValueError):
+        ops.TemplateBatch(desc + desc, 128)                # more than MAX_BATCH containers
