@@ -394,6 +394,8 @@ def run_native(args):
         cpu = {"value": n_cpu / dt, "unit": UNIT, "cores": chain.threads, "kind": "port",
                "sample": "%d synthetic events, one step of the oracle port (OpenMP, %d threads)" % (n_cpu, chain.threads)}
 
+    if world > 1:
+        dist.destroy_process_group()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -401,9 +403,24 @@ def run_native(args):
             "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, n_gpu, world),
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+        return line
+    return None
+
+
+class _StdoutToStderr:
+    """Route fd 1 to stderr while libraries initialise (NCCL prints its version banner on stdout), so that
+    the ONE JSON line is the only thing this program writes to stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
 
 
 def main():
@@ -411,7 +428,10 @@ def main():
     if args.impl == "reference":
         run_reference(args)
     else:
-        run_native(args)
+        with _StdoutToStderr():
+            line = run_native(args)
+        if line is not None:
+            print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

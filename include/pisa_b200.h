@@ -242,6 +242,13 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
 int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const double *d_observed,
                    int32_t n_bins, double *d_out, void *stream);
 
+/* Scan / fit driver: sum the container maps of one template (d_hist = [n_containers][2][n_bins] as
+ * written by pisab_reweight_hist_batch_*: sum w, sum w^2), take sigma^2 = sum of the sum-w^2 maps
+ * (MapSet sum with sumw2 errors, hist.py:205-218) and evaluate mod_chi2 against d_observed.  d_total
+ * (optional, [2][n_bins]) receives the summed map and sigma^2; d_out is one double on the device. */
+int pisab_template_chi2(const double *d_hist, int32_t n_containers, int32_t n_bins,
+                        const double *d_observed, double *d_total, double *d_out, void *stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------- */
 /* Dependent-chain-free DFMA microbenchmark: runs `iters` x 8 independent FMAs per thread
  * on a full grid and returns achieved FP64 FLOP/s (synchronises). Roofline denominator. */

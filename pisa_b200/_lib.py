@@ -101,6 +101,7 @@ _UNTYPED = {
     "pisab_hist_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "pisab_template_chi2": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pisab_fp64_peak_probe": (c_i32, [c_i32, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "pisab_launch_count": (c_i64, [c_i32]),
     "pisab_set_profiling": (c_i32, [c_i32]),

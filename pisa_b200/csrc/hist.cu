@@ -246,6 +246,35 @@ mod_chi2_kernel(const double *__restrict__ expected, const double *__restrict__ 
     if (threadIdx.x == 0) out[0] = s[0];
 }
 
+// One template -> one number: total map = sum over containers (container order), sigma^2 = sum of the
+// containers' sum-w^2 maps (MapSet sum + sumw2 errors, hist.py:205-218), then mod_chi2 against `observed`.
+// Optionally writes the summed map / sigma^2 (total[2][n_bins]).
+__global__ void __launch_bounds__(256)
+template_chi2_kernel(const double *__restrict__ hist, int n_containers, int n_bins,
+                     const double *__restrict__ observed, double *__restrict__ total,
+                     double *__restrict__ out) {
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        double e = 0.0, sig2 = 0.0;
+        for (int c = 0; c < n_containers; ++c) {
+            e += hist[((size_t)c * 2) * n_bins + b];
+            sig2 += hist[((size_t)c * 2 + 1) * n_bins + b];
+        }
+        if (total) { total[b] = e; total[n_bins + b] = sig2; }
+        e = fmax(e, 1e-10);
+        const double d = observed[b] - e;
+        acc += d * d / (sig2 + e);
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = s[0];
+}
+
 static int ew_grid(int64_t n) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + 255) / 256;
@@ -425,6 +454,15 @@ int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const 
                    int32_t n_bins, double *d_out, void *stream) {
     PISAB_EW_CHECK(n_bins >= 1 && d_expected && d_observed && d_out);
     mod_chi2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_expected, d_expected_w2, d_observed, n_bins, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_template_chi2(const double *d_hist, int32_t n_containers, int32_t n_bins,
+                        const double *d_observed, double *d_total, double *d_out, void *stream) {
+    PISAB_EW_CHECK(n_bins >= 1 && n_containers >= 1 && d_hist && d_observed && d_out);
+    template_chi2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_hist, n_containers, n_bins, d_observed, d_total, d_out);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;

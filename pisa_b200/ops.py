@@ -364,6 +364,23 @@ def mod_chi2(expected, expected_w2, observed):
     return out
 
 
+def template_chi2(hist, observed, out=None, total=None):
+    """``mod_chi2`` of one template against ``observed``: ``hist`` is ``[n_containers, 2, n_bins]`` as returned
+    by ``reweight_hist_batch``; containers are summed (MapSet sum, sumw2 errors).  ``out``: 1-element
+    float64 tensor (or a view into a scan's result array); ``total``: optional ``[2, n_bins]`` output."""
+    _chk(hist, "hist", torch.float64)
+    _chk(observed, "observed", torch.float64)
+    if hist.dim() != 3 or hist.shape[1] != 2 or observed.numel() != hist.shape[2]:
+        raise ValueError("hist must be [n_containers, 2, n_bins] and observed [n_bins]")
+    if out is None:
+        out = torch.empty(1, dtype=torch.float64, device=hist.device)
+    _chk(out, "out", torch.float64)
+    _chk(total, "total", torch.float64, allow_none=True)
+    _lib.check(_lib.load().pisab_template_chi2(_ptr(hist), hist.shape[0], hist.shape[2], _ptr(observed), _ptr(total),
+                                               _ptr(out), _stream()))
+    return out
+
+
 def fp64_peak_probe(iters=20000):
     """Measured DFMA throughput of the device (FLOP/s): the FP64 roofline denominator."""
     flops, ms = ctypes.c_double(), ctypes.c_double()

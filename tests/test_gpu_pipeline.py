@@ -202,3 +202,105 @@ def test_engine_host_mode_equals_resident_mode():
     assert np.allclose(ra, ru, rtol=1e-12, atol=0)     # different thread order -> rounding only
     assert b.last_h2d_bytes == sum(blk.n for blk in b.blocks) * 44 and b.last_d2h_bytes == 5 * 2 * 128 * 8
     assert shard_slice(10, 0, 3) == (0, 4) and shard_slice(10, 2, 3) == (7, 10)
+
+
+def test_scan_chi2_matches_oracle_chain():
+    """theta23 x dm31 scan (BASELINE configs[4]): device chi2 per point == mod_chi2 of the oracle templates."""
+    _need_gpu()
+    import oracle
+    from pisa_b200 import ops, scan
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    OL = oracle.OracleLayers(np.loadtxt(PREM12), 2.0, 20.0)
+    OL.setElecFrac(0.4656, 0.4656, 0.4957)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    eng = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    host, scales = [], []
+    for i, (name, nubar, flav) in enumerate(syn.CONTAINERS[:3] + syn.CONTAINERS[6:9]):
+        ev = syn.make_events_numpy(4000 + 11 * i, seed=20 + i)
+        t = {k: torch.tensor(v, device=dev) for k, v in ev.items()}
+        idx = ops.hist_index(binning, [t["reco_energy"], t["reco_coszen"], t["pid"]])
+        eng.add_container(name, nubar, flav, t["true_energy"], t["true_coszen"], t["nu_flux"], t["weights"], idx)
+        scales.append(100.0 * (1 + 0.1 * i))
+        host.append((nubar, flav, ev, idx.cpu().numpy()))
+    eng.set_scales(scales)
+    p = syn.NUFIT20_NH
+    fixed = dict(theta12=np.deg2rad(p["theta12"]), theta13=np.deg2rad(p["theta13"]), deltacp=np.deg2rad(p["deltacp"]),
+                 dm21=p["deltam21"])
+    truth = (np.deg2rad(p["theta23"]), p["deltam31"])
+    observed = scan.asimov(eng, scan.osc_consts(theta23=truth[0], dm31=truth[1], **fixed))
+    points = [(t, d) for t in np.deg2rad([38.0, 42.3, 47.0]) for d in (2.3e-3, 2.457e-3, 2.6e-3)]
+    chi2 = scan.scan_chi2(eng, observed, points, fixed).cpu().numpy()
+
+    def oracle_template(t23, dm31):
+        c = scan.osc_consts(theta23=t23, dm31=dm31, **fixed)
+        dm = np.array(c.dm).reshape(3, 3)
+        mix = np.array(c.mix).reshape(3, 3, 2)
+        mix = mix[..., 0] + 1j * mix[..., 1]
+        mp = np.array(c.mat_pot).reshape(3, 3, 2)
+        mp = mp[..., 0] + 1j * mp[..., 1]
+        zc, zf = np.zeros((3, 3), dtype=np.complex128), np.zeros((3, 3))
+        tot, sig2 = np.zeros(128), np.zeros(128)
+        for (nubar, flav, ev, idx), sc in zip(host, scales):
+            _, den, dis = OL.calcLayers(ev["true_coszen"])
+            prob = oracle.propagate_array(dm, mix, mp, -1, zc, zf, nubar, ev["true_energy"], den, dis)
+            w = ev["weights"] * (ev["nu_flux"][:, 0] * prob[:, 0, flav] + ev["nu_flux"][:, 1] * prob[:, 1, flav]) * sc
+            tot += oracle.accumulate(idx, w, 128)
+            sig2 += oracle.accumulate(idx, w * w, 128)
+        return tot, sig2
+
+    obs_ref, _ = oracle_template(*truth)
+    assert np.allclose(observed.cpu().numpy(), obs_ref, rtol=1e-10)
+    for (t23, dm31), got in zip(points, chi2):
+        e, s2 = oracle_template(t23, dm31)
+        e = np.clip(e, 1e-10, np.inf)
+        ref = ((obs_ref - e) ** 2 / (s2 + e)).sum()      # stats.py:651-695
+        assert abs(got - ref) <= 1e-8 * max(ref, 1e-6) + 1e-12, (t23, dm31, got, ref)
+    assert chi2[4] < 1e-12 and chi2.argmin() == 4        # the true point is the minimum
+
+
+def test_grid_calc_events_apply_pipeline_matches_reference_chain():
+    """BASELINE config C2 shape: prob3 on the 200 x 200 true grid, looked up per event
+    (translation.lookup, container.binned_to_array), then aeff and the 8x8x2 histogram.  The oracle
+    chain evaluates the SAME approximation: probabilities at the grid points (weighted bin centres),
+    gathered with the reference's index rule, so parity stays at 1e-10 and indices bit-exact."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.utils import synthetic as syn
+    pipe = Pipeline("settings/pipeline/b200_icecube3y_like.cfg")
+    out = pipe.get_outputs()
+    assert out["numu_cc"].hist.shape == (8, 8, 2)
+    dm, mix, mat_pot = _matrices(pipe["prob3"])
+    L = _oracle_layers()
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    e_edges, cz_edges = np.logspace(0, 3, 201), np.linspace(-1, 1, 201)
+    e = np.sqrt(e_edges[:-1] * e_edges[1:])
+    cz = 0.5 * (cz_edges[:-1] + cz_edges[1:])
+    E, CZ = (a.ravel() for a in np.meshgrid(e, cz, indexing="ij"))
+    _, den, dis = L.calcLayers(CZ)
+    grid_prob = {nb: oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nb, E, den, dis, n_threads=os.cpu_count())
+                 for nb in (1, -1)}
+    livetime = 2.5 * 365 * 86400.0
+    for c in pipe.data.containers:
+        c.representation = "events"
+        ev = {k: c[k].cpu().numpy() for k in ("true_energy", "true_coszen", "reco_energy", "reco_coszen", "pid",
+                                               "nu_flux", "weighted_aeff", "initial_weights")}
+        nubar, flav = int(c["nubar"]), int(c["flav"])
+        # lookup_regular_2d (translation.py:427-438) on the regularised grid: log(E) x coszen
+        gi, _ = oracle.regular_index([np.log(ev["true_energy"]), ev["true_coszen"]],
+                                     [np.log(1.0), -1.0], [np.log(1000.0), 1.0], [200, 200])
+        inside = gi >= 0
+        pe = np.where(inside, grid_prob[nubar][np.clip(gi, 0, None), 0, flav], 0.0)
+        pmu = np.where(inside, grid_prob[nubar][np.clip(gi, 0, None), 1, flav], 0.0)
+        assert np.allclose(c["prob_e"].cpu().numpy(), pe, rtol=1e-10, atol=1e-12), c.name
+        w = ev["initial_weights"] * (ev["nu_flux"][:, 0] * pe + ev["nu_flux"][:, 1] * pmu)
+        w = w * (ev["weighted_aeff"] * (1.0 * livetime))
+        ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
+        i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
+        idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
+        ref = oracle.accumulate(idx, w, 128).reshape(8, 8, 2)
+        assert np.allclose(out[c.name].hist, ref, rtol=1e-10, atol=0), c.name
