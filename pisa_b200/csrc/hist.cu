@@ -8,6 +8,8 @@ namespace pisab {
 // ---------------------------------------------------------------------------------------------
 // bin index (translation.py:417-455 rule; hist.py:93-113 for irregular dims)
 // ---------------------------------------------------------------------------------------------
+constexpr int kSlotsMaxBins = 512; // above: match-based warp-private scheme
+
 struct BinningTable {
     int n_dims;
     int kind[PISAB_MAX_DIMS];
@@ -106,6 +108,83 @@ hist_accumulate_kernel(const int32_t *__restrict__ index, const IO *__restrict__
         wh.add(b, w);
     }
     wh.flush(partials + (size_t)blockIdx.x * 2 * n_bins);
+}
+
+// ---- small binnings (the analysis binnings: 8x8x2 = 128 bins): lane-replicated private bins ----
+// Every WARP owns R copies ("slots") of the bins, slot = lane % R, each entry a (sum w, sum w^2) pair:
+//     s_bins[warp][bin][slot]  (16 bytes)  ->  R * n_bins * 16 bytes per warp.
+// Lanes with different slots can never collide, so the 32 lanes are served in 32/R passes of R lanes;
+// inside a pass each lane does a plain 128-bit read-modify-write per event (LDS.128, DADD, DFMA,
+// STS.128 -- bank-conflict free: bank = 4 * slot) for all U events it has in registers, and only the
+// pass boundary needs a __syncwarp().  No match, no staging, no atomics: ~50 instructions per 32 events
+// instead of ~100 for the match-based scheme below (__match_any_sync alone costs more than a whole
+// step here; variants with match or xor-shuffle de-duplication over a slot column, and with paired
+// read-modify-writes, were measured slower: profiles/r01_hist_variants.txt), and the summation order
+// is fixed by the launch geometry alone (bit-reproducible).
+template <typename IO, int R, int U>
+__global__ void __launch_bounds__(kHistBlock)
+hist_accumulate_slots_kernel(const int32_t *__restrict__ index, const IO *__restrict__ weights, int64_t n,
+                             int n_bins, double *__restrict__ partials) {
+    extern __shared__ __align__(16) double2 s_slots[]; // [warps][n_bins][R]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    double2 *mine = s_slots + (size_t)warp * n_bins * R + (lane % R);
+    for (int i = threadIdx.x; i < n_warps * n_bins * R; i += blockDim.x) s_slots[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t warp_first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x - lane;
+    const int group = lane / R;
+    auto load_tile = [&](int64_t base, int (&b)[U], double (&w)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = base + u * stride + lane;
+            const bool ok = i < n;
+            const int bb = ok ? __ldg(index + i) : -1;
+            b[u] = (unsigned)bb < (unsigned)n_bins ? bb : -1;
+            w[u] = ok ? (weights ? (double)__ldg(weights + i) : 1.0) : 0.0;
+        }
+    };
+    auto bin_tile = [&](const int (&b)[U], const double (&w)[U]) {
+#pragma unroll
+        for (int p = 0; p < 32 / R; ++p) {
+            if (group == p) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (b[u] >= 0) {
+                        double2 *slot = mine + (size_t)b[u] * R;
+                        double2 v = *slot;
+                        v.x += w[u];
+                        v.y = fma(w[u], w[u], v.y);
+                        *slot = v;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+    };
+    // double buffered: the loads of tile k+1 are in flight while tile k is binned (the kernel is bound by
+    // DRAM latency x bytes in flight: 12 warps/SM x U x 384 B)
+    const int64_t tile = (int64_t)U * stride;
+    int b0[U], b1[U];
+    double w0[U], w1[U];
+    load_tile(warp_first, b0, w0);
+    for (int64_t base = warp_first; base < n; base += 2 * tile) { // warp-uniform trip count
+        load_tile(base + tile, b1, w1);
+        bin_tile(b0, w0);
+        load_tile(base + 2 * tile, b0, w0);
+        bin_tile(b1, w1);
+    }
+    __syncthreads();
+    // block partial: slots in ascending order, then warps in ascending order (fixed)
+    double *dst = partials + (size_t)blockIdx.x * 2 * n_bins;
+    for (int bin = threadIdx.x; bin < n_bins; bin += blockDim.x) {
+        double sw = 0.0, sw2 = 0.0;
+        for (int wp = 0; wp < n_warps; ++wp) {
+            const double2 *src = s_slots + ((size_t)wp * n_bins + bin) * R;
+            for (int r = 0; r < R; ++r) { sw += src[r].x; sw2 += src[r].y; }
+        }
+        dst[bin] = sw;
+        dst[n_bins + bin] = sw2;
+    }
 }
 
 // large binnings: global atomics (not run-to-run bit-reproducible; documented in DESIGN.md)
@@ -336,11 +415,36 @@ static int hist_accumulate_impl(const int32_t *d_index, const IO *d_weights, int
         set_error("workspace too small: need %lld bytes", (long long)pisab_hist_workspace_bytes(n, n_bins));
         return PISAB_ERR_WORKSPACE;
     }
-    const int grid = hist_grid(n);
-    const size_t smem = WarpHist::smem_bytes(kHistBlock, n_bins);
-    if (smem > 48 * 1024)
-        PISAB_CUDA_CHECK(cudaFuncSetAttribute(hist_accumulate_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    {
+    int grid;
+    if (n_bins <= kSlotsMaxBins) {
+        // replicated-slot kernel: R chosen so that a warp's bins stay <= 16 KB
+#ifndef PISAB_HIST_U
+#define PISAB_HIST_U 12
+#endif
+#ifndef PISAB_HIST_R
+#define PISAB_HIST_R 8
+#endif
+        constexpr int U = PISAB_HIST_U, R0 = PISAB_HIST_R;
+        const int R = n_bins <= 128 ? R0 : (n_bins <= 256 ? 4 : 2);
+        const size_t smem = (size_t)(kHistBlock / 32) * n_bins * R * sizeof(double2);
+        auto kernel = R == R0 ? hist_accumulate_slots_kernel<IO, R0, U>
+                              : (R == 4 ? hist_accumulate_slots_kernel<IO, 4, U> : hist_accumulate_slots_kernel<IO, 2, U>);
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kHistBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+        if (occ > 8) occ = 8; // workspace bound (pisab_hist_workspace_bytes)
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        int64_t want = (n + kHistBlock - 1) / kHistBlock;
+        if (want < 1) want = 1;
+        grid = (int)(want < (int64_t)sms * occ ? want : (int64_t)sms * occ);
+        LaunchTimer t(s);
+        kernel<<<grid, kHistBlock, smem, s>>>(d_index, d_weights, n, n_bins, (double *)d_workspace);
+        note_launch();
+    } else {
+        grid = hist_grid(n);
+        const size_t smem = WarpHist::smem_bytes(kHistBlock, n_bins);
+        if (smem > 48 * 1024)
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(hist_accumulate_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
         hist_accumulate_kernel<IO><<<grid, kHistBlock, smem, s>>>(d_index, d_weights, n, n_bins, (double *)d_workspace);
         note_launch();

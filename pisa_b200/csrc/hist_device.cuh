@@ -13,7 +13,10 @@
 
 namespace pisab {
 
-constexpr int kHistBlock = 128;
+#ifndef PISAB_HIST_BLOCK
+#define PISAB_HIST_BLOCK 128
+#endif
+constexpr int kHistBlock = PISAB_HIST_BLOCK;
 
 struct WarpHist {
     double *bins;  // this warp's [2][n_bins]: w then w^2

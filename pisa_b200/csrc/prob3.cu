@@ -34,43 +34,88 @@ __device__ __forceinline__ void copy_tables(const OscTable &osc, const EarthTabl
     __syncthreads();
 }
 
-// One thread per event, layers computed in-kernel from coszen.
+__device__ __forceinline__ void copy_earth(const EarthTable &earth, EarthTable *s_earth) {
+    const int *srci = reinterpret_cast<const int *>(&earth);
+    int *dsti = reinterpret_cast<int *>(s_earth);
+    for (int i = threadIdx.x; i < (int)(sizeof(EarthTable) / 4); i += blockDim.x) dsti[i] = srci[i];
+    __syncthreads();
+}
+
+// ---- per-thread asynchronous staging (LDGSTS): global -> shared without touching registers ----
+template <int BYTES>
+__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// One thread per event, layers computed in-kernel from coszen (osc.prob3 compute_function).
 //   FULL: probability[n,3,3] ; otherwise prob_e / prob_mu of the event's final flavour.
-template <typename IO, bool FULL>
+// Same layout as the fused kernel: propagation state and h0 in per-thread shared-memory columns, the
+// next event's energy / coszen staged by cp.async while the current one is propagated.
+template <bool FULL>
+static size_t earth_smem_bytes(size_t io_bytes) {
+    const size_t doubles = (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) +
+                                    H0Smem::kDoubles) * kBlock;
+    return doubles * sizeof(double) + 2 * (size_t)kBlock * io_bytes;
+}
+
+template <typename IO, bool FULL, bool STD>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                    int nubar, const int32_t *__restrict__ d_nubar, int flav,
                    const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
                    const IO *__restrict__ coszen, const int32_t *__restrict__ order, int64_t n,
                    IO *__restrict__ probability, IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
-    __shared__ OscTable s_osc;
+    constexpr int NR = FULL ? 3 : 1, NC = FULL ? 3 : 2;
+    extern __shared__ __align__(16) double s_dyn_earth[];
     __shared__ EarthTable s_earth;
-    copy_tables(osc, earth, &s_osc, &s_earth);
+    double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn_earth);
+    double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn_earth + PropagatorSmem<NR, NC>::kDoubles * kBlock);
+    IO *s_e = reinterpret_cast<IO *>(&s_h0[H0Smem::kDoubles][0]), *s_cz = s_e + kBlock;
+    copy_earth(earth, &s_earth);
+    const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
-        // `order` (optional) lists the events grouped by number of crossed shells so that the 32
-        // lanes of a warp walk the same number of layers; results go back to the event's own slot
-        const int64_t i = order ? (int64_t)__ldg(order + t) : t;
-        const double e = ld(energy, i), cz = ld(coszen, i);
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
+    // `order` (optional) lists the events grouped by number of crossed shells so that the 32
+    // lanes of a warp walk the same number of layers; results go back to the event's own slot
+    auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
+    int i_cur = event_of(first), i_next = event_of(first + stride);
+    if (i_cur >= 0) { s_e[tid] = __ldg(energy + i_cur); s_cz[tid] = __ldg(coszen + i_cur); }
+    for (int64_t t = first; t < n; t += stride) {
+        const int i_nn = event_of(t + 2 * stride);
+        const int64_t i = i_cur;
+        const double e = (double)s_e[tid], cz = (double)s_cz[tid];
+        if (i_next >= 0) {
+            cp_async<sizeof(IO)>(&s_e[tid], energy + i_next);
+            cp_async<sizeof(IO)>(&s_cz[tid], coszen + i_next);
+        }
+        cp_async_commit();
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
         const double inv_e = rcp_fast(e);
-        H0Reg h0;
-        h0.h = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+        H0Smem h0{&s_h0[0][tid], kBlock};
+        {
+            const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
+            h0.store(hh);
+            if (STD) h0.set_poly(hh);
+        }
+        PropagatorSmem<NR, NC> P{&s_state[0][tid], kBlock};
+        propagate_earth<NR, NC, STD>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
         if (FULL) {
-            Propagator<3, 3> P;
-            propagate_earth<3, 3, false>(h0, s_osc, s_earth, cz, inv_e, nb, 0, P);
             IO *o = probability + i * 9;
 #pragma unroll
             for (int a = 0; a < 3; ++a)
 #pragma unroll
                 for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a); // P(a->b) = |A[b][a]|^2
         } else {
-            Propagator<1, 2> P;
-            propagate_earth<1, 2, false>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
             prob_e[i] = (IO)P.prob(0, 0);
             prob_mu[i] = (IO)P.prob(0, 1);
         }
+        cp_async_wait_all();
+        i_cur = i_next;
+        i_next = i_nn;
     }
 }
 
@@ -146,15 +191,6 @@ static size_t fused_smem_bytes(int n_bins) {
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
-// ---- per-thread asynchronous staging (LDGSTS): global -> shared without touching registers ----
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // Fused template evaluation: probabilities + reweighting + weighted histogram (w, w^2), for up to
 // PISAB_MAX_BATCH flavour containers in ONE launch.
 //
@@ -196,7 +232,6 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 + invariants 14 x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     extern __shared__ __align__(16) double s_hist[];
-    __shared__ OscTable s_osc;
     __shared__ EarthTable s_earth;
     const int n_bins = batch.n_bins;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
@@ -208,7 +243,9 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
     WarpHist wh(s_hist, n_bins);
-    copy_tables(osc, earth, &s_osc, &s_earth);
+    // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
+    // DFMA takes such an operand directly); the Earth table is indexed per lane and goes to shared memory
+    copy_earth(earth, &s_earth);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
@@ -248,12 +285,12 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
                 const double inv_e = rcp_fast(e);
                 H0Smem h0{&s_h0[0][tid], kBlock};
                 {
-                    const Herm3 hh = herm_axpy(inv_e, s_osc.hv[nb > 0 ? 0 : 1], s_osc.lr);
+                    const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
                     h0.store(hh);
                     if (STD) h0.set_poly(hh);
                 }
                 PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
-                propagate_earth<1, 2, STD>(h0, s_osc, s_earth, cz, inv_e, nb, fl, P);
+                propagate_earth<1, 2, STD>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
                 const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
                 cp_async_wait_all();
                 // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
@@ -305,6 +342,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
                                 const int32_t *d_order, int64_t n, IO *d_probability, IO *d_prob_e,
                                 IO *d_prob_mu, void *stream) {
     if (n < 0 || (n > 0 && (!d_energy || !d_coszen))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if (n > 2147483647LL) { set_error("at most 2^31-1 events per call (32-bit event indices)"); return PISAB_ERR_ARG; }
     if (!d_nubar && nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
     if ((d_prob_e == nullptr) != (d_prob_mu == nullptr)) { set_error("prob_e and prob_mu go together"); return PISAB_ERR_ARG; }
     if (d_prob_e && !d_flav && (flav < 0 || flav > 2)) { set_error("flav must be 0, 1 or 2"); return PISAB_ERR_ARG; }
@@ -316,9 +354,13 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     if (rc) return rc;
     if (n == 0) return PISAB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    const bool std_matter = ot.std_matter != 0.0;
     if (d_probability) {
+        auto kernel = std_matter ? prob3_earth_kernel<IO, true, true> : prob3_earth_kernel<IO, true, false>;
+        const size_t smem = earth_smem_bytes<true>(sizeof(IO));
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
-        prob3_earth_kernel<IO, true><<<resident_grid(prob3_earth_kernel<IO, true>, n, 0), kBlock, 0, s>>>(
+        kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, d_probability, nullptr, nullptr);
         note_launch();
     }
@@ -334,8 +376,11 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
                  : pisab_fill_probs_f32((const float *)d_probability, 1, flav, n, (float *)d_prob_mu, stream);
         if (r1) return r1;
     } else if (d_prob_e) {
+        auto kernel = std_matter ? prob3_earth_kernel<IO, false, true> : prob3_earth_kernel<IO, false, false>;
+        const size_t smem = earth_smem_bytes<false>(sizeof(IO));
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
-        prob3_earth_kernel<IO, false><<<resident_grid(prob3_earth_kernel<IO, false>, n, 0), kBlock, 0, s>>>(
+        kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, nullptr, d_prob_e, d_prob_mu);
         note_launch();
     }

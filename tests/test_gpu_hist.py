@@ -249,3 +249,50 @@ def test_batched_template_equals_per_container_calls():
             assert np.allclose(d["weights_out"].cpu().numpy(), w, rtol=1e-10, atol=1e-13)
     with pytest.raises(ValueError):
         ops.TemplateBatch(desc + desc, 128)                # more than MAX_BATCH containers
+
+
+def test_full_size_properties_of_the_fused_path():
+    """BASELINE-size launch (2e7 events in one container, the per-container size of config C4 at 8 GPUs is
+    1.3e7): properties that do not need the oracle -- checksum of checksums, exact linearity under a
+    power-of-two weight scale, bit-reproducibility, invariance under event permutation (rounding only)."""
+    from pisa_b200 import ops
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    dm, mix, mat_pot = syn.osc_matrices(nsi=syn.STD_NSI)
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    n = 20_000_000
+    ev = syn.make_events_torch(n, seed=5, dtype=np.float64, device=dev)
+    # push some events out of range so that index == -1 occurs at scale
+    ev["reco_coszen"][::97] = 1.5
+    idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
+    assert int((idx < 0).sum()) >= n // 97
+    wout = torch.empty(n, dtype=torch.float64, device=dev)
+    args = (consts, earth, -1, 1, ev["true_energy"], ev["true_coszen"], ev["nu_flux"])
+    h, h2 = ops.reweight_hist(*args, ev["weights"], idx, 128, weights_out=wout)
+    inside = idx >= 0
+    # checksum of checksums: every in-range event landed in exactly one bin
+    assert abs(float(h.sum()) / float(wout[inside].sum()) - 1) < 1e-12
+    assert abs(float(h2.sum()) / float((wout[inside] ** 2).sum()) - 1) < 1e-12
+    assert float(wout.min()) >= 0.0 and torch.isfinite(wout).all()
+    # per-bin cross-check against an independent device reduction (torch index_add, plumbing only)
+    ref = torch.zeros(128, dtype=torch.float64, device=dev).index_add_(0, idx[inside].long(), wout[inside])
+    assert torch.allclose(h, ref, rtol=1e-11, atol=0)
+    # bit-reproducible, exactly linear under a power-of-two scale
+    hb, _ = ops.reweight_hist(*args, ev["weights"], idx, 128)
+    assert torch.equal(h, hb)
+    h4, h42 = ops.reweight_hist(*args, (ev["weights"] * 4.0).contiguous(), idx, 128)
+    assert torch.equal(h4, 4.0 * h) and torch.equal(h42, 16.0 * h2)
+    # permutation of the events: same histogram up to summation order
+    perm = torch.randperm(n, device=dev)
+    hp, _ = ops.reweight_hist(consts, earth, -1, 1, ev["true_energy"][perm].contiguous(),
+                              ev["true_coszen"][perm].contiguous(), ev["nu_flux"][perm].contiguous(),
+                              ev["weights"][perm].contiguous(), idx[perm].contiguous(), 128)
+    assert torch.allclose(hp, h, rtol=1e-11, atol=0)
+    # unitarity of the full matrix on 1e7 of the events
+    p, _, _ = ops.propagate_earth(consts, earth, -1, ev["true_energy"][:10_000_000].contiguous(),
+                                  ev["true_coszen"][:10_000_000].contiguous())
+    assert float((p.sum(dim=1) - 1).abs().max()) < 5e-12 and float((p.sum(dim=2) - 1).abs().max()) < 5e-12
