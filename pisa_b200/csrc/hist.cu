@@ -120,7 +120,10 @@ hist_accumulate_kernel(const int32_t *__restrict__ index, const IO *__restrict__
 // instead of ~100 for the match-based scheme below (__match_any_sync alone costs more than a whole
 // step here; variants with match or xor-shuffle de-duplication over a slot column, and with paired
 // read-modify-writes, were measured slower: profiles/r01_hist_variants.txt), and the summation order
-// is fixed by the launch geometry alone (bit-reproducible).
+// is fixed by the launch geometry alone (bit-reproducible).  A TMA-fed variant (ring of cp.async.bulk
+// tiles + mbarriers, one block per SM) was also measured: 0.49 ms vs 0.44 ms for this kernel at 1e8
+// events -- once the data delivery is solved the limit is the 2 warps per scheduler that 16 KB of private
+// bins per warp allow, so it was not kept.
 template <typename IO, int R, int U>
 __global__ void __launch_bounds__(kHistBlock)
 hist_accumulate_slots_kernel(const int32_t *__restrict__ index, const IO *__restrict__ weights, int64_t n,
@@ -279,6 +282,30 @@ lookup_kernel(const int32_t *__restrict__ index, const IO *__restrict__ flat_his
         const int w = (int)(k - i * width);
         const int b = __ldg(index + i);
         out[k] = b >= 0 ? __ldg(flat_hist + (int64_t)b * width + w) : (IO)0;
+    }
+}
+
+// width == 1 (every per-event scalar: prob_e, prob_mu, weights ...): no index arithmetic, 4 independent
+// gathers per thread in flight.  HBM-bound: 4 B in + sizeof(IO) out per event.
+template <typename IO>
+__global__ void __launch_bounds__(256)
+lookup1_kernel(const int32_t *__restrict__ index, const IO *__restrict__ flat_hist, int64_t n,
+               IO *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        int b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) b[u] = __ldg(index + i + u * stride);
+        IO v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = b[u] >= 0 ? __ldg(flat_hist + b[u]) : (IO)0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) out[i + u * stride] = v[u];
+    }
+    for (; i < n; i += stride) {
+        const int b = __ldg(index + i);
+        out[i] = b >= 0 ? __ldg(flat_hist + b) : (IO)0;
     }
 }
 
@@ -501,7 +528,8 @@ int pisab_lookup_f64(const int32_t *d_index, const double *d_flat_hist, int64_t 
                      double *d_out, void *stream) {
     PISAB_EW_CHECK(n >= 0 && width >= 1 && (n == 0 || (d_index && d_flat_hist && d_out)));
     if (n == 0) return PISAB_OK;
-    lookup_kernel<double><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
+    if (width == 1) lookup1_kernel<double><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, d_out);
+    else lookup_kernel<double><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
@@ -510,7 +538,8 @@ int pisab_lookup_f32(const int32_t *d_index, const float *d_flat_hist, int64_t n
                      float *d_out, void *stream) {
     PISAB_EW_CHECK(n >= 0 && width >= 1 && (n == 0 || (d_index && d_flat_hist && d_out)));
     if (n == 0) return PISAB_OK;
-    lookup_kernel<float><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
+    if (width == 1) lookup1_kernel<float><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, d_out);
+    else lookup_kernel<float><<<ew_grid(n * width), 256, 0, (cudaStream_t)stream>>>(d_index, d_flat_hist, n, width, d_out);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;

@@ -296,3 +296,34 @@ def test_full_size_properties_of_the_fused_path():
     p, _, _ = ops.propagate_earth(consts, earth, -1, ev["true_energy"][:10_000_000].contiguous(),
                                   ev["true_coszen"][:10_000_000].contiguous())
     assert float((p.sum(dim=1) - 1).abs().max()) < 5e-12 and float((p.sum(dim=2) - 1).abs().max()) < 5e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32, None])
+def test_large_input_histogram(dtype):
+    """3e6 events through the stand-alone histogram kernel: ragged tail, invalid and out-of-range indices,
+    all storage types.  Checked against the oracle (exact for counts) and for bit-reproducibility."""
+    from pisa_b200 import ops
+    dev = _dev()
+    n = 3_000_000 + 777
+    rng = np.random.default_rng(3)
+    idx = rng.integers(-1, 128, n).astype(np.int32)
+    idx[::1001] = 500                       # beyond the binning: must be ignored, not written
+    w = None if dtype is None else rng.uniform(0, 2, n).astype(dtype)
+    ti = torch.tensor(idx, device=dev)
+    tw = None if w is None else torch.tensor(w, device=dev)
+    h, h2 = ops.hist_accumulate(ti, tw, 128)
+    hb, h2b = ops.hist_accumulate(ti, tw, 128)
+    assert torch.equal(h, hb) and torch.equal(h2, h2b)
+    ok = (idx >= 0) & (idx < 128)
+    wd = np.ones(n) if w is None else w.astype(np.float64)
+    ref = oracle.accumulate(np.where(ok, idx, -1), wd, 128)
+    ref2 = oracle.accumulate(np.where(ok, idx, -1), wd * wd, 128)
+    if w is None:
+        assert np.array_equal(h.cpu().numpy(), ref) and np.array_equal(h2.cpu().numpy(), ref2)
+    else:
+        assert np.allclose(h.cpu().numpy(), ref, rtol=1e-11, atol=0)
+        assert np.allclose(h2.cpu().numpy(), ref2, rtol=1e-11, atol=0)
+    # an unaligned view (offset by one element)
+    h_u, _ = ops.hist_accumulate(ti[1:], None if tw is None else tw[1:], 128)
+    ref_u = oracle.accumulate(np.where(ok[1:], idx[1:], -1), wd[1:], 128)
+    assert np.allclose(h_u.cpu().numpy(), ref_u, rtol=1e-11, atol=0)
