@@ -375,9 +375,23 @@ def run_native(args):
         torch.cuda.synchronize()
         t_e2e = max_over_ranks(time.perf_counter() - t0)
         barrier()
+        # raw pinned-host -> device copy bandwidth of this box, as the yardstick for the e2e number
+        probe = torch.empty(1 << 28, dtype=torch.uint8).pin_memory()
+        probe_d = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        probe_d.copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(4):
+            probe_d.copy_(probe, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_peak = 4 * probe.numel() / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        del probe, probe_d
         e2e = {"value": n_gpu * world * args.steps / t_e2e, "unit": UNIT,
                "h2d_bytes_per_step": int(eng_host.last_h2d_bytes), "d2h_bytes_per_step": int(eng_host.last_d2h_bytes),
                "ms_per_step": 1e3 * t_e2e / args.steps,
+               "h2d_gbs": eng_host.last_h2d_bytes * args.steps / t_e2e / 1e9, "h2d_peak_gbs_measured": h2d_peak,
                "api": "pisa_b200.engine.ReweightEngine.evaluate_host (pinned host arrays, double-buffered H2D)"}
         if world == 1 and abs(float(host_out[:, 0].sum()) / hist_total - 1) > 1e-9:
             raise SystemExit("bench.py: e2e and resident histograms disagree")

@@ -154,6 +154,19 @@ int pisab_apply_osc_weights_f64(const double *d_nu_flux, const double *d_prob_e,
 int pisab_apply_osc_weights_f32(const float *d_nu_flux, const float *d_prob_e,
                                 const float *d_prob_mu, int64_t n, float *d_weights, void *stream);
 
+/* ---- flux.barr_simple (pisa/stages/flux/barr_simple.py:145-226, utils/barr_parameterization.py) ---- */
+/* apply_sys_vectorized: nu_flux[n,2] from the nominal (nue, numu) fluxes of neutrinos and antineutrinos
+ * ([n,2] each) and the five Barr-style systematic parameters; nubar = +1 / -1 is the container's aux
+ * scalar.  A "next" row of the scope table. */
+int pisab_flux_barr_simple_f64(const double *d_energy, const double *d_coszen, const double *d_nu_flux_nominal,
+                               const double *d_nubar_flux_nominal, int32_t nubar, double nue_numu_ratio,
+                               double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                               double barr_nu_nubar_ratio, int64_t n, double *d_nu_flux, void *stream);
+int pisab_flux_barr_simple_f32(const float *d_energy, const float *d_coszen, const float *d_nu_flux_nominal,
+                               const float *d_nubar_flux_nominal, int32_t nubar, double nue_numu_ratio,
+                               double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                               double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux, void *stream);
+
 /* ---- histogramming (hist.py:129-218, translation.py:90-223,417-597) -------------------- */
 /* Flat row-major bin index per event, -1 when outside in any dimension.  d_coords[d] are
  * device pointers to the n RAW sample values of dimension d (LOG dims are logged

@@ -1,0 +1,148 @@
+// flux.cu -- flux.barr_simple: Barr-style flux systematics per event.
+//
+// Reference: pisa/stages/flux/barr_simple.py:107-197 (apply_ratio_scale, spectral_index_scale,
+// apply_sys_kernel) and pisa/utils/barr_parameterization.py:17-113 (LogLogParam, norm_fcn, ModFlux,
+// modRatioUpHor, modRatioNuBar).  Per event:
+//     nue/numu ratio (sum preserving) -> spectral index (E/E0)^delta -> nu/nubar ratio (sum preserving)
+//     -> pick nu or nubar -> Barr nu/nubar modification -> Barr up/horizontal modification.
+// Every LogLogParam of the reference is s * 10^(slope * log10(E) + intercept) [* exp(-E/cutoff)] with
+// constants that do not depend on the event; they are folded on the host into BarrTable, so an event
+// costs one log10, five 10^x, two exp(-E/cutoff), two Gaussians in coszen and one pow.  With ~12 FP64
+// transcendentals per 64 bytes this kernel is FP64-bound, not HBM-bound (measured in profiles/).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace pisab {
+
+struct LogLog {
+    double sign, slope, icpt; // sign * 10^(slope * log10(E) + icpt)
+};
+struct BarrTable {
+    LogLog ave_mu, shape_mu, ave_e, shape_e, uphor_e;
+    double nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys;
+};
+
+static double sgn_h(double v) { return v == 0 ? 0.0 : (v >= 0 ? 1.0 : -1.0); }
+// barr_parameterization.py:26-35 with the event-independent part evaluated once
+static LogLog fold_loglog(double y1, double y2, double x1, double x2) {
+    LogLog r;
+    r.sign = sgn_h(y2);
+    const double Y1 = sgn_h(y1) * log10(fabs(y1) + 0.0001);
+    const double Y2 = log10(fabs(y2 + 0.0001));
+    r.slope = (Y2 - Y1) / (x2 - x1);
+    r.icpt = Y1 - 2. - r.slope * x1;
+    return r;
+}
+
+__device__ __forceinline__ double loglog(const LogLog &p, double log10e) {
+    return p.sign * exp10(fma(p.slope, log10e, p.icpt));
+}
+// barr_parameterization.py:37-40: A / sqrt(2 pi sigma^2) * exp(-x^2 / (2 sigma^2))
+__device__ __forceinline__ double norm_fcn(double x, double A, double inv_norm, double inv_2s2) {
+    return A * inv_norm * exp(-x * x * inv_2s2);
+}
+// barr_simple.py:107-136 with sum_constant = True
+__device__ __forceinline__ void ratio_scale(double scale, double in1, double in2, double &o0, double &o1) {
+    if (in1 == 0. && in2 == 0.) { o0 = 0.; o1 = 0.; return; }
+    const double orig_ratio = in1 / in2;
+    const double nw = (in1 + in2) / (1. + scale * orig_ratio);
+    o0 = scale * orig_ratio * nw;
+    o1 = nw;
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+flux_barr_simple_kernel(const __grid_constant__ BarrTable T, const IO *__restrict__ energy,
+                        const IO *__restrict__ coszen, const IO *__restrict__ nu_nom,
+                        const IO *__restrict__ nubar_nom, int nubar, int64_t n, IO *__restrict__ out) {
+    const double inv_norm36 = 1.0 / sqrt(2 * M_PI * 0.36 * 0.36), inv_2s36 = 1.0 / (2 * 0.36 * 0.36);
+    const double inv_norm35 = 1.0 / sqrt(2 * M_PI * 0.35 * 0.35), inv_2s35 = 1.0 / (2 * 0.35 * 0.35);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = (double)__ldg(energy + i), cz = (double)__ldg(coszen + i);
+        double nu0 = (double)__ldg(nu_nom + 2 * i), nu1 = (double)__ldg(nu_nom + 2 * i + 1);
+        double nb0 = (double)__ldg(nubar_nom + 2 * i), nb1 = (double)__ldg(nubar_nom + 2 * i + 1);
+        // nue/numu ratio, spectral index (apply_sys_kernel :158-176)
+        double a0, a1, b0, b1;
+        ratio_scale(T.nue_numu_ratio, nu0, nu1, a0, a1);
+        ratio_scale(T.nue_numu_ratio, nb0, nb1, b0, b1);
+        const double idx_scale = pow(e / 24.0900951261, T.delta_index);
+        a0 *= idx_scale; a1 *= idx_scale; b0 *= idx_scale; b1 *= idx_scale;
+        // nu/nubar ratio (:178-190)
+        double e_nu, e_nb, m_nu, m_nb;
+        ratio_scale(T.nu_nubar_ratio, a0, b0, e_nu, e_nb);
+        ratio_scale(T.nu_nubar_ratio, a1, b1, m_nu, m_nb);
+        double o0 = nubar < 0 ? e_nb : e_nu, o1 = nubar < 0 ? m_nb : m_nu;
+        // Barr nu/nubar (ModFlux with unit shape parameters, :42-81,106-113)
+        const double l10 = log10(e);
+        const double cut_e = exp(-e / 650.), cut_mu = exp(-e / 1000.);
+        const double gauss36 = exp(-cz * cz * inv_2s36);
+        {
+            const double A_ave = loglog(T.ave_e, l10), A_shape = loglog(T.shape_e, l10) * cut_e;
+            const double mod = T.nubar_sys * (A_ave - (1.5 * (A_shape * inv_norm36 * gauss36) - 0.7 * A_shape));
+            o0 *= nubar < 0 ? fmax(0., 1. / (1 + 0.5 * mod)) : fmax(0., 1. + 0.5 * mod);
+        }
+        {
+            const double A_ave = loglog(T.ave_mu, l10), A_shape = 2.5 * (loglog(T.shape_mu, l10) * cut_mu);
+            const double mod = T.nubar_sys * (A_ave - ((A_shape * inv_norm36 * gauss36) - 0.6 * A_shape));
+            o1 *= nubar < 0 ? fmax(0., 1. / (1 + 0.5 * mod)) : fmax(0., 1. + 0.5 * mod);
+        }
+        // Barr up/horizontal: nue only (:83-104)
+        {
+            const double A_shape = fabs(T.uphor) * (loglog(T.uphor_e, l10) * cut_e);
+            const double s = T.uphor == 0 ? 0.0 : (T.uphor > 0 ? 1.0 : -1.0);
+            o0 *= 1 - 0.3 * s * norm_fcn(cz, A_shape, inv_norm35, inv_2s35);
+        }
+        out[2 * i] = (IO)o0;
+        out[2 * i + 1] = (IO)o1;
+    }
+}
+
+template <typename IO>
+static int flux_impl(const IO *d_energy, const IO *d_coszen, const IO *d_nu, const IO *d_nubar, int32_t nubar,
+                     double nue_numu_ratio, double nu_nubar_ratio, double delta_index, double uphor,
+                     double nubar_sys, int64_t n, IO *d_out, void *stream) {
+    if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_nu || !d_nubar || !d_out))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if (nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    BarrTable T;
+    // constants of ModFlux / modRatioUpHor (barr_parameterization.py:44-61,85-94)
+    const double e1max_mu = 3., e2max_mu = 43, e1max_e = 2.5, e2max_e = 10, x1e = 0.5, x2e = 3.;
+    const double z1max_mu = 0.6, z2max_mu = 5., z1max_e = 0.3, z2max_e = 5., x1z = 0.5, x2z = 2.;
+    T.ave_mu = fold_loglog(e1max_mu, e2max_mu, x1e, x2e);
+    T.shape_mu = fold_loglog(z1max_mu, z2max_mu, x1z, x2z);
+    T.ave_e = fold_loglog(e1max_mu + e1max_e, e2max_mu + e2max_e, x1e, x2e);
+    T.shape_e = fold_loglog(z1max_mu + z1max_e, z2max_mu + z2max_e, x1z, x2z);
+    T.uphor_e = fold_loglog(z1max_e + z1max_mu, z2max_e + z2max_mu, x1z, x2z);
+    T.nue_numu_ratio = nue_numu_ratio; T.nu_nubar_ratio = nu_nubar_ratio; T.delta_index = delta_index;
+    T.uphor = uphor; T.nubar_sys = nubar_sys;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    flux_barr_simple_kernel<IO><<<grid, 256, 0, (cudaStream_t)stream>>>(T, d_energy, d_coszen, d_nu, d_nubar, nubar, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+} // namespace pisab
+
+using namespace pisab;
+
+extern "C" {
+int pisab_flux_barr_simple_f64(const double *d_energy, const double *d_coszen, const double *d_nu_flux_nominal,
+                               const double *d_nubar_flux_nominal, int32_t nubar, double nue_numu_ratio,
+                               double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                               double barr_nu_nubar_ratio, int64_t n, double *d_nu_flux, void *stream) {
+    return flux_impl<double>(d_energy, d_coszen, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio,
+                             nu_nubar_ratio, delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
+}
+int pisab_flux_barr_simple_f32(const float *d_energy, const float *d_coszen, const float *d_nu_flux_nominal,
+                               const float *d_nubar_flux_nominal, int32_t nubar, double nue_numu_ratio,
+                               double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                               double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux, void *stream) {
+    return flux_impl<float>(d_energy, d_coszen, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio,
+                            nu_nubar_ratio, delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
+}
+}

@@ -60,6 +60,29 @@ def device_info():
     return dict(sm_count=sms.value, cc=(maj.value, mnr.value))
 
 
+# ------------------------------------------------------------------------------- flux -----
+
+def flux_barr_simple(true_energy, true_coszen, nu_flux_nominal, nubar_flux_nominal, nubar, nue_numu_ratio,
+                     nu_nubar_ratio, delta_index, Barr_uphor_ratio, Barr_nu_nubar_ratio, out=None):
+    """``apply_sys_vectorized`` of flux.barr_simple (barr_simple.py:200-226): returns ``nu_flux`` [n, 2]."""
+    _chk(true_energy, "true_energy")
+    dt = true_energy.dtype
+    n = true_energy.numel()
+    for t, nm in ((true_coszen, "true_coszen"), (nu_flux_nominal, "nu_flux_nominal"),
+                  (nubar_flux_nominal, "nubar_flux_nominal")):
+        _chk(t, nm, dt)
+    if nu_flux_nominal.shape != (n, 2) or nubar_flux_nominal.shape != (n, 2) or true_coszen.numel() != n:
+        raise ValueError("inconsistent event array shapes")
+    if out is None:
+        out = torch.empty((n, 2), dtype=dt, device=true_energy.device)
+    _chk(out, "out", dt)
+    f = _lib.fn("pisab_flux_barr_simple", dt)
+    _lib.check(f(_ptr(true_energy), _ptr(true_coszen), _ptr(nu_flux_nominal), _ptr(nubar_flux_nominal), int(nubar),
+                 float(nue_numu_ratio), float(nu_nubar_ratio), float(delta_index), float(Barr_uphor_ratio),
+                 float(Barr_nu_nubar_ratio), n, _ptr(out), _stream()))
+    return out
+
+
 # ----------------------------------------------------------------------------- layers -----
 
 def layers_calc(earth, coszen):

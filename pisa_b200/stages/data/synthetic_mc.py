@@ -33,6 +33,9 @@ class synthetic_mc(Stage):  # pylint: disable=invalid-name
             ev = syn.make_events_torch(n_events, seed + i, FTYPE, dev)
             for key in ("true_energy", "true_coszen", "reco_energy", "reco_coszen", "pid", "nu_flux"):
                 container[key] = ev[key]
+            # nominal fluxes as flux.honda_ip would provide them (nu and nubar tables differ by ~20 %)
+            container["nu_flux_nominal"] = ev["nu_flux"]
+            container["nubar_flux_nominal"] = (ev["nu_flux"] * 0.8).contiguous()
             container["weighted_aeff"] = ev["weights"]
             container["initial_weights"] = ev["weights"].new_ones(n_events)
             container["weights"] = ev["weights"].new_ones(n_events)

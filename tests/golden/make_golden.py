@@ -15,6 +15,7 @@ Outputs (all small, committed):
   ref_layers_{f8,f4}.npz   reference Layers/extCalcLayers for PREM 4/12/59
   ref_params_f8.npz        OscParams / StdNSIParams matrices
   ref_hist_f8.npz          find_index / lookup_regular_* / numpy.histogramdd
+  ref_flux_{f8,f4}.npz     reference flux.barr_simple (apply_sys_vectorized) for 5 parameter sets
 The generating inputs are stored alongside the outputs, so tests never need the
 reference at run time.
 """
@@ -259,12 +260,43 @@ def gen_hist(ns):
     np.savez_compressed(os.path.join(HERE, "ref_hist_f8.npz"), **out)
 
 
+FLUX_CASES = {
+    # name: (nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio, Barr_nu_nubar_ratio)
+    "nominal": (1.0, 1.0, 0.0, 0.0, 0.0),
+    "all_up": (1.03, 0.97, 0.05, 0.3, -0.2),
+    "all_down": (0.95, 1.1, -0.1, -1.0, 1.0),
+    "uphor_only": (1.0, 1.0, 0.0, 2.0, 0.0),
+    "nubar_only": (1.0, 1.0, 0.0, 0.0, -3.0),
+}
+
+
+def gen_flux(ns, tag, n_events=1500):
+    """Reference flux.barr_simple (apply_sys_vectorized, barr_simple.py:200-226) on seeded events."""
+    ft = ns.pisa.FTYPE
+    rng = np.random.default_rng(42)
+    e = (10 ** rng.uniform(0, 3, n_events)).astype(ft)
+    cz = rng.uniform(-1, 1, n_events).astype(ft)
+    nu = rng.uniform(0.5, 1.5, (n_events, 2)).astype(ft)
+    nb = rng.uniform(0.5, 1.5, (n_events, 2)).astype(ft)
+    nu[:3] = 0.0   # the in1 == in2 == 0 branch of apply_ratio_scale
+    nb[:2] = 0.0
+    out = {"true_energy": e, "true_coszen": cz, "nu_flux_nominal": nu, "nubar_flux_nominal": nb}
+    for name, pars in FLUX_CASES.items():
+        out[name + "/params"] = np.array(pars, dtype=np.float64)
+        for nubar in (1, -1):
+            res = np.empty((n_events, 2), dtype=ft)
+            ns.barr_simple.apply_sys_vectorized(e, cz, nu, nb, nubar, *[ft(p) for p in pars], out=res)
+            out["%s/%s" % (name, "nu" if nubar > 0 else "nubar")] = res
+    np.savez_compressed(os.path.join(HERE, "ref_flux_%s.npz" % tag), **out)
+
+
 def main():
     ns = ref_loader.load()
     tag = "f4" if ns.pisa.FTYPE == np.float32 else "f8"
     gen_pickles(ns, tag)
     gen_layers(ns, tag)
     gen_prob3(ns, tag)
+    gen_flux(ns, tag)
     if tag == "f8":
         gen_params(ns)
         gen_hist(ns)

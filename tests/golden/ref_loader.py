@@ -14,6 +14,7 @@ reference *files* are symlinked into it (never copied into this repo):
     pisa/stages/osc/prob3numba/numba_osc_kernels.py, numba_osc_hostfuncs.py
     pisa/stages/osc/layers.py, osc_params.py, nsi_params.py
     pisa/core/translation.py, bin_indexing.py   (binning / fast_histogram stubbed)
+    pisa/stages/flux/barr_simple.py, pisa/utils/barr_parameterization.py   (Stage / Param stubbed)
 
 The float type is fixed at import time by the reference (``PISA_FTYPE``), so
 FP32 fixtures are produced in a separate process.
@@ -74,6 +75,9 @@ def from_file(fname, as_array=False, **kw):
 ''',
     "pisa/utils/profiler.py": "def profile(f): return f\n",
     "pisa/core/binning.py": "class OneDimBinning: pass\nclass MultiDimBinning: pass\n",
+    "pisa/stages/flux/__init__.py": "",
+    "pisa/core/param.py": "class Param:\n    def __init__(self, **k): pass\nclass ParamSet(list):\n    pass\n",
+    "pisa/core/stage.py": "class Stage:\n    def __init__(self, **k): pass\n",
     "fast_histogram/__init__.py": "",
 }
 
@@ -86,6 +90,8 @@ _LINKS = [
     "pisa/stages/osc/nsi_params.py",
     "pisa/core/translation.py",
     "pisa/core/bin_indexing.py",
+    "pisa/utils/barr_parameterization.py",
+    "pisa/stages/flux/barr_simple.py",
 ]
 
 _loaded = None
@@ -130,6 +136,7 @@ def load():
     ns.nsi_params = importlib.import_module("pisa.stages.osc.nsi_params")
     ns.translation = importlib.import_module("pisa.core.translation")
     ns.bin_indexing = importlib.import_module("pisa.core.bin_indexing")
+    ns.barr_simple = importlib.import_module("pisa.stages.flux.barr_simple")
     ns.resources = os.path.join(REFERENCE_ROOT, "pisa_examples", "resources")
     _loaded = ns
     return ns

@@ -1,0 +1,80 @@
+"""GPU parity tests of flux.barr_simple: CUDA kernel vs the reference fixtures and the oracle."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from conftest import load_golden  # noqa: E402
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def test_flux_barr_simple_vs_reference_fixture():
+    """every fixture case (5 systematic settings x nu/nubar) produced by the unmodified reference."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_flux_f8.npz")
+    T = lambda k: torch.tensor(g[k], device=dev)  # noqa: E731
+    e, cz, nu, nb = T("true_energy"), T("true_coszen"), T("nu_flux_nominal"), T("nubar_flux_nominal")
+    for name in sorted({k.split("/")[0] for k in g.files if "/" in k}):
+        pars = [float(x) for x in g[name + "/params"]]
+        for nubar, tag in ((1, "nu"), (-1, "nubar")):
+            out = ops.flux_barr_simple(e, cz, nu, nb, nubar, *pars).cpu().numpy()
+            ref = g["%s/%s" % (name, tag)]
+            assert np.allclose(out, ref, rtol=1e-10, atol=1e-300), (name, tag, np.abs(out - ref).max())
+            assert np.array_equal(out == 0, ref == 0)      # the zero-flux branch of apply_ratio_scale
+    # FP32 storage mode against the reference's f4 fixture
+    g4 = load_golden("ref_flux_f4.npz")
+    T4 = lambda k: torch.tensor(g4[k], device=dev)  # noqa: E731
+    out = ops.flux_barr_simple(T4("true_energy"), T4("true_coszen"), T4("nu_flux_nominal"), T4("nubar_flux_nominal"),
+                               -1, *[float(x) for x in g4["all_down/params"]]).cpu().numpy()
+    assert out.dtype == np.float32 and np.allclose(out, g4["all_down/nubar"], rtol=2e-5, atol=1e-6)
+
+
+def test_flux_barr_simple_large_random_vs_oracle():
+    from pisa_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(9)
+    n = 300_000
+    e = 10 ** rng.uniform(0, 4, n)
+    cz = rng.uniform(-1, 1, n)
+    nu, nb = rng.uniform(0.0, 2.0, (n, 2)), rng.uniform(0.0, 2.0, (n, 2))
+    for pars in ((1.2, 0.8, 0.2, -2.5, 2.0), (0.7, 1.3, -0.3, 1.7, -4.0)):
+        for nubar in (1, -1):
+            ref = oracle.flux_barr_simple(e, cz, nu, nb, nubar, *pars)
+            out = ops.flux_barr_simple(*(torch.tensor(a, device=dev) for a in (e, cz, nu, nb)), nubar, *pars)
+            assert np.allclose(out.cpu().numpy(), ref, rtol=1e-10, atol=1e-300)
+    with pytest.raises(ValueError):
+        ops.flux_barr_simple(torch.tensor(e, device=dev), torch.tensor(cz[:-1], device=dev),
+                             torch.tensor(nu, device=dev), torch.tensor(nb, device=dev), 1, 1, 1, 0, 0, 0)
+
+
+def test_flux_stage_in_a_pipeline():
+    """flux.barr_simple selected from a cfg: nu_flux follows the systematic parameters and feeds prob3."""
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.utils.units import ureg
+    _dev()
+    pipe = Pipeline("settings/pipeline/b200_flux_events.cfg")
+    assert [s.service_name for s in pipe.stages] == ["synthetic_mc", "barr_simple", "prob3", "aeff", "hist"]
+    out0 = pipe.get_outputs()
+    c = pipe.data["numu_cc"]
+    c.representation = "events"
+    got = c["nu_flux"].cpu().numpy()
+    ref = oracle.flux_barr_simple(c["true_energy"].cpu().numpy(), c["true_coszen"].cpu().numpy(),
+                                  c["nu_flux_nominal"].cpu().numpy(), c["nubar_flux_nominal"].cpu().numpy(), 1,
+                                  1.0, 1.0, 0.0, 0.0, 0.0)
+    assert np.allclose(got, ref, rtol=1e-10)
+    pipe.params.delta_index = 0.1 * ureg.dimensionless
+    out1 = pipe.get_outputs()
+    assert not np.allclose(out1["numu_cc"].hist, out0["numu_cc"].hist, rtol=1e-4)
+    c.representation = "events"
+    ref1 = oracle.flux_barr_simple(c["true_energy"].cpu().numpy(), c["true_coszen"].cpu().numpy(),
+                                   c["nu_flux_nominal"].cpu().numpy(), c["nubar_flux_nominal"].cpu().numpy(), 1,
+                                   1.0, 1.0, 0.1, 0.0, 0.0)
+    assert np.allclose(c["nu_flux"].cpu().numpy(), ref1, rtol=1e-10)

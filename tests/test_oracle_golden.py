@@ -239,3 +239,23 @@ def test_digitize_irregular_matches_numpy():
     ref = np.searchsorted(edges, x, side="right") - 1
     ref[x == edges[-1]] -= 1
     assert np.array_equal(oracle.digitize_irregular(x, edges), ref)
+
+
+def test_flux_barr_simple_oracle_matches_reference():
+    """oracle.flux_barr_simple vs the unmodified reference's apply_sys_vectorized
+    (pisa/stages/flux/barr_simple.py:200-226) for 5 systematic settings x {nu, nubar}."""
+    g = load_golden("ref_flux_f8.npz")
+    cases = sorted({k.split("/")[0] for k in g.files if "/" in k})
+    assert len(cases) == 5
+    for name in cases:
+        pars = g[name + "/params"]
+        for nubar, tag in ((1, "nu"), (-1, "nubar")):
+            out = oracle.flux_barr_simple(g["true_energy"], g["true_coszen"], g["nu_flux_nominal"],
+                                          g["nubar_flux_nominal"], nubar, *pars)
+            ref = g["%s/%s" % (name, tag)]
+            assert np.allclose(out, ref, rtol=1e-13, atol=1e-300), (name, tag, np.abs(out / np.where(ref == 0, 1, ref) - 1).max())
+    # FP32 fixture: float32 storage of the same arithmetic
+    g4 = load_golden("ref_flux_f4.npz")
+    out = oracle.flux_barr_simple(g4["true_energy"], g4["true_coszen"], g4["nu_flux_nominal"],
+                                  g4["nubar_flux_nominal"], 1, *g4["all_up/params"])
+    assert np.allclose(out, g4["all_up/nu"], rtol=2e-5, atol=1e-6)
