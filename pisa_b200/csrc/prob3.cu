@@ -55,9 +55,9 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // Same layout as the fused kernel: propagation state and h0 in per-thread shared-memory columns, the
 // next event's energy / coszen staged by cp.async while the current one is propagated.
 template <bool FULL>
-static size_t earth_smem_bytes(size_t io_bytes) {
+static size_t earth_smem_bytes(size_t io_bytes, bool std_matter) {
     const size_t doubles = (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) +
-                                    H0Smem::kDoubles) * kBlock;
+                                    (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return doubles * sizeof(double) + 2 * (size_t)kBlock * io_bytes;
 }
 
@@ -73,7 +73,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
     __shared__ EarthTable s_earth;
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn_earth);
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn_earth + PropagatorSmem<NR, NC>::kDoubles * kBlock);
-    IO *s_e = reinterpret_cast<IO *>(&s_h0[H0Smem::kDoubles][0]), *s_cz = s_e + kBlock;
+    IO *s_e = reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]), *s_cz = s_e + kBlock;
     copy_earth(earth, &s_earth);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -95,7 +95,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
         const double inv_e = rcp_fast(e);
-        H0Smem h0{&s_h0[0][tid], kBlock};
+        H0Smem<STD> h0{&s_h0[0][tid], kBlock};
         {
             const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
             h0.store(hh);
@@ -186,8 +186,9 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
-static size_t fused_smem_bytes(int n_bins) {
-    const size_t doubles = (size_t)(PropagatorSmem<1, 2>::kDoubles + H0Smem::kDoubles) * kBlock;
+static size_t fused_smem_bytes(int n_bins, bool std_matter) {
+    const size_t doubles = (size_t)(PropagatorSmem<1, 2>::kDoubles +
+                                    (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
@@ -238,7 +239,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
-    s_dyn += H0Smem::kDoubles * kBlock;
+    s_dyn += H0Smem<STD>::kDoubles * kBlock;
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
@@ -283,7 +284,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
                 const int nb = C.d_nubar ? __ldg(C.d_nubar + i) : C.nubar;
                 const int fl = C.d_flav ? __ldg(C.d_flav + i) : C.flav;
                 const double inv_e = rcp_fast(e);
-                H0Smem h0{&s_h0[0][tid], kBlock};
+                H0Smem<STD> h0{&s_h0[0][tid], kBlock};
                 {
                     const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
                     h0.store(hh);
@@ -356,8 +357,9 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     cudaStream_t s = (cudaStream_t)stream;
     const bool std_matter = ot.std_matter != 0.0;
     if (d_probability) {
-        auto kernel = std_matter ? prob3_earth_kernel<IO, true, true> : prob3_earth_kernel<IO, true, false>;
-        const size_t smem = earth_smem_bytes<true>(sizeof(IO));
+        // the 3x3 state (74 KB per block) leaves no room for the cached H0^2 of the standard-matter path
+        auto kernel = prob3_earth_kernel<IO, true, false>;
+        const size_t smem = earth_smem_bytes<true>(sizeof(IO), false);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
         kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
@@ -377,7 +379,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
         if (r1) return r1;
     } else if (d_prob_e) {
         auto kernel = std_matter ? prob3_earth_kernel<IO, false, true> : prob3_earth_kernel<IO, false, false>;
-        const size_t smem = earth_smem_bytes<false>(sizeof(IO));
+        const size_t smem = earth_smem_bytes<false>(sizeof(IO), std_matter);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
         kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
@@ -450,9 +452,14 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     rc = build_earth_table(earth, &et);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t smem = fused_smem_bytes<IO>(n_bins);
     // standard matter potential (no NSI) -> the specialised instantiation (see H0Reg)
-    auto kernel = ot.std_matter != 0.0 ? reweight_hist_kernel<IO, true> : reweight_hist_kernel<IO, false>;
+#ifdef PISAB_NO_STD
+    const bool std_matter = false;
+#else
+    const bool std_matter = ot.std_matter != 0.0;
+#endif
+    const size_t smem = fused_smem_bytes<IO>(n_bins, std_matter);
+    auto kernel = std_matter ? reweight_hist_kernel<IO, true> : reweight_hist_kernel<IO, false>;
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;

@@ -224,17 +224,15 @@ __device__ __forceinline__ void char_poly(const Herm3 &h, double &c2, double &c1
     c0 = fma(h.d0, n12, fma(h.d1, n02, h.d2 * n01)) - 2.0 * rpa - h.d0 * h.d1 * h.d2;
 }
 
-// T = exp(-i h t) up to a global phase, given the characteristic polynomial of h.
-// `h` in eV^2/GeV, t = 2 * 2.534 * distance[km].
-__device__ __forceinline__ void transition_matrix(const Herm3 &h, double c2, double c1, double c0, double t,
-                                                  Mat3 T) {
-    const double n01 = fma(h.r01, h.r01, h.i01 * h.i01);
-    const double n02 = fma(h.r02, h.r02, h.i02 * h.i02);
-    const double n12 = fma(h.r12, h.r12, h.i12 * h.i12);
-    const double ur = fma(h.r01, h.r12, -h.i01 * h.i12); // h01*h12
-    const double ui = fma(h.r01, h.i12, h.i01 * h.r12);
-
-    // ---- roots (:766-814): p, q and the cancellation-safe p^3 - q^2
+// Roots of x^3 + c2 x^2 + c1 x + c0 (three real roots: the matrix is Hermitian) and the Lagrange
+// denominators, numba_osc_kernels.py:766-814 / :870-872.  They depend on the layer's density but not on
+// its length, so the two pieces of the detector shell share one solve.
+struct Eigen {
+    double l0, l1, l2;    // ascending
+    double id0, id1, id2; // 1 / prod_{j != k} (l_k - l_j)
+};
+__device__ __forceinline__ Eigen eigen_solve(double c2, double c1, double c0) {
+    // p, q and the cancellation-safe p^3 - q^2
     double p = fma(c2, c2, -3.0 * c1);
     p = fmax(p, 0.0);
     const double q = fma(4.5 * c1, c2, fma(-13.5, c0, -c2 * c2 * c2));
@@ -250,63 +248,85 @@ __device__ __forceinline__ void transition_matrix(const Herm3 &h, double c2, dou
     // theta = atan2(sqrt(disc), q) / 3 in [0, pi/3]
     unit_cube_root(p_ok ? q * inv : 1.0, p_ok ? sqrt_fast(disc) * inv : 0.0, &ct, &st);
     const double kh = 0.5, ks = kTab[15]; // cos, sin of pi/3
+    Eigen e;
     // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
-    const double l0 = fma(b, -kh * ct - ks * st, base);
-    const double l1 = fma(b, -kh * ct + ks * st, base);
-    const double l2 = fma(b, ct, base);
-
-    // ---- Lagrange weights with the global phase exp(-i l2 t) dropped
-    const double g01 = l0 - l1, g02 = l0 - l2, g12 = l1 - l2;
+    e.l0 = fma(b, -kh * ct - ks * st, base);
+    e.l1 = fma(b, -kh * ct + ks * st, base);
+    e.l2 = fma(b, ct, base);
+    const double g01 = e.l0 - e.l1, g02 = e.l0 - e.l2, g12 = e.l1 - e.l2;
     const double inv_g = rcp_fast(g01 * g02 * g12);
-    const double id0 = g12 * inv_g;  // 1/((l0-l1)(l0-l2))
-    const double id1 = -g02 * inv_g; // 1/((l1-l0)(l1-l2))
-    const double id2 = g01 * inv_g;  // 1/((l2-l0)(l2-l1))
+    e.id0 = g12 * inv_g;  // 1/((l0-l1)(l0-l2))
+    e.id1 = -g02 * inv_g; // 1/((l1-l0)(l1-l2))
+    e.id2 = g01 * inv_g;  // 1/((l2-l0)(l2-l1))
+    return e;
+}
+
+// H^2 of a Hermitian 3x3, packed like H (diagonal real, upper triangle complex)
+__device__ __forceinline__ Herm3 herm_square(const Herm3 &h) {
+    const double n01 = fma(h.r01, h.r01, h.i01 * h.i01);
+    const double n02 = fma(h.r02, h.r02, h.i02 * h.i02);
+    const double n12 = fma(h.r12, h.r12, h.i12 * h.i12);
+    const double t01 = h.d0 + h.d1, t02 = h.d0 + h.d2, t12 = h.d1 + h.d2;
+    Herm3 s;
+    s.d0 = fma(h.d0, h.d0, n01 + n02);
+    s.d1 = fma(h.d1, h.d1, n01 + n12);
+    s.d2 = fma(h.d2, h.d2, n02 + n12);
+    s.r01 = fma(h.r01, t01, fma(h.r02, h.r12, h.i02 * h.i12));
+    s.i01 = fma(h.i01, t01, fma(h.i02, h.r12, -h.r02 * h.i12));
+    s.r02 = fma(h.r02, t02, fma(h.r01, h.r12, -h.i01 * h.i12));
+    s.i02 = fma(h.i02, t02, fma(h.r01, h.i12, h.i01 * h.r12));
+    s.r12 = fma(h.r12, t12, fma(h.r01, h.r02, h.i01 * h.i02));
+    s.i12 = fma(h.i12, t12, fma(h.r01, h.i02, -h.i01 * h.r02));
+    return s;
+}
+
+// T = exp(-i H t) up to a global phase, H = h + x e00 e00^T, from the roots of H, h and h^2.
+// exp(-iHt) = a0 + a1 H + a2 H^2 (Cayley-Hamilton form of the Lagrange sum :481-531,834-872) and
+//     H^2 = h^2 + x (e00 h + h e00) + x^2 e00 ,
+// so only row / column 0 see the shift: with b1 = a1 + a2 x they use (b1, a2) where the rest uses (a1, a2).
+// SHIFT = false (x == 0): h, hsq are the layer's own H and H^2.  `t` = 2 * 2.534 * distance[km].
+template <bool SHIFT>
+__device__ __forceinline__ void assemble_transition(const Herm3 &h, const Herm3 &hsq, double x, const Eigen &e,
+                                                    double t, Mat3 T) {
+    // ---- Lagrange weights with the global phase exp(-i l2 t) dropped
     double s0, k0, s1, k1;
-    sincos_small(-g02 * t, &s0, &k0); // exp(-i (l0-l2) t)
-    sincos_small(-g12 * t, &s1, &k1); // exp(-i (l1-l2) t)
-    const Cplx w0{k0 * id0, s0 * id0};
-    const Cplx w1{k1 * id1, s1 * id1};
-    const double w2 = id2;
-    // exp(-iHt) = a0 + a1 H + a2 H^2
-    const double m12 = l1 + l2, m02 = l0 + l2, m01 = l0 + l1;
-    const double p12 = l1 * l2, p02 = l0 * l2, p01 = l0 * l1;
+    sincos_small((e.l2 - e.l0) * t, &s0, &k0); // exp(-i (l0-l2) t)
+    sincos_small((e.l2 - e.l1) * t, &s1, &k1); // exp(-i (l1-l2) t)
+    const Cplx w0{k0 * e.id0, s0 * e.id0};
+    const Cplx w1{k1 * e.id1, s1 * e.id1};
+    const double w2 = e.id2;
+    const double m12 = e.l1 + e.l2, m02 = e.l0 + e.l2, m01 = e.l0 + e.l1;
+    const double p12 = e.l1 * e.l2, p02 = e.l0 * e.l2, p01 = e.l0 * e.l1;
     const Cplx a2{w0.re + w1.re + w2, w0.im + w1.im};
     const Cplx a1{-fma(w0.re, m12, fma(w1.re, m02, w2 * m01)), -fma(w0.im, m12, w1.im * m02)};
     const Cplx a0{fma(w0.re, p12, fma(w1.re, p02, w2 * p01)), fma(w0.im, p12, w1.im * p02)};
-
-    // ---- H^2 (Hermitian)
-    const double q0 = fma(h.d0, h.d0, n01 + n02);
-    const double q1 = fma(h.d1, h.d1, n01 + n12);
-    const double q2 = fma(h.d2, h.d2, n02 + n12);
-    const double t01 = h.d0 + h.d1, t02 = h.d0 + h.d2, t12 = h.d1 + h.d2;
-    const double s01r = fma(h.r01, t01, fma(h.r02, h.r12, h.i02 * h.i12));
-    const double s01i = fma(h.i01, t01, fma(h.i02, h.r12, -h.r02 * h.i12));
-    const double s02r = fma(h.r02, t02, ur);
-    const double s02i = fma(h.i02, t02, ui);
-    const double s12r = fma(h.r12, t12, fma(h.r01, h.r02, h.i01 * h.i02));
-    const double s12i = fma(h.i12, t12, fma(h.r01, h.i02, -h.i01 * h.r02));
+    const Cplx b1 = SHIFT ? Cplx{fma(a2.re, x, a1.re), fma(a2.im, x, a1.im)} : a1;
+    const double d0 = SHIFT ? h.d0 + x : h.d0;
+    const double q0 = SHIFT ? fma(x, fma(2.0, h.d0, x), hsq.d0) : hsq.d0;
 
     // ---- assemble T
-    T[0][0] = Cplx{fma(a2.re, q0, fma(a1.re, h.d0, a0.re)), fma(a2.im, q0, fma(a1.im, h.d0, a0.im))};
-    T[1][1] = Cplx{fma(a2.re, q1, fma(a1.re, h.d1, a0.re)), fma(a2.im, q1, fma(a1.im, h.d1, a0.im))};
-    T[2][2] = Cplx{fma(a2.re, q2, fma(a1.re, h.d2, a0.re)), fma(a2.im, q2, fma(a1.im, h.d2, a0.im))};
-#define PISAB_OFFDIAG(I, J, RE, IM, SR, SI)                                   \
+    T[0][0] = Cplx{fma(a2.re, q0, fma(a1.re, d0, a0.re)), fma(a2.im, q0, fma(a1.im, d0, a0.im))};
+    T[1][1] = Cplx{fma(a2.re, hsq.d1, fma(a1.re, h.d1, a0.re)), fma(a2.im, hsq.d1, fma(a1.im, h.d1, a0.im))};
+    T[2][2] = Cplx{fma(a2.re, hsq.d2, fma(a1.re, h.d2, a0.re)), fma(a2.im, hsq.d2, fma(a1.im, h.d2, a0.im))};
+#define PISAB_OFFDIAG(I, J, C1, RE, IM, SR, SI)                               \
     {                                                                         \
-        const double xr = fma(a2.re, SR, a1.re * RE), xi = fma(a2.im, SR, a1.im * RE); \
-        const double yr = fma(a2.re, SI, a1.re * IM), yi = fma(a2.im, SI, a1.im * IM); \
+        const double xr = fma(a2.re, SR, C1.re * RE), xi = fma(a2.im, SR, C1.im * RE); \
+        const double yr = fma(a2.re, SI, C1.re * IM), yi = fma(a2.im, SI, C1.im * IM); \
         T[I][J] = Cplx{xr - yi, xi + yr};                                     \
         T[J][I] = Cplx{xr + yi, xi - yr};                                     \
     }
-    PISAB_OFFDIAG(0, 1, h.r01, h.i01, s01r, s01i)
-    PISAB_OFFDIAG(0, 2, h.r02, h.i02, s02r, s02i)
-    PISAB_OFFDIAG(1, 2, h.r12, h.i12, s12r, s12i)
+    PISAB_OFFDIAG(0, 1, b1, h.r01, h.i01, hsq.r01, hsq.i01)
+    PISAB_OFFDIAG(0, 2, b1, h.r02, h.i02, hsq.r02, hsq.i02)
+    PISAB_OFFDIAG(1, 2, a1, h.r12, h.i12, hsq.r12, hsq.i12)
 #undef PISAB_OFFDIAG
 }
 
+// T = exp(-i h t) up to a global phase.  `h` in eV^2/GeV, t = 2 * 2.534 * distance[km].
 __device__ __forceinline__ void transition_matrix(const Herm3 &h, double t, Mat3 T) {
     double c2, c1, c0;
     char_poly(h, c2, c1, c0);
-    transition_matrix(h, c2, c1, c0, t, T);
+    const Eigen e = eigen_solve(c2, c1, c0);
+    assemble_transition<false>(h, herm_square(h), 0.0, e, t, T);
 }
 
 // ---- small dense helpers on NR x 3 / 3 x NC blocks ----------------------------------------
@@ -530,13 +550,15 @@ __device__ __forceinline__ void vacuum_columns(const OscTable &o, double ts, PRO
 //     c2 = c2_0 - x ,  c1 = c1_0 + x (d1 + d2) ,  c0 = c0_0 - x (d1 d2 - |h12|^2)
 // so the provider also keeps the 5 per-event invariants and a layer costs 3 FMAs instead of 17 + 9.
 struct H0Reg {
-    Herm3 h;
+    Herm3 h, hsq;
     double inv[5]; // c2_0, c1_0, c0_0, d1 + d2, d1 d2 - |h12|^2 (only set by set_poly)
     __device__ __forceinline__ Herm3 load() const { return h; }
+    __device__ __forceinline__ Herm3 load_sq() const { return hsq; }
     __device__ __forceinline__ void set_poly() {
         char_poly(h, inv[0], inv[1], inv[2]);
         inv[3] = h.d1 + h.d2;
         inv[4] = fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12));
+        hsq = herm_square(h);
     }
     __device__ __forceinline__ void poly(double x, double &c2, double &c1, double &c0) const {
         c2 = inv[0] - x;
@@ -544,10 +566,11 @@ struct H0Reg {
         c0 = fma(-x, inv[4], inv[2]);
     }
 };
+template <bool STD>
 struct H0Smem {
-    double *col; // &s_h0[0][threadIdx.x], 14 rows: h0 (9) + invariants (5)
+    double *col; // &s_h0[0][threadIdx.x]; rows: h0 (9) [+ invariants (5) + h0^2 (9) when STD]
     int pitch;   // block size
-    static constexpr int kDoubles = 14;
+    static constexpr int kDoubles = STD ? 23 : 9;
     __device__ __forceinline__ void store(const Herm3 &h) {
         col[0] = h.d0; col[pitch] = h.d1; col[2 * pitch] = h.d2;
         col[3 * pitch] = h.r01; col[4 * pitch] = h.i01; col[5 * pitch] = h.r02;
@@ -566,6 +589,17 @@ struct H0Smem {
         col[9 * pitch] = c2; col[10 * pitch] = c1; col[11 * pitch] = c0;
         col[12 * pitch] = h.d1 + h.d2;
         col[13 * pitch] = fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12));
+        const Herm3 s = herm_square(h);
+        col[14 * pitch] = s.d0; col[15 * pitch] = s.d1; col[16 * pitch] = s.d2;
+        col[17 * pitch] = s.r01; col[18 * pitch] = s.i01; col[19 * pitch] = s.r02;
+        col[20 * pitch] = s.i02; col[21 * pitch] = s.r12; col[22 * pitch] = s.i12;
+    }
+    __device__ __forceinline__ Herm3 load_sq() const {
+        Herm3 s;
+        s.d0 = col[14 * pitch]; s.d1 = col[15 * pitch]; s.d2 = col[16 * pitch];
+        s.r01 = col[17 * pitch]; s.i01 = col[18 * pitch]; s.r02 = col[19 * pitch];
+        s.i02 = col[20 * pitch]; s.r12 = col[21 * pitch]; s.i12 = col[22 * pitch];
+        return s;
     }
     __device__ __forceinline__ void poly(double x, double &c2, double &c1, double &c0) const {
         c2 = col[9 * pitch] - x;
@@ -643,17 +677,19 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
                 ++j;
             }
         }
+        // (Sharing one eigenvalue solve between the two pieces of the detector shell -- same density,
+        // different lengths -- was tried: the solve's results have to stay live across the second
+        // assembly, which costs 120 B of spills and 9 % of the kernel; not kept.)
         const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
         if (seg > 0.0) {
             Mat3 T;
             if (STD) {
-                // standard matter: only H[0][0] moves with the density (see H0Reg)
+                // standard matter: only H[0][0] moves with the density (see H0Reg); H0 and H0^2 are per-event
                 const double x = E.rho[rho_shell] * vm.d0;
-                Herm3 h = h0.load();
-                h.d0 += x;
                 double c2, c1, c0;
                 h0.poly(x, c2, c1, c0);
-                transition_matrix(h, c2, c1, c0, T_SCALE * seg, T);
+                const Eigen eig = eigen_solve(c2, c1, c0);
+                assemble_transition<true>(h0.load(), h0.load_sq(), x, eig, T_SCALE * seg, T);
             } else {
                 transition_matrix(herm_axpy(E.rho[rho_shell], vm, h0.load()), T_SCALE * seg, T);
             }

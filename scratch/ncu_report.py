@@ -86,10 +86,10 @@ with open(os.path.join(P, "%s_launches.csv" % name), "w") as f:
     f.write("kernel,launches,total_us,share_pct,avg_us\n")
     for k, v in t.most_common():
         f.write("%s,%d,%.1f,%.1f,%.1f\n" % (k, c[k], v, 100 * v / sum(t.values()), v / c[k]))
-for s in ("bench_%s.json", "bench_ref_%s.json"):
-    src_f = os.path.join(G, s % tag)
+for src_n, dst_n in (("bench_%s.json" % tag, "%s_bench.json" % name), ("bench_ref_%s.json" % tag, "%s_bench_ref.json" % name)):
+    src_f = os.path.join(G, src_n)
     if os.path.exists(src_f):
-        open(os.path.join(P, (s % name)), "w").write(open(src_f).read())
+        open(os.path.join(P, dst_n), "w").write(open(src_f).read())
 tj = os.path.join(P, "ncu_traffic.json")
 d = json.load(open(tj)) if os.path.exists(tj) else {}
 d["reweight_hist_kernel<double>"] = {

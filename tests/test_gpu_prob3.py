@@ -240,3 +240,32 @@ def test_event_order_changes_speed_not_results():
     _, pe3, pm3 = ops.propagate_earth(consts, earth, -1, e, cz, flav=1, want_probability=False)
     assert torch.equal(pe2, pe3) and torch.equal(pm2, pm3)
     _assert_prob(pe2.cpu().numpy(), p0[:, 0, 1].cpu().numpy(), "row mode vs full mode")
+
+
+def test_edge_directions_and_energies():
+    """Energies 0.1 GeV .. 100 TeV x every special direction (coszen = -1, 0, 1, each shell's tangent limit and
+    its two floating-point neighbours), nu and nubar, NSI: same bar as the bulk (1e-10 / 1e-12) and no NaN."""
+    from pisa_b200 import ops
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L, earth = _earth()
+    lims = np.asarray(L.coszen_limit)
+    lims = lims[lims < 1]
+    cz_special = np.concatenate([[-1.0, 1.0, 0.0, np.nextafter(-1.0, 0), np.nextafter(1.0, 0)], lims,
+                                 np.nextafter(lims, 1), np.nextafter(lims, -1)])
+    E, CZ = (a.ravel() for a in np.meshgrid(np.logspace(-1, 5, 25), cz_special, indexing="ij"))
+    dm, mix, mat_pot = syn.osc_matrices(nsi=syn.STD_NSI)
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    _, den, dis = L.calcLayers(CZ)
+    for nubar in (1, -1):
+        ref = oracle.propagate_array(dm, mix, mat_pot, -1, zero, np.zeros((3, 3)), nubar, E, den, dis)
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, torch.tensor(E, device=dev), torch.tensor(CZ, device=dev))
+        out = full.cpu().numpy()
+        assert np.isfinite(out).all()
+        assert np.allclose(out, ref, rtol=1e-10, atol=1e-12), np.abs(out - ref).max()
+        for flav in (0, 1, 2):
+            _, pe, pmu = ops.propagate_earth(consts, earth, nubar, torch.tensor(E, device=dev),
+                                             torch.tensor(CZ, device=dev), flav=flav, want_probability=False)
+            assert np.allclose(pe.cpu().numpy(), ref[:, 0, flav], rtol=1e-10, atol=1e-12)
+            assert np.allclose(pmu.cpu().numpy(), ref[:, 1, flav], rtol=1e-10, atol=1e-12)
