@@ -146,3 +146,129 @@ int pisab_flux_barr_simple_f32(const float *d_energy, const float *d_coszen, con
                             nu_nubar_ratio, delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
 }
 }
+
+// ---------------------------------------------------------------------------------------------
+// flux.honda_ip: integral-preserving interpolation of an azimuth-averaged Honda table
+// ---------------------------------------------------------------------------------------------
+// Reference per event (pisa/utils/flux_weights.py:337-349): 20 x splev(log10 E, energy spline, der=1), cumsum * 0.1,
+// splrep through the 21 points, splev(coszen, der=1), / E**enpow -- for each of the four primaries.  Here:
+//   * splev(.., der=1) is FITPACK's splder: knot interval by its search rule, the three non-zero quadratic
+//     B-splines by fpbspl's recursion (shared by all 80 splines of a table: one knot vector), and the
+//     derivative coefficients k (c[i+1] - c[i]) / (t[i+k+1] - t[i+1]) precomputed on the host from the
+//     reference's own splrep coefficients (pisa_b200/utils/flux_weights.py);
+//   * the per-event spline FIT in coszen is linear in its 21 values, so it is a fixed table of cardinal-spline
+//     derivative polynomials D[piece][k][3]:  flux = sum_k D_k(coszen) * int_vals[k] / E**enpow.
+namespace pisab {
+
+constexpr int kHondaCz = 20;
+
+template <typename IO>
+__global__ void __launch_bounds__(128)
+flux_honda_2d_kernel(const double *__restrict__ knots, int n_knots, const double *__restrict__ dcoef,
+                     const double *__restrict__ cz_breaks, int n_pieces, const double *__restrict__ cz_table,
+                     int enpow, const IO *__restrict__ energy, const IO *__restrict__ coszen, int64_t n,
+                     IO *__restrict__ nu_out, IO *__restrict__ nubar_out) {
+    const int nk1 = n_knots - 4; // FITPACK's nk1 for k = 3
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = (double)__ldg(energy + i), cz = (double)__ldg(coszen + i);
+        const double x = log10(e);
+        // ---- splder: t(l) <= x < t(l+1), l in [k1, nk1] (1-based); uniform interior knots give the guess
+        int l = 4;
+        {
+            const double t0 = __ldg(knots + 4), t1 = __ldg(knots + 5); // first interior knots
+            int g = 5 + (int)floor((x - t0) / (t1 - t0));
+            g = g < 4 ? 4 : (g > nk1 ? nk1 : g);
+            l = g;
+            while (l > 4 && x < __ldg(knots + l - 1)) --l;            // t(l) > x: go down
+            while (l < nk1 && !(x < __ldg(knots + l))) ++l;            // x >= t(l+1): go up
+        }
+        // ---- fpbspl, degree 2 (h(1..3), knots t(l-1) .. t(l+2))
+        double h0 = 1.0, h1 = 0.0, h2 = 0.0;
+        {
+            const double tl = __ldg(knots + l - 1), tl1 = __ldg(knots + l);          // t(l), t(l+1)
+            const double tlm = __ldg(knots + l - 2), tl2 = __ldg(knots + l + 1);      // t(l-1), t(l+2)
+            // j = 1
+            double f = h0 / (tl1 - tl);
+            h0 = f * (tl1 - x);
+            h1 = f * (x - tl);
+            // j = 2
+            const double a0 = h0, a1 = h1;
+            f = a0 / (tl1 - tlm);
+            h0 = f * (tl1 - x);
+            h1 = f * (x - tlm);
+            f = a1 / (tl2 - tl);
+            h1 = h1 + f * (tl2 - x);
+            h2 = f * (x - tl);
+        }
+        const double *c0 = dcoef + (size_t)(l - 4) * (4 * kHondaCz); // wrk(ll+1..ll+3), ll = l - k1
+        const double *c1 = c0 + 4 * kHondaCz, *c2 = c1 + 4 * kHondaCz;
+        // ---- coszen piece of the cardinal splines
+        int p = 0;
+        while (p + 1 < n_pieces && cz >= __ldg(cz_breaks + p + 1)) ++p;
+        const double u = cz - __ldg(cz_breaks + p);
+        const double *D = cz_table + (size_t)p * (kHondaCz + 1) * 3;
+        double scale = 1.0;
+        for (int k = 0; k < enpow; ++k) scale *= e;
+        double out[4];
+#pragma unroll
+        for (int prim = 0; prim < 4; ++prim) {
+            double acc = 0.0, sum = 0.0; // int_vals[0] = 0 contributes nothing
+#pragma unroll 4
+            for (int j = 0; j < kHondaCz; ++j) {
+                const int q = prim * kHondaCz + j;
+                double v = __ldg(c0 + q) * h0;
+                v = v + __ldg(c1 + q) * h1;
+                v = v + __ldg(c2 + q) * h2;
+                acc += v;                                            // cumsum
+                const double *d = D + (j + 1) * 3;
+                const double dk = fma(fma(__ldg(d), u, __ldg(d + 1)), u, __ldg(d + 2));
+                sum = fma(dk, acc * 0.1, sum);
+            }
+            out[prim] = sum / scale;
+        }
+        nu_out[2 * i] = (IO)out[0];
+        nu_out[2 * i + 1] = (IO)out[1];
+        nubar_out[2 * i] = (IO)out[2];
+        nubar_out[2 * i + 1] = (IO)out[3];
+    }
+}
+
+template <typename IO>
+static int honda_impl(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
+                      int32_t n_pieces, const double *d_cz_table, int32_t enpow, const IO *d_energy,
+                      const IO *d_coszen, int64_t n, IO *d_nu, IO *d_nubar, void *stream) {
+    if (!d_knots || !d_dcoef || !d_cz_breaks || !d_cz_table || n_knots < 9 || n_pieces < 1 || enpow < 0) {
+        set_error("bad flux table");
+        return PISAB_ERR_ARG;
+    }
+    if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_nu || !d_nubar))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t want = (n + 127) / 128;
+    const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+    flux_honda_2d_kernel<IO><<<grid, 128, 0, (cudaStream_t)stream>>>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces,
+                                                                     d_cz_table, enpow, d_energy, d_coszen, n, d_nu, d_nubar);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+} // namespace pisab
+
+extern "C" {
+int pisab_flux_honda_2d_f64(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
+                            int32_t n_pieces, const double *d_cz_table, int32_t enpow, const double *d_energy,
+                            const double *d_coszen, int64_t n, double *d_nu_flux_nominal,
+                            double *d_nubar_flux_nominal, void *stream) {
+    return pisab::honda_impl<double>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces, d_cz_table, enpow, d_energy,
+                                     d_coszen, n, d_nu_flux_nominal, d_nubar_flux_nominal, stream);
+}
+int pisab_flux_honda_2d_f32(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
+                            int32_t n_pieces, const double *d_cz_table, int32_t enpow, const float *d_energy,
+                            const float *d_coszen, int64_t n, float *d_nu_flux_nominal,
+                            float *d_nubar_flux_nominal, void *stream) {
+    return pisab::honda_impl<float>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces, d_cz_table, enpow, d_energy,
+                                    d_coszen, n, d_nu_flux_nominal, d_nubar_flux_nominal, stream);
+}
+}

@@ -83,6 +83,30 @@ def flux_barr_simple(true_energy, true_coszen, nu_flux_nominal, nubar_flux_nomin
     return out
 
 
+def flux_honda_2d(table, true_energy, true_coszen, nu_flux_nominal=None, nubar_flux_nominal=None):
+    """``calculate_2d_flux_weights`` (flux_weights.py:267-350) for the four primaries of ``table``
+    (a ``pisa_b200.utils.flux_weights.HondaTable2D``): returns (nu_flux_nominal, nubar_flux_nominal), [n, 2] each."""
+    _chk(true_energy, "true_energy")
+    dt = true_energy.dtype
+    _chk(true_coszen, "true_coszen", dt)
+    n = true_energy.numel()
+    if true_coszen.numel() != n:
+        raise ValueError("length of energy and coszen arrays must match")
+    if n and not bool(((true_coszen >= -1.0) & (true_coszen <= 1.0)).all()):
+        raise ValueError("Not all coszens found between -1 and 1")      # flux_weights.py:323-324
+    if nu_flux_nominal is None:
+        nu_flux_nominal = torch.empty((n, 2), dtype=dt, device=true_energy.device)
+    if nubar_flux_nominal is None:
+        nubar_flux_nominal = torch.empty((n, 2), dtype=dt, device=true_energy.device)
+    _chk(nu_flux_nominal, "nu_flux_nominal", dt)
+    _chk(nubar_flux_nominal, "nubar_flux_nominal", dt)
+    knots, dcoef, breaks, cz_table = table.device_tables(true_energy.device)
+    f = _lib.fn("pisab_flux_honda_2d", dt)
+    _lib.check(f(_ptr(knots), knots.numel(), _ptr(dcoef), _ptr(breaks), breaks.numel(), _ptr(cz_table), int(table.enpow),
+                 _ptr(true_energy), _ptr(true_coszen), n, _ptr(nu_flux_nominal), _ptr(nubar_flux_nominal), _stream()))
+    return nu_flux_nominal, nubar_flux_nominal
+
+
 # ----------------------------------------------------------------------------- layers -----
 
 def layers_calc(earth, coszen):

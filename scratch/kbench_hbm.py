@@ -38,3 +38,7 @@ a = torch.empty(n * 4, dtype=torch.float64, device=dev); b = torch.empty_like(a)
 t = timeit(lambda: b.copy_(a)); print("torch copy 3.2 GB            %9.3f ms  %8.1f GB/s" % (t, 2 * a.numel() * 8 / t / 1e6))
 nb_nom = (ev["nu_flux"] * 0.8).contiguous(); fo = torch.empty_like(ev["nu_flux"])
 rep("flux_barr_simple", timeit(lambda: ops.flux_barr_simple(ev["true_energy"], ev["true_coszen"], ev["nu_flux"], nb_nom, 1, 1.03, 0.97, 0.05, 0.3, -0.2, out=fo)), 64)
+from pisa_b200.utils.flux_weights import HondaTable2D
+HT = HondaTable2D("flux/honda-2015-spl-solmin-aa.d")
+nu_o = torch.empty_like(ev["nu_flux"]); nb_o = torch.empty_like(ev["nu_flux"])
+rep("flux_honda_2d (4 primaries)", timeit(lambda: ops.flux_honda_2d(HT, ev["true_energy"], ev["true_coszen"], nu_o, nb_o)), 48)

@@ -16,6 +16,7 @@ Outputs (all small, committed):
   ref_params_f8.npz        OscParams / StdNSIParams matrices
   ref_hist_f8.npz          find_index / lookup_regular_* / numpy.histogramdd
   ref_flux_{f8,f4}.npz     reference flux.barr_simple (apply_sys_vectorized) for 5 parameter sets
+  ref_honda_f8.npz         reference flux_weights.calculate_2d_flux_weights on the Honda 2015 table
 The generating inputs are stored alongside the outputs, so tests never need the
 reference at run time.
 """
@@ -290,6 +291,26 @@ def gen_flux(ns, tag, n_events=1500):
     np.savez_compressed(os.path.join(HERE, "ref_flux_%s.npz" % tag), **out)
 
 
+def gen_honda(ns, n_events=600):
+    """Reference honda_ip arithmetic (flux_weights.load_2d_table + calculate_2d_flux_weights) on seeded events,
+    incl. energies outside the table (extrapolation) and the coszen end points."""
+    fw = ns.flux_weights
+    table = "flux/honda-2015-spl-solmin-aa.d"
+    splines = fw.load_2d_table(table)
+    rng = np.random.default_rng(7)
+    e = 10 ** rng.uniform(-1.2, 4.3, n_events)
+    cz = rng.uniform(-1, 1, n_events)
+    cz[:6] = [-1.0, 1.0, -0.8, 0.8, 0.0, -0.95]
+    out = {"true_energy": e, "true_coszen": cz, "table": np.array(table)}
+    for prim in ("nue", "numu", "nuebar", "numubar"):
+        out[prim] = fw.calculate_2d_flux_weights(e, cz, splines[prim])
+        # spline coefficients of two rows, to pin the product's own table construction bit for bit
+        for key in ("-0.95", "0.45"):
+            t, c, k = splines[prim][key]
+            out["tck/%s/%s/t" % (prim, key)], out["tck/%s/%s/c" % (prim, key)] = np.asarray(t), np.asarray(c)
+    np.savez_compressed(os.path.join(HERE, "ref_honda_f8.npz"), **out)
+
+
 def main():
     ns = ref_loader.load()
     tag = "f4" if ns.pisa.FTYPE == np.float32 else "f8"
@@ -300,6 +321,7 @@ def main():
     if tag == "f8":
         gen_params(ns)
         gen_hist(ns)
+        gen_honda(ns)
         env = dict(os.environ, PISA_FTYPE="fp32")
         subprocess.check_call([sys.executable, os.path.abspath(__file__)], env=env)
 

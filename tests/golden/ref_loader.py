@@ -74,6 +74,14 @@ def from_file(fname, as_array=False, **kw):
     return np.loadtxt(fname)
 ''',
     "pisa/utils/profiler.py": "def profile(f): return f\n",
+    "pisa/utils/resources.py": '''
+import os
+RES = os.path.join(os.environ.get("PISA_REFERENCE_ROOT", "/root/reference"), "pisa_examples", "resources")
+def find_resource(name, fail=True):
+    return name if os.path.exists(name) else os.path.join(RES, name)
+def open_resource(name, mode="r"):
+    return open(find_resource(name), mode)
+''',
     "pisa/core/binning.py": "class OneDimBinning: pass\nclass MultiDimBinning: pass\n",
     "pisa/stages/flux/__init__.py": "",
     "pisa/core/param.py": "class Param:\n    def __init__(self, **k): pass\nclass ParamSet(list):\n    pass\n",
@@ -92,6 +100,7 @@ _LINKS = [
     "pisa/core/bin_indexing.py",
     "pisa/utils/barr_parameterization.py",
     "pisa/stages/flux/barr_simple.py",
+    "pisa/utils/flux_weights.py",
 ]
 
 _loaded = None
@@ -137,6 +146,7 @@ def load():
     ns.translation = importlib.import_module("pisa.core.translation")
     ns.bin_indexing = importlib.import_module("pisa.core.bin_indexing")
     ns.barr_simple = importlib.import_module("pisa.stages.flux.barr_simple")
+    ns.flux_weights = importlib.import_module("pisa.utils.flux_weights")
     ns.resources = os.path.join(REFERENCE_ROOT, "pisa_examples", "resources")
     _loaded = ns
     return ns

@@ -78,3 +78,72 @@ def test_flux_stage_in_a_pipeline():
                                    c["nu_flux_nominal"].cpu().numpy(), c["nubar_flux_nominal"].cpu().numpy(), 1,
                                    1.0, 1.0, 0.1, 0.0, 0.0)
     assert np.allclose(c["nu_flux"].cpu().numpy(), ref1, rtol=1e-10)
+
+
+def test_honda_flux_kernel_vs_reference_fixture():
+    """flux.honda_ip arithmetic: the one-pass CUDA evaluation against the unmodified reference
+    (calculate_2d_flux_weights on 600 seeded events incl. extrapolated energies and coszen = +-1)."""
+    from pisa_b200 import ops
+    from pisa_b200.utils.flux_weights import HondaTable2D
+    dev = _dev()
+    g = load_golden("ref_honda_f8.npz")
+    T = HondaTable2D(str(g["table"]))
+    e, cz = torch.tensor(g["true_energy"], device=dev), torch.tensor(g["true_coszen"], device=dev)
+    nu, nubar = ops.flux_honda_2d(T, e, cz)
+    got = {"nue": nu[:, 0], "numu": nu[:, 1], "nuebar": nubar[:, 0], "numubar": nubar[:, 1]}
+    for prim, t in got.items():
+        out, ref = t.cpu().numpy(), g[prim]
+        assert np.allclose(out, ref, rtol=1e-10, atol=0), (prim, np.abs(out / ref - 1).max())
+    # FP32 storage mode
+    nu4, _ = ops.flux_honda_2d(T, e.float(), cz.float())
+    assert nu4.dtype == torch.float32 and np.allclose(nu4[:, 1].cpu().numpy(), g["numu"], rtol=3e-5)
+    with pytest.raises(ValueError):
+        ops.flux_honda_2d(T, e, cz * 1.5)
+
+
+def test_honda_flux_larger_sample_vs_oracle():
+    from oracle import honda
+    from pisa_b200 import ops
+    from pisa_b200.utils.flux_weights import HondaTable2D
+    dev = _dev()
+    T = HondaTable2D("flux/honda-2015-spl-solmin-aa.d")
+    rng = np.random.default_rng(21)
+    n = 1500
+    e = 10 ** rng.uniform(0, 3, n)
+    cz = rng.uniform(-1, 1, n)
+    nu, nubar = ops.flux_honda_2d(T, torch.tensor(e, device=dev), torch.tensor(cz, device=dev))
+    for prim, t in (("numu", nu[:, 1]), ("nuebar", nubar[:, 0])):
+        ref = honda.honda_2d_flux(e, cz, T.spline_dict[prim])
+        assert np.allclose(t.cpu().numpy(), ref, rtol=1e-10, atol=0)
+    # size-independent properties on 2e6 events: positive, finite, nu_mu > nu_e above 10 GeV, smooth in E
+    n2 = 2_000_000
+    e2 = torch.tensor(10 ** rng.uniform(0, 3, n2), device=dev)
+    c2 = torch.tensor(rng.uniform(-1, 1, n2), device=dev)
+    nu2, nb2 = ops.flux_honda_2d(T, e2, c2)
+    assert torch.isfinite(nu2).all() and torch.isfinite(nb2).all() and float(nu2.min()) > 0 and float(nb2.min()) > 0
+    hi = e2 > 10
+    assert bool((nu2[hi, 1] > nu2[hi, 0]).all())
+
+
+def test_full_flux_chain_pipeline():
+    """flux.honda_ip -> flux.barr_simple -> osc.prob3 -> aeff.aeff -> utils.hist selected from one cfg (the stage
+    order of the reference's IceCube_3y_neutrinos.cfg) on synthetic events."""
+    from oracle import honda
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.utils.flux_weights import HondaTable2D
+    _dev()
+    pipe = Pipeline("settings/pipeline/b200_icecube3y_events.cfg")
+    assert [s.service_name for s in pipe.stages] == ["synthetic_mc", "honda_ip", "barr_simple", "prob3", "aeff", "hist"]
+    out = pipe.get_outputs()
+    assert out["numu_cc"].hist.shape == (8, 8, 2) and np.isfinite(out["numu_cc"].hist).all()
+    c = pipe.data["nuebar_nc"]
+    c.representation = "events"
+    T = HondaTable2D("flux/honda-2015-spl-solmin-aa.d")
+    sel = slice(0, 200)
+    e, cz = c["true_energy"].cpu().numpy()[sel], c["true_coszen"].cpu().numpy()[sel]
+    assert np.allclose(c["nubar_flux_nominal"].cpu().numpy()[sel, 1], honda.honda_2d_flux(e, cz, T.spline_dict["numubar"]),
+                       rtol=1e-10)
+    ref = oracle.flux_barr_simple(c["true_energy"].cpu().numpy(), c["true_coszen"].cpu().numpy(),
+                                  c["nu_flux_nominal"].cpu().numpy(), c["nubar_flux_nominal"].cpu().numpy(), -1,
+                                  1.0, 1.0, 0.0, 0.0, 0.0)
+    assert np.allclose(c["nu_flux"].cpu().numpy(), ref, rtol=1e-10)

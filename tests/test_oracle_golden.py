@@ -259,3 +259,26 @@ def test_flux_barr_simple_oracle_matches_reference():
     out = oracle.flux_barr_simple(g4["true_energy"], g4["true_coszen"], g4["nu_flux_nominal"],
                                   g4["nubar_flux_nominal"], 1, *g4["all_up/params"])
     assert np.allclose(out, g4["all_up/nu"], rtol=2e-5, atol=1e-6)
+
+
+def test_honda_flux_oracle_and_table_construction_match_reference():
+    """oracle.honda (scipy FITPACK call sequence of flux_weights.py:267-350) and the product's host-side table
+    construction (pisa_b200.utils.flux_weights.load_2d_table: the same splrep calls as :50-130) against the
+    unmodified reference on seeded events incl. extrapolated energies and the coszen end points."""
+    from oracle import honda
+    from pisa_b200.utils.flux_weights import HondaTable2D
+    g = load_golden("ref_honda_f8.npz")
+    T = HondaTable2D(str(g["table"]))
+    for prim in ("nue", "numu", "nuebar", "numubar"):
+        for key in ("-0.95", "0.45"):
+            t, c, k = T.spline_dict[prim][key]
+            assert np.array_equal(t, g["tck/%s/%s/t" % (prim, key)])      # bit-identical B-spline coefficients
+            assert np.array_equal(c, g["tck/%s/%s/c" % (prim, key)])
+        sel = slice(0, 150)
+        out = honda.honda_2d_flux(g["true_energy"][sel], g["true_coszen"][sel], T.spline_dict[prim])
+        assert np.array_equal(out, g[prim][sel]), prim                     # same calls, same bits
+    assert T.dcoef.shape == (101, 80) and T.cz_table.shape == (18, 21, 3)
+    with pytest.raises(ValueError):
+        honda.honda_2d_flux([1.0], [1.5], T.spline_dict["nue"])
+    with pytest.raises(NotImplementedError):
+        HondaTable2D("flux/bartol-2004-sno-solmax-aa.d")
