@@ -133,14 +133,22 @@ class OneDimBinning:
 
     # --- identity -----------------------------------------------------------------------------
     def _state(self):
-        scale = 10 ** HASH_SIGFIGS
-        with np.errstate(invalid="ignore", over="ignore"):
-            rounded = tuple(float(np.format_float_scientific(x, precision=HASH_SIGFIGS)) if np.isfinite(x) else x
-                            for x in self._edges)
-        return (self.name, self._units.name, self._is_log, rounded)
+        # binnings are immutable: the rounded-edge state (HASH_SIGFIGS significant figures, like the
+        # reference's normQuant-based hashes) is computed once -- representations are hashed on every
+        # container access, and re-formatting 200 edges each time cost 200 ms per template
+        st = getattr(self, "_state_cache", None)
+        if st is None:
+            with np.errstate(invalid="ignore", over="ignore"):
+                rounded = tuple(float(np.format_float_scientific(x, precision=HASH_SIGFIGS)) if np.isfinite(x) else x
+                                for x in self._edges)
+            st = (self.name, self._units.name, self._is_log, rounded)
+            self._state_cache = st
+            self._hash_cache = hash(st)
+        return st
 
     def __hash__(self):
-        return hash(self._state())
+        self._state()
+        return self._hash_cache
 
     def __eq__(self, other):
         return isinstance(other, OneDimBinning) and self._state() == other._state()
@@ -236,10 +244,15 @@ class MultiDimBinning:
         return grids
 
     def __hash__(self):
-        return hash(tuple(hash(d) for d in self._dims))
+        h = getattr(self, "_hash_cache", None)
+        if h is None:
+            h = self._hash_cache = hash(tuple(hash(d) for d in self._dims))
+        return h
 
     def __eq__(self, other):
-        return isinstance(other, MultiDimBinning) and self._dims == other._dims
+        if self is other:
+            return True
+        return isinstance(other, MultiDimBinning) and hash(self) == hash(other) and self._dims == other._dims
 
     def __repr__(self):
         return "MultiDimBinning(%s)" % ", ".join(repr(d) for d in self._dims)
