@@ -469,7 +469,29 @@ class ContainerSet:
         return iter([c for c in self.containers if not c.linked] + self.linked_containers)
 
     def get_mapset(self, key, error=None):
-        """MapSet with one Map per container (container.py:339-355)."""
-        return MapSet(name=self.name, maps=[c.get_map(key, error=error) for c in self])
+        """MapSet with one Map per container (container.py:339-355).  The per-container histograms are
+        gathered on the device and read back with ONE device->host copy per key (a copy per container
+        costs a stream synchronisation each: 24 per template for 12 containers with errors)."""
+        conts = list(self)
+        if not conts or not all(c.is_map for c in conts):
+            return MapSet(name=self.name, maps=[c.get_map(key, error=error) for c in conts])
+
+        def fetch(k):
+            tensors = [c[k].detach() for c in conts]
+            if len({(tuple(t.shape), t.dtype) for t in tensors}) != 1:
+                return [t.cpu().numpy() for t in tensors]
+            return list(torch.stack(tensors).cpu().numpy())
+
+        hists = fetch(key)
+        errs = fetch(error) if error is not None else [None] * len(conts)
+        maps = []
+        for c, h, e in zip(conts, hists, errs):
+            binning = c.representation
+            full_shape = list(binning.shape) + ([-1] if h.ndim > 1 else [])
+            h = h.reshape(full_shape)
+            assert h.ndim == binning.num_dims
+            maps.append(Map(name=c.name, hist=h, error_hist=None if e is None else np.abs(e.reshape(full_shape)),
+                            binning=binning))
+        return MapSet(name=self.name, maps=maps)
 
     glob_aux_data_keys = property(lambda self: self._glob_aux_data.keys())

@@ -29,45 +29,79 @@ __device__ __forceinline__ int digitize_right(const double *__restrict__ edges, 
     int lo = 0, hi = n_edges;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        if (__ldg(edges + mid) <= v) lo = mid + 1;
+        if (edges[mid] <= v) lo = mid + 1;
         else hi = mid;
     }
     int idx = lo - 1;
-    if (v == __ldg(edges + n_edges - 1)) idx -= 1;
+    if (v == edges[n_edges - 1]) idx -= 1;
     return idx;
 }
 
+// One dimension of one event: bin id and in-range flag (shared by the generic and unrolled kernels)
 template <typename IO>
+__device__ __forceinline__ int index_1d(const BinningTable &B, int d, double x, bool &ok) {
+    // arithmetic is double in both storage modes (numba promotes float32 op float64; fast_histogram
+    // converts to double)
+    if (B.kind[d] == PISAB_DIM_EDGES) {
+        const int id = digitize_right(B.edges[d], B.n_bins[d] + 1, x);
+        ok = ok && id >= 0 && id < B.n_bins[d];
+        return id;
+    }
+    // Container.translate: np.log on the FTYPE array (container.py:845-850)
+    if (B.kind[d] == PISAB_DIM_LOG) x = sizeof(IO) == 4 ? (double)logf((float)x) : log(x);
+    const bool in = x >= B.lo[d] && x < B.hi[d];
+    // (int)((x - lo) * norm): no FMA contraction
+    int id = in ? (int)__dmul_rn(__dsub_rn(x, B.lo[d]), B.norm[d]) : 0;
+    // x < hi whose product rounds up to n: out-of-bounds access in the reference, folded into the last
+    // bin here and in the oracle
+    if (id >= B.n_bins[d]) id = B.n_bins[d] - 1;
+    ok = ok && in;
+    return id;
+}
+
+// NDIMS is a compile-time constant (1..PISAB_MAX_DIMS) so the dimension loop unrolls, and every thread
+// handles two events per iteration so that 2 NDIMS loads are in flight.  HBM-bound: 8 NDIMS B in + 4 B out.
+constexpr int kSmemEdges = 128; // per dimension; longer edge lists are searched in global memory
+
+template <typename IO, int NDIMS>
 __global__ void __launch_bounds__(256)
-hist_index_kernel(const __grid_constant__ BinningTable B, const __grid_constant__ CoordPtrs<IO> C,
+hist_index_kernel(const __grid_constant__ BinningTable Bg, const __grid_constant__ CoordPtrs<IO> C,
                   int64_t n, int32_t *__restrict__ out) {
+    // explicit edge lists (irregular dimensions) are searched per event: stage them in shared memory
+    __shared__ double s_edges[NDIMS][kSmemEdges];
+    BinningTable B = Bg;
+#pragma unroll
+    for (int d = 0; d < NDIMS; ++d) {
+        if (B.kind[d] == PISAB_DIM_EDGES && B.n_bins[d] + 1 <= kSmemEdges) {
+            for (int k = threadIdx.x; k <= B.n_bins[d]; k += blockDim.x) s_edges[d][k] = __ldg(Bg.edges[d] + k);
+            B.edges[d] = s_edges[d];
+        }
+    }
+    __syncthreads();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < n; i += 2 * stride) {
+        double xa[NDIMS], xb[NDIMS];
+#pragma unroll
+        for (int d = 0; d < NDIMS; ++d) {
+            xa[d] = (double)__ldg(C.p[d] + i);
+            xb[d] = (double)__ldg(C.p[d] + i + stride);
+        }
+        int fa = 0, fb = 0;
+        bool oka = true, okb = true;
+#pragma unroll
+        for (int d = 0; d < NDIMS; ++d) {
+            fa = fa * B.n_bins[d] + index_1d<IO>(B, d, xa[d], oka);
+            fb = fb * B.n_bins[d] + index_1d<IO>(B, d, xb[d], okb);
+        }
+        out[i] = oka ? fa : -1;
+        out[i + stride] = okb ? fb : -1;
+    }
+    for (; i < n; i += stride) {
         int flat = 0;
         bool ok = true;
 #pragma unroll
-        for (int d = 0; d < PISAB_MAX_DIMS; ++d) {
-            if (d >= B.n_dims) break;
-            // arithmetic is double in both storage modes (numba promotes float32 op float64;
-            // fast_histogram converts to double)
-            double x = (double)__ldg(C.p[d] + i);
-            int id;
-            if (B.kind[d] == PISAB_DIM_EDGES) {
-                id = digitize_right(B.edges[d], B.n_bins[d] + 1, x);
-                ok = ok && id >= 0 && id < B.n_bins[d];
-            } else {
-                // Container.translate: np.log on the FTYPE array (container.py:845-850)
-                if (B.kind[d] == PISAB_DIM_LOG) x = sizeof(IO) == 4 ? (double)logf((float)x) : log(x);
-                const bool in = x >= B.lo[d] && x < B.hi[d];
-                // (int)((x - lo) * norm): no FMA contraction
-                id = in ? (int)__dmul_rn(__dsub_rn(x, B.lo[d]), B.norm[d]) : 0;
-                // x < hi whose product rounds up to n: out-of-bounds access in the reference,
-                // folded into the last bin here and in the oracle
-                if (id >= B.n_bins[d]) id = B.n_bins[d] - 1;
-                ok = ok && in;
-            }
-            flat = flat * B.n_bins[d] + id;
-        }
+        for (int d = 0; d < NDIMS; ++d) flat = flat * B.n_bins[d] + index_1d<IO>(B, d, (double)__ldg(C.p[d] + i), ok);
         out[i] = ok ? flat : -1;
     }
 }
@@ -415,7 +449,12 @@ static int hist_index_impl(const pisab_binning_t *binning, const IO *const *d_co
     }
     if (total > 2147483647LL) { set_error("too many bins"); return PISAB_ERR_ARG; }
     if (n == 0) return PISAB_OK;
-    hist_index_kernel<IO><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index);
+    switch (B.n_dims) {
+    case 1: hist_index_kernel<IO, 1><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index); break;
+    case 2: hist_index_kernel<IO, 2><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index); break;
+    case 3: hist_index_kernel<IO, 3><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index); break;
+    default: hist_index_kernel<IO, 4><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(B, C, n, d_index); break;
+    }
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
