@@ -464,6 +464,14 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
         PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+        int dev = 0, optin = 0;
+        PISAB_CUDA_CHECK(cudaGetDevice(&dev));
+        PISAB_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (fa.sharedSizeBytes + smem > (size_t)optin) {
+            set_error("fused reweight+hist: %d bins need %zu bytes of shared memory per block (limit %d); "
+                      "use propagate_earth + hist_accumulate", n_bins, fa.sharedSizeBytes + smem, optin);
+            return PISAB_ERR_UNSUPPORTED;
+        }
         if (fa.sharedSizeBytes + smem > 48 * 1024)
             PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }

@@ -327,3 +327,36 @@ def test_large_input_histogram(dtype):
     h_u, _ = ops.hist_accumulate(ti[1:], None if tw is None else tw[1:], 128)
     ref_u = oracle.accumulate(np.where(ok[1:], idx[1:], -1), wd[1:], 128)
     assert np.allclose(h_u.cpu().numpy(), ref_u, rtol=1e-11, atol=0)
+
+
+@pytest.mark.parametrize("n_bins", [1, 400, 1024])
+def test_fused_kernel_other_bin_counts(n_bins):
+    """Fused template kernel with 1, 400 and 1024 bins (one block per SM at the large counts: 225 KB of shared
+    memory) against the unfused path; more than PISAB_DET_MAX_BINS bins must be refused, not mis-launched."""
+    from pisa_b200 import ops
+    from pisa_b200._lib import PisabError
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    dm, mix, mat_pot = syn.osc_matrices()
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    n = 200_000
+    ev = syn.make_events_torch(n, seed=8, dtype=np.float64, device=dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4)
+    idx = torch.randint(-1, n_bins, (n,), generator=g, device=dev, dtype=torch.int32)
+    h, h2 = ops.reweight_hist(consts, earth, 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
+                              idx, n_bins)
+    _, pe, pmu = ops.propagate_earth(consts, earth, 1, ev["true_energy"], ev["true_coszen"], flav=0,
+                                     want_probability=False)
+    w = ops.apply_osc_weights(ev["nu_flux"], pe, pmu, ev["weights"].clone())
+    hu, hu2 = ops.hist_accumulate(idx, w, n_bins)
+    assert torch.allclose(h, hu, rtol=1e-12, atol=0) and torch.allclose(h2, hu2, rtol=1e-12, atol=0)
+    assert abs(float(h.sum()) / float(w[idx >= 0].sum()) - 1) < 1e-12
+    if n_bins == 1024:
+        big = torch.randint(-1, 1025, (n,), generator=g, device=dev, dtype=torch.int32)
+        with pytest.raises(PisabError):
+            ops.reweight_hist(consts, earth, 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"],
+                              ev["weights"], big, 1025)
