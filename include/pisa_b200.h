@@ -279,6 +279,21 @@ int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const 
 int pisab_template_chi2(const double *d_hist, int32_t n_containers, int32_t n_bins,
                         const double *d_observed, double *d_total, double *d_out, void *stream);
 
+/* Parameter scan (BASELINE configs[4]): n_templates hypotheses in ONE launch.  `consts` is a HOST array of
+ * n_templates oscillation-parameter sets; containers as in pisab_reweight_hist_batch_* (d_weights_out is
+ * ignored).  d_hist: [n_templates][n_containers][2][n_bins].  pisab_template_chi2_batch then gives one mod_chi2
+ * per template (d_out[n_templates]).  For analysis-size samples (1e5 .. 1e6 events) a single template cannot
+ * fill the GPU; batching the hypotheses does. */
+int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_containers, int32_t n_bins, int64_t n_max);
+int pisab_reweight_hist_scan_f64(const pisab_osc_consts_t *consts, int32_t n_templates, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 double *d_hist, void *d_workspace, int64_t workspace_bytes, void *stream);
+int pisab_reweight_hist_scan_f32(const pisab_osc_consts_t *consts, int32_t n_templates, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 double *d_hist, void *d_workspace, int64_t workspace_bytes, void *stream);
+int pisab_template_chi2_batch(const double *d_hist, int32_t n_templates, int32_t n_containers, int32_t n_bins,
+                              const double *d_observed, double *d_out, void *stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------- */
 /* Dependent-chain-free DFMA microbenchmark: runs `iters` x 8 independent FMAs per thread
  * on a full grid and returns achieved FP64 FLOP/s (synchronises). Roofline denominator. */

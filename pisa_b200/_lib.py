@@ -97,6 +97,8 @@ _SIGNATURES = {
     "pisab_flux_barr_simple": (c_i32, [c_vp, c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, c_vp,
                                        c_vp]),
     "pisab_flux_honda_2d": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "pisab_reweight_hist_scan": (c_i32, [ctypes.POINTER(OscConsts), c_i32, ctypes.POINTER(Earth),
+                                         ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
                                           ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
 }
@@ -105,6 +107,8 @@ _UNTYPED = {
     "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pisab_template_chi2": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "pisab_template_chi2_batch": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    "pisab_reweight_scan_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     "pisab_fp64_peak_probe": (c_i32, [c_i32, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "pisab_launch_count": (c_i64, [c_i32]),
     "pisab_set_profiling": (c_i32, [c_i32]),

@@ -415,6 +415,32 @@ template_chi2_kernel(const double *__restrict__ hist, int n_containers, int n_bi
     if (threadIdx.x == 0) out[0] = s[0];
 }
 
+// one block per template of a scan: out[t] = mod_chi2(sum_c hist[t][c][0], sigma^2 = sum_c hist[t][c][1] | observed)
+__global__ void __launch_bounds__(128)
+template_chi2_batch_kernel(const double *__restrict__ hist, int n_containers, int n_bins,
+                           const double *__restrict__ observed, double *__restrict__ out) {
+    __shared__ double s[128];
+    const double *mine = hist + (size_t)blockIdx.x * n_containers * 2 * n_bins;
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        double e = 0.0, sig2 = 0.0;
+        for (int c = 0; c < n_containers; ++c) {
+            e += mine[((size_t)c * 2) * n_bins + b];
+            sig2 += mine[((size_t)c * 2 + 1) * n_bins + b];
+        }
+        e = fmax(e, 1e-10);
+        const double d = observed[b] - e;
+        acc += d * d / (sig2 + e);
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 64; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+
 static int ew_grid(int64_t n) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + 255) / 256;
@@ -528,7 +554,7 @@ extern "C" {
 int64_t pisab_hist_workspace_bytes(int64_t n, int32_t n_bins) {
     (void)n;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    return (int64_t)sms * 8 * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
+    return (int64_t)sms * 16 * 2 * (int64_t)n_bins * (int64_t)sizeof(double); // up to 16 blocks per SM-slot
 }
 
 int64_t pisab_reweight_batch_workspace_bytes(int32_t n_containers, int32_t n_bins) {
@@ -635,6 +661,15 @@ int pisab_template_chi2(const double *d_hist, int32_t n_containers, int32_t n_bi
                         const double *d_observed, double *d_total, double *d_out, void *stream) {
     PISAB_EW_CHECK(n_bins >= 1 && n_containers >= 1 && d_hist && d_observed && d_out);
     template_chi2_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_hist, n_containers, n_bins, d_observed, d_total, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_template_chi2_batch(const double *d_hist, int32_t n_templates, int32_t n_containers, int32_t n_bins,
+                              const double *d_observed, double *d_out, void *stream) {
+    PISAB_EW_CHECK(n_templates >= 1 && n_bins >= 1 && n_containers >= 1 && d_hist && d_observed && d_out);
+    template_chi2_batch_kernel<<<n_templates, 128, 0, (cudaStream_t)stream>>>(d_hist, n_containers, n_bins, d_observed, d_out);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;

@@ -2,6 +2,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <vector>
+
 #include "hist_device.cuh"
 #include "prob3_device.cuh"
 
@@ -226,14 +228,15 @@ struct FusedBatch {
     FusedContainer<IO> c[PISAB_MAX_BATCH];
 };
 
+// Body shared by the one-template kernel (oscillation table in the parameter constant bank) and the
+// multi-template scan kernel (table of this block's template in shared memory): `rank` of `n_ranks`
+// blocks cooperate on one template; partials: [container][n_ranks][2 n_bins] of that template.
 template <typename IO, bool STD>
-__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
-reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
-                     const __grid_constant__ FusedBatch<IO> batch, double *__restrict__ partials) {
+__device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
+                                                    const FusedBatch<IO> &batch, int rank, int n_ranks,
+                                                    double *__restrict__ partials, double *s_hist) {
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
-    // [per-thread h0 + invariants 14 x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
-    extern __shared__ __align__(16) double s_hist[];
-    __shared__ EarthTable s_earth;
+    // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
@@ -244,12 +247,9 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
     WarpHist wh(s_hist, n_bins);
-    // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
-    // DFMA takes such an operand directly); the Earth table is indexed per lane and goes to shared memory
-    copy_earth(earth, &s_earth);
     const int tid = threadIdx.x;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t first = (int64_t)blockIdx.x * blockDim.x + tid;
+    const int64_t stride = (int64_t)n_ranks * blockDim.x;
+    const int64_t first = (int64_t)rank * blockDim.x + tid;
     // warp-uniform trip count so that the warp-collective histogram step is always converged
     const int64_t warp_first = first - (tid & 31);
 
@@ -306,9 +306,45 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
             i_cur = i_next;
             i_next = i_nn;
         }
-        wh.flush(partials + ((size_t)ci * gridDim.x + blockIdx.x) * 2 * n_bins);
+        wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
         __syncthreads(); // the next container clears the bins
     }
+}
+
+template <typename IO, bool STD>
+__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
+reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
+                     const __grid_constant__ FusedBatch<IO> batch, double *__restrict__ partials) {
+    extern __shared__ __align__(16) double s_hist[];
+    __shared__ EarthTable s_earth;
+    // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
+    // DFMA takes such an operand directly); the Earth table is indexed per lane and goes to shared memory
+    copy_earth(earth, &s_earth);
+    fused_template_body<IO, STD>(osc, s_earth, batch, blockIdx.x, gridDim.x, partials, s_hist);
+}
+
+// Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves template b / R with rank
+// b % R; its oscillation table comes from a device array (P tables do not fit the parameter space) and is
+// staged in shared memory.  For the event samples of a real analysis (1e5 .. 1e6 events) one template does
+// not fill the GPU and a per-template launch is bound by launch + host overhead (~270 us); batching the
+// hypotheses restores full occupancy.  Per-event outputs are not written (they would race between templates).
+template <typename IO, bool STD>
+__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
+reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_constant__ EarthTable earth,
+                          const __grid_constant__ FusedBatch<IO> batch, int ranks_per_template,
+                          double *__restrict__ partials) {
+    extern __shared__ __align__(16) double s_hist[];
+    __shared__ EarthTable s_earth;
+    __shared__ OscTable s_osc;
+    const int tmpl = blockIdx.x / ranks_per_template, rank = blockIdx.x - tmpl * ranks_per_template;
+    {
+        const double *src = reinterpret_cast<const double *>(tables + tmpl);
+        double *dst = reinterpret_cast<double *>(&s_osc);
+        for (int i = threadIdx.x; i < (int)(sizeof(OscTable) / 8); i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    copy_earth(earth, &s_earth); // ends with __syncthreads()
+    double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
+    fused_template_body<IO, STD>(s_osc, s_earth, batch, rank, ranks_per_template, mine, s_hist);
 }
 
 } // namespace pisab
@@ -475,7 +511,20 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (fa.sharedSizeBytes + smem > 48 * 1024)
             PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = resident_grid(kernel, n_max, smem);
+    // PISAB_WAVES static waves of blocks instead of one persistent wave: a block's share of the deep-core
+    // events varies, and with one wave nothing refills an SM whose two blocks finish early (measured tail:
+    // ~6 %); the hardware scheduler balances several smaller waves, and the block -> events map stays static,
+    // so the histogram is still bit-reproducible.  Each thread keeps >= 8 events per container.
+#ifndef PISAB_WAVES
+#define PISAB_WAVES 4
+#endif
+    int grid = resident_grid(kernel, n_max, smem);
+    {
+        const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
+        int64_t g = (int64_t)grid * PISAB_WAVES;
+        if (g > by_work) g = by_work;
+        if (g > grid) grid = (int)g;
+    }
     {
         LaunchTimer t(s);
         kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, (double *)d_workspace);
@@ -534,6 +583,84 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
     }
     return reweight_hist_batch_impl<IO>(consts, earth, batch, n_max, d_hist, nullptr, nullptr, d_workspace,
                                         workspace_bytes, stream);
+}
+
+// ranks (blocks) per template of a scan: every thread should see >= 8 events of the largest container, and
+// the launch should have at least one full wave of blocks
+static int scan_ranks(int64_t n_max, int n_templates) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t r = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
+    const int64_t fill = ((int64_t)sms * 2 + n_templates - 1) / n_templates;
+    if (r < fill) r = fill;
+    if (r < 1) r = 1;
+    if (r > (int64_t)sms * 2) r = (int64_t)sms * 2;
+    return (int)r;
+}
+
+template <typename IO>
+static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_templates,
+                                  const pisab_earth_t *earth, const pisab_container_t *containers,
+                                  int32_t n_containers, int32_t n_bins, double *d_hist, void *d_workspace,
+                                  int64_t workspace_bytes, void *stream) {
+    if (!consts || n_templates < 1 || !containers || n_containers < 1 || n_containers > PISAB_MAX_BATCH || !d_hist) {
+        set_error("scan needs >= 1 template, 1..%d containers and a non-null output", PISAB_MAX_BATCH);
+        return PISAB_ERR_ARG;
+    }
+    if (n_bins < 1 || n_bins > PISAB_DET_MAX_BINS) { set_error("n_bins outside [1, %d]", PISAB_DET_MAX_BINS); return PISAB_ERR_UNSUPPORTED; }
+    FusedBatch<IO> batch = {};
+    batch.n_containers = n_containers;
+    batch.n_bins = n_bins;
+    int64_t n_max = 0;
+    for (int c = 0; c < n_containers; ++c) {
+        const pisab_container_t &S = containers[c];
+        FusedContainer<IO> &C = batch.c[c];
+        if (S.n < 0 || S.n > 2147483647LL || (S.n > 0 && (!S.d_energy || !S.d_coszen || !S.d_nu_flux || !S.d_weights || !S.d_index))) {
+            set_error("container %d: bad event arrays", c);
+            return PISAB_ERR_ARG;
+        }
+        if ((S.nubar != 1 && S.nubar != -1) || S.flav < 0 || S.flav > 2) { set_error("container %d: bad nubar / flav", c); return PISAB_ERR_ARG; }
+        C.energy = (const IO *)S.d_energy; C.coszen = (const IO *)S.d_coszen;
+        C.nu_flux = (const IO *)S.d_nu_flux; C.weights_in = (const IO *)S.d_weights;
+        C.index = S.d_index; C.order = S.d_order;
+        C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav; // per-event outputs stay NULL
+        if (S.n > n_max) n_max = S.n;
+    }
+    std::vector<OscTable> tables((size_t)n_templates);
+    bool all_std = true;
+    for (int t = 0; t < n_templates; ++t) {
+        const int rc = build_osc_table(consts + t, &tables[t]);
+        if (rc) return rc;
+        all_std = all_std && tables[t].std_matter != 0.0;
+    }
+    EarthTable et;
+    const int rc = build_earth_table(earth, &et);
+    if (rc) return rc;
+    const int ranks = scan_ranks(n_max, n_templates);
+    const int64_t need = pisab_reweight_scan_workspace_bytes(n_templates, n_containers, n_bins, n_max);
+    if (!d_workspace || workspace_bytes < need) { set_error("workspace too small: need %lld bytes", (long long)need); return PISAB_ERR_WORKSPACE; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t table_bytes = ((size_t)n_templates * sizeof(OscTable) + 255) / 256 * 256;
+    OscTable *d_tables = (OscTable *)d_workspace;
+    double *d_partials = (double *)((char *)d_workspace + table_bytes);
+    PISAB_CUDA_CHECK(cudaMemcpyAsync(d_tables, tables.data(), (size_t)n_templates * sizeof(OscTable), cudaMemcpyHostToDevice, s));
+    const size_t smem = fused_smem_bytes<IO>(n_bins, all_std);
+    auto kernel = all_std ? reweight_hist_scan_kernel<IO, true> : reweight_hist_scan_kernel<IO, false>;
+    {
+        cudaFuncAttributes fa;
+        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+        int dev = 0, optin = 0;
+        PISAB_CUDA_CHECK(cudaGetDevice(&dev));
+        PISAB_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (fa.sharedSizeBytes + smem > (size_t)optin) { set_error("scan: %d bins exceed the shared-memory budget", n_bins); return PISAB_ERR_UNSUPPORTED; }
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    {
+        LaunchTimer t(s);
+        kernel<<<n_templates * ranks, kBlock, smem, s>>>(d_tables, et, batch, ranks, d_partials);
+        note_launch();
+    }
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return hist_reduce_batch(d_partials, ranks, n_bins, n_templates * n_containers, d_hist, s);
 }
 
 extern "C" {
@@ -606,6 +733,26 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
                                   int64_t workspace_bytes, void *stream) {
     return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
                                           workspace_bytes, stream);
+}
+
+int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_containers, int32_t n_bins, int64_t n_max) {
+    if (n_templates < 1) n_templates = 1;
+    if (n_containers < 1) n_containers = 1;
+    const int ranks = scan_ranks(n_max, n_templates);
+    const int64_t table_bytes = ((int64_t)n_templates * (int64_t)sizeof(OscTable) + 255) / 256 * 256;
+    return table_bytes + (int64_t)n_templates * n_containers * ranks * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
+}
+int pisab_reweight_hist_scan_f64(const pisab_osc_consts_t *consts, int32_t n_templates, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 double *d_hist, void *d_workspace, int64_t workspace_bytes, void *stream) {
+    return reweight_hist_scan_abi<double>(consts, n_templates, earth, containers, n_containers, n_bins, d_hist,
+                                          d_workspace, workspace_bytes, stream);
+}
+int pisab_reweight_hist_scan_f32(const pisab_osc_consts_t *consts, int32_t n_templates, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 double *d_hist, void *d_workspace, int64_t workspace_bytes, void *stream) {
+    return reweight_hist_scan_abi<float>(consts, n_templates, earth, containers, n_containers, n_bins, d_hist,
+                                         d_workspace, workspace_bytes, stream);
 }
 
 } // extern "C"

@@ -129,6 +129,17 @@ class ReweightEngine:
             self.allreduce(out)
         return out
 
+    def evaluate_many(self, consts_list, allreduce=True):
+        """P hypotheses in ONE launch (``pisab_reweight_hist_scan``): returns ``[P, n_containers, 2, n_bins]``.
+        The single histogram exchange covers all P templates when sharded over GPUs."""
+        batches = self._get_batches()
+        if len(batches) != 1:
+            raise NotImplementedError("evaluate_many supports up to %d containers" % ops.MAX_BATCH)
+        out = ops.reweight_hist_scan(list(consts_list), self.earth, batches[0][1])
+        if allreduce:
+            self.allreduce(out)
+        return out
+
     def evaluate_host(self, consts, allreduce=True):
         """Host mode: event arrays live in pinned host memory; every call copies them to the
         device (double-buffered on a copy stream so the copy of container i+1 overlaps the

@@ -407,6 +407,48 @@ def reweight_hist_batch(consts, earth, batch, out=None):
     return out
 
 
+_scan_ws = {}
+
+
+def reweight_hist_scan(consts_list, earth, batch, out=None):
+    """P templates (``consts_list``: sequence of OscConsts) over the containers of ``batch`` in ONE launch;
+    returns ``[P, n_containers, 2, n_bins]``."""
+    n_t = len(consts_list)
+    if n_t < 1:
+        raise ValueError("at least one template")
+    arr = (OscConsts * n_t)(*consts_list)
+    if out is None:
+        out = torch.empty((n_t, batch.n, 2, batch.n_bins), dtype=torch.float64, device=batch.device)
+    _chk(out, "out", torch.float64)
+    if out.numel() != n_t * batch.n * 2 * batch.n_bins:
+        raise ValueError("out must hold [n_templates, n_containers, 2, n_bins] doubles")
+    n_max = max(int(d.n) for d in batch.desc)
+    need = int(_lib.load().pisab_reweight_scan_workspace_bytes(n_t, batch.n, batch.n_bins, n_max))
+    key = batch.device.index if batch.device.index is not None else torch.cuda.current_device()
+    ws = _scan_ws.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, dtype=torch.uint8, device=batch.device)
+        _scan_ws[key] = ws
+    f = _lib.fn("pisab_reweight_hist_scan", batch.dtype)
+    _lib.check(f(arr, n_t, ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(out), _ptr(ws), ws.numel(),
+                 _stream()))
+    return out
+
+
+def template_chi2_batch(hist, observed, out=None):
+    """One ``mod_chi2`` per template: ``hist`` is ``[P, n_containers, 2, n_bins]``; returns float64 ``[P]``."""
+    _chk(hist, "hist", torch.float64)
+    _chk(observed, "observed", torch.float64)
+    if hist.dim() != 4 or hist.shape[2] != 2 or observed.numel() != hist.shape[3]:
+        raise ValueError("hist must be [n_templates, n_containers, 2, n_bins] and observed [n_bins]")
+    if out is None:
+        out = torch.empty(hist.shape[0], dtype=torch.float64, device=hist.device)
+    _chk(out, "out", torch.float64)
+    _lib.check(_lib.load().pisab_template_chi2_batch(_ptr(hist), hist.shape[0], hist.shape[1], hist.shape[3],
+                                                     _ptr(observed), _ptr(out), _stream()))
+    return out
+
+
 def mod_chi2(expected, expected_w2, observed):
     """``mod_chi2`` (pisa/utils/stats.py:651-695) on device; returns a 1-element float64 tensor."""
     _chk(expected, "expected", torch.float64)

@@ -35,8 +35,12 @@ def asimov(engine, consts):
     return engine.evaluate(consts)[:, 0].sum(dim=0).contiguous()
 
 
-def scan_chi2(engine, observed, points, fixed, mat_pot=None):
+def scan_chi2(engine, observed, points, fixed, mat_pot=None, batch=64):
     """``mod_chi2`` of the template against ``observed`` at every (theta23, dm31) point.
+
+    ``batch`` hypotheses are evaluated per kernel launch (``ReweightEngine.evaluate_many``): for the event
+    samples of a real analysis (1e5 .. 1e6 events) one template cannot fill the GPU and a launch per template
+    is bound by launch + host overhead; ``batch=1`` takes the one-launch-per-template path.
 
     engine   : ReweightEngine with resident containers (scales set through ``set_scales``)
     observed : float64 device tensor [n_bins]
@@ -46,8 +50,16 @@ def scan_chi2(engine, observed, points, fixed, mat_pot=None):
     """
     points = list(points)
     out = torch.empty(len(points), dtype=torch.float64, device=engine.device)
-    for i, (t23, dm31) in enumerate(points):
-        consts = osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
-        hist = engine.evaluate(consts)
-        ops.template_chi2(hist, observed, out=out[i:i + 1])
+    if batch <= 1:
+        for i, (t23, dm31) in enumerate(points):
+            consts = osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
+            hist = engine.evaluate(consts)
+            ops.template_chi2(hist, observed, out=out[i:i + 1])
+        return out
+    for lo in range(0, len(points), batch):
+        chunk = points[lo:lo + batch]
+        consts = [osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
+                  for t23, dm31 in chunk]
+        hist = engine.evaluate_many(consts)
+        ops.template_chi2_batch(hist, observed, out=out[lo:lo + len(chunk)])
     return out

@@ -234,7 +234,15 @@ def test_scan_chi2_matches_oracle_chain():
     truth = (np.deg2rad(p["theta23"]), p["deltam31"])
     observed = scan.asimov(eng, scan.osc_consts(theta23=truth[0], dm31=truth[1], **fixed))
     points = [(t, d) for t in np.deg2rad([38.0, 42.3, 47.0]) for d in (2.3e-3, 2.457e-3, 2.6e-3)]
-    chi2 = scan.scan_chi2(eng, observed, points, fixed).cpu().numpy()
+    chi2 = scan.scan_chi2(eng, observed, points, fixed, batch=1).cpu().numpy()
+    # the same scan with all hypotheses in one launch (pisab_reweight_hist_scan) and in chunks of 4
+    chi2_b = scan.scan_chi2(eng, observed, points, fixed, batch=64).cpu().numpy()
+    chi2_c = scan.scan_chi2(eng, observed, points, fixed, batch=4).cpu().numpy()
+    assert np.allclose(chi2_b, chi2, rtol=1e-9, atol=1e-12) and np.allclose(chi2_c, chi2, rtol=1e-9, atol=1e-12)
+    many = eng.evaluate_many([scan.osc_consts(theta23=t, dm31=d, **fixed) for t, d in points[:3]]).cpu().numpy()
+    for k, (t, d) in enumerate(points[:3]):
+        one = eng.evaluate(scan.osc_consts(theta23=t, dm31=d, **fixed)).cpu().numpy()
+        assert np.allclose(many[k], one, rtol=1e-12, atol=0)
 
     def oracle_template(t23, dm31):
         c = scan.osc_consts(theta23=t23, dm31=dm31, **fixed)
