@@ -520,10 +520,11 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
 #endif
     int grid = resident_grid(kernel, n_max, smem);
     {
+        // whole waves only (a partial last wave is the tail this is meant to remove)
         const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
-        int64_t g = (int64_t)grid * PISAB_WAVES;
-        if (g > by_work) g = by_work;
-        if (g > grid) grid = (int)g;
+        int64_t waves = by_work / grid;
+        if (waves > PISAB_WAVES) waves = PISAB_WAVES;
+        if (waves > 1) grid = (int)(grid * waves);
     }
     {
         LaunchTimer t(s);
