@@ -357,3 +357,33 @@ def test_csv_loader_pipeline(tmp_path):
         idx = c.bin_index(pipe.output_binning).cpu().numpy()
         assert np.isclose(out[c.name].hist.sum(), w[idx >= 0].sum(), rtol=1e-12)
     assert sum(sizes.values()) == n
+
+
+def test_full_icecube3y_stage_order_with_hypersurfaces():
+    """data -> flux.honda_ip -> flux.barr_simple -> osc.prob3 -> aeff.aeff -> utils.hist -> discr_sys.hypersurfaces
+    (the stage order of the reference's IceCube_3y_neutrinos.cfg): the last stage multiplies the binned maps and
+    their errors by offset + sum gradient * value of the data-release hyperplanes."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.stages.discr_sys.hypersurfaces import evaluate_hyperplane
+    from pisa_b200.utils.units import ureg
+    full = Pipeline("settings/pipeline/b200_icecube3y_full.cfg")
+    base = Pipeline("settings/pipeline/b200_icecube3y_events.cfg")
+    assert full.stages[-1].service_name == "hypersurfaces"
+    out_f, out_b = full.get_outputs(), base.get_outputs()
+    st = full.stages[-1]
+    vals = {n: float(st.params[n].m) for n in st.hypersurface_param_names}
+    groups = {"nue_cc+nuebar_cc": ["nue_cc", "nuebar_cc"], "numu_cc+numubar_cc": ["numu_cc", "numubar_cc"],
+              "nutau_cc+nutaubar_cc": ["nutau_cc", "nutaubar_cc"],
+              "nu_nc+nubar_nc": ["nue_nc", "numu_nc", "nutau_nc", "nuebar_nc", "numubar_nc", "nutaubar_nc"]}
+    for key, names in groups.items():
+        scales = evaluate_hyperplane(st.hypersurfaces[key], vals)
+        for name in names:
+            assert np.allclose(out_f[name].hist, np.clip(out_b[name].hist * scales, 0, np.inf), rtol=1e-13), name
+            assert np.allclose(out_f[name].std_devs, out_b[name].std_devs * scales, rtol=1e-13), name
+    # a systematic parameter moves the maps; osc.prob3 does not recompute (its parameter hash is unchanged)
+    full.params.opt_eff_overall = 1.1 * ureg.dimensionless
+    out2 = full.get_outputs()
+    vals["opt_eff_overall"] = 1.1
+    scales = evaluate_hyperplane(st.hypersurfaces["numu_cc+numubar_cc"], vals)
+    assert np.allclose(out2["numu_cc"].hist, np.clip(out_b["numu_cc"].hist * scales, 0, np.inf), rtol=1e-13)

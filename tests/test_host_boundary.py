@@ -190,3 +190,29 @@ def test_csv_loader_event_selection(tmp_path):
     st = csv_loader(events_file=str(f), data_dict="{'true_energy': 'true_energy', 'weighted_aeff': 'weight'}",
                     output_names="nue_cc, numubar_nc", calc_mode="events", apply_mode="events")
     assert st.output_names == ["nue_cc", "numubar_nc"] and st.data_dict["weighted_aeff"] == "weight"
+
+
+def test_hyperplane_loader_and_formula():
+    """discr_sys.hypersurfaces host side: data-release CSV loader (hypersurface.py:2065-2172) and the linear
+    hyperplane scale = offset + sum_p gradient_p * value_p (:421-428), checked against pandas directly."""
+    import pandas as pd
+    from pisa_b200.stages.discr_sys.hypersurfaces import evaluate_hyperplane, load_hypersurfaces_data_release
+    from pisa_b200.utils.config_parser import parse_pipeline_config
+    from pisa_b200.utils.resources import find_resource
+    cfg = parse_pipeline_config("settings/pipeline/b200_icecube3y_full.cfg")
+    binning = cfg[("discr_sys", "hypersurfaces")]["calc_mode"]
+    hs, names = load_hypersurfaces_data_release("events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2", binning)
+    assert names == ["ice_absorption", "ice_scattering", "opt_eff_headon", "opt_eff_lateral", "opt_eff_overall"]
+    assert list(hs) == ["nue_cc+nuebar_cc", "numu_cc+numubar_cc", "nutau_cc+nutaubar_cc", "nu_nc+nubar_nc"]
+    vals = dict(opt_eff_overall=1.07, opt_eff_lateral=31.0, opt_eff_headon=-0.4, ice_scattering=2.5, ice_absorption=-3.0)
+    raw = pd.read_csv(find_resource("events/IceCube_3y_oscillations/hyperplanes_numu_cc.csv.bz2"))
+    ref = raw["offset"].values.copy()
+    for p in names:
+        ref += raw[p].values * vals[p]
+    got = evaluate_hyperplane(hs["numu_cc+numubar_cc"], vals)
+    assert got.shape == (8, 8, 2) and np.allclose(got.ravel(), ref, rtol=1e-15)
+    # rows are ordered (reco_energy, reco_coszen, pid) row-major: the first rows of the file are the first energy bin
+    assert raw["reco_energy"].values[:16].std() == 0 and set(raw["pid"].values[:2]) == {0, 1}
+    other = parse_pipeline_config("settings/pipeline/b200_oscillogram.cfg")[("osc", "prob3")]["calc_mode"]
+    with pytest.raises((AssertionError, KeyError)):      # a binning the files were not made for
+        load_hypersurfaces_data_release("events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2", other)
