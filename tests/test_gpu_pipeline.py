@@ -387,3 +387,36 @@ def test_full_icecube3y_stage_order_with_hypersurfaces():
     vals["opt_eff_overall"] = 1.1
     scales = evaluate_hyperplane(st.hypersurfaces["numu_cc+numubar_cc"], vals)
     assert np.allclose(out2["numu_cc"].hist, np.clip(out_b["numu_cc"].hist * scales, 0, np.inf), rtol=1e-13)
+
+
+def test_engine_large_binning_falls_back_to_unfused_kernels():
+    """40 x 40 x 2 = 3200 bins exceed the fused kernel's budget: the engine must still give the right template."""
+    _need_gpu()
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    dims = [dict(name="reco_energy", kind="log", n_bins=40, lo=5.62341325, hi=56.23413252),
+            dict(name="reco_coszen", kind="lin", n_bins=40, lo=-1.0, hi=1.0),
+            dict(name="pid", kind="lin", n_bins=2, lo=-0.5, hi=1.5)]
+    binning, keep = ops.make_binning(dims, dev)
+    dm, mix, mat_pot = syn.osc_matrices()
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    big = ReweightEngine(L.earth_struct(), 3200, np.float64, dev)
+    small = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    b128, keep2 = ops.make_binning(syn.DRAGON_DIMS, dev)
+    for i, (name, nubar, flav) in enumerate(syn.CONTAINERS[:3]):
+        ev = syn.make_events_torch(50_000, seed=70 + i, dtype=np.float64, device=dev)
+        coords = [ev["reco_energy"], ev["reco_coszen"], ev["pid"]]
+        big.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
+                          ops.hist_index(binning, coords))
+        small.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
+                            ops.hist_index(b128, coords))
+    hb, hs = big.evaluate(consts), small.evaluate(consts)
+    assert hb.shape == (3, 2, 3200)
+    # same events, same weights: the totals agree whatever the binning (both binnings cover the same range)
+    assert torch.allclose(hb[:, 0].sum(dim=1), hs[:, 0].sum(dim=1), rtol=1e-11)
+    assert torch.allclose(hb[:, 1].sum(dim=1), hs[:, 1].sum(dim=1), rtol=1e-11)
