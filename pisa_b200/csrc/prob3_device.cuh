@@ -60,7 +60,9 @@ __constant__ double kTab[24] = {
     /* 16 */ 0.33333333333333333333,  // 1/3
     /* 17 */ 0.66666666666666666667,  // 2/3
     /* 18 */ 5.068,                   // 2 * 2.534  (numba_osc_kernels.py:524)
-    /* 19 */ 0.375, 0, 0, 0, 0};
+    /* 19 */ 0.375,
+    /* 20 */ 1e-200, // lower clamp of p and of the discriminant
+    0, 0, 0};
 
 // 1/x, 1/sqrt(x) and sqrt(x) from the hardware approximations (MUFU.RCP64H / RSQ64H, ~2^-22) refined
 // by ONE third-order step (error -> ~2^-64 before rounding, result ~1 ulp): a dependent chain of 3-4
@@ -85,30 +87,6 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
 #endif
     return r;
 }
-#ifdef PISAB_NEWTON2
-__device__ __forceinline__ double rcp_fast(double x) {
-    double r = rcp_seed(x);
-    double e = fma(-x, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-x, r, 1.0);
-    return fma(r, e, r);
-}
-__device__ __forceinline__ double rsqrt_fast(double x) {
-    double r = rsqrt_seed(x);
-    double h = 0.5 * x;
-    r = r * fma(-h * r, r, 1.5);
-    r = r * fma(-h * r, r, 1.5);
-    return r;
-}
-// sqrt(x) for x >= 0 (0 allowed) to ~1 ulp
-__device__ __forceinline__ double sqrt_fast(double x) {
-    const double xs = fmax(x, 1e-290);
-    const double r = rsqrt_fast(xs);
-    double s = xs * r;
-    s = fma(fma(-s, s, xs), 0.5 * r, s); // one Newton correction of the product
-    return x > 0.0 ? s : 0.0;
-}
-#else
 __device__ __forceinline__ double rcp_fast(double x) {
     const double r = rcp_seed(x);
     const double e = fma(-x, r, 1.0);      // 1/x = r / (1 - e) = r (1 + e + e^2 + O(e^3))
@@ -130,7 +108,15 @@ __device__ __forceinline__ double sqrt_fast(double x) {
     const double s = fma(t * e, fma(e, kTab[19], 0.5), t);
     return x > 0.0 ? s : 0.0;
 }
-#endif
+
+// sqrt(max(x, tiny)) without the final select (callers for which sqrt(tiny) ~ 1e-100 is as good as 0)
+__device__ __forceinline__ double sqrt_pos(double x) {
+    const double xs = x > kTab[20] ? x : kTab[20];
+    const double r = rsqrt_seed(xs);
+    const double t = xs * r;
+    const double e = fma(-t, r, 1.0);
+    return fma(t * e, fma(e, kTab[19], 0.5), t);
+}
 
 // sin/cos for |x| < ~1e5 rad (phases here are < 1e3): two-term Cody-Waite reduction with FMA and
 // the fdlibm kernel polynomials on [-pi/4, pi/4].  No Payne-Hanek slow path (keeps the code small
@@ -141,27 +127,12 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
     double r = fma(-kd, kTab[1], x);
     r = fma(-kd, kTab[2], r);
     const double z = r * r;
-#ifdef PISAB_HORNER
-    double ps = fma(z, kTab[3], kTab[4]);
-    ps = fma(z, ps, kTab[5]);
-    ps = fma(z, ps, kTab[6]);
-    ps = fma(z, ps, kTab[7]);
-    ps = fma(z, ps, kTab[8]);
-    const double s = fma(r * z, ps, r);
-    double pc = fma(z, kTab[9], kTab[10]);
-    pc = fma(z, pc, kTab[11]);
-    pc = fma(z, pc, kTab[12]);
-    pc = fma(z, pc, kTab[13]);
-    pc = fma(z, pc, kTab[14]);
-    const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
-#else
     // Estrin evaluation: dependency depth 3 after z instead of 5 (the kernel is latency-bound)
     const double zz = z * z;
     const double ps = fma(zz, fma(zz, fma(z, kTab[3], kTab[4]), fma(z, kTab[5], kTab[6])), fma(z, kTab[7], kTab[8]));
     const double s = fma(r * z, ps, r);
     const double pc = fma(zz, fma(zz, fma(z, kTab[9], kTab[10]), fma(z, kTab[11], kTab[12])), fma(z, kTab[13], kTab[14]));
     const double c = fma(zz, pc, fma(z, -0.5, 1.0));
-#endif
     const double ss = (k & 1) ? c : s;
     const double cc = (k & 1) ? s : c;
     *sn = (k & 2) ? -ss : ss;
@@ -232,21 +203,21 @@ struct Eigen {
     double id0, id1, id2; // 1 / prod_{j != k} (l_k - l_j)
 };
 __device__ __forceinline__ Eigen eigen_solve(double c2, double c1, double c0) {
-    // p, q and the cancellation-safe p^3 - q^2
+    // p, q and the cancellation-safe p^3 - q^2.  Both are clamped from below with a plain compare-select
+    // (fmax's NaN handling costs 5 instructions); p == 0 would mean H proportional to 1 (three equal roots),
+    // which no oscillation Hamiltonian with a non-zero mass splitting or matter term produces.
     double p = fma(c2, c2, -3.0 * c1);
-    p = fmax(p, 0.0);
+    p = p > kTab[20] ? p : kTab[20];
     const double q = fma(4.5 * c1, c2, fma(-13.5, c0, -c2 * c2 * c2));
-    double disc = 27.0 * fma(0.25 * c1 * c1, p - c1, c0 * fma(6.75, c0, q));
-    disc = fmax(disc, 0.0);
-    // sqrt(p) and p^(-3/2) from one rsqrt; p == 0 only for H proportional to 1 (all roots equal)
-    const bool p_ok = p > 1e-290;
-    const double rs = rsqrt_fast(p_ok ? p : 1.0);
-    const double b = p_ok ? kTab[17] * (p * rs) : 0.0;
+    const double disc = 27.0 * fma(0.25 * c1 * c1, p - c1, c0 * fma(6.75, c0, q));
+    // sqrt(p) and p^(-3/2) from one rsqrt
+    const double rs = rsqrt_fast(p);
+    const double b = kTab[17] * (p * rs);
     const double inv = rs * rs * rs;
     const double base = -c2 * kTab[16];
     double st, ct;
     // theta = atan2(sqrt(disc), q) / 3 in [0, pi/3]
-    unit_cube_root(p_ok ? q * inv : 1.0, p_ok ? sqrt_fast(disc) * inv : 0.0, &ct, &st);
+    unit_cube_root(q * inv, sqrt_pos(disc) * inv, &ct, &st);
     const double kh = 0.5, ks = kTab[15]; // cos, sin of pi/3
     Eigen e;
     // theta+2pi/3 -> smallest root, theta-2pi/3 -> middle, theta -> largest (:795-797)
