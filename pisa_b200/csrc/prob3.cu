@@ -231,7 +231,9 @@ struct FusedBatch {
 // Body shared by the one-template kernel (oscillation table in the parameter constant bank) and the
 // multi-template scan kernel (table of this block's template in shared memory): `rank` of `n_ranks`
 // blocks cooperate on one template; partials: [container][n_ranks][2 n_bins] of that template.
-template <typename IO, bool STD>
+// PLAIN: no per-event outputs and no per-event nubar / flav arrays (the fit-loop case): the null checks and
+// the three optional stores disappear from the event loop.
+template <typename IO, bool STD, bool PLAIN>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
                                                     const FusedBatch<IO> &batch, int rank, int n_ranks,
                                                     double *__restrict__ partials, double *s_hist) {
@@ -281,8 +283,8 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                     cp_async<sizeof(IO)>(&s_cz[tid], coszen + i_next);
                 }
                 cp_async_commit();
-                const int nb = C.d_nubar ? __ldg(C.d_nubar + i) : C.nubar;
-                const int fl = C.d_flav ? __ldg(C.d_flav + i) : C.flav;
+                const int nb = (!PLAIN && C.d_nubar) ? __ldg(C.d_nubar + i) : C.nubar;
+                const int fl = (!PLAIN && C.d_flav) ? __ldg(C.d_flav + i) : C.flav;
                 const double inv_e = rcp_fast(e);
                 H0Smem<STD> h0{&s_h0[0][tid], kBlock};
                 {
@@ -298,9 +300,11 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
                 w = (double)s_w[tid] * (fe * pe + fm * pmu) * C.scale;
                 bin = s_bin[tid];
-                if (C.weights_out) C.weights_out[i] = (IO)w;
-                if (C.prob_e) C.prob_e[i] = (IO)pe;
-                if (C.prob_mu) C.prob_mu[i] = (IO)pmu;
+                if (!PLAIN) {
+                    if (C.weights_out) C.weights_out[i] = (IO)w;
+                    if (C.prob_e) C.prob_e[i] = (IO)pe;
+                    if (C.prob_mu) C.prob_mu[i] = (IO)pmu;
+                }
             }
             wh.add(bin, w);
             i_cur = i_next;
@@ -311,7 +315,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     }
 }
 
-template <typename IO, bool STD>
+template <typename IO, bool STD, bool PLAIN>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      const __grid_constant__ FusedBatch<IO> batch, double *__restrict__ partials) {
@@ -320,7 +324,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
     // DFMA takes such an operand directly); the Earth table is indexed per lane and goes to shared memory
     copy_earth(earth, &s_earth);
-    fused_template_body<IO, STD>(osc, s_earth, batch, blockIdx.x, gridDim.x, partials, s_hist);
+    fused_template_body<IO, STD, PLAIN>(osc, s_earth, batch, blockIdx.x, gridDim.x, partials, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves template b / R with rank
@@ -344,7 +348,7 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     }
     copy_earth(earth, &s_earth); // ends with __syncthreads()
     double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
-    fused_template_body<IO, STD>(s_osc, s_earth, batch, rank, ranks_per_template, mine, s_hist);
+    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, rank, ranks_per_template, mine, s_hist);
 }
 
 } // namespace pisab
@@ -495,7 +499,13 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     const bool std_matter = ot.std_matter != 0.0;
 #endif
     const size_t smem = fused_smem_bytes<IO>(n_bins, std_matter);
-    auto kernel = std_matter ? reweight_hist_kernel<IO, true> : reweight_hist_kernel<IO, false>;
+    bool plain = true;
+    for (int c = 0; c < batch.n_containers; ++c) {
+        const FusedContainer<IO> &C = batch.c[c];
+        plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu;
+    }
+    auto kernel = std_matter ? (plain ? reweight_hist_kernel<IO, true, true> : reweight_hist_kernel<IO, true, false>)
+                             : (plain ? reweight_hist_kernel<IO, false, true> : reweight_hist_kernel<IO, false, false>);
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;

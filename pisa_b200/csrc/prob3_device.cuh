@@ -72,7 +72,7 @@ __constant__ double kTab[24] = {
 __device__ __forceinline__ double rcp_seed(double x) {
     double r;
 #ifdef PISAB_HOST_EMU
-    r = (double)(float)(1.0 / x);
+    r = pisab_emu_hi32(1.0 / x); // the hardware result carries only the upper 32 bits
 #else
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
@@ -81,7 +81,7 @@ __device__ __forceinline__ double rcp_seed(double x) {
 __device__ __forceinline__ double rsqrt_seed(double x) {
     double r;
 #ifdef PISAB_HOST_EMU
-    r = (double)(float)(1.0 / sqrt(x));
+    r = pisab_emu_hi32(1.0 / sqrt(x));
 #else
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
 #endif
@@ -358,7 +358,7 @@ __device__ __forceinline__ double shell_root_fast(double rd2, double cz2, double
 #ifdef PISAB_EXACT_SQRT
     return shell_root(rd2, cz2, rj2);
 #else
-    return sqrt_fast(__dadd_rn(__dsub_rn(__dmul_rn(rd2, cz2), rd2), rj2));
+    return sqrt_pos(__dadd_rn(__dsub_rn(__dmul_rn(rd2, cz2), rd2), rj2)); // (a crossed shell has a positive argument)
 #endif
 }
 

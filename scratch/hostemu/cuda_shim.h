@@ -25,3 +25,7 @@ static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x)
 #define __sincosf pisab_emu_sincosf
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
+#include <cstring>
+static inline double pisab_emu_hi32(double v) {
+    uint64_t b; std::memcpy(&b, &v, 8); b &= 0xffffffff00000000ull; std::memcpy(&v, &b, 8); return v;
+}
