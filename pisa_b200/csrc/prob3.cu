@@ -243,7 +243,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
-    double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn);
+    double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn); // 16-byte aligned: see H0Smem
     s_dyn += H0Smem<STD>::kDoubles * kBlock;
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;

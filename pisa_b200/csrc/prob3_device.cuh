@@ -573,43 +573,57 @@ struct H0Reg {
 };
 template <bool STD>
 struct H0Smem {
-    double *col; // &s_h0[0][threadIdx.x]; rows: h0 (9) [+ invariants (5) + h0^2 (9) when STD]
+    // Per-thread column in shared memory, stored as double2 rows (one 128-bit access per pair, conflict free)
+    // plus one trailing double row:
+    //   general : (d0,d1) (d2,r01) (i01,r02) (i02,r12) | i12                                  = 9 doubles
+    //   STD     : (d0,d1) (d2,r01) (i01,r02) (i02,r12) (i12,c2_0) (c1_0,c0_0) (d1+d2, m00)
+    //             (q.d0,q.d1) (q.d2,q.r01) (q.i01,q.r02) (q.i02,q.r12) | q.i12   (q = h0^2)   = 23 doubles
+    double *col; // &s_h0[0][threadIdx.x] of a [kDoubles][pitch] double block
     int pitch;   // block size
-    static constexpr int kDoubles = STD ? 23 : 9;
+    static constexpr int kPairs = STD ? 11 : 4;
+    static constexpr int kDoubles = 2 * kPairs + 1;
+    __device__ __forceinline__ double2 &pair(int r) const { return reinterpret_cast<double2 *>(col - threadIdx.x)[r * pitch + threadIdx.x]; }
+    __device__ __forceinline__ double &single() const { return (col - threadIdx.x)[2 * kPairs * pitch + threadIdx.x]; }
+
     __device__ __forceinline__ void store(const Herm3 &h) {
-        col[0] = h.d0; col[pitch] = h.d1; col[2 * pitch] = h.d2;
-        col[3 * pitch] = h.r01; col[4 * pitch] = h.i01; col[5 * pitch] = h.r02;
-        col[6 * pitch] = h.i02; col[7 * pitch] = h.r12; col[8 * pitch] = h.i12;
+        pair(0) = make_double2(h.d0, h.d1);
+        pair(1) = make_double2(h.d2, h.r01);
+        pair(2) = make_double2(h.i01, h.r02);
+        pair(3) = make_double2(h.i02, h.r12);
+        if (!STD) single() = h.i12;
     }
     __device__ __forceinline__ Herm3 load() const {
         Herm3 h;
-        h.d0 = col[0]; h.d1 = col[pitch]; h.d2 = col[2 * pitch];
-        h.r01 = col[3 * pitch]; h.i01 = col[4 * pitch]; h.r02 = col[5 * pitch];
-        h.i02 = col[6 * pitch]; h.r12 = col[7 * pitch]; h.i12 = col[8 * pitch];
+        const double2 a = pair(0), b = pair(1), c = pair(2), e = pair(3);
+        h.d0 = a.x; h.d1 = a.y; h.d2 = b.x; h.r01 = b.y; h.i01 = c.x; h.r02 = c.y; h.i02 = e.x; h.r12 = e.y;
+        h.i12 = STD ? pair(4).x : single();
         return h;
     }
     __device__ __forceinline__ void set_poly(const Herm3 &h) {
         double c2, c1, c0;
         char_poly(h, c2, c1, c0);
-        col[9 * pitch] = c2; col[10 * pitch] = c1; col[11 * pitch] = c0;
-        col[12 * pitch] = h.d1 + h.d2;
-        col[13 * pitch] = fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12));
+        pair(4) = make_double2(h.i12, c2);
+        pair(5) = make_double2(c1, c0);
+        pair(6) = make_double2(h.d1 + h.d2, fma(h.d1, h.d2, -fma(h.r12, h.r12, h.i12 * h.i12)));
         const Herm3 s = herm_square(h);
-        col[14 * pitch] = s.d0; col[15 * pitch] = s.d1; col[16 * pitch] = s.d2;
-        col[17 * pitch] = s.r01; col[18 * pitch] = s.i01; col[19 * pitch] = s.r02;
-        col[20 * pitch] = s.i02; col[21 * pitch] = s.r12; col[22 * pitch] = s.i12;
+        pair(7) = make_double2(s.d0, s.d1);
+        pair(8) = make_double2(s.d2, s.r01);
+        pair(9) = make_double2(s.i01, s.r02);
+        pair(10) = make_double2(s.i02, s.r12);
+        single() = s.i12;
     }
     __device__ __forceinline__ Herm3 load_sq() const {
         Herm3 s;
-        s.d0 = col[14 * pitch]; s.d1 = col[15 * pitch]; s.d2 = col[16 * pitch];
-        s.r01 = col[17 * pitch]; s.i01 = col[18 * pitch]; s.r02 = col[19 * pitch];
-        s.i02 = col[20 * pitch]; s.r12 = col[21 * pitch]; s.i12 = col[22 * pitch];
+        const double2 a = pair(7), b = pair(8), c = pair(9), e = pair(10);
+        s.d0 = a.x; s.d1 = a.y; s.d2 = b.x; s.r01 = b.y; s.i01 = c.x; s.r02 = c.y; s.i02 = e.x; s.r12 = e.y;
+        s.i12 = single();
         return s;
     }
     __device__ __forceinline__ void poly(double x, double &c2, double &c1, double &c0) const {
-        c2 = col[9 * pitch] - x;
-        c1 = fma(x, col[12 * pitch], col[10 * pitch]);
-        c0 = fma(-x, col[13 * pitch], col[11 * pitch]);
+        const double2 u = pair(5), v = pair(6);
+        c2 = pair(4).y - x;
+        c1 = fma(x, v.x, u.x);
+        c0 = fma(-x, v.y, u.y);
     }
 };
 
