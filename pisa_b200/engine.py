@@ -155,7 +155,7 @@ class ReweightEngine:
         batches = self._get_batches()
         if len(batches) != 1:
             raise NotImplementedError("evaluate_many supports up to %d containers" % ops.MAX_BATCH)
-        out = ops.reweight_hist_scan(list(consts_list), self.earth, batches[0][1])
+        out = ops.reweight_hist_scan(consts_list, self.earth, batches[0][1])
         if allreduce:
             self.allreduce(out)
         return out

@@ -416,7 +416,7 @@ def reweight_hist_scan(consts_list, earth, batch, out=None):
     n_t = len(consts_list)
     if n_t < 1:
         raise ValueError("at least one template")
-    arr = (OscConsts * n_t)(*consts_list)
+    arr = consts_list if isinstance(consts_list, ctypes.Array) else (OscConsts * n_t)(*consts_list)
     if out is None:
         out = torch.empty((n_t, batch.n, 2, batch.n_bins), dtype=torch.float64, device=batch.device)
     _chk(out, "out", torch.float64)

@@ -15,7 +15,7 @@ import torch
 from . import ops
 from .stages.osc.osc_params import OscParams
 
-__all__ = ["osc_consts", "scan_chi2", "asimov"]
+__all__ = ["osc_consts", "osc_consts_array", "scan_chi2", "asimov"]
 
 
 def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
@@ -28,6 +28,50 @@ def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
         mat_pot = np.zeros((3, 3), dtype=np.complex128)
         mat_pot[0, 0] = 1.0
     return ops.OscConsts.from_matrices(op.dm_matrix, op.mix_matrix_complex, mat_pot)
+
+
+def osc_consts_array(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
+    """Vectorised ``osc_consts``: any of the six parameters may be an array of P values (the others
+    broadcast); returns a ctypes array ``OscConsts[P]`` for ``ops.reweight_hist_scan``.  Same arithmetic as
+    ``OscParams`` (sines stored, cosines as sqrt(1 - s^2), osc_params.py:175-211,266-292); building the
+    hypotheses one by one costs ~50 us each in Python, which would dominate a scan over an analysis-size
+    sample."""
+    t12, t13, t23, dcp, m21, m31 = np.broadcast_arrays(*[np.atleast_1d(np.asarray(x, dtype=np.float64))
+                                                         for x in (theta12, theta13, theta23, deltacp, dm21, dm31)])
+    n = t12.shape[0]
+    if not np.all((dcp >= 0.0) & (dcp <= 2 * np.pi)):
+        raise AssertionError("deltacp must be within [0, 2pi]")
+    s12, s13, s23 = np.sin(t12), np.sin(t13), np.sin(t23)
+    c12, c13, c23 = np.sqrt(1.0 - s12 ** 2), np.sqrt(1.0 - s13 ** 2), np.sqrt(1.0 - s23 ** 2)
+    sd, cd = np.sin(dcp), np.cos(dcp)
+    rec = np.zeros((n, 73), dtype=np.float64)   # dm[9] mix[18] mat_pot[18] mat_decay[18] lri_pot[9] decay_flag
+    # dm matrix (osc_params.py:266-292)
+    m = np.stack([np.zeros(n), m21, m31], axis=1)
+    m[:, 0] -= np.where(m[:, 1] == 0.0, 5.0e-9, 0.0)
+    m[:, 2] += np.where(m[:, 2] == 0.0, 5.0e-9, 0.0)
+    dm = m[:, :, None] - m[:, None, :]
+    dm[:, [0, 1, 2], [0, 1, 2]] = 0.0
+    rec[:, 0:9] = dm.reshape(n, 9)
+    # PMNS, standard parameterisation (re, im interleaved, row-major)
+    u = np.zeros((n, 3, 3, 2))
+    u[:, 0, 0, 0] = c12 * c13
+    u[:, 0, 1, 0] = s12 * c13
+    u[:, 0, 2, 0], u[:, 0, 2, 1] = s13 * cd, -s13 * sd
+    u[:, 1, 0, 0], u[:, 1, 0, 1] = -s12 * c23 - c12 * s23 * s13 * cd, -c12 * s23 * s13 * sd
+    u[:, 1, 1, 0], u[:, 1, 1, 1] = c12 * c23 - s12 * s23 * s13 * cd, -s12 * s23 * s13 * sd
+    u[:, 1, 2, 0] = s23 * c13
+    u[:, 2, 0, 0], u[:, 2, 0, 1] = s12 * s23 - c12 * c23 * s13 * cd, -c12 * c23 * s13 * sd
+    u[:, 2, 1, 0], u[:, 2, 1, 1] = -c12 * s23 - s12 * c23 * s13 * cd, -s12 * c23 * s13 * sd
+    u[:, 2, 2, 0] = c23 * c13
+    rec[:, 9:27] = u.reshape(n, 18)
+    if mat_pot is None:
+        rec[:, 27] = 1.0
+    else:
+        mp = np.asarray(mat_pot, dtype=np.complex128).reshape(3, 3)
+        rec[:, 27:45] = np.stack([mp.real, mp.imag], axis=-1).ravel()
+    rec[:, 72] = np.array([-1], dtype=np.int64).view(np.float64)[0]   # decay_flag = -1
+    arr = (ops.OscConsts * n).from_buffer_copy(np.ascontiguousarray(rec).tobytes())
+    return arr
 
 
 def asimov(engine, consts):
@@ -56,10 +100,11 @@ def scan_chi2(engine, observed, points, fixed, mat_pot=None, batch=64):
             hist = engine.evaluate(consts)
             ops.template_chi2(hist, observed, out=out[i:i + 1])
         return out
+    pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
     for lo in range(0, len(points), batch):
-        chunk = points[lo:lo + batch]
-        consts = [osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
-                  for t23, dm31 in chunk]
+        chunk = pts[lo:lo + batch]
+        consts = osc_consts_array(fixed["theta12"], fixed["theta13"], chunk[:, 0], fixed["deltacp"], fixed["dm21"],
+                                  chunk[:, 1], mat_pot)
         hist = engine.evaluate_many(consts)
         ops.template_chi2_batch(hist, observed, out=out[lo:lo + len(chunk)])
     return out

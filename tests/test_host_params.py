@@ -2,6 +2,7 @@
 import os
 
 import numpy as np
+import pytest
 
 from conftest import ROOT, load_golden
 from pisa_b200.stages.osc.layers import Layers
@@ -63,3 +64,23 @@ def test_layers_host_tables_bitwise():
         rhos = L.rhos.copy()
         L.setElecFrac(yei, yeo, yem)
         assert np.array_equal(rhos, L.rhos)
+
+
+def test_vectorised_osc_consts_equal_the_scalar_builder():
+    """scan.osc_consts_array (one numpy pass for P hypotheses) == scan.osc_consts per hypothesis, bit for bit."""
+    import ctypes
+    from pisa_b200 import scan
+    rng = np.random.default_rng(3)
+    n = 40
+    t23, dm31 = rng.uniform(0.5, 1.0, n), rng.uniform(-3e-3, 3e-3, n)
+    dm31[3] = 0.0    # degeneracy nudge branch of dm_matrix
+    fixed = dict(theta12=0.58, theta13=0.148, deltacp=4.1, dm21=7.5e-5)
+    mp = np.array([[1.0, 0.07 + 0.02j, 0], [0.07 - 0.02j, 0, 0.003j], [0, -0.003j, 0.1]])
+    for mat_pot in (None, mp):
+        arr = scan.osc_consts_array(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
+        assert len(arr) == n
+        for k in range(n):
+            one = scan.osc_consts(fixed["theta12"], fixed["theta13"], t23[k], fixed["deltacp"], fixed["dm21"], dm31[k], mat_pot)
+            assert bytes(one) == bytes(arr[k]), k
+    with pytest.raises(AssertionError):
+        scan.osc_consts_array(0.5, 0.1, 0.7, 7.0, 7e-5, 2e-3)
