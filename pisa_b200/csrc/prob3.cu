@@ -368,6 +368,21 @@ static int grid_for(int64_t n, int blocks_per_sm) {
 
 // Persistent grid: exactly the number of blocks that are resident at once (one wave), so that the
 // grid-stride loop gives every block the same share of every layer-count class.
+#ifndef PISAB_WAVES
+#define PISAB_WAVES 4
+#endif
+
+// PISAB_WAVES static waves of blocks instead of one persistent wave: a block's share of the deep-core events
+// varies, and with one wave nothing refills an SM whose blocks finish early (measured tail: ~3-6 %); the
+// hardware scheduler balances several smaller waves, and the block -> events map stays static, so histograms
+// remain bit-reproducible.  Whole waves only, and every thread keeps >= 8 events.
+static int waved_grid(int resident, int64_t n_max) {
+    const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
+    int64_t waves = by_work / (resident > 0 ? resident : 1);
+    if (waves > PISAB_WAVES) waves = PISAB_WAVES;
+    return waves > 1 ? (int)(resident * waves) : resident;
+}
+
 template <typename K>
 static int resident_grid(K kernel, int64_t n, size_t smem) {
     int occ = 0;
@@ -402,7 +417,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
         const size_t smem = earth_smem_bytes<true>(sizeof(IO), false);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
-        kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
+        kernel<<<waved_grid(resident_grid(kernel, n, smem), n), kBlock, smem, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, d_probability, nullptr, nullptr);
         note_launch();
     }
@@ -422,7 +437,7 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
         const size_t smem = earth_smem_bytes<false>(sizeof(IO), std_matter);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
-        kernel<<<resident_grid(kernel, n, smem), kBlock, smem, s>>>(
+        kernel<<<waved_grid(resident_grid(kernel, n, smem), n), kBlock, smem, s>>>(
             ot, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n, nullptr, d_prob_e, d_prob_mu);
         note_launch();
     }
@@ -521,21 +536,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (fa.sharedSizeBytes + smem > 48 * 1024)
             PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    // PISAB_WAVES static waves of blocks instead of one persistent wave: a block's share of the deep-core
-    // events varies, and with one wave nothing refills an SM whose two blocks finish early (measured tail:
-    // ~6 %); the hardware scheduler balances several smaller waves, and the block -> events map stays static,
-    // so the histogram is still bit-reproducible.  Each thread keeps >= 8 events per container.
-#ifndef PISAB_WAVES
-#define PISAB_WAVES 4
-#endif
-    int grid = resident_grid(kernel, n_max, smem);
-    {
-        // whole waves only (a partial last wave is the tail this is meant to remove)
-        const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
-        int64_t waves = by_work / grid;
-        if (waves > PISAB_WAVES) waves = PISAB_WAVES;
-        if (waves > 1) grid = (int)(grid * waves);
-    }
+    const int grid = waved_grid(resident_grid(kernel, n_max, smem), n_max);
     {
         LaunchTimer t(s);
         kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, (double *)d_workspace);
