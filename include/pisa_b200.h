@@ -167,6 +167,21 @@ int pisab_flux_barr_simple_f32(const float *d_energy, const float *d_coszen, con
                                double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
                                double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux, void *stream);
 
+/* Fit-loop form of flux.barr_simple: everything transcendental in apply_sys_kernel depends on the event only.
+ * pisab_flux_barr_terms_* stores those four per-event terms once (d_terms: double[n,4], 32-byte aligned);
+ * pisab_flux_barr_apply_* then evaluates nu_flux for a set of systematic parameters from the terms and the
+ * nominal fluxes (HBM-bound, 80 B/event).  Same result as pisab_flux_barr_simple_* to rounding. */
+int pisab_flux_barr_terms_f64(const double *d_energy, const double *d_coszen, int64_t n, double *d_terms, void *stream);
+int pisab_flux_barr_terms_f32(const float *d_energy, const float *d_coszen, int64_t n, double *d_terms, void *stream);
+int pisab_flux_barr_apply_f64(const double *d_terms, const double *d_nu_flux_nominal, const double *d_nubar_flux_nominal,
+                              int32_t nubar, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
+                              double barr_uphor_ratio, double barr_nu_nubar_ratio, int64_t n, double *d_nu_flux,
+                              void *stream);
+int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nominal, const float *d_nubar_flux_nominal,
+                              int32_t nubar, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
+                              double barr_uphor_ratio, double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux,
+                              void *stream);
+
 /* ---- flux.honda_ip (pisa/stages/flux/honda_ip.py:86-104, pisa/utils/flux_weights.py:267-350) ---------- */
 /* calculate_2d_flux_weights for all four primaries of one azimuth-averaged Honda table in one pass:
  * d_nu_flux_nominal[n,2] = (nue, numu), d_nubar_flux_nominal[n,2] = (nuebar, numubar).

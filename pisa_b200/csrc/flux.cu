@@ -99,14 +99,81 @@ flux_barr_simple_kernel(const __grid_constant__ BarrTable T, const IO *__restric
     }
 }
 
+// ---- fit-loop form: parameter-independent terms once, cheap per-template apply -----------------
+// Everything transcendental in apply_sys_kernel depends on the event only, not on the five systematic
+// parameters:   t0 = ln(E / E0)                       (spectral index: (E/E0)^delta = exp(delta t0))
+//               t1 = ModFlux(nue; E, cz), t2 = ModFlux(numu; E, cz)    (Barr nu/nubar, unit shape parameters)
+//               t3 = LogLog(E) exp(-E/650) N(cz; 0.35)                 (Barr up/horizontal: 1 - 0.3 uphor t3)
+// flux_barr_terms_kernel stores them once per container ([n,4] doubles); flux_barr_apply_kernel then needs one
+// exp, nine reciprocals and ~30 FMAs per event and is HBM-bound (80 B/event) instead of bound by ~12 FP64
+// transcendentals.  ratio_scale is homogeneous of degree one, so the spectral-index factor is applied last.
 template <typename IO>
-static int flux_impl(const IO *d_energy, const IO *d_coszen, const IO *d_nu, const IO *d_nubar, int32_t nubar,
-                     double nue_numu_ratio, double nu_nubar_ratio, double delta_index, double uphor,
-                     double nubar_sys, int64_t n, IO *d_out, void *stream) {
-    if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_nu || !d_nubar || !d_out))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
-    if (nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
-    if (n == 0) return PISAB_OK;
-    BarrTable T;
+__global__ void __launch_bounds__(256)
+flux_barr_terms_kernel(const __grid_constant__ BarrTable T, const IO *__restrict__ energy,
+                       const IO *__restrict__ coszen, int64_t n, double *__restrict__ terms) {
+    const double inv_norm36 = 1.0 / sqrt(2 * M_PI * 0.36 * 0.36), inv_2s36 = 1.0 / (2 * 0.36 * 0.36);
+    const double inv_norm35 = 1.0 / sqrt(2 * M_PI * 0.35 * 0.35), inv_2s35 = 1.0 / (2 * 0.35 * 0.35);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = (double)__ldg(energy + i), cz = (double)__ldg(coszen + i);
+        const double l10 = log10(e);
+        const double cut_e = exp(-e / 650.), cut_mu = exp(-e / 1000.);
+        const double gauss36 = exp(-cz * cz * inv_2s36), gauss35 = exp(-cz * cz * inv_2s35);
+        const double As_e = loglog(T.shape_e, l10) * cut_e, As_mu = 2.5 * (loglog(T.shape_mu, l10) * cut_mu);
+        double4 t;
+        t.x = log(e / 24.0900951261);
+        t.y = loglog(T.ave_e, l10) - (1.5 * (As_e * inv_norm36 * gauss36) - 0.7 * As_e);
+        t.z = loglog(T.ave_mu, l10) - ((As_mu * inv_norm36 * gauss36) - 0.6 * As_mu);
+        t.w = loglog(T.uphor_e, l10) * cut_e * inv_norm35 * gauss35;
+        reinterpret_cast<double4 *>(terms)[i] = t;
+    }
+}
+
+__device__ __forceinline__ double rcp_nr(double x) { // 1/x to ~1 ulp (MUFU seed + third-order step)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double e = fma(-x, r, 1.0);
+    return fma(r * e, 1.0 + e, r);
+}
+__device__ __forceinline__ void ratio_scale_fast(double scale, double in1, double in2, double &o0, double &o1) {
+    if (in1 == 0. && in2 == 0.) { o0 = 0.; o1 = 0.; return; }
+    const double sr = scale * (in1 * rcp_nr(in2));
+    const double nw = (in1 + in2) * rcp_nr(1. + sr);
+    o0 = sr * nw;
+    o1 = nw;
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+flux_barr_apply_kernel(const __grid_constant__ BarrTable T, const double *__restrict__ terms,
+                       const IO *__restrict__ nu_nom, const IO *__restrict__ nubar_nom, int nubar, int64_t n,
+                       IO *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double2 ta = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i);
+        const double2 tb = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i + 1);
+        struct { double x, y, z, w; } t = {ta.x, ta.y, tb.x, tb.y};
+        const double nu0 = (double)__ldg(nu_nom + 2 * i), nu1 = (double)__ldg(nu_nom + 2 * i + 1);
+        const double nb0 = (double)__ldg(nubar_nom + 2 * i), nb1 = (double)__ldg(nubar_nom + 2 * i + 1);
+        double a0, a1, b0, b1, e_nu, e_nb, m_nu, m_nb;
+        ratio_scale_fast(T.nue_numu_ratio, nu0, nu1, a0, a1);
+        ratio_scale_fast(T.nue_numu_ratio, nb0, nb1, b0, b1);
+        ratio_scale_fast(T.nu_nubar_ratio, a0, b0, e_nu, e_nb);
+        ratio_scale_fast(T.nu_nubar_ratio, a1, b1, m_nu, m_nb);
+        double o0 = nubar < 0 ? e_nb : e_nu, o1 = nubar < 0 ? m_nb : m_nu;
+        const double h0 = 0.5 * T.nubar_sys * t.y, h1 = 0.5 * T.nubar_sys * t.z;
+        const double f0 = nubar < 0 ? rcp_nr(1. + h0) : 1. + h0, f1 = nubar < 0 ? rcp_nr(1. + h1) : 1. + h1;
+        o0 *= fmax(0., f0);
+        o1 *= fmax(0., f1);
+        o0 *= fma(-0.3 * T.uphor, t.w, 1.0);
+        const double idx_scale = exp(T.delta_index * t.x);
+        out[2 * i] = (IO)(o0 * idx_scale);
+        out[2 * i + 1] = (IO)(o1 * idx_scale);
+    }
+}
+
+static void fill_barr_table(BarrTable &T, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
+                            double uphor, double nubar_sys) {
     // constants of ModFlux / modRatioUpHor (barr_parameterization.py:44-61,85-94)
     const double e1max_mu = 3., e2max_mu = 43, e1max_e = 2.5, e2max_e = 10, x1e = 0.5, x2e = 3.;
     const double z1max_mu = 0.6, z2max_mu = 5., z1max_e = 0.3, z2max_e = 5., x1z = 0.5, x2z = 2.;
@@ -117,6 +184,52 @@ static int flux_impl(const IO *d_energy, const IO *d_coszen, const IO *d_nu, con
     T.uphor_e = fold_loglog(z1max_e + z1max_mu, z2max_e + z2max_mu, x1z, x2z);
     T.nue_numu_ratio = nue_numu_ratio; T.nu_nubar_ratio = nu_nubar_ratio; T.delta_index = delta_index;
     T.uphor = uphor; T.nubar_sys = nubar_sys;
+}
+
+static int flux_grid(int64_t n) {
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t want = (n + 255) / 256;
+    return (int)(want < (int64_t)sms * 8 ? (want < 1 ? 1 : want) : (int64_t)sms * 8);
+}
+
+template <typename IO>
+static int flux_terms_impl(const IO *d_energy, const IO *d_coszen, int64_t n, double *d_terms, void *stream) {
+    if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_terms))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if ((uintptr_t)d_terms % 32 != 0) { set_error("d_terms must be 32-byte aligned"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    BarrTable T;
+    fill_barr_table(T, 1, 1, 0, 0, 0);
+    flux_barr_terms_kernel<IO><<<flux_grid(n), 256, 0, (cudaStream_t)stream>>>(T, d_energy, d_coszen, n, d_terms);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+template <typename IO>
+static int flux_apply_impl(const double *d_terms, const IO *d_nu, const IO *d_nubar, int32_t nubar,
+                           double nue_numu_ratio, double nu_nubar_ratio, double delta_index, double uphor,
+                           double nubar_sys, int64_t n, IO *d_out, void *stream) {
+    if (n < 0 || (n > 0 && (!d_terms || !d_nu || !d_nubar || !d_out))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if (nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
+    if ((uintptr_t)d_terms % 32 != 0) { set_error("d_terms must be 32-byte aligned"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    BarrTable T;
+    fill_barr_table(T, nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys);
+    flux_barr_apply_kernel<IO><<<flux_grid(n), 256, 0, (cudaStream_t)stream>>>(T, d_terms, d_nu, d_nubar, nubar, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+template <typename IO>
+static int flux_impl(const IO *d_energy, const IO *d_coszen, const IO *d_nu, const IO *d_nubar, int32_t nubar,
+                     double nue_numu_ratio, double nu_nubar_ratio, double delta_index, double uphor,
+                     double nubar_sys, int64_t n, IO *d_out, void *stream) {
+    if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_nu || !d_nubar || !d_out))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if (nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
+    if (n == 0) return PISAB_OK;
+    BarrTable T;
+    fill_barr_table(T, nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys);
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + 255) / 256;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
@@ -144,6 +257,26 @@ int pisab_flux_barr_simple_f32(const float *d_energy, const float *d_coszen, con
                                double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux, void *stream) {
     return flux_impl<float>(d_energy, d_coszen, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio,
                             nu_nubar_ratio, delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
+}
+int pisab_flux_barr_terms_f64(const double *d_energy, const double *d_coszen, int64_t n, double *d_terms, void *stream) {
+    return flux_terms_impl<double>(d_energy, d_coszen, n, d_terms, stream);
+}
+int pisab_flux_barr_terms_f32(const float *d_energy, const float *d_coszen, int64_t n, double *d_terms, void *stream) {
+    return flux_terms_impl<float>(d_energy, d_coszen, n, d_terms, stream);
+}
+int pisab_flux_barr_apply_f64(const double *d_terms, const double *d_nu_flux_nominal, const double *d_nubar_flux_nominal,
+                              int32_t nubar, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
+                              double barr_uphor_ratio, double barr_nu_nubar_ratio, int64_t n, double *d_nu_flux,
+                              void *stream) {
+    return flux_apply_impl<double>(d_terms, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio, nu_nubar_ratio,
+                                   delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
+}
+int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nominal, const float *d_nubar_flux_nominal,
+                              int32_t nubar, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
+                              double barr_uphor_ratio, double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux,
+                              void *stream) {
+    return flux_apply_impl<float>(d_terms, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio, nu_nubar_ratio,
+                                  delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
 }
 }
 

@@ -90,6 +90,43 @@ def flux_barr_simple(true_energy, true_coszen, nu_flux_nominal, nubar_flux_nomin
     return out
 
 
+def flux_barr_terms(true_energy, true_coszen, out=None):
+    """The four parameter-independent per-event terms of flux.barr_simple (float64 [n, 4]); see
+    ``pisab_flux_barr_terms_*``.  Computed once per container; ``flux_barr_apply`` uses them per template."""
+    _chk(true_energy, "true_energy")
+    _chk(true_coszen, "true_coszen", true_energy.dtype)
+    n = true_energy.numel()
+    if true_coszen.numel() != n:
+        raise ValueError("inconsistent event array shapes")
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.float64, device=true_energy.device)
+    _chk(out, "out", torch.float64)
+    f = _lib.fn("pisab_flux_barr_terms", true_energy.dtype)
+    _lib.check(f(_ptr(true_energy), _ptr(true_coszen), n, _ptr(out), _stream()))
+    return out
+
+
+def flux_barr_apply(terms, nu_flux_nominal, nubar_flux_nominal, nubar, nue_numu_ratio, nu_nubar_ratio, delta_index,
+                    Barr_uphor_ratio, Barr_nu_nubar_ratio, out=None):
+    """``nu_flux`` [n, 2] from precomputed ``flux_barr_terms`` and the nominal fluxes: the fit-loop form of
+    ``flux_barr_simple`` (same result to rounding, HBM-bound)."""
+    _chk(terms, "terms", torch.float64)
+    _chk(nu_flux_nominal, "nu_flux_nominal")
+    dt = nu_flux_nominal.dtype
+    _chk(nubar_flux_nominal, "nubar_flux_nominal", dt)
+    n = terms.shape[0]
+    if terms.shape != (n, 4) or nu_flux_nominal.shape != (n, 2) or nubar_flux_nominal.shape != (n, 2):
+        raise ValueError("inconsistent event array shapes")
+    if out is None:
+        out = torch.empty((n, 2), dtype=dt, device=terms.device)
+    _chk(out, "out", dt)
+    f = _lib.fn("pisab_flux_barr_apply", dt)
+    _lib.check(f(_ptr(terms), _ptr(nu_flux_nominal), _ptr(nubar_flux_nominal), int(nubar), float(nue_numu_ratio),
+                 float(nu_nubar_ratio), float(delta_index), float(Barr_uphor_ratio), float(Barr_nu_nubar_ratio), n,
+                 _ptr(out), _stream()))
+    return out
+
+
 def flux_honda_2d(table, true_energy, true_coszen, nu_flux_nominal=None, nubar_flux_nominal=None):
     """``calculate_2d_flux_weights`` (flux_weights.py:267-350) for the four primaries of ``table``
     (a ``pisa_b200.utils.flux_weights.HondaTable2D``): returns (nu_flux_nominal, nubar_flux_nominal), [n, 2] each."""

@@ -6,8 +6,10 @@ keys ``true_energy, true_coszen, nu_flux_nominal, nubar_flux_nominal, nubar`` re
 written (``setup_function`` allocates it :73-75, ``compute_function`` fills it and marks it changed
 :78-104).  Like the reference it implements no ``apply_function``.
 
-``compute_function`` makes one call per container into the CUDA library (``pisab_flux_barr_simple``); the
-parameterisations of pisa/utils/barr_parameterization.py are evaluated there in FP64.
+Everything transcendental in the reference's ``apply_sys_kernel`` (the parameterisations of
+pisa/utils/barr_parameterization.py) depends on the event only, not on the five systematic parameters: those
+terms are evaluated once in ``setup_function`` (``pisab_flux_barr_terms``, FP64), and ``compute_function`` makes
+one HBM-bound call per container (``pisab_flux_barr_apply``) whenever a flux parameter changes.
 """
 from pisa_b200 import ops
 from pisa_b200.core.stage import Stage
@@ -27,6 +29,7 @@ class barr_simple(Stage):  # pylint: disable=invalid-name
         for container in self.data:
             e = container["true_energy"]
             container["nu_flux"] = e.new_empty((container.size, 2))
+            container["flux_barr_terms"] = ops.flux_barr_terms(e, container["true_coszen"])
 
     def compute_function(self):
         p = self.params
@@ -36,9 +39,9 @@ class barr_simple(Stage):  # pylint: disable=invalid-name
         uphor = p.Barr_uphor_ratio.value.m_as("dimensionless")
         nubar_sys = p.Barr_nu_nubar_ratio.value.m_as("dimensionless")
         for container in self.data:
-            ops.flux_barr_simple(container["true_energy"], container["true_coszen"], container["nu_flux_nominal"],
-                                 container["nubar_flux_nominal"], int(container["nubar"]), nue_numu_ratio,
-                                 nu_nubar_ratio, delta_index, uphor, nubar_sys, out=container["nu_flux"])
+            ops.flux_barr_apply(container["flux_barr_terms"], container["nu_flux_nominal"],
+                                container["nubar_flux_nominal"], int(container["nubar"]), nue_numu_ratio,
+                                nu_nubar_ratio, delta_index, uphor, nubar_sys, out=container["nu_flux"])
             container.mark_changed("nu_flux")
 
 

@@ -42,3 +42,6 @@ from pisa_b200.utils.flux_weights import HondaTable2D
 HT = HondaTable2D("flux/honda-2015-spl-solmin-aa.d")
 nu_o = torch.empty_like(ev["nu_flux"]); nb_o = torch.empty_like(ev["nu_flux"])
 rep("flux_honda_2d (4 primaries)", timeit(lambda: ops.flux_honda_2d(HT, ev["true_energy"], ev["true_coszen"], nu_o, nb_o)), 48)
+terms = ops.flux_barr_terms(ev["true_energy"], ev["true_coszen"])
+rep("flux_barr_terms (setup)", timeit(lambda: ops.flux_barr_terms(ev["true_energy"], ev["true_coszen"], out=terms)), 48)
+rep("flux_barr_apply (per template)", timeit(lambda: ops.flux_barr_apply(terms, ev["nu_flux"], nb_nom, 1, 1.03, 0.97, 0.05, 0.3, -0.2, out=fo)), 80)

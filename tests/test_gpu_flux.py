@@ -147,3 +147,26 @@ def test_full_flux_chain_pipeline():
                                   c["nu_flux_nominal"].cpu().numpy(), c["nubar_flux_nominal"].cpu().numpy(), -1,
                                   1.0, 1.0, 0.0, 0.0, 0.0)
     assert np.allclose(c["nu_flux"].cpu().numpy(), ref, rtol=1e-10)
+
+
+def test_flux_terms_plus_apply_equal_the_direct_kernel_and_the_oracle():
+    """fit-loop form (terms once, cheap apply per template) vs the direct kernel and vs the oracle, all five
+    fixture parameter sets, nu and nubar, incl. the zero-flux rows."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_flux_f8.npz")
+    T = lambda k: torch.tensor(g[k], device=dev)  # noqa: E731
+    e, cz, nu, nb = T("true_energy"), T("true_coszen"), T("nu_flux_nominal"), T("nubar_flux_nominal")
+    terms = ops.flux_barr_terms(e, cz)
+    assert terms.shape == (e.numel(), 4) and torch.isfinite(terms).all()
+    for name in sorted({k.split("/")[0] for k in g.files if "/" in k}):
+        pars = [float(x) for x in g[name + "/params"]]
+        for nubar, tag in ((1, "nu"), (-1, "nubar")):
+            out = ops.flux_barr_apply(terms, nu, nb, nubar, *pars).cpu().numpy()
+            ref = g["%s/%s" % (name, tag)]
+            assert np.allclose(out, ref, rtol=1e-10, atol=1e-300), (name, tag, np.abs(out - ref).max())
+            direct = ops.flux_barr_simple(e, cz, nu, nb, nubar, *pars).cpu().numpy()
+            assert np.allclose(out, direct, rtol=1e-13, atol=1e-300)
+    # float32 storage of the fluxes, terms stay float64
+    out4 = ops.flux_barr_apply(terms, nu.float(), nb.float(), -1, 0.95, 1.1, -0.1, -1.0, 1.0)
+    assert out4.dtype == torch.float32 and np.allclose(out4.cpu().numpy(), g["all_down/nubar"], rtol=3e-5, atol=1e-6)

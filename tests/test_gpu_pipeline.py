@@ -420,3 +420,47 @@ def test_engine_large_binning_falls_back_to_unfused_kernels():
     # same events, same weights: the totals agree whatever the binning (both binnings cover the same range)
     assert torch.allclose(hb[:, 0].sum(dim=1), hs[:, 0].sum(dim=1), rtol=1e-11)
     assert torch.allclose(hb[:, 1].sum(dim=1), hs[:, 1].sum(dim=1), rtol=1e-11)
+
+
+def test_engine_with_floating_flux_systematics():
+    """Fit loop with flux systematics: engine.set_flux_params rewrites nu_flux (flux.barr_simple from cached terms)
+    before the fused template; compared with oracle flux + oracle propagation + oracle histogram."""
+    _need_gpu()
+    import oracle as orc
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    OL = _oracle_layers()
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    dm, mix, mat_pot = syn.osc_matrices()
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    eng = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    host = []
+    for i, (name, nubar, flav) in enumerate([syn.CONTAINERS[1], syn.CONTAINERS[6]]):
+        ev = syn.make_events_numpy(6000 + i, seed=90 + i)
+        nom_nu, nom_nb = ev["nu_flux"], ev["nu_flux"] * 0.8
+        t = {k: torch.tensor(v, device=dev) for k, v in ev.items()}
+        idx = ops.hist_index(binning, [t["reco_energy"], t["reco_coszen"], t["pid"]])
+        eng.add_container(name, nubar, flav, t["true_energy"], t["true_coszen"], t["nu_flux"].clone(), t["weights"], idx,
+                          nu_flux_nominal=t["nu_flux"], nubar_flux_nominal=torch.tensor(nom_nb, device=dev))
+        host.append((nubar, flav, ev, nom_nu, nom_nb, idx.cpu().numpy()))
+    pars = dict(nue_numu_ratio=1.04, nu_nubar_ratio=0.93, delta_index=0.07, Barr_uphor_ratio=-0.8, Barr_nu_nubar_ratio=1.5)
+    eng.set_flux_params(**pars)
+    out = eng.evaluate(consts).cpu().numpy()
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    for c, (nubar, flav, ev, nom_nu, nom_nb, idx) in enumerate(host):
+        flux = orc.flux_barr_simple(ev["true_energy"], ev["true_coszen"], nom_nu, nom_nb, nubar, *pars.values())
+        _, den, dis = OL.calcLayers(ev["true_coszen"])
+        prob = orc.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, ev["true_energy"], den, dis)
+        w = ev["weights"] * (flux[:, 0] * prob[:, 0, flav] + flux[:, 1] * prob[:, 1, flav])
+        assert np.allclose(out[c, 0], orc.accumulate(idx, w, 128), rtol=1e-10, atol=1e-300)
+    plain = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    with pytest.raises(ValueError):
+        ev = syn.make_events_torch(100, 1, np.float64, dev)
+        plain.add_container("x", 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
+                            torch.zeros(100, dtype=torch.int32, device=dev))
+        plain.set_flux_params()
