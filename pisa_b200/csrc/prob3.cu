@@ -235,8 +235,9 @@ struct FusedBatch {
 // the three optional stores disappear from the event loop.
 template <typename IO, bool STD, bool PLAIN>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
-                                                    const FusedBatch<IO> &batch, int rank, int n_ranks,
-                                                    double *__restrict__ partials, double *s_hist) {
+                                                    const FusedBatch<IO> &batch, int ci_begin, int ci_end,
+                                                    int rank, int n_ranks, double *__restrict__ partials,
+                                                    double *s_hist) {
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
@@ -255,7 +256,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     // warp-uniform trip count so that the warp-collective histogram step is always converged
     const int64_t warp_first = first - (tid & 31);
 
-    for (int ci = 0; ci < batch.n_containers; ++ci) {
+    for (int ci = ci_begin; ci < ci_end; ++ci) {
         const FusedContainer<IO> &C = batch.c[ci];
         const IO *__restrict__ energy = C.energy, *__restrict__ coszen = C.coszen;
         const IO *__restrict__ nu_flux = C.nu_flux, *__restrict__ weights_in = C.weights_in;
@@ -318,13 +319,17 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
 template <typename IO, bool STD, bool PLAIN>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
-                     const __grid_constant__ FusedBatch<IO> batch, double *__restrict__ partials) {
+                     const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials) {
     extern __shared__ __align__(16) double s_hist[];
     __shared__ EarthTable s_earth;
     // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
     // DFMA takes such an operand directly); the Earth table is indexed per lane and goes to shared memory
     copy_earth(earth, &s_earth);
-    fused_template_body<IO, STD, PLAIN>(osc, s_earth, batch, blockIdx.x, gridDim.x, partials, s_hist);
+    // block -> (container, rank): `ranks` blocks share one container (grid = n_containers * ranks).  A block
+    // never walks more than one container, so a template over analysis-size containers (1e4 events each)
+    // costs one or two event latencies instead of one per container.
+    const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
+    fused_template_body<IO, STD, PLAIN>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves template b / R with rank
@@ -348,7 +353,8 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     }
     copy_earth(earth, &s_earth); // ends with __syncthreads()
     double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
-    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, rank, ranks_per_template, mine, s_hist);
+    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, 0, batch.n_containers, rank, ranks_per_template, mine,
+                                       s_hist);
 }
 
 } // namespace pisab
@@ -370,6 +376,9 @@ static int grid_for(int64_t n, int blocks_per_sm) {
 // grid-stride loop gives every block the same share of every layer-count class.
 #ifndef PISAB_WAVES
 #define PISAB_WAVES 4
+#endif
+#ifndef PISAB_SPREAD_WAVES
+#define PISAB_SPREAD_WAVES 32
 #endif
 
 // PISAB_WAVES static waves of blocks instead of one persistent wave: a block's share of the deep-core events
@@ -536,16 +545,38 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (fa.sharedSizeBytes + smem > 48 * 1024)
             PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    const int grid = waved_grid(resident_grid(kernel, n_max, smem), n_max);
+    // ranks (blocks) per container: at most PISAB_SPREAD_WAVES waves of resident blocks in total (blocks of
+    // different containers differ in cost, so they are kept short: 1/32 of the run each; 4 waves cost 12 %, 8
+    // waves 5 %, 32 and 64 are level -- profiles/r01_fused_kernel_variants.txt) with >= 8 events per thread; small containers instead get up to one block per 256 events as long as one resident wave holds
+    // them all (latency of one or two events per template)
+    int ranks;
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+        const int resident = (sm_count() > 0 ? sm_count() : 148) * occ;
+        const int nc = batch.n_containers;
+        const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
+        const int64_t by_thread = (n_max + kBlock - 1) / kBlock;
+        int64_t r = by_work;
+        const int64_t cap = ((int64_t)resident * PISAB_SPREAD_WAVES + nc - 1) / nc;
+        if (r > cap) r = cap;
+        const int64_t fill = (resident + nc - 1) / nc; // one resident wave spread over the containers
+        if (r < fill) r = by_thread < fill ? by_thread : fill;
+        const int64_t ws_cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16; // pisab_hist_workspace_bytes
+        if (r > ws_cap) r = ws_cap;
+        if (r < 1) r = 1;
+        ranks = (int)r;
+    }
+    const int grid = ranks * batch.n_containers;
     {
         LaunchTimer t(s);
-        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, (double *)d_workspace);
+        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
     if (d_batch_out)
-        return hist_reduce_batch((const double *)d_workspace, grid, n_bins, batch.n_containers, d_batch_out, s);
-    return hist_reduce_partials((const double *)d_workspace, grid, n_bins, d_hist, d_hist_w2, s);
+        return hist_reduce_batch((const double *)d_workspace, ranks, n_bins, batch.n_containers, d_batch_out, s);
+    return hist_reduce_partials((const double *)d_workspace, ranks, n_bins, d_hist, d_hist_w2, s);
 }
 
 template <typename IO>

@@ -84,3 +84,20 @@ def test_vectorised_osc_consts_equal_the_scalar_builder():
             assert bytes(one) == bytes(arr[k]), k
     with pytest.raises(AssertionError):
         scan.osc_consts_array(0.5, 0.1, 0.7, 7.0, 7e-5, 2e-3)
+
+
+def test_scalar_osc_consts_equal_oscparams_matrices():
+    """scan.osc_consts (scalar fast path of the fit loop) == OscConsts.from_matrices(OscParams ...), bit for bit."""
+    from pisa_b200 import ops, scan
+    rng = np.random.default_rng(11)
+    for _ in range(200):
+        t12, t13, t23 = rng.uniform(0.1, 1.4, 3)
+        dcp = rng.uniform(0, 2 * np.pi)
+        m21, m31 = rng.uniform(1e-5, 1e-4), rng.choice([-1, 1]) * rng.uniform(1e-3, 4e-3)
+        op = OscParams()
+        op.theta12, op.theta13, op.theta23, op.deltacp, op.dm21, op.dm31 = t12, t13, t23, dcp, m21, m31
+        mp = np.zeros((3, 3), dtype=np.complex128)
+        mp[0, 0] = 1.0
+        ref = ops.OscConsts.from_matrices(op.dm_matrix, op.mix_matrix_complex, mp)
+        got = scan.osc_consts(t12, t13, t23, dcp, m21, m31)
+        assert bytes(ref) == bytes(got)
