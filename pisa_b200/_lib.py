@@ -98,7 +98,7 @@ _SIGNATURES = {
                                        c_vp]),
     "pisab_flux_barr_terms": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pisab_flux_barr_apply": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, c_vp, c_vp]),
-    "pisab_flux_honda_2d": (c_i32, [c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "pisab_flux_honda_2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_scan": (c_i32, [ctypes.POINTER(OscConsts), c_i32, ctypes.POINTER(Earth),
                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),

@@ -9,6 +9,8 @@ Dropped: slicing, rebinning, tex, serialisation, masks, VarBinning.
 """
 from collections.abc import Sequence
 
+from collections import OrderedDict
+
 import numpy as np
 
 from pisa_b200 import FTYPE, HASH_SIGFIGS
@@ -131,6 +133,22 @@ class OneDimBinning:
                 self._is_irregular = not self.is_bin_spacing_lin_uniform(self._edges)
         return self._is_irregular
 
+    # --- serialisation (binning.py:551-600,676-694) -----------------------------------------
+    @property
+    def serializable_state(self):
+        return OrderedDict([("name", self.name), ("bin_edges", self._edges), ("units", str(self._units)),
+                            ("is_log", self.is_log), ("is_lin", self.is_lin), ("bin_names", self.bin_names),
+                            ("tex", self.tex)])
+
+    def to_json(self, filename, **kwargs):
+        from pisa_b200.utils import jsons
+        jsons.to_json(self.serializable_state, filename=filename, **kwargs)
+
+    @classmethod
+    def from_json(cls, resource):
+        from pisa_b200.utils import jsons
+        return cls(**jsons.from_json(resource))
+
     # --- identity -----------------------------------------------------------------------------
     def _state(self):
         # binnings are immutable: the rounded-edge state (HASH_SIGFIGS significant figures, like the
@@ -242,6 +260,21 @@ class MultiDimBinning:
         if attach_units:
             return [Quantity(g, d.units) for g, d in zip(grids, self._dims)]
         return grids
+
+    # --- serialisation (binning.py:1680-1740,1842-1859) ---------------------------------------
+    @property
+    def serializable_state(self):
+        return OrderedDict([("dimensions", [d.serializable_state for d in self._dims]), ("name", self.name),
+                            ("mask", None)])
+
+    def to_json(self, filename, **kwargs):
+        from pisa_b200.utils import jsons
+        jsons.to_json(self.serializable_state, filename=filename, **kwargs)
+
+    @classmethod
+    def from_json(cls, resource):
+        from pisa_b200.utils import jsons
+        return cls(**jsons.from_json(resource))
 
     def __hash__(self):
         h = getattr(self, "_hash_cache", None)

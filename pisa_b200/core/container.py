@@ -14,7 +14,7 @@ it once), and the two translations that touch every event run in the CUDA librar
 (``ops.hist_index`` + ``ops.hist_accumulate`` / ``ops.lookup``); the flat bin index of every
 (container, binning) pair is computed once and cached, because the sample coordinates of a fit do
 not change between templates.  ``get_map`` / ``get_mapset`` return host ``Map`` objects.
-Binned -> binned resampling is not part of the hot path and raises NotImplementedError.
+Binned -> binned goes through ``resample`` (average mode only, as in the reference).
 """
 from collections import defaultdict
 from collections.abc import Sequence
@@ -258,8 +258,8 @@ class Container:
         mode = self.translation_modes[key]
         if mode == "average":
             if from_map and to_map:
-                raise NotImplementedError("binned -> binned resampling is outside the pisa_b200 hot path")
-            if to_map:
+                out = self.resample(key, src_representation, dest_representation)
+            elif to_map:
                 out = self.array_to_binned(key, src_representation, dest_representation)
             elif from_map:
                 out = self.binned_to_array(key, src_representation, dest_representation)
@@ -298,6 +298,31 @@ class Container:
             if ok and self.precedence[h] < best:
                 best, representation = self.precedence[h], self._representations[h]
         return representation
+
+    def resample(self, key, src_representation, dest_representation):
+        """binned -> binned (container.py:913-931 -> translation.resample, translation.py:49-85): the old bin
+        centres are histogrammed into the new binning (mean of the values where more than one old bin lands in a
+        new bin); every other new bin takes the value of the old bin its own centre falls into."""
+        from pisa_b200 import ops
+        if src_representation.names != dest_representation.names:
+            raise ValueError("cannot translate betwen %s and %s" % (src_representation, dest_representation))
+        self.representation = src_representation
+        old_sample = [self[name] for name in src_representation.names]
+        weights = self[key]
+        self.representation = dest_representation
+        new_sample = [self[name] for name in dest_representation.names]
+        if weights.dim() != 1:
+            raise NotImplementedError("resampling of vector-valued maps")
+        dev = weights.device
+        new_b, _ = ops.make_binning(regularized_dims(dest_representation), dev)
+        old_b, _ = ops.make_binning(regularized_dims(src_representation), dev)
+        into_new = ops.hist_index(new_b, old_sample)
+        n_bins = dest_representation.size
+        summed, _ = ops.hist_accumulate(into_new, weights, n_bins, want_w2=False)
+        counts, _ = ops.hist_accumulate(into_new, None, n_bins, want_w2=False)
+        mean = torch.nan_to_num(summed / counts, nan=0.0, posinf=0.0, neginf=0.0)
+        looked_up = ops.lookup(ops.hist_index(old_b, new_sample), weights)
+        return torch.where(counts > 1, mean.to(looked_up.dtype), looked_up).to(TDTYPE)
 
     def array_to_binned(self, key, src_representation, dest_representation, averaged=True):
         """events -> binned: weighted histogram, divided by the counts when `averaged`

@@ -3,9 +3,12 @@
 The thin subset of pisa/core/map.py (:221,2108) that ``ContainerSet.get_mapset`` and a chi-square
 scan need: ``Map(name, hist, error_hist, binning)`` (container.py:792-800), ``nominal_values`` /
 ``std_devs`` (the reference packs both into ``uncertainties`` arrays), sums and element-wise
-arithmetic of same-binning maps, ``MapSet`` lookup by name and summation.  No plotting, slicing,
-rebinning, fluctuation or serialisation.
+arithmetic of same-binning maps, ``MapSet`` lookup by name and summation, and ``to_json`` / ``from_json``
+in the reference's file layout (map.py:1272-1362,2206-2262) so that templates can be handed to real PISA
+tooling.  No plotting, slicing, rebinning or fluctuation.
 """
+from collections import OrderedDict
+
 import numpy as np
 
 from pisa_b200.core.binning import MultiDimBinning
@@ -15,12 +18,15 @@ __all__ = ["Map", "MapSet"]
 
 class Map:
     def __init__(self, name, hist, binning, error_hist=None, hash=None, tex=None, full_comparison=False):
-        if not isinstance(binning, MultiDimBinning):
+        if isinstance(binning, dict):
+            binning = MultiDimBinning(**binning)
+        elif not isinstance(binning, MultiDimBinning):
             binning = MultiDimBinning(binning)
         hist = np.asarray(hist)
         if hist.shape != binning.shape:
             raise ValueError("hist shape %s does not match binning shape %s" % (hist.shape, binning.shape))
         self.name, self.binning, self.tex = name, binning, tex
+        self.hash, self.full_comparison = hash, full_comparison
         self._hist = hist
         self._err = None
         if error_hist is not None:
@@ -98,14 +104,32 @@ class Map:
         e = np.clip(expected.hist, 1e-10, np.inf)
         return float(((self._hist - e) ** 2 / (expected.std_devs ** 2 + e)).sum())
 
+    # --- serialisation (map.py:1272-1362) ----------------------------------------------------
+    @property
+    def serializable_state(self):
+        stddevs = self.std_devs
+        return OrderedDict([("name", self.name), ("hist", self._hist),
+                            ("binning", self.binning.serializable_state),
+                            ("error_hist", None if np.all(stddevs == 0) else stddevs), ("hash", self.hash),
+                            ("tex", self.tex), ("full_comparison", self.full_comparison)])
+
+    def to_json(self, filename, **kwargs):
+        from pisa_b200.utils import jsons
+        jsons.to_json(self.serializable_state, filename=filename, **kwargs)
+
+    @classmethod
+    def from_json(cls, resource):
+        from pisa_b200.utils import jsons
+        return cls(**jsons.from_json(resource))
+
     def __repr__(self):
         return "Map(%r, sum=%g, shape=%s)" % (self.name, self.sum(), self.shape)
 
 
 class MapSet:
-    def __init__(self, maps, name=None, tex=None):
-        self.maps = list(maps)
-        self.name, self.tex = name, tex
+    def __init__(self, maps, name=None, tex=None, hash=None, collate_by_name=True):
+        self.maps = [m if isinstance(m, Map) else Map(**m) for m in maps]
+        self.name, self.tex, self.hash, self.collate_by_name = name, tex, hash, collate_by_name
 
     names = property(lambda self: [m.name for m in self.maps])
 
@@ -138,6 +162,21 @@ class MapSet:
         if isinstance(other, MapSet):
             return MapSet([a + other[a.name] for a in self.maps], name=self.name)
         return MapSet([a + other for a in self.maps], name=self.name)
+
+    # --- serialisation (map.py:2206-2262) ----------------------------------------------------
+    @property
+    def serializable_state(self):
+        return OrderedDict([("maps", [m.serializable_state for m in self.maps]), ("name", self.name),
+                            ("tex", self.tex), ("collate_by_name", self.collate_by_name)])
+
+    def to_json(self, filename, **kwargs):
+        from pisa_b200.utils import jsons
+        jsons.to_json(self.serializable_state, filename=filename, **kwargs)
+
+    @classmethod
+    def from_json(cls, resource):
+        from pisa_b200.utils import jsons
+        return cls(**jsons.from_json(resource))
 
     def __repr__(self):
         return "MapSet(%r: %s)" % (self.name, self.names)

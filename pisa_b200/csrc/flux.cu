@@ -284,104 +284,97 @@ int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nomi
 // flux.honda_ip: integral-preserving interpolation of an azimuth-averaged Honda table
 // ---------------------------------------------------------------------------------------------
 // Reference per event (pisa/utils/flux_weights.py:337-349): 20 x splev(log10 E, energy spline, der=1), cumsum * 0.1,
-// splrep through the 21 points, splev(coszen, der=1), / E**enpow -- for each of the four primaries.  Here:
-//   * splev(.., der=1) is FITPACK's splder: knot interval by its search rule, the three non-zero quadratic
-//     B-splines by fpbspl's recursion (shared by all 80 splines of a table: one knot vector), and the
-//     derivative coefficients k (c[i+1] - c[i]) / (t[i+k+1] - t[i+1]) precomputed on the host from the
-//     reference's own splrep coefficients (pisa_b200/utils/flux_weights.py);
-//   * the per-event spline FIT in coszen is linear in its 21 values, so it is a fixed table of cardinal-spline
-//     derivative polynomials D[piece][k][3]:  flux = sum_k D_k(coszen) * int_vals[k] / E**enpow.
+// splrep through the 21 points, splev(coszen, der=1), / E**enpow -- for each of the four primaries.
+//   * splev(.., der=1) is FITPACK's splder: a quadratic in s = log10(E) - t(l) on the knot interval l found by
+//     its search rule (l clamped to [k1, nk1]: the end polynomials extrapolate);
+//   * the per-event spline FIT in coszen is linear in its 21 values, so it is a fixed set of cardinal-spline
+//     derivative polynomials, quadratic in u = coszen - break(p) on piece p.
+// Both being piecewise quadratic, the flux of a primary on a cell (l, p) is one biquadratic
+//     flux = sum_ab K[l][p][primary][a][b] s^a u^b / E**enpow,
+// with K expanded once on the host from the reference's own splrep coefficients
+// (pisa_b200/utils/flux_weights.py::HondaTable2D._cell_polynomials).  Per event: log10, two interval searches,
+// 36 coefficients (288 contiguous bytes, L2-resident table of ~0.5 MB) and 32 FMAs -- instead of 80 spline
+// evaluations of 3 coefficients each.
 namespace pisab {
 
-constexpr int kHondaCz = 20;
+constexpr int kHondaMaxKnots = 256, kHondaMaxPieces = 64;
 
 template <typename IO>
-__global__ void __launch_bounds__(128)
-flux_honda_2d_kernel(const double *__restrict__ knots, int n_knots, const double *__restrict__ dcoef,
-                     const double *__restrict__ cz_breaks, int n_pieces, const double *__restrict__ cz_table,
-                     int enpow, const IO *__restrict__ energy, const IO *__restrict__ coszen, int64_t n,
-                     IO *__restrict__ nu_out, IO *__restrict__ nubar_out) {
+__global__ void __launch_bounds__(256)
+flux_honda_2d_kernel(const double *__restrict__ knots, int n_knots, const double *__restrict__ cz_breaks,
+                     int n_pieces, const double *__restrict__ cells, int enpow, const IO *__restrict__ energy,
+                     const IO *__restrict__ coszen, int64_t n, IO *__restrict__ nu_out, IO *__restrict__ nubar_out) {
+    __shared__ double s_knots[kHondaMaxKnots], s_breaks[kHondaMaxPieces];
+    for (int i = threadIdx.x; i < n_knots; i += blockDim.x) s_knots[i] = knots[i];
+    for (int i = threadIdx.x; i < n_pieces; i += blockDim.x) s_breaks[i] = cz_breaks[i];
+    __syncthreads();
     const int nk1 = n_knots - 4; // FITPACK's nk1 for k = 3
+    const double t0 = s_knots[4], inv_dt = 1.0 / (s_knots[5] - s_knots[4]); // first interior knots
+    const double b1 = s_breaks[n_pieces > 1 ? 1 : 0];
+    const double inv_db = n_pieces > 2 ? 1.0 / (s_breaks[2] - s_breaks[1]) : 0.0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double e = (double)__ldg(energy + i), cz = (double)__ldg(coszen + i);
         const double x = log10(e);
         // ---- splder: t(l) <= x < t(l+1), l in [k1, nk1] (1-based); uniform interior knots give the guess
-        int l = 4;
-        {
-            const double t0 = __ldg(knots + 4), t1 = __ldg(knots + 5); // first interior knots
-            int g = 5 + (int)floor((x - t0) / (t1 - t0));
-            g = g < 4 ? 4 : (g > nk1 ? nk1 : g);
-            l = g;
-            while (l > 4 && x < __ldg(knots + l - 1)) --l;            // t(l) > x: go down
-            while (l < nk1 && !(x < __ldg(knots + l))) ++l;            // x >= t(l+1): go up
+        int l = 5 + (int)floor((x - t0) * inv_dt);
+        l = l < 4 ? 4 : (l > nk1 ? nk1 : l);
+        while (l > 4 && x < s_knots[l - 1]) --l;            // t(l) > x: go down
+        while (l < nk1 && !(x < s_knots[l])) ++l;            // x >= t(l+1): go up
+        const double s = x - s_knots[l - 1];
+        // ---- coszen piece: break(p) <= cz < break(p+1), the last piece closed
+        int p = 1 + (int)floor((cz - b1) * inv_db);
+        p = p < 0 ? 0 : (p > n_pieces - 1 ? n_pieces - 1 : p);
+        while (p > 0 && cz < s_breaks[p]) --p;
+        while (p + 1 < n_pieces && cz >= s_breaks[p + 1]) ++p;
+        const double u = cz - s_breaks[p];
+        const double2 *K = reinterpret_cast<const double2 *>(cells + ((size_t)(l - 4) * n_pieces + p) * 36);
+        double k[36];
+#pragma unroll
+        for (int q = 0; q < 18; ++q) {
+            const double2 v = __ldg(K + q);
+            k[2 * q] = v.x;
+            k[2 * q + 1] = v.y;
         }
-        // ---- fpbspl, degree 2 (h(1..3), knots t(l-1) .. t(l+2))
-        double h0 = 1.0, h1 = 0.0, h2 = 0.0;
-        {
-            const double tl = __ldg(knots + l - 1), tl1 = __ldg(knots + l);          // t(l), t(l+1)
-            const double tlm = __ldg(knots + l - 2), tl2 = __ldg(knots + l + 1);      // t(l-1), t(l+2)
-            // j = 1
-            double f = h0 / (tl1 - tl);
-            h0 = f * (tl1 - x);
-            h1 = f * (x - tl);
-            // j = 2
-            const double a0 = h0, a1 = h1;
-            f = a0 / (tl1 - tlm);
-            h0 = f * (tl1 - x);
-            h1 = f * (x - tlm);
-            f = a1 / (tl2 - tl);
-            h1 = h1 + f * (tl2 - x);
-            h2 = f * (x - tl);
-        }
-        const double *c0 = dcoef + (size_t)(l - 4) * (4 * kHondaCz); // wrk(ll+1..ll+3), ll = l - k1
-        const double *c1 = c0 + 4 * kHondaCz, *c2 = c1 + 4 * kHondaCz;
-        // ---- coszen piece of the cardinal splines
-        int p = 0;
-        while (p + 1 < n_pieces && cz >= __ldg(cz_breaks + p + 1)) ++p;
-        const double u = cz - __ldg(cz_breaks + p);
-        const double *D = cz_table + (size_t)p * (kHondaCz + 1) * 3;
         double scale = 1.0;
-        for (int k = 0; k < enpow; ++k) scale *= e;
+        for (int j = 0; j < enpow; ++j) scale *= e;
+        const double inv_scale = 1.0 / scale;
         double out[4];
 #pragma unroll
         for (int prim = 0; prim < 4; ++prim) {
-            double acc = 0.0, sum = 0.0; // int_vals[0] = 0 contributes nothing
-#pragma unroll 4
-            for (int j = 0; j < kHondaCz; ++j) {
-                const int q = prim * kHondaCz + j;
-                double v = __ldg(c0 + q) * h0;
-                v = v + __ldg(c1 + q) * h1;
-                v = v + __ldg(c2 + q) * h2;
-                acc += v;                                            // cumsum
-                const double *d = D + (j + 1) * 3;
-                const double dk = fma(fma(__ldg(d), u, __ldg(d + 1)), u, __ldg(d + 2));
-                sum = fma(dk, acc * 0.1, sum);
-            }
-            out[prim] = sum / scale;
+            const double *c = k + prim * 9; // [a][b]
+            const double r0 = fma(fma(c[2], u, c[1]), u, c[0]);
+            const double r1 = fma(fma(c[5], u, c[4]), u, c[3]);
+            const double r2 = fma(fma(c[8], u, c[7]), u, c[6]);
+            out[prim] = fma(fma(r2, s, r1), s, r0) * inv_scale;
         }
-        nu_out[2 * i] = (IO)out[0];
-        nu_out[2 * i + 1] = (IO)out[1];
-        nubar_out[2 * i] = (IO)out[2];
-        nubar_out[2 * i + 1] = (IO)out[3];
+        if (sizeof(IO) == 8) {
+            reinterpret_cast<double2 *>(nu_out)[i] = make_double2(out[0], out[1]);
+            reinterpret_cast<double2 *>(nubar_out)[i] = make_double2(out[2], out[3]);
+        } else {
+            reinterpret_cast<float2 *>(nu_out)[i] = make_float2((float)out[0], (float)out[1]);
+            reinterpret_cast<float2 *>(nubar_out)[i] = make_float2((float)out[2], (float)out[3]);
+        }
     }
 }
 
 template <typename IO>
-static int honda_impl(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
-                      int32_t n_pieces, const double *d_cz_table, int32_t enpow, const IO *d_energy,
-                      const IO *d_coszen, int64_t n, IO *d_nu, IO *d_nubar, void *stream) {
-    if (!d_knots || !d_dcoef || !d_cz_breaks || !d_cz_table || n_knots < 9 || n_pieces < 1 || enpow < 0) {
+static int honda_impl(const double *d_knots, int32_t n_knots, const double *d_cz_breaks, int32_t n_pieces,
+                      const double *d_cells, int32_t enpow, const IO *d_energy, const IO *d_coszen, int64_t n,
+                      IO *d_nu, IO *d_nubar, void *stream) {
+    if (!d_knots || !d_cz_breaks || !d_cells || n_knots < 9 || n_knots > kHondaMaxKnots || n_pieces < 1 ||
+        n_pieces > kHondaMaxPieces || enpow < 0) {
         set_error("bad flux table");
         return PISAB_ERR_ARG;
     }
     if (n < 0 || (n > 0 && (!d_energy || !d_coszen || !d_nu || !d_nubar))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
+    if ((((uintptr_t)d_nu | (uintptr_t)d_nubar) & (2 * sizeof(IO) - 1)) != 0) { set_error("flux outputs must be aligned to a (nue, numu) pair"); return PISAB_ERR_ARG; }
     if (n == 0) return PISAB_OK;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    int64_t want = (n + 127) / 128;
-    const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-    flux_honda_2d_kernel<IO><<<grid, 128, 0, (cudaStream_t)stream>>>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces,
-                                                                     d_cz_table, enpow, d_energy, d_coszen, n, d_nu, d_nubar);
+    int64_t want = (n + 255) / 256;
+    const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+    flux_honda_2d_kernel<IO><<<grid, 256, 0, (cudaStream_t)stream>>>(d_knots, n_knots, d_cz_breaks, n_pieces, d_cells,
+                                                                     enpow, d_energy, d_coszen, n, d_nu, d_nubar);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
@@ -390,18 +383,16 @@ static int honda_impl(const double *d_knots, int32_t n_knots, const double *d_dc
 } // namespace pisab
 
 extern "C" {
-int pisab_flux_honda_2d_f64(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
-                            int32_t n_pieces, const double *d_cz_table, int32_t enpow, const double *d_energy,
-                            const double *d_coszen, int64_t n, double *d_nu_flux_nominal,
-                            double *d_nubar_flux_nominal, void *stream) {
-    return pisab::honda_impl<double>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces, d_cz_table, enpow, d_energy,
-                                     d_coszen, n, d_nu_flux_nominal, d_nubar_flux_nominal, stream);
+int pisab_flux_honda_2d_f64(const double *d_knots, int32_t n_knots, const double *d_cz_breaks, int32_t n_pieces,
+                            const double *d_cells, int32_t enpow, const double *d_energy, const double *d_coszen,
+                            int64_t n, double *d_nu_flux_nominal, double *d_nubar_flux_nominal, void *stream) {
+    return pisab::honda_impl<double>(d_knots, n_knots, d_cz_breaks, n_pieces, d_cells, enpow, d_energy, d_coszen, n,
+                                     d_nu_flux_nominal, d_nubar_flux_nominal, stream);
 }
-int pisab_flux_honda_2d_f32(const double *d_knots, int32_t n_knots, const double *d_dcoef, const double *d_cz_breaks,
-                            int32_t n_pieces, const double *d_cz_table, int32_t enpow, const float *d_energy,
-                            const float *d_coszen, int64_t n, float *d_nu_flux_nominal,
-                            float *d_nubar_flux_nominal, void *stream) {
-    return pisab::honda_impl<float>(d_knots, n_knots, d_dcoef, d_cz_breaks, n_pieces, d_cz_table, enpow, d_energy,
-                                    d_coszen, n, d_nu_flux_nominal, d_nubar_flux_nominal, stream);
+int pisab_flux_honda_2d_f32(const double *d_knots, int32_t n_knots, const double *d_cz_breaks, int32_t n_pieces,
+                            const double *d_cells, int32_t enpow, const float *d_energy, const float *d_coszen,
+                            int64_t n, float *d_nu_flux_nominal, float *d_nubar_flux_nominal, void *stream) {
+    return pisab::honda_impl<float>(d_knots, n_knots, d_cz_breaks, n_pieces, d_cells, enpow, d_energy, d_coszen, n,
+                                    d_nu_flux_nominal, d_nubar_flux_nominal, stream);
 }
 }

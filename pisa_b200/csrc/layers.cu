@@ -5,11 +5,17 @@
 
 namespace pisab {
 
+// Rows are [max_layers] long, so a thread writing its own row touches one sector per store.  Each warp
+// therefore builds its 32 rows in shared memory (row stride odd in 8-byte units: conflict-free) and then
+// copies the 32 * max_layers contiguous output elements with coalesced stores.
+__host__ __device__ inline int layers_row_stride(int max_layers) { return max_layers | 1; }
+
 template <typename IO>
 __global__ void __launch_bounds__(128)
 layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO *__restrict__ coszen,
               int64_t n, IO *__restrict__ densities, IO *__restrict__ distances,
               int32_t *__restrict__ n_layers) {
+    extern __shared__ __align__(16) unsigned char s_raw[];
     __shared__ EarthTable E;
     {
         const int *src = reinterpret_cast<const int *>(&earth);
@@ -17,12 +23,19 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
         for (int i = threadIdx.x; i < (int)(sizeof(EarthTable) / 4); i += blockDim.x) dst[i] = src[i];
         __syncthreads();
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row = layers_row_stride(max_layers);
+    IO *tile_den = reinterpret_cast<IO *>(s_raw) + (size_t)warp * 2 * 32 * row; // [32][row] densities, then distances
+    IO *tile_dis = tile_den + 32 * row;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const IO czs = __ldg(coszen + i);
+    // warp-uniform trip count: every lane takes part in the copy-out of its warp's tile
+    for (int64_t first = (int64_t)blockIdx.x * blockDim.x + warp * 32; first < n; first += stride) {
+        const int64_t i = first + lane;
+        const bool live = i < n;
+        const IO czs = live ? __ldg(coszen + i) : (IO)1;
         const double cz = (double)czs;
-        IO *den = densities + i * max_layers;
-        IO *dis = distances + i * max_layers;
+        IO *den = tile_den + lane * row;
+        IO *dis = tile_dis + lane * row;
         const int idx = E.idx_first_inner;
         const double base = __dmul_rn(-E.r_det, cz);
         int count = 0, slot = 0;
@@ -74,7 +87,17 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
             }
         }
         for (; slot < max_layers; ++slot) { den[slot] = (IO)0; dis[slot] = (IO)0; }
-        if (n_layers) n_layers[i] = count;
+        if (n_layers && live) n_layers[i] = count;
+        __syncwarp();
+        const int64_t rows_left = n - first;
+        const int total = (int)(rows_left < 32 ? rows_left : 32) * max_layers;
+        IO *out_den = densities + first * max_layers, *out_dis = distances + first * max_layers;
+        for (int k = lane; k < total; k += 32) {
+            const int r = k / max_layers, c = k - r * max_layers;
+            out_den[k] = tile_den[r * row + c];
+            out_dis[k] = tile_dis[r * row + c];
+        }
+        __syncwarp();
     }
 }
 
@@ -120,8 +143,15 @@ static int layers_impl(const pisab_earth_t *earth, const IO *d_coszen, int64_t n
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + 127) / 128;
     const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-    layers_kernel<IO><<<grid, 128, 0, (cudaStream_t)stream>>>(et, earth->max_layers, d_coszen, n, d_densities,
-                                                             d_distances, d_n_layers);
+    // 32 rows of both arrays per warp; as many warps per block (<= 4) as ~200 KB of shared memory hold
+    const size_t per_warp = (size_t)2 * 32 * layers_row_stride(earth->max_layers) * sizeof(IO);
+    int warps = (int)((200 * 1024) / per_warp);
+    warps = warps > 4 ? 4 : warps;
+    if (warps < 1) { set_error("max_layers too large"); return PISAB_ERR_UNSUPPORTED; }
+    const size_t smem = per_warp * warps;
+    PISAB_CUDA_CHECK(cudaFuncSetAttribute(layers_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    layers_kernel<IO><<<grid, 32 * warps, smem, (cudaStream_t)stream>>>(et, earth->max_layers, d_coszen, n, d_densities,
+                                                                       d_distances, d_n_layers);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;

@@ -144,9 +144,9 @@ def flux_honda_2d(table, true_energy, true_coszen, nu_flux_nominal=None, nubar_f
         nubar_flux_nominal = torch.empty((n, 2), dtype=dt, device=true_energy.device)
     _chk(nu_flux_nominal, "nu_flux_nominal", dt)
     _chk(nubar_flux_nominal, "nubar_flux_nominal", dt)
-    knots, dcoef, breaks, cz_table = table.device_tables(true_energy.device)
+    knots, breaks, cells = table.device_tables(true_energy.device)
     f = _lib.fn("pisab_flux_honda_2d", dt)
-    _lib.check(f(_ptr(knots), knots.numel(), _ptr(dcoef), _ptr(breaks), breaks.numel(), _ptr(cz_table), int(table.enpow),
+    _lib.check(f(_ptr(knots), knots.numel(), _ptr(breaks), breaks.numel(), _ptr(cells), int(table.enpow),
                  _ptr(true_energy), _ptr(true_coszen), n, _ptr(nu_flux_nominal), _ptr(nubar_flux_nominal), _stream()))
     return nu_flux_nominal, nubar_flux_nominal
 

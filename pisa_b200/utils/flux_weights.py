@@ -122,12 +122,58 @@ class HondaTable2D:
         # layout [coef index][primary * 20 + coszen row]: the 80 values needed for one basis function are contiguous
         self.dcoef = np.ascontiguousarray(np.array(rows).T)      # [n - 5, 80]
         self.cz_breaks, self.cz_table = _cardinal_derivative_table()
+        self.cells = self._cell_polynomials()
         self._dev = {}
+
+    def _cell_polynomials(self):
+        """Both steps are piecewise quadratic -- in s = log10(E) - t_l on knot interval l and in u = coszen - break_p
+        on coszen piece p -- so on every (l, p) cell the flux of a primary is ONE biquadratic
+        sum_ab K[l, p, primary, a, b] s^a u^b.  K is expanded here once (in extended precision: the cardinal-spline
+        weights alternate in sign) from the same ``dcoef`` / ``cz_table`` the step-by-step evaluation uses:
+        the three non-zero quadratic B-splines of fpbspl as polynomials in s, the cumulative sum over the coszen
+        rows, the 0.1 bin width and the cardinal derivative polynomials."""
+        LD = np.longdouble
+        t = self.knots.astype(LD)
+        n = len(t)
+        nk1 = n - 4
+        n_int = nk1 - 3                                # FITPACK intervals l = 4 .. nk1 (1-based)
+        dcoef = self.dcoef.astype(LD).reshape(-1, 4, N_CZ)
+        alpha = np.zeros((n_int, 3, 3), dtype=LD)      # [interval][basis m][power of s]
+        for L in range(n_int):
+            l = L + 4
+            tl, tl1, tlm, tl2 = t[l - 1], t[l], t[l - 2], t[l + 1]
+            d, a, b = tl1 - tl, tl - tlm, tl2 - tl
+            alpha[L, 0] = np.array([d * d, -2 * d, 1], dtype=LD) / (d * (d + a))
+            alpha[L, 2] = np.array([0, 0, 1], dtype=LD) / (d * b)
+            alpha[L, 1] = (np.array([d * a, d - a, -1], dtype=LD) / (d * (d + a))
+                           + np.array([0, b, -1], dtype=LD) / (d * b))
+        # v[L, prim, j, a] = sum_m dcoef[L + m, prim, j] alpha[L, m, a]; cumulative over the coszen rows j
+        v = sum(dcoef[m:m + n_int, :, :, None] * alpha[:, m, None, None, :] for m in range(3))
+        acc = np.cumsum(v, axis=2)
+        dz = self.cz_table.astype(LD)[:, 1:, ::-1]     # [piece][k = 1..20][power of u]
+        cells = LD(0.1) * np.einsum("lqja,pjb->lpqab", acc, dz)
+        return np.ascontiguousarray(cells.astype(np.float64))   # [n_int, pieces, 4, 3, 3]
+
+    def evaluate_cells(self, true_energy, true_coszen):
+        """Host restatement of the device evaluation (used by the CPU tests): [n, 4] in OUT_ORDER."""
+        x = np.log10(np.asarray(true_energy, dtype=np.float64))
+        cz = np.asarray(true_coszen, dtype=np.float64)
+        t = self.knots
+        nk1 = len(t) - 4
+        l = np.clip(np.searchsorted(t, x, side="right"), 4, nk1)       # t(l) <= x < t(l+1), clamped like splder
+        s = x - t[l - 1]
+        p = np.clip(np.searchsorted(self.cz_breaks, cz, side="right") - 1, 0, len(self.cz_breaks) - 1)
+        u = cz - self.cz_breaks[p]
+        K = self.cells[l - 4, p]                                        # [n, 4, 3, 3]
+        sp = np.stack([np.ones_like(s), s, s * s], axis=1)
+        up = np.stack([np.ones_like(u), u, u * u], axis=1)
+        return np.einsum("nqab,na,nb->nq", K, sp, up) / np.power(np.asarray(true_energy, dtype=np.float64),
+                                                                  self.enpow)[:, None]
 
     def device_tables(self, device):
         import torch
         key = str(device)
         if key not in self._dev:
             self._dev[key] = tuple(torch.tensor(a, dtype=torch.float64, device=device)
-                                   for a in (self.knots, self.dcoef, self.cz_breaks, self.cz_table))
+                                   for a in (self.knots, self.cz_breaks, self.cells))
         return self._dev[key]

@@ -172,6 +172,56 @@ def test_container_translations_roundtrip():
         c["nonexistent"]
 
 
+def test_container_resample_binned_to_binned():
+    """binned -> binned (translation.resample, translation.py:49-85): mean over the old bins where several land in
+    a new bin, lookup of the old bin otherwise; checked against a numpy restatement of the reference's two steps."""
+    _need_gpu()
+    from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+    from pisa_b200.core.container import Container
+
+    def make(nx, ny):
+        return MultiDimBinning([OneDimBinning("x", num_bins=nx, is_lin=True, domain=[0, 100]),
+                                OneDimBinning("y", num_bins=ny, is_log=True, domain=[1, 100])])
+
+    def centres(b):
+        g = np.meshgrid(*[np.asarray(d.weighted_centers.magnitude, dtype=np.float64) for d in b], indexing="ij")
+        return [a.ravel() for a in g]
+
+    def edges(b):
+        return [np.asarray(d.bin_edges.magnitude, dtype=np.float64) for d in b]
+
+    def restated(vals, old, new):
+        s_old, s_new = centres(old), centres(new)
+        hw, _ = np.histogramdd(np.stack(s_old, 1), bins=edges(new), weights=vals)
+        hc, _ = np.histogramdd(np.stack(s_old, 1), bins=edges(new))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            mean = np.nan_to_num(hw / hc).ravel()
+        idx = [np.searchsorted(e, s, side="right") - 1 for e, s in zip(edges(old), s_new)]
+        looked = vals.reshape(old.shape)[tuple(idx)]
+        return np.where(hc.ravel() > 1, mean, looked)
+
+    fine, coarse, odd = make(40, 30), make(8, 10), make(7, 9)
+    for old, new in ((fine, coarse), (coarse, fine), (fine, odd), (odd, coarse)):
+        c = Container("test")
+        c.representation = old
+        x, y = centres(old)
+        vals = np.sin(x / 17.0) * np.log(y + 1.0) + 2.0
+        c["v"] = vals
+        c.representation = new
+        got = c["v"].cpu().numpy()
+        assert got.shape == (new.size,)
+        assert np.allclose(got, restated(vals, old, new), rtol=1e-12, atol=0), (old.shape, new.shape)
+    # different dimension names cannot be resampled (translation.py:66-67)
+    other = MultiDimBinning([OneDimBinning("x", num_bins=4, is_lin=True, domain=[0, 100]),
+                             OneDimBinning("z", num_bins=4, is_lin=True, domain=[0, 1])])
+    c = Container("test")
+    c.representation = fine
+    c["v"] = np.ones(fine.size)
+    c.representation = other
+    with pytest.raises(ValueError):
+        c["v"]
+
+
 def test_engine_host_mode_equals_resident_mode():
     _need_gpu()
     from pisa_b200 import ops

@@ -216,3 +216,53 @@ def test_hyperplane_loader_and_formula():
     other = parse_pipeline_config("settings/pipeline/b200_oscillogram.cfg")[("osc", "prob3")]["calc_mode"]
     with pytest.raises((AssertionError, KeyError)):      # a binning the files were not made for
         load_hypersurfaces_data_release("events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2", other)
+
+
+def test_mapset_json_interchange(tmp_path):
+    """MapSet.to_json / from_json in the reference's layout (map.py:1272-1362,2206-2262; binning.py:676-694,
+    1842-1859; jsons.py:196-330): state keys, nested lists, .json and .json.bz2, and a file shaped like real
+    PISA's output (pint long unit names, integer hashes) reads back."""
+    import bz2, json
+    from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+    from pisa_b200.core.map import Map, MapSet
+    from pisa_b200.utils import jsons
+    b = MultiDimBinning([OneDimBinning("reco_energy", num_bins=4, is_log=True, domain=[1, 100], units="GeV"),
+                         OneDimBinning("reco_coszen", num_bins=3, is_lin=True, domain=[-1, 1])], name="reco")
+    rng = np.random.default_rng(0)
+    ms = MapSet([Map("nue_cc", rng.random((4, 3)), b, error_hist=rng.random((4, 3))),
+                 Map("numu_cc", rng.random((4, 3)), b)], name="template")
+    for ext in ("json", "json.bz2"):
+        path = str(tmp_path / ("maps." + ext))
+        ms.to_json(path)
+        raw = open(path, "rb").read()
+        state = json.loads(bz2.decompress(raw) if ext.endswith("bz2") else raw)
+        assert list(state) == ["maps", "name", "tex", "collate_by_name"]
+        assert list(state["maps"][0]) == ["name", "hist", "binning", "error_hist", "hash", "tex", "full_comparison"]
+        assert list(state["maps"][0]["binning"]) == ["dimensions", "name", "mask"]
+        assert list(state["maps"][0]["binning"]["dimensions"][0]) == ["name", "bin_edges", "units", "is_log", "is_lin",
+                                                                     "bin_names", "tex"]
+        assert state["maps"][1]["error_hist"] is None                  # all-zero errors are written as null
+        back = MapSet.from_json(path)
+        assert back.names == ms.names and back.name == "template"
+        for m0, m1 in zip(ms, back):
+            assert np.array_equal(m0.hist, m1.hist) and np.array_equal(m0.std_devs, m1.std_devs)   # repr round trip
+            assert m0.binning == m1.binning and m1.binning.dimensions[0].is_log
+    with pytest.raises(ValueError):
+        ms.to_json(str(tmp_path / "maps.txt"))
+    # a file as the reference writes it
+    ref_like = {"maps": [{"name": "nutau_cc", "hist": [[1.5, 2.5], [3.5, 4.5]],
+                          "binning": {"dimensions": [
+                              {"name": "true_energy", "bin_edges": [1.0, 10.0, 100.0], "units": "gigaelectron_volt",
+                               "is_log": True, "is_lin": False, "bin_names": None, "tex": r"E_{\rm true}"},
+                              {"name": "true_coszen", "bin_edges": [-1.0, 0.0, 1.0], "units": "dimensionless",
+                               "is_log": False, "is_lin": True, "bin_names": None, "tex": None}],
+                              "name": None, "mask": None},
+                          "error_hist": [[0.1, 0.2], [0.3, 0.4]], "hash": -1234567890123, "tex": None,
+                          "full_comparison": False}],
+                "name": "dist", "tex": None, "collate_by_name": True}
+    path = str(tmp_path / "ref_like.json")
+    open(path, "w").write(json.dumps(ref_like, indent=2))
+    got = MapSet.from_json(path)
+    assert got["nutau_cc"].hist.tolist() == [[1.5, 2.5], [3.5, 4.5]] and got["nutau_cc"].std_devs[1, 1] == 0.4
+    assert got["nutau_cc"].binning.names == ["true_energy", "true_coszen"] and got["nutau_cc"].hash == -1234567890123
+    assert jsons.from_json(path)["name"] == "dist"

@@ -277,7 +277,12 @@ def test_honda_flux_oracle_and_table_construction_match_reference():
         sel = slice(0, 150)
         out = honda.honda_2d_flux(g["true_energy"][sel], g["true_coszen"][sel], T.spline_dict[prim])
         assert np.array_equal(out, g[prim][sel]), prim                     # same calls, same bits
-    assert T.dcoef.shape == (101, 80) and T.cz_table.shape == (18, 21, 3)
+    assert T.dcoef.shape == (101, 80) and T.cz_table.shape == (18, 21, 3) and T.cells.shape == (99, 18, 4, 3, 3)
+    # the per-cell biquadratics the device evaluates (host restatement of the kernel) against the reference
+    from pisa_b200.utils.flux_weights import OUT_ORDER
+    cells = T.evaluate_cells(g["true_energy"], g["true_coszen"])
+    for k, prim in enumerate(OUT_ORDER):
+        assert np.allclose(cells[:, k], g[prim], rtol=1e-11, atol=0), (prim, np.abs(cells[:, k] / g[prim] - 1).max())
     with pytest.raises(ValueError):
         honda.honda_2d_flux([1.0], [1.5], T.spline_dict["nue"])
     with pytest.raises(NotImplementedError):
