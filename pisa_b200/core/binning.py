@@ -200,13 +200,17 @@ class MultiDimBinning:
             raise ValueError("dimension names must be unique")
         self._dims = tuple(dims)
         self.name = name
+        # binnings are immutable and these are read on every container access
+        self._names = [d.name for d in dims]
+        self._shape = tuple(d.num_bins for d in dims)
+        self._size = int(np.prod(self._shape))
 
     dimensions = property(lambda self: self._dims)
-    names = property(lambda self: [d.name for d in self._dims])
+    names = property(lambda self: list(self._names))
     num_dims = property(lambda self: len(self._dims))
-    shape = property(lambda self: tuple(d.num_bins for d in self._dims))
+    shape = property(lambda self: self._shape)
     num_bins = property(lambda self: [d.num_bins for d in self._dims])
-    size = property(lambda self: int(np.prod([d.num_bins for d in self._dims])))
+    size = property(lambda self: self._size)
     tot_num_bins = size
     bin_edges = property(lambda self: [d.bin_edges for d in self._dims])
     domains = property(lambda self: [d.domain for d in self._dims])

@@ -31,11 +31,19 @@ __all__ = ["Container", "VirtualContainer", "ContainerSet", "default_device", "T
 TDTYPE = torch.float64 if FTYPE == np.float64 else torch.float32
 
 
+_DEVICES = {}
+
+
 def default_device():
-    if not torch.cuda.is_available():
+    # asked on every container write: cache one torch.device per CUDA ordinal
+    if not _DEVICES and not torch.cuda.is_available():
         raise RuntimeError("pisa_b200 containers are device resident and need a CUDA device "
                            "(there is no CPU fallback)")
-    return torch.device("cuda", torch.cuda.current_device())
+    ordinal = torch.cuda.current_device()
+    dev = _DEVICES.get(ordinal)
+    if dev is None:
+        dev = _DEVICES[ordinal] = torch.device("cuda", ordinal)
+    return dev
 
 
 def regularized_dims(binning):
@@ -70,6 +78,7 @@ class Container:
         self._representations = {}
         self.precedence = defaultdict(int)
         self._index_cache = {}
+        self._index_cache_names = set()   # coordinate names any cached bin index depends on
         self.representation = representation
 
     def __repr__(self):
@@ -139,8 +148,9 @@ class Container:
         if key in self.current_data.keys():
             self.mark_valid(key)
         # a changed coordinate invalidates every cached bin index that used it
-        for ck in [ck for ck, (names, _) in self._index_cache.items() if key in names]:
-            del self._index_cache[ck]
+        if key in self._index_cache_names:
+            for ck in [ck for ck, (names, _) in self._index_cache.items() if key in names]:
+                del self._index_cache[ck]
 
     def mark_valid(self, key):
         self.validity[key][hash(self.representation)] = True
@@ -149,6 +159,8 @@ class Container:
     def _to_device(self, data):
         dev = self.device or default_device()
         if isinstance(data, torch.Tensor):
+            if data.device == dev and (data.dtype == TDTYPE or not data.is_floating_point()) and data.is_contiguous():
+                return data
             t = data.to(dev)
         else:
             t = torch.as_tensor(np.ascontiguousarray(data), device=dev)
@@ -246,6 +258,7 @@ class Container:
         b, keep = ops.make_binning(regularized_dims(binning), coords[0].device)
         idx = ops.hist_index(b, coords)
         self._index_cache[ck] = (tuple(binning.names), idx)
+        self._index_cache_names.update(binning.names)
         return idx
 
     def translate(self, key, src_representation):

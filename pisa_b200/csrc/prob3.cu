@@ -372,8 +372,8 @@ static int grid_for(int64_t n, int blocks_per_sm) {
     return (int)(want < cap ? want : cap);
 }
 
-// Persistent grid: exactly the number of blocks that are resident at once (one wave), so that the
-// grid-stride loop gives every block the same share of every layer-count class.
+// Grid sizing.  PISAB_WAVES: whole waves of resident blocks for kernels whose blocks all do the same work (scan,
+// propagate); PISAB_SPREAD_WAVES: cap for the batched template kernel, whose blocks serve one container each.
 #ifndef PISAB_WAVES
 #define PISAB_WAVES 4
 #endif
@@ -547,8 +547,9 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     }
     // ranks (blocks) per container: at most PISAB_SPREAD_WAVES waves of resident blocks in total (blocks of
     // different containers differ in cost, so they are kept short: 1/32 of the run each; 4 waves cost 12 %, 8
-    // waves 5 %, 32 and 64 are level -- profiles/r01_fused_kernel_variants.txt) with >= 8 events per thread; small containers instead get up to one block per 256 events as long as one resident wave holds
-    // them all (latency of one or two events per template)
+    // waves 5 %, 32 and 64 are level -- profiles/r01_fused_kernel_variants.txt) with >= 8 events per thread;
+    // small containers instead get up to one block per 256 events as long as one resident wave holds them all
+    // (latency of one or two events per template)
     int ranks;
     {
         int occ = 0;
