@@ -332,11 +332,11 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     fused_template_body<IO, STD, PLAIN>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist);
 }
 
-// Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves template b / R with rank
-// b % R; its oscillation table comes from a device array (P tables do not fit the parameter space) and is
-// staged in shared memory.  For the event samples of a real analysis (1e5 .. 1e6 events) one template does
-// not fill the GPU and a per-template launch is bound by launch + host overhead (~270 us); batching the
-// hypotheses restores full occupancy.  Per-event outputs are not written (they would race between templates).
+// Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
+// = (b / (C R), (b / R) % C, b % R); its oscillation table comes from a device array (P tables do not fit the
+// parameter space) and is staged in shared memory.  For the event samples of a real analysis (1e5 .. 1e6
+// events) one template does not fill the GPU and a per-template launch is bound by launch latency plus one or
+// two event latencies (~45 us); batching the hypotheses restores full occupancy.  Per-event outputs are not written (they would race between templates).
 template <typename IO, bool STD>
 __global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
 reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_constant__ EarthTable earth,
@@ -345,7 +345,10 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     extern __shared__ __align__(16) double s_hist[];
     __shared__ EarthTable s_earth;
     __shared__ OscTable s_osc;
-    const int tmpl = blockIdx.x / ranks_per_template, rank = blockIdx.x - tmpl * ranks_per_template;
+    // block -> (template, container, rank): as in reweight_hist_kernel a block serves one container
+    const int per_template = batch.n_containers * ranks_per_template;
+    const int tmpl = blockIdx.x / per_template, rem = blockIdx.x - tmpl * per_template;
+    const int ci = rem / ranks_per_template, rank = rem - ci * ranks_per_template;
     {
         const double *src = reinterpret_cast<const double *>(tables + tmpl);
         double *dst = reinterpret_cast<double *>(&s_osc);
@@ -353,8 +356,7 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     }
     copy_earth(earth, &s_earth); // ends with __syncthreads()
     double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
-    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, 0, batch.n_containers, rank, ranks_per_template, mine,
-                                       s_hist);
+    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, ci, ci + 1, rank, ranks_per_template, mine, s_hist);
 }
 
 } // namespace pisab
@@ -629,13 +631,15 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
                                         workspace_bytes, stream);
 }
 
-// ranks (blocks) per template of a scan: every thread should see >= 8 events of the largest container, and
-// the launch should have at least one full wave of blocks
-static int scan_ranks(int64_t n_max, int n_templates) {
+// ranks (blocks) per (template, container) of a scan: every thread should see >= 8 events of the largest
+// container, and the launch should have at least one full wave of blocks
+static int scan_ranks(int64_t n_max, int n_templates, int n_containers) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
+    const int64_t pairs = (int64_t)n_templates * n_containers;
     int64_t r = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
-    const int64_t fill = ((int64_t)sms * 2 + n_templates - 1) / n_templates;
-    if (r < fill) r = fill;
+    const int64_t by_thread = (n_max + kBlock - 1) / kBlock;
+    const int64_t fill = ((int64_t)sms * 2 + pairs - 1) / pairs;
+    if (r < fill) r = by_thread < fill ? by_thread : fill;
     if (r < 1) r = 1;
     if (r > (int64_t)sms * 2) r = (int64_t)sms * 2;
     return (int)r;
@@ -679,7 +683,7 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     EarthTable et;
     const int rc = build_earth_table(earth, &et);
     if (rc) return rc;
-    const int ranks = scan_ranks(n_max, n_templates);
+    const int ranks = scan_ranks(n_max, n_templates, n_containers);
     const int64_t need = pisab_reweight_scan_workspace_bytes(n_templates, n_containers, n_bins, n_max);
     if (!d_workspace || workspace_bytes < need) { set_error("workspace too small: need %lld bytes", (long long)need); return PISAB_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
@@ -700,7 +704,7 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     }
     {
         LaunchTimer t(s);
-        kernel<<<n_templates * ranks, kBlock, smem, s>>>(d_tables, et, batch, ranks, d_partials);
+        kernel<<<n_templates * n_containers * ranks, kBlock, smem, s>>>(d_tables, et, batch, ranks, d_partials);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
@@ -782,7 +786,7 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
 int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_containers, int32_t n_bins, int64_t n_max) {
     if (n_templates < 1) n_templates = 1;
     if (n_containers < 1) n_containers = 1;
-    const int ranks = scan_ranks(n_max, n_templates);
+    const int ranks = scan_ranks(n_max, n_templates, n_containers);
     const int64_t table_bytes = ((int64_t)n_templates * (int64_t)sizeof(OscTable) + 255) / 256 * 256;
     return table_bytes + (int64_t)n_templates * n_containers * ranks * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
 }
