@@ -266,3 +266,27 @@ def test_mapset_json_interchange(tmp_path):
     assert got["nutau_cc"].hist.tolist() == [[1.5, 2.5], [3.5, 4.5]] and got["nutau_cc"].std_devs[1, 1] == 0.4
     assert got["nutau_cc"].binning.names == ["true_energy", "true_coszen"] and got["nutau_cc"].hash == -1234567890123
     assert jsons.from_json(path)["name"] == "dist"
+
+
+def test_import_alias_serves_pisa_names_from_this_package():
+    """``pisa_b200.compat.install_as_pisa``: reference-style imports (pipeline.py:284-296 resolves
+    ``pisa.stages.<stage>.<service>``) land on the same module objects; missing subsystems fail loudly."""
+    import importlib
+    import sys
+    import pisa_b200.compat as compat
+    assert "pisa" not in sys.modules
+    compat.install_as_pisa()
+    try:
+        compat.install_as_pisa()                                   # idempotent
+        pipeline_mod = importlib.import_module("pisa.core.pipeline")
+        prob3_mod = importlib.import_module("pisa.stages.osc.prob3")
+        hist_mod = importlib.import_module("pisa.stages.utils.hist")
+        import pisa_b200.core.pipeline, pisa_b200.stages.osc.prob3, pisa_b200.stages.utils.hist
+        assert pipeline_mod is pisa_b200.core.pipeline and prob3_mod is pisa_b200.stages.osc.prob3
+        assert hist_mod.hist is pisa_b200.stages.utils.hist.hist
+        assert importlib.import_module("pisa").FTYPE is pisa_b200.FTYPE
+        with pytest.raises(ModuleNotFoundError):
+            importlib.import_module("pisa.analysis.analysis")      # outside the hot path: not silently replaced
+    finally:
+        compat.uninstall()
+    assert not [m for m in sys.modules if m == "pisa" or m.startswith("pisa.")]
