@@ -23,3 +23,6 @@ HASH_SIGFIGS = 12
 TARGET = "cuda"  # the only target of this implementation (reference: cpu / parallel / cuda)
 
 RESOURCES_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "resources")
+
+# `from pisa import ureg, Q_` (reference pisa/__init__.py:59-64): the unit registry of this package
+from pisa_b200.utils.units import Quantity as Q_, ureg  # noqa: E402  pylint: disable=wrong-import-position
