@@ -143,8 +143,15 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
     const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
     const double ss = (k & 1) ? c : s;
     const double cc = (k & 1) ? s : c;
+#if defined(PISAB_HOST_EMU) || defined(PISAB_SIGN_SELECT)
     *sn = (k & 2) ? -ss : ss;
     *cs = ((k + 1) & 2) ? -cc : cc;
+#else
+    // quadrant signs as sign-bit XORs (bit 1 of k resp. k + 1 moved to bit 31 of the high word): three integer
+    // instructions per value instead of a negate and two selects
+    *sn = __hiloint2double(__double2hiint(ss) ^ ((k << 30) & 0x80000000), __double2loint(ss));
+    *cs = __hiloint2double(__double2hiint(cc) ^ (((k + 1) << 30) & 0x80000000), __double2loint(cc));
+#endif
 }
 
 // (cos t, sin t) with 3t = atan2(zi, zr), zi >= 0, i.e. the principal cube root of the unit complex
