@@ -16,7 +16,9 @@ import torch
 
 from . import ops
 
-__all__ = ["osc_consts", "osc_consts_array", "scan_chi2", "asimov"]
+__all__ = ["osc_consts", "osc_consts_array", "scan_chi2", "asimov", "fit_chi2", "OSC_PARAM_NAMES"]
+
+OSC_PARAM_NAMES = ("theta12", "theta13", "theta23", "deltacp", "dm21", "dm31")
 
 
 def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
@@ -129,3 +131,60 @@ def scan_chi2(engine, observed, points, fixed, mat_pot=None, batch=64):
         hist = engine.evaluate_many(consts)
         ops.template_chi2_batch(hist, observed, out=out[lo:lo + len(chunk)])
     return out
+
+
+def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=None, method="L-BFGS-B", options=None):
+    """Minimise ``mod_chi2`` of the template against ``observed`` over the oscillation parameters in ``start``
+    (what a minimiser iteration of ``Analysis.fit_hypo`` does through ``DistributionMaker.get_outputs``,
+    pisa/analysis/analysis.py; here only the oscillation parameters of the hot path can float).
+
+    Every objective call evaluates the point AND its central-difference gradient -- 2k + 1 hypotheses for k free
+    parameters -- in ONE launch (``ReweightEngine.evaluate_many`` + ``template_chi2_batch``) and reads 2k + 1
+    doubles back: for an analysis-size sample a launch is latency-bound, so the gradient costs nothing extra.
+
+    start  : dict name -> start value for the free parameters (names from ``OSC_PARAM_NAMES``; rad / eV^2)
+    fixed  : dict with the remaining parameters
+    bounds : optional dict name -> (lo, hi)
+    steps  : optional dict name -> finite-difference half step (default 1e-4 of the start value's magnitude)
+    Returns ``scipy.optimize.OptimizeResult`` with ``x`` as a dict, plus ``n_templates`` evaluated.
+    """
+    from scipy import optimize
+    names = list(start)
+    for nm in names + list(fixed):
+        if nm not in OSC_PARAM_NAMES:
+            raise ValueError("unknown oscillation parameter %r (known: %s)" % (nm, ", ".join(OSC_PARAM_NAMES)))
+    missing = [nm for nm in OSC_PARAM_NAMES if nm not in start and nm not in fixed]
+    if missing or set(start) & set(fixed):
+        raise ValueError("every oscillation parameter must be either free or fixed (missing: %s)" % missing)
+    k = len(names)
+    x0 = np.array([float(start[nm]) for nm in names])
+    # the minimiser works in units of `scale` so that angles (~1) and mass splittings (~1e-3) are comparable
+    scale = np.where(x0 != 0.0, np.abs(x0), 1.0)
+    h = np.array([float((steps or {}).get(nm, 1e-4 * s)) for nm, s in zip(names, scale)])
+    lo = np.array([(bounds or {}).get(nm, (-np.inf, np.inf))[0] for nm in names], dtype=np.float64)
+    hi = np.array([(bounds or {}).get(nm, (-np.inf, np.inf))[1] for nm in names], dtype=np.float64)
+    out = torch.empty(2 * k + 1, dtype=torch.float64, device=engine.device)
+    counter = [0]
+
+    def objective(u):
+        x = u * scale
+        pts = np.repeat(x[None, :], 2 * k + 1, axis=0)
+        for i in range(k):
+            # one-sided at a bound: keep both stencil points inside it
+            up, dn = min(x[i] + h[i], hi[i]), max(x[i] - h[i], lo[i])
+            pts[1 + 2 * i, i], pts[2 + 2 * i, i] = up, dn
+        args = {nm: pts[:, i] for i, nm in enumerate(names)}
+        args.update(fixed)
+        consts = osc_consts_array(args["theta12"], args["theta13"], args["theta23"], args["deltacp"], args["dm21"],
+                                  args["dm31"], mat_pot)
+        ops.template_chi2_batch(engine.evaluate_many(consts), observed, out=out)
+        counter[0] += 2 * k + 1
+        c = out.cpu().numpy()
+        grad = np.array([(c[1 + 2 * i] - c[2 + 2 * i]) / (pts[1 + 2 * i, i] - pts[2 + 2 * i, i]) for i in range(k)])
+        return float(c[0]), grad * scale
+
+    res = optimize.minimize(objective, x0 / scale, jac=True, method=method,
+                            bounds=list(zip(lo / scale, hi / scale)) if bounds else None, options=options)
+    res.x = {nm: float(v) for nm, v in zip(names, res.x * scale)}
+    res.n_templates = counter[0]
+    return res

@@ -12,6 +12,17 @@ L = Layers(os.path.join(ROOT, "pisa_b200/resources/osc/PREM_12layer.dat"), 2.0, 
 binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
 p = syn.NUFIT20_NH
 fixed = dict(theta12=np.deg2rad(p["theta12"]), theta13=np.deg2rad(p["theta13"]), deltacp=np.deg2rad(p["deltacp"]), dm21=p["deltam21"])
+# sequential gradient fit (objective + central differences in one launch per iteration)
+import time as _time
+from pisa_b200 import scan as _scan
+def fit_timing(eng, observed, fixed, start, bounds):
+    _scan.fit_chi2(eng, observed, start, fixed, bounds=bounds)
+    torch.cuda.synchronize(); t0 = _time.perf_counter()
+    res = _scan.fit_chi2(eng, observed, start, fixed, bounds=bounds)
+    dt = _time.perf_counter() - t0
+    print("fit theta23, dm31: %d objective calls (%d templates) in %.2f ms = %.1f us per call; chi2 %.2e; x = %s" % (
+        res.nfev, res.n_templates, dt * 1e3, dt / res.nfev * 1e6, res.fun, res.x))
+
 for per in (10_000, 100_000):
     eng = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
     for c, (name, nubar, flav) in enumerate(syn.CONTAINERS):
@@ -33,3 +44,5 @@ for per in (10_000, 100_000):
              t(lambda: ops.template_chi2(eng.evaluate(consts), obs, out=out)),
              t(lambda: ops.template_chi2(eng.evaluate(scan.osc_consts(theta23=0.74, dm31=2.5e-3, **fixed)), obs, out=out)),
              e0.elapsed_time(e1) * 1e3), flush=True)
+    fit_timing(eng, obs, fixed, dict(theta23=np.deg2rad(39.0), dm31=2.6e-3),
+               dict(theta23=(np.deg2rad(30.0), np.deg2rad(45.0)), dm31=(2.0e-3, 3.0e-3)))

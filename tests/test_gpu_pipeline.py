@@ -514,3 +514,42 @@ def test_engine_with_floating_flux_systematics():
         plain.add_container("x", 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
                             torch.zeros(100, dtype=torch.int32, device=dev))
         plain.set_flux_params()
+
+
+def test_fit_chi2_recovers_injected_parameters():
+    """Gradient fit over theta23 and dm31 (objective + central differences in one launch per iteration) returns to the
+    parameters the pseudo-data were made with; argument checking like a Stage's expected_params."""
+    _need_gpu()
+    from pisa_b200 import ops, scan
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    eng = ReweightEngine(L.earth_struct(), 128, np.float64, dev)
+    for i, (name, nubar, flav) in enumerate(syn.CONTAINERS):
+        ev = syn.make_events_numpy(20_000 + 13 * i, seed=40 + i)
+        tt = {k: torch.tensor(v, device=dev) for k, v in ev.items()}
+        idx = ops.hist_index(binning, [tt["reco_energy"], tt["reco_coszen"], tt["pid"]])
+        eng.add_container(name, nubar, flav, tt["true_energy"], tt["true_coszen"], tt["nu_flux"], tt["weights"], idx)
+    eng.set_scales([50.0] * len(syn.CONTAINERS))
+    p = syn.NUFIT20_NH
+    fixed = dict(theta12=np.deg2rad(p["theta12"]), theta13=np.deg2rad(p["theta13"]), deltacp=np.deg2rad(p["deltacp"]),
+                 dm21=p["deltam21"])
+    truth = dict(theta23=np.deg2rad(p["theta23"]), dm31=p["deltam31"])
+    observed = scan.asimov(eng, scan.osc_consts(**truth, **fixed))
+    start = dict(theta23=np.deg2rad(39.0), dm31=2.6e-3)
+    res = scan.fit_chi2(eng, observed, start, fixed,
+                        bounds=dict(theta23=(np.deg2rad(30.0), np.deg2rad(45.0)), dm31=(2.0e-3, 3.0e-3)))
+    assert res.fun < 1e-6, res
+    assert abs(res.x["theta23"] - truth["theta23"]) < 2e-4 and abs(res.x["dm31"] / truth["dm31"] - 1) < 2e-4, res.x
+    assert res.n_templates == 5 * res.nfev
+    # the objective is the scan's chi2: same value at the point the fit returned
+    c_fit = scan.scan_chi2(eng, observed, [(res.x["theta23"], res.x["dm31"])], fixed, batch=1).cpu().numpy()[0]
+    assert np.isclose(res.fun, c_fit, rtol=1e-6, atol=1e-12)
+    with pytest.raises(ValueError):
+        scan.fit_chi2(eng, observed, dict(theta24=0.1), fixed)
+    with pytest.raises(ValueError):
+        scan.fit_chi2(eng, observed, dict(theta23=0.7), fixed)          # dm31 neither free nor fixed
