@@ -1,8 +1,9 @@
 """``utils.hist`` service: events -> weighted histograms (+ sumw2 errors) on the output binning.
 
 Drop-in for pisa/stages/utils/hist.py (reference :27-223): constructor kwargs
-``apply_unc_weights, unweighted``; ``expected_params = ()``; ``calc_mode`` "events" (the
-binned->binned ``hist_transform`` mode :73-84,131-164 is outside the hot path and raises);
+``apply_unc_weights, unweighted``; ``expected_params = ()``; ``calc_mode`` "events", or a binning
+disjoint from the output binning: then a per-container ``hist_transform`` [calc bins, output bins]
+(event counts on the joint binning, :69-84) is built at setup and applied as a matrix product (:131-160);
 ``apply_mode`` defaults to ``data["output_binning"]`` (:64-67); with ``error_method == 'sumw2'`` the
 stage also writes ``errors = sqrt(sum w^2)`` and ``bin_unc2`` (:205-218).
 
@@ -38,14 +39,45 @@ class hist(Stage):  # pylint: disable=invalid-name
         else:
             assert self.apply_mode == self.data["output_binning"]
         if isinstance(self.calc_mode, MultiDimBinning):
-            raise NotImplementedError("utils.hist with a binned calc_mode (hist_transform) is outside the "
-                                      "pisa_b200 hot path; use calc_mode = events")
+            # the two binnings must be exclusive (hist.py:71-72)
+            assert len(set(self.calc_mode.names) & set(self.apply_mode.names)) == 0
+            transform_binning = self.calc_mode + self.apply_mode
+            for container in self.data:
+                container.representation = "events"
+                counts, _ = ops.hist_accumulate(container.bin_index(transform_binning), None, transform_binning.size,
+                                                want_w2=False)
+                container.representation = self.calc_mode
+                container["hist_transform"] = counts.reshape(self.calc_mode.size, self.apply_mode.size)
+            return
         # regularised binning + static per-event bin index (hist.py:86-127; cached on the container)
         self.data["regularized_output_binning"] = self.apply_mode
         for container in self.data:
             container.bin_index(self.apply_mode)
 
+    def _apply_transform(self):
+        """calc_mode binned: hist = (unc * w) @ hist_transform (hist.py:131-160)."""
+        if self.unweighted:
+            raise NotImplementedError("Unweighted hist only implemented in event-wise calculation")
+        for container in self.data:
+            container.representation = self.calc_mode
+            weights = container["weights"]
+            if "astro_weights" in container.keys:
+                weights = weights + container["astro_weights"]
+            unc = container["unc_weights"] if self.apply_unc_weights else torch.ones_like(weights)
+            transform = container["hist_transform"]
+            h = (unc * weights) @ transform
+            if self.error_method == "sumw2":
+                sumw2 = torch.square(unc * weights) @ transform
+                bin_unc2 = (torch.square(unc) * weights) @ transform
+            container.representation = self.apply_mode
+            container["weights"] = h
+            if self.error_method == "sumw2":
+                container["errors"] = torch.sqrt(sumw2)
+                container["bin_unc2"] = bin_unc2
+
     def apply_function(self):
+        if isinstance(self.calc_mode, MultiDimBinning):
+            return self._apply_transform()
         n_bins = self.apply_mode.size
         for container in self.data:
             container.representation = "events"

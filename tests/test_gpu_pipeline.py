@@ -553,3 +553,56 @@ def test_fit_chi2_recovers_injected_parameters():
         scan.fit_chi2(eng, observed, dict(theta24=0.1), fixed)
     with pytest.raises(ValueError):
         scan.fit_chi2(eng, observed, dict(theta23=0.7), fixed)          # dm31 neither free nor fixed
+
+
+def test_hist_stage_with_binned_calc_mode_uses_a_transform():
+    """utils.hist with calc_mode = a binning disjoint from the output binning (hist.py:69-84,131-160): the per-container
+    hist_transform is the event count on the joint binning and the output is (unc * w) @ transform, incl. sumw2 keys."""
+    _need_gpu()
+    from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+    from pisa_b200.core.container import Container, ContainerSet
+    from pisa_b200.stages.utils.hist import hist
+    rng = np.random.default_rng(11)
+    calc = MultiDimBinning([OneDimBinning("true_energy", num_bins=6, is_log=True, domain=[1, 1000]),
+                            OneDimBinning("true_coszen", num_bins=5, is_lin=True, domain=[-1, 1])], name="calc")
+    out = MultiDimBinning([OneDimBinning("reco_energy", num_bins=4, is_log=True, domain=[5, 60]),
+                           OneDimBinning("pid", bin_edges=[0.0, 0.3, 1.0])], name="reco")
+    data = ContainerSet("events")
+    host = {}
+    for name, n in (("nue_cc", 5000), ("numu_cc", 7001)):
+        c = Container(name)
+        ev = dict(true_energy=10 ** rng.uniform(0, 3, n), true_coszen=rng.uniform(-1, 1, n),
+                  reco_energy=10 ** rng.uniform(0.5, 2, n), pid=rng.uniform(0, 1, n))
+        for k, v in ev.items():
+            c[k] = v
+        c["weights"] = np.ones(n)
+        c.representation = calc
+        ev["w_binned"] = rng.uniform(0.5, 2.0, calc.size)
+        ev["unc_binned"] = rng.uniform(0.9, 1.1, calc.size)
+        c["weights"] = ev["w_binned"]
+        c["unc_weights"] = ev["unc_binned"]
+        c.representation = "events"
+        data.add_container(c)
+        host[name] = ev
+    data["output_binning"] = out
+    st = hist(calc_mode=calc, apply_mode=out, error_method="sumw2", apply_unc_weights=True, data=data)
+    st.setup()
+    st.run()
+    edges = [np.asarray(d.bin_edges.magnitude, dtype=np.float64) for d in (calc + out)]
+    for c in data:
+        ev = host[c.name]
+        sample = np.stack([ev["true_energy"], ev["true_coszen"], ev["reco_energy"], ev["pid"]], axis=1)
+        T, _ = np.histogramdd(sample, bins=edges)
+        T = T.reshape(calc.size, out.size)
+        c.representation = calc
+        got_T = c["hist_transform"].cpu().numpy()
+        assert np.abs(got_T - T).sum() <= 2            # log axes: device log vs numpy edges, 1-ulp edge cases only
+        w, u = ev["w_binned"], ev["unc_binned"]
+        c.representation = out
+        assert np.allclose(c["weights"].cpu().numpy(), (u * w) @ got_T, rtol=1e-12)
+        assert np.allclose(c["errors"].cpu().numpy(), np.sqrt(np.square(u * w) @ got_T), rtol=1e-12)
+        assert np.allclose(c["bin_unc2"].cpu().numpy(), (np.square(u) * w) @ got_T, rtol=1e-12)
+    with pytest.raises(NotImplementedError):
+        bad = hist(calc_mode=calc, apply_mode=out, unweighted=True, data=data)
+        bad.setup()
+        bad.run()
