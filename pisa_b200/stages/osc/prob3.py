@@ -15,19 +15,25 @@ at setup, :406-409) and the propagation (``propagate_array`` :439-450) in one ke
 ``distances`` arrays of the reference are therefore not materialised by default
 (``store_layers=True`` restores them for inspection).
 
-Out of scope (raise at construction): neutrino decay (numpy eigvals branch), vacuum-like NSI,
-Earth tomography, long-range interactions parameter classes.
+Both NSI parameterisations (:232-254,341-346), the long-range-interaction potential (:272-275,519-520,567-575)
+and the Earth-tomography density scalings (:278-297,368-395,521-537) are host-side parameter -> matrix / density
+work and follow the reference's sequence of calls.  Out of scope (raises at construction): neutrino decay
+(numpy eigvals branch).
 """
 import numpy as np
 
 from pisa_b200 import ops
 from pisa_b200.core.stage import Stage
 from pisa_b200.stages.osc.layers import Layers
-from pisa_b200.stages.osc.nsi_params import StdNSIParams
+from pisa_b200.stages.osc.lri_params import LRI_TYPES, LRIParams
+from pisa_b200.stages.osc.nsi_params import StdNSIParams, VacuumLikeNSIParams
+from pisa_b200.stages.osc.scaling_params import (FIVE_LAYER_RADII, FIVE_LAYER_RHOS, TOMOGRAPHY_ERROR_MSG,
+                                                 TOMOGRAPHY_TYPES, Core_scaling_w_constrain,
+                                                 Core_scaling_wo_constrain, Mass_scaling)
 from pisa_b200.stages.osc.osc_params import OscParams
 from pisa_b200.utils.resources import find_resource
 
-__all__ = ["prob3", "init_test", "NSI_TYPES"]
+__all__ = ["prob3", "init_test", "NSI_TYPES", "LRI_TYPES", "TOMOGRAPHY_TYPES"]
 
 NSI_TYPES = ["standard", "vacuum-like"]
 
@@ -46,28 +52,43 @@ class prob3(Stage):  # pylint: disable=invalid-name
             nsi_type = nsi_type.strip().lower()
             if nsi_type not in NSI_TYPES:
                 raise ValueError('Chosen NSI type "%s" not available! Choose one of %s.' % (nsi_type, NSI_TYPES))
-            if nsi_type == "vacuum-like":
-                raise NotImplementedError("vacuum-like NSI is outside the scope of pisa_b200")
         self.nsi_type = nsi_type
         self.reparam_mix_matrix = reparam_mix_matrix
         if neutrino_decay:
             raise NotImplementedError("neutrino decay (numpy.linalg.eigvals branch) is outside the scope of pisa_b200")
-        if tomography_type is not None:
-            raise NotImplementedError("Earth tomography is outside the scope of pisa_b200")
-        if lri_type is not None:
-            raise NotImplementedError("long-range interactions are outside the scope of pisa_b200")
         self.neutrino_decay, self.decay_flag = False, -1
-        self.tomography_type, self.lri_type = None, None
+        lri_params = ()
+        if lri_type is not None:
+            lri_type = lri_type.strip().lower()
+            if lri_type not in LRI_TYPES:
+                raise ValueError('Chosen LRI symmetry type "%s" not available! Choose one of %s.' % (lri_type, LRI_TYPES))
+            lri_params = ("v_lri",)
+        self.lri_type = lri_type
+        tomography_params = ()
+        if tomography_type is not None:
+            tomography_type = tomography_type.strip().lower()
+            if tomography_type not in TOMOGRAPHY_TYPES:
+                raise ValueError('Chosen tomography type "%s" not available! Choose one of %s.'
+                                 % (tomography_type, TOMOGRAPHY_TYPES))
+            tomography_params = {"mass_of_earth": ("density_scale",),
+                                 "mass_of_core_w_constrain": ("core_density_scale",),
+                                 "mass_of_core_wo_constrain": ("core_density_scale", "innermantle_density_scale",
+                                                               "middlemantle_density_scale")}[tomography_type]
+        self.tomography_type = tomography_type
         nsi_params = ()
         if nsi_type == "standard":
             nsi_params = ("eps_ee", "eps_emu_magn", "eps_emu_phase", "eps_etau_magn", "eps_etau_phase",
                           "eps_mumu", "eps_mutau_magn", "eps_mutau_phase", "eps_tautau")
-        super().__init__(expected_params=expected_params + nsi_params,
+        elif nsi_type == "vacuum-like":
+            nsi_params = ("eps_scale", "eps_prime", "phi12", "phi13", "phi23", "alpha1", "alpha2", "deltansi")
+        super().__init__(expected_params=expected_params + nsi_params + lri_params + tomography_params,
                          expected_container_keys=expected_container_keys, **std_kwargs)
         self.store_layers = store_layers
         self.layers = None
         self.osc_params = None
         self.nsi_params = None
+        self.lri_params = None
+        self.tomography_params = None
         self.gen_mat_pot_matrix_complex = None
         self.decay_matrix = np.zeros((3, 3), dtype=np.complex128)
         self.lri_pot = np.zeros((3, 3), dtype=np.float64)
@@ -93,6 +114,10 @@ class prob3(Stage):  # pylint: disable=invalid-name
         self.osc_params = OscParams()
         if self.nsi_type == "standard":
             self.nsi_params = StdNSIParams()
+        elif self.nsi_type == "vacuum-like":
+            self.nsi_params = VacuumLikeNSIParams()
+        if self.lri_type is not None:
+            self.lri_params = LRIParams()
         earth_model = find_resource(self.params.earth_model.value)
         self.YeI = self.params.YeI.value.m_as("dimensionless")
         self.YeO = self.params.YeO.value.m_as("dimensionless")
@@ -102,6 +127,18 @@ class prob3(Stage):  # pylint: disable=invalid-name
         self.layers = Layers(earth_model, detector_depth, prop_height)
         self.layers.setElecFrac(self.YeI, self.YeO, self.YeM)
         self._earth = self.layers.earth_struct()
+        if self.tomography_type == "mass_of_earth":
+            self.tomography_params = Mass_scaling()
+        elif self.tomography_type is not None:
+            # the external Earth model must be the hard-coded 5-layer one (:378-389)
+            radii_ext = self.layers.radii[::-1][:-1]
+            rhos_ext = self.layers.rhos_unweighted[::-1][:-1]
+            if len(radii_ext) != len(FIVE_LAYER_RADII) or len(rhos_ext) != len(FIVE_LAYER_RHOS):
+                raise ValueError(TOMOGRAPHY_ERROR_MSG)
+            if not (np.allclose(radii_ext + 1, FIVE_LAYER_RADII + 1) and np.allclose(rhos_ext + 1, FIVE_LAYER_RHOS + 1)):
+                raise ValueError(TOMOGRAPHY_ERROR_MSG)
+            self.tomography_params = (Core_scaling_w_constrain() if self.tomography_type == "mass_of_core_w_constrain"
+                                      else Core_scaling_wo_constrain())
 
         # layers do not care about flavour: link everything while touching true_coszen (:398-412)
         if self.is_map:
@@ -150,11 +187,42 @@ class prob3(Stage):  # pylint: disable=invalid-name
             n.eps_mutau = (p.eps_mutau_magn.value.m_as("dimensionless"), p.eps_mutau_phase.value.m_as("rad"))
             n.eps_tautau = p.eps_tautau.value.m_as("dimensionless")
             self.gen_mat_pot_matrix_complex = std + n.eps_matrix
+        elif self.nsi_type == "vacuum-like":
+            n = self.nsi_params
+            n.eps_scale = p.eps_scale.value.m_as("dimensionless")
+            n.eps_prime = p.eps_prime.value.m_as("dimensionless")
+            for name in ("phi12", "phi13", "phi23", "alpha1", "alpha2", "deltansi"):
+                setattr(n, name, p[name].value.m_as("rad"))
+            self.gen_mat_pot_matrix_complex = std + n.eps_matrix
         else:
             self.gen_mat_pot_matrix_complex = std
+        if self.lri_type is not None:                        # :519-520,567-575
+            self.lri_params.v_lri = p.v_lri.value.m_as("eV")
+            self.lri_pot = self.lri_params.potential_matrix(self.lri_type)
         mix = o.mix_matrix_reparam_complex if self.reparam_mix_matrix else o.mix_matrix_complex
         return ops.OscConsts.from_matrices(o.dm_matrix, mix, self.gen_mat_pot_matrix_complex, self.decay_flag,
                                            self.decay_matrix, self.lri_pot)
+
+    def _apply_tomography(self):
+        """prob3.py:521-537, call for call: ``Layers.scaling`` with the type's factors, then ``setElecFrac`` and new
+        layer densities.  (``setElecFrac`` weights ``rhos_unweighted`` -- layers.py:411-439 -- which ``scaling``
+        does not touch, so in this reference revision the factors do not reach the propagated densities; the
+        sequence is kept as it is so that results stay identical.)"""
+        p, t = self.params, self.tomography_params
+        if self.tomography_type == "mass_of_earth":
+            t.density_scale = p.density_scale.value.m_as("dimensionless")
+            self.layers.scaling(scaling_array=t.density_scale)
+        elif self.tomography_type == "mass_of_core_w_constrain":
+            t.core_density_scale = p.core_density_scale.value.m_as("dimensionless")
+            self.layers.scaling(scaling_array=t.scaling_array)
+        else:
+            t.core_density_scale = p.core_density_scale.value.m_as("dimensionless")
+            t.innermantle_density_scale = p.innermantle_density_scale.value.m_as("dimensionless")
+            t.middlemantle_density_scale = p.middlemantle_density_scale.value.m_as("dimensionless")
+            self.layers.scaling(scaling_array=t.scaling_factor_array)
+        self.layers.setElecFrac(self.YeI, self.YeO, self.YeM)
+        self._earth = self.layers.earth_struct()
+        self._store_layers()
 
     def compute_function(self):
         YeI = self.params.YeI.value.m_as("dimensionless")
@@ -165,6 +233,8 @@ class prob3(Stage):  # pylint: disable=invalid-name
             self.layers.setElecFrac(YeI, YeO, YeM)
             self._earth = self.layers.earth_struct()
             self._store_layers()
+        if self.tomography_type is not None:
+            self._apply_tomography()
         consts = self._update_matrices()
 
         self._link()

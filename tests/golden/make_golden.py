@@ -205,6 +205,24 @@ def gen_params(ns):
     op = ns.osc_params.OscParams()
     op.dm21, op.dm31 = 0.0, 0.0
     out["degenerate/dm"] = op.dm_matrix
+    # vacuum-like NSI parameterisation (nsi_params.py:184-384): seeded parameter sets + the reference's default
+    rng = np.random.default_rng(7)
+    sets = [dict(eps_scale=1.0, eps_prime=0.0, phi12=0.0, phi13=0.0, phi23=0.0, alpha1=0.0, alpha2=0.0, deltansi=0.0)]
+    for _ in range(6):
+        sets.append(dict(eps_scale=rng.uniform(0.5, 1.5), eps_prime=rng.uniform(-0.3, 0.3),
+                         phi12=rng.uniform(-np.pi, np.pi), phi13=rng.uniform(-np.pi, np.pi),
+                         phi23=rng.uniform(-np.pi, np.pi), alpha1=rng.uniform(0, 2 * np.pi),
+                         alpha2=rng.uniform(0, 2 * np.pi), deltansi=rng.uniform(0, 2 * np.pi)))
+    names = sorted(sets[0])
+    out["vacuum_nsi/names"] = np.array(names)
+    out["vacuum_nsi/values"] = np.array([[s[k] for k in names] for s in sets])
+    mats = []
+    for s in sets:
+        v = ns.nsi_params.VacuumLikeNSIParams()
+        for k in names:
+            setattr(v, k, s[k])
+        mats.append(v.eps_matrix)
+    out["vacuum_nsi/eps"] = np.array(mats)
     np.savez_compressed(os.path.join(HERE, "ref_params_f8.npz"), **out)
 
 

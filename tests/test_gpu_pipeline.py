@@ -606,3 +606,74 @@ def test_hist_stage_with_binned_calc_mode_uses_a_transform():
         bad = hist(calc_mode=calc, apply_mode=out, unweighted=True, data=data)
         bad.setup()
         bad.run()
+
+
+def _prob3_stage(extra_params=(), **ctor):
+    from pisa_b200.core.container import Container, ContainerSet
+    from pisa_b200.core.param import Param, ParamSet
+    from pisa_b200.stages.osc.prob3 import prob3
+    from pisa_b200.utils.units import ureg
+    rng = np.random.default_rng(3)
+    data = ContainerSet("events")
+    for name, nubar, flav in (("numu_cc", 1, 1), ("nuebar_cc", -1, 0)):
+        c = Container(name)
+        n = 3000
+        c["true_energy"] = 10 ** rng.uniform(0, 2.5, n)
+        c["true_coszen"] = rng.uniform(-1, 1, n)
+        c["nu_flux"] = rng.uniform(0.5, 1.5, (n, 2))
+        c["weights"] = np.ones(n)
+        c.set_aux_data("nubar", nubar)
+        c.set_aux_data("flav", flav)
+        data.add_container(c)
+    params = [Param(name="detector_depth", value=2.0 * ureg.km), Param(name="prop_height", value=20.0 * ureg.km),
+              Param(name="earth_model", value="osc/PREM_12layer.dat"), Param(name="YeI", value=0.4656),
+              Param(name="YeO", value=0.4656), Param(name="YeM", value=0.4957),
+              Param(name="theta12", value=33.48 * ureg.degree), Param(name="theta13", value=8.5 * ureg.degree),
+              Param(name="theta23", value=42.3 * ureg.degree), Param(name="deltam21", value=7.5e-5 * ureg.eV ** 2),
+              Param(name="deltam31", value=2.457e-3 * ureg.eV ** 2), Param(name="deltacp", value=306 * ureg.degree)]
+    st = prob3(params=ParamSet(params + list(extra_params)), data=data, calc_mode="events", apply_mode="events", **ctor)
+    st.setup()
+    st.run()
+    return st
+
+
+def _oracle_probs(st, container):
+    L = _oracle_layers()
+    o = st.osc_params
+    c = container
+    c.representation = "events"
+    _, den, dis = L.calcLayers(c["true_coszen"].cpu().numpy())
+    zc = np.zeros((3, 3), dtype=complex)
+    return oracle.propagate_array(o.dm_matrix, o.mix_matrix_complex, st.gen_mat_pot_matrix_complex, -1, zc,
+                                  np.asarray(st.lri_pot, dtype=np.float64), int(c["nubar"]),
+                                  c["true_energy"].cpu().numpy(), den, dis)
+
+
+def test_prob3_stage_vacuum_like_nsi_lri_and_tomography():
+    """The remaining branches of prob3.compute_function (prob3.py:485-537,567-575): vacuum-like NSI, a long-range
+    potential and the tomography call sequence, through the Stage API against the oracle fed with the stage's
+    own matrices."""
+    _need_gpu()
+    from pisa_b200.core.param import Param
+    from pisa_b200.utils.units import ureg
+    vac = [Param(name="eps_scale", value=1.1), Param(name="eps_prime", value=0.15),
+           Param(name="phi12", value=0.3 * ureg.rad), Param(name="phi13", value=-0.2 * ureg.rad),
+           Param(name="phi23", value=0.5 * ureg.rad), Param(name="alpha1", value=0.4 * ureg.rad),
+           Param(name="alpha2", value=1.1 * ureg.rad), Param(name="deltansi", value=2.0 * ureg.rad)]
+    lri = [Param(name="v_lri", value=2.0e-14 * ureg.eV)]
+    st = _prob3_stage(vac + lri, nsi_type="vacuum-like", lri_type="etau-symmetry")
+    assert np.array_equal(st.lri_pot, np.diag([2.0e-14, 0.0, -2.0e-14]))
+    assert abs(st.gen_mat_pot_matrix_complex[0, 1]) > 1e-3          # a genuinely non-standard potential
+    plain = _prob3_stage()
+    for c, c0 in zip(st.data, plain.data):
+        prob = _oracle_probs(st, c)
+        flav = int(c["flav"])
+        assert np.allclose(c["prob_e"].cpu().numpy(), prob[:, 0, flav], rtol=0, atol=1e-10)
+        assert np.allclose(c["prob_mu"].cpu().numpy(), prob[:, 1, flav], rtol=0, atol=1e-10)
+        assert np.abs(c["prob_mu"].cpu().numpy() - c0["prob_mu"].cpu().numpy()).max() > 1e-3
+    # tomography: the reference's call sequence leaves the propagated densities unchanged (see _apply_tomography)
+    tomo = _prob3_stage([Param(name="density_scale", value=1.3)], tomography_type="mass_of_earth")
+    for c, c0 in zip(tomo.data, plain.data):
+        assert np.array_equal(c["prob_mu"].cpu().numpy(), c0["prob_mu"].cpu().numpy())
+    with pytest.raises(ValueError, match="5-layer"):
+        _prob3_stage([Param(name="core_density_scale", value=1.02)], tomography_type="mass_of_core_w_constrain")

@@ -155,9 +155,19 @@ def test_stage_contract_errors():
     h.data = "not a container set"
     with pytest.raises(TypeError):
         h.setup()
-    # nsi_type='standard' adds the nine eps_* names (prob3.py:244-254)
+    # nsi_type='standard' adds the nine eps_* names (prob3.py:244-254), 'vacuum-like' its eight (:234-243)
     with pytest.raises(ValueError, match="eps_ee"):
         prob3(params=good, nsi_type="standard")
+    with pytest.raises(ValueError, match="eps_scale"):
+        prob3(params=good, nsi_type="vacuum-like")
+    with pytest.raises(ValueError, match="v_lri"):
+        prob3(params=good, lri_type="emu-symmetry")
+    with pytest.raises(ValueError, match="not available"):
+        prob3(params=good, lri_type="ee-symmetry")
+    with pytest.raises(ValueError, match="density_scale"):
+        prob3(params=good, tomography_type="mass_of_earth")
+    with pytest.raises(ValueError, match="not available"):
+        prob3(params=good, tomography_type="mass_of_moon")
 
 
 def test_csv_loader_event_selection(tmp_path):
