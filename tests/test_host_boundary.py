@@ -84,14 +84,16 @@ def test_paramset_selector_and_hash():
 
 def test_binning_classification_is_ftype_dependent_rule():
     """dragon_datarelease.reco_energy has 9-digit edges whose ratios differ by 5.5e-10,
-    so in FP64 (rtol 1e-12) it is IRREGULAR -> searchsorted on the real edges."""
+    so in FP64 (rtol 1e-12) it is IRREGULAR -> searchsorted on the real edges; under PISA_FTYPE=fp32 (rtol 1e-5) the
+    same axis is regular-log."""
+    from pisa_b200 import FTYPE
     e = OneDimBinning("reco_energy", is_log=True, bin_edges=[5.62341325, 7.49894209, 10.0, 13.33521432, 17.7827941,
                                                              23.71373706, 31.6227766, 42.16965034, 56.23413252] * ureg.GeV)
-    assert e.is_irregular and e.is_log and e.num_bins == 8
+    assert e.is_irregular == (FTYPE == np.float64) and e.is_log and e.num_bins == 8
     t = OneDimBinning("true_energy", num_bins=200, is_log=True, domain=[1., 1000] * ureg.GeV)
     c = OneDimBinning("true_coszen", num_bins=200, is_lin=True, domain=[-1, 1])
     assert not t.is_irregular and not c.is_irregular
-    assert np.array_equal(t.bin_edges.m, np.logspace(0, 3, 201))
+    assert np.array_equal(t.bin_edges.m, np.logspace(0, 3, 201, dtype=FTYPE))
     assert np.allclose(t.weighted_centers.m, np.sqrt(t.bin_edges.m[:-1] * t.bin_edges.m[1:]), rtol=0, atol=0)
     m = MultiDimBinning([t, c], name="calc_grid")
     assert m.shape == (200, 200) and m.size == 40000 and m.names == ["true_energy", "true_coszen"]
@@ -122,7 +124,7 @@ def test_parse_own_and_reference_pipeline_cfgs():
         assert d[("osc", "prob3")]["calc_mode"].shape == (200, 200)
         p = d[("osc", "prob3")]["params"].params
         assert p.theta23.value.m_as("deg") == 42.0 and p.deltacp.value.m_as("deg") == 0.0
-        assert np.array_equal(p.theta13.range.m, [7.85, 9.1]) and p.theta13.prior["kind"] == "gaussian"
+        assert np.allclose(p.theta13.range.m, [7.85, 9.1], rtol=1e-6) and p.theta13.prior["kind"] == "gaussian"
         d = parse_pipeline_config("settings/pipeline/IceCube_3y_neutrinos.cfg")
         assert d[("utils", "hist")]["error_method"] == "sumw2"
         assert d[("osc", "prob3")]["calc_mode"].shape == (200, 200) and d[("osc", "prob3")]["apply_mode"] == "events"
