@@ -75,7 +75,8 @@ typedef struct pisab_binning {
     int32_t n_dims;
     int32_t kind[PISAB_MAX_DIMS];
     int32_t n_bins[PISAB_MAX_DIMS];
-    double lo[PISAB_MAX_DIMS];             /* LIN: domain; LOG: log(domain) (hist.py:118-120) */
+    double lo[PISAB_MAX_DIMS];             /* LIN and LOG: the domain (LOG: raw, > 0; the library takes    */
+                                           /* its log on the device like the samples', hist.py:118-120)     */
     double hi[PISAB_MAX_DIMS];
     const double *d_edges[PISAB_MAX_DIMS]; /* EDGES: device pointer to n_bins+1 edges         */
 } pisab_binning_t;

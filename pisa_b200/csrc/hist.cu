@@ -78,6 +78,18 @@ hist_index_kernel(const __grid_constant__ BinningTable Bg, const __grid_constant
         }
     }
     __syncthreads();
+    // LOG dimensions arrive with their RAW domain: its logarithm is taken here, by the same function (and in the
+    // same precision) as the samples' below, so that a sample equal to an edge lands on the edge -- like the
+    // reference, whose regularised domain and samples both go through np.log of FTYPE values (hist.py:118-120,
+    // container.py:845-850).  Host-side logs can differ from the device's by an ulp.
+#pragma unroll
+    for (int d = 0; d < NDIMS; ++d) {
+        if (B.kind[d] == PISAB_DIM_LOG) {
+            B.lo[d] = sizeof(IO) == 4 ? (double)logf((float)B.lo[d]) : log(B.lo[d]);
+            B.hi[d] = sizeof(IO) == 4 ? (double)logf((float)B.hi[d]) : log(B.hi[d]);
+            B.norm[d] = (double)B.n_bins[d] / (B.hi[d] - B.lo[d]);
+        }
+    }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + stride < n; i += 2 * stride) {
@@ -470,6 +482,7 @@ static int hist_index_impl(const pisab_binning_t *binning, const IO *const *d_co
         B.edges[d] = binning->d_edges[d];
         if (B.kind[d] == PISAB_DIM_EDGES && !B.edges[d]) { set_error("dimension %d: edges missing", d); return PISAB_ERR_ARG; }
         if (B.kind[d] != PISAB_DIM_EDGES && !(B.hi[d] > B.lo[d])) { set_error("dimension %d: empty range", d); return PISAB_ERR_ARG; }
+        if (B.kind[d] == PISAB_DIM_LOG && !(B.lo[d] > 0.0)) { set_error("dimension %d: a logarithmic axis needs a positive domain", d); return PISAB_ERR_ARG; }
         C.p[d] = d_coords[d];
         if (!C.p[d]) { set_error("dimension %d: null sample", d); return PISAB_ERR_ARG; }
     }

@@ -268,7 +268,8 @@ def apply_osc_weights(nu_flux, prob_e, prob_mu, weights):
 
 def make_binning(dims, device):
     """dims: list of dicts {kind: 'lin'|'log'|'edges', n_bins, lo, hi, edges}.  For 'log', lo/hi
-    are the RAW domain; log() is taken here exactly like hist.py:118-120 (np.log(domain)).
+    are the RAW domain; its log (hist.py:118-120) is taken on the device by the library, with the function
+    and precision used for the samples, so that samples equal to an edge stay on it.
     Returns (Binning struct, keep-alive list of edge tensors)."""
     if not 1 <= len(dims) <= _lib.MAX_DIMS:
         raise ValueError("1..%d dimensions supported" % _lib.MAX_DIMS)
@@ -287,8 +288,9 @@ def make_binning(dims, device):
             b.d_edges[i] = edges.data_ptr()
             b.lo[i], b.hi[i] = float(edges[0]), float(edges[-1])
         elif kind == "log":
-            lo, hi = np.log(np.asarray([d["lo"], d["hi"]], dtype=np.float64))
-            b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LOG, float(lo), float(hi)
+            if not 0.0 < float(d["lo"]) < float(d["hi"]):
+                raise ValueError("a logarithmic dimension needs 0 < lo < hi")
+            b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LOG, float(d["lo"]), float(d["hi"])
         elif kind == "lin":
             b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LIN, float(d["lo"]), float(d["hi"])
         else:

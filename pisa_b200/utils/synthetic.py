@@ -68,7 +68,22 @@ def make_events_numpy(n, seed, dtype=np.float64):
     pid = rng.integers(0, 2, n).astype(np.float64)
     out = dict(true_energy=true_energy, true_coszen=true_coszen, nu_flux=nu_flux, weights=weights,
                reco_energy=reco_energy, reco_coszen=reco_coszen, pid=pid)
-    return {k: np.ascontiguousarray(v.astype(dtype)) for k, v in out.items()}
+    out = {k: np.ascontiguousarray(v.astype(dtype)) for k, v in out.items()}
+    _clip_in_storage_type(out, np.minimum, np.dtype(dtype).type)
+    return out
+
+
+def _clip_in_storage_type(ev, minimum, ftype):
+    """Rounding to float32 can move a clipped value onto the (excluded) upper edge: clip once more in the storage
+    type, so that the reconstructed coordinates stay inside the half-open binning range in both FTYPE modes."""
+    if ftype == np.float64:
+        return
+    # (on the logarithmic energy axis the in-range test is made on float32 logs, which cannot resolve one ulp of
+    # the edge itself: stay 2^-20 below it)
+    top_e = float(np.float32(DRAGON_E_EDGES[-1]) * np.float32(1.0 - 2.0 ** -20))
+    top_cz = float(np.nextafter(np.float32(1.0), np.float32(0)))
+    ev["reco_energy"] = minimum(ev["reco_energy"], ev["reco_energy"] * 0 + top_e)
+    ev["reco_coszen"] = minimum(ev["reco_coszen"], ev["reco_coszen"] * 0 + top_cz)
 
 
 def make_events_torch(n, seed, dtype, device):
@@ -89,7 +104,9 @@ def make_events_torch(n, seed, dtype, device):
     pid = torch.randint(0, 2, (n,), generator=g, device=device).to(torch.float64)
     out = dict(true_energy=true_energy, true_coszen=true_coszen, nu_flux=nu_flux, weights=weights,
                reco_energy=reco_energy, reco_coszen=reco_coszen, pid=pid)
-    return {k: v.to(tdt).contiguous() for k, v in out.items()}
+    out = {k: v.to(tdt).contiguous() for k, v in out.items()}
+    _clip_in_storage_type(out, torch.minimum, np.dtype(dtype).type)
+    return out
 
 
 def layer_counts(coszen_limit, coszen, idx_first_inner=2):

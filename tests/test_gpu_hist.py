@@ -64,15 +64,28 @@ def test_index_bit_exact_lin_log_edges(dtype):
     # (b) log-regular energy axis: linear bins in log(x) (hist.py:114-121)
     with np.errstate(all="ignore"):
         log_e = np.log(reco_e)  # numpy log in FTYPE, like Container.translate
-    b, keep = ops.make_binning([dict(kind="log", n_bins=8, lo=5.62341325, hi=56.23413252),
+    # the binning's edges are FTYPE values, and the regularised domain is their FTYPE log (hist.py:118-120)
+    e_lo, e_hi = dtype(5.62341325), dtype(56.23413252)
+    b, keep = ops.make_binning([dict(kind="log", n_bins=8, lo=float(e_lo), hi=float(e_hi)),
                                 dict(kind="lin", n_bins=8, lo=-1.0, hi=1.0),
                                 dict(kind="lin", n_bins=2, lo=0.0, hi=2.0)], dev)
     idx = ops.hist_index(b, t).cpu().numpy()
-    lo, hi = np.log(5.62341325), np.log(56.23413252)
+    lo, hi = float(np.log(e_lo)), float(np.log(e_hi))
     ref, _ = oracle.regular_index([log_e, reco_cz, pid], [lo, -1.0, 0.0], [hi, 1.0, 2.0], [8, 8, 2], dtype)
     diff = np.flatnonzero(idx != ref)
     # device log vs numpy log can differ by 1 ulp: only events within 1 ulp of an edge may move
     assert len(diff) <= 2, (len(diff), reco_e[diff][:5])
+    # samples sitting exactly on the ends of the logarithmic domain (clipped reconstructions pile up there): the
+    # domain's log is taken by the same device function as the samples', so lo is inside and hi outside in both
+    # precisions, as in the reference (np.log of the FTYPE edge and of the FTYPE sample)
+    for lo_raw, hi_raw in ((5.62341325, 56.23413252), (1.0, 1000.0), (0.3, 7.7)):
+        lo_t, hi_t = dtype(lo_raw), dtype(hi_raw)
+        b1, _ = ops.make_binning([dict(kind="log", n_bins=8, lo=float(lo_t), hi=float(hi_t))], dev)
+        ends = np.array([lo_t, hi_t, np.nextafter(lo_t, dtype(0)), np.nextafter(hi_t, dtype(0))], dtype=dtype)
+        got = ops.hist_index(b1, [torch.tensor(ends, device=dev)]).cpu().numpy()
+        # (a value one ulp below an end may share the end's logarithm: the in-range test is made in log space, as in
+        # the reference, so it goes with the end or to the other side)
+        assert got[0] == 0 and got[1] == -1 and got[2] in (-1, 0) and got[3] in (7, -1), (lo_raw, hi_raw, got)
 
 
 def test_accumulate_vs_oracle_and_deterministic():

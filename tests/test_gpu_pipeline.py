@@ -677,3 +677,35 @@ def test_prob3_stage_vacuum_like_nsi_lri_and_tomography():
         assert np.array_equal(c["prob_mu"].cpu().numpy(), c0["prob_mu"].cpu().numpy())
     with pytest.raises(ValueError, match="5-layer"):
         _prob3_stage([Param(name="core_density_scale", value=1.02)], tomography_type="mass_of_core_w_constrain")
+
+
+def test_pipeline_in_fp32_process_mode(tmp_path):
+    """PISA_FTYPE=fp32 (pisa/__init__.py:152-179: f4 containers everywhere) through the same cfg: float32 device
+    arrays end to end, maps within float32 accuracy of the FP64 pipeline (bin flips of edge events aside)."""
+    _need_gpu()
+    import subprocess
+    import sys
+    from pisa_b200.core.pipeline import Pipeline
+    out_file = str(tmp_path / "fp32_maps.npz")
+    code = (
+        "import numpy as np, torch\n"
+        "import pisa_b200\n"
+        "from pisa_b200.core.pipeline import Pipeline\n"
+        "assert pisa_b200.FTYPE == np.float32\n"
+        "p = Pipeline('settings/pipeline/b200_events.cfg')\n"
+        "m = p.get_outputs()\n"
+        "c = p.data.containers[0]; c.representation = 'events'\n"
+        "assert c['true_energy'].dtype == torch.float32 and c['prob_mu'].dtype == torch.float32\n"
+        "assert c['weights'].dtype == torch.float32\n"
+        "np.savez(%r, **{k.name: k.hist for k in m})\n" % out_file)
+    env = dict(os.environ, PISA_FTYPE="fp32", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    res = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    got = np.load(out_file)
+    ref = Pipeline("settings/pipeline/b200_events.cfg").get_outputs()
+    for m in ref:
+        a, b = got[m.name].astype(np.float64), m.hist
+        assert a.shape == b.shape
+        assert abs(a.sum() / b.sum() - 1) < 1e-4, m.name
+        # per bin: float32 rounding of ~150 events per bin plus the odd event changing bins
+        assert np.allclose(a, b, rtol=2e-2, atol=2e-3 * b.max()), (m.name, np.abs(a - b).max() / b.max())
