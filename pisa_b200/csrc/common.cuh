@@ -1,7 +1,7 @@
 // common.cuh -- error handling, launch bookkeeping and device tables shared by the kernels.
 #pragma once
 #ifdef PISAB_HOST_EMU
-#include "../../scratch/hostemu/cuda_shim.h" // development-only: device math compiled by g++
+#include "../../tests/hostemu/cuda_shim.h" // test infrastructure only: the device math compiled by g++ (tests/hostemu/)
 #else
 #include <cuda_runtime.h>
 #endif

@@ -1,4 +1,8 @@
-"""Compare the host-emulated device math with the CPU oracle (development tool)."""
+"""Compare the host-emulated device math with the CPU oracle.
+
+Test infrastructure (tests/test_device_math_emulation.py builds libemu.so with g++ and calls `run`); also a
+stand-alone development tool:  g++ -O2 -fopenmp -shared -fPIC -std=c++17 -DPISAB_HOST_EMU -include cuda_shim.h
+-I../../pisa_b200/csrc -I../../include -o libemu.so emu.cpp && python check.py"""
 import ctypes, os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -7,7 +11,14 @@ import oracle
 from pisa_b200._lib import OscConsts, Earth
 from pisa_b200.utils import synthetic as syn
 
-emu = ctypes.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "libemu.so"))
+emu = None
+
+
+def load(path=None):
+    global emu
+    emu = ctypes.CDLL(path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libemu.so"))
+    return emu
+
 
 def layers_obj(model="PREM_12layer.dat", depth=2.0, height=20.0):
     prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", model))
@@ -41,6 +52,7 @@ def run(n=200000, nsi=False, nubar=1, lri=None, model="PREM_12layer.dat", seed=0
     return worst
 
 if __name__ == "__main__":
+    load()
     w = 0
     for nubar in (1, -1):
         for nsi in (False, True):

@@ -26,6 +26,9 @@ static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #include <cstring>
+// the shared-memory state classes index by thread: never instantiated on the host, but they must parse
+struct pisab_emu_dim3 { int x, y, z; };
+static const pisab_emu_dim3 threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, blockIdx = {0, 0, 0}, gridDim = {1, 1, 1};
 static inline double pisab_emu_hi32(double v) {
     uint64_t b; std::memcpy(&b, &v, 8); b &= 0xffffffff00000000ull; std::memcpy(&v, &b, 8); return v;
 }

@@ -1,5 +1,7 @@
 // Host emulation of the per-event device math (development tool, see cuda_shim.h).
+#ifndef PISAB_HOST_EMU
 #define PISAB_HOST_EMU
+#endif
 #include "../../pisa_b200/csrc/prob3_device.cuh"
 #include "../../pisa_b200/csrc/tables.cu"
 #include <stdarg.h>

@@ -1,0 +1,44 @@
+"""The per-event DEVICE math (pisa_b200/csrc/prob3_device.cuh: eigenvalues, Cayley-Hamilton transition matrices,
+shell-twin propagation, vacuum shortcut, standard-matter specialisation) compiled for the HOST with g++ through a small
+shim (tests/hostemu/) and compared with the oracle on seeded events.  This is a CPU-side guard for numerics changes in
+the CUDA headers -- it runs where there is no GPU; the GPU parity tests (tests/test_gpu_prob3.py) remain the parity
+tests proper.  Nothing here is part of the product: the library is only ever built by nvcc without PISAB_HOST_EMU."""
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+HOSTEMU = os.path.join(ROOT, "tests", "hostemu")
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("hostemu") / "libemu.so")
+    cmd = [gxx, "-O2", "-fopenmp", "-shared", "-fPIC", "-std=c++17", "-DPISAB_HOST_EMU", "-include",
+           os.path.join(HOSTEMU, "cuda_shim.h"), "-I" + os.path.join(ROOT, "pisa_b200", "csrc"),
+           "-I" + os.path.join(ROOT, "include"), "-o", out, os.path.join(HOSTEMU, "emu.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    sys.path.insert(0, HOSTEMU)
+    import check
+    check.load(out)
+    return check
+
+
+@pytest.mark.parametrize("nsi,nubar", [(False, 1), (True, 1), (False, -1), (True, -1)])
+def test_device_math_on_host_matches_oracle(emu, nsi, nubar):
+    assert emu.run(n=30000, nsi=nsi, nubar=nubar, seed=5) < 1e-10     # measured ~4e-13
+
+
+def test_device_math_on_host_lri_and_other_earth_models(emu):
+    assert emu.run(n=20000, lri=np.diag([1e-14, -1e-14, 0.0]), seed=6) < 1e-10
+    assert emu.run(n=20000, model="PREM_10layer.dat", seed=7) < 1e-10
+    assert emu.run(n=20000, model="PREM_4layer.dat", depth=10.0, seed=8) < 1e-10
