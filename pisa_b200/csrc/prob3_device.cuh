@@ -62,7 +62,8 @@ __constant__ double kTab[24] = {
     /* 18 */ 5.068,                   // 2 * 2.534  (numba_osc_kernels.py:524)
     /* 19 */ 0.375,
     /* 20 */ 1e-200, // lower clamp of p and of the discriminant
-    0, 0, 0};
+    /* 21 */ 6755399441055744.0, // 1.5 * 2^52: adding it rounds to an integer that sits in the low word
+    0, 0};
 
 // 1/x, 1/sqrt(x) and sqrt(x) from the hardware approximations (MUFU.RCP64H / RSQ64H, ~2^-22) refined
 // by ONE third-order step (error -> ~2^-64 before rounding, result ~1 ulp): a dependent chain of 3-4
@@ -122,8 +123,16 @@ __device__ __forceinline__ double sqrt_pos(double x) {
 // the fdlibm kernel polynomials on [-pi/4, pi/4].  No Payne-Hanek slow path (keeps the code small
 // enough for the instruction cache); max error ~1 ulp, same as the CUDA fast path.
 __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
+#ifdef PISAB_SINCOS_RINT
     const double kd = rint(x * kTab[0]);
     const int k = (int)kd;
+#else
+    // round-to-nearest by the 1.5 * 2^52 shift (|x * 2/pi| < 2^31 here): the integer is the low word of the
+    // shifted sum, so no FRND / F2I conversions sit on the dependent chain
+    const double shifted = fma(x, kTab[0], kTab[21]);
+    const int k = __double2loint(shifted);
+    const double kd = shifted - kTab[21];
+#endif
     double r = fma(-kd, kTab[1], x);
     r = fma(-kd, kTab[2], r);
     const double z = r * r;
@@ -143,7 +152,7 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
     const double c = fma(z * z, pc, fma(z, -0.5, 1.0));
     const double ss = (k & 1) ? c : s;
     const double cc = (k & 1) ? s : c;
-#if defined(PISAB_HOST_EMU) || defined(PISAB_SIGN_SELECT)
+#ifdef PISAB_SIGN_SELECT
     *sn = (k & 2) ? -ss : ss;
     *cs = ((k + 1) & 2) ? -cc : cc;
 #else

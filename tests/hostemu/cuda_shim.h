@@ -26,6 +26,11 @@ static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x)
 struct double2 { double x, y; };
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #include <cstring>
+static inline int __double2loint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b & 0xffffffffull); }
+static inline int __double2hiint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b >> 32); }
+static inline double __hiloint2double(int hi, int lo) {
+    const uint64_t b = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double v; std::memcpy(&v, &b, 8); return v;
+}
 // the shared-memory state classes index by thread: never instantiated on the host, but they must parse
 struct pisab_emu_dim3 { int x, y, z; };
 static const pisab_emu_dim3 threadIdx = {0, 0, 0}, blockDim = {1, 1, 1}, blockIdx = {0, 0, 0}, gridDim = {1, 1, 1};
