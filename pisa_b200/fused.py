@@ -1,0 +1,107 @@
+"""A ``Pipeline`` evaluated through the fused template kernel.
+
+``Pipeline.run()`` executes ``osc.prob3 -> aeff.aeff -> utils.hist`` as separate stages: per container a propagation
+kernel, two gathers, two multiplies and a histogram pass, with every intermediate (``probability``, ``prob_e``,
+``prob_mu``, reweighted ``weights``) written to HBM, and ~70 Python-level container operations per template
+(2.4 ms per template however small the sample, profiles/r01_pipeline_timings.txt).  ``FusedPipeline`` keeps the
+pipeline object -- its cfg, its ``ParamSet``s, its stages before the oscillation stage (loaders, flux) and after the
+histogram stage (``discr_sys.hypersurfaces``) -- and replaces exactly that segment by ONE launch of
+``pisab_reweight_hist_batch`` over all containers (``ReweightEngine``), writing ``weights`` / ``errors`` /
+``bin_unc2`` into the containers' output-binning representation as ``utils.hist`` would.  ``get_outputs()`` returns the
+same ``MapSet`` as ``Pipeline.get_outputs()`` (tests: 1e-10 relative).
+
+Supported shape (checked at construction, ``NotImplementedError`` otherwise): ``osc.prob3`` in events mode, then
+optionally ``aeff.aeff``, then ``utils.hist`` with ``calc_mode = events`` and ``error_method = sumw2`` or None,
+without ``unc_weights`` / ``astro_weights`` / ``unweighted``; any stages before and after.
+"""
+import numpy as np
+import torch
+
+from pisa_b200.core.binning import MultiDimBinning
+from pisa_b200.engine import ReweightEngine
+
+__all__ = ["FusedPipeline"]
+
+
+def _is(stage, stage_name, service_name):
+    return stage.stage_name == stage_name and stage.service_name == service_name
+
+
+class FusedPipeline:
+    def __init__(self, pipeline):
+        self.pipeline = pipeline
+        stages = pipeline.stages
+        osc = [i for i, s in enumerate(stages) if _is(s, "osc", "prob3")]
+        if len(osc) != 1:
+            raise NotImplementedError("FusedPipeline needs exactly one osc.prob3 stage")
+        k = osc[0]
+        self.pre, self.osc = stages[:k], stages[k]
+        rest = stages[k + 1:]
+        self.aeff = rest.pop(0) if rest and _is(rest[0], "aeff", "aeff") else None
+        if not rest or not _is(rest[0], "utils", "hist"):
+            raise NotImplementedError("FusedPipeline needs utils.hist right after osc.prob3 (and an optional aeff.aeff)")
+        self.hist, self.post = rest[0], rest[1:]
+        if self.osc.calc_mode != "events" or self.osc.apply_mode != "events":
+            raise NotImplementedError("FusedPipeline: osc.prob3 must calculate and apply in events mode")
+        if self.hist.calc_mode != "events" or self.hist.apply_unc_weights or self.hist.unweighted:
+            raise NotImplementedError("FusedPipeline: utils.hist must histogram plain event weights")
+        if self.hist.error_method not in (None, "sumw2"):
+            raise NotImplementedError("FusedPipeline: error_method must be None or sumw2")
+        pipeline.run()                       # set-up of every stage, bin indices, first template the staged way
+        self.binning = self.hist.apply_mode
+        assert isinstance(self.binning, MultiDimBinning)
+        self._engine = None
+        self._pre_hash = None
+
+    # ------------------------------------------------------------------------------------------------
+    def _inputs_hash(self):
+        return tuple(s.params.values_hash for s in self.pre)
+
+    def _build_engine(self, earth):
+        data = self.pipeline.data
+        for stage in self.pre:               # loaders reset `weights`, flux stages write `nu_flux`
+            stage.run()
+        engine = None
+        self._containers = list(data.containers)
+        for c in self._containers:
+            c.representation = "events"
+            if "astro_weights" in c.keys:
+                raise NotImplementedError("FusedPipeline: astro_weights are not supported")
+            w = c["weights"]
+            if self.aeff is not None:
+                w = w * c["weighted_aeff"]   # the per-event part of aeff.aeff; its scalar part goes in as `scale`
+            if engine is None:
+                engine = ReweightEngine(earth, self.binning.size, np.float64 if w.dtype == torch.float64 else np.float32,
+                                        w.device)
+            engine.add_container(c.name, int(c["nubar"]), int(c["flav"]), c["true_energy"], c["true_coszen"],
+                                 c["nu_flux"], w.contiguous(), c.bin_index(self.binning))
+        self._engine = engine
+        self._pre_hash = self._inputs_hash()
+
+    def run(self):
+        consts, earth = self.osc.update_hypothesis()
+        if self._engine is None or self._inputs_hash() != self._pre_hash:
+            self._build_engine(earth)
+        self._engine.earth = earth
+        if self.aeff is not None:
+            self._engine.set_scales([self.aeff.container_scale(c.name) for c in self._containers])
+        out = self._engine.evaluate(consts)                  # [containers, 2, bins], one launch
+        want_w2 = self.hist.error_method == "sumw2"
+        errors = torch.sqrt(out[:, 1]) if want_w2 else None
+        for i, c in enumerate(self._containers):
+            c.representation = self.binning
+            c["weights"] = out[i, 0].clone()
+            if want_w2:
+                c["errors"] = errors[i].clone()
+                c["bin_unc2"] = out[i, 0].clone()            # unc_weights == 1: sum(unc^2 w) == sum(w)
+        for stage in self.post:
+            stage.run()
+
+    def get_outputs(self):
+        self.run()
+        data = self.pipeline.data
+        data.representation = self.binning
+        key = self.pipeline.output_key
+        if isinstance(key, tuple):
+            return data.get_mapset(key[0], error=key[1])
+        return data.get_mapset(key)

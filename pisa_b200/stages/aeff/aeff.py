@@ -13,20 +13,21 @@ class aeff(Stage):  # pylint: disable=invalid-name
         super().__init__(expected_params=("livetime", "aeff_scale", "nutau_cc_norm", "nutau_norm", "nu_nc_norm"),
                          expected_container_keys=("weights", "weighted_aeff"), **std_kwargs)
 
+    def container_scale(self, name):
+        """The scalar part of the weight factor of container `name` (aeff.py:68-88): livetime, overall scale
+        and the flavour / interaction norms."""
+        p = self.params
+        scale = p.aeff_scale.m_as("dimensionless") * p.livetime.m_as("sec")
+        if name in ["nutau_cc", "nutaubar_cc"]:
+            scale *= p.nutau_cc_norm.m_as("dimensionless")
+        if "nutau" in name:
+            scale *= p.nutau_norm.m_as("dimensionless")
+        if "nc" in name:
+            scale *= p.nu_nc_norm.m_as("dimensionless")
+        return scale
+
     def apply_function(self):
-        aeff_scale = self.params.aeff_scale.m_as("dimensionless")
-        livetime_s = self.params.livetime.m_as("sec")
-        nutau_cc_norm = self.params.nutau_cc_norm.m_as("dimensionless")
-        nutau_norm = self.params.nutau_norm.m_as("dimensionless")
-        nu_nc_norm = self.params.nu_nc_norm.m_as("dimensionless")
         for container in self.data:
-            scale = aeff_scale * livetime_s
-            if container.name in ["nutau_cc", "nutaubar_cc"]:
-                scale *= nutau_cc_norm
-            if "nutau" in container.name:
-                scale *= nutau_norm
-            if "nc" in container.name:
-                scale *= nu_nc_norm
             w = container["weights"]
-            w *= container["weighted_aeff"] * scale
+            w *= container["weighted_aeff"] * self.container_scale(container.name)
             container.mark_changed("weights")

@@ -224,7 +224,10 @@ class prob3(Stage):  # pylint: disable=invalid-name
         self._earth = self.layers.earth_struct()
         self._store_layers()
 
-    def compute_function(self):
+    def update_hypothesis(self):
+        """Host part of ``compute_function`` (:463-567): Earth densities for the current electron fractions /
+        tomography scalings and the oscillation matrices.  Returns (OscConsts, Earth struct); also used by
+        ``pisa_b200.fused.FusedPipeline``."""
         YeI = self.params.YeI.value.m_as("dimensionless")
         YeO = self.params.YeO.value.m_as("dimensionless")
         YeM = self.params.YeM.value.m_as("dimensionless")
@@ -235,7 +238,10 @@ class prob3(Stage):  # pylint: disable=invalid-name
             self._store_layers()
         if self.tomography_type is not None:
             self._apply_tomography()
-        consts = self._update_matrices()
+        return self._update_matrices(), self._earth
+
+    def compute_function(self):
+        consts, _ = self.update_hypothesis()
 
         self._link()
         for container in self.data:

@@ -38,8 +38,30 @@ def bench(cfg, n_events=None, reps=10):
     print("%-48s events %9d  first run incl. setup %7.1f ms   run()+get_outputs per template: median %7.2f ms  min %7.2f ms"
           % (cfg.split("/")[-1] + ("" if n_events is None else " n=%g" % n_events), n, 1e3 * t_setup, 1e3 * np.median(ts), 1e3 * min(ts)), flush=True)
 
+def bench_fused(cfg, n_events, reps=20):
+    from pisa_b200.fused import FusedPipeline
+    pipe = Pipeline(cfg)
+    for st in pipe.stages:
+        if "n_events" in st.params.names:
+            st.params.n_events = n_events * ureg.dimensionless
+    pipe.setup()
+    fp = FusedPipeline(pipe)
+    fp.get_outputs(); torch.cuda.synchronize()
+    th, ts = 42.3, []
+    for i in range(reps):
+        th += 0.37
+        pipe.params.theta23 = th * ureg.deg
+        torch.cuda.synchronize(); t1 = time.perf_counter()
+        fp.get_outputs()
+        torch.cuda.synchronize(); ts.append(time.perf_counter() - t1)
+    print("%-48s FusedPipeline.get_outputs per template: median %7.2f ms  min %7.2f ms"
+          % (cfg.split("/")[-1] + " n=%g" % n_events, 1e3 * np.median(ts), 1e3 * min(ts)), flush=True)
+
 bench("settings/pipeline/b200_oscillogram.cfg")
 for n in (20000, 1000000):
     bench("settings/pipeline/b200_events.cfg", n)
     bench("settings/pipeline/b200_icecube3y_like.cfg", n)
     bench("settings/pipeline/b200_icecube3y_events.cfg", n)
+for n in (20000, 1000000):
+    bench_fused("settings/pipeline/b200_events.cfg", n)
+    bench_fused("settings/pipeline/b200_icecube3y_events.cfg", n)

@@ -709,3 +709,51 @@ def test_pipeline_in_fp32_process_mode(tmp_path):
         assert abs(a.sum() / b.sum() - 1) < 1e-4, m.name
         # per bin: float32 rounding of ~150 events per bin plus the odd event changing bins
         assert np.allclose(a, b, rtol=2e-2, atol=2e-3 * b.max()), (m.name, np.abs(a - b).max() / b.max())
+
+
+@pytest.mark.parametrize("cfg", ["settings/pipeline/b200_events.cfg", "settings/pipeline/b200_icecube3y_full.cfg"])
+def test_fused_pipeline_equals_staged_pipeline(cfg):
+    """FusedPipeline replaces osc.prob3 -> aeff.aeff -> utils.hist by one fused launch and must return the MapSet of
+    Pipeline.get_outputs(): maps and sumw2 errors within 1e-10, also after oscillation, aeff, flux and detector
+    systematic parameters change (stages before the oscillation stage and after the histogram stage keep running)."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.fused import FusedPipeline
+    from pisa_b200.utils.units import ureg
+    staged, fused = Pipeline(cfg), FusedPipeline(Pipeline(cfg))
+    assert fused.post == [] or fused.post[-1].service_name == "hypersurfaces"
+
+    def compare():
+        a, b = staged.get_outputs(), fused.get_outputs()
+        assert a.names == b.names
+        for m in a:
+            assert np.allclose(b[m.name].hist, m.hist, rtol=1e-10, atol=0), (m.name, "hist")
+            assert np.allclose(b[m.name].std_devs, m.std_devs, rtol=1e-10, atol=0), (m.name, "errors")
+
+    compare()
+    for p in (staged, fused.pipeline):
+        p.params.theta23 = 47.5 * ureg.deg
+        p.params.deltam31 = 2.6e-3 * ureg.eV ** 2
+        p.params.aeff_scale = 1.07 * ureg.dimensionless
+    compare()
+    names = staged.params.names
+    if "delta_index" in names:                       # flux.barr_simple upstream of the oscillation stage
+        for p in (staged, fused.pipeline):
+            p.params.delta_index = 0.04 * ureg.dimensionless
+            p.params.nue_numu_ratio = 1.03 * ureg.dimensionless
+        compare()
+    if "opt_eff_overall" in names:                   # discr_sys.hypersurfaces downstream of the histogram stage
+        for p in (staged, fused.pipeline):
+            p.params.opt_eff_overall = 1.08 * ureg.dimensionless
+        compare()
+    for p in (staged, fused.pipeline):
+        p.params.theta23 = 42.3 * ureg.deg
+    compare()
+
+
+def test_fused_pipeline_rejects_other_shapes():
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.fused import FusedPipeline
+    with pytest.raises(NotImplementedError):
+        FusedPipeline(Pipeline("settings/pipeline/b200_oscillogram.cfg"))     # grid mode, no histogram stage
