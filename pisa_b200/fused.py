@@ -52,6 +52,7 @@ class FusedPipeline:
         assert isinstance(self.binning, MultiDimBinning)
         self._engine = None
         self._pre_hash = None
+        self._scales = None
 
     # ------------------------------------------------------------------------------------------------
     def _inputs_hash(self):
@@ -78,30 +79,50 @@ class FusedPipeline:
         self._engine = engine
         self._pre_hash = self._inputs_hash()
 
-    def run(self):
+    def _evaluate(self):
         consts, earth = self.osc.update_hypothesis()
         if self._engine is None or self._inputs_hash() != self._pre_hash:
             self._build_engine(earth)
+            self._scales = None
         self._engine.earth = earth
         if self.aeff is not None:
-            self._engine.set_scales([self.aeff.container_scale(c.name) for c in self._containers])
-        out = self._engine.evaluate(consts)                  # [containers, 2, bins], one launch
+            scales = [self.aeff.container_scale(c.name) for c in self._containers]
+            if scales != self._scales:
+                self._engine.set_scales(scales)
+                self._scales = scales
+        return self._engine.evaluate(consts)                 # [containers, 2, bins], one launch
+
+    def run(self):
+        """Like ``Pipeline.run()``: afterwards the containers hold the binned ``weights`` (and ``errors``,
+        ``bin_unc2`` with sumw2 errors) of this hypothesis, stages after the histogram stage included."""
+        out = self._evaluate().clone()                       # the engine reuses its result buffer
         want_w2 = self.hist.error_method == "sumw2"
         errors = torch.sqrt(out[:, 1]) if want_w2 else None
         for i, c in enumerate(self._containers):
             c.representation = self.binning
-            c["weights"] = out[i, 0].clone()
+            c["weights"] = out[i, 0]
             if want_w2:
-                c["errors"] = errors[i].clone()
+                c["errors"] = errors[i]
                 c["bin_unc2"] = out[i, 0].clone()            # unc_weights == 1: sum(unc^2 w) == sum(w)
         for stage in self.post:
             stage.run()
 
     def get_outputs(self):
+        key = self.pipeline.output_key
+        error = key[1] if isinstance(key, tuple) else None
+        name = key[0] if isinstance(key, tuple) else key
+        if not self.post and name == "weights" and error in (None, "errors"):
+            # nothing downstream needs the containers: one device->host copy, maps built directly
+            from pisa_b200.core.map import Map, MapSet
+            from pisa_b200 import FTYPE
+            host = self._evaluate().cpu().numpy()
+            shape = self.binning.shape
+            # (containers store FTYPE arrays: same rounding as the staged path in FP32 mode)
+            maps = [Map(name=c.name, hist=host[i, 0].astype(FTYPE).reshape(shape), binning=self.binning,
+                        error_hist=np.sqrt(host[i, 1]).astype(FTYPE).reshape(shape) if error else None)
+                    for i, c in enumerate(self._containers)]
+            return MapSet(name=self.pipeline.data.name, maps=maps)
         self.run()
         data = self.pipeline.data
         data.representation = self.binning
-        key = self.pipeline.output_key
-        if isinstance(key, tuple):
-            return data.get_mapset(key[0], error=key[1])
-        return data.get_mapset(key)
+        return data.get_mapset(name, error=error) if error else data.get_mapset(name)
