@@ -21,11 +21,12 @@ EVENT_KEYS = ("true_energy", "true_coszen", "nu_flux", "weights", "index")
 
 
 class _Block:
-    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage", "order")
+    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage", "order", "pack_index")
 
     def __init__(self, name, nubar, flav, n):
         self.name, self.nubar, self.flav, self.n = name, int(nubar), int(flav), int(n)
         self.dev, self.host, self.stage, self.order = {}, {}, None, None
+        self.pack_index = False
 
 
 class ReweightEngine:
@@ -71,6 +72,7 @@ class ReweightEngine:
                 blk.dev[k] = t.contiguous()
             else:
                 blk.host[k] = t.contiguous().pin_memory() if not t.is_pinned() else t
+        blk.pack_index = "index" in blk.host and self.n_bins < 255
         if self.sort_events:
             # setup-time, depends on true_coszen only (like calcLayers in prob3.setup_function): the events
             # are physically re-ordered so that a warp's 32 events cross the same number of Earth shells
@@ -83,6 +85,12 @@ class ReweightEngine:
                 order_h = order.cpu()
                 for k in list(blk.host):
                     blk.host[k] = blk.host[k][order_h].contiguous().pin_memory()
+        if blk.pack_index:
+            # host mode: the static bin index (-1 .. n_bins-1) travels as index + 1 in ONE byte per event and is
+            # widened on the device after the copy (41 instead of 44 bytes per event over PCIe)
+            idx = blk.host.pop("index")
+            idx = torch.where((idx >= 0) & (idx < self.n_bins), idx, torch.full_like(idx, -1))   # anything else is "outside"
+            blk.host["index_u8"] = (idx + 1).to(torch.uint8).contiguous().pin_memory()
         if "nu_flux_nominal" in blk.dev:
             # parameter-independent terms of flux.barr_simple, once (after the re-ordering)
             blk.dev["flux_barr_terms"] = ops.flux_barr_terms(blk.dev["true_energy"], blk.dev["true_coszen"])
@@ -200,7 +208,8 @@ class ReweightEngine:
                     true_coszen=torch.empty(nmax, dtype=self.tdtype, device=self.device),
                     nu_flux=torch.empty((nmax, 2), dtype=self.tdtype, device=self.device),
                     weights=torch.empty(nmax, dtype=self.tdtype, device=self.device),
-                    index=torch.empty(nmax, dtype=torch.int32, device=self.device)))
+                    index=torch.empty(nmax, dtype=torch.int32, device=self.device),
+                    index_u8=torch.empty(nmax, dtype=torch.uint8, device=self.device)))
             self._stages = stages
             self._host_batches = {}
             self._stage_free = [torch.cuda.Event(), torch.cuda.Event()]
@@ -215,9 +224,16 @@ class ReweightEngine:
                 self._copy_stream.wait_event(self._stage_free[s])
                 views = {}
                 for k in EVENT_KEYS:
-                    src = blk.host[k]
+                    packed = k == "index" and blk.pack_index
+                    src = blk.host["index_u8" if packed else k]
                     dst = st[k][:blk.n]
-                    dst.copy_(src, non_blocking=True)
+                    if packed:
+                        raw = st["index_u8"][:blk.n]
+                        raw.copy_(src, non_blocking=True)
+                        dst.copy_(raw)          # uint8 -> int32 on the device
+                        dst.sub_(1)
+                    else:
+                        dst.copy_(src, non_blocking=True)
                     views[k] = dst
                     h2d += src.numel() * src.element_size()
                 self._stage_ready[s].record(self._copy_stream)

@@ -250,7 +250,8 @@ def test_engine_host_mode_equals_resident_mode():
     ru = u.evaluate(consts).cpu().numpy()
     assert np.allclose(ra, rb, rtol=1e-12, atol=0)     # per-container launches: other block split -> rounding only
     assert np.allclose(ra, ru, rtol=1e-12, atol=0)     # different thread order -> rounding only
-    assert b.last_h2d_bytes == sum(blk.n for blk in b.blocks) * 44 and b.last_d2h_bytes == 5 * 2 * 128 * 8
+    # 40 B of event data + the bin index as one byte (128 bins < 255)
+    assert b.last_h2d_bytes == sum(blk.n for blk in b.blocks) * 41 and b.last_d2h_bytes == 5 * 2 * 128 * 8
     assert shard_slice(10, 0, 3) == (0, 4) and shard_slice(10, 2, 3) == (7, 10)
 
 
