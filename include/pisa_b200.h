@@ -188,9 +188,10 @@ int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nomi
  * d_nu_flux_nominal[n,2] = (nue, numu), d_nubar_flux_nominal[n,2] = (nuebar, numubar).
  * Tables (all double, built on the host by pisa_b200.utils.flux_weights.HondaTable2D from the reference's own
  * splrep coefficients): d_knots[n_knots] the common knot vector of the 80 energy splines; d_cz_breaks[n_pieces]
- * the break points of the per-event coszen spline fit; d_cells[n_knots-7][n_pieces][4][3][3] the biquadratic
+ * the break points of the per-event coszen spline fit; d_cells[n_knots-7][n_pieces][3][3][4] the biquadratic
  * sum_ab K[a][b] s^a u^b (s = log10 E - knot, u = coszen - break) that the reference's two-step evaluation
- * reduces to on each (energy interval, coszen piece) cell, primaries in output order.  16-byte aligned.
+ * reduces to on each (energy interval, coszen piece) cell, index order [a][b][primary], primaries in output
+ * order.  16-byte aligned.
  * A "next" row of the scope table. */
 int pisab_flux_honda_2d_f64(const double *d_knots, int32_t n_knots, const double *d_cz_breaks, int32_t n_pieces,
                             const double *d_cells, int32_t enpow, const double *d_energy, const double *d_coszen,

@@ -300,7 +300,7 @@ namespace pisab {
 constexpr int kHondaMaxKnots = 256, kHondaMaxPieces = 64;
 
 template <typename IO>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 flux_honda_2d_kernel(const double *__restrict__ knots, int n_knots, const double *__restrict__ cz_breaks,
                      int n_pieces, const double *__restrict__ cells, int enpow, const IO *__restrict__ energy,
                      const IO *__restrict__ coszen, int64_t n, IO *__restrict__ nu_out, IO *__restrict__ nubar_out) {
@@ -328,26 +328,30 @@ flux_honda_2d_kernel(const double *__restrict__ knots, int n_knots, const double
         while (p > 0 && cz < s_breaks[p]) --p;
         while (p + 1 < n_pieces && cz >= s_breaks[p + 1]) ++p;
         const double u = cz - s_breaks[p];
+        // cell layout [a][b][primary]: one 32-byte group holds the coefficient of s^a u^b for the four primaries, so
+        // the Horner scheme in u (inner) and s (outer) runs on four accumulators with 9 x 2 128-bit loads and no
+        // 36-entry register array (64 registers -> 4 blocks of 256 threads per SM keep the L2 gathers in flight)
         const double2 *K = reinterpret_cast<const double2 *>(cells + ((size_t)(l - 4) * n_pieces + p) * 36);
-        double k[36];
-#pragma unroll
-        for (int q = 0; q < 18; ++q) {
-            const double2 v = __ldg(K + q);
-            k[2 * q] = v.x;
-            k[2 * q + 1] = v.y;
-        }
         double scale = 1.0;
         for (int j = 0; j < enpow; ++j) scale *= e;
         const double inv_scale = 1.0 / scale;
-        double out[4];
+        double out[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int prim = 0; prim < 4; ++prim) {
-            const double *c = k + prim * 9; // [a][b]
-            const double r0 = fma(fma(c[2], u, c[1]), u, c[0]);
-            const double r1 = fma(fma(c[5], u, c[4]), u, c[3]);
-            const double r2 = fma(fma(c[8], u, c[7]), u, c[6]);
-            out[prim] = fma(fma(r2, s, r1), s, r0) * inv_scale;
+        for (int a = 2; a >= 0; --a) {
+            double r[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int b = 2; b >= 0; --b) {
+                const double2 lo2 = __ldg(K + (a * 3 + b) * 2), hi2 = __ldg(K + (a * 3 + b) * 2 + 1);
+                r[0] = fma(r[0], u, lo2.x);
+                r[1] = fma(r[1], u, lo2.y);
+                r[2] = fma(r[2], u, hi2.x);
+                r[3] = fma(r[3], u, hi2.y);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = fma(out[q], s, r[q]);
         }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[q] *= inv_scale;
         if (sizeof(IO) == 8) {
             reinterpret_cast<double2 *>(nu_out)[i] = make_double2(out[0], out[1]);
             reinterpret_cast<double2 *>(nubar_out)[i] = make_double2(out[2], out[3]);

@@ -174,6 +174,8 @@ class HondaTable2D:
         import torch
         key = str(device)
         if key not in self._dev:
+            # device layout of the cells: [interval][piece][a][b][primary] (one 32-byte group per monomial)
+            cells_dev = np.ascontiguousarray(np.transpose(self.cells, (0, 1, 3, 4, 2)))
             self._dev[key] = tuple(torch.tensor(a, dtype=torch.float64, device=device)
-                                   for a in (self.knots, self.cz_breaks, self.cells))
+                                   for a in (self.knots, self.cz_breaks, cells_dev))
         return self._dev[key]
