@@ -19,7 +19,13 @@ import os
 import torch
 import torch.distributed as dist
 
-__all__ = ["init_from_env", "world", "shard_slice", "shard_arrays", "combine_histograms"]
+__all__ = ["init_from_env", "world", "shard_slice", "shard_arrays", "combine_histograms", "enable_event_sharding",
+           "event_sharding", "local_slice"]
+
+# Stage API: with sharding on, the event-mode loaders keep only this rank's slice of every container and
+# ``utils.hist`` (or the fused engine) exchanges the binned results once per template.  Off by default, so that a
+# process group initialised for another purpose does not change what a Pipeline computes.
+_SHARD_EVENTS = os.environ.get("PISAB_SHARD_EVENTS", "0").strip().lower() not in ("", "0", "false", "no")
 
 
 def init_from_env(backend=None, device=None):
@@ -43,6 +49,26 @@ def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def enable_event_sharding(on=True):
+    """Switch the sharding of events over the ranks of the process group on or off (also: PISAB_SHARD_EVENTS=1)."""
+    global _SHARD_EVENTS
+    _SHARD_EVENTS = bool(on)
+
+
+def event_sharding():
+    """True when events are sharded: switched on AND more than one rank."""
+    return _SHARD_EVENTS and world()[1] > 1
+
+
+def local_slice(n):
+    """``slice`` of the n events of a container that this rank keeps (all of them without sharding)."""
+    if not event_sharding():
+        return slice(0, int(n))
+    rank, world_size = world()
+    start, stop = shard_slice(n, rank, world_size)
+    return slice(start, stop)
 
 
 def shard_slice(n, rank, world_size):

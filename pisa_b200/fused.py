@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from pisa_b200.core.binning import MultiDimBinning
+from pisa_b200.distributed import event_sharding
 from pisa_b200.engine import ReweightEngine
 
 __all__ = ["FusedPipeline"]
@@ -90,7 +91,8 @@ class FusedPipeline:
             if scales != self._scales:
                 self._engine.set_scales(scales)
                 self._scales = scales
-        return self._engine.evaluate(consts)                 # [containers, 2, bins], one launch
+        # [containers, 2, bins], one launch; one exchange when the loaders sharded the events over GPUs
+        return self._engine.evaluate(consts, allreduce=event_sharding())
 
     def run(self):
         """Like ``Pipeline.run()``: afterwards the containers hold the binned ``weights`` (and ``errors``,

@@ -17,6 +17,7 @@ import numpy as np
 from pisa_b200 import FTYPE
 from pisa_b200.core.container import Container
 from pisa_b200.core.stage import Stage
+from pisa_b200.distributed import local_slice
 from pisa_b200.utils.resources import find_resource
 
 __all__ = ["csv_loader", "select_events", "init_test"]
@@ -89,6 +90,7 @@ class csv_loader(Stage):  # pylint: disable=invalid-name
                 container.set_aux_data("nubar", nubar)
                 container.set_aux_data("flav", flav)
             events = select_events(raw_data, name, self.neutrinos)
+            events = events.iloc[local_slice(len(events))]      # this rank's share when events are sharded over GPUs
             container["initial_weights"] = np.ones(len(events), dtype=FTYPE)
             container["weights"] = np.ones(len(events), dtype=FTYPE)
             for key, val in self.data_dict.items():

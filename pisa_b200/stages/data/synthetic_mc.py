@@ -11,6 +11,7 @@ Events are generated on the device.  ``apply_function`` resets the weights like 
 from pisa_b200 import FTYPE
 from pisa_b200.core.container import Container, default_device
 from pisa_b200.core.stage import Stage
+from pisa_b200.distributed import local_slice
 from pisa_b200.utils import synthetic as syn
 
 __all__ = ["synthetic_mc"]
@@ -31,14 +32,20 @@ class synthetic_mc(Stage):  # pylint: disable=invalid-name
             nubar = -1 if "bar" in name else 1
             flav = 2 if "tau" in name else (1 if "mu" in name else 0)
             ev = syn.make_events_torch(n_events, seed + i, FTYPE, dev)
+            keep = local_slice(n_events)                         # this rank's share when events are sharded over GPUs
+            if keep != slice(0, n_events):
+                ev = {k: v[keep].contiguous() for k, v in ev.items()}
+                n_events_local = keep.stop - keep.start
+            else:
+                n_events_local = n_events
             for key in ("true_energy", "true_coszen", "reco_energy", "reco_coszen", "pid", "nu_flux"):
                 container[key] = ev[key]
             # nominal fluxes as flux.honda_ip would provide them (nu and nubar tables differ by ~20 %)
             container["nu_flux_nominal"] = ev["nu_flux"]
             container["nubar_flux_nominal"] = (ev["nu_flux"] * 0.8).contiguous()
             container["weighted_aeff"] = ev["weights"]
-            container["initial_weights"] = ev["weights"].new_ones(n_events)
-            container["weights"] = ev["weights"].new_ones(n_events)
+            container["initial_weights"] = ev["weights"].new_ones(n_events_local)
+            container["weights"] = ev["weights"].new_ones(n_events_local)
             container.set_aux_data("nubar", nubar)
             container.set_aux_data("flav", flav)
             self.data.add_container(container)

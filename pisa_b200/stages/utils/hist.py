@@ -18,6 +18,7 @@ import torch
 from pisa_b200 import ops
 from pisa_b200.core.binning import MultiDimBinning
 from pisa_b200.core.stage import Stage
+from pisa_b200.distributed import combine_histograms, event_sharding
 
 __all__ = ["hist", "init_test"]
 
@@ -58,6 +59,7 @@ class hist(Stage):  # pylint: disable=invalid-name
         """calc_mode binned: hist = (unc * w) @ hist_transform (hist.py:131-160)."""
         if self.unweighted:
             raise NotImplementedError("Unweighted hist only implemented in event-wise calculation")
+        local = []
         for container in self.data:
             container.representation = self.calc_mode
             weights = container["weights"]
@@ -66,11 +68,32 @@ class hist(Stage):  # pylint: disable=invalid-name
             unc = container["unc_weights"] if self.apply_unc_weights else torch.ones_like(weights)
             transform = container["hist_transform"]
             h = (unc * weights) @ transform
+            sumw2 = bin_unc2 = None
             if self.error_method == "sumw2":
                 sumw2 = torch.square(unc * weights) @ transform
                 bin_unc2 = (torch.square(unc) * weights) @ transform
+            local.append((container, h, sumw2, bin_unc2))
+        self._write(self._exchange(local), revalidate_events=False)
+
+    def _exchange(self, local):
+        """Events sharded over GPUs (pisa_b200.distributed.enable_event_sharding): the single exchange of the path --
+        all containers' (sum w, sum w^2, bin_unc2) in ONE buffer, rank-ordered sum, identical on every rank."""
+        if not event_sharding() or not local:
+            return local
+        zeros = torch.zeros_like(local[0][1])
+        buf = torch.stack([torch.stack([h, zeros if s is None else s, zeros if b is None else b])
+                           for _, h, s, b in local]).to(torch.float64)
+        combine_histograms(buf)
+        return [(c, buf[i, 0], None if s is None else buf[i, 1], None if b is None else buf[i, 2])
+                for i, (c, _, s, b) in enumerate(local)]
+
+    def _write(self, results, revalidate_events):
+        for container, h, sumw2, bin_unc2 in results:
             container.representation = self.apply_mode
             container["weights"] = h
+            if revalidate_events:
+                # histogramming does not invalidate the "events" representation (hist.py:213)
+                container.validity["weights"][hash("events")] = True
             if self.error_method == "sumw2":
                 container["errors"] = torch.sqrt(sumw2)
                 container["bin_unc2"] = bin_unc2
@@ -79,6 +102,7 @@ class hist(Stage):  # pylint: disable=invalid-name
         if isinstance(self.calc_mode, MultiDimBinning):
             return self._apply_transform()
         n_bins = self.apply_mode.size
+        local = []
         for container in self.data:
             container.representation = "events"
             idx = container.bin_index(self.apply_mode)
@@ -97,14 +121,8 @@ class hist(Stage):  # pylint: disable=invalid-name
             h, h2 = ops.hist_accumulate(idx, weights, n_bins, want_w2=want_w2)
             if want_w2 and bin_unc2 is None:
                 bin_unc2 = h   # unc_weights == 1: sum(unc^2 * w) == sum(w)
-
-            container.representation = self.apply_mode
-            container["weights"] = h
-            # histogramming does not invalidate the "events" representation (hist.py:213)
-            container.validity["weights"][hash("events")] = True
-            if want_w2:
-                container["errors"] = torch.sqrt(h2)
-                container["bin_unc2"] = bin_unc2
+            local.append((container, h, h2, bin_unc2))
+        self._write(self._exchange(local), revalidate_events=True)
 
 
 def init_test(**param_kwargs):

@@ -112,3 +112,15 @@ def test_two_rank_gloo_sharded_template_equals_unsharded(tmp_path):
     whole = _oracle_template(_containers(501))
     assert whole[:, 0].sum() > 0
     np.testing.assert_allclose(r0["det"], whole, rtol=1e-12, atol=1e-300)
+
+
+def test_event_sharding_switch_and_local_slice():
+    """Stage-API sharding is opt-in: without a process group (or switched off) every rank keeps all events."""
+    from pisa_b200 import distributed as D
+    D.enable_event_sharding(True)
+    try:
+        assert not D.event_sharding()                     # one rank: nothing to shard
+        assert D.local_slice(10) == slice(0, 10)
+    finally:
+        D.enable_event_sharding(False)
+    assert D.local_slice(7) == slice(0, 7)
