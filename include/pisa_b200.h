@@ -262,7 +262,9 @@ int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_
  * aeff.aeff multiplies into the weights (livetime * aeff_scale * norms, pisa/stages/aeff/aeff.py:68-88):
  *   w = weights[i] * (nu_flux[i,0]*prob_e + nu_flux[i,1]*prob_mu) * scale
  * d_hist: [n_containers][2][n_bins] (sum w, sum w^2), overwritten.  The descriptor array is a HOST
- * array; all pointers inside are device pointers of the storage type of the entry point. */
+ * array; all pointers inside are device pointers of the storage type of the entry point.
+ * Summation order is fixed by (container sizes, n_containers, device): bit-reproducible run to run; the same
+ * container evaluated inside a different batch is split over blocks differently and may differ in the last bits. */
 #define PISAB_MAX_BATCH 16
 typedef struct pisab_container {
     const void *d_energy, *d_coszen, *d_nu_flux, *d_weights;
