@@ -302,3 +302,33 @@ def test_import_alias_serves_pisa_names_from_this_package():
     finally:
         compat.uninstall()
     assert not [m for m in sys.modules if m == "pisa" or m.startswith("pisa.")]
+
+
+def test_fused_pipeline_shape_checks_without_a_gpu():
+    """FusedPipeline only accepts osc.prob3 (events) -> [aeff.aeff] -> utils.hist (events, plain weights): anything
+    else is refused before any device work (structure checks run on stage metadata only)."""
+    from types import SimpleNamespace as NS
+    from pisa_b200.fused import FusedPipeline
+
+    def stage(stage_name, service_name, **kw):
+        return NS(stage_name=stage_name, service_name=service_name, **kw)
+
+    def pipe(*stages):
+        return NS(stages=list(stages), run=lambda: (_ for _ in ()).throw(AssertionError("must not run")))
+
+    osc = stage("osc", "prob3", calc_mode="events", apply_mode="events")
+    hist_ok = dict(calc_mode="events", apply_unc_weights=False, unweighted=False, error_method="sumw2")
+    cases = [
+        pipe(stage("data", "csv_loader"), stage("utils", "hist", **hist_ok)),                      # no oscillation stage
+        pipe(osc, osc, stage("utils", "hist", **hist_ok)),                                         # two of them
+        pipe(osc, stage("aeff", "aeff")),                                                          # no histogram stage
+        pipe(osc, stage("flux", "barr_simple"), stage("utils", "hist", **hist_ok)),                # something in between
+        pipe(stage("osc", "prob3", calc_mode="grid", apply_mode="events"), stage("utils", "hist", **hist_ok)),
+        pipe(osc, stage("utils", "hist", **dict(hist_ok, apply_unc_weights=True))),
+        pipe(osc, stage("utils", "hist", **dict(hist_ok, unweighted=True))),
+        pipe(osc, stage("utils", "hist", **dict(hist_ok, calc_mode="binned"))),
+        pipe(osc, stage("aeff", "aeff"), stage("utils", "hist", **dict(hist_ok, error_method="fluctuate"))),
+    ]
+    for p in cases:
+        with pytest.raises(NotImplementedError):
+            FusedPipeline(p)
