@@ -7,72 +7,67 @@ The framework calls ``setup()`` once (representation = ``calc_mode``), then per 
 ``apply()`` (representation = ``apply_mode``).  ``params`` must contain exactly ``expected_params``
 (:270-298).  Stage / service names come from the module path ``...<stage>.<service>`` (:103-109).
 """
+import time
 from collections.abc import Mapping, Sequence
-from time import time
 
 from pisa_b200.core.binning import MultiDimBinning
 from pisa_b200.core.container import Container, ContainerSet
-from pisa_b200.core.param import ParamSelector, ParamSet
+from pisa_b200.core.param import ParamSelector
 
 __all__ = ["Stage"]
 
+_MODES = ("calc_mode", "apply_mode")
+_SELECTOR_KWARGS = frozenset(("regular_params", "selector_param_sets", "selections"))
+_HOOKS = ("setup_function", "compute_function", "apply_function")
 
-def _str_seq(inputs, name):
-    if inputs is None:
+
+def _names(value, what):
+    """None, one name or a sequence of names -> list of names (or None)."""
+    if value is None:
         return None
-    if isinstance(inputs, str):
-        return [inputs]
-    if not isinstance(inputs, Sequence) or not all(isinstance(i, str) for i in inputs):
-        raise TypeError("`%s` must be a string or a sequence of strings" % name)
-    return list(inputs)
+    if isinstance(value, str):
+        return [value]
+    if isinstance(value, Sequence) and all(isinstance(v, str) for v in value):
+        return list(value)
+    raise TypeError("`%s` must be a string or a sequence of strings" % what)
+
+
+def _selector_from(params):
+    """The three ways a service may be handed its parameters (:111-124)."""
+    if isinstance(params, ParamSelector):
+        return params
+    if isinstance(params, Mapping) and _SELECTOR_KWARGS == set(params):
+        return ParamSelector(**params)
+    return ParamSelector(regular_params=params)
 
 
 class Stage:
     def __init__(self, data=None, params=None, expected_params=None, expected_container_keys=None,
                  debug_mode=None, error_method=None, supported_reps=None, calc_mode=None, apply_mode=None,
                  profile=False, in_standalone_mode=False):
-        expected_params = _str_seq(expected_params, "expected_params")
-        expected_container_keys = _str_seq(expected_container_keys, "expected_container_keys")
-        module_path = self.__module__.split(".")
-        self.stage_name = module_path[-2] if len(module_path) > 1 else module_path[-1]
-        self.service_name = module_path[-1]
-        self.expected_params = expected_params
-        self.expected_container_keys = expected_container_keys
+        # `....<stage>.<service>` -> names
+        *parents, service = self.__module__.split(".")
+        self.stage_name, self.service_name = (parents[-1] if parents else service), service
 
-        selector_keys = {"regular_params", "selector_param_sets", "selections"}
-        if isinstance(params, Mapping) and set(params.keys()) == selector_keys:
-            self._param_selector = ParamSelector(**params)
-        elif isinstance(params, ParamSelector):
-            self._param_selector = params
-        else:
-            self._param_selector = ParamSelector(regular_params=params)
-        p = self._param_selector.params
-        self._check_params(p, getattr(p, "has_derived", False))
-        self.validate_params(p)
-        self._params = p
+        self.expected_params = _names(expected_params, "expected_params")
+        self.expected_container_keys = _names(expected_container_keys, "expected_container_keys")
+        self._param_selector = _selector_from(params)
+        current = self._param_selector.params
+        self._check_params(current, ignore_excess=getattr(current, "has_derived", False))
+        self.validate_params(current)
+        self._params = current
 
-        self._debug_mode = debug_mode if bool(debug_mode) else None
-        self.has_setup = type(self).setup_function is not Stage.setup_function
-        self.has_compute = type(self).compute_function is not Stage.compute_function
-        self.has_apply = type(self).apply_function is not Stage.apply_function
-
-        supported_reps = dict(supported_reps or {})
-        assert set(supported_reps.keys()).issubset(("calc_mode", "apply_mode"))
-        for mode_str in ("calc_mode", "apply_mode"):
-            allowed = (self.has_setup or self.has_compute) if mode_str == "calc_mode" else self.has_apply
-            if mode_str not in supported_reps:
-                supported_reps[mode_str] = (list(Container.array_representations) + [MultiDimBinning]
-                                            if allowed else [None])
-            elif isinstance(supported_reps[mode_str], str) or not isinstance(supported_reps[mode_str], Sequence):
-                supported_reps[mode_str] = [supported_reps[mode_str]]
-        self.supported_reps = supported_reps
-
-        self._check_representation(calc_mode, "calc_mode", always_allow_none=True)
-        self._calc_mode = calc_mode
-        self._check_representation(apply_mode, "apply_mode", always_allow_none=True)
-        self._apply_mode = apply_mode
+        self._debug_mode = debug_mode or None
         self._error_method = error_method
-        self.param_hash = None
+        # which hooks the service overrides decides which modes it can be given at all
+        self.has_setup, self.has_compute, self.has_apply = (
+            getattr(type(self), hook) is not getattr(Stage, hook) for hook in _HOOKS)
+        self.supported_reps = self._normalised_reps(supported_reps)
+        for mode, value in zip(_MODES, (calc_mode, apply_mode)):
+            self._check_representation(value, mode, always_allow_none=True)
+        self._calc_mode, self._apply_mode = calc_mode, apply_mode
+
+        self.param_hash = None                       # None: never set up; -1: set up, nothing computed yet
         self.profile = profile
         self.setup_times, self.calc_times, self.apply_times = [], [], []
         self.in_standalone_mode = in_standalone_mode
@@ -80,28 +75,38 @@ class Stage:
         self.data = data
 
     def __repr__(self):
-        return 'Stage "%s"' % self.__class__.__name__
+        return 'Stage "%s"' % type(self).__name__
+
+    def _normalised_reps(self, supported_reps):
+        """{"calc_mode": [...], "apply_mode": [...]}: defaults are every array representation plus binnings for a
+        mode whose hooks the service implements, and only ``None`` otherwise (:150-171)."""
+        reps = dict(supported_reps or {})
+        unknown = set(reps) - set(_MODES)
+        assert not unknown, "unknown keys in supported_reps: %s" % sorted(unknown)
+        used = {"calc_mode": self.has_setup or self.has_compute, "apply_mode": self.has_apply}
+        for mode in _MODES:
+            if mode not in reps:
+                reps[mode] = [*Container.array_representations, MultiDimBinning] if used[mode] else [None]
+            elif isinstance(reps[mode], str) or not isinstance(reps[mode], Sequence):
+                reps[mode] = [reps[mode]]
+        return reps
 
     # ------------------------------------------------------------------------ params -----
     def _check_params(self, params, ignore_excess=False):
+        """``params`` must hold exactly ``expected_params`` (:270-298)."""
         assert self.expected_params is not None
-        exp_p, got_p = set(self.expected_params), set(params.names)
-        if exp_p == got_p:
-            return
-        excess, missing = got_p - exp_p, exp_p - got_p
-        errs = []
+        wanted, given = set(self.expected_params), set(params.names)
+        missing, excess = sorted(wanted - given), sorted(given - wanted)
+        problems = []
         if missing:
-            errs.append("Missing params: %s" % ", ".join(sorted(missing)))
-        if excess:
-            if ignore_excess:
-                if not errs:
-                    return
-            else:
-                errs.append("Excess params provided: %s" % ", ".join(sorted(excess)))
-        raise ValueError("Expected parameters: %s;\n" % ", ".join(sorted(exp_p)) + ";\n".join(errs))
+            problems.append("Missing params: %s" % ", ".join(missing))
+        if excess and not ignore_excess:
+            problems.append("Excess params provided: %s" % ", ".join(excess))
+        if problems:
+            raise ValueError("Expected parameters: %s;\n%s" % (", ".join(sorted(wanted)), ";\n".join(problems)))
 
     def validate_params(self, params):
-        return
+        """Hook for services with constraints between parameters."""
 
     params = property(lambda self: self._params)
     param_selections = property(lambda self: sorted(self._param_selector.param_selections))
@@ -116,103 +121,90 @@ class Stage:
                 raise
 
     # ------------------------------------------------------------------------- modes -----
-    @property
-    def calc_mode(self):
-        return self._calc_mode
+    def _set_mode(self, mode, value):
+        if value == getattr(self, "_" + mode):
+            return False
+        self._check_representation(value, mode)
+        setattr(self, "_" + mode, value)
+        return True
 
-    @calc_mode.setter
-    def calc_mode(self, value):
-        if value != self._calc_mode:
-            self._check_representation(value, "calc_mode")
-            self._calc_mode = value
-            if self.in_standalone_mode and self.param_hash is not None:
-                self.setup()
+    def _set_calc_mode(self, value):
+        # a stand-alone stage that was already set up re-runs its setup in the new representation (:334-339)
+        if self._set_mode("calc_mode", value) and self.in_standalone_mode and self.param_hash is not None:
+            self.setup()
 
-    @property
-    def apply_mode(self):
-        return self._apply_mode
-
-    @apply_mode.setter
-    def apply_mode(self, value):
-        if value != self._apply_mode:
-            self._check_representation(value, "apply_mode")
-            self._apply_mode = value
+    calc_mode = property(lambda self: self._calc_mode, _set_calc_mode)
+    apply_mode = property(lambda self: self._apply_mode, lambda self, value: self._set_mode("apply_mode", value))
 
     @property
     def data(self):
         return self._data
 
     @data.setter
-    def data(self, value):
-        self._data = value
+    def data(self, container_set):
+        self._data = container_set
 
     def _check_representation(self, rep, mode, always_allow_none=False):
-        where = "%s.%s" % (self.stage_name, self.service_name)
+        allowed = self.supported_reps[mode]
         if rep is None:
-            if None not in self.supported_reps[mode] and not always_allow_none:
-                raise ValueError("%s='%s' is not supported by %s" % (mode, rep, where))
+            ok, shown = always_allow_none or None in allowed, "%s='%s'" % (mode, rep)
         elif isinstance(rep, str):
-            if rep not in self.supported_reps[mode]:
-                raise ValueError("%s='%s' is not supported by %s" % (mode, rep, where))
-        elif type(rep) not in self.supported_reps[mode]:
-            raise ValueError("%s of type %s is not supported by %s" % (mode, type(rep), where))
+            ok, shown = rep in allowed, "%s='%s'" % (mode, rep)
+        else:
+            ok, shown = type(rep) in allowed, "%s of type %s" % (mode, type(rep))
+        if not ok:
+            raise ValueError("%s is not supported by %s.%s" % (shown, self.stage_name, self.service_name))
 
-    @property
-    def is_map(self):
-        return self.data.is_map
+    is_map = property(lambda self: self.data.is_map)
 
     # --------------------------------------------------------------------- execution -----
-    def _timed(self, fn, times):
-        if self.profile:
-            t0 = time()
-            fn()
-            times.append(time() - t0)
-        else:
-            fn()
+    def _call(self, hook, mode, log):
+        """Run one hook with the containers in the representation of `mode`, timed when profiling."""
+        representation = getattr(self, mode)
+        self._check_representation(representation, mode)
+        if representation is not None:
+            self.data.representation = representation
+        if not self.profile:
+            hook()
+            return
+        start = time.time()
+        hook()
+        log.append(time.time() - start)
 
     def setup(self):
         if self.data is not None and not isinstance(self.data, ContainerSet):
             raise TypeError("`data` must be a `pisa_b200.core.container.ContainerSet`")
-        self._check_representation(self.calc_mode, "calc_mode")
-        if self.calc_mode is not None:
-            self.data.representation = self.calc_mode
-        self._timed(self.setup_function, self.setup_times)
+        self._call(self.setup_function, "calc_mode", self.setup_times)
         self.param_hash = -1
 
     def compute(self):
-        new_hash = self.params.values_hash
-        if new_hash == self.param_hash:
+        values_hash = self.params.values_hash
+        if values_hash == self.param_hash:       # the one cache of the framework (:538-542)
             return
-        self._check_representation(self.calc_mode, "calc_mode")
-        if self.calc_mode is not None:
-            self.data.representation = self.calc_mode
-        self._timed(self.compute_function, self.calc_times)
-        self.param_hash = new_hash
+        self._call(self.compute_function, "calc_mode", self.calc_times)
+        self.param_hash = values_hash
 
     def apply(self):
-        self._check_representation(self.apply_mode, "apply_mode")
-        if self.apply_mode is not None:
-            self.data.representation = self.apply_mode
-        self._timed(self.apply_function, self.apply_times)
+        self._call(self.apply_function, "apply_mode", self.apply_times)
 
     def run(self):
         self.compute()
         self.apply()
 
     def setup_function(self):
-        """Implement in services (subclasses of Stage)"""
+        """Overridden by services: one-time work (representation = calc_mode)."""
 
     def compute_function(self):
-        """Implement in services (subclasses of Stage)"""
+        """Overridden by services: work that depends on the parameters only (representation = calc_mode)."""
 
     def apply_function(self):
-        """Implement in services (subclasses of Stage)"""
+        """Overridden by services: per-template work (representation = apply_mode)."""
 
     def report_profile(self, detailed=False):
         print(self.stage_name, self.service_name)
-        for label, times in (("- setup:   ", self.setup_times), ("- compute: ", self.calc_times),
-                             ("- apply:   ", self.apply_times)):
-            if times:
-                print(label, "total %.5f s, n calls: %d, mean %.5f s" % (sum(times), len(times), sum(times) / len(times)))
+        for label, log in (("- setup:   ", self.setup_times), ("- compute: ", self.calc_times),
+                           ("- apply:   ", self.apply_times)):
+            if log:
+                print(label, "total %.5f s, n calls: %d, mean %.5f s" % (sum(log), len(log), sum(log) / len(log)))
             else:
                 print(label, "0 calls")
