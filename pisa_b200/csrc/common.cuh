@@ -1,8 +1,6 @@
 // common.cuh -- error handling, launch bookkeeping and device tables shared by the kernels.
 #pragma once
-#ifdef PISAB_HOST_EMU
-#include "../../tests/hostemu/cuda_shim.h" // test infrastructure only: the device math compiled by g++ (tests/hostemu/)
-#else
+#ifndef PISAB_HOST_EMU // (defined only by tests/hostemu, which pre-includes its own shim to let g++ parse the device math)
 #include <cuda_runtime.h>
 #endif
 #include <stdint.h>
