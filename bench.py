@@ -53,6 +53,8 @@ def parse_args():
     p.add_argument("--events-per-gpu", type=float, default=1e8)
     p.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     p.add_argument("--nsi", action="store_true", help="standard-NSI matter potential (config C4)")
+    p.add_argument("--f32-math", default="mixed", choices=["mixed", "fp64"],
+                   help="arithmetic behind --dtype f32: mixed precision (the FP32 mode) or FP64 on float32 storage")
     p.add_argument("--no-e2e", action="store_true")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -261,6 +263,7 @@ def run_native(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     dtype = np.float64 if args.dtype == "f64" else np.float32
+    ops.set_f32_math(args.f32_math)
     n_gpu = int(args.events_per_gpu) // 12 * 12
 
     L = Layers(os.path.join(ROOT, "pisa_b200", "resources", syn.EARTH["earth_model"]),

@@ -84,6 +84,17 @@ typedef struct pisab_binning {
 /* ---- library ------------------------------------------------------------------------ */
 const char *pisab_last_error(void);
 const char *pisab_version(void);
+/* Arithmetic behind the *_f32 propagation entry points (the reference's FP32 mode, PISA_FTYPE=fp32,
+ * pisa/__init__.py:152-179, computes everything in float32 / complex64):
+ *   PISAB_F32_MATH_MIXED (default)  eigenvalues of the layer Hamiltonians, the phase arguments and the shell geometry
+ *                                   in FP64; sin / cos polynomials, divided-difference coefficients, transition
+ *                                   matrices, matrix-vector products and the propagation state in float32
+ *                                   (csrc/prob3_mp.cuh).  <= 1e-5 absolute on probabilities vs the FP64 result.
+ *   PISAB_F32_MATH_FP64             float32 storage only, all arithmetic in FP64 (round-1 behaviour).
+ * Process-wide; the *_f64 entry points are not affected. */
+enum { PISAB_F32_MATH_FP64 = 0, PISAB_F32_MATH_MIXED = 1 };
+int pisab_set_f32_math(int32_t mode);
+int pisab_get_f32_math(void);
 /* sm count / compute capability of the current device; fails without a CUDA device. */
 int pisab_device_info(int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
 

@@ -15,6 +15,7 @@ MAX_LAYERS = 120
 MAX_DIMS = 4
 DET_MAX_BINS = 1024
 DIM_LIN, DIM_LOG, DIM_EDGES = 0, 1, 2
+F32_MATH_FP64, F32_MATH_MIXED = 0, 1
 
 c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -114,6 +115,8 @@ _UNTYPED = {
     "pisab_fp64_peak_probe": (c_i32, [c_i32, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),
     "pisab_launch_count": (c_i64, [c_i32]),
     "pisab_set_profiling": (c_i32, [c_i32]),
+    "pisab_set_f32_math": (c_i32, [c_i32]),
+    "pisab_get_f32_math": (c_i32, []),
     "pisab_last_kernel_ms": (c_dbl, []),
 }
 _NO_SUFFIX = ("pisab_last_error", "pisab_version", "pisab_device_info")

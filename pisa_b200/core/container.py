@@ -46,13 +46,21 @@ def default_device():
     return dev
 
 
-def regularized_dims(binning):
-    """Per-dimension description of a binning for ops.make_binning (hist.py:86-127 logic):
-    irregular -> explicit edges (searchsorted), log -> linear bins in log(x), else linear."""
+def regularized_dims(binning, policy="hist"):
+    """Per-dimension description of a binning for ops.make_binning.
+
+    policy "hist"   : what ``utils.hist`` does (hist.py:86-127): irregular -> explicit edges (searchsorted on the real
+                      edges), log -> linear bins in log(x) (half-open, ``log_events`` sample), else linear (half-open);
+    policy "generic": what the Container translations do (translation.histogram / lookup, translation.py:88-129,
+                      228-344): linear-regular dimensions through the fast_histogram / lookup_regular rule (half-open),
+                      EVERYTHING ELSE (log or irregular) through ``np.histogramdd`` / ``find_index`` on the real edges,
+                      i.e. upper edge inclusive."""
+    if policy not in ("hist", "generic"):
+        raise ValueError("unknown index policy %r" % policy)
     dims = []
     for d in binning:
         edges = np.asarray(d.bin_edges.magnitude, dtype=np.float64)
-        if d.is_irregular:
+        if d.is_irregular or (policy == "generic" and d.is_log):
             dims.append(dict(kind="edges", n_bins=d.num_bins, edges=edges))
         elif d.is_log:
             dims.append(dict(kind="log", n_bins=d.num_bins, lo=float(edges[0]), hi=float(edges[-1])))
@@ -243,11 +251,12 @@ class Container:
         return iter(self.keys)
 
     # --------------------------------------------------------------------- translation ---
-    def bin_index(self, binning):
+    def bin_index(self, binning, policy="generic"):
         """Flat row-major bin index (int32, -1 outside) of every event on `binning`, cached.
-        Equivalent to what the reference recomputes inside every histogram()/lookup() call."""
+        Equivalent to what the reference recomputes inside every histogram()/lookup() call; ``policy`` selects the
+        edge rule (see ``regularized_dims``): "generic" for the container translations, "hist" for ``utils.hist``."""
         from pisa_b200 import ops
-        ck = ("index", hash(binning))
+        ck = ("index", hash(binning), policy)
         hit = self._index_cache.get(ck)
         if hit is not None:
             return hit[1]
@@ -255,7 +264,7 @@ class Container:
         self.representation = "events"
         coords = [self[name] for name in binning.names]
         self.representation = saved
-        b, keep = ops.make_binning(regularized_dims(binning), coords[0].device)
+        b, _keep = ops.make_binning(regularized_dims(binning, policy), coords[0].device)
         idx = ops.hist_index(b, coords)
         self._index_cache[ck] = (tuple(binning.names), idx)
         self._index_cache_names.update(binning.names)
@@ -327,8 +336,9 @@ class Container:
         if weights.dim() != 1:
             raise NotImplementedError("resampling of vector-valued maps")
         dev = weights.device
-        new_b, _ = ops.make_binning(regularized_dims(dest_representation), dev)
-        old_b, _ = ops.make_binning(regularized_dims(src_representation), dev)
+        # (both keep-alive lists must outlive the hist_index calls below: the structs hold raw edge pointers)
+        new_b, _keep_new = ops.make_binning(regularized_dims(dest_representation, "generic"), dev)
+        old_b, _keep_old = ops.make_binning(regularized_dims(src_representation, "generic"), dev)
         into_new = ops.hist_index(new_b, old_sample)
         n_bins = dest_representation.size
         summed, _ = ops.hist_accumulate(into_new, weights, n_bins, want_w2=False)
@@ -402,10 +412,11 @@ class VirtualContainer:
             c.set_aux_data(key, val)
 
     def mark_changed(self, key):
-        # device tensors are shared by reference between linked containers: no copy needed
+        # every linked container gets its OWN copy (np.copy in the reference, container.py:427-433): stages that
+        # later mutate one container's array in place (aeff, prob3.apply) must not reach the others
         src = self.containers[0][key]
         for c in self.containers[1:]:
-            c[key] = src
+            c[key] = src.clone()
         for c in self:
             c.mark_changed(key)
 
@@ -426,8 +437,8 @@ class VirtualContainer:
     size = property(lambda self: int(np.prod(self.shape)))
     is_map = property(lambda self: self.containers[0].is_map)
 
-    def bin_index(self, binning):
-        return self.containers[0].bin_index(binning)
+    def bin_index(self, binning, policy="generic"):
+        return self.containers[0].bin_index(binning, policy)
 
 
 class ContainerSet:

@@ -108,8 +108,8 @@ class ParamSet:
                 self._params[self.index(p.name)] = p
             elif extend:
                 self._params.append(p)
-            else:
-                raise ValueError("Param %s not in set" % p.name)
+            # (extend=False: params this set does not hold are ignored -- Pipeline.update_params passes every
+            # param to every stage, pipeline.py:579-596 of the reference)
 
     def extend(self, obj):
         self.update(obj, extend=True)
@@ -205,36 +205,44 @@ class ParamSelector:
         return list(self._selections)
 
     def select_params(self, selections=None, error_on_missing=False):
+        """Apply the named selector sets to the current params IN ORDER (param.py:1649-1684 of the reference):
+        every selection that exists is applied before a missing one raises (``error_on_missing``) or is skipped."""
         if selections is None:
-            return self._current
+            selections = list(self._selections)
         if isinstance(selections, str):
-            selections = [selections]
-        selections = [s.strip().lower() for s in selections]
-        found = [s for s in selections if s in self._selector_sets]
-        if error_on_missing and len(found) < len(selections):
-            raise KeyError("selections %s not all present" % (selections,))
-        # update in place so that stages holding a reference to `.params` see the change
-        self._selections = selections
-        new = ParamSet(self._regular)
-        for sel in found:
-            new.update(self._selector_sets[sel])
-        self._current._params[:] = new._params
+            selections = selections.split(",")
+        distilled = []
+        for sel in selections:
+            if sel is None:
+                continue
+            if not isinstance(sel, str):
+                raise ValueError("Selection should be a str. Got %s instead." % type(sel))
+            sel = sel.strip().lower()
+            if sel in self._selector_sets:
+                # in place, so that stages holding a reference to `.params` see the change
+                self._current.update(self._selector_sets[sel])
+            elif error_on_missing:
+                raise KeyError('No selection "%s" available; valid selections are %s (case-insensitive).'
+                               % (sel, list(self._selector_sets)))
+            distilled.append(sel)
+        self._selections = sorted(distilled)
         return self._current
 
-    def update(self, p, selector=None):
+    def update(self, p, selector=None, existing_must_match=False, extend=True):
+        """Reference semantics (param.py:1708-1730): without ``selector`` the regular set, the current set AND
+        every active selector set take the new params, so that a later ``select_params`` does not revert them."""
+        p = p if isinstance(p, ParamSet) else ParamSet(p)
         if selector is None:
-            self._regular.update(p)
+            self._regular.update(p, existing_must_match=existing_must_match, extend=extend)
+            self._current.update(p, existing_must_match=existing_must_match, extend=extend)
+            for sel in self._selections:
+                if sel in self._selector_sets:
+                    self._selector_sets[sel].update(p, existing_must_match=existing_must_match, extend=extend)
         else:
             sel = selector.strip().lower()
-            self._selector_sets.setdefault(sel, ParamSet()).update(p)
-        if self._current is None:
-            self._rebuild()
-        else:
-            new = ParamSet(self._regular)
-            for s in self._selections:
-                if s in self._selector_sets:
-                    new.update(self._selector_sets[s])
-            self._current._params[:] = new._params
+            self._selector_sets.setdefault(sel, ParamSet()).update(p, existing_must_match=existing_must_match,
+                                                                   extend=extend)
+            self.select_params(error_on_missing=False)   # re-select in case the update touched an active set
 
     def get(self, name, selector=None):
         if selector is None:

@@ -104,10 +104,11 @@ class Pipeline:
             s.select_params(selections, error_on_missing=False)
 
     def update_params(self, params, existing_must_match=False, extend=False):
+        """Through every stage's ParamSelector (pipeline.py:579-596 of the reference): the regular set, the current set
+        and the active selector sets are updated, so a later ``select_params`` does not revert the new values."""
+        plist = [params] if not hasattr(params, "__iter__") else list(params)
         for s in self._stages:
-            for p in ([params] if not hasattr(params, "__iter__") else params):
-                if p.name in s.params.names:
-                    s.params.update(p)
+            s._param_selector.update(plist, existing_must_match=existing_must_match, extend=extend)
 
     # -------------------------------------------------------------------------- execution -----
     @property

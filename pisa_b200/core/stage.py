@@ -114,11 +114,9 @@ class Stage:
     error_method = property(lambda self: self._error_method)
 
     def select_params(self, selections, error_on_missing=False):
-        try:
-            self._param_selector.select_params(selections, error_on_missing=True)
-        except KeyError:
-            if error_on_missing:
-                raise
+        # selections this stage has are applied in order; a missing one raises only when asked to (stage.py:300-306
+        # and param.py:1649-1684 of the reference)
+        self._param_selector.select_params(selections, error_on_missing=error_on_missing)
 
     # ------------------------------------------------------------------------- modes -----
     def _set_mode(self, mode, value):

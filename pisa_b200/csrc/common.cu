@@ -27,6 +27,10 @@ int cuda_fail(cudaError_t e, const char *what) {
 
 void note_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+// arithmetic of the *_f32 propagation entry points (pisab_set_f32_math)
+static std::atomic<int> g_f32_math{PISAB_F32_MATH_MIXED};
+bool f32_math_mixed() { return g_f32_math.load(std::memory_order_relaxed) == PISAB_F32_MATH_MIXED; }
+
 // CUDA-event timing of one launch on the stream it is issued to (bench.py roofline numbers).
 static thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 LaunchTimer::LaunchTimer(cudaStream_t s) : stream(s), active(g_profiling.load() != 0) {
@@ -91,6 +95,16 @@ int pisab_device_info(int32_t *sms, int32_t *cc_major, int32_t *cc_minor) {
     if (cc_minor) *cc_minor = p.minor;
     return PISAB_OK;
 }
+
+int pisab_set_f32_math(int32_t mode) {
+    if (mode != PISAB_F32_MATH_FP64 && mode != PISAB_F32_MATH_MIXED) {
+        set_error("f32 math mode must be PISAB_F32_MATH_FP64 (0) or PISAB_F32_MATH_MIXED (1)");
+        return PISAB_ERR_ARG;
+    }
+    g_f32_math.store(mode);
+    return PISAB_OK;
+}
+int pisab_get_f32_math(void) { return g_f32_math.load(); }
 
 int64_t pisab_launch_count(int32_t reset) {
     const long long v = g_launches.load();

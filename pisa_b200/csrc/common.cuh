@@ -32,6 +32,9 @@ struct LaunchTimer {
     ~LaunchTimer();
 };
 
+// true when the *_f32 propagation entry points use the mixed-precision FP32 arithmetic (prob3_mp.cuh)
+bool f32_math_mixed();
+
 // number of SMs of the current device (cached); 0 on failure
 int sm_count();
 

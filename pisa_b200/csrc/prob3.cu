@@ -5,7 +5,7 @@
 #include <vector>
 
 #include "hist_device.cuh"
-#include "prob3_device.cuh"
+#include "prob3_walk.cuh"
 
 namespace pisab {
 
@@ -56,15 +56,21 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 //   FULL: probability[n,3,3] ; otherwise prob_e / prob_mu of the event's final flavour.
 // Same layout as the fused kernel: propagation state and h0 in per-thread shared-memory columns, the
 // next event's energy / coszen staged by cp.async while the current one is propagated.
+// MP = the FP32 mode's mixed-precision arithmetic (prob3_mp.cuh): state and per-event Hamiltonian in registers, so
+// the dynamic shared memory shrinks to the two staging slots per thread.
+#ifndef PISAB_MP_MIN_BLOCKS
+#define PISAB_MP_MIN_BLOCKS 2
+#endif
 template <bool FULL>
-static size_t earth_smem_bytes(size_t io_bytes, bool std_matter) {
+static size_t earth_smem_bytes(size_t io_bytes, bool std_matter, bool mp = false) {
+    if (mp) return 2 * (size_t)kBlock * io_bytes;
     const size_t doubles = (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) +
                                     (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return doubles * sizeof(double) + 2 * (size_t)kBlock * io_bytes;
 }
 
-template <typename IO, bool FULL, bool STD>
-__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
+template <typename IO, bool FULL, bool STD, bool MP = false>
+__global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                    int nubar, const int32_t *__restrict__ d_nubar, int flav,
                    const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
@@ -75,7 +81,8 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
     __shared__ EarthTable s_earth;
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn_earth);
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn_earth + PropagatorSmem<NR, NC>::kDoubles * kBlock);
-    IO *s_e = reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]), *s_cz = s_e + kBlock;
+    IO *s_e = MP ? reinterpret_cast<IO *>(s_dyn_earth) : reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]);
+    IO *s_cz = s_e + kBlock;
     copy_earth(earth, &s_earth);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -97,23 +104,32 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
         const double inv_e = rcp_fast(e);
-        H0Smem<STD> h0{&s_h0[0][tid], kBlock};
-        {
-            const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
+        const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
+        auto emit = [&](const auto &P) {
+            if (FULL) {
+                IO *o = probability + i * 9;
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a); // P(a->b) = |A[b][a]|^2
+            } else {
+                prob_e[i] = (IO)P.prob(0, 0);
+                prob_mu[i] = (IO)P.prob(0, 1);
+            }
+        };
+        if constexpr (MP) {
+            H0MP<STD> h0;
+            h0.init(hh);
+            PropagatorF<NR, NC> P;
+            propagate_earth<NR, NC, STD>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
+            emit(P);
+        } else {
+            H0Smem<STD> h0{&s_h0[0][tid], kBlock};
             h0.store(hh);
             if (STD) h0.set_poly(hh);
-        }
-        PropagatorSmem<NR, NC> P{&s_state[0][tid], kBlock};
-        propagate_earth<NR, NC, STD>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
-        if (FULL) {
-            IO *o = probability + i * 9;
-#pragma unroll
-            for (int a = 0; a < 3; ++a)
-#pragma unroll
-                for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a); // P(a->b) = |A[b][a]|^2
-        } else {
-            prob_e[i] = (IO)P.prob(0, 0);
-            prob_mu[i] = (IO)P.prob(0, 1);
+            PropagatorSmem<NR, NC> P{&s_state[0][tid], kBlock};
+            propagate_earth<NR, NC, STD>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
+            emit(P);
         }
         cp_async_wait_all();
         i_cur = i_next;
@@ -188,9 +204,9 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
-static size_t fused_smem_bytes(int n_bins, bool std_matter) {
-    const size_t doubles = (size_t)(PropagatorSmem<1, 2>::kDoubles +
-                                    (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
+static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false) {
+    const size_t doubles = mp ? 0 : (size_t)(PropagatorSmem<1, 2>::kDoubles +
+                                             (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
@@ -233,7 +249,7 @@ struct FusedBatch {
 // blocks cooperate on one template; partials: [container][n_ranks][2 n_bins] of that template.
 // PLAIN: no per-event outputs and no per-event nubar / flav arrays (the fit-loop case): the null checks and
 // the three optional stores disappear from the event loop.
-template <typename IO, bool STD, bool PLAIN>
+template <typename IO, bool STD, bool PLAIN, bool MP = false>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
                                                     const FusedBatch<IO> &batch, int ci_begin, int ci_end,
                                                     int rank, int n_ranks, double *__restrict__ partials,
@@ -243,9 +259,9 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     const int n_bins = batch.n_bins;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
-    s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
+    if (!MP) s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn); // 16-byte aligned: see H0Smem
-    s_dyn += H0Smem<STD>::kDoubles * kBlock;
+    if (!MP) s_dyn += H0Smem<STD>::kDoubles * kBlock;   // (FP32 mode: state and Hamiltonian live in registers)
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
@@ -287,15 +303,24 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 const int nb = (!PLAIN && C.d_nubar) ? __ldg(C.d_nubar + i) : C.nubar;
                 const int fl = (!PLAIN && C.d_flav) ? __ldg(C.d_flav + i) : C.flav;
                 const double inv_e = rcp_fast(e);
-                H0Smem<STD> h0{&s_h0[0][tid], kBlock};
-                {
-                    const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
+                const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
+                double pe, pmu;
+                if constexpr (MP) {
+                    H0MP<STD> h0;
+                    h0.init(hh);
+                    PropagatorF<1, 2> P;
+                    propagate_earth<1, 2, STD>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
+                    pe = P.prob(0, 0);
+                    pmu = P.prob(0, 1);
+                } else {
+                    H0Smem<STD> h0{&s_h0[0][tid], kBlock};
                     h0.store(hh);
                     if (STD) h0.set_poly(hh);
+                    PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
+                    propagate_earth<1, 2, STD>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
+                    pe = P.prob(0, 0);
+                    pmu = P.prob(0, 1);
                 }
-                PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
-                propagate_earth<1, 2, STD>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
-                const double pe = P.prob(0, 0), pmu = P.prob(0, 1);
                 cp_async_wait_all();
                 // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
                 const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
@@ -316,8 +341,8 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     }
 }
 
-template <typename IO, bool STD, bool PLAIN>
-__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
+template <typename IO, bool STD, bool PLAIN, bool MP = false>
+__global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials) {
     extern __shared__ __align__(16) double s_hist[];
@@ -329,7 +354,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // never walks more than one container, so a template over analysis-size containers (1e4 events each)
     // costs one or two event latencies instead of one per container.
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, STD, PLAIN>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist);
+    fused_template_body<IO, STD, PLAIN, MP>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -337,8 +362,8 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
 // parameter space) and is staged in shared memory.  For the event samples of a real analysis (1e5 .. 1e6
 // events) one template does not fill the GPU and a per-template launch is bound by launch latency plus one or
 // two event latencies (~45 us); batching the hypotheses restores full occupancy.  Per-event outputs are not written (they would race between templates).
-template <typename IO, bool STD>
-__global__ void __launch_bounds__(kBlock, PISAB_MIN_BLOCKS)
+template <typename IO, bool STD, bool MP = false>
+__global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<IO> batch, int ranks_per_template,
                           double *__restrict__ partials) {
@@ -356,7 +381,7 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     }
     copy_earth(earth, &s_earth); // ends with __syncthreads()
     double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
-    fused_template_body<IO, STD, true>(s_osc, s_earth, batch, ci, ci + 1, rank, ranks_per_template, mine, s_hist);
+    fused_template_body<IO, STD, true, MP>(s_osc, s_earth, batch, ci, ci + 1, rank, ranks_per_template, mine, s_hist);
 }
 
 } // namespace pisab
@@ -365,6 +390,29 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
 // C ABI
 // ---------------------------------------------------------------------------------------------
 using namespace pisab;
+
+// kernel selection: the mixed-precision instantiations exist for float storage only
+template <typename IO, bool FULL, bool STD>
+static auto earth_kernel(bool mp) {
+    if constexpr (sizeof(IO) == 4) {
+        if (mp) return prob3_earth_kernel<IO, FULL, STD, true>;
+    }
+    return prob3_earth_kernel<IO, FULL, STD, false>;
+}
+template <typename IO, bool STD, bool PLAIN>
+static auto fused_kernel(bool mp) {
+    if constexpr (sizeof(IO) == 4) {
+        if (mp) return reweight_hist_kernel<IO, STD, PLAIN, true>;
+    }
+    return reweight_hist_kernel<IO, STD, PLAIN, false>;
+}
+template <typename IO, bool STD>
+static auto scan_kernel(bool mp) {
+    if constexpr (sizeof(IO) == 4) {
+        if (mp) return reweight_hist_scan_kernel<IO, STD, true>;
+    }
+    return reweight_hist_scan_kernel<IO, STD, false>;
+}
 
 static int grid_for(int64_t n, int blocks_per_sm) {
     const int sms = sm_count();
@@ -422,10 +470,11 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     if (n == 0) return PISAB_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const bool std_matter = ot.std_matter != 0.0;
+    const bool mp = sizeof(IO) == 4 && f32_math_mixed();
     if (d_probability) {
         // the 3x3 state (74 KB per block) leaves no room for the cached H0^2 of the standard-matter path
-        auto kernel = prob3_earth_kernel<IO, true, false>;
-        const size_t smem = earth_smem_bytes<true>(sizeof(IO), false);
+        auto kernel = earth_kernel<IO, true, false>(mp);
+        const size_t smem = earth_smem_bytes<true>(sizeof(IO), false, mp);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
         kernel<<<waved_grid(resident_grid(kernel, n, smem), n), kBlock, smem, s>>>(
@@ -444,8 +493,8 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
                  : pisab_fill_probs_f32((const float *)d_probability, 1, flav, n, (float *)d_prob_mu, stream);
         if (r1) return r1;
     } else if (d_prob_e) {
-        auto kernel = std_matter ? prob3_earth_kernel<IO, false, true> : prob3_earth_kernel<IO, false, false>;
-        const size_t smem = earth_smem_bytes<false>(sizeof(IO), std_matter);
+        auto kernel = std_matter ? earth_kernel<IO, false, true>(mp) : earth_kernel<IO, false, false>(mp);
+        const size_t smem = earth_smem_bytes<false>(sizeof(IO), std_matter, mp);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         LaunchTimer t(s);
         kernel<<<waved_grid(resident_grid(kernel, n, smem), n), kBlock, smem, s>>>(
@@ -524,14 +573,15 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
 #else
     const bool std_matter = ot.std_matter != 0.0;
 #endif
-    const size_t smem = fused_smem_bytes<IO>(n_bins, std_matter);
+    const bool mp = sizeof(IO) == 4 && f32_math_mixed();
+    const size_t smem = fused_smem_bytes<IO>(n_bins, std_matter, mp);
     bool plain = true;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
         plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu;
     }
-    auto kernel = std_matter ? (plain ? reweight_hist_kernel<IO, true, true> : reweight_hist_kernel<IO, true, false>)
-                             : (plain ? reweight_hist_kernel<IO, false, true> : reweight_hist_kernel<IO, false, false>);
+    auto kernel = std_matter ? (plain ? fused_kernel<IO, true, true>(mp) : fused_kernel<IO, true, false>(mp))
+                             : (plain ? fused_kernel<IO, false, true>(mp) : fused_kernel<IO, false, false>(mp));
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
@@ -691,8 +741,9 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     OscTable *d_tables = (OscTable *)d_workspace;
     double *d_partials = (double *)((char *)d_workspace + table_bytes);
     PISAB_CUDA_CHECK(cudaMemcpyAsync(d_tables, tables.data(), (size_t)n_templates * sizeof(OscTable), cudaMemcpyHostToDevice, s));
-    const size_t smem = fused_smem_bytes<IO>(n_bins, all_std);
-    auto kernel = all_std ? reweight_hist_scan_kernel<IO, true> : reweight_hist_scan_kernel<IO, false>;
+    const bool mp = sizeof(IO) == 4 && f32_math_mixed();
+    const size_t smem = fused_smem_bytes<IO>(n_bins, all_std, mp);
+    auto kernel = all_std ? scan_kernel<IO, true>(mp) : scan_kernel<IO, false>(mp);
     {
         cudaFuncAttributes fa;
         PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));

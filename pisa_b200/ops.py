@@ -61,6 +61,17 @@ def _species(val, n, name):
     return int(val), None
 
 
+def set_f32_math(mode):
+    """Arithmetic behind float32 event arrays: "mixed" (default; FP64 eigenvalues / phases, float32 matrices and
+    state: the FP32 mode) or "fp64" (float32 storage only).  Process-wide (``pisab_set_f32_math``)."""
+    code = {"mixed": _lib.F32_MATH_MIXED, "fp64": _lib.F32_MATH_FP64}.get(mode, mode)
+    _lib.check(_lib.load().pisab_set_f32_math(int(code)))
+
+
+def get_f32_math():
+    return {_lib.F32_MATH_MIXED: "mixed", _lib.F32_MATH_FP64: "fp64"}[int(_lib.load().pisab_get_f32_math())]
+
+
 def device_info():
     sms, maj, mnr = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     _lib.check(_lib.load().pisab_device_info(ctypes.byref(sms), ctypes.byref(maj), ctypes.byref(mnr)))
@@ -295,6 +306,9 @@ def make_binning(dims, device):
             b.kind[i], b.lo[i], b.hi[i] = _lib.DIM_LIN, float(d["lo"]), float(d["hi"])
         else:
             raise ValueError("unknown dimension kind %r" % kind)
+    # the struct only holds raw device pointers: tie the edge tensors' lifetime to it, so that a caller that drops the
+    # second return value cannot leave `d_edges` dangling
+    b._keep = keep
     return b, keep
 
 

@@ -2,7 +2,7 @@
 #ifndef PISAB_HOST_EMU
 #define PISAB_HOST_EMU
 #endif
-#include "../../pisa_b200/csrc/prob3_device.cuh"
+#include "../../pisa_b200/csrc/prob3_walk.cuh"
 #include "../../pisa_b200/csrc/tables.cu"
 #include <stdarg.h>
 namespace pisab {
@@ -30,6 +30,33 @@ extern "C" int emu_propagate(const pisab_osc_consts_t *c, const pisab_earth_t *e
             Propagator<1, 2> P;
             if (ot.std_matter != 0.0) propagate_earth<1, 2, true>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
             else propagate_earth<1, 2, false>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
+            prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
+        }
+    }
+    return 0;
+}
+
+// FP32 mode (prob3_mp.cuh): eigenvalues / phase arguments in FP64, matrices and state in float
+extern "C" int emu_propagate_mp(const pisab_osc_consts_t *c, const pisab_earth_t *e, int nubar, int flav,
+                                const double *energy, const double *coszen, int64_t n, double *probability,
+                                double *prob_e, double *prob_mu) {
+    OscTable ot; EarthTable et;
+    int rc = build_osc_table(c, &ot); if (rc) return rc;
+    rc = build_earth_table(e, &et); if (rc) return rc;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) {
+        const double inv_e = rcp_fast(energy[i]);
+        const Herm3 hh = herm_axpy(inv_e, ot.hv[nubar > 0 ? 0 : 1], ot.lr);
+        if (probability) {
+            H0MP<false> h0; h0.init(hh);
+            PropagatorF<3, 3> P;
+            propagate_earth<3, 3, false>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) probability[i * 9 + a * 3 + b] = P.prob(b, a);
+        }
+        if (prob_e) {
+            PropagatorF<1, 2> P;
+            if (ot.std_matter != 0.0) { H0MP<true> h0; h0.init(hh); propagate_earth<1, 2, true>(h0, ot, et, coszen[i], inv_e, nubar, flav, P); }
+            else { H0MP<false> h0; h0.init(hh); propagate_earth<1, 2, false>(h0, ot, et, coszen[i], inv_e, nubar, flav, P); }
             prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
         }
     }

@@ -42,3 +42,16 @@ def test_device_math_on_host_lri_and_other_earth_models(emu):
     assert emu.run(n=20000, lri=np.diag([1e-14, -1e-14, 0.0]), seed=6) < 1e-10
     assert emu.run(n=20000, model="PREM_10layer.dat", seed=7) < 1e-10
     assert emu.run(n=20000, model="PREM_4layer.dat", depth=10.0, seed=8) < 1e-10
+
+
+@pytest.mark.parametrize("nsi,nubar", [(False, 1), (True, -1)])
+def test_fp32_mode_math_on_host_within_1e5_of_fp64_oracle(emu, nsi, nubar):
+    """The mixed-precision FP32 mode (prob3_mp.cuh: FP64 eigenvalues / phases, float matrices and state) against the
+    FP64 oracle on float32-rounded inputs, energies 1 GeV .. 1 TeV: BASELINE tolerance 1e-5 absolute.  Measured on
+    1e6 events: max 6.5e-6, 99.9 % below 2.6e-6, mean 3e-7 (the floor of float matrices times ~50 rad phases)."""
+    assert emu.run_mp(n=60000, nsi=nsi, nubar=nubar, seed=11, verbose=False) < 1e-5
+
+
+def test_fp32_mode_math_on_host_lri_and_small_earth(emu):
+    assert emu.run_mp(n=20000, lri=np.diag([1e-14, -1e-14, 0.0]), seed=12, verbose=False) < 1e-5
+    assert emu.run_mp(n=20000, model="PREM_4layer.dat", depth=10.0, seed=13, verbose=False) < 1e-5
