@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--ftype", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--target", default="parallel", choices=["cpu", "parallel"])
     ap.add_argument("--events", type=int, default=1200000)
+    ap.add_argument("--seconds-per-step", type=float, default=0.0,
+                    help="size the sample for about this much CPU time per step (pilot run after the JIT); overrides --events")
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--nsi", action="store_true")
@@ -73,21 +75,25 @@ def main():
     L = Layers(prem, syn.EARTH["detector_depth"], syn.EARTH["prop_height"])
     L.setElecFrac(syn.EARTH["YeI"], syn.EARTH["YeO"], syn.EARTH["YeM"])
 
-    n = args.events // 12 * 12
-    ev = syn.make_events_numpy(n, args.seed, dtype=FT)
-    per = n // 12
-    blocks = []
-    for c, (name, nubar, flav) in enumerate(syn.CONTAINERS):
-        sl = slice(c * per, (c + 1) * per)
-        b = {k: np.ascontiguousarray(v[sl]) for k, v in ev.items()}
-        L.calcLayers(b["true_coszen"])                                 # setup_function
-        b["densities"] = L.density.reshape((per, L.max_layers)).astype(FT)
-        b["distances"] = L.distance.reshape((per, L.max_layers)).astype(FT)
-        b["probability"] = np.empty((per, 3, 3), dtype=FT)
-        b["prob_e"] = np.empty(per, dtype=FT)
-        b["prob_mu"] = np.empty(per, dtype=FT)
-        blocks.append((nubar, flav, b))
     edges = [syn.DRAGON_E_EDGES, np.linspace(-1.0, 1.0, 9), np.linspace(-0.5, 1.5, 3)]
+    blocks = []
+
+    def make(n):
+        n = n // 12 * 12
+        ev = syn.make_events_numpy(n, args.seed, dtype=FT)
+        per = n // 12
+        del blocks[:]
+        for c, (name, nubar, flav) in enumerate(syn.CONTAINERS):
+            sl = slice(c * per, (c + 1) * per)
+            b = {k: np.ascontiguousarray(v[sl]) for k, v in ev.items()}
+            L.calcLayers(b["true_coszen"])                                 # setup_function
+            b["densities"] = L.density.reshape((per, L.max_layers)).astype(FT)
+            b["distances"] = L.distance.reshape((per, L.max_layers)).astype(FT)
+            b["probability"] = np.empty((per, 3, 3), dtype=FT)
+            b["prob_e"] = np.empty(per, dtype=FT)
+            b["prob_mu"] = np.empty(per, dtype=FT)
+            blocks.append((nubar, flav, b))
+        return n
 
     def step():
         out = np.zeros((12, 2, 128))
@@ -102,9 +108,16 @@ def main():
             out[c, 1] = np.histogramdd(sample, bins=edges, weights=w * w)[0].ravel()
         return out
 
+    n = make(48000 if args.seconds_per_step > 0 else args.events)
     t0 = time.perf_counter()
     step()                                                             # first call: includes JIT compilation
     t_first = time.perf_counter() - t0
+    if args.seconds_per_step > 0:
+        t0 = time.perf_counter()
+        step()
+        rate = n / (time.perf_counter() - t0)
+        n = make(int(min(max(rate * args.seconds_per_step, 48000), 2e7)))
+        step()
     for _ in range(max(0, args.warmup - 1)):
         step()
     t0 = time.perf_counter()

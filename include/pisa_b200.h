@@ -323,6 +323,23 @@ int pisab_reweight_hist_scan_f32(const pisab_osc_consts_t *consts, int32_t n_tem
 int pisab_template_chi2_batch(const double *d_hist, int32_t n_templates, int32_t n_containers, int32_t n_bins,
                               const double *d_observed, double *d_out, void *stream);
 
+/* ---- small stage-API operators ---------------------------------------------------------- */
+/* aeff.aeff apply_function (pisa/stages/aeff/aeff.py:68-88): weights[i] *= factor[i] * scale in FTYPE arithmetic
+ * (d_factor = weighted_aeff, may be NULL: weights[i] *= scale). */
+int pisab_scale_weights_f64(const double *d_factor, double scale, int64_t n, double *d_weights, void *stream);
+int pisab_scale_weights_f32(const float *d_factor, double scale, int64_t n, float *d_weights, void *stream);
+/* Flat index on the joint binning a + b (utils.hist with a binned calc_mode, hist.py:69-84) from two cached
+ * sub-indices: out = a * size_b + b, -1 where either is -1. */
+int pisab_joint_index(const int32_t *d_index_a, const int32_t *d_index_b, int32_t size_b, int64_t n,
+                      int32_t *d_out, void *stream);
+/* utils.hist apply_function with a binned calc_mode (hist.py:131-160): hist = (unc w) @ T, sumw2 = (unc w)^2 @ T,
+ * bin_unc2 = (unc^2 w) @ T, T = hist_transform [n_calc][n_out] row-major; d_unc, d_sumw2, d_bin_unc2 may be NULL.
+ * Fixed summation order (bit-reproducible). */
+int pisab_hist_transform_f64(const double *d_weights, const double *d_unc, const double *d_transform, int32_t n_calc,
+                             int32_t n_out, double *d_hist, double *d_sumw2, double *d_bin_unc2, void *stream);
+int pisab_hist_transform_f32(const float *d_weights, const float *d_unc, const float *d_transform, int32_t n_calc,
+                             int32_t n_out, double *d_hist, double *d_sumw2, double *d_bin_unc2, void *stream);
+
 /* ---- measurement helpers (bench.py) ---------------------------------------------------- */
 /* Dependent-chain-free DFMA microbenchmark: runs `iters` x 8 independent FMAs per thread
  * on a full grid and returns achieved FP64 FLOP/s (synchronises). Roofline denominator. */

@@ -52,15 +52,20 @@ def regularized_dims(binning, policy="hist"):
     policy "hist"   : what ``utils.hist`` does (hist.py:86-127): irregular -> explicit edges (searchsorted on the real
                       edges), log -> linear bins in log(x) (half-open, ``log_events`` sample), else linear (half-open);
     policy "generic": what the Container translations do (translation.histogram / lookup, translation.py:88-129,
-                      228-344): linear-regular dimensions through the fast_histogram / lookup_regular rule (half-open),
-                      EVERYTHING ELSE (log or irregular) through ``np.histogramdd`` / ``find_index`` on the real edges,
-                      i.e. upper edge inclusive."""
-    if policy not in ("hist", "generic"):
+                      228-344): a binning whose dimensions are ALL linear-regular goes through the fast_histogram /
+                      lookup_regular rule (half-open); as soon as one dimension is logarithmic or irregular the WHOLE
+                      binning goes through ``np.histogramdd`` / ``find_index`` on the real edges, i.e. the upper edge
+                      of every dimension is inclusive;
+    policy "edges"  : every dimension by its real edges (the second branch of "generic", forced: used for the two
+                      halves of a joint binning)."""
+    if policy not in ("hist", "generic", "edges"):
         raise ValueError("unknown index policy %r" % policy)
+    if policy == "generic" and any(d.is_irregular or d.is_log for d in binning):
+        policy = "edges"
     dims = []
     for d in binning:
         edges = np.asarray(d.bin_edges.magnitude, dtype=np.float64)
-        if d.is_irregular or (policy == "generic" and d.is_log):
+        if policy == "edges" or d.is_irregular:
             dims.append(dict(kind="edges", n_bins=d.num_bins, edges=edges))
         elif d.is_log:
             dims.append(dict(kind="log", n_bins=d.num_bins, lo=float(edges[0]), hi=float(edges[-1])))

@@ -453,6 +453,68 @@ template_chi2_batch_kernel(const double *__restrict__ hist, int n_containers, in
     if (threadIdx.x == 0) out[blockIdx.x] = s[0];
 }
 
+// aeff.aeff (pisa/stages/aeff/aeff.py:68-88): weights *= weighted_aeff * scale, evaluated in FTYPE like numpy does
+// (the temporary `weighted_aeff * scale` is rounded to FTYPE before the in-place multiply).  24 B/event, HBM-bound.
+template <typename IO>
+__global__ void __launch_bounds__(256)
+scale_weights_kernel(const IO *__restrict__ factor, double scale, int64_t n, IO *__restrict__ weights) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const IO s = (IO)scale;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        if (sizeof(IO) == 8) {
+            const double t = factor ? __dmul_rn((double)__ldg(factor + i), (double)s) : (double)s;
+            weights[i] = (IO)__dmul_rn((double)weights[i], t);
+        } else {
+            const float t = factor ? __fmul_rn((float)__ldg(factor + i), (float)s) : (float)s;
+            weights[i] = (IO)__fmul_rn((float)weights[i], t);
+        }
+    }
+}
+
+// flat index on the joint binning (calc_mode + apply_mode of utils.hist, hist.py:69-84) from the two cached
+// sub-indices: lifts the PISAB_MAX_DIMS limit of hist_index for the 5-dimensional true x reco layouts
+__global__ void __launch_bounds__(256)
+joint_index_kernel(const int32_t *__restrict__ a, const int32_t *__restrict__ b, int32_t size_b, int64_t n,
+                   int32_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const int32_t ia = __ldg(a + i), ib = __ldg(b + i);
+        out[i] = (ia < 0 || ib < 0) ? -1 : ia * size_b + ib;
+    }
+}
+
+// utils.hist with a binned calc_mode (hist.py:131-160): hist = (unc w) @ T, sumw2 = (unc w)^2 @ T,
+// bin_unc2 = (unc^2 w) @ T with T = hist_transform [n_calc, n_out].  One block serves 32 output bins: thread
+// (ox, cy) walks the calc bins cy, cy + 8, ... (coalesced rows of T), the 8 partial sums per output bin are added in
+// fixed order -- bit-reproducible.  Setup-size arithmetic (n_calc x n_out ~ 5e6 products).
+template <typename IO>
+__global__ void __launch_bounds__(256)
+hist_transform_kernel(const IO *__restrict__ w, const IO *__restrict__ unc, const IO *__restrict__ T, int n_calc,
+                      int n_out, double *__restrict__ h, double *__restrict__ sumw2, double *__restrict__ bin_unc2) {
+    __shared__ double s[3][8][33];
+    const int ox = threadIdx.x & 31, cy = threadIdx.x >> 5;
+    const int o = blockIdx.x * 32 + ox;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+    if (o < n_out) {
+        for (int c = cy; c < n_calc; c += 8) {
+            const double wc = (double)__ldg(w + c), u = unc ? (double)__ldg(unc + c) : 1.0;
+            const double t = (double)__ldg(T + (size_t)c * n_out + o);
+            const double uw = u * wc;
+            a0 = fma(uw, t, a0);
+            a1 = fma(uw * uw, t, a1);
+            a2 = fma(u * uw, t, a2);
+        }
+    }
+    s[0][cy][ox] = a0; s[1][cy][ox] = a1; s[2][cy][ox] = a2;
+    __syncthreads();
+    if (cy < 3 && o < n_out) {
+        double acc = 0.0;
+        for (int k = 0; k < 8; ++k) acc += s[cy][k][ox];
+        double *dst = cy == 0 ? h : (cy == 1 ? sumw2 : bin_unc2);
+        if (dst) dst[o] = acc;
+    }
+}
+
 static int ew_grid(int64_t n) {
     const int sms = sm_count() > 0 ? sm_count() : 148;
     int64_t want = (n + 255) / 256;
@@ -656,6 +718,52 @@ int pisab_apply_osc_weights_f32(const float *d_nu_flux, const float *d_prob_e, c
     PISAB_EW_CHECK(n >= 0 && (n == 0 || (d_nu_flux && d_prob_e && d_prob_mu && d_weights)));
     if (n == 0) return PISAB_OK;
     apply_osc_weights_kernel<float><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_nu_flux, d_prob_e, d_prob_mu, n, d_weights);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_scale_weights_f64(const double *d_factor, double scale, int64_t n, double *d_weights, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && (n == 0 || d_weights));
+    if (n == 0) return PISAB_OK;
+    scale_weights_kernel<double><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_factor, scale, n, d_weights);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+int pisab_scale_weights_f32(const float *d_factor, double scale, int64_t n, float *d_weights, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && (n == 0 || d_weights));
+    if (n == 0) return PISAB_OK;
+    scale_weights_kernel<float><<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_factor, scale, n, d_weights);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_joint_index(const int32_t *d_index_a, const int32_t *d_index_b, int32_t size_b, int64_t n,
+                      int32_t *d_out, void *stream) {
+    PISAB_EW_CHECK(n >= 0 && size_b >= 1 && (n == 0 || (d_index_a && d_index_b && d_out)));
+    if (n == 0) return PISAB_OK;
+    joint_index_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(d_index_a, d_index_b, size_b, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+int pisab_hist_transform_f64(const double *d_weights, const double *d_unc, const double *d_transform, int32_t n_calc,
+                             int32_t n_out, double *d_hist, double *d_sumw2, double *d_bin_unc2, void *stream) {
+    PISAB_EW_CHECK(n_calc >= 1 && n_out >= 1 && d_weights && d_transform && d_hist);
+    hist_transform_kernel<double><<<(n_out + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
+        d_weights, d_unc, d_transform, n_calc, n_out, d_hist, d_sumw2, d_bin_unc2);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+int pisab_hist_transform_f32(const float *d_weights, const float *d_unc, const float *d_transform, int32_t n_calc,
+                             int32_t n_out, double *d_hist, double *d_sumw2, double *d_bin_unc2, void *stream) {
+    PISAB_EW_CHECK(n_calc >= 1 && n_out >= 1 && d_weights && d_transform && d_hist);
+    hist_transform_kernel<float><<<(n_out + 31) / 32, 256, 0, (cudaStream_t)stream>>>(
+        d_weights, d_unc, d_transform, n_calc, n_out, d_hist, d_sumw2, d_bin_unc2);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;

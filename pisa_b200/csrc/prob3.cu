@@ -63,7 +63,8 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 template <bool FULL>
 static size_t earth_smem_bytes(size_t io_bytes, bool std_matter, bool mp = false) {
-    if (mp) return 2 * (size_t)kBlock * io_bytes;
+    if (mp) return (size_t)(FULL ? PropagatorSmemF<3, 3>::kFloat2s : PropagatorSmemF<1, 2>::kFloat2s) * kBlock * sizeof(float2) +
+                   2 * (size_t)kBlock * io_bytes;
     const size_t doubles = (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) +
                                     (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return doubles * sizeof(double) + 2 * (size_t)kBlock * io_bytes;
@@ -81,7 +82,9 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
     __shared__ EarthTable s_earth;
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn_earth);
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn_earth + PropagatorSmem<NR, NC>::kDoubles * kBlock);
-    IO *s_e = MP ? reinterpret_cast<IO *>(s_dyn_earth) : reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]);
+    float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn_earth); // FP32 mode: float2 state columns
+    IO *s_e = MP ? reinterpret_cast<IO *>(&s_statef[PropagatorSmemF<NR, NC>::kFloat2s][0])
+                 : reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]);
     IO *s_cz = s_e + kBlock;
     copy_earth(earth, &s_earth);
     const int tid = threadIdx.x;
@@ -120,7 +123,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
         if constexpr (MP) {
             H0MP<STD> h0;
             h0.init(hh);
-            PropagatorF<NR, NC> P;
+            PropagatorSmemF<NR, NC> P{&s_statef[0][tid], kBlock};
             propagate_earth<NR, NC, STD>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
             emit(P);
         } else {
@@ -205,8 +208,10 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
 static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false) {
-    const size_t doubles = mp ? 0 : (size_t)(PropagatorSmem<1, 2>::kDoubles +
-                                             (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
+    // (FP32 mode: 9 float2 of state per thread = 9 doubles' worth; the Hamiltonian lives in registers)
+    const size_t doubles = mp ? (size_t)PropagatorSmemF<1, 2>::kFloat2s * kBlock
+                              : (size_t)(PropagatorSmem<1, 2>::kDoubles +
+                                         (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
@@ -259,9 +264,10 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     const int n_bins = batch.n_bins;
     double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
-    if (!MP) s_dyn += PropagatorSmem<1, 2>::kDoubles * kBlock;
+    float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn); // FP32 mode: float2 state columns
+    s_dyn += (MP ? PropagatorSmemF<1, 2>::kFloat2s : PropagatorSmem<1, 2>::kDoubles) * kBlock;
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn); // 16-byte aligned: see H0Smem
-    if (!MP) s_dyn += H0Smem<STD>::kDoubles * kBlock;   // (FP32 mode: state and Hamiltonian live in registers)
+    if (!MP) s_dyn += H0Smem<STD>::kDoubles * kBlock;   // (FP32 mode: the per-event Hamiltonian lives in registers)
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
@@ -308,7 +314,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 if constexpr (MP) {
                     H0MP<STD> h0;
                     h0.init(hh);
-                    PropagatorF<1, 2> P;
+                    PropagatorSmemF<1, 2> P{&s_statef[0][tid], kBlock};
                     propagate_earth<1, 2, STD>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
                     pe = P.prob(0, 0);
                     pmu = P.prob(0, 1);

@@ -106,7 +106,6 @@ __device__ __forceinline__ RootsC eigen_roots_centered(double c1, double c0) {
 //   s_i  = sum_{j != i} |h_ij|^2                      (diagonal of M^2 minus m_i^2)
 //   c_ij = h_ik h_kj, k the third index               (off-diagonal of M^2 minus (m_i + m_j) h_ij)
 struct LayerMatF {
-    float m0, m1, m2;
     float r01, i01, r02, i02, r12, i12;
     float s0, s1, s2;
     CplxF c01, c02, c12;
@@ -126,31 +125,32 @@ __device__ __forceinline__ void layer_products(LayerMatF &L) {
 // T = 1 + n1 (M - mu0) + n2 (M - mu0)(M - mu1) = exp(-i M t) up to the global phase exp(+i mu0 t).
 //   (M - mu0)(M - mu1)_ii = (m_i - mu0)(m_i - mu1) + s_i
 //   (M - mu0)(M - mu1)_ij = h_ij (mu2 - m_k) + c_ij          (trace-free: m_i + m_j = -m_k, mu0 + mu1 = -mu2)
-__device__ __forceinline__ void assemble_transition_mp(const LayerMatF &L, const RootsC &R, double t, Mat3F T) {
+// The diagonal enters only through ea_i = m_i - mu0, which the caller forms in FP64 and rounds once (L.m* is not
+// read here); m_i - mu1 = ea_i - g10 and mu2 - m_k = g20 - ea_k, so besides them only the three gaps are converted.
+__device__ __forceinline__ void assemble_transition_mp(const LayerMatF &L, float ea0, float ea1, float ea2,
+                                                       const RootsC &R, double t, Mat3F T) {
     const double g10d = R.m1 - R.m0, g20d = R.m2 - R.m0, g21d = R.m2 - R.m1;
     const CplxF e01 = expm1i_neg(g10d * t), e02 = expm1i_neg(g20d * t);
     const float g10 = (float)g10d, g20 = (float)g20d, g21 = (float)g21d;
-    const float mu0 = (float)R.m0, mu1 = (float)R.m1, mu2 = (float)R.m2;
-    // (three equal roots cannot occur: see eigen_solve; a vanishing gap gives inf * 0 only if H is a multiple of 1)
-    const float r10 = rcp_f32(fmaxf(g10, 1e-30f)), r20 = rcp_f32(fmaxf(g20, 1e-30f)), r21 = rcp_f32(fmaxf(g21, 1e-30f));
+    // (a gap that underflows in float would give 0 * inf: clamp; three equal roots cannot occur, see eigen_solve)
+    const float r10 = rcp_f32(fmaxf(g10, 1e-30f)), r20 = rcp_f32(g20), r21 = rcp_f32(fmaxf(g21, 1e-30f));
     const CplxF n1{e01.re * r10, e01.im * r10};
     const CplxF f02{e02.re * r20, e02.im * r20};
     const CplxF n2{(f02.re - n1.re) * r21, (f02.im - n1.im) * r21};
     // ---- diagonal
-#define PISAB_MP_DIAG(I, M, S)                                                              \
+#define PISAB_MP_DIAG(I, EA, S)                                                             \
     {                                                                                       \
-        const float ea = M - mu0, eb = M - mu1;                                             \
-        const float pp = fmaf(ea, eb, S);                                                   \
-        T[I][I] = CplxF{fmaf(n2.re, pp, fmaf(n1.re, ea, 1.0f)), fmaf(n2.im, pp, n1.im * ea)}; \
+        const float pp = fmaf(EA, EA - g10, S);                                             \
+        T[I][I] = CplxF{fmaf(n2.re, pp, fmaf(n1.re, EA, 1.0f)), fmaf(n2.im, pp, n1.im * EA)}; \
     }
-    PISAB_MP_DIAG(0, L.m0, L.s0)
-    PISAB_MP_DIAG(1, L.m1, L.s1)
-    PISAB_MP_DIAG(2, L.m2, L.s2)
+    PISAB_MP_DIAG(0, ea0, L.s0)
+    PISAB_MP_DIAG(1, ea1, L.s1)
+    PISAB_MP_DIAG(2, ea2, L.s2)
 #undef PISAB_MP_DIAG
     // ---- off-diagonal pairs: T_ij = h z + n2 c, T_ji = conj(h) z + n2 conj(c), z = n1 + n2 (mu2 - m_k)
-#define PISAB_MP_OFF(I, J, MK, HR, HI, C)                                    \
+#define PISAB_MP_OFF(I, J, EAK, HR, HI, C)                                   \
     {                                                                        \
-        const float u = mu2 - MK;                                            \
+        const float u = g20 - EAK;                                           \
         const float zr = fmaf(n2.re, u, n1.re), zi = fmaf(n2.im, u, n1.im);  \
         const float s1 = fmaf(HR, zr, n2.re * C.re);                         \
         const float s2 = fmaf(HI, zi, n2.im * C.im);                         \
@@ -159,9 +159,9 @@ __device__ __forceinline__ void assemble_transition_mp(const LayerMatF &L, const
         T[I][J] = CplxF{s1 - s2, s3 + s4};                                   \
         T[J][I] = CplxF{s1 + s2, s3 - s4};                                   \
     }
-    PISAB_MP_OFF(0, 1, L.m2, L.r01, L.i01, L.c01)
-    PISAB_MP_OFF(0, 2, L.m1, L.r02, L.i02, L.c02)
-    PISAB_MP_OFF(1, 2, L.m0, L.r12, L.i12, L.c12)
+    PISAB_MP_OFF(0, 1, ea2, L.r01, L.i01, L.c01)
+    PISAB_MP_OFF(0, 2, ea1, L.r02, L.i02, L.c02)
+    PISAB_MP_OFF(1, 2, ea0, L.r12, L.i12, L.c12)
 #undef PISAB_MP_OFF
 }
 
@@ -216,19 +216,66 @@ struct PropagatorF {
         const CplxF acc = cfmaf(L[r][2], R[c][2], cfmaf(L[r][1], R[c][1], cmulf(L[r][0], R[c][0])));
         return (double)fmaf(acc.re, acc.re, acc.im * acc.im);
     }
-    __device__ __forceinline__ void set_identity(bool right, bool left, int flav) {
-        if (right) {
+};
+
+// The same state in a per-thread column of shared memory, one (re, im) float2 per 64-bit access, [(v*3+k)][thread]:
+// the in-place vector updates of a loop-carried register state cost ~190 register moves per event (ncu, round 2),
+// the shared-memory form ~70 conflict-free LDS.64 / STS.64.  Vectors 0..NC-1 = columns of R, NC.. = rows of L.
+template <int NR, int NC>
+struct PropagatorSmemF {
+    static constexpr bool kF32 = true;
+    typedef CplxF cplx;
+    float2 *col; // &state[0][threadIdx.x]
+    int pitch;   // block size
+    static constexpr int kFloat2s = (NR + NC) * 3;
+
+    __device__ __forceinline__ CplxF ld(int v, int k) const {
+        const float2 z = col[(v * 3 + k) * pitch];
+        return CplxF{z.x, z.y};
+    }
+    __device__ __forceinline__ void st(int v, int k, CplxF z) { col[(v * 3 + k) * pitch] = make_float2(z.re, z.im); }
+    __device__ __forceinline__ void set_right(int c, int k, CplxF v) { st(c, k, v); }
+    __device__ __forceinline__ void init_right(const Mat3F T) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
+        for (int c = 0; c < NC; ++c)
 #pragma unroll
-                for (int k = 0; k < 3; ++k) R[c][k] = CplxF{c == k ? 1.0f : 0.0f, 0.0f};
+            for (int k = 0; k < 3; ++k) st(c, k, T[k][c]);
+    }
+    __device__ __forceinline__ void init_left(const Mat3F T, int flav) {
+        if (NR == 3) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) st(NC + r, c, T[r][c]);
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                CplxF v = T[0][c];
+                if (flav == 1) v = T[1][c];
+                if (flav == 2) v = T[2][c];
+                st(NC, c, v);
+            }
         }
-        if (left) {
+    }
+    __device__ __forceinline__ void mul_right(const Mat3F T) {
 #pragma unroll
-            for (int r = 0; r < NR; ++r)
+        for (int c = 0; c < NC; ++c) {
+            const CplxF r0 = ld(c, 0), r1 = ld(c, 1), r2 = ld(c, 2);
 #pragma unroll
-                for (int c = 0; c < 3; ++c) L[r][c] = CplxF{(NR == 3 ? r : flav) == c ? 1.0f : 0.0f, 0.0f};
+            for (int k = 0; k < 3; ++k) st(c, k, cfmaf(T[k][2], r2, cfmaf(T[k][1], r1, cmulf(T[k][0], r0))));
         }
+    }
+    __device__ __forceinline__ void mul_left(const Mat3F T) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) {
+            const CplxF l0 = ld(NC + r, 0), l1 = ld(NC + r, 1), l2 = ld(NC + r, 2);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) st(NC + r, c, cfmaf(l2, T[2][c], cfmaf(l1, T[1][c], cmulf(l0, T[0][c]))));
+        }
+    }
+    __device__ __forceinline__ double prob(int r, int c) const {
+        const CplxF acc = cfmaf(ld(NC + r, 2), ld(c, 2), cfmaf(ld(NC + r, 1), ld(c, 1), cmulf(ld(NC + r, 0), ld(c, 0))));
+        return (double)fmaf(acc.re, acc.re, acc.im * acc.im);
     }
 };
 
@@ -242,7 +289,7 @@ template <bool STD>
 struct H0MP {
     LayerMatF base; // STD: float image of H0c and its invariants; general: scratch
     Herm3 h;        // general: H0 = hv/E + lr in FP64 (STD: unused after init)
-    double c1_0, c0_0, d0c, m00; // STD only
+    double c1_0, c0_0, d0c, d1c, d2c, m00; // STD only
 
     __device__ __forceinline__ void init(const Herm3 &h0) {
         if (STD) {
@@ -251,9 +298,8 @@ struct H0MP {
             c.d0 -= tr3; c.d1 -= tr3; c.d2 -= tr3;
             double c2;
             char_poly(c, c2, c1_0, c0_0); // c2 == 0 up to rounding
-            d0c = c.d0;
+            d0c = c.d0; d1c = c.d1; d2c = c.d2;
             m00 = fma(c.d1, c.d2, -fma(c.r12, c.r12, c.i12 * c.i12));
-            base.m0 = (float)c.d0; base.m1 = (float)c.d1; base.m2 = (float)c.d2;
             base.r01 = (float)c.r01; base.i01 = (float)c.i01; base.r02 = (float)c.r02;
             base.i02 = (float)c.i02; base.r12 = (float)c.r12; base.i12 = (float)c.i12;
             layer_products(base);
@@ -272,12 +318,9 @@ struct H0MP {
             const double c1p = fma(-3.0 * y, y, c1);
             const double c0p = fma(y, fma(-2.0 * y, y, c1), c0);
             const RootsC R = eigen_roots_centered(c1p, c0p);
-            LayerMatF L = base;
-            const float yf = (float)y;
-            L.m0 = fmaf(2.0f, yf, base.m0);
-            L.m1 = base.m1 - yf;
-            L.m2 = base.m2 - yf;
-            assemble_transition_mp(L, R, t, T);
+            // diagonal of M: (d0c + 2y, d1c - y, d2c - y); its distance to mu0 in FP64, rounded once
+            const double o0 = fma(-2.0, y, R.m0), o12 = R.m0 + y;
+            assemble_transition_mp(base, (float)(d0c - o0), (float)(d1c - o12), (float)(d2c - o12), R, t, T);
         } else {
             Herm3 c = herm_axpy(rho, vm, h);
             const double tr3 = (c.d0 + c.d1 + c.d2) * kTab[16];
@@ -286,11 +329,10 @@ struct H0MP {
             char_poly(c, c2, c1, c0);
             const RootsC R = eigen_roots_centered(c1, c0);
             LayerMatF L;
-            L.m0 = (float)c.d0; L.m1 = (float)c.d1; L.m2 = (float)c.d2;
             L.r01 = (float)c.r01; L.i01 = (float)c.i01; L.r02 = (float)c.r02;
             L.i02 = (float)c.i02; L.r12 = (float)c.r12; L.i12 = (float)c.i12;
             layer_products(L);
-            assemble_transition_mp(L, R, t, T);
+            assemble_transition_mp(L, (float)(c.d0 - R.m0), (float)(c.d1 - R.m0), (float)(c.d2 - R.m0), R, t, T);
         }
     }
 };
@@ -302,13 +344,13 @@ __device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, 
     const CplxF z2 = expm1i_neg(-o.hdm21 * ts), z3 = expm1i_neg(-o.hdm31 * ts);
     // vacuum_columns uses (cos - 1, +sin) of (hdm * ts): exp(+i hdm ts) - 1 = expm1i_neg(-hdm ts)
     const float z2r = z2.re, z2i = z2.im, z3r = z3.re, z3i = z3.im;
-    const Herm3 &A = o.pr2, &B = o.pr3;
+    const Herm3F &A = o.pr2f, &B = o.pr3f;
 #define PISAB_VAC_DIAG(C, DA, DB) \
-    P.set_right(C, C, CplxF{fmaf(z2r, (float)DA, fmaf(z3r, (float)DB, 1.0f)), fmaf(z2i, (float)DA, z3i * (float)DB)});
+    P.set_right(C, C, CplxF{fmaf(z2r, DA, fmaf(z3r, DB, 1.0f)), fmaf(z2i, DA, z3i * DB)});
 #define PISAB_VAC_OFF(I, J, AR, AI, BR, BI)                                                                   \
     {                                                                                                         \
-        const float xr = fmaf(z2r, (float)AR, z3r * (float)BR), xi = fmaf(z2i, (float)AR, z3i * (float)BR);     \
-        const float yr = fmaf(z2r, (float)AI, z3r * (float)BI), yi = fmaf(z2i, (float)AI, z3i * (float)BI);     \
+        const float xr = fmaf(z2r, AR, z3r * BR), xi = fmaf(z2i, AR, z3i * BR);                                 \
+        const float yr = fmaf(z2r, AI, z3r * BI), yi = fmaf(z2i, AI, z3i * BI);                                 \
         if (J < NC) P.set_right(J, I, CplxF{xr - yi, xi + yr});                                               \
         if (I < NC) P.set_right(I, J, CplxF{xr + yi, xi - yr});                                               \
     }

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib, ops
-from .distributed import combine_histograms, shard_slice  # noqa: F401  (shard_slice re-exported)
+from .distributed import combine_histograms, event_sharding, shard_slice  # noqa: F401  (shard_slice re-exported)
 
 _NP2T = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32}
 
@@ -141,11 +141,12 @@ class ReweightEngine:
                 self._batches.append((lo, ops.TemplateBatch(desc, self.n_bins)))
         return self._batches
 
-    def evaluate(self, consts, allreduce=True, events=None):
+    def evaluate(self, consts, allreduce=None, events=None):
         """Resident mode: all event arrays already in HBM.  ONE fused launch for all containers
         (+ one reduction of the per-block partial histograms).  Returns [n_containers, 2, n_bins].
         ``events``: optional list that receives one (start, stop) CUDA-event pair per fused
         launch (for the roofline timing in bench.py)."""
+        allreduce = self._want_exchange(allreduce)
         out = self._result_buffer()
         if self.n_bins > _lib.DET_MAX_BINS:
             return self._evaluate_unfused(consts, out, allreduce)
@@ -179,21 +180,36 @@ class ReweightEngine:
             self.allreduce(out)
         return out
 
-    def evaluate_many(self, consts_list, allreduce=True):
+    def evaluate_many(self, consts_list, allreduce=None):
         """P hypotheses in ONE launch (``pisab_reweight_hist_scan``): returns ``[P, n_containers, 2, n_bins]``.
         The single histogram exchange covers all P templates when sharded over GPUs."""
         batches = self._get_batches()
         if len(batches) != 1:
             raise NotImplementedError("evaluate_many supports up to %d containers" % ops.MAX_BATCH)
         out = ops.reweight_hist_scan(consts_list, self.earth, batches[0][1])
-        if allreduce:
+        if self._want_exchange(allreduce):
             self.allreduce(out)
         return out
 
-    def evaluate_host(self, consts, allreduce=True):
+    def evaluate_host(self, consts, allreduce=None, changed=None):
         """Host mode: event arrays live in pinned host memory; every call copies them to the
         device (double-buffered on a copy stream so the copy of container i+1 overlaps the
-        kernel of container i) and returns the histograms as a HOST numpy array."""
+        kernel of container i) and returns the histograms as a HOST numpy array.
+
+        ``changed``: None = every array travels on every call (44 B/event in FP64, 41 with the packed bin index);
+        or a tuple of keys (e.g. ``("weights", "nu_flux")``, the only arrays a fit changes between templates): the
+        other arrays are uploaded ONCE on the first such call and stay resident, so a call moves 24 B/event."""
+        if changed is not None:
+            changed = tuple(changed)
+            unknown = [k for k in changed if k not in EVENT_KEYS]
+            if unknown:
+                raise ValueError("unknown event arrays %s (known: %s)" % (unknown, ", ".join(EVENT_KEYS)))
+            for blk in self.blocks:
+                for k in EVENT_KEYS:
+                    if k not in changed and k not in blk.dev:
+                        src = blk.host["index_u8"] if (k == "index" and blk.pack_index) else blk.host[k]
+                        t = src.to(self.device, non_blocking=True)
+                        blk.dev[k] = (t.to(torch.int32) - 1) if (k == "index" and blk.pack_index) else t
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         out = self._result_buffer()
@@ -224,6 +240,9 @@ class ReweightEngine:
                 self._copy_stream.wait_event(self._stage_free[s])
                 views = {}
                 for k in EVENT_KEYS:
+                    if changed is not None and k not in changed:
+                        views[k] = blk.dev[k]          # resident static array
+                        continue
                     packed = k == "index" and blk.pack_index
                     src = blk.host["index_u8" if packed else k]
                     dst = st[k][:blk.n]
@@ -238,17 +257,17 @@ class ReweightEngine:
                     h2d += src.numel() * src.element_size()
                 self._stage_ready[s].record(self._copy_stream)
             main.wait_event(self._stage_ready[s])
-            batch = self._host_batches.get((i, s))
+            batch = self._host_batches.get((i, s, changed))
             if batch is None:
                 scales = getattr(self, "scales", None) or [1.0] * len(self.blocks)
                 batch = ops.TemplateBatch([dict(nubar=blk.nubar, flav=blk.flav, energy=views["true_energy"],
                                                 coszen=views["true_coszen"], nu_flux=views["nu_flux"],
                                                 weights=views["weights"], index=views["index"],
                                                 scale=scales[i])], self.n_bins)
-                self._host_batches[(i, s)] = batch
+                self._host_batches[(i, s, changed)] = batch
             ops.reweight_hist_batch(consts, self.earth, batch, out=out[i:i + 1])
             self._stage_free[s].record(main)
-        if allreduce:
+        if self._want_exchange(allreduce):
             self.allreduce(out)
         if self._host_out is None or self._host_out.shape != out.shape:
             self._host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
@@ -257,6 +276,13 @@ class ReweightEngine:
         self.last_h2d_bytes = h2d
         self.last_d2h_bytes = out.numel() * out.element_size()
         return self._host_out.numpy()
+
+    @staticmethod
+    def _want_exchange(allreduce):
+        """``allreduce=None`` (default) exchanges exactly when the events are sharded over the ranks
+        (``pisa_b200.distributed.enable_event_sharding``): a process group initialised for another purpose must not
+        silently sum histograms across ranks.  True / False force it."""
+        return event_sharding() if allreduce is None else bool(allreduce)
 
     def allreduce(self, buf):
         """Sum the per-GPU histograms: the single exchange step per template (no-op on one rank)."""

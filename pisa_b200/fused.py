@@ -76,7 +76,7 @@ class FusedPipeline:
                 engine = ReweightEngine(earth, self.binning.size, np.float64 if w.dtype == torch.float64 else np.float32,
                                         w.device)
             engine.add_container(c.name, int(c["nubar"]), int(c["flav"]), c["true_energy"], c["true_coszen"],
-                                 c["nu_flux"], w.contiguous(), c.bin_index(self.binning))
+                                 c["nu_flux"], w.contiguous(), c.bin_index(self.binning, "hist"))
         self._engine = engine
         self._pre_hash = self._inputs_hash()
 

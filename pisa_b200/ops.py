@@ -275,7 +275,52 @@ def apply_osc_weights(nu_flux, prob_e, prob_mu, weights):
     return weights
 
 
+def scale_weights(weights, factor, scale):
+    """In place ``weights *= factor * scale`` (aeff.aeff, pisa/stages/aeff/aeff.py:68-88); ``factor`` may be None."""
+    _chk(weights, "weights")
+    dt = weights.dtype
+    _chk(factor, "factor", dt, allow_none=True)
+    n = weights.numel()
+    if factor is not None and factor.numel() != n:
+        raise ValueError("factor and weights must have the same length")
+    _lib.check(_lib.fn("pisab_scale_weights", dt)(_ptr(factor), float(scale), n, _ptr(weights), _stream()))
+    return weights
+
+
 # -------------------------------------------------------------------------- histogram -----
+
+def joint_index(index_a, index_b, size_b, out=None):
+    """Flat index on the joint binning a + b from the two sub-indices (-1 where either is outside)."""
+    _chk(index_a, "index_a", torch.int32)
+    _chk(index_b, "index_b", torch.int32)
+    n = index_a.numel()
+    if index_b.numel() != n:
+        raise ValueError("the two indices must have the same length")
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=index_a.device)
+    _chk(out, "out", torch.int32)
+    _lib.check(_lib.load().pisab_joint_index(_ptr(index_a), _ptr(index_b), int(size_b), n, _ptr(out), _stream()))
+    return out
+
+
+def hist_transform(weights, unc, transform, want_errors=True):
+    """``utils.hist`` with a binned calc_mode (hist.py:131-160): returns float64 (hist, sumw2, bin_unc2) with
+    hist = (unc w) @ T etc.; ``unc`` may be None; the last two are None unless ``want_errors``."""
+    _chk(weights, "weights")
+    dt = weights.dtype
+    _chk(unc, "unc", dt, allow_none=True)
+    _chk(transform, "transform", dt)
+    n_calc = weights.numel()
+    if transform.dim() != 2 or transform.shape[0] != n_calc or (unc is not None and unc.numel() != n_calc):
+        raise ValueError("transform must be [n_calc, n_out] with one weight per calc bin")
+    n_out = transform.shape[1]
+    mk = lambda: torch.empty(n_out, dtype=torch.float64, device=weights.device)  # noqa: E731
+    h = mk()
+    s2, b2 = (mk(), mk()) if want_errors else (None, None)
+    _lib.check(_lib.fn("pisab_hist_transform", dt)(_ptr(weights), _ptr(unc), _ptr(transform), n_calc, n_out, _ptr(h),
+                                                  _ptr(s2), _ptr(b2), _stream()))
+    return h, s2, b2
+
 
 def make_binning(dims, device):
     """dims: list of dicts {kind: 'lin'|'log'|'edges', n_bins, lo, hi, edges}.  For 'log', lo/hi

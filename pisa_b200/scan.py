@@ -161,13 +161,20 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
     # the minimiser works in units of `scale` so that angles (~1) and mass splittings (~1e-3) are comparable
     scale = np.where(x0 != 0.0, np.abs(x0), 1.0)
     h = np.array([float((steps or {}).get(nm, 1e-4 * s)) for nm, s in zip(names, scale)])
-    lo = np.array([(bounds or {}).get(nm, (-np.inf, np.inf))[0] for nm in names], dtype=np.float64)
-    hi = np.array([(bounds or {}).get(nm, (-np.inf, np.inf))[1] for nm in names], dtype=np.float64)
+    # physical domains the host-side parameter code enforces (osc_params.py: deltacp in [0, 2 pi]): a stencil point or a
+    # minimiser step outside would abort the fit with an AssertionError, so they act as default bounds
+    domain = {"deltacp": (0.0, 2 * np.pi)}
+    def _bound(nm, k):
+        user = (bounds or {}).get(nm, (-np.inf, np.inf))[k]
+        dom = domain.get(nm, (-np.inf, np.inf))[k]
+        return max(user, dom) if k == 0 else min(user, dom)
+    lo = np.array([_bound(nm, 0) for nm in names], dtype=np.float64)
+    hi = np.array([_bound(nm, 1) for nm in names], dtype=np.float64)
     out = torch.empty(2 * k + 1, dtype=torch.float64, device=engine.device)
     counter = [0]
 
     def objective(u):
-        x = u * scale
+        x = np.clip(u * scale, lo, hi)
         pts = np.repeat(x[None, :], 2 * k + 1, axis=0)
         for i in range(k):
             # one-sided at a bound: keep both stencil points inside it
@@ -184,7 +191,8 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
         return float(c[0]), grad * scale
 
     res = optimize.minimize(objective, x0 / scale, jac=True, method=method,
-                            bounds=list(zip(lo / scale, hi / scale)) if bounds else None, options=options)
+                            bounds=list(zip(lo / scale, hi / scale)) if np.isfinite(np.concatenate([lo, hi])).any() else None,
+                            options=options)
     res.x = {nm: float(v) for nm, v in zip(names, res.x * scale)}
     res.n_templates = counter[0]
     return res

@@ -1,8 +1,10 @@
 """``aeff.aeff`` service: ``weights *= weighted_aeff * livetime * norms`` (pisa/stages/aeff/aeff.py:22-88).
 
-A "next" row of the scope table: one multiply per event.  It runs as a single
-in-place device operation through torch (plumbing) until it is folded into the fused kernel.
+A "next" row of the scope table: one multiply per event, ``pisab_scale_weights`` (24 B/event,
+HBM-bound); in the fit loop the per-event factor is folded into the weights once and the scalar part travels as the
+per-container ``scale`` of the fused kernel (``pisa_b200.fused``).
 """
+from pisa_b200 import ops
 from pisa_b200.core.stage import Stage
 
 __all__ = ["aeff"]
@@ -28,6 +30,5 @@ class aeff(Stage):  # pylint: disable=invalid-name
 
     def apply_function(self):
         for container in self.data:
-            w = container["weights"]
-            w *= container["weighted_aeff"] * self.container_scale(container.name)
+            ops.scale_weights(container["weights"], container["weighted_aeff"], self.container_scale(container.name))
             container.mark_changed("weights")

@@ -42,18 +42,28 @@ class hist(Stage):  # pylint: disable=invalid-name
         if isinstance(self.calc_mode, MultiDimBinning):
             # the two binnings must be exclusive (hist.py:71-72)
             assert len(set(self.calc_mode.names) & set(self.apply_mode.names)) == 0
-            transform_binning = self.calc_mode + self.apply_mode
+            # event counts on the joint binning calc_mode + apply_mode (hist.py:73-84): the joint flat index comes from
+            # the two cached sub-indices, so the usual 2 + 3 dimensional layout is not limited by PISAB_MAX_DIMS.
+            # Both sub-indices follow the edge rule of the reference's histogram on the joint binning
+            # (translation.histogram: fast_histogram for linear dimensions, np.histogramdd otherwise).
+            n_joint = self.calc_mode.size * self.apply_mode.size
+            if n_joint > 2 ** 31 - 1:
+                raise ValueError("hist_transform of %d x %d bins exceeds the 32-bit bin index"
+                                 % (self.calc_mode.size, self.apply_mode.size))
+            joint_dims = list(self.calc_mode) + list(self.apply_mode)
+            policy = "edges" if any(d.is_irregular or d.is_log for d in joint_dims) else "generic"
             for container in self.data:
                 container.representation = "events"
-                counts, _ = ops.hist_accumulate(container.bin_index(transform_binning), None, transform_binning.size,
-                                                want_w2=False)
+                joint = ops.joint_index(container.bin_index(self.calc_mode, policy),
+                                        container.bin_index(self.apply_mode, policy), self.apply_mode.size)
+                counts, _ = ops.hist_accumulate(joint, None, n_joint, want_w2=False)
                 container.representation = self.calc_mode
                 container["hist_transform"] = counts.reshape(self.calc_mode.size, self.apply_mode.size)
             return
         # regularised binning + static per-event bin index (hist.py:86-127; cached on the container)
         self.data["regularized_output_binning"] = self.apply_mode
         for container in self.data:
-            container.bin_index(self.apply_mode)
+            container.bin_index(self.apply_mode, "hist")
 
     def _apply_transform(self):
         """calc_mode binned: hist = (unc * w) @ hist_transform (hist.py:131-160)."""
@@ -65,13 +75,9 @@ class hist(Stage):  # pylint: disable=invalid-name
             weights = container["weights"]
             if "astro_weights" in container.keys:
                 weights = weights + container["astro_weights"]
-            unc = container["unc_weights"] if self.apply_unc_weights else torch.ones_like(weights)
-            transform = container["hist_transform"]
-            h = (unc * weights) @ transform
-            sumw2 = bin_unc2 = None
-            if self.error_method == "sumw2":
-                sumw2 = torch.square(unc * weights) @ transform
-                bin_unc2 = (torch.square(unc) * weights) @ transform
+            unc = container["unc_weights"] if self.apply_unc_weights else None
+            h, sumw2, bin_unc2 = ops.hist_transform(weights.contiguous(), unc, container["hist_transform"],
+                                                    want_errors=self.error_method == "sumw2")
             local.append((container, h, sumw2, bin_unc2))
         self._write(self._exchange(local), revalidate_events=False)
 
@@ -105,7 +111,7 @@ class hist(Stage):  # pylint: disable=invalid-name
         local = []
         for container in self.data:
             container.representation = "events"
-            idx = container.bin_index(self.apply_mode)
+            idx = container.bin_index(self.apply_mode, "hist")
             weights = container["weights"]
             if "astro_weights" in container.keys:
                 weights = weights + container["astro_weights"]
@@ -120,7 +126,7 @@ class hist(Stage):  # pylint: disable=invalid-name
             want_w2 = self.error_method == "sumw2"
             h, h2 = ops.hist_accumulate(idx, weights, n_bins, want_w2=want_w2)
             if want_w2 and bin_unc2 is None:
-                bin_unc2 = h   # unc_weights == 1: sum(unc^2 * w) == sum(w)
+                bin_unc2 = h.clone()   # unc_weights == 1: sum(unc^2 * w) == sum(w); its own array, like the reference's
             local.append((container, h, h2, bin_unc2))
         self._write(self._exchange(local), revalidate_events=True)
 

@@ -24,6 +24,8 @@ using std::fma; using std::fmax; using std::fmin; using std::rint; using std::sq
 static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 #define __sincosf pisab_emu_sincosf
 struct double2 { double x, y; };
+struct float2 { float x, y; };
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #include <cstring>
 static inline int __double2loint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b & 0xffffffffull); }
