@@ -59,7 +59,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // MP = the FP32 mode's mixed-precision arithmetic (prob3_mp.cuh): state and per-event Hamiltonian in registers, so
 // the dynamic shared memory shrinks to the two staging slots per thread.
 #ifndef PISAB_MP_MIN_BLOCKS
-#define PISAB_MP_MIN_BLOCKS 2
+#define PISAB_MP_MIN_BLOCKS 3
 #endif
 template <bool FULL>
 static size_t earth_smem_bytes(size_t io_bytes, bool std_matter, bool mp = false) {

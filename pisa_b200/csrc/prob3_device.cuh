@@ -169,38 +169,39 @@ __device__ __forceinline__ void sincos_small(double x, double *sn, double *cs) {
 //     d = Im(z conj(w^3)) / 3 ,  w <- w (1 - d^2/2 + i d)
 // which leaves an error ~1.5 d^3 ~ 1e-18.  The conditioning of the eigenvalues sits entirely in
 // (zr, zi), not in this step.
-__device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_out, double *s_out) {
+__device__ __forceinline__ void unit_cube_root_seed(double zr, double zi, float *c_seed, float *s_seed) {
     // (zr, zi) is already of unit modulus (up to rounding): the caller scales by p^(-3/2), because
     // q^2 + (p^3 - q^2) = p^3 -- no second rsqrt here.  A modulus error delta only enters the
     // correction step as delta * d ~ 1e-23.
     // float seed of theta = atan2(zi, zr) / 3, zi >= 0, good to ~5e-7 rad: octant reduction, a degree-6
     // minimax polynomial for atan(t)/t on [0, 1] (5.5e-7), then sin / cos polynomials valid on [0, pi/3]
     // (no range reduction needed) -- 27 instructions instead of the 45 of atan2f + __sincosf.
-    float sf, cf;
-    {
-        const float x = (float)zr, y = (float)zi;
-        const float ax = fabsf(x);
-        const float mx = fmaxf(ax, y), mn = fminf(ax, y);
+    const float x = (float)zr, y = (float)zi;
+    const float ax = fabsf(x);
+    const float mx = fmaxf(ax, y), mn = fminf(ax, y);
 #ifdef PISAB_HOST_EMU
-        const float t = mn / mx;
+    const float t = mn / mx;
 #else
-        const float t = __fdividef(mn, mx);
+    const float t = __fdividef(mn, mx);
 #endif
-        const float u = t * t;
-        float a = fmaf(u, 0.00782548263669014f, -0.03689862787723541f);
-        a = fmaf(u, a, 0.08374155312776566f);
-        a = fmaf(u, a, -0.13480405509471893f);
-        a = fmaf(u, a, 0.19879871606826782f);
-        a = fmaf(u, a, -0.3332637548446655f);
-        a = fmaf(u, a, 0.9999993443489075f) * t;
-        a = y > ax ? 1.57079632679489662f - a : a;
-        a = x < 0.0f ? 3.14159265358979324f - a : a;
-        const float th = a * (1.0f / 3.0f), v = th * th;
-        sf = th * fmaf(v, fmaf(v, fmaf(v, -0.00019222621631342918f, 0.008328950963914394f), -0.1666656732559204f),
-                       0.9999999403953552f);
-        cf = fmaf(v, fmaf(v, fmaf(v, -0.0013333901297301054f, 0.041627395898103714f), -0.4999910891056061f),
-                  0.9999997019767761f);
-    }
+    const float u = t * t;
+    float a = fmaf(u, 0.00782548263669014f, -0.03689862787723541f);
+    a = fmaf(u, a, 0.08374155312776566f);
+    a = fmaf(u, a, -0.13480405509471893f);
+    a = fmaf(u, a, 0.19879871606826782f);
+    a = fmaf(u, a, -0.3332637548446655f);
+    a = fmaf(u, a, 0.9999993443489075f) * t;
+    a = y > ax ? 1.57079632679489662f - a : a;
+    a = x < 0.0f ? 3.14159265358979324f - a : a;
+    const float th = a * (1.0f / 3.0f), v = th * th;
+    *s_seed = th * fmaf(v, fmaf(v, fmaf(v, -0.00019222621631342918f, 0.008328950963914394f), -0.1666656732559204f),
+                        0.9999999403953552f);
+    *c_seed = fmaf(v, fmaf(v, fmaf(v, -0.0013333901297301054f, 0.041627395898103714f), -0.4999910891056061f),
+                   0.9999997019767761f);
+}
+__device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_out, double *s_out) {
+    float sf, cf;
+    unit_cube_root_seed(zr, zi, &cf, &sf);
     const double c = (double)cf, s = (double)sf;
     // u = (c, s) has |u|^2 = 1 + m, m ~ 1e-7.  The normalisation (1+m)^(-1/2) = rho and the angle
     // correction are evaluated as two independent chains (depth 9 instead of 15):
@@ -215,6 +216,21 @@ __device__ __forceinline__ void unit_cube_root(double zr, double zi, double *c_o
     const double k = fma(-0.5 * d, d, 1.0);
     *c_out = fma(cr, k, -sr * d);
     *s_out = fma(sr, k, cr * d);
+}
+// FP32-mode variant: first-order angle correction and first-order normalisation, w' = (1 - m/2) u (1 + i d).  The
+// neglected terms are d^2 / 2 ~ 1e-13 and 3 m^2 / 8 ~ 4e-15 -- far below the 1e-9 the eigenvalue gaps need there.
+__device__ __forceinline__ void unit_cube_root_mp(double zr, double zi, double *c_out, double *s_out) {
+    float sf, cf;
+    unit_cube_root_seed(zr, zi, &cf, &sf);
+    const double c = (double)cf, s = (double)sf;
+    const double m = fma(c, c, fma(s, s, -1.0));
+    const double rho = fma(m, -0.5, 1.0);
+    const double third = fma(m, -0.5, kTab[16]);
+    const double u2r = fma(c, c, -s * s), u2i = 2.0 * c * s;
+    const double u3r = fma(u2r, c, -u2i * s), u3i = fma(u2r, s, u2i * c);
+    const double d = fma(zi, u3r, -zr * u3i) * third;
+    *c_out = fma(-s, d, c) * rho;
+    *s_out = fma(c, d, s) * rho;
 }
 
 // H = hv * inv_e + lr   (per event), then + rho * vm per layer

@@ -93,7 +93,7 @@ __device__ __forceinline__ RootsC eigen_roots_centered(double c1, double c0) {
     const double b = kTab[17] * (p * rs);
     const double inv = rs * rs * rs;
     double st, ct;
-    unit_cube_root(q * inv, sqrt_pos(disc) * inv, &ct, &st);
+    unit_cube_root_mp(q * inv, sqrt_pos(disc) * inv, &ct, &st);
     const double kh = 0.5, ks = kTab[15];
     RootsC r;
     r.m0 = b * (-kh * ct - ks * st);

@@ -11,8 +11,13 @@ histogram stage (``discr_sys.hypersurfaces``) -- and replaces exactly that segme
 same ``MapSet`` as ``Pipeline.get_outputs()`` (tests: 1e-10 relative).
 
 Supported shape (checked at construction, ``NotImplementedError`` otherwise): ``osc.prob3`` in events mode, then
-optionally ``aeff.aeff``, then ``utils.hist`` with ``calc_mode = events`` and ``error_method = sumw2`` or None,
-without ``unc_weights`` / ``astro_weights`` / ``unweighted``; any stages before and after.
+optionally ``aeff.aeff``, then ``utils.hist`` with ``calc_mode = events`` and ``error_method = sumw2`` or None; any
+stages before and after.  ``utils.hist``'s options (hist.py:141-145,198-209) map onto the fused kernel like this:
+  * ``apply_unc_weights``: hist = sum(unc w), sumw2 = sum((unc w)^2) come from one launch over the weights ``unc * w0``;
+    ``bin_unc2 = sum(unc^2 w)`` is the "sum w" plane of a second launch over ``unc^2 * w0`` (only with sumw2 errors);
+  * ``unweighted``: the weights are ones, nothing has to be propagated: one pass of the histogram kernel per container;
+  * ``astro_weights`` (an additive per-event term no stage of this package produces): not fused --
+    ``NotImplementedError``, ``DistributionMaker`` then evaluates the pipeline stage by stage.
 """
 import numpy as np
 import torch
@@ -44,14 +49,15 @@ class FusedPipeline:
         self.hist, self.post = rest[0], rest[1:]
         if self.osc.calc_mode != "events" or self.osc.apply_mode != "events":
             raise NotImplementedError("FusedPipeline: osc.prob3 must calculate and apply in events mode")
-        if self.hist.calc_mode != "events" or self.hist.apply_unc_weights or self.hist.unweighted:
-            raise NotImplementedError("FusedPipeline: utils.hist must histogram plain event weights")
+        if self.hist.calc_mode != "events":
+            raise NotImplementedError("FusedPipeline: utils.hist must histogram events (calc_mode = events)")
         if self.hist.error_method not in (None, "sumw2"):
             raise NotImplementedError("FusedPipeline: error_method must be None or sumw2")
         pipeline.run()                       # set-up of every stage, bin indices, first template the staged way
         self.binning = self.hist.apply_mode
         assert isinstance(self.binning, MultiDimBinning)
         self._engine = None
+        self._engine_unc2 = None             # second engine (weights unc^2 * w0) for bin_unc2 with unc_weights
         self._pre_hash = None
         self._scales = None
 
@@ -63,7 +69,8 @@ class FusedPipeline:
         data = self.pipeline.data
         for stage in self.pre:               # loaders reset `weights`, flux stages write `nu_flux`
             stage.run()
-        engine = None
+        engine = engine2 = None
+        want_unc2 = self.hist.apply_unc_weights and self.hist.error_method == "sumw2"
         self._containers = list(data.containers)
         for c in self._containers:
             c.representation = "events"
@@ -73,14 +80,42 @@ class FusedPipeline:
             if self.aeff is not None:
                 w = w * c["weighted_aeff"]   # the per-event part of aeff.aeff; its scalar part goes in as `scale`
             if engine is None:
-                engine = ReweightEngine(earth, self.binning.size, np.float64 if w.dtype == torch.float64 else np.float32,
-                                        w.device)
-            engine.add_container(c.name, int(c["nubar"]), int(c["flav"]), c["true_energy"], c["true_coszen"],
-                                 c["nu_flux"], w.contiguous(), c.bin_index(self.binning, "hist"))
-        self._engine = engine
+                dt = np.float64 if w.dtype == torch.float64 else np.float32
+                engine = ReweightEngine(earth, self.binning.size, dt, w.device)
+                engine2 = ReweightEngine(earth, self.binning.size, dt, w.device) if want_unc2 else None
+            idx = c.bin_index(self.binning, "hist")
+            unc = c["unc_weights"] if self.hist.apply_unc_weights else None
+            args = (c.name, int(c["nubar"]), int(c["flav"]), c["true_energy"], c["true_coszen"], c["nu_flux"])
+            engine.add_container(*args, (w if unc is None else unc * w).contiguous(), idx)
+            if want_unc2:
+                engine2.add_container(*args, (unc * unc * w).contiguous(), idx)
+        self._engine, self._engine_unc2 = engine, engine2
         self._pre_hash = self._inputs_hash()
 
+    def _evaluate_unweighted(self):
+        """``unweighted`` (hist.py:141-145): weights of one -- times ``unc_weights`` if asked for -- so the oscillation
+        stage does not enter; [containers, 3, bins] = (sum, sumw2, bin_unc2) from the histogram kernel alone."""
+        from pisa_b200 import ops
+        from pisa_b200.distributed import combine_histograms
+        for stage in self.pre:
+            stage.run()
+        data = self.pipeline.data
+        self._containers = list(data.containers)
+        rows = []
+        for c in self._containers:
+            c.representation = "events"
+            idx = c.bin_index(self.binning, "hist")
+            unc = c["unc_weights"].contiguous() if self.hist.apply_unc_weights else None
+            h, h2 = ops.hist_accumulate(idx, unc, self.binning.size)
+            rows.append(torch.stack([h, h2, h2]))            # w = unc: sum (unc w)^2 == sum unc^2 w == sum unc^2
+        out = torch.stack(rows)
+        if event_sharding():
+            combine_histograms(out)
+        return out
+
     def _evaluate(self):
+        if self.hist.unweighted:
+            return self._evaluate_unweighted()
         consts, earth = self.osc.update_hypothesis()
         if self._engine is None or self._inputs_hash() != self._pre_hash:
             self._build_engine(earth)
@@ -91,8 +126,15 @@ class FusedPipeline:
             if scales != self._scales:
                 self._engine.set_scales(scales)
                 self._scales = scales
+                if self._engine_unc2 is not None:
+                    self._engine_unc2.set_scales(scales)
         # [containers, 2, bins], one launch; one exchange when the loaders sharded the events over GPUs
-        return self._engine.evaluate(consts, allreduce=event_sharding())
+        out = self._engine.evaluate(consts, allreduce=event_sharding())
+        if self._engine_unc2 is None:
+            return out
+        self._engine_unc2.earth = earth
+        unc2 = self._engine_unc2.evaluate(consts, allreduce=event_sharding())
+        return torch.cat([out, unc2[:, :1]], dim=1)          # [containers, 3, bins]: sum, sumw2, bin_unc2
 
     def run(self):
         """Like ``Pipeline.run()``: afterwards the containers hold the binned ``weights`` (and ``errors``,
@@ -105,11 +147,14 @@ class FusedPipeline:
             c["weights"] = out[i, 0]
             if want_w2:
                 c["errors"] = errors[i]
-                c["bin_unc2"] = out[i, 0].clone()            # unc_weights == 1: sum(unc^2 w) == sum(w)
+                # (without unc_weights: sum(unc^2 w) == sum(w))
+                c["bin_unc2"] = (out[i, 2] if out.shape[1] > 2 else out[i, 0]).clone()
         for stage in self.post:
             stage.run()
 
-    def get_outputs(self):
+    def get_outputs(self, output_binning=None, output_key=None):
+        if output_binning is not None or output_key is not None:
+            raise NotImplementedError("FusedPipeline.get_outputs: use the pipeline's own output_binning / output_key")
         key = self.pipeline.output_key
         error = key[1] if isinstance(key, tuple) else None
         name = key[0] if isinstance(key, tuple) else key

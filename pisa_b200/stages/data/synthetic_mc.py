@@ -18,8 +18,9 @@ __all__ = ["synthetic_mc"]
 
 
 class synthetic_mc(Stage):  # pylint: disable=invalid-name
-    def __init__(self, output_names, **std_kwargs):
+    def __init__(self, output_names, unc_weights=False, **std_kwargs):
         self.output_names = output_names
+        self.with_unc_weights = bool(unc_weights)   # also provide `unc_weights` ~ U(0.5, 1.5) (utils.hist apply_unc_weights)
         super().__init__(expected_params=("n_events", "seed"), expected_container_keys=(),
                          supported_reps={"calc_mode": ["events"], "apply_mode": ["events"]}, **std_kwargs)
 
@@ -44,6 +45,12 @@ class synthetic_mc(Stage):  # pylint: disable=invalid-name
             container["nu_flux_nominal"] = ev["nu_flux"]
             container["nubar_flux_nominal"] = (ev["nu_flux"] * 0.8).contiguous()
             container["weighted_aeff"] = ev["weights"]
+            if self.with_unc_weights:
+                import torch
+                g = torch.Generator(device=dev)
+                g.manual_seed(seed + 100_003 + i)
+                container["unc_weights"] = (0.5 + torch.rand(n_events_local, generator=g, device=dev,
+                                                             dtype=torch.float64)).to(ev["weights"].dtype)
             container["initial_weights"] = ev["weights"].new_ones(n_events_local)
             container["weights"] = ev["weights"].new_ones(n_events_local)
             container.set_aux_data("nubar", nubar)

@@ -84,6 +84,12 @@ def _clip_in_storage_type(ev, minimum, ftype):
     top_cz = float(np.nextafter(np.float32(1.0), np.float32(0)))
     ev["reco_energy"] = minimum(ev["reco_energy"], ev["reco_energy"] * 0 + top_e)
     ev["reco_coszen"] = minimum(ev["reco_coszen"], ev["reco_coszen"] * 0 + top_cz)
+    # ... and the LOWER energy edge rounds DOWN in float32 (5.62341309 < 5.62341325): every event clipped onto it
+    # would fall out of the binning in FP32 mode only.  Clip to the smallest float32 not below the edge.
+    lo32 = np.float32(DRAGON_E_EDGES[0])
+    if float(lo32) < float(DRAGON_E_EDGES[0]):
+        lo32 = np.nextafter(lo32, np.float32(np.inf))
+    ev["reco_energy"] = -minimum(-ev["reco_energy"], ev["reco_energy"] * 0 - float(lo32))
 
 
 def make_events_torch(n, seed, dtype, device):

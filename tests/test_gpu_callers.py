@@ -1,0 +1,196 @@
+"""GPU tests of the callers and loaders around the hot path (SURVEY 8f.4 and the fit-loop caller of 3.5):
+``data.simple_data_loader``, ``DistributionMaker.get_outputs(return_sum=True)``, and ``utils.hist``'s
+``apply_unc_weights`` / ``unweighted`` options through the fused template kernel."""
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from conftest import ROOT  # noqa: E402
+
+CFG_DIR = os.path.join(ROOT, "pisa_b200", "resources", "settings", "pipeline")
+NAMES = ["nue_cc", "numu_cc", "nutau_cc", "nue_nc", "numu_nc", "nutau_nc", "nuebar_cc", "numubar_cc", "nutaubar_cc",
+         "nuebar_nc", "numubar_nc", "nutaubar_nc"]
+
+
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _events_cfg(tmp_path, loader_section, hist_extra="", order_head="data.simple_data_loader"):
+    base = open(os.path.join(CFG_DIR, "b200_events.cfg")).read()
+    head, rest = base.split("[data.synthetic_mc]")
+    rest = rest[rest.index("[osc.prob3]"):]
+    text = head.replace("data.synthetic_mc", order_head) + loader_section + "\n" + rest
+    if hist_extra:
+        text = text.replace("error_method = sumw2", "error_method = sumw2\n" + hist_extra)
+    cfg = tmp_path / "pipeline.cfg"
+    cfg.write_text(text)
+    return str(cfg)
+
+
+def test_simple_data_loader_pipeline_matches_oracle_chain(tmp_path):
+    """data.simple_data_loader (PISA-style events file in the .npz layout, variable mapping with a stacked flux,
+    mc_cuts, down-sampling) -> osc.prob3 -> aeff.aeff -> utils.hist, against the oracle chain on the loaded events."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.stages.data.simple_data_loader import apply_cut, load_events
+    from pisa_b200.utils import synthetic as syn
+    rng = np.random.default_rng(11)
+    arrays = {}
+    for name in NAMES:
+        n = 4000 + 100 * len(name)
+        e = 10 ** rng.uniform(0, 3, n)
+        cz = rng.uniform(-1, 1, n)
+        cols = dict(true_energy=e, true_coszen=cz, reco_energy=np.clip(e * rng.lognormal(0, 0.3, n), 5.7, 56.0),
+                    reco_coszen=np.clip(cz + rng.normal(0, 0.2, n), -1, 0.999), pid=rng.integers(0, 2, n).astype(float),
+                    weighted_aeff=rng.uniform(0, 1e-4, n), nominal_nue_flux=rng.uniform(0.5, 1.5, n),
+                    nominal_numu_flux=rng.uniform(0.5, 1.5, n))
+        for k, v in cols.items():
+            arrays["%s/%s" % (name, k)] = v
+    arrays["__metadata__/livetime"] = np.float64(2.5)
+    path = tmp_path / "events.npz"
+    np.savez(path, **arrays)
+    data_dict = ("{'true_energy': 'true_energy', 'true_coszen': 'true_coszen', 'reco_energy': 'reco_energy', "
+                 "'reco_coszen': 'reco_coszen', 'pid': 'pid', 'weighted_aeff': 'weighted_aeff', "
+                 "'nu_flux': ['nominal_nue_flux', 'nominal_numu_flux']}")
+    cut = "(true_coszen <= 0.5) & (true_energy <= 700)"
+    loader = ("[data.simple_data_loader]\napply_mode = events\noutput_names = %s\nevents_file = %s\nmc_cuts = %s\n"
+              "data_dict = %s\nfraction_events_to_keep = 0.5\nevents_subsample_index = 1\nrequired_metadata = livetime\n"
+              % (", ".join(NAMES), path, cut, data_dict))
+    pipe = Pipeline(_events_cfg(tmp_path, loader))
+    assert pipe.stages[0].service_name == "simple_data_loader" and pipe.stages[0].metadata["livetime"] == 2.5
+    out = pipe.get_outputs()
+    import ast
+    host, _ = load_events(str(path), ast.literal_eval(data_dict), fraction_events_to_keep=0.5, events_subsample_index=1)
+    host = apply_cut(host, cut)
+    o = pipe["prob3"].osc_params
+    dm, mix, mat_pot = o.dm_matrix, o.mix_matrix_complex, pipe["prob3"].gen_mat_pot_matrix_complex
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    livetime = 2.5 * 365 * 86400.0
+    for c in pipe.data.containers:
+        ev = host[c.name]
+        c.representation = "events"
+        assert c.size == len(ev["true_energy"]) and 0 < c.size < 0.5 * (4000 + 100 * len(c.name)) + 1
+        assert float(ev["true_coszen"].max()) <= 0.5 and float(ev["true_energy"].max()) <= 700
+        assert np.array_equal(c["nu_flux"].cpu().numpy(), ev["nu_flux"]) and ev["nu_flux"].shape[1] == 2
+        # down-sampled: initial weights carry the inverse fraction (simple_data_loader.py:218-224)
+        assert np.all(c["initial_weights"].cpu().numpy() == 2.0)
+        nubar, flav = int(c["nubar"]), int(c["flav"])
+        _, den, dis = L.calcLayers(ev["true_coszen"])
+        prob = oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, ev["true_energy"], den, dis)
+        w = 2.0 * (ev["nu_flux"][:, 0] * prob[:, 0, flav] + ev["nu_flux"][:, 1] * prob[:, 1, flav])
+        w = w * (ev["weighted_aeff"] * (1.0 * livetime))
+        ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
+        i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
+        idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
+        assert np.allclose(out[c.name].hist, oracle.accumulate(idx, w, 128).reshape(8, 8, 2), rtol=1e-10, atol=0), c.name
+    # the two halves of a 50 % split are disjoint and together cover the file (independent sub-samples)
+    a, _ = load_events(str(path), {"e": "true_energy"}, fraction_events_to_keep=0.5, events_subsample_index=0)
+    b, _ = load_events(str(path), {"e": "true_energy"}, fraction_events_to_keep=0.5, events_subsample_index=1)
+    full, _ = load_events(str(path), {"e": "true_energy"})
+    for name in NAMES:
+        assert len(np.intersect1d(a[name]["e"], b[name]["e"])) == 0
+        assert np.array_equal(np.sort(np.concatenate([a[name]["e"], b[name]["e"]])), np.sort(full[name]["e"]))
+
+
+def test_simple_data_loader_errors(tmp_path):
+    _need_gpu()
+    from pisa_b200.stages.data.simple_data_loader import simple_data_loader
+    ev = {"numu_cc": {"true_energy": np.ones(4), "weights": np.ones(4)}}
+    stage = simple_data_loader(events_file=ev, mc_cuts=None, data_dict=None, output_names=["numu_cc"])
+    from pisa_b200.core.container import ContainerSet
+    stage.data = ContainerSet("x")
+    with pytest.raises(KeyError):          # a `weights` field in the file would be overwritten
+        stage.setup()
+    with pytest.raises(ValueError):        # duplicate output names
+        simple_data_loader(events_file=ev, mc_cuts=None, data_dict=None, output_names=["numu_cc", "numu_cc"])
+    with pytest.raises(ValueError):        # categories not split by flavour / interaction
+        simple_data_loader(events_file={"numu": {"true_energy": np.ones(4)}}, mc_cuts=None, data_dict=None,
+                           output_names=["numu"])
+    with pytest.raises(ImportError):       # HDF5 needs h5py
+        try:
+            import h5py  # noqa: F401
+            raise ImportError("h5py present: nothing to check")
+        except ImportError:
+            p = tmp_path / "x.hdf5"
+            p.write_bytes(b"")
+            simple_data_loader(events_file=str(p), mc_cuts=None, data_dict=None, output_names=["numu_cc"])
+
+
+def test_distribution_maker_sum_and_param_updates():
+    """DistributionMaker.get_outputs(return_sum=True) (distribution_maker.py:251-294) over two pipelines, fused and
+    staged evaluation, update_params / select_params across pipelines."""
+    _need_gpu()
+    from pisa_b200.core.distribution_maker import DistributionMaker
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.fused import FusedPipeline
+    from pisa_b200.utils.units import ureg
+    cfgs = ["settings/pipeline/b200_events.cfg", "settings/pipeline/b200_flux_events.cfg"]
+    fused, staged = DistributionMaker(cfgs), DistributionMaker(cfgs, fused=False)
+    assert all(isinstance(e, FusedPipeline) for e in fused.evaluators)
+    assert all(isinstance(e, Pipeline) for e in staged.evaluators)
+
+    def check():
+        tot_f, tot_s = fused.get_outputs(return_sum=True), staged.get_outputs(return_sum=True)
+        assert len(tot_f) == 1 and tot_f.names == ["total"]
+        parts = staged.get_outputs()
+        manual = sum(m.hist for ms in parts for m in ms)
+        assert np.allclose(tot_s["total"].hist, manual, rtol=1e-13, atol=0)
+        assert np.allclose(tot_f["total"].hist, tot_s["total"].hist, rtol=1e-10, atol=0)
+        err = np.sqrt(sum(m.std_devs ** 2 for ms in parts for m in ms))
+        assert np.allclose(tot_f["total"].std_devs, err, rtol=1e-10, atol=0)
+        return tot_f["total"].hist
+
+    first = check()
+    for dm in (fused, staged):
+        p = dm.params.theta23
+        p.value = 48.0 * ureg.deg
+        dm.update_params(p)
+    second = check()
+    assert not np.allclose(first, second, rtol=1e-6)
+    for dm in (fused, staged):
+        dm.select_params("ih")
+        assert all(pl.params.deltam31.value.m < 0 for pl in dm)
+    check()
+    with pytest.raises(KeyError):
+        fused.select_params("no_such_selection")
+    fused.select_params("no_such_selection", error_on_missing=False)
+
+
+@pytest.mark.parametrize("hist_extra,loader_extra", [("apply_unc_weights = True", "unc_weights = True"),
+                                                      ("unweighted = True", ""),
+                                                      ("unweighted = True\napply_unc_weights = True", "unc_weights = True")])
+def test_fused_pipeline_with_hist_options(tmp_path, hist_extra, loader_extra):
+    """utils.hist's apply_unc_weights / unweighted (hist.py:141-145,198-209) through FusedPipeline: weights, errors and
+    bin_unc2 equal the staged pipeline's."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.fused import FusedPipeline
+    from pisa_b200.utils.units import ureg
+    base = open(os.path.join(CFG_DIR, "b200_events.cfg")).read()
+    base = base.replace("error_method = sumw2", "error_method = sumw2\n" + hist_extra)
+    if loader_extra:
+        base = base.replace("param.n_events = 20000", loader_extra + "\nparam.n_events = 20000")
+    cfg = tmp_path / "pipeline.cfg"
+    cfg.write_text(base)
+    staged, fused = Pipeline(str(cfg)), FusedPipeline(Pipeline(str(cfg)))
+    for theta in (42.3, 49.0):
+        for p in (staged, fused.pipeline):
+            p.params.theta23 = theta * ureg.deg
+        staged.run()
+        fused.run()
+        for cs, cf in zip(staged.data.containers, fused.pipeline.data.containers):
+            cs.representation = cf.representation = staged.output_binning
+            for key in ("weights", "errors", "bin_unc2"):
+                a, b = cs[key].cpu().numpy(), cf[key].cpu().numpy()
+                assert np.allclose(b, a, rtol=1e-10, atol=0), (cs.name, key, hist_extra)
+            if "unweighted" in hist_extra and not loader_extra:
+                assert float(cs["weights"].sum()) == cs["weights"].sum().round().item()   # plain counts

@@ -67,6 +67,52 @@ def test_oscillogram_pipeline_matches_oracle_on_the_grid():
     assert float((prob.sum(dim=1) - 1).abs().max()) < 5e-12
 
 
+def test_reference_osc_example_cfg_runs_unmodified(monkeypatch):
+    """The drop-in claim of BASELINE.json's north_star on config C1: the REFERENCE's own, byte-identical
+    ``settings/pipeline/osc_example.cfg`` (README.md:44-68; copies of the cfg text and of the three settings files it
+    includes under tests/golden/ref_cfg/, checked byte for byte against the reference tree by
+    test_host_boundary.py::test_reference_cfg_copies_are_byte_identical) selects this package's services:
+    ``Pipeline(cfg).run(); data.get_mapset('prob_mu')`` against the oracle on all 80 000 grid points."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    monkeypatch.setenv("PISA_RESOURCES", os.path.join(ROOT, "tests", "golden", "ref_cfg"))
+    pipe = Pipeline("settings/pipeline/osc_example.cfg")
+    assert [(s.stage_name, s.service_name) for s in pipe.stages] == [
+        ("data", "toy_event_generator"), ("flux", "barr_simple"), ("osc", "prob3")]
+    assert pipe.param_selections == ["nh"]
+    pipe.run()
+    grid = pipe.data["output_binning"]
+    assert grid.shape == (200, 200)
+    pipe.data.representation = grid
+    maps_mu = pipe.data.get_mapset("prob_mu")
+    maps_e = pipe.data.get_mapset("prob_e")
+    assert len(maps_mu) == 12 and maps_mu["numu_cc"].hist.shape == (200, 200)
+    e_edges, cz_edges = np.logspace(0, 3, 201), np.linspace(-1, 1, 201)
+    e = np.sqrt(e_edges[:-1] * e_edges[1:])
+    cz = 0.5 * (cz_edges[:-1] + cz_edges[1:])
+    E, CZ = (a.ravel() for a in np.meshgrid(e, cz, indexing="ij"))
+    L = _oracle_layers()
+    _, den, dis = L.calcLayers(CZ)
+    dm, mix, mat_pot = _matrices(pipe["prob3"])
+    zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
+    names = [c.name for c in pipe.data.containers]
+    assert len(names) == 12
+    for nubar in (1, -1):
+        ref = oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, E, den, dis, n_threads=os.cpu_count())
+        for name in [n for n in names if ("bar" in n) == (nubar < 0)]:
+            flav = 2 if "tau" in name else (1 if "mu" in name else 0)
+            for maps, init in ((maps_e, 0), (maps_mu, 1)):
+                assert np.allclose(maps[name].hist.ravel(), ref[:, init, flav], rtol=1e-10, atol=1e-14), (name, init)
+    # the pipeline's output key: weights = initial_weights * (nu_flux_e * prob_e + nu_flux_mu * prob_mu) with the
+    # flux.barr_simple flux of the toy generator's nominal (0, 1) flux
+    out = pipe.get_outputs()
+    for name in ("nue_cc", "numubar_nc", "nutau_cc"):
+        c = pipe.data[name]
+        flux = c["nu_flux"].cpu().numpy()
+        want = flux[:, 0] * maps_e[name].hist.ravel() + flux[:, 1] * maps_mu[name].hist.ravel()
+        assert np.allclose(out[name].hist.ravel(), want, rtol=1e-13, atol=0), name
+
+
 def test_stage_cache_and_param_update():
     _need_gpu()
     from pisa_b200.core.pipeline import Pipeline
@@ -118,7 +164,7 @@ def test_events_pipeline_matches_oracle_chain():
         ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
         i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
         idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
-        total_bad_idx += int((c.bin_index(pipe.output_binning).cpu().numpy() != idx).sum())
+        total_bad_idx += int((c.bin_index(pipe.output_binning, "hist").cpu().numpy() != idx).sum())
         ref = oracle.accumulate(idx, w, 128).reshape(8, 8, 2)
         ref_err = np.sqrt(oracle.accumulate(idx, w * w, 128)).reshape(8, 8, 2)
         assert np.allclose(out[c.name].hist, ref, rtol=1e-10, atol=0), c.name
@@ -405,7 +451,7 @@ def test_csv_loader_pipeline(tmp_path):
         assert c.size == int(sel.sum())
         assert np.array_equal(c["true_energy"].cpu().numpy(), df["true_energy"][sel].values)
         w = c["weights"].cpu().numpy()
-        idx = c.bin_index(pipe.output_binning).cpu().numpy()
+        idx = c.bin_index(pipe.output_binning, "hist").cpu().numpy()
         assert np.isclose(out[c.name].hist.sum(), w[idx >= 0].sum(), rtol=1e-12)
     assert sum(sizes.values()) == n
 
@@ -750,6 +796,45 @@ def test_fused_pipeline_equals_staged_pipeline(cfg):
     for p in (staged, fused.pipeline):
         p.params.theta23 = 42.3 * ureg.deg
     compare()
+
+
+def test_container_resample_to_irregular_binning():
+    """binned -> binned onto an IRREGULAR destination (explicit edge lists on the device): the edge tensors of both
+    binning structs must stay alive across the two hist_index calls of Container.resample (round-1 advisor finding:
+    the destination's keep-alive list was dropped before use)."""
+    _need_gpu()
+    from pisa_b200.core.binning import MultiDimBinning, OneDimBinning
+    from pisa_b200.core.container import Container
+    src = MultiDimBinning([OneDimBinning("x", num_bins=40, is_lin=True, domain=[0.0, 10.0]),
+                           OneDimBinning("y", num_bins=30, is_lin=True, domain=[-1.0, 1.0])])
+    dst = MultiDimBinning([OneDimBinning("x", bin_edges=[0.0, 0.7, 2.0, 2.1, 5.5, 10.0]),
+                           OneDimBinning("y", bin_edges=[-1.0, -0.35, 0.1, 0.15, 1.0])])
+    assert all(d.is_irregular for d in dst)
+    c = Container("c", representation=src)
+    rng = np.random.default_rng(2)
+    vals = rng.uniform(1.0, 2.0, src.size)
+    c["v"] = vals
+    for _ in range(3):                       # repeated: freed edge memory would be reused by the allocations in between
+        c.representation = dst
+        got = c["v"].cpu().numpy().reshape(dst.shape)
+        junk = [torch.empty(5, dtype=torch.float64, device="cuda") for _ in range(8)]  # noqa: F841
+        c.validity["v"][hash(dst)] = False      # translate again from the source representation
+    xc = 0.5 * (np.linspace(0, 10, 41)[:-1] + np.linspace(0, 10, 41)[1:])
+    yc = 0.5 * (np.linspace(-1, 1, 31)[:-1] + np.linspace(-1, 1, 31)[1:])
+    X, Y = np.meshgrid(xc, yc, indexing="ij")
+    ex, ey = np.array([0.0, 0.7, 2.0, 2.1, 5.5, 10.0]), np.array([-1.0, -0.35, 0.1, 0.15, 1.0])
+    ix, iy = np.searchsorted(ex, X.ravel(), "right") - 1, np.searchsorted(ey, Y.ravel(), "right") - 1
+    want = np.zeros(dst.shape)
+    v2 = vals.reshape(src.shape)
+    for a in range(5):
+        for b in range(4):
+            sel = (ix == a) & (iy == b)
+            if sel.sum() > 1:
+                want[a, b] = vals[sel].mean()
+            else:   # value of the old bin the new bin's centre falls into
+                cx, cy = 0.5 * (ex[a] + ex[a + 1]), 0.5 * (ey[b] + ey[b + 1])
+                want[a, b] = v2[min(int(cx / 0.25), 39), min(int((cy + 1) / (2 / 30)), 29)]
+    assert np.allclose(got, want, rtol=1e-12, atol=0)
 
 
 def test_fused_pipeline_rejects_other_shapes():

@@ -1,10 +1,10 @@
 """GPU parity tests of the propagation kernels against the CPU oracle (through the C ABI).
 
-Tolerance (FP64): the reference's own golden-vector criterion (numba_osc_tests.py:82)
-rtol = 1e-10, atol = 1e-14 is required of >= 99.9 % of the probabilities, and every probability
-must satisfy rtol = 1e-10 with atol = 1e-12: the reference's own unitarity noise on these inputs is
-6e-14 (tests/golden/make_golden.py log), i.e. its results carry ~1e-13 absolute rounding noise, so
-a tighter absolute bound would compare noise with noise.
+Tolerance (FP64): the reference's own golden-vector criterion (numba_osc_tests.py:82), rtol = 1e-10 with
+atol = 1e-14, is required of EVERY probability (|out - ref| <= 1e-14 + 1e-10 |ref|).  Measured: max absolute
+difference 3.7e-13 (at P ~ 1), max RELATIVE difference 8.4e-9 (at P ~ 4e-12, i.e. 3e-20 absolute): the relative
+bound alone does not hold for vanishing probabilities -- neither does it for the reference against itself, whose
+unitarity noise on these inputs is 6e-14 (tests/golden/make_golden.py log).
 """
 import os
 
@@ -36,10 +36,9 @@ def _earth(prem_file=PREM12, depth=2.0, height=20.0, ye=(0.4656, 0.4656, 0.4957)
 
 def _assert_prob(out, ref, what):
     err = np.abs(out - ref)
-    strict = np.isclose(out, ref, **AC_KW_F8)
-    loose = np.isclose(out, ref, rtol=1e-10, atol=1e-12)
-    assert loose.all(), (what, "max abs", err.max(), "n_bad", (~loose).sum())
-    assert strict.mean() >= 0.999, (what, "fraction within (1e-10, 1e-14)", strict.mean())
+    strict = np.isclose(out, ref, **AC_KW_F8)          # the reference's AC_KW on 100 % of the entries
+    assert strict.all(), (what, "max abs", err.max(), "n_bad", (~strict).sum(), "of", strict.size,
+                          "worst excess", (err - (1e-14 + 1e-10 * np.abs(ref))).max())
 
 
 def _keys(g):
@@ -107,7 +106,7 @@ def test_reference_fixture_events_earth_and_layers():
 
 @pytest.mark.parametrize("nubar", [1, -1])
 def test_large_random_sample_vs_oracle(nubar):
-    """2e5 seeded events (SURVEY 8d laws) against the oracle, NSI + deltacp, plus unitarity on 2e6."""
+    """1e6 seeded events (SURVEY 8d laws; nu and nubar) against the oracle, NSI + deltacp, plus unitarity on 2e6."""
     from pisa_b200 import ops
     dev = _dev()
     g = load_golden("ref_prob3_f8.npz")
@@ -115,7 +114,7 @@ def test_large_random_sample_vs_oracle(nubar):
     consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"])
     L, earth = _earth()
     rng = np.random.default_rng(0)
-    n = 200_000
+    n = 1_000_000
     energy = 10 ** rng.uniform(0, 3, n)
     coszen = rng.uniform(-1, 1, n)
     _, den, dis = L.calcLayers(coszen)
@@ -132,6 +131,33 @@ def test_large_random_sample_vs_oracle(nubar):
     p2, _, _ = ops.propagate_earth(consts, earth, nubar, e2, c2)
     assert float((p2.sum(dim=1) - 1).abs().max()) < 5e-12
     assert float((p2.sum(dim=2) - 1).abs().max()) < 5e-12
+
+
+@pytest.mark.parametrize("nubar", [1, -1])
+def test_large_random_sample_standard_matter_vs_oracle(nubar):
+    """1e6 seeded events through the standard-matter specialisation (no NSI: the path the headline benchmark takes),
+    row mode (prob_e / prob_mu of every final flavour) and full matrix, against the oracle."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    key = "nufit20_nh_dcp306/nu"
+    consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"])
+    L, earth = _earth()
+    rng = np.random.default_rng(17)
+    n = 1_000_000
+    energy = 10 ** rng.uniform(0, 3, n)
+    coszen = rng.uniform(-1, 1, n)
+    _, den, dis = L.calcLayers(coszen)
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    ref = oracle.propagate_array(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], -1, zero, np.zeros((3, 3)),
+                                 nubar, energy, den, dis, n_threads=os.cpu_count())
+    e, cz = torch.tensor(energy, device=dev), torch.tensor(coszen, device=dev)
+    full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+    _assert_prob(full.cpu().numpy(), ref, "std matter full %d" % nubar)
+    for flav in (0, 1, 2):
+        _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=flav, want_probability=False)
+        _assert_prob(pe.cpu().numpy(), ref[:, 0, flav], "std matter prob_e %d" % flav)
+        _assert_prob(pmu.cpu().numpy(), ref[:, 1, flav], "std matter prob_mu %d" % flav)
 
 
 def test_per_event_species_arrays():
@@ -155,8 +181,11 @@ def test_per_event_species_arrays():
 
 
 def test_fp32_mode_vs_fp64_oracle():
-    """FP32 storage mode: <= 1e-5 absolute against the FP64 oracle on the same (float32) inputs
-    (BASELINE.json north_star); the distance to the reference's own FP32 fixtures is reported."""
+    """FP32 mode on the reference's own FP32 fixture inputs, both arithmetic settings of the *_f32 entry points:
+    <= 1e-5 absolute against the FP64 oracle on the same (float32) inputs (BASELINE.json north_star), and the distance
+    to the reference's FP32 results.  The reference's f4 fixtures themselves sit up to 4.3e-5 from the FP64 oracle
+    (measured per case: 6e-6 .. 4.3e-5, tests/golden/ref_prob3_f4.npz), so the pinned bound is that distance plus
+    this implementation's own tolerance."""
     from pisa_b200 import ops
     dev = _dev()
     g4 = load_golden("ref_prob3_f4.npz")
@@ -164,20 +193,68 @@ def test_fp32_mode_vs_fp64_oracle():
     e32, cz32 = g4["energy"], g4["coszen"]
     _, den, dis = L.calcLayers(cz32.astype(np.float64))
     zero = np.zeros((3, 3), dtype=np.complex128)
-    for key in _keys(g4):
-        nubar = int(g4[key + "/nubar"])
-        dm, mix, mp, lri = (g4[key + "/" + k].astype(np.complex128 if k in ("mix", "mat_pot") else np.float64)
-                            for k in ("dm", "mix", "mat_pot", "lri_pot"))
-        consts = ops.OscConsts.from_matrices(dm, mix, mp, -1, None, lri)
-        ref64 = oracle.propagate_array(dm, mix, mp, -1, zero, lri, nubar, e32.astype(np.float64), den, dis)
-        full, _, _ = ops.propagate_earth(consts, earth, nubar, torch.tensor(e32, device=dev),
-                                         torch.tensor(cz32, device=dev))
-        assert full.dtype == torch.float32
-        out = full.cpu().numpy().astype(np.float64)
-        assert np.abs(out - ref64).max() <= 1e-5, (key, np.abs(out - ref64).max())
-        # informational: the reference's own FP32 path on the same inputs
-        d_ref4 = np.abs(out - g4[key + "/probability"]).max()
-        assert d_ref4 < 5e-4, (key, d_ref4)
+    try:
+        for math, tol in (("mixed", 1e-5), ("fp64", 5e-7)):
+            ops.set_f32_math(math)
+            assert ops.get_f32_math() == math
+            for key in _keys(g4):
+                nubar = int(g4[key + "/nubar"])
+                dm, mix, mp, lri = (g4[key + "/" + k].astype(np.complex128 if k in ("mix", "mat_pot") else np.float64)
+                                    for k in ("dm", "mix", "mat_pot", "lri_pot"))
+                consts = ops.OscConsts.from_matrices(dm, mix, mp, -1, None, lri)
+                ref64 = oracle.propagate_array(dm, mix, mp, -1, zero, lri, nubar, e32.astype(np.float64), den, dis)
+                full, _, _ = ops.propagate_earth(consts, earth, nubar, torch.tensor(e32, device=dev),
+                                                 torch.tensor(cz32, device=dev))
+                assert full.dtype == torch.float32
+                out = full.cpu().numpy().astype(np.float64)
+                assert np.abs(out - ref64).max() <= tol, (math, key, np.abs(out - ref64).max())
+                d_ref4 = np.abs(out - g4[key + "/probability"]).max()
+                d_ref4_oracle = np.abs(ref64 - g4[key + "/probability"]).max()   # the reference's own FP32 error
+                assert d_ref4_oracle <= 4.3e-5, (key, d_ref4_oracle)
+                assert d_ref4 <= d_ref4_oracle + tol, (math, key, d_ref4, d_ref4_oracle)
+    finally:
+        ops.set_f32_math("mixed")
+
+
+@pytest.mark.parametrize("nubar,nsi", [(1, False), (-1, False), (1, True), (-1, True)])
+def test_fp32_mode_large_sample_within_1e5_of_fp64_oracle(nubar, nsi):
+    """The mixed-precision FP32 mode on 1e6 seeded events, 1 GeV .. 1 TeV, full matrix and row mode, standard matter
+    and NSI: <= 1e-5 absolute on every probability vs the FP64 oracle on the float32-rounded inputs (measured: max
+    7e-6, 99.9 % below 2.7e-6).  The fused template kernel is held to the same events through its histogram."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    key = "nufit20_nh_dcp306_stdnsi/nu" if nsi else "nufit20_nh_dcp306/nu"
+    dm, mix, mp = g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"]
+    consts = ops.OscConsts.from_matrices(dm, mix, mp)
+    L, earth = _earth()
+    rng = np.random.default_rng(23)
+    n = 1_000_000
+    e32 = (10 ** rng.uniform(0, 3, n)).astype(np.float32)
+    cz32 = rng.uniform(-1, 1, n).astype(np.float32)
+    _, den, dis = L.calcLayers(cz32.astype(np.float64))
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    ref = oracle.propagate_array(dm, mix, mp, -1, zero, np.zeros((3, 3)), nubar, e32.astype(np.float64), den, dis,
+                                 n_threads=os.cpu_count())
+    ops.set_f32_math("mixed")
+    e, cz = torch.tensor(e32, device=dev), torch.tensor(cz32, device=dev)
+    full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+    d = np.abs(full.cpu().numpy().astype(np.float64) - ref)
+    assert d.max() <= 1e-5, ("full", d.max())
+    assert np.quantile(d.max(axis=(1, 2)), 0.999) <= 5e-6
+    for flav in (0, 1, 2):
+        _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=flav, want_probability=False)
+        assert np.abs(pe.cpu().numpy() - ref[:, 0, flav]).max() <= 1e-5
+        assert np.abs(pmu.cpu().numpy() - ref[:, 1, flav]).max() <= 1e-5
+    # fused kernel: weights = 1, flux = (1, 1), one bin -> sum over events of (P_e->flav + P_mu->flav)
+    flav = 1
+    ones = torch.ones(n, dtype=torch.float32, device=dev)
+    flux = torch.ones((n, 2), dtype=torch.float32, device=dev)
+    idx = torch.zeros(n, dtype=torch.int32, device=dev)
+    h, h2 = ops.reweight_hist(consts, earth, nubar, flav, e, cz, flux, ones, idx, 4)
+    want = float((ref[:, 0, flav] + ref[:, 1, flav]).sum())
+    assert abs(float(h[0]) - want) <= 2e-6 * want      # mean error of the mode ~3e-7 per probability, mostly unsigned
+    assert float(h[1:].abs().sum()) == 0.0
 
 
 def test_layers_kernel_bit_exact():

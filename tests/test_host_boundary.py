@@ -82,6 +82,67 @@ def test_paramset_selector_and_hash():
         ps.theta23.value = 3 * ureg.km
 
 
+def test_param_selector_update_survives_reselection():
+    """Pipeline.update_params goes through ParamSelector.update (pipeline.py:579-596 / param.py:1708-1730 of the
+    reference): the regular set, the current set and the ACTIVE selector sets take the new value, so selecting again
+    does not revert it; selections are applied in order and a missing one only raises when asked to."""
+    t23 = Param("theta23", 42 * ureg.deg, is_fixed=False)
+    nh = Param("deltam31", 2.457e-3 * ureg.eV ** 2)
+    ih = Param("deltam31", -2.374e-3 * ureg.eV ** 2)
+    sel = ParamSelector(regular_params=[t23], selector_param_sets={"nh": [nh], "ih": [ih]}, selections=["nh"])
+    sel.update([Param("theta23", 47 * ureg.deg, is_fixed=False), Param("deltam31", 2.6e-3 * ureg.eV ** 2)])
+    assert sel.params.theta23.value.m == 47 and sel.params.deltam31.value.m == 2.6e-3
+    sel.select_params(["ih"])
+    assert sel.params.deltam31.value.m == -2.374e-3 and sel.params.theta23.value.m == 47   # regular update kept
+    sel.select_params(["nh"])
+    assert sel.params.deltam31.value.m == 2.6e-3            # the active selector set was updated too
+    sel.update(Param("not_mine", 1.0), extend=False)        # excess params of other stages are ignored
+    assert "not_mine" not in sel.params.names
+    sel.select_params(["ih", "no_such"], error_on_missing=False)
+    assert sel.params.deltam31.value.m == -2.374e-3         # the available selection was applied
+    with pytest.raises(KeyError):
+        sel.select_params(["nh", "no_such"], error_on_missing=True)
+    assert sel.params.deltam31.value.m == 2.6e-3            # ... in order, before the missing one raised
+
+
+def test_simple_data_loader_host_logic(tmp_path):
+    """File reading (.npz layout), variable mapping with stacking, cuts and the reference's sub-sampling algorithm
+    (events_pi.py:175-505), without a device."""
+    from pisa_b200 import FTYPE
+    from pisa_b200.stages.data.simple_data_loader import apply_cut, load_events
+    rng = np.random.RandomState(3)
+    arrays = {}
+    for cat in ("nue_cc", "numubar_nc"):
+        arrays[cat + "/true_energy"] = 1 + 79 * rng.rand(1000)
+        arrays[cat + "/true_coszen"] = 2 * rng.rand(1000) - 1
+        arrays[cat + "/fa"], arrays[cat + "/fb"] = rng.rand(1000), rng.rand(1000)
+    arrays["__metadata__/livetime"] = np.float64(3.0)
+    path = str(tmp_path / "ev.npz")
+    np.savez(path, **arrays)
+    mapping = {"true_energy": "true_energy", "true_coszen": "true_coszen", "flux": ["fa", "fb"]}
+    ev, meta = load_events([path, path], mapping, required_metadata=["livetime"])
+    assert meta == {"livetime": 6.0}                                   # livetimes of several files add up
+    assert ev["nue_cc"]["flux"].shape == (2000, 2) and ev["nue_cc"]["flux"].dtype == FTYPE
+    assert np.array_equal(ev["nue_cc"]["flux"][:1000, 1], arrays["nue_cc/fb"].astype(FTYPE))
+    cut = apply_cut(ev, "(true_coszen <= 0.5) & (np.log10(true_energy) < 1.5)")
+    keep = (ev["nue_cc"]["true_coszen"] <= 0.5) & (ev["nue_cc"]["true_energy"] < 10 ** 1.5)
+    assert np.array_equal(cut["nue_cc"]["true_energy"], ev["nue_cc"]["true_energy"][keep])
+    # sub-samples: reproducible, disjoint, the same choice for every variable of a category
+    a, _ = load_events(path, mapping, fraction_events_to_keep=0.25, events_subsample_index=0)
+    a2, _ = load_events(path, mapping, fraction_events_to_keep=0.25, events_subsample_index=0)
+    b, _ = load_events(path, mapping, fraction_events_to_keep=0.25, events_subsample_index=2)
+    assert len(a["nue_cc"]["true_energy"]) == 250 and np.array_equal(a["nue_cc"]["flux"], a2["nue_cc"]["flux"])
+    assert len(np.intersect1d(a["nue_cc"]["true_energy"], b["nue_cc"]["true_energy"])) == 0
+    full = arrays["nue_cc/true_energy"].astype(FTYPE)
+    pos = np.searchsorted(np.sort(full), a["nue_cc"]["true_energy"])
+    order = np.argsort(full)[pos]
+    assert np.array_equal(a["nue_cc"]["true_coszen"], arrays["nue_cc/true_coszen"].astype(FTYPE)[order])
+    with pytest.raises(KeyError):
+        load_events(path, {"x": "no_such_variable"})
+    with pytest.raises(ValueError):
+        load_events(path, mapping, fraction_events_to_keep=0.5, events_subsample_index=2)
+
+
 def test_binning_classification_is_ftype_dependent_rule():
     """dragon_datarelease.reco_energy has 9-digit edges whose ratios differ by 5.5e-10,
     so in FP64 (rtol 1e-12) it is IRREGULAR -> searchsorted on the real edges; under PISA_FTYPE=fp32 (rtol 1e-5) the
@@ -102,6 +163,30 @@ def test_binning_classification_is_ftype_dependent_rule():
     assert g[0].shape == (200, 200) and g[0][3, 0] == g[0][3, 7] and g[1][0, 5] == g[1][9, 5]  # 'ij', row-major
     pid = OneDimBinning("pid", bin_edges=[-np.inf, 0.55, np.inf])
     assert pid.is_irregular
+
+
+def test_reference_cfg_copies_are_byte_identical():
+    """tests/golden/ref_cfg holds the cfg TEXT of the reference's README example (config text, not code) so that the
+    GPU box, which has no reference tree, can run it; here -- where the tree exists -- the copies are checked byte for
+    byte, and they must parse to the reference's stage order on their own."""
+    cfg_root = os.path.join(ROOT, "tests", "golden", "ref_cfg")
+    rels = ["settings/pipeline/osc_example.cfg", "settings/binning/example.cfg", "settings/osc/nufitv20.cfg",
+            "settings/osc/earth.cfg"]
+    for rel in rels:
+        assert os.path.exists(os.path.join(cfg_root, rel)), rel
+        if os.path.isdir(REF_RES):
+            assert open(os.path.join(cfg_root, rel), "rb").read() == open(os.path.join(REF_RES, rel), "rb").read(), rel
+    old = os.environ.get("PISA_RESOURCES")
+    os.environ["PISA_RESOURCES"] = cfg_root
+    try:
+        d = parse_pipeline_config("settings/pipeline/osc_example.cfg")
+        assert list(d.keys())[1:] == [("data", "toy_event_generator"), ("flux", "barr_simple"), ("osc", "prob3")]
+        assert d[("osc", "prob3")]["calc_mode"].shape == (200, 200)
+    finally:
+        if old is None:
+            del os.environ["PISA_RESOURCES"]
+        else:
+            os.environ["PISA_RESOURCES"] = old
 
 
 def test_parse_own_and_reference_pipeline_cfgs():
@@ -305,8 +390,9 @@ def test_import_alias_serves_pisa_names_from_this_package():
 
 
 def test_fused_pipeline_shape_checks_without_a_gpu():
-    """FusedPipeline only accepts osc.prob3 (events) -> [aeff.aeff] -> utils.hist (events, plain weights): anything
-    else is refused before any device work (structure checks run on stage metadata only)."""
+    """FusedPipeline only accepts osc.prob3 (events) -> [aeff.aeff] -> utils.hist (events; apply_unc_weights and
+    unweighted are handled, tests/test_gpu_callers.py): anything else is refused before any device work (structure
+    checks run on stage metadata only)."""
     from types import SimpleNamespace as NS
     from pisa_b200.fused import FusedPipeline
 
@@ -324,8 +410,6 @@ def test_fused_pipeline_shape_checks_without_a_gpu():
         pipe(osc, stage("aeff", "aeff")),                                                          # no histogram stage
         pipe(osc, stage("flux", "barr_simple"), stage("utils", "hist", **hist_ok)),                # something in between
         pipe(stage("osc", "prob3", calc_mode="grid", apply_mode="events"), stage("utils", "hist", **hist_ok)),
-        pipe(osc, stage("utils", "hist", **dict(hist_ok, apply_unc_weights=True))),
-        pipe(osc, stage("utils", "hist", **dict(hist_ok, unweighted=True))),
         pipe(osc, stage("utils", "hist", **dict(hist_ok, calc_mode="binned"))),
         pipe(osc, stage("aeff", "aeff"), stage("utils", "hist", **dict(hist_ok, error_method="fluctuate"))),
     ]
