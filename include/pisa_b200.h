@@ -227,7 +227,8 @@ int64_t pisab_hist_workspace_bytes(int64_t n, int32_t n_bins);
 /* hist[b] = sum w, hist_w2[b] = sum w^2 over events with index b (d_hist_w2 may be NULL).
  * d_weights may be NULL (unweighted counts, hist.py:179-185).  Deterministic: fixed
  * per-warp accumulation order and a fixed-order two-stage reduction (no float atomics)
- * whenever n_bins <= PISAB_DET_MAX_BINS. Output is overwritten, always double. */
+ * whenever n_bins <= PISAB_DET_MAX_BINS; larger binnings are accumulated EXACTLY in 128-bit fixed point with integer
+ * atomics (the sum rounded once), which is bit-reproducible as well.  Output is overwritten, always double. */
 #define PISAB_DET_MAX_BINS 1024
 int pisab_hist_accumulate_f64(const int32_t *d_index, const double *d_weights, int64_t n,
                               int32_t n_bins, double *d_hist, double *d_hist_w2,
@@ -322,6 +323,25 @@ int pisab_reweight_hist_scan_f32(const pisab_osc_consts_t *consts, int32_t n_tem
                                  double *d_hist, void *d_workspace, int64_t workspace_bytes, void *stream);
 int pisab_template_chi2_batch(const double *d_hist, int32_t n_templates, int32_t n_containers, int32_t n_bins,
                               const double *d_observed, double *d_out, void *stream);
+
+/* ---- planned histogram (the fit-loop form of utils.hist.apply_function) ------------------------------------
+ * The bin index of an event is computed once at hist.setup_function (hist.py:86-127) and never changes during a fit.
+ * pisab_hist_plan_build turns it, once, into a PLAN: per tile of 2048 events the permutation that groups the tile's
+ * events by bin (uint16, stable) and the n_bins + 1 group offsets.  pisab_hist_accumulate_planned_* then produces
+ * sum w and sum w^2 from the plan and the current weights: one thread per bin walks its group in shared memory and
+ * accumulates in registers -- no private bins, no atomics, fixed summation order (bit-reproducible), 8 + 2 B/event
+ * of DRAM traffic.  Supported for n_bins <= 256 (pisab_hist_plan_bytes returns 0 otherwise: use
+ * pisab_hist_accumulate_*).  Events whose index is outside [0, n_bins) are dropped, as in pisab_hist_accumulate_*.
+ * d_weights must be 16-byte aligned.  Workspace: pisab_hist_workspace_bytes(n, n_bins). */
+int64_t pisab_hist_plan_bytes(int64_t n, int32_t n_bins);
+int pisab_hist_plan_build(const int32_t *d_index, int64_t n, int32_t n_bins, void *d_plan, int64_t plan_bytes,
+                          void *stream);
+int pisab_hist_accumulate_planned_f64(const void *d_plan, const double *d_weights, int64_t n, int32_t n_bins,
+                                      double *d_hist, double *d_hist_w2, void *d_workspace, int64_t workspace_bytes,
+                                      void *stream);
+int pisab_hist_accumulate_planned_f32(const void *d_plan, const float *d_weights, int64_t n, int32_t n_bins,
+                                      double *d_hist, double *d_hist_w2, void *d_workspace, int64_t workspace_bytes,
+                                      void *stream);
 
 /* ---- small stage-API operators ---------------------------------------------------------- */
 /* aeff.aeff apply_function (pisa/stages/aeff/aeff.py:68-88): weights[i] *= factor[i] * scale in FTYPE arithmetic

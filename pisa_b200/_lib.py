@@ -102,6 +102,7 @@ _SIGNATURES = {
     "pisab_flux_honda_2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_scan": (c_i32, [ctypes.POINTER(OscConsts), c_i32, ctypes.POINTER(Earth),
                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+    "pisab_hist_accumulate_planned": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_scale_weights": (c_i32, [c_vp, c_dbl, c_i64, c_vp, c_vp]),
     "pisab_hist_transform": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
@@ -110,6 +111,8 @@ _SIGNATURES = {
 _UNTYPED = {
     "pisab_hist_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
+    "pisab_hist_plan_bytes": (c_i64, [c_i64, c_i32]),
+    "pisab_hist_plan_build": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "pisab_joint_index": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pisab_template_chi2": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),

@@ -275,6 +275,18 @@ class Container:
         self._index_cache_names.update(binning.names)
         return idx
 
+    def bin_plan(self, binning, policy="generic"):
+        """``ops.HistPlan`` of ``bin_index(binning, policy)`` (cached with it; None when the binning is not plannable):
+        the fit-loop form of the histogram, see ``pisab_hist_plan_build``."""
+        from pisa_b200 import ops
+        ck = ("plan", hash(binning), policy)
+        hit = self._index_cache.get(ck)
+        if hit is not None:
+            return hit[1]
+        plan = ops.hist_plan(self.bin_index(binning, policy), binning.size)
+        self._index_cache[ck] = (tuple(binning.names), plan)
+        return plan
+
     def translate(self, key, src_representation):
         assert hash(src_representation) in self.representation_keys
         dest_representation = self.representation
@@ -444,6 +456,9 @@ class VirtualContainer:
 
     def bin_index(self, binning, policy="generic"):
         return self.containers[0].bin_index(binning, policy)
+
+    def bin_plan(self, binning, policy="generic"):
+        return self.containers[0].bin_plan(binning, policy)
 
 
 class ContainerSet:

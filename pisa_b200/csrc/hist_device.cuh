@@ -71,6 +71,40 @@ struct WarpHist {
     }
 };
 
+// ---- large binnings (> PISAB_DET_MAX_BINS): exact fixed-point accumulation ---------------------------------
+// Private copies of the bins no longer fit in shared memory, and floating-point atomics on shared bins are not
+// reproducible (the order of the additions changes from run to run).  INTEGER addition is associative, so every
+// weight is converted to a 128-bit two's-complement fixed-point number  w * 2^k = hi * 2^64 + lo  and added with two
+// 64-bit integer atomics (the carry out of the low word is detected from the returned old value and added to the
+// high word).  k is chosen from an upper bound of N * max|w| so that the sum cannot overflow; with N = 1e8 events a
+// weight keeps all 53 bits of its mantissa as long as it is within 2^47 of the largest one.  The result is the
+// EXACT sum rounded once: bit-reproducible on any grid, any number of GPUs' worth of event order, any run.
+struct FixedAcc {
+    unsigned long long lo, hi;
+};
+// scale = 2^(62 - ex) with 2^ex > n * bound  (so |sum| * scale < 2^62); bound == 0 (all weights zero) -> 1
+__device__ __forceinline__ double fixed_scale(double bound, double n) {
+    const double tot = bound * n;
+    if (!(tot > 0.0)) return 1.0;
+    int ex;
+    frexp(tot, &ex);
+    return ldexp(1.0, 62 - ex);
+}
+__device__ __forceinline__ void fixed_add(FixedAcc *acc, double v, double scale) {
+    const double s = v * scale;               // exact: scale is a power of two
+    const double fl = floor(s);
+    const double rem = s - fl;                // [0, 1), exact
+    const unsigned long long lo = (unsigned long long)(rem * 18446744073709551616.0);
+    const long long hi = (long long)fl;
+    const unsigned long long old = atomicAdd(&acc->lo, lo);
+    const unsigned long long carry = (old + lo) < old ? 1ull : 0ull;
+    const unsigned long long add_hi = (unsigned long long)hi + carry;
+    if (add_hi) atomicAdd(&acc->hi, add_hi);
+}
+__device__ __forceinline__ double fixed_value(const FixedAcc &a, double scale) {
+    return ((double)(long long)a.hi + (double)a.lo * 5.421010862427522e-20) / scale; // lo * 2^-64
+}
+
 // persistent grid for the histogramming kernels (fixed by the device -> reproducible sums)
 int hist_grid(int64_t n);
 // hist[b] = sum over blocks (in block order) of partials[block][b]; w2 likewise (nullable)

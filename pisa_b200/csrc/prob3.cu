@@ -254,15 +254,19 @@ struct FusedBatch {
 // blocks cooperate on one template; partials: [container][n_ranks][2 n_bins] of that template.
 // PLAIN: no per-event outputs and no per-event nubar / flav arrays (the fit-loop case): the null checks and
 // the three optional stores disappear from the event loop.
-template <typename IO, bool STD, bool PLAIN, bool MP = false>
+// LARGE (n_bins > PISAB_DET_MAX_BINS): no private bins; every weight goes to the exact fixed-point accumulators in
+// global memory (hist_device.cuh), `partials` then points at FixedAcc[container][2][n_bins] and `bounds` at the
+// per-container weight bounds written by fused_bound_kernel.
+template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
                                                     const FusedBatch<IO> &batch, int ci_begin, int ci_end,
                                                     int rank, int n_ranks, double *__restrict__ partials,
-                                                    double *s_hist) {
+                                                    double *s_hist,
+                                                    const unsigned long long *__restrict__ bounds = nullptr) {
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
-    double *s_dyn = s_hist + WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double);
+    double *s_dyn = s_hist + (LARGE ? 0 : WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double));
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn); // FP32 mode: float2 state columns
     s_dyn += (MP ? PropagatorSmemF<1, 2>::kFloat2s : PropagatorSmem<1, 2>::kDoubles) * kBlock;
@@ -284,7 +288,16 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
         const IO *__restrict__ nu_flux = C.nu_flux, *__restrict__ weights_in = C.weights_in;
         const int32_t *__restrict__ index = C.index, *__restrict__ order = C.order;
         const int64_t n = C.n;
-        wh.clear();
+        FixedAcc *acc = nullptr;
+        double sc1 = 1.0, sc2 = 1.0;
+        if (LARGE) {
+            acc = reinterpret_cast<FixedAcc *>(partials) + (size_t)ci * 2 * n_bins;
+            const double bound = __longlong_as_double((long long)bounds[ci]);
+            sc1 = fixed_scale(bound, (double)n);
+            sc2 = fixed_scale(bound * bound, (double)n);
+        } else {
+            wh.clear();
+        }
         // `order` (optional) lists the events grouped by number of crossed shells; -1 = no event
         // (n < 2^31 is checked by the host wrapper: 32-bit event indices save registers)
         auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
@@ -338,19 +351,65 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                     if (C.prob_mu) C.prob_mu[i] = (IO)pmu;
                 }
             }
-            wh.add(bin, w);
+            if (LARGE) {
+                if ((unsigned)bin < (unsigned)n_bins) {
+                    fixed_add(acc + bin, w, sc1);
+                    fixed_add(acc + n_bins + bin, w * w, sc2);
+                }
+            } else {
+                wh.add(bin, w);
+            }
             i_cur = i_next;
             i_next = i_nn;
         }
-        wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
-        __syncthreads(); // the next container clears the bins
+        if (!LARGE) {
+            wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
+            __syncthreads(); // the next container clears the bins
+        }
     }
 }
 
-template <typename IO, bool STD, bool PLAIN, bool MP = false>
+// Weight bound per container for the fixed-point accumulators: max over events of |w_in| (|flux_e| + |flux_mu|) |scale|
+// >= |w| because both probabilities are <= 1.  24 B/event, HBM-bound (4 % of the fused kernel's time).
+template <typename IO>
+__global__ void __launch_bounds__(256)
+fused_bound_kernel(const __grid_constant__ FusedBatch<IO> batch, int blocks_per_container,
+                   unsigned long long *__restrict__ bounds) {
+    __shared__ double s[256];
+    const int ci = blockIdx.x / blocks_per_container, r = blockIdx.x - ci * blocks_per_container;
+    const FusedContainer<IO> &C = batch.c[ci];
+    double m = 0.0;
+    const int64_t stride = (int64_t)blocks_per_container * blockDim.x;
+    for (int64_t i = (int64_t)r * blockDim.x + threadIdx.x; i < C.n; i += stride)
+        m = fmax(m, fabs((double)__ldg(C.weights_in + i)) *
+                        (fabs((double)__ldg(C.nu_flux + 2 * i)) + fabs((double)__ldg(C.nu_flux + 2 * i + 1))));
+    s[threadIdx.x] = m * fabs(C.scale);
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] = fmax(s[threadIdx.x], s[threadIdx.x + off]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicMax(bounds + ci, (unsigned long long)__double_as_longlong(s[0]));
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+fused_fixed_finish_kernel(const __grid_constant__ FusedBatch<IO> batch, const FixedAcc *__restrict__ acc,
+                          const unsigned long long *__restrict__ bounds, double *__restrict__ out) {
+    const int n_bins = batch.n_bins;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x; // (container, plane, bin)
+    if (v >= batch.n_containers * 2 * n_bins) return;
+    const int ci = v / (2 * n_bins), plane = (v - ci * 2 * n_bins) / n_bins;
+    const double bound = __longlong_as_double((long long)bounds[ci]);
+    const double sc = fixed_scale(plane ? bound * bound : bound, (double)batch.c[ci].n);
+    out[v] = fixed_value(acc[v], sc);
+}
+
+template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false>
 __global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
-                     const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials) {
+                     const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials,
+                     const unsigned long long *__restrict__ bounds = nullptr) {
     extern __shared__ __align__(16) double s_hist[];
     __shared__ EarthTable s_earth;
     // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
@@ -360,7 +419,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // never walks more than one container, so a template over analysis-size containers (1e4 events each)
     // costs one or two event latencies instead of one per container.
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, STD, PLAIN, MP>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist);
+    fused_template_body<IO, STD, PLAIN, MP, LARGE>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -408,9 +467,16 @@ static auto earth_kernel(bool mp) {
 template <typename IO, bool STD, bool PLAIN>
 static auto fused_kernel(bool mp) {
     if constexpr (sizeof(IO) == 4) {
-        if (mp) return reweight_hist_kernel<IO, STD, PLAIN, true>;
+        if (mp) return reweight_hist_kernel<IO, STD, PLAIN, true, false>;
     }
-    return reweight_hist_kernel<IO, STD, PLAIN, false>;
+    return reweight_hist_kernel<IO, STD, PLAIN, false, false>;
+}
+template <typename IO, bool STD>
+static auto fused_kernel_large(bool mp) { // > PISAB_DET_MAX_BINS: fixed-point accumulators, fit-loop (PLAIN) form only
+    if constexpr (sizeof(IO) == 4) {
+        if (mp) return reweight_hist_kernel<IO, STD, true, true, true>;
+    }
+    return reweight_hist_kernel<IO, STD, true, false, true>;
 }
 template <typename IO, bool STD>
 static auto scan_kernel(bool mp) {
@@ -547,10 +613,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
                                     int64_t workspace_bytes, void *stream) {
     const int n_bins = batch.n_bins;
     if (n_bins < 1) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
-    if (n_bins > PISAB_DET_MAX_BINS) {
-        set_error("fused reweight+hist supports up to %d bins; use propagate_earth + hist_accumulate", PISAB_DET_MAX_BINS);
-        return PISAB_ERR_UNSUPPORTED;
-    }
+    const bool large = n_bins > PISAB_DET_MAX_BINS;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
         if (C.n < 0 || (C.n > 0 && (!C.energy || !C.coszen || !C.nu_flux || !C.weights_in || !C.index))) {
@@ -580,14 +643,20 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     const bool std_matter = ot.std_matter != 0.0;
 #endif
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
-    const size_t smem = fused_smem_bytes<IO>(n_bins, std_matter, mp);
+    const size_t smem = fused_smem_bytes<IO>(large ? 0 : n_bins, std_matter, mp);
     bool plain = true;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
         plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu;
     }
-    auto kernel = std_matter ? (plain ? fused_kernel<IO, true, true>(mp) : fused_kernel<IO, true, false>(mp))
-                             : (plain ? fused_kernel<IO, false, true>(mp) : fused_kernel<IO, false, false>(mp));
+    if (large && (!plain || !d_batch_out)) {
+        set_error("more than %d bins: only the batched form without per-event outputs is fused; use propagate_earth + "
+                  "hist_accumulate", PISAB_DET_MAX_BINS);
+        return PISAB_ERR_UNSUPPORTED;
+    }
+    auto kernel = large ? (std_matter ? fused_kernel_large<IO, true>(mp) : fused_kernel_large<IO, false>(mp))
+                        : std_matter ? (plain ? fused_kernel<IO, true, true>(mp) : fused_kernel<IO, true, false>(mp))
+                                     : (plain ? fused_kernel<IO, false, true>(mp) : fused_kernel<IO, false, false>(mp));
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
@@ -627,9 +696,30 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         ranks = (int)r;
     }
     const int grid = ranks * batch.n_containers;
+    if (large) {
+        // workspace: [bounds: one u64 per container, padded to 256 B] [FixedAcc containers x 2 x n_bins]
+        unsigned long long *d_bounds = (unsigned long long *)d_workspace;
+        FixedAcc *d_acc = (FixedAcc *)((char *)d_workspace + 256);
+        const size_t acc_bytes = sizeof(FixedAcc) * (size_t)batch.n_containers * 2 * n_bins;
+        PISAB_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, 256 + acc_bytes, s));
+        int64_t bpc64 = (n_max + 256 * 64 - 1) / (256 * 64); // >= 64 events per thread, at most 1024 blocks per container
+        const int bpc = (int)(bpc64 < 1 ? 1 : (bpc64 > 1024 ? 1024 : bpc64));
+        fused_bound_kernel<IO><<<bpc * batch.n_containers, 256, 0, s>>>(batch, bpc, d_bounds);
+        note_launch();
+        {
+            LaunchTimer t(s);
+            kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_acc, d_bounds);
+            note_launch();
+        }
+        const int total = batch.n_containers * 2 * n_bins;
+        fused_fixed_finish_kernel<IO><<<(total + 255) / 256, 256, 0, s>>>(batch, d_acc, d_bounds, d_batch_out);
+        note_launch();
+        PISAB_CUDA_CHECK(cudaGetLastError());
+        return PISAB_OK;
+    }
     {
         LaunchTimer t(s);
-        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace);
+        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace, nullptr);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());

@@ -148,8 +148,8 @@ class ReweightEngine:
         launch (for the roofline timing in bench.py)."""
         allreduce = self._want_exchange(allreduce)
         out = self._result_buffer()
-        if self.n_bins > _lib.DET_MAX_BINS:
-            return self._evaluate_unfused(consts, out, allreduce)
+        # (binnings beyond _lib.DET_MAX_BINS take the same launch: the library switches to exact fixed-point
+        # accumulators in global memory, bit-reproducible as well)
         for lo, batch in self._get_batches():
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -158,24 +158,6 @@ class ReweightEngine:
             if events is not None:
                 e1.record()
                 events.append((e0, e1))
-        if allreduce:
-            self.allreduce(out)
-        return out
-
-    def _evaluate_unfused(self, consts, out, allreduce):
-        """Binnings beyond the fused kernel's shared-memory budget (> 1024 bins): propagation, reweighting and
-        histogramming as three kernels per container (global-atomic histogram, not bit-reproducible)."""
-        scales = getattr(self, "scales", None) or [1.0] * len(self.blocks)
-        for i, blk in enumerate(self.blocks):
-            d = blk.dev
-            _, pe, pmu = ops.propagate_earth(consts, self.earth, blk.nubar, d["true_energy"], d["true_coszen"],
-                                             flav=blk.flav, want_probability=False)
-            w = ops.apply_osc_weights(d["nu_flux"], pe, pmu, d["weights"].clone())
-            if scales[i] != 1.0:
-                w *= scales[i]
-            h, h2 = ops.hist_accumulate(d["index"], w, self.n_bins)
-            out[i, 0].copy_(h)
-            out[i, 1].copy_(h2)
         if allreduce:
             self.allreduce(out)
         return out

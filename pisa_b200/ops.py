@@ -389,10 +389,43 @@ def _workspace(device, n, n_bins, n_containers=1):
     return ws
 
 
-def hist_accumulate(index, weights, n_bins, want_w2=True):
-    """(hist, hist_w2) as float64 tensors; ``weights`` may be None (counts, hist.py:179-185)."""
+class HistPlan:
+    """Setup-time plan of a histogram over static bin indices (``pisab_hist_plan_build``): per tile of 2048 events
+    the permutation grouping the events by bin and the group offsets.  ``hist_accumulate(..., plan=plan)`` then needs
+    only the current weights.  ``None`` from ``hist_plan`` means the binning is not plannable (> 256 bins)."""
+
+    def __init__(self, buf, n, n_bins):
+        self.buf, self.n, self.n_bins = buf, int(n), int(n_bins)
+
+
+def hist_plan(index, n_bins):
     _chk(index, "index", torch.int32)
     n = index.numel()
+    nbytes = int(_lib.load().pisab_hist_plan_bytes(n, int(n_bins)))
+    if nbytes == 0:
+        return None
+    buf = torch.empty(nbytes, dtype=torch.uint8, device=index.device)
+    _lib.check(_lib.load().pisab_hist_plan_build(_ptr(index), n, int(n_bins), _ptr(buf), nbytes, _stream()))
+    return HistPlan(buf, n, n_bins)
+
+
+def hist_accumulate(index, weights, n_bins, want_w2=True, plan=None):
+    """(hist, hist_w2) as float64 tensors; ``weights`` may be None (counts, hist.py:179-185).  With a ``plan``
+    (``hist_plan`` of the same index) the bin-sorted-tile kernel is used."""
+    _chk(index, "index", torch.int32)
+    n = index.numel()
+    if plan is not None and weights is not None and weights.data_ptr() % 16 == 0:
+        if plan.n != n or plan.n_bins != int(n_bins):
+            raise ValueError("the plan was built for %d events / %d bins" % (plan.n, plan.n_bins))
+        _chk(weights, "weights")
+        if weights.numel() != n:
+            raise ValueError("weights and index must have the same length")
+        hist = torch.empty(n_bins, dtype=torch.float64, device=index.device)
+        w2 = torch.empty(n_bins, dtype=torch.float64, device=index.device) if want_w2 else None
+        ws = _workspace(index.device, n, n_bins)
+        f = _lib.fn("pisab_hist_accumulate_planned", weights.dtype)
+        _lib.check(f(_ptr(plan.buf), _ptr(weights), n, int(n_bins), _ptr(hist), _ptr(w2), _ptr(ws), ws.numel(), _stream()))
+        return hist, w2
     dt = torch.float64 if weights is None else weights.dtype
     if weights is not None:
         _chk(weights, "weights")

@@ -64,6 +64,7 @@ class hist(Stage):  # pylint: disable=invalid-name
         self.data["regularized_output_binning"] = self.apply_mode
         for container in self.data:
             container.bin_index(self.apply_mode, "hist")
+            container.bin_plan(self.apply_mode, "hist")      # bin-sorted tiles: the per-template pass reads 10 B/event
 
     def _apply_transform(self):
         """calc_mode binned: hist = (unc * w) @ hist_transform (hist.py:131-160)."""
@@ -112,6 +113,7 @@ class hist(Stage):  # pylint: disable=invalid-name
         for container in self.data:
             container.representation = "events"
             idx = container.bin_index(self.apply_mode, "hist")
+            plan = container.bin_plan(self.apply_mode, "hist")
             weights = container["weights"]
             if "astro_weights" in container.keys:
                 weights = weights + container["astro_weights"]
@@ -121,10 +123,11 @@ class hist(Stage):  # pylint: disable=invalid-name
             if self.apply_unc_weights:
                 unc = container["unc_weights"]
                 if self.error_method == "sumw2":
-                    bin_unc2, _ = ops.hist_accumulate(idx, (unc * unc * weights).contiguous(), n_bins, want_w2=False)
+                    bin_unc2, _ = ops.hist_accumulate(idx, (unc * unc * weights).contiguous(), n_bins, want_w2=False,
+                                                      plan=plan)
                 weights = (unc * weights).contiguous()
             want_w2 = self.error_method == "sumw2"
-            h, h2 = ops.hist_accumulate(idx, weights, n_bins, want_w2=want_w2)
+            h, h2 = ops.hist_accumulate(idx, weights, n_bins, want_w2=want_w2, plan=plan)
             if want_w2 and bin_unc2 is None:
                 bin_unc2 = h.clone()   # unc_weights == 1: sum(unc^2 * w) == sum(w); its own array, like the reference's
             local.append((container, h, h2, bin_unc2))

@@ -373,3 +373,116 @@ def test_fused_kernel_other_bin_counts(n_bins):
         with pytest.raises(PisabError):
             ops.reweight_hist(consts, earth, 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"],
                               ev["weights"], big, 1025)
+
+
+@pytest.mark.parametrize("n,n_bins", [(0, 128), (1, 1), (2048, 128), (2049, 7), (4095, 129), (300_001, 128),
+                                      (1_000_003, 256)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_planned_histogram_vs_oracle(n, n_bins, dtype):
+    """pisab_hist_plan_build + pisab_hist_accumulate_planned (bin-sorted tiles, one thread per bin): empty, single,
+    tile-boundary and ragged sizes, out-of-range indices dropped, a hot bin, both storage types; identical bits run
+    to run; the plan is refused for a different index length and is not offered above 256 bins."""
+    from pisa_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(n + n_bins)
+    idx = rng.integers(-2, n_bins + 2, n).astype(np.int32)
+    if n > 10:
+        idx[rng.random(n) < 0.2] = n_bins // 2
+    w = rng.uniform(-0.5, 2, n).astype(dtype)
+    ti, tw = torch.tensor(idx, device=dev), torch.tensor(w, device=dev)
+    plan = ops.hist_plan(ti, n_bins)
+    assert plan is not None
+    h, h2 = ops.hist_accumulate(ti, tw, n_bins, plan=plan)
+    ok = (idx >= 0) & (idx < n_bins)
+    wd = w.astype(np.float64)
+    ref = oracle.accumulate(np.where(ok, idx, -1), wd, n_bins)
+    ref2 = oracle.accumulate(np.where(ok, idx, -1), wd * wd, n_bins)
+    scale = max(1.0, float(np.abs(wd).sum()))
+    assert np.allclose(h.cpu().numpy(), ref, rtol=1e-11, atol=1e-15 * scale)
+    assert np.allclose(h2.cpu().numpy(), ref2, rtol=1e-11, atol=1e-15 * scale)
+    for _ in range(2):
+        hb, hb2 = ops.hist_accumulate(ti, tw, n_bins, plan=plan)
+        assert torch.equal(hb, h) and torch.equal(hb2, h2)
+    h_only, none = ops.hist_accumulate(ti, tw, n_bins, want_w2=False, plan=plan)
+    assert none is None and torch.equal(h_only, h)
+    if n > 1:
+        with pytest.raises(ValueError):
+            ops.hist_accumulate(ti[1:].contiguous(), tw[1:].contiguous(), n_bins, plan=plan)
+    assert ops.hist_plan(ti, 257) is None
+
+
+def test_large_binning_is_exact_and_order_independent():
+    """More than PISAB_DET_MAX_BINS bins: 128-bit fixed-point accumulation with integer atomics.  The result is the
+    exact sum rounded once, so it is bit-identical run to run AND for any permutation of the events (float atomics,
+    round 1, differed in the last bits from run to run), and it agrees with math.fsum."""
+    import math
+    from pisa_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(12)
+    n, n_bins = 600_000, 3200
+    idx = rng.integers(-1, n_bins + 1, n).astype(np.int32)
+    w = (rng.uniform(0, 1, n) * 10.0 ** rng.uniform(-6, 3, n)) * rng.choice([1.0, 1.0, 1.0, -1.0], n)
+    ti, tw = torch.tensor(idx, device=dev), torch.tensor(w, device=dev)
+    h, h2 = ops.hist_accumulate(ti, tw, n_bins)
+    perm = rng.permutation(n)
+    hp, hp2 = ops.hist_accumulate(torch.tensor(idx[perm], device=dev), torch.tensor(w[perm], device=dev), n_bins)
+    assert torch.equal(h, hp) and torch.equal(h2, hp2)
+    for _ in range(2):
+        hb, hb2 = ops.hist_accumulate(ti, tw, n_bins)
+        assert torch.equal(hb, h) and torch.equal(hb2, h2)
+    hh, hh2 = h.cpu().numpy(), h2.cpu().numpy()
+    for b in (0, 17, 1599, 3199):
+        sel = idx == b
+        assert hh[b] == math.fsum(w[sel]), b                       # exactly rounded
+        assert abs(hh2[b] - math.fsum(w[sel] ** 2)) <= 2e-16 * hh2[b]   # (w*w is rounded before it is accumulated)
+    ok = (idx >= 0) & (idx < n_bins)
+    assert np.allclose(hh, oracle.accumulate(np.where(ok, idx, -1), w, n_bins), rtol=1e-9, atol=1e-12 * np.abs(w).sum())
+    # counts and float32 weights
+    c, _ = ops.hist_accumulate(ti, None, n_bins, want_w2=False)
+    assert np.array_equal(c.cpu().numpy(), np.bincount(idx[ok], minlength=n_bins).astype(np.float64))
+    w32 = np.abs(w).astype(np.float32)
+    h32, _ = ops.hist_accumulate(ti, torch.tensor(w32, device=dev), n_bins)
+    assert h32.cpu().numpy()[5] == math.fsum(w32[idx == 5].astype(np.float64))
+    # all-zero weights and an empty input
+    z, z2 = ops.hist_accumulate(ti, torch.zeros(n, dtype=torch.float64, device=dev), n_bins)
+    assert float(z.abs().sum()) == 0.0 and float(z2.abs().sum()) == 0.0
+    e, _ = ops.hist_accumulate(ti[:0].contiguous(), tw[:0].contiguous(), n_bins)
+    assert float(e.abs().sum()) == 0.0
+
+
+def test_fused_template_with_3200_bins_is_deterministic():
+    """The fused template kernel above PISAB_DET_MAX_BINS (the 40 x 40 x 2 stress binning of SURVEY 8d): same launch,
+    exact fixed-point accumulators; equal to propagate + reweight + histogram, bit-identical run to run."""
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    n_bins, n = 3200, 150_000
+    g = torch.Generator(device=dev)
+    g.manual_seed(9)
+    for dtype, nsi, tol in ((np.float64, False, 1e-12), (np.float64, True, 1e-12), (np.float32, False, 2e-5)):
+        dm, mix, mat_pot = syn.osc_matrices(nsi=syn.STD_NSI if nsi else None)
+        consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+        eng = ReweightEngine(earth, n_bins, dtype, dev)
+        parts = []
+        for c, (name, nubar, flav) in enumerate(syn.CONTAINERS[:3] + syn.CONTAINERS[7:9]):
+            ev = syn.make_events_torch(n + 1000 * c, seed=30 + c, dtype=dtype, device=dev)
+            idx = torch.randint(-1, n_bins, (n + 1000 * c,), generator=g, device=dev, dtype=torch.int32)
+            eng.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"], idx)
+            parts.append((nubar, flav, ev, idx))
+        eng.set_scales([1.0, 2.5, 0.5, 1.0, 3.0])
+        out = eng.evaluate(consts).clone()
+        for _ in range(2):
+            assert torch.equal(eng.evaluate(consts), out)
+        for c, ((nubar, flav, ev, idx), scale) in enumerate(zip(parts, [1.0, 2.5, 0.5, 1.0, 3.0])):
+            _, pe, pmu = ops.propagate_earth(consts, earth, nubar, ev["true_energy"], ev["true_coszen"], flav=flav,
+                                             want_probability=False)
+            w = (ev["weights"].double() * (ev["nu_flux"][:, 0].double() * pe.double() + ev["nu_flux"][:, 1].double() * pmu.double())
+                 * scale).contiguous()
+            hu, hu2 = ops.hist_accumulate(idx, w, n_bins)
+            nz = hu != 0
+            assert float(((out[c, 0] - hu).abs()[nz] / hu.abs()[nz]).max()) < tol, (dtype, nsi, c)
+            assert float(((out[c, 1] - hu2).abs()[nz] / hu2.abs()[nz]).max()) < 2 * tol, (dtype, nsi, c)
