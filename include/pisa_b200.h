@@ -343,6 +343,23 @@ int pisab_hist_accumulate_planned_f32(const void *d_plan, const float *d_weights
                                       double *d_hist, double *d_hist_w2, void *d_workspace, int64_t workspace_bytes,
                                       void *stream);
 
+/* ---- multi-GPU: the histogram exchange as ONE kernel over NVLink peer memory ------------------
+ * One process per GPU.  pisab_exchange_create allocates this rank's exchange buffer and returns its 64-byte CUDA IPC
+ * handle; the host side gathers the handles of all ranks (torch.distributed, plumbing) and passes them, in rank order,
+ * to pisab_exchange_connect.  pisab_exchange_allreduce then sums d_buf[count] over the ranks IN RANK ORDER, in place,
+ * with one kernel launch per rank: peer stores into every rank's slot, system-scope release / acquire flags, fixed-order
+ * sum -- the result is bit-identical on every rank and from run to run.  Every rank must make the same sequence of
+ * calls; a wait for a peer that never arrives ends after ~4 s and is reported by pisab_exchange_status (0 = ok).
+ * pisab_sum_slots is the one-launch rank-ordered sum used after a library all_gather where peer mapping is not
+ * available. */
+int pisab_exchange_create(int32_t rank, int32_t world, int64_t capacity_doubles, void **ctx_out,
+                          unsigned char *handle_out /* [64] */);
+int pisab_exchange_connect(void *ctx, const unsigned char *all_handles /* [world][64] */);
+int pisab_exchange_allreduce(void *ctx, double *d_buf, int64_t count, void *stream);
+int pisab_exchange_status(void *ctx);
+int pisab_exchange_destroy(void *ctx);
+int pisab_sum_slots(const double *d_gathered, int32_t world, int64_t count, double *d_out, void *stream);
+
 /* ---- small stage-API operators ---------------------------------------------------------- */
 /* aeff.aeff apply_function (pisa/stages/aeff/aeff.py:68-88): weights[i] *= factor[i] * scale in FTYPE arithmetic
  * (d_factor = weighted_aeff, may be NULL: weights[i] *= scale). */

@@ -113,6 +113,12 @@ _UNTYPED = {
     "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "pisab_hist_plan_bytes": (c_i64, [c_i64, c_i32]),
     "pisab_hist_plan_build": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
+    "pisab_exchange_create": (c_i32, [c_i32, c_i32, c_i64, ctypes.POINTER(c_vp), c_vp]),
+    "pisab_exchange_connect": (c_i32, [c_vp, c_vp]),
+    "pisab_exchange_allreduce": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
+    "pisab_exchange_status": (c_i32, [c_vp]),
+    "pisab_exchange_destroy": (c_i32, [c_vp]),
+    "pisab_sum_slots": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
     "pisab_joint_index": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pisab_template_chi2": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),

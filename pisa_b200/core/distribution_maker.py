@@ -100,10 +100,11 @@ class DistributionMaker:
             return
         successes = 0
         for p in self._pipelines:
-            have = set(p.param_selections)
-            sels = [selections] if isinstance(selections, str) else list(selections)
-            if all(s.strip().lower() in have for s in sels):
-                p.select_params(sels, error_on_missing=False)
+            try:
+                p.select_params(selections, error_on_missing=True)
+            except KeyError:
+                pass
+            else:
                 successes += 1
         if error_on_missing and successes == 0:
             raise KeyError("None of the stages from any pipeline in this distribution maker has all of the selections "

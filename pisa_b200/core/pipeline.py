@@ -100,8 +100,19 @@ class Pipeline:
         return sorted({sel for s in self._stages for sel in s.param_selections})
 
     def select_params(self, selections, error_on_missing=False):
+        """pipeline.py:598-625 of the reference: every stage applies the selections it has; KeyError only if asked
+        for and NO stage has all of them."""
+        successes = 0
         for s in self._stages:
-            s.select_params(selections, error_on_missing=False)
+            try:
+                s.select_params(selections, error_on_missing=True)
+            except KeyError:
+                pass
+            else:
+                successes += 1
+        if error_on_missing and successes == 0:
+            raise KeyError("None of the stages in this pipeline has all of the selections %s available."
+                           % (selections,))
 
     def update_params(self, params, existing_must_match=False, extend=False):
         """Through every stage's ParamSelector (pipeline.py:579-596 of the reference): the regular set, the current set

@@ -5,12 +5,17 @@ and evaluates it with the same kernels; per-launch constants are replicated.  Th
 crosses NVLink is the ``[containers, 2, n_bins]`` float64 histogram buffer (24 KB for the
 ``dragon_datarelease`` binning), combined once per template.
 
-Two combination modes:
-  * ``deterministic=True`` (default): ``all_gather`` the per-rank buffers and sum them in rank
-    order on every rank -- the N-GPU histogram is then bit-reproducible run to run and identical on
-    all ranks, whatever algorithm / channel count NCCL picks;
+Combination modes (``combine_histograms``):
+  * ``deterministic=True`` (default), CUDA buffers: ONE kernel launch per rank over NVLink peer memory
+    (``csrc/exchange.cu``: every rank stores its buffer into a slot of every peer's exchange buffer, publishes a
+    system-scope flag, waits for the peers' flags and sums the slots in rank order) -- bit-reproducible run to run and
+    identical on all ranks.  The exchange buffers are mapped once through CUDA IPC handles gathered with
+    ``torch.distributed`` (plumbing).  ``PISAB_EXCHANGE=nccl`` (or a failed peer mapping) selects the library form:
+    ``all_gather`` + one rank-ordered sum kernel (2 launches);
+  * CPU tensors (``gloo``, the host-logic tests): ``all_gather`` + rank-ordered sum in torch;
   * ``deterministic=False``: a plain ``all_reduce(SUM)`` (NVLS in-switch reduction when available).
-Both are latency-bound at this size (tens of microseconds against a >= 18 ms step).
+All are latency-bound at this size (tens of microseconds against an 11 ms step at 1e8 events; the one-launch form
+matters for analysis-size templates of ~45 us).
 
 The same code runs over ``gloo`` on CPU tensors (tests/test_multi_rank.py).
 """
@@ -20,7 +25,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["init_from_env", "world", "shard_slice", "shard_arrays", "combine_histograms", "enable_event_sharding",
-           "event_sharding", "local_slice"]
+           "event_sharding", "local_slice", "PeerExchange", "exchange_mode", "exchange_status"]
 
 # Stage API: with sharding on, the event-mode loaders keep only this rank's slice of every container and
 # ``utils.hist`` (or the fused engine) exchanges the binned results once per template.  Off by default, so that a
@@ -95,6 +100,77 @@ def shard_arrays(arrays, rank, world_size):
     return {k: a[start:stop] for k, a in arrays.items()}
 
 
+class PeerExchange:
+    """This rank's end of the peer-memory exchange (``pisab_exchange_*``): buffer, IPC handshake, one-launch
+    rank-ordered all-reduce of float64 CUDA buffers up to ``capacity`` values."""
+
+    def __init__(self, device, capacity):
+        import ctypes
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        rank, world_size = world()
+        self.capacity, self.device = int(capacity), device
+        self.ctx = ctypes.c_void_p()
+        handle = (ctypes.c_ubyte * 64)()
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().pisab_exchange_create(rank, world_size, self.capacity, ctypes.byref(self.ctx), handle))
+            handles = [None] * world_size
+            dist.all_gather_object(handles, bytes(handle))
+            blob = b"".join(handles)
+            rc = _lib.load().pisab_exchange_connect(self.ctx, blob)
+        ok = torch.tensor([1 if rc == 0 else 0], device=device if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks take the same path
+        if int(ok) == 0:
+            self.close()
+            raise RuntimeError("peer mapping of the exchange buffers failed on at least one rank: %s"
+                               % (_lib.load().pisab_last_error().decode() if rc else "another rank"))
+
+    def allreduce(self, buf):
+        from . import ops
+        self._lib.check(self._lib.load().pisab_exchange_allreduce(self.ctx, self._ct.c_void_p(buf.data_ptr()),
+                                                                   buf.numel(), ops._stream()))
+        return buf
+
+    def status(self):
+        return int(self._lib.load().pisab_exchange_status(self.ctx))
+
+    def close(self):
+        if self.ctx:
+            self._lib.load().pisab_exchange_destroy(self.ctx)
+            self.ctx = None
+
+
+_peer = {"exchange": None, "failed": False}
+
+
+def exchange_mode():
+    """How CUDA histogram buffers are combined: "peer" (one kernel over NVLink peer memory) or "nccl"."""
+    if os.environ.get("PISAB_EXCHANGE", "peer").strip().lower() == "nccl" or _peer["failed"]:
+        return "nccl"
+    return "peer"
+
+
+def _peer_exchange(device, count):
+    ex = _peer["exchange"]
+    if ex is not None and ex.capacity >= count and ex.device == device:
+        return ex
+    if ex is not None:
+        ex.close()
+    try:
+        _peer["exchange"] = PeerExchange(device, max(int(count), 1 << 16))
+    except RuntimeError as exc:
+        import warnings
+        warnings.warn("pisa_b200: peer-memory exchange unavailable (%s); using all_gather + sum kernel" % exc)
+        _peer["exchange"], _peer["failed"] = None, True
+    return _peer["exchange"]
+
+
+def exchange_status():
+    """0 = every peer wait so far succeeded (None when the peer exchange is not in use).  Synchronises the device."""
+    ex = _peer["exchange"]
+    return None if ex is None else ex.status()
+
+
 def combine_histograms(buf, deterministic=True):
     """Sum the per-rank histogram buffers in place (the single exchange step of the path)."""
     rank, world_size = world()
@@ -102,6 +178,18 @@ def combine_histograms(buf, deterministic=True):
         return buf
     if not deterministic:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+        return buf
+    if buf.is_cuda and buf.dtype == torch.float64 and buf.is_contiguous():
+        if exchange_mode() == "peer":
+            ex = _peer_exchange(buf.device, buf.numel())
+            if ex is not None:
+                return ex.allreduce(buf)
+        from . import _lib, ops
+        import ctypes
+        gathered = torch.empty((world_size,) + tuple(buf.shape), dtype=buf.dtype, device=buf.device)
+        dist.all_gather_into_tensor(gathered, buf)
+        _lib.check(_lib.load().pisab_sum_slots(ctypes.c_void_p(gathered.data_ptr()), world_size, buf.numel(),
+                                               ctypes.c_void_p(buf.data_ptr()), ops._stream()))
         return buf
     gathered = torch.empty((world_size,) + tuple(buf.shape), dtype=buf.dtype, device=buf.device)
     dist.all_gather(list(gathered.unbind(0)), buf.contiguous())
