@@ -194,6 +194,23 @@ int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nomi
                               double barr_uphor_ratio, double barr_nu_nubar_ratio, int64_t n, float *d_nu_flux,
                               void *stream);
 
+/* The same for up to PISAB_MAX_BATCH flavour containers in ONE launch (a fit that floats the flux systematics
+ * re-evaluates nu_flux for every hypothesis; twelve launches per template dominate an analysis-size sample). */
+typedef struct pisab_flux_item {
+    const double *d_terms;            /* [n][4] from pisab_flux_barr_terms_*, 32-byte aligned           */
+    const void *d_nu_flux_nominal;    /* [n][2] of the call's storage type                                */
+    const void *d_nubar_flux_nominal; /* [n][2]                                                           */
+    void *d_nu_flux;                  /* [n][2] output                                                    */
+    int64_t n;
+    int32_t nubar, pad;
+} pisab_flux_item_t;
+int pisab_flux_barr_apply_batch_f64(const pisab_flux_item_t *items, int32_t n_items, double nue_numu_ratio,
+                                    double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                                    double barr_nu_nubar_ratio, void *stream);
+int pisab_flux_barr_apply_batch_f32(const pisab_flux_item_t *items, int32_t n_items, double nue_numu_ratio,
+                                    double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                                    double barr_nu_nubar_ratio, void *stream);
+
 /* ---- flux.honda_ip (pisa/stages/flux/honda_ip.py:86-104, pisa/utils/flux_weights.py:267-350) ---------- */
 /* calculate_2d_flux_weights for all four primaries of one azimuth-averaged Honda table in one pass:
  * d_nu_flux_nominal[n,2] = (nue, numu), d_nubar_flux_nominal[n,2] = (nuebar, numubar).
@@ -296,6 +313,22 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
                                   const pisab_container_t *containers, int32_t n_containers,
                                   int32_t n_bins, double *d_hist, void *d_workspace,
                                   int64_t workspace_bytes, void *stream);
+
+/* One hypothesis of a fit in ONE call and two launches: the batched template kernel, then one kernel that
+ * reduces the per-block partial histograms, applies the optional per-bin detector-systematics scales of
+ * discr_sys.hypersurfaces (pisa/stages/discr_sys/hypersurfaces.py:219-243; d_bin_scales [n_containers][n_bins] or NULL:
+ * sum w -> max(s * sum w, 0), sum w^2 -> s^2 sum w^2), sums the containers (MapSet sum, sumw2 errors) and evaluates
+ * mod_chi2 (pisa/utils/stats.py:651-695) against d_observed [n_bins] in its last-arriving block.  Outputs: d_hist
+ * [n_containers][2][n_bins] (required), d_total [2][n_bins] (optional), d_chi2 one double (optional when d_observed is
+ * NULL).  n_bins <= PISAB_DET_MAX_BINS.  Launches of one device must come from one stream at a time. */
+int pisab_reweight_hist_chi2_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream);
+int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* mod_chi2 (pisa/utils/stats.py:651-695) on device for the scan driver:
  * sum_b (obs-exp)^2 / (sigma^2 + max(exp,1e-10)); result is one double on the device. */

@@ -72,6 +72,12 @@ class ContainerDesc(ctypes.Structure):
                 ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32)]
 
 
+class FluxItem(ctypes.Structure):
+    """pisab_flux_item_t -- one flavour container of a batched flux.barr_simple evaluation."""
+    _fields_ = [("d_terms", c_vp), ("d_nu_flux_nominal", c_vp), ("d_nubar_flux_nominal", c_vp), ("d_nu_flux", c_vp),
+                ("n", c_i64), ("nubar", c_i32), ("pad", c_i32)]
+
+
 MAX_BATCH = 16
 
 _lib = None
@@ -99,12 +105,16 @@ _SIGNATURES = {
                                        c_vp]),
     "pisab_flux_barr_terms": (c_i32, [c_vp, c_vp, c_i64, c_vp, c_vp]),
     "pisab_flux_barr_apply": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, c_vp, c_vp]),
+    "pisab_flux_barr_apply_batch": (c_i32, [ctypes.POINTER(FluxItem), c_i32, c_dbl, c_dbl, c_dbl, c_dbl, c_dbl, c_vp]),
     "pisab_flux_honda_2d": (c_i32, [c_vp, c_i32, c_vp, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_scan": (c_i32, [ctypes.POINTER(OscConsts), c_i32, ctypes.POINTER(Earth),
                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "pisab_hist_accumulate_planned": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_scale_weights": (c_i32, [c_vp, c_dbl, c_i64, c_vp, c_vp]),
     "pisab_hist_transform": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "pisab_reweight_hist_chi2": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
+                                         ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         c_i64, c_vp]),
     "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
                                           ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
 }

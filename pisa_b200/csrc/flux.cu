@@ -144,12 +144,11 @@ __device__ __forceinline__ void ratio_scale_fast(double scale, double in1, doubl
 }
 
 template <typename IO>
-__global__ void __launch_bounds__(256)
-flux_barr_apply_kernel(const __grid_constant__ BarrTable T, const double *__restrict__ terms,
-                       const IO *__restrict__ nu_nom, const IO *__restrict__ nubar_nom, int nubar, int64_t n,
-                       IO *__restrict__ out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+__device__ __forceinline__ void flux_barr_apply_range(const BarrTable &T, const double *__restrict__ terms,
+                                                      const IO *__restrict__ nu_nom, const IO *__restrict__ nubar_nom,
+                                                      int nubar, int64_t n, IO *__restrict__ out, int64_t first,
+                                                      int64_t stride) {
+    for (int64_t i = first; i < n; i += stride) {
         const double2 ta = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i);
         const double2 tb = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i + 1);
         struct { double x, y, z, w; } t = {ta.x, ta.y, tb.x, tb.y};
@@ -170,6 +169,30 @@ flux_barr_apply_kernel(const __grid_constant__ BarrTable T, const double *__rest
         out[2 * i] = (IO)(o0 * idx_scale);
         out[2 * i + 1] = (IO)(o1 * idx_scale);
     }
+}
+
+template <typename IO>
+__global__ void __launch_bounds__(256)
+flux_barr_apply_kernel(const __grid_constant__ BarrTable T, const double *__restrict__ terms,
+                       const IO *__restrict__ nu_nom, const IO *__restrict__ nubar_nom, int nubar, int64_t n,
+                       IO *__restrict__ out) {
+    flux_barr_apply_range<IO>(T, terms, nu_nom, nubar_nom, nubar, n, out, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                              (int64_t)gridDim.x * blockDim.x);
+}
+
+// all flavour containers of a template in ONE launch (a fit that floats the flux systematics re-evaluates nu_flux for
+// every hypothesis: 12 launches per template dominate an analysis-size sample): block -> (container, rank)
+struct FluxBatch {
+    int32_t n_containers, blocks_per_container;
+    struct Item { const double *terms; const void *nu_nom, *nubar_nom; void *out; int64_t n; int32_t nubar, pad; } c[PISAB_MAX_BATCH];
+};
+template <typename IO>
+__global__ void __launch_bounds__(256)
+flux_barr_apply_batch_kernel(const __grid_constant__ BarrTable T, const __grid_constant__ FluxBatch B) {
+    const int ci = blockIdx.x / B.blocks_per_container, r = blockIdx.x - ci * B.blocks_per_container;
+    const FluxBatch::Item &C = B.c[ci];
+    flux_barr_apply_range<IO>(T, C.terms, (const IO *)C.nu_nom, (const IO *)C.nubar_nom, C.nubar, C.n, (IO *)C.out,
+                              (int64_t)r * blockDim.x + threadIdx.x, (int64_t)B.blocks_per_container * blockDim.x);
 }
 
 static void fill_barr_table(BarrTable &T, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,
@@ -216,6 +239,36 @@ static int flux_apply_impl(const double *d_terms, const IO *d_nu, const IO *d_nu
     BarrTable T;
     fill_barr_table(T, nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys);
     flux_barr_apply_kernel<IO><<<flux_grid(n), 256, 0, (cudaStream_t)stream>>>(T, d_terms, d_nu, d_nubar, nubar, n, d_out);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
+template <typename IO>
+static int flux_apply_batch_impl(const pisab_flux_item_t *items, int32_t n_items, double nue_numu_ratio,
+                                 double nu_nubar_ratio, double delta_index, double uphor, double nubar_sys, void *stream) {
+    if (!items || n_items < 1 || n_items > PISAB_MAX_BATCH) { set_error("flux batch: 1..%d containers", PISAB_MAX_BATCH); return PISAB_ERR_ARG; }
+    FluxBatch B = {};
+    B.n_containers = n_items;
+    int64_t n_max = 0;
+    for (int c = 0; c < n_items; ++c) {
+        const pisab_flux_item_t &S = items[c];
+        if (S.n < 0 || (S.n > 0 && (!S.d_terms || !S.d_nu_flux_nominal || !S.d_nubar_flux_nominal || !S.d_nu_flux))) { set_error("flux batch: container %d: bad event arrays", c); return PISAB_ERR_ARG; }
+        if (S.nubar != 1 && S.nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
+        if ((uintptr_t)S.d_terms % 32 != 0) { set_error("d_terms must be 32-byte aligned"); return PISAB_ERR_ARG; }
+        B.c[c].terms = S.d_terms; B.c[c].nu_nom = S.d_nu_flux_nominal; B.c[c].nubar_nom = S.d_nubar_flux_nominal;
+        B.c[c].out = S.d_nu_flux; B.c[c].n = S.n; B.c[c].nubar = S.nubar;
+        if (S.n > n_max) n_max = S.n;
+    }
+    if (n_max == 0) return PISAB_OK;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    int64_t bpc = (n_max + 255) / 256;
+    const int64_t cap = ((int64_t)sms * 8 + n_items - 1) / n_items;
+    if (bpc > cap) bpc = cap;
+    B.blocks_per_container = (int32_t)bpc;
+    BarrTable T;
+    fill_barr_table(T, nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys);
+    flux_barr_apply_batch_kernel<IO><<<(unsigned)(bpc * n_items), 256, 0, (cudaStream_t)stream>>>(T, B);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
@@ -270,6 +323,18 @@ int pisab_flux_barr_apply_f64(const double *d_terms, const double *d_nu_flux_nom
                               void *stream) {
     return flux_apply_impl<double>(d_terms, d_nu_flux_nominal, d_nubar_flux_nominal, nubar, nue_numu_ratio, nu_nubar_ratio,
                                    delta_index, barr_uphor_ratio, barr_nu_nubar_ratio, n, d_nu_flux, stream);
+}
+int pisab_flux_barr_apply_batch_f64(const pisab_flux_item_t *items, int32_t n_items, double nue_numu_ratio,
+                                    double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                                    double barr_nu_nubar_ratio, void *stream) {
+    return flux_apply_batch_impl<double>(items, n_items, nue_numu_ratio, nu_nubar_ratio, delta_index, barr_uphor_ratio,
+                                         barr_nu_nubar_ratio, stream);
+}
+int pisab_flux_barr_apply_batch_f32(const pisab_flux_item_t *items, int32_t n_items, double nue_numu_ratio,
+                                    double nu_nubar_ratio, double delta_index, double barr_uphor_ratio,
+                                    double barr_nu_nubar_ratio, void *stream) {
+    return flux_apply_batch_impl<float>(items, n_items, nue_numu_ratio, nu_nubar_ratio, delta_index, barr_uphor_ratio,
+                                        barr_nu_nubar_ratio, stream);
 }
 int pisab_flux_barr_apply_f32(const double *d_terms, const float *d_nu_flux_nominal, const float *d_nubar_flux_nominal,
                               int32_t nubar, double nue_numu_ratio, double nu_nubar_ratio, double delta_index,

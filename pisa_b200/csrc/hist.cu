@@ -456,6 +456,76 @@ hist_reduce_batch_kernel(const double *__restrict__ partials, int n_blocks, int 
     if (lane == 0) out[v] = s;
 }
 
+// Fit-loop epilogue in ONE launch: the per-container reduction of hist_reduce_batch_kernel, the per-bin
+// detector-systematics scale of discr_sys.hypersurfaces (hypersurfaces.py:219-243: errors *= s, weights =
+// clip(weights * s, 0); here sum w *= max(s, 0)-clipped product and sum w^2 *= s^2), the MapSet sum over containers
+// and mod_chi2 against the observed map (stats.py:651-695).  Blocks reduce their values as before; the LAST block to
+// finish (device-scope arrival counter) owns the epilogue, so no second launch is needed and nothing synchronises.
+__global__ void __launch_bounds__(256)
+hist_reduce_chi2_kernel(const double *__restrict__ partials, int n_blocks, int n_bins, int n_containers,
+                        const double *__restrict__ bin_scales, const double *__restrict__ observed,
+                        double *__restrict__ out, double *__restrict__ total, double *__restrict__ chi2,
+                        unsigned *__restrict__ arrive) {
+    const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // warp-uniform: (container, plane, bin)
+    const int lane = threadIdx.x & 31;
+    if (v < n_containers * 2 * n_bins) {
+        const int c = v / (2 * n_bins), b = v - c * 2 * n_bins;
+        const double *src = partials + (size_t)c * n_blocks * 2 * n_bins + b;
+        double s = 0.0;
+        for (int k = lane; k < n_blocks; k += 32) s += __ldg(src + (size_t)k * 2 * n_bins);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            if (bin_scales) {
+                const double sc = bin_scales[(size_t)c * n_bins + (b < n_bins ? b : b - n_bins)];
+                s = b < n_bins ? fmax(s * sc, 0.0) : s * sc * sc;
+            }
+            out[v] = s;
+        }
+    }
+    __shared__ bool s_last;
+    __shared__ double s_acc[256];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *arrive = 0; // the next launch on this stream starts from zero
+    __threadfence();
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        double e = 0.0, sig2 = 0.0;
+        for (int c = 0; c < n_containers; ++c) { // container order: fixed
+            e += __ldcg(out + ((size_t)c * 2) * n_bins + b);
+            sig2 += __ldcg(out + ((size_t)c * 2 + 1) * n_bins + b);
+        }
+        if (total) { total[b] = e; total[n_bins + b] = sig2; }
+        if (observed) {
+            e = fmax(e, 1e-10);
+            const double d = observed[b] - e;
+            acc += d * d / (sig2 + e);
+        }
+    }
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s_acc[threadIdx.x] += s_acc[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && chi2) chi2[0] = s_acc[0];
+}
+
+int hist_reduce_chi2(const double *d_partials, int n_blocks, int n_bins, int n_containers, const double *d_bin_scales,
+                     const double *d_observed, double *d_out, double *d_total, double *d_chi2, unsigned *d_arrive,
+                     cudaStream_t s) {
+    const int warps = n_containers * 2 * n_bins;
+    hist_reduce_chi2_kernel<<<(warps * 32 + 255) / 256, 256, 0, s>>>(d_partials, n_blocks, n_bins, n_containers,
+                                                                      d_bin_scales, d_observed, d_out, d_total, d_chi2, d_arrive);
+    note_launch();
+    PISAB_CUDA_CHECK(cudaGetLastError());
+    return PISAB_OK;
+}
+
 int hist_reduce_batch(const double *d_partials, int n_blocks, int n_bins, int n_containers, double *d_out,
                       cudaStream_t s) {
     const int warps = n_containers * 2 * n_bins;

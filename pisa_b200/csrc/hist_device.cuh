@@ -113,5 +113,9 @@ int hist_reduce_partials(const double *d_partials, int n_blocks, int n_bins, dou
 
 int hist_reduce_batch(const double *d_partials, int n_blocks, int n_bins, int n_containers, double *d_out,
                       cudaStream_t s);
+// the same reduction + per-bin scales + container sum + mod_chi2 in one launch (last-block epilogue)
+int hist_reduce_chi2(const double *d_partials, int n_blocks, int n_bins, int n_containers, const double *d_bin_scales,
+                     const double *d_observed, double *d_out, double *d_total, double *d_chi2, unsigned *d_arrive,
+                     cudaStream_t s);
 
 } // namespace pisab

@@ -606,11 +606,33 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
     return PISAB_OK;
 }
 
+// Arrival counter of the reduce + chi2 epilogue kernel: one zero-initialised word per device, owned by the library
+// (the kernel resets it to zero before it exits, so launches on ONE stream can reuse it; concurrent epilogues on
+// several streams of the same device are not supported).
+static unsigned *epilogue_counter() {
+    static unsigned *counters[64] = {nullptr};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!counters[dev]) {
+        unsigned *p = nullptr;
+        if (cudaMalloc(&p, 256) != cudaSuccess) return nullptr;
+        if (cudaMemset(p, 0, 256) != cudaSuccess) return nullptr;
+        counters[dev] = p;
+    }
+    return counters[dev];
+}
+
+// optional fit-loop epilogue of a batched template (pisab_reweight_hist_chi2_*)
+struct Chi2Epilogue {
+    const double *d_bin_scales, *d_observed;
+    double *d_total, *d_chi2;
+};
+
 template <typename IO>
 static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     const FusedBatch<IO> &batch, int64_t n_max, double *d_batch_out,
                                     double *d_hist, double *d_hist_w2, void *d_workspace,
-                                    int64_t workspace_bytes, void *stream) {
+                                    int64_t workspace_bytes, void *stream, const Chi2Epilogue *epi = nullptr) {
     const int n_bins = batch.n_bins;
     if (n_bins < 1) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
     const bool large = n_bins > PISAB_DET_MAX_BINS;
@@ -723,6 +745,12 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
+    if (d_batch_out && epi) {
+        unsigned *d_arrive = epilogue_counter();
+        if (!d_arrive) { set_error("could not allocate the epilogue arrival counter"); return PISAB_ERR_CUDA; }
+        return hist_reduce_chi2((const double *)d_workspace, ranks, n_bins, batch.n_containers, epi->d_bin_scales,
+                                epi->d_observed, d_batch_out, epi->d_total, epi->d_chi2, d_arrive, s);
+    }
     if (d_batch_out)
         return hist_reduce_batch((const double *)d_workspace, ranks, n_bins, batch.n_containers, d_batch_out, s);
     return hist_reduce_partials((const double *)d_workspace, ranks, n_bins, d_hist, d_hist_w2, s);
@@ -754,7 +782,7 @@ template <typename IO>
 static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                    const pisab_container_t *containers, int32_t n_containers,
                                    int32_t n_bins, double *d_hist, void *d_workspace,
-                                   int64_t workspace_bytes, void *stream) {
+                                   int64_t workspace_bytes, void *stream, const Chi2Epilogue *epi = nullptr) {
     if (!containers || n_containers < 1 || n_containers > PISAB_MAX_BATCH || !d_hist) {
         set_error("n_containers must be in [1, %d] and the output non-null", PISAB_MAX_BATCH);
         return PISAB_ERR_ARG;
@@ -773,8 +801,12 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
         C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav;
         if (S.n > n_max) n_max = S.n;
     }
+    if (epi && n_bins > PISAB_DET_MAX_BINS) {
+        set_error("the chi2 epilogue supports up to %d bins", PISAB_DET_MAX_BINS);
+        return PISAB_ERR_UNSUPPORTED;
+    }
     return reweight_hist_batch_impl<IO>(consts, earth, batch, n_max, d_hist, nullptr, nullptr, d_workspace,
-                                        workspace_bytes, stream);
+                                        workspace_bytes, stream, epi);
 }
 
 // ranks (blocks) per (template, container) of a scan: every thread should see >= 8 events of the largest
@@ -928,6 +960,23 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
                                   int64_t workspace_bytes, void *stream) {
     return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
                                           workspace_bytes, stream);
+}
+
+int pisab_reweight_hist_chi2_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream) {
+    const Chi2Epilogue epi{d_bin_scales, d_observed, d_total, d_chi2};
+    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                           workspace_bytes, stream, &epi);
+}
+int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
+                                 const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
+                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream) {
+    const Chi2Epilogue epi{d_bin_scales, d_observed, d_total, d_chi2};
+    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                          workspace_bytes, stream, &epi);
 }
 
 int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_containers, int32_t n_bins, int64_t n_max) {

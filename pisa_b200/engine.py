@@ -97,6 +97,7 @@ class ReweightEngine:
         self.blocks.append(blk)
         self._out = None
         self._batches = None
+        self._flux_batches = None
         return blk
 
     @property
@@ -113,13 +114,18 @@ class ReweightEngine:
                         Barr_nu_nubar_ratio=0.0):
         """flux.barr_simple for every container registered with nominal fluxes: rewrites ``nu_flux`` in place
         (``pisab_flux_barr_apply``, 80 B/event at ~90 % of the HBM roofline)."""
-        for blk in self.blocks:
-            d = blk.dev
-            if "flux_barr_terms" not in d:
-                raise ValueError("container %s was registered without nominal fluxes" % blk.name)
-            ops.flux_barr_apply(d["flux_barr_terms"], d["nu_flux_nominal"], d["nubar_flux_nominal"], blk.nubar,
-                                nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio, Barr_nu_nubar_ratio,
-                                out=d["nu_flux"])
+        if getattr(self, "_flux_batches", None) is None or self._flux_batches[0] != len(self.blocks):
+            for blk in self.blocks:
+                if "flux_barr_terms" not in blk.dev:
+                    raise ValueError("container %s was registered without nominal fluxes" % blk.name)
+            chunks = [self.blocks[lo:lo + ops.MAX_BATCH] for lo in range(0, len(self.blocks), ops.MAX_BATCH)]
+            self._flux_batches = (len(self.blocks), [ops.FluxBatch([dict(
+                terms=b.dev["flux_barr_terms"], nu_flux_nominal=b.dev["nu_flux_nominal"],
+                nubar_flux_nominal=b.dev["nubar_flux_nominal"], nu_flux=b.dev["nu_flux"], nubar=b.nubar) for b in ch])
+                for ch in chunks])
+        for fb in self._flux_batches[1]:      # ONE launch for all containers of a template
+            ops.flux_barr_apply_batch(fb, nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio,
+                                      Barr_nu_nubar_ratio)
 
     def set_scales(self, scales):
         """Per-container factor folded into the weights (aeff.aeff: livetime * aeff_scale * norms)."""
@@ -161,6 +167,27 @@ class ReweightEngine:
         if allreduce:
             self.allreduce(out)
         return out
+
+    def evaluate_chi2(self, consts, observed, chi2_out=None, bin_scales=None, allreduce=None):
+        """One hypothesis of a fit: template + ``mod_chi2`` against ``observed`` ([n_bins] float64 device tensor) with
+        nothing synchronising.  On one rank this is ONE library call and two launches (``pisab_reweight_hist_chi2``:
+        template kernel, then reduce + per-bin ``bin_scales`` + container sum + chi2 in one kernel); with events sharded
+        over GPUs the exchange sits between the reduction and the chi2 (three launches).  Returns (hist, chi2)."""
+        batches = self._get_batches()
+        out = self._result_buffer()
+        if chi2_out is None:
+            chi2_out = torch.empty(1, dtype=torch.float64, device=self.device)
+        if len(batches) == 1 and not self._want_exchange(allreduce) and self.n_bins <= _lib.DET_MAX_BINS:
+            ops.reweight_hist_chi2(consts, self.earth, batches[0][1], observed, out=out, chi2=chi2_out,
+                                   bin_scales=bin_scales)
+            return out, chi2_out
+        out = self.evaluate(consts, allreduce=allreduce)
+        if bin_scales is not None:
+            out = out.clone()
+            out[:, 0] = torch.clamp(out[:, 0] * bin_scales, min=0.0)
+            out[:, 1] = out[:, 1] * bin_scales * bin_scales
+        ops.template_chi2(out, observed, out=chi2_out)
+        return out, chi2_out
 
     def evaluate_many(self, consts_list, allreduce=None):
         """P hypotheses in ONE launch (``pisab_reweight_hist_scan``): returns ``[P, n_containers, 2, n_bins]``.

@@ -138,6 +138,36 @@ def flux_barr_apply(terms, nu_flux_nominal, nubar_flux_nominal, nubar, nue_numu_
     return out
 
 
+class FluxBatch:
+    """Descriptor array for ``flux_barr_apply_batch``: the flux.barr_simple re-evaluation of up to MAX_BATCH containers
+    in one launch.  items: dicts with terms, nu_flux_nominal, nubar_flux_nominal, nu_flux (output), nubar."""
+
+    def __init__(self, items):
+        if not 1 <= len(items) <= MAX_BATCH:
+            raise ValueError("a batch holds 1..%d containers" % MAX_BATCH)
+        self.n = len(items)
+        self.desc = (_lib.FluxItem * self.n)()
+        self._keep, dt = [], None
+        for d, c in zip(self.desc, items):
+            t = _chk(c["terms"], "terms", torch.float64)
+            nu = _chk(c["nu_flux_nominal"], "nu_flux_nominal")
+            dt = dt or nu.dtype
+            nb, out = _chk(c["nubar_flux_nominal"], "nubar_flux_nominal", dt), _chk(c["nu_flux"], "nu_flux", dt)
+            n = t.shape[0]
+            if t.shape != (n, 4) or nu.shape != (n, 2) or nb.shape != (n, 2) or out.shape != (n, 2):
+                raise ValueError("inconsistent event array shapes")
+            d.d_terms, d.d_nu_flux_nominal, d.d_nubar_flux_nominal = t.data_ptr(), nu.data_ptr(), nb.data_ptr()
+            d.d_nu_flux, d.n, d.nubar = out.data_ptr(), n, int(c["nubar"])
+            self._keep.append((t, nu, nb, out))
+        self.dtype = dt
+
+
+def flux_barr_apply_batch(batch, nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio, Barr_nu_nubar_ratio):
+    f = _lib.fn("pisab_flux_barr_apply_batch", batch.dtype)
+    _lib.check(f(batch.desc, batch.n, float(nue_numu_ratio), float(nu_nubar_ratio), float(delta_index),
+                 float(Barr_uphor_ratio), float(Barr_nu_nubar_ratio), _stream()))
+
+
 def flux_honda_2d(table, true_energy, true_coszen, nu_flux_nominal=None, nubar_flux_nominal=None):
     """``calculate_2d_flux_weights`` (flux_weights.py:267-350) for the four primaries of ``table``
     (a ``pisa_b200.utils.flux_weights.HondaTable2D``): returns (nu_flux_nominal, nubar_flux_nominal), [n, 2] each."""
@@ -414,9 +444,9 @@ def hist_accumulate(index, weights, n_bins, want_w2=True, plan=None):
     (``hist_plan`` of the same index) the bin-sorted-tile kernel is used."""
     _chk(index, "index", torch.int32)
     n = index.numel()
+    if plan is not None and (plan.n != n or plan.n_bins != int(n_bins)):
+        raise ValueError("the plan was built for %d events / %d bins" % (plan.n, plan.n_bins))
     if plan is not None and weights is not None and weights.data_ptr() % 16 == 0:
-        if plan.n != n or plan.n_bins != int(n_bins):
-            raise ValueError("the plan was built for %d events / %d bins" % (plan.n, plan.n_bins))
         _chk(weights, "weights")
         if weights.numel() != n:
             raise ValueError("weights and index must have the same length")
@@ -536,6 +566,33 @@ def reweight_hist_batch(consts, earth, batch, out=None):
     _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(out), _ptr(ws),
                  ws.numel(), _stream()))
     return out
+
+
+def reweight_hist_chi2(consts, earth, batch, observed, out=None, chi2=None, total=None, bin_scales=None):
+    """One hypothesis of a fit in one call: all containers of ``batch`` in one launch, then ONE kernel that reduces
+    the partial histograms, applies optional per-bin scales (``bin_scales`` [n_containers, n_bins], the
+    discr_sys.hypersurfaces factors), sums the containers and evaluates ``mod_chi2`` against ``observed`` [n_bins]
+    into ``chi2`` (1-element float64 tensor or a slot of a scan's result array).  Returns (hist, chi2)."""
+    if out is None:
+        out = torch.empty((batch.n, 2, batch.n_bins), dtype=torch.float64, device=batch.device)
+    _chk(out, "out", torch.float64)
+    if out.numel() != batch.n * 2 * batch.n_bins:
+        raise ValueError("out must hold [n_containers, 2, n_bins] doubles")
+    _chk(observed, "observed", torch.float64, allow_none=True)
+    if observed is not None and observed.numel() != batch.n_bins:
+        raise ValueError("observed must be [n_bins]")
+    if chi2 is None and observed is not None:
+        chi2 = torch.empty(1, dtype=torch.float64, device=batch.device)
+    _chk(chi2, "chi2", torch.float64, allow_none=True)
+    _chk(total, "total", torch.float64, allow_none=True)
+    _chk(bin_scales, "bin_scales", torch.float64, allow_none=True)
+    if bin_scales is not None and bin_scales.numel() != batch.n * batch.n_bins:
+        raise ValueError("bin_scales must be [n_containers, n_bins]")
+    ws = _workspace(batch.device, 0, batch.n_bins, batch.n)
+    f = _lib.fn("pisab_reweight_hist_chi2", batch.dtype)
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(bin_scales),
+                 _ptr(observed), _ptr(out), _ptr(total), _ptr(chi2), _ptr(ws), ws.numel(), _stream()))
+    return out, chi2
 
 
 _scan_ws = {}

@@ -120,8 +120,7 @@ def scan_chi2(engine, observed, points, fixed, mat_pot=None, batch=64):
     if batch <= 1:
         for i, (t23, dm31) in enumerate(points):
             consts = osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
-            hist = engine.evaluate(consts)
-            ops.template_chi2(hist, observed, out=out[i:i + 1])
+            engine.evaluate_chi2(consts, observed, chi2_out=out[i:i + 1])   # one call, two launches per hypothesis
         return out
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
     for lo in range(0, len(points), batch):

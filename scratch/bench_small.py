@@ -39,6 +39,9 @@ for per in (10_000, 100_000):
     out = torch.empty(1, dtype=torch.float64, device=dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     eng.evaluate(consts); torch.cuda.synchronize(); e0.record(); eng.evaluate(consts); e1.record(); torch.cuda.synchronize()
+    print("events/template %8d: ONE-CALL evaluate_chi2 (template + reduce/chi2 epilogue) %6.1f us | with osc_consts %6.1f us"
+          % (12 * per, t(lambda: eng.evaluate_chi2(consts, obs, chi2_out=out)),
+             t(lambda: eng.evaluate_chi2(scan.osc_consts(theta23=0.74, dm31=2.5e-3, **fixed), obs, chi2_out=out))), flush=True)
     print("events/template %8d: osc_consts %6.1f us | evaluate (host+GPU, pipelined) %6.1f us | + chi2 %6.1f us | full (consts+eval+chi2) %6.1f us | GPU time of one evaluate %6.1f us"
           % (12 * per, t(lambda: scan.osc_consts(theta23=0.74, dm31=2.5e-3, **fixed)), t(lambda: eng.evaluate(consts)),
              t(lambda: ops.template_chi2(eng.evaluate(consts), obs, out=out)),

@@ -194,3 +194,45 @@ def test_fused_pipeline_with_hist_options(tmp_path, hist_extra, loader_extra):
                 assert np.allclose(b, a, rtol=1e-10, atol=0), (cs.name, key, hist_extra)
             if "unweighted" in hist_extra and not loader_extra:
                 assert float(cs["weights"].sum()) == cs["weights"].sum().round().item()   # plain counts
+
+
+def test_one_call_template_chi2_with_bin_scales():
+    """pisab_reweight_hist_chi2: template kernel + ONE epilogue kernel (reduce, per-bin hypersurface scales, container
+    sum, mod_chi2 in the last-arriving block) against the separate launches; repeated calls reuse the arrival counter."""
+    _need_gpu()
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(os.path.join(ROOT, "pisa_b200", "resources", syn.EARTH["earth_model"]), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = L.earth_struct()
+    binning, _keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    eng = ReweightEngine(earth, 128, np.float64, dev)
+    for c, (name, nubar, flav) in enumerate(syn.CONTAINERS):
+        ev = syn.make_events_torch(9000 + 500 * c, seed=60 + c, dtype=np.float64, device=dev)
+        idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
+        eng.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"], idx)
+
+    def consts(theta23):
+        dm, mix, mp = syn.osc_matrices(dict(syn.NUFIT20_NH, theta23=theta23))
+        return ops.OscConsts.from_matrices(dm, mix, mp)
+    observed = eng.evaluate(consts(45.0))[:, 0].sum(dim=0).contiguous()
+    g = torch.Generator(device=dev)
+    g.manual_seed(3)
+    scales = (0.7 + 0.6 * torch.rand((12, 128), generator=g, device=dev, dtype=torch.float64))
+    scales[3, 5] = -0.2                                    # a negative scale: weights clipped at 0, errors scaled by |s|
+    for theta in (40.0, 45.0, 51.0, 40.0):
+        c = consts(theta)
+        plain = eng.evaluate(c).clone()
+        want = ops.template_chi2(plain, observed).clone()
+        hist, chi2 = eng.evaluate_chi2(c, observed)
+        assert torch.equal(hist, plain) and torch.equal(chi2, want), theta      # same reductions, same order
+        hist_s, chi2_s = eng.evaluate_chi2(c, observed, bin_scales=scales)
+        ref = plain.clone()
+        ref[:, 0] = torch.clamp(plain[:, 0] * scales, min=0.0)
+        ref[:, 1] = plain[:, 1] * scales * scales
+        assert torch.allclose(hist_s, ref, rtol=1e-15, atol=0)
+        assert torch.allclose(chi2_s, ops.template_chi2(ref, observed), rtol=1e-13, atol=0)
+    assert float(eng.evaluate_chi2(consts(45.0), observed)[1]) < 1e-20           # Asimov point
