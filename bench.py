@@ -467,6 +467,9 @@ def run_variants(h, args):
                   "dtype": "f32", "math": "mixed: FP64 eigenvalues / phase arguments / geometry, float32 matrices, "
                                           "products and state (csrc/prob3_mp.cuh)",
                   "max_rel_diff_binned_weights_vs_f64_run": rel,
+                  "max_rel_diff_note": "includes events that the float32 rounding of the reco coordinates moves across a "
+                                       "bin edge (one event in ~1e4 per bin); the arithmetic alone: <= 1e-5 per "
+                                       "probability, tests/test_gpu_prob3.py",
                   "value_f32_storage_fp64_math": n * h.world / (ms_s * 1e-3), "steps": steps, "warmup": warmup}
     del eng32, res
     torch.cuda.empty_cache()
@@ -574,6 +577,7 @@ def run_native(args):
     peak_flops = max(ops.fp64_peak_probe(20000)[0] for _ in range(3))   # best of 3: the first probe can catch a clock ramp
     kname = "reweight_hist_kernel<%s>" % ("double" if args.dtype == "f64" else "float")
     traffic = pipe_active = executed_flop = tr_src = None
+    tr = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tr = json.load(f)[kname]
@@ -603,6 +607,21 @@ def run_native(args):
                                         "peak; > 1 because this kernel's formulation executes ~6.6x fewer FLOPs",
         "algorithmic_bytes_per_event": bytes_event, "hbm_gbs": bytes_event * n_gpu / (launch_ms * 1e-3) / 1e9,
     }
+
+    if args.dtype == "f32" and args.f32_math == "mixed" and tr.get("warp_instructions_per_warp_event"):
+        # the FP32 mode is bound by the ISSUE port (one warp instruction per cycle per SM sub-partition;
+        # profiles/r02_pipe_mix.txt), not by the FP64 pipe: report that fraction as `frac`
+        sms = ops.device_info()["sm_count"]
+        clk = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        issued = tr["warp_instructions_per_warp_event"] * (n_gpu / 32.0) / (launch_ms * 1e-3) / (sms * 4 * clk)
+        roofline.update({
+            "bound": "issue", "achieved": issued, "peak": 1.0, "unit": "warp-instructions/cycle/SM sub-partition",
+            "frac": issued, "frac_is": "executed warp instructions per event (ncu capture below) x events / launch time / "
+                                       "(SMs x 4 sub-partitions x SM clock): the issue-port utilisation",
+            "issue_active_pct_ncu": tr.get("issue_active_pct"),
+            "executed_fp32_flops_per_event_ncu": tr.get("executed_fp32_flop_per_event"),
+            "executed_fp64_tflops": None if executed is None else executed / 1e12,
+        })
 
     # ---- end to end (host buffers) -------------------------------------------------------------
     e2e = e2e_changed = None

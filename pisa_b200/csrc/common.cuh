@@ -44,10 +44,9 @@ struct Herm3 {
     double d0, d1, d2;
     double r01, i01, r02, i02, r12, i12;
 };
-struct Herm3F { // float image (FP32 mode); 9 floats + 1 pad = 40 bytes, keeps OscTable a multiple of 8 bytes
+struct Herm3F { // float image (FP32 mode)
     float d0, d1, d2;
     float r01, i01, r02, i02, r12, i12;
-    float pad;
 };
 
 // Per-launch constants of the propagation (built on the host from pisab_osc_consts_t).
@@ -69,8 +68,11 @@ struct OscTable {
     double hdm21, hdm31; // 0.5 * dm21, 0.5 * dm31
     double vac_ok;       // 1.0 when the shortcut is valid (lri_pot == 0), else 0.0
     double std_matter;   // 1.0 when vm = diag(a, 0, 0) (no NSI): layers only move H[0][0]
-    Herm3F pr2f, pr3f;   // the projectors rounded to float (FP32 mode: saves 12 conversions per event)
+    // (keep this struct at 464 bytes: the FP64 scan kernel stages it in STATIC shared memory and fits two blocks per SM
+    // with 48 bytes to spare -- 80 bytes of float projector copies here cost it half its occupancy, -40 %)
 };
+
+static_assert(sizeof(OscTable) == 464, "OscTable feeds the static shared memory of the scan kernel: see the note above");
 
 struct EarthTable {
     int n_radii;

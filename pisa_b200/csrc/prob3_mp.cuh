@@ -337,6 +337,11 @@ struct H0MP {
     }
 };
 
+__device__ __forceinline__ Herm3F herm_to_float(const Herm3 &h) {
+    return Herm3F{(float)h.d0, (float)h.d1, (float)h.d2, (float)h.r01, (float)h.i01,
+                  (float)h.r02, (float)h.i02, (float)h.r12, (float)h.i12};
+}
+
 // Vacuum columns 1 + z2 P2 + z3 P3 (see vacuum_columns) with z_k = exp(-i phi_k) - 1 from expm1i_neg.
 template <int NC, typename PROP>
 __device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, PROP &P) {
@@ -344,7 +349,7 @@ __device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, 
     const CplxF z2 = expm1i_neg(-o.hdm21 * ts), z3 = expm1i_neg(-o.hdm31 * ts);
     // vacuum_columns uses (cos - 1, +sin) of (hdm * ts): exp(+i hdm ts) - 1 = expm1i_neg(-hdm ts)
     const float z2r = z2.re, z2i = z2.im, z3r = z3.re, z3i = z3.im;
-    const Herm3F &A = o.pr2f, &B = o.pr3f;
+    const Herm3F A = herm_to_float(o.pr2), B = herm_to_float(o.pr3);
 #define PISAB_VAC_DIAG(C, DA, DB) \
     P.set_right(C, C, CplxF{fmaf(z2r, DA, fmaf(z3r, DB, 1.0f)), fmaf(z2i, DA, z3i * DB)});
 #define PISAB_VAC_OFF(I, J, AR, AI, BR, BI)                                                                   \

@@ -79,14 +79,6 @@ int build_osc_table(const pisab_osc_consts_t *c, OscTable *out) {
             }
     pack_herm(P[0], 1.0, &out->pr2);
     pack_herm(P[1], 1.0, &out->pr3);
-    for (int k = 0; k < 2; ++k) {
-        const Herm3 &src = k ? out->pr3 : out->pr2;
-        Herm3F &dst = k ? out->pr3f : out->pr2f;
-        dst.d0 = (float)src.d0; dst.d1 = (float)src.d1; dst.d2 = (float)src.d2;
-        dst.r01 = (float)src.r01; dst.i01 = (float)src.i01; dst.r02 = (float)src.r02;
-        dst.i02 = (float)src.i02; dst.r12 = (float)src.r12; dst.i12 = (float)src.i12;
-        dst.pad = 0.0f;
-    }
     out->hdm21 = 0.5 * d[1];
     out->hdm31 = 0.5 * d[2];
     bool lr_zero = true;
