@@ -303,7 +303,15 @@ typedef struct pisab_container {
     int64_t n;
     double scale;
     int32_t nubar, flav;
+    int32_t flags;            /* PISAB_CONTAINER_*                                              */
+    int32_t pad;
 } pisab_container_t;
+/* The caller guarantees: n is even and events 2k and 2k+1 cross the same number of Earth shells
+ * (pisab_layer_count_*), e.g. because the events are sorted by that count and every class was padded to an even size
+ * with zero-weight events.  With float storage and the mixed-precision arithmetic the batched template kernel then
+ * handles TWO events per thread in the lanes of the packed FP32 instructions (same results, bit for bit, as one
+ * event per thread).  A pair that breaks the promise poisons its weights with NaN instead of histogramming them. */
+#define PISAB_CONTAINER_PAIR_ALIGNED 1
 int64_t pisab_reweight_batch_workspace_bytes(int32_t n_containers, int32_t n_bins);
 int pisab_reweight_hist_batch_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                   const pisab_container_t *containers, int32_t n_containers,

@@ -16,6 +16,7 @@ MAX_DIMS = 4
 DET_MAX_BINS = 1024
 DIM_LIN, DIM_LOG, DIM_EDGES = 0, 1, 2
 F32_MATH_FP64, F32_MATH_MIXED = 0, 1
+CONTAINER_PAIR_ALIGNED = 1
 
 c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -69,7 +70,7 @@ class ContainerDesc(ctypes.Structure):
     """pisab_container_t -- one flavour container of a batched template evaluation."""
     _fields_ = [("d_energy", c_vp), ("d_coszen", c_vp), ("d_nu_flux", c_vp), ("d_weights", c_vp),
                 ("d_index", c_vp), ("d_order", c_vp), ("d_weights_out", c_vp), ("n", c_i64),
-                ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32)]
+                ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32), ("flags", c_i32), ("pad", c_i32)]
 
 
 class FluxItem(ctypes.Structure):

@@ -63,7 +63,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 #endif
 template <bool FULL>
 static size_t earth_smem_bytes(size_t io_bytes, bool std_matter, bool mp = false) {
-    if (mp) return (size_t)(FULL ? PropagatorSmemF<3, 3>::kFloat2s : PropagatorSmemF<1, 2>::kFloat2s) * kBlock * sizeof(float2) +
+    if (mp) return (size_t)(FULL ? PropagatorSmemF<3, 3>::kSlots : PropagatorSmemF<1, 2>::kSlots) * kBlock * sizeof(float2) +
                    2 * (size_t)kBlock * io_bytes;
     const size_t doubles = (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) +
                                     (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
@@ -83,7 +83,7 @@ prob3_earth_kernel(const __grid_constant__ OscTable osc, const __grid_constant__
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn_earth);
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn_earth + PropagatorSmem<NR, NC>::kDoubles * kBlock);
     float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn_earth); // FP32 mode: float2 state columns
-    IO *s_e = MP ? reinterpret_cast<IO *>(&s_statef[PropagatorSmemF<NR, NC>::kFloat2s][0])
+    IO *s_e = MP ? reinterpret_cast<IO *>(&s_statef[PropagatorSmemF<NR, NC>::kSlots][0])
                  : reinterpret_cast<IO *>(&s_h0[H0Smem<STD>::kDoubles][0]);
     IO *s_cz = s_e + kBlock;
     copy_earth(earth, &s_earth);
@@ -209,7 +209,7 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 template <typename IO>
 static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false) {
     // (FP32 mode: 9 float2 of state per thread = 9 doubles' worth; the Hamiltonian lives in registers)
-    const size_t doubles = mp ? (size_t)PropagatorSmemF<1, 2>::kFloat2s * kBlock
+    const size_t doubles = mp ? (size_t)PropagatorSmemF<1, 2>::kSlots * kBlock
                               : (size_t)(PropagatorSmem<1, 2>::kDoubles +
                                          (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
@@ -241,6 +241,7 @@ struct FusedContainer {
     int64_t n;
     double scale; // per-container factor folded into the weight (aeff.aeff: livetime * aeff_scale * norms)
     int32_t nubar, flav;
+    int32_t flags; // PISAB_CONTAINER_*
 };
 template <typename IO>
 struct FusedBatch {
@@ -269,7 +270,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     double *s_dyn = s_hist + (LARGE ? 0 : WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double));
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn); // FP32 mode: float2 state columns
-    s_dyn += (MP ? PropagatorSmemF<1, 2>::kFloat2s : PropagatorSmem<1, 2>::kDoubles) * kBlock;
+    s_dyn += (MP ? PropagatorSmemF<1, 2>::kSlots : PropagatorSmem<1, 2>::kDoubles) * kBlock;
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn); // 16-byte aligned: see H0Smem
     if (!MP) s_dyn += H0Smem<STD>::kDoubles * kBlock;   // (FP32 mode: the per-event Hamiltonian lives in registers)
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
@@ -420,6 +421,100 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // costs one or two event latencies instead of one per container.
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
     fused_template_body<IO, STD, PLAIN, MP, LARGE>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds);
+}
+
+// ---- FP32 mode, TWO events per thread (prob3_mp.cuh: the float part of a pair runs in the two lanes of the packed
+// FP32 instructions, halving its issue slots per event; FP64 eigenvalues / phases / geometry stay per event) ----------
+// Requirements, guaranteed by the host (PISAB_CONTAINER_PAIR_ALIGNED): float storage, an even number of events,
+// events 2k and 2k+1 cross the same Earth shells, no `order` indirection, no per-event outputs.
+#ifndef PISAB_PAIR_MIN_BLOCKS
+#define PISAB_PAIR_MIN_BLOCKS 2
+#endif
+static size_t fused_pair_smem_bytes(int n_bins) {
+    return WarpHist::smem_bytes(kBlock, n_bins) + (size_t)kBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + 48);
+}
+
+template <bool STD>
+__device__ __forceinline__ void fused_pair_body(const OscTable &osc, const EarthTable &s_earth,
+                                                const FusedBatch<float> &batch, int ci, int rank, int n_ranks,
+                                                double *__restrict__ partials, double *s_hist) {
+    // dynamic shared memory: [histogram] [state: 9 float4 x block] [flux float4] [e, cz, w: float2 each] [bin int2]
+    const int n_bins = batch.n_bins;
+    unsigned char *s_dyn = reinterpret_cast<unsigned char *>(s_hist) + WarpHist::smem_bytes(kBlock, n_bins);
+    float4(*s_state)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(s_dyn);
+    s_dyn += (size_t)PropagatorSmemP<1, 2>::kSlots * kBlock * sizeof(float4);
+    float4 *s_flux = reinterpret_cast<float4 *>(s_dyn);
+    float2 *s_e = reinterpret_cast<float2 *>(s_flux + kBlock), *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
+    int2 *s_bin = reinterpret_cast<int2 *>(s_w + kBlock);
+    WarpHist wh(s_hist, n_bins);
+    const int tid = threadIdx.x;
+    const int64_t stride = (int64_t)n_ranks * blockDim.x;
+    const int64_t first = (int64_t)rank * blockDim.x + tid;
+    const int64_t warp_first = first - (tid & 31);
+    const FusedContainer<float> &C = batch.c[ci];
+    const float2 *__restrict__ energy = reinterpret_cast<const float2 *>(C.energy);
+    const float2 *__restrict__ coszen = reinterpret_cast<const float2 *>(C.coszen);
+    const float4 *__restrict__ nu_flux = reinterpret_cast<const float4 *>(C.nu_flux);
+    const float2 *__restrict__ weights_in = reinterpret_cast<const float2 *>(C.weights_in);
+    const int2 *__restrict__ index = reinterpret_cast<const int2 *>(C.index);
+    const int64_t n_pairs = C.n >> 1;
+    wh.clear();
+    auto pair_of = [&](int64_t t) -> int { return t < n_pairs ? (int)t : -1; };
+    int p_cur = pair_of(first), p_next = pair_of(first + stride);
+    if (p_cur >= 0) { s_e[tid] = __ldg(energy + p_cur); s_cz[tid] = __ldg(coszen + p_cur); }
+    for (int64_t base = warp_first; base < n_pairs; base += stride) {
+        const int64_t t = base + (tid & 31);
+        const int p_nn = pair_of(t + 2 * stride);
+        double w0 = 0.0, w1 = 0.0;
+        int bin0 = -1, bin1 = -1;
+        if (p_cur >= 0) {
+            const float2 e2 = s_e[tid], c2 = s_cz[tid];
+            cp_async<16>(&s_flux[tid], nu_flux + p_cur);
+            cp_async<8>(&s_w[tid], weights_in + p_cur);
+            cp_async<8>(&s_bin[tid], index + p_cur);
+            if (p_next >= 0) {
+                cp_async<8>(&s_e[tid], energy + p_next);
+                cp_async<8>(&s_cz[tid], coszen + p_next);
+            }
+            cp_async_commit();
+            const double cz[2] = {(double)c2.x, (double)c2.y};
+            const double inv_e[2] = {rcp_fast((double)e2.x), rcp_fast((double)e2.y)};
+            const double sg = C.nubar > 0 ? 1.0 : -1.0;
+            H0MP2<STD> h0;
+            h0.init(herm_axpy(sg * inv_e[0], osc.hv[0], osc.lr), herm_axpy(sg * inv_e[1], osc.hv[0], osc.lr)); // hv[1] = -hv[0]
+            PropagatorSmemP<1, 2> P{&s_state[0][tid], kBlock};
+            bool mismatch;
+            propagate_earth_pair<1, 2, STD>(h0, osc, s_earth, cz, inv_e, C.nubar, C.flav, P, mismatch);
+            const f2 pe = P.prob_r(0, 0), pmu = P.prob_r(0, 1);
+            cp_async_wait_all();
+            const float4 fl = s_flux[tid]; // (flux_e, flux_mu) of event 0, then of event 1
+            const float2 ww = s_w[tid];
+            const int2 bb = s_bin[tid];
+            // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
+            w0 = (double)ww.x * ((double)fl.x * (double)pe.x + (double)fl.y * (double)pmu.x) * C.scale;
+            w1 = (double)ww.y * ((double)fl.z * (double)pe.y + (double)fl.w * (double)pmu.y) * C.scale;
+            if (mismatch) w0 = w1 = __longlong_as_double(0x7ff8000000000000LL); // the host broke the pairing contract
+            bin0 = bb.x;
+            bin1 = bb.y;
+        }
+        wh.add(bin0, w0);
+        wh.add(bin1, w1);
+        p_cur = p_next;
+        p_next = p_nn;
+    }
+    wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
+}
+
+template <bool STD>
+__global__ void __launch_bounds__(kBlock, PISAB_PAIR_MIN_BLOCKS)
+reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
+                          const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
+                          const unsigned long long *__restrict__ /* bounds: same signature as reweight_hist_kernel */) {
+    extern __shared__ __align__(16) double s_hist[];
+    __shared__ EarthTable s_earth;
+    copy_earth(earth, &s_earth);
+    const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
+    fused_pair_body<STD>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -665,11 +760,17 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     const bool std_matter = ot.std_matter != 0.0;
 #endif
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
-    const size_t smem = fused_smem_bytes<IO>(large ? 0 : n_bins, std_matter, mp);
+    const size_t smem_events = fused_smem_bytes<IO>(large ? 0 : n_bins, std_matter, mp);
     bool plain = true;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
         plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu;
+    }
+    // FP32 mode with pair-aligned containers: two events per thread (reweight_hist_pair_kernel)
+    bool pairs = mp && plain && !large && sizeof(IO) == 4;
+    for (int c = 0; c < batch.n_containers && pairs; ++c) {
+        const FusedContainer<IO> &C = batch.c[c];
+        pairs = (C.flags & PISAB_CONTAINER_PAIR_ALIGNED) && (C.n % 2 == 0) && !C.order;
     }
     if (large && (!plain || !d_batch_out)) {
         set_error("more than %d bins: only the batched form without per-event outputs is fused; use propagate_earth + "
@@ -679,6 +780,12 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     auto kernel = large ? (std_matter ? fused_kernel_large<IO, true>(mp) : fused_kernel_large<IO, false>(mp))
                         : std_matter ? (plain ? fused_kernel<IO, true, true>(mp) : fused_kernel<IO, true, false>(mp))
                                      : (plain ? fused_kernel<IO, false, true>(mp) : fused_kernel<IO, false, false>(mp));
+    if (pairs) {
+        if constexpr (sizeof(IO) == 4) kernel = std_matter ? reweight_hist_pair_kernel<true> : reweight_hist_pair_kernel<false>;
+    }
+    const size_t smem = pairs ? fused_pair_smem_bytes(n_bins) : smem_events;
+    const int64_t n_units = pairs ? (n_max + 1) / 2 : n_max;   // what a thread iterates over: events or pairs
+    const int64_t unit_min = pairs ? 4 : 8;                    // >= 8 events per thread
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
@@ -705,8 +812,8 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
         const int resident = (sm_count() > 0 ? sm_count() : 148) * occ;
         const int nc = batch.n_containers;
-        const int64_t by_work = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
-        const int64_t by_thread = (n_max + kBlock - 1) / kBlock;
+        const int64_t by_work = (n_units + (int64_t)kBlock * unit_min - 1) / ((int64_t)kBlock * unit_min);
+        const int64_t by_thread = (n_units + kBlock - 1) / kBlock;
         int64_t r = by_work;
         const int64_t cap = ((int64_t)resident * PISAB_SPREAD_WAVES + nc - 1) / nc;
         if (r > cap) r = cap;
@@ -798,7 +905,7 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
         C.nu_flux = (const IO *)S.d_nu_flux; C.weights_in = (const IO *)S.d_weights;
         C.index = S.d_index; C.order = S.d_order; C.d_nubar = nullptr; C.d_flav = nullptr;
         C.weights_out = (IO *)S.d_weights_out; C.prob_e = nullptr; C.prob_mu = nullptr;
-        C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav;
+        C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav; C.flags = S.flags;
         if (S.n > n_max) n_max = S.n;
     }
     if (epi && n_bins > PISAB_DET_MAX_BINS) {

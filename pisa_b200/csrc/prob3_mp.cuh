@@ -27,10 +27,89 @@
 
 namespace pisab {
 
-struct CplxF {
-    float re, im;
+// Two arithmetic "real" types share the float part of this file:
+//   float : one event per thread;
+//   f2    : TWO events per thread, one in each lane of the packed FP32 instructions of sm_100 (fma.rn.f32x2 ...).
+//           A packed instruction occupies the FP32 pipe for two cycles -- the same pipe time per event as two
+//           scalar ones -- but only ONE issue slot, and the FP32 mode is issue-bound; ptxas folds negations into the
+//           operand modifiers of FFMA2 / FADD2 / FMUL2, so every scalar float operation below has a one-instruction
+//           packed twin and both forms round identically (the pair path is bit-identical to the scalar one).
+struct alignas(8) f2 {
+    float x, y; // lane x: first event of the pair, lane y: second
 };
+#ifdef PISAB_HOST_EMU
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) { return f2{fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)}; }
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) { return f2{a.x * b.x, a.y * b.y}; }
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) { return f2{a.x + b.x, a.y + b.y}; }
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) { return f2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ f2 f2_neg(f2 a) { return f2{-a.x, -a.y}; }
+#else
+__device__ __forceinline__ unsigned long long f2_bits(f2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ f2 f2_from(unsigned long long v) {
+    f2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+    return f2_from(r);
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+__device__ __forceinline__ f2 f2_sub(f2 a, f2 b) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+    return f2_from(r);
+}
+__device__ __forceinline__ f2 f2_neg(f2 a) { return f2{-a.x, -a.y}; } // folded into the consumer's operand modifier
+#endif
+// the common vocabulary of the templated code: t_fma(a, b, c) = a b + c, t_mul, t_add, t_sub, t_neg, t_splat<R>(float)
+__device__ __forceinline__ float t_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ float t_mul(float a, float b) { return a * b; }
+__device__ __forceinline__ float t_add(float a, float b) { return a + b; }
+__device__ __forceinline__ float t_sub(float a, float b) { return a - b; }
+__device__ __forceinline__ float t_neg(float a) { return -a; }
+__device__ __forceinline__ f2 t_fma(f2 a, f2 b, f2 c) { return f2_fma(a, b, c); }
+__device__ __forceinline__ f2 t_mul(f2 a, f2 b) { return f2_mul(a, b); }
+__device__ __forceinline__ f2 t_add(f2 a, f2 b) { return f2_add(a, b); }
+__device__ __forceinline__ f2 t_sub(f2 a, f2 b) { return f2_sub(a, b); }
+__device__ __forceinline__ f2 t_neg(f2 a) { return f2_neg(a); }
+template <typename R> __device__ __forceinline__ R t_splat(float v);
+template <> __device__ __forceinline__ float t_splat<float>(float v) { return v; }
+template <> __device__ __forceinline__ f2 t_splat<f2>(float v) { return f2{v, v}; }
+
+template <typename R>
+struct CplxT {
+    R re, im;
+};
+typedef CplxT<float> CplxF;
+typedef CplxT<f2> Cplx2;
 typedef CplxF Mat3F[3][3];
+
+template <typename R>
+__device__ __forceinline__ CplxT<R> t_cmul(CplxT<R> a, CplxT<R> b) {
+    return CplxT<R>{t_fma(a.re, b.re, t_neg(t_mul(a.im, b.im))), t_fma(a.re, b.im, t_mul(a.im, b.re))};
+}
+template <typename R>
+__device__ __forceinline__ CplxT<R> t_cfma(CplxT<R> a, CplxT<R> b, CplxT<R> c) { // a*b + c
+    CplxT<R> r;
+    r.re = t_fma(a.re, b.re, t_fma(t_neg(a.im), b.im, c.re));
+    r.im = t_fma(a.re, b.im, t_fma(a.im, b.re, c.im));
+    return r;
+}
 
 __device__ __forceinline__ CplxF cmulf(CplxF a, CplxF b) {
     return CplxF{fmaf(a.re, b.re, -a.im * b.im), fmaf(a.re, b.im, a.im * b.re)};
@@ -102,146 +181,129 @@ __device__ __forceinline__ RootsC eigen_roots_centered(double c1, double c0) {
     return r;
 }
 
-// The float image of one layer's trace-free Hamiltonian M and the invariants its square needs:
+// The float image of one layer's trace-free Hamiltonian M (off-diagonal part) and the invariants its square needs:
 //   s_i  = sum_{j != i} |h_ij|^2                      (diagonal of M^2 minus m_i^2)
 //   c_ij = h_ik h_kj, k the third index               (off-diagonal of M^2 minus (m_i + m_j) h_ij)
-struct LayerMatF {
-    float r01, i01, r02, i02, r12, i12;
-    float s0, s1, s2;
-    CplxF c01, c02, c12;
+// R = float: one event; R = f2: the two events of a pair, lane-wise.
+template <typename R>
+struct LayerMatT {
+    R r01, i01, r02, i02, r12, i12;
+    R s0, s1, s2;
+    CplxT<R> c01, c02, c12;
 };
-__device__ __forceinline__ void layer_products(LayerMatF &L) {
-    const float n01 = fmaf(L.r01, L.r01, L.i01 * L.i01);
-    const float n02 = fmaf(L.r02, L.r02, L.i02 * L.i02);
-    const float n12 = fmaf(L.r12, L.r12, L.i12 * L.i12);
-    L.s0 = n01 + n02;
-    L.s1 = n01 + n12;
-    L.s2 = n02 + n12;
-    L.c01 = CplxF{fmaf(L.r02, L.r12, L.i02 * L.i12), fmaf(L.i02, L.r12, -L.r02 * L.i12)};  // h02 conj(h12)
-    L.c02 = CplxF{fmaf(L.r01, L.r12, -L.i01 * L.i12), fmaf(L.r01, L.i12, L.i01 * L.r12)};  // h01 h12
-    L.c12 = CplxF{fmaf(L.r01, L.r02, L.i01 * L.i02), fmaf(L.r01, L.i02, -L.i01 * L.r02)};  // conj(h01) h02
+typedef LayerMatT<float> LayerMatF;
+template <typename R>
+__device__ __forceinline__ void layer_products(LayerMatT<R> &L) {
+    const R n01 = t_fma(L.r01, L.r01, t_mul(L.i01, L.i01));
+    const R n02 = t_fma(L.r02, L.r02, t_mul(L.i02, L.i02));
+    const R n12 = t_fma(L.r12, L.r12, t_mul(L.i12, L.i12));
+    L.s0 = t_add(n01, n02);
+    L.s1 = t_add(n01, n12);
+    L.s2 = t_add(n02, n12);
+    L.c01 = CplxT<R>{t_fma(L.r02, L.r12, t_mul(L.i02, L.i12)), t_fma(L.i02, L.r12, t_neg(t_mul(L.r02, L.i12)))};  // h02 conj(h12)
+    L.c02 = CplxT<R>{t_fma(L.r01, L.r12, t_neg(t_mul(L.i01, L.i12))), t_fma(L.r01, L.i12, t_mul(L.i01, L.r12))};  // h01 h12
+    L.c12 = CplxT<R>{t_fma(L.r01, L.r02, t_mul(L.i01, L.i02)), t_fma(L.r01, L.i02, t_neg(t_mul(L.i01, L.r02)))};  // conj(h01) h02
 }
 
-// T = 1 + n1 (M - mu0) + n2 (M - mu0)(M - mu1) = exp(-i M t) up to the global phase exp(+i mu0 t).
-//   (M - mu0)(M - mu1)_ii = (m_i - mu0)(m_i - mu1) + s_i
-//   (M - mu0)(M - mu1)_ij = h_ij (mu2 - m_k) + c_ij          (trace-free: m_i + m_j = -m_k, mu0 + mu1 = -mu2)
-// The diagonal enters only through ea_i = m_i - mu0, which the caller forms in FP64 and rounds once (L.m* is not
-// read here); m_i - mu1 = ea_i - g10 and mu2 - m_k = g20 - ea_k, so besides them only the three gaps are converted.
-__device__ __forceinline__ void assemble_transition_mp(const LayerMatF &L, float ea0, float ea1, float ea2,
-                                                       const RootsC &R, double t, Mat3F T) {
+// Scalar coefficients of one layer of one event:  T = 1 + n1 (M - mu0) + n2 (M - mu0)(M - mu1)  (global phase
+// exp(+i mu0 t) dropped), with the diagonal of M given through ea_i = m_i - mu0 (formed in FP64 by the caller and
+// rounded once); m_i - mu1 = ea_i - g10 and mu2 - m_k = g20 - ea_k.
+template <typename R>
+struct LayerCoefT {
+    CplxT<R> n1, n2;
+    R g10, g20, ea0, ea1, ea2;
+};
+typedef LayerCoefT<float> LayerCoefF;
+// FP64 roots -> phases (FP64 reduction) -> float divided differences; per event, always scalar
+__device__ __forceinline__ LayerCoefF layer_coefficients(float ea0, float ea1, float ea2, const RootsC &R, double t) {
     const double g10d = R.m1 - R.m0, g20d = R.m2 - R.m0, g21d = R.m2 - R.m1;
     const CplxF e01 = expm1i_neg(g10d * t), e02 = expm1i_neg(g20d * t);
     const float g10 = (float)g10d, g20 = (float)g20d, g21 = (float)g21d;
     // (a gap that underflows in float would give 0 * inf: clamp; three equal roots cannot occur, see eigen_solve)
     const float r10 = rcp_f32(fmaxf(g10, 1e-30f)), r20 = rcp_f32(g20), r21 = rcp_f32(fmaxf(g21, 1e-30f));
-    const CplxF n1{e01.re * r10, e01.im * r10};
+    LayerCoefF k;
+    k.n1 = CplxF{e01.re * r10, e01.im * r10};
     const CplxF f02{e02.re * r20, e02.im * r20};
-    const CplxF n2{(f02.re - n1.re) * r21, (f02.im - n1.im) * r21};
-    // ---- diagonal
-#define PISAB_MP_DIAG(I, EA, S)                                                             \
-    {                                                                                       \
-        const float pp = fmaf(EA, EA - g10, S);                                             \
-        T[I][I] = CplxF{fmaf(n2.re, pp, fmaf(n1.re, EA, 1.0f)), fmaf(n2.im, pp, n1.im * EA)}; \
+    k.n2 = CplxF{(f02.re - k.n1.re) * r21, (f02.im - k.n1.im) * r21};
+    k.g10 = g10; k.g20 = g20; k.ea0 = ea0; k.ea1 = ea1; k.ea2 = ea2;
+    return k;
+}
+__device__ __forceinline__ LayerCoefT<f2> pack_coef(const LayerCoefF &a, const LayerCoefF &b) {
+    LayerCoefT<f2> k;
+    k.n1 = Cplx2{f2{a.n1.re, b.n1.re}, f2{a.n1.im, b.n1.im}};
+    k.n2 = Cplx2{f2{a.n2.re, b.n2.re}, f2{a.n2.im, b.n2.im}};
+    k.g10 = f2{a.g10, b.g10}; k.g20 = f2{a.g20, b.g20};
+    k.ea0 = f2{a.ea0, b.ea0}; k.ea1 = f2{a.ea1, b.ea1}; k.ea2 = f2{a.ea2, b.ea2};
+    return k;
+}
+
+//   (M - mu0)(M - mu1)_ii = (m_i - mu0)(m_i - mu1) + s_i
+//   (M - mu0)(M - mu1)_ij = h_ij (mu2 - m_k) + c_ij          (trace-free: m_i + m_j = -m_k, mu0 + mu1 = -mu2)
+template <typename R>
+__device__ __forceinline__ void assemble_matrix(const LayerMatT<R> &L, const LayerCoefT<R> &k, CplxT<R> (*T)[3]) {
+    const CplxT<R> n1 = k.n1, n2 = k.n2;
+    const R one = t_splat<R>(1.0f);
+#define PISAB_MP_DIAG(I, EA, S)                                                                          \
+    {                                                                                                    \
+        const R pp = t_fma(EA, t_sub(EA, k.g10), S);                                                     \
+        T[I][I] = CplxT<R>{t_fma(n2.re, pp, t_fma(n1.re, EA, one)), t_fma(n2.im, pp, t_mul(n1.im, EA))}; \
     }
-    PISAB_MP_DIAG(0, ea0, L.s0)
-    PISAB_MP_DIAG(1, ea1, L.s1)
-    PISAB_MP_DIAG(2, ea2, L.s2)
+    PISAB_MP_DIAG(0, k.ea0, L.s0)
+    PISAB_MP_DIAG(1, k.ea1, L.s1)
+    PISAB_MP_DIAG(2, k.ea2, L.s2)
 #undef PISAB_MP_DIAG
-    // ---- off-diagonal pairs: T_ij = h z + n2 c, T_ji = conj(h) z + n2 conj(c), z = n1 + n2 (mu2 - m_k)
-#define PISAB_MP_OFF(I, J, EAK, HR, HI, C)                                   \
-    {                                                                        \
-        const float u = g20 - EAK;                                           \
-        const float zr = fmaf(n2.re, u, n1.re), zi = fmaf(n2.im, u, n1.im);  \
-        const float s1 = fmaf(HR, zr, n2.re * C.re);                         \
-        const float s2 = fmaf(HI, zi, n2.im * C.im);                         \
-        const float s3 = fmaf(HR, zi, n2.im * C.re);                         \
-        const float s4 = fmaf(HI, zr, n2.re * C.im);                         \
-        T[I][J] = CplxF{s1 - s2, s3 + s4};                                   \
-        T[J][I] = CplxF{s1 + s2, s3 - s4};                                   \
+    // off-diagonal pairs: T_ij = h z + n2 c, T_ji = conj(h) z + n2 conj(c), z = n1 + n2 (mu2 - m_k)
+#define PISAB_MP_OFF(I, J, EAK, HR, HI, C)                                         \
+    {                                                                              \
+        const R u = t_sub(k.g20, EAK);                                             \
+        const R zr = t_fma(n2.re, u, n1.re), zi = t_fma(n2.im, u, n1.im);          \
+        const R s1 = t_fma(HR, zr, t_mul(n2.re, C.re));                            \
+        const R s2 = t_fma(HI, zi, t_mul(n2.im, C.im));                            \
+        const R s3 = t_fma(HR, zi, t_mul(n2.im, C.re));                            \
+        const R s4 = t_fma(HI, zr, t_mul(n2.re, C.im));                            \
+        T[I][J] = CplxT<R>{t_sub(s1, s2), t_add(s3, s4)};                          \
+        T[J][I] = CplxT<R>{t_add(s1, s2), t_sub(s3, s4)};                          \
     }
-    PISAB_MP_OFF(0, 1, ea2, L.r01, L.i01, L.c01)
-    PISAB_MP_OFF(0, 2, ea1, L.r02, L.i02, L.c02)
-    PISAB_MP_OFF(1, 2, ea0, L.r12, L.i12, L.c12)
+    PISAB_MP_OFF(0, 1, k.ea2, L.r01, L.i01, L.c01)
+    PISAB_MP_OFF(0, 2, k.ea1, L.r02, L.i02, L.c02)
+    PISAB_MP_OFF(1, 2, k.ea0, L.r12, L.i12, L.c12)
 #undef PISAB_MP_OFF
 }
 
-// Register-resident propagation state in float (same interface as Propagator / PropagatorSmem).
-template <int NR, int NC>
-struct PropagatorF {
-    static constexpr bool kF32 = true;
-    typedef CplxF cplx;
-    CplxF L[NR][3];
-    CplxF R[NC][3];
-
-    __device__ __forceinline__ void set_right(int c, int k, CplxF v) { R[c][k] = v; }
-    __device__ __forceinline__ void init_right(const Mat3F T) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) R[c][k] = T[k][c];
-    }
-    __device__ __forceinline__ void init_left(const Mat3F T, int flav) {
-        if (NR == 3) {
-#pragma unroll
-            for (int r = 0; r < 3; ++r)
-#pragma unroll
-                for (int c = 0; c < 3; ++c) L[r][c] = T[r][c];
-        } else {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                CplxF v = T[0][c];
-                if (flav == 1) v = T[1][c];
-                if (flav == 2) v = T[2][c];
-                L[0][c] = v;
-            }
-        }
-    }
-    __device__ __forceinline__ void mul_right(const Mat3F T) {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const CplxF r0 = R[c][0], r1 = R[c][1], r2 = R[c][2];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) R[c][k] = cfmaf(T[k][2], r2, cfmaf(T[k][1], r1, cmulf(T[k][0], r0)));
-        }
-    }
-    __device__ __forceinline__ void mul_left(const Mat3F T) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            const CplxF l0 = L[r][0], l1 = L[r][1], l2 = L[r][2];
-#pragma unroll
-            for (int c = 0; c < 3; ++c) L[r][c] = cfmaf(l2, T[2][c], cfmaf(l1, T[1][c], cmulf(l0, T[0][c])));
-        }
-    }
-    __device__ __forceinline__ double prob(int r, int c) const {
-        const CplxF acc = cfmaf(L[r][2], R[c][2], cfmaf(L[r][1], R[c][1], cmulf(L[r][0], R[c][0])));
-        return (double)fmaf(acc.re, acc.re, acc.im * acc.im);
-    }
+// Propagation state of the FP32 mode in a per-thread column of shared memory, [(v*3+k)][thread]: one (re, im) float2
+// per complex number (R = float, 64-bit accesses) or one (re_A, re_B, im_A, im_B) float4 for a pair (R = f2, 128-bit
+// accesses).  A register-resident state costs ~190 loop-carried register moves per event (ncu, round 2), this form
+// ~70 conflict-free LDS / STS.  Vectors 0..NC-1 = columns of R, NC.. = rows of L.
+template <typename R> struct StateSlot;
+template <> struct StateSlot<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ CplxF get(const float2 &z) { return CplxF{z.x, z.y}; }
+    static __device__ __forceinline__ float2 put(const CplxF &z) { return make_float2(z.re, z.im); }
 };
-
-// The same state in a per-thread column of shared memory, one (re, im) float2 per 64-bit access, [(v*3+k)][thread]:
-// the in-place vector updates of a loop-carried register state cost ~190 register moves per event (ncu, round 2),
-// the shared-memory form ~70 conflict-free LDS.64 / STS.64.  Vectors 0..NC-1 = columns of R, NC.. = rows of L.
-template <int NR, int NC>
-struct PropagatorSmemF {
+template <> struct StateSlot<f2> {
+    typedef float4 type;
+    static __device__ __forceinline__ Cplx2 get(const float4 &z) { return Cplx2{f2{z.x, z.y}, f2{z.z, z.w}}; }
+    static __device__ __forceinline__ float4 put(const Cplx2 &z) { return make_float4(z.re.x, z.re.y, z.im.x, z.im.y); }
+};
+template <int NR, int NC, typename R>
+struct PropagatorSmemT {
     static constexpr bool kF32 = true;
-    typedef CplxF cplx;
-    float2 *col; // &state[0][threadIdx.x]
-    int pitch;   // block size
-    static constexpr int kFloat2s = (NR + NC) * 3;
+    typedef CplxT<R> cplx;
+    typedef typename StateSlot<R>::type slot;
+    slot *col; // &state[0][threadIdx.x]
+    int pitch; // block size
+    static constexpr int kSlots = (NR + NC) * 3;
 
-    __device__ __forceinline__ CplxF ld(int v, int k) const {
-        const float2 z = col[(v * 3 + k) * pitch];
-        return CplxF{z.x, z.y};
-    }
-    __device__ __forceinline__ void st(int v, int k, CplxF z) { col[(v * 3 + k) * pitch] = make_float2(z.re, z.im); }
-    __device__ __forceinline__ void set_right(int c, int k, CplxF v) { st(c, k, v); }
-    __device__ __forceinline__ void init_right(const Mat3F T) {
+    __device__ __forceinline__ cplx ld(int v, int k) const { return StateSlot<R>::get(col[(v * 3 + k) * pitch]); }
+    __device__ __forceinline__ void st(int v, int k, cplx z) { col[(v * 3 + k) * pitch] = StateSlot<R>::put(z); }
+    __device__ __forceinline__ void set_right(int c, int k, cplx v) { st(c, k, v); }
+    __device__ __forceinline__ void init_right(const cplx (*T)[3]) {
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
             for (int k = 0; k < 3; ++k) st(c, k, T[k][c]);
     }
-    __device__ __forceinline__ void init_left(const Mat3F T, int flav) {
+    __device__ __forceinline__ void init_left(const cplx (*T)[3], int flav) {
         if (NR == 3) {
 #pragma unroll
             for (int r = 0; r < 3; ++r)
@@ -250,65 +312,78 @@ struct PropagatorSmemF {
         } else {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                CplxF v = T[0][c];
+                cplx v = T[0][c];
                 if (flav == 1) v = T[1][c];
                 if (flav == 2) v = T[2][c];
                 st(NC, c, v);
             }
         }
     }
-    __device__ __forceinline__ void mul_right(const Mat3F T) {
+    __device__ __forceinline__ void mul_right(const cplx (*T)[3]) {
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
-            const CplxF r0 = ld(c, 0), r1 = ld(c, 1), r2 = ld(c, 2);
+            const cplx r0 = ld(c, 0), r1 = ld(c, 1), r2 = ld(c, 2);
 #pragma unroll
-            for (int k = 0; k < 3; ++k) st(c, k, cfmaf(T[k][2], r2, cfmaf(T[k][1], r1, cmulf(T[k][0], r0))));
+            for (int k = 0; k < 3; ++k) st(c, k, t_cfma(T[k][2], r2, t_cfma(T[k][1], r1, t_cmul(T[k][0], r0))));
         }
     }
-    __device__ __forceinline__ void mul_left(const Mat3F T) {
+    __device__ __forceinline__ void mul_left(const cplx (*T)[3]) {
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            const CplxF l0 = ld(NC + r, 0), l1 = ld(NC + r, 1), l2 = ld(NC + r, 2);
+            const cplx l0 = ld(NC + r, 0), l1 = ld(NC + r, 1), l2 = ld(NC + r, 2);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) st(NC + r, c, cfmaf(l2, T[2][c], cfmaf(l1, T[1][c], cmulf(l0, T[0][c]))));
+            for (int c = 0; c < 3; ++c) st(NC + r, c, t_cfma(l2, T[2][c], t_cfma(l1, T[1][c], t_cmul(l0, T[0][c]))));
         }
     }
-    __device__ __forceinline__ double prob(int r, int c) const {
-        const CplxF acc = cfmaf(ld(NC + r, 2), ld(c, 2), cfmaf(ld(NC + r, 1), ld(c, 1), cmulf(ld(NC + r, 0), ld(c, 0))));
-        return (double)fmaf(acc.re, acc.re, acc.im * acc.im);
+    // |amplitude|^2 of (row r, column c); one value per lane
+    __device__ __forceinline__ R prob_r(int r, int c) const {
+        const cplx acc = t_cfma(ld(NC + r, 2), ld(c, 2), t_cfma(ld(NC + r, 1), ld(c, 1), t_cmul(ld(NC + r, 0), ld(c, 0))));
+        return t_fma(acc.re, acc.re, t_mul(acc.im, acc.im));
     }
+    __device__ __forceinline__ double prob(int r, int c) const; // scalar form only
 };
+template <int NR, int NC>
+using PropagatorSmemF = PropagatorSmemT<NR, NC, float>;
+template <int NR, int NC>
+using PropagatorSmemP = PropagatorSmemT<NR, NC, f2>;
+template <int NR, int NC, typename R>
+__device__ __forceinline__ double PropagatorSmemT<NR, NC, R>::prob(int r, int c) const {
+    static_assert(sizeof(R) == sizeof(float), "prob() is the one-event form; use prob_r() for a pair");
+    return (double)prob_r(r, c);
+}
 
-// Per-event Hamiltonian provider of the FP32 mode.
-//   STD (standard matter potential, vm = diag(a, 0, 0)): per event the trace-free H0c = hv/E + lr - tr/3 is kept in
-//   float together with s_i, c_ij (which do not depend on the density) and, in FP64, the invariants that make the
-//   cubic of H0c + x e00 - x/3 linear in x = rho * a:
-//       c1(x) = c1_0 - x d0c - x^2/3 ,   c0(x) = c0_0 - x m00 + (x/3) c1(x) + ... (see layer_poly)
-//   General (NSI): the layer Hamiltonian is formed and centred in FP64 per layer, then rounded.
+__device__ __forceinline__ void herm_offdiag_to_float(const Herm3 &c, LayerMatF &L) {
+    L.r01 = (float)c.r01; L.i01 = (float)c.i01; L.r02 = (float)c.r02;
+    L.i02 = (float)c.i02; L.r12 = (float)c.r12; L.i12 = (float)c.i12;
+}
+
+// Per-event FP64 side of the FP32 mode (everything that needs double precision lives here):
+//   STD (standard matter potential, vm = diag(a, 0, 0)): per event the trace-free H0c = hv/E + lr - tr/3 and the
+//   invariants that make the cubic of H0c + x e00 - x/3 a polynomial in x = rho a;
+//   general (NSI): the layer Hamiltonian is formed and centred in FP64 per layer.
 template <bool STD>
-struct H0MP {
-    LayerMatF base; // STD: float image of H0c and its invariants; general: scratch
-    Herm3 h;        // general: H0 = hv/E + lr in FP64 (STD: unused after init)
-    double c1_0, c0_0, d0c, d1c, d2c, m00; // STD only
+struct H0Core {
+    Herm3 h;                               // general: H0 = hv/E + lr (STD: only used by init)
+    double c1_0, c0_0, d0c, d1c, d2c, m00; // STD
 
-    __device__ __forceinline__ void init(const Herm3 &h0) {
+    // returns the trace-free H0c (STD) whose off-diagonal part the caller rounds to float
+    __device__ __forceinline__ Herm3 init(const Herm3 &h0) {
+        Herm3 c = h0;
         if (STD) {
             const double tr3 = (h0.d0 + h0.d1 + h0.d2) * kTab[16];
-            Herm3 c = h0;
             c.d0 -= tr3; c.d1 -= tr3; c.d2 -= tr3;
             double c2;
             char_poly(c, c2, c1_0, c0_0); // c2 == 0 up to rounding
             d0c = c.d0; d1c = c.d1; d2c = c.d2;
             m00 = fma(c.d1, c.d2, -fma(c.r12, c.r12, c.i12 * c.i12));
-            base.r01 = (float)c.r01; base.i01 = (float)c.i01; base.r02 = (float)c.r02;
-            base.i02 = (float)c.i02; base.r12 = (float)c.r12; base.i12 = (float)c.i12;
-            layer_products(base);
         } else {
             h = h0;
         }
+        return c;
     }
-    // transition matrix of a layer of density rho, t = 2 * 2.534 * length
-    __device__ __forceinline__ void layer(double rho, const Herm3 &vm, double t, Mat3F T) const {
+    // coefficients of a layer of density rho and t = 2 * 2.534 * length; general path: also the layer's own float
+    // off-diagonal part in `Lgen`
+    __device__ __forceinline__ LayerCoefF layer(double rho, const Herm3 &vm, double t, LayerMatF *Lgen) const {
         if (STD) {
             // H = H0c + x e00 has trace x; M = H - x/3 is trace-free with diagonal shifts (2x/3, -x/3, -x/3) and
             // det(M - mu) from the cubic of H0c + x e00 (c2 = -x, c1 = c1_0 - x d0c, c0 = c0_0 - x m00) shifted
@@ -320,7 +395,7 @@ struct H0MP {
             const RootsC R = eigen_roots_centered(c1p, c0p);
             // diagonal of M: (d0c + 2y, d1c - y, d2c - y); its distance to mu0 in FP64, rounded once
             const double o0 = fma(-2.0, y, R.m0), o12 = R.m0 + y;
-            assemble_transition_mp(base, (float)(d0c - o0), (float)(d1c - o12), (float)(d2c - o12), R, t, T);
+            return layer_coefficients((float)(d0c - o0), (float)(d1c - o12), (float)(d2c - o12), R, t);
         } else {
             Herm3 c = herm_axpy(rho, vm, h);
             const double tr3 = (c.d0 + c.d1 + c.d2) * kTab[16];
@@ -328,11 +403,70 @@ struct H0MP {
             double c2, c1, c0;
             char_poly(c, c2, c1, c0);
             const RootsC R = eigen_roots_centered(c1, c0);
+            herm_offdiag_to_float(c, *Lgen);
+            return layer_coefficients((float)(c.d0 - R.m0), (float)(c.d1 - R.m0), (float)(c.d2 - R.m0), R, t);
+        }
+    }
+};
+
+// One event per thread
+template <bool STD>
+struct H0MP {
+    H0Core<STD> core;
+    LayerMatF base; // STD: float image of H0c's off-diagonal part and its invariants
+
+    __device__ __forceinline__ void init(const Herm3 &h0) {
+        const Herm3 c = core.init(h0);
+        if (STD) {
+            herm_offdiag_to_float(c, base);
+            layer_products(base);
+        }
+    }
+    __device__ __forceinline__ void layer(double rho, const Herm3 &vm, double t, Mat3F T) const {
+        if (STD) {
+            assemble_matrix<float>(base, core.layer(rho, vm, t, nullptr), T);
+        } else {
             LayerMatF L;
-            L.r01 = (float)c.r01; L.i01 = (float)c.i01; L.r02 = (float)c.r02;
-            L.i02 = (float)c.i02; L.r12 = (float)c.r12; L.i12 = (float)c.i12;
+            const LayerCoefF k = core.layer(rho, vm, t, &L);
             layer_products(L);
-            assemble_transition_mp(L, (float)(c.d0 - R.m0), (float)(c.d1 - R.m0), (float)(c.d2 - R.m0), R, t, T);
+            assemble_matrix<float>(L, k, T);
+        }
+    }
+};
+
+__device__ __forceinline__ void pack_offdiag(const LayerMatF &a, const LayerMatF &b, LayerMatT<f2> &L) {
+    L.r01 = f2{a.r01, b.r01}; L.i01 = f2{a.i01, b.i01}; L.r02 = f2{a.r02, b.r02};
+    L.i02 = f2{a.i02, b.i02}; L.r12 = f2{a.r12, b.r12}; L.i12 = f2{a.i12, b.i12};
+}
+
+// Two events per thread (a pair that crosses the same Earth shells): FP64 cores per event, float part lane-packed
+template <bool STD>
+struct H0MP2 {
+    H0Core<STD> core[2];
+    LayerMatT<f2> base;
+
+    __device__ __forceinline__ void init(const Herm3 &ha, const Herm3 &hb) {
+        const Herm3 ca = core[0].init(ha), cb = core[1].init(hb);
+        if (STD) {
+            LayerMatF a, b;
+            herm_offdiag_to_float(ca, a);
+            herm_offdiag_to_float(cb, b);
+            pack_offdiag(a, b, base);
+            layer_products(base);
+        }
+    }
+    // same shell for both events (same density), their own lengths
+    __device__ __forceinline__ void layer(double rho, const Herm3 &vm, double ta, double tb, Cplx2 (*T)[3]) const {
+        if (STD) {
+            const LayerCoefF ka = core[0].layer(rho, vm, ta, nullptr), kb = core[1].layer(rho, vm, tb, nullptr);
+            assemble_matrix<f2>(base, pack_coef(ka, kb), T);
+        } else {
+            LayerMatF a, b;
+            const LayerCoefF ka = core[0].layer(rho, vm, ta, &a), kb = core[1].layer(rho, vm, tb, &b);
+            LayerMatT<f2> L;
+            pack_offdiag(a, b, L);
+            layer_products(L);
+            assemble_matrix<f2>(L, pack_coef(ka, kb), T);
         }
     }
 };
@@ -342,22 +476,21 @@ __device__ __forceinline__ Herm3F herm_to_float(const Herm3 &h) {
                   (float)h.r02, (float)h.i02, (float)h.r12, (float)h.i12};
 }
 
-// Vacuum columns 1 + z2 P2 + z3 P3 (see vacuum_columns) with z_k = exp(-i phi_k) - 1 from expm1i_neg.
-template <int NC, typename PROP>
-__device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, PROP &P) {
-    // ts carries the nu / nubar sign: exp(-i hdm ts) with ts = -/+ t / E  (vacuum_columns)
-    const CplxF z2 = expm1i_neg(-o.hdm21 * ts), z3 = expm1i_neg(-o.hdm31 * ts);
-    // vacuum_columns uses (cos - 1, +sin) of (hdm * ts): exp(+i hdm ts) - 1 = expm1i_neg(-hdm ts)
-    const float z2r = z2.re, z2i = z2.im, z3r = z3.re, z3i = z3.im;
+// Vacuum columns 1 + z2 P2 + z3 P3 (see vacuum_columns) with z_k = exp(-i phi_k) - 1 (expm1i_neg); R = float: one
+// event, z2 / z3 scalar; R = f2: a pair, the projector entries splatted to both lanes.
+template <int NC, typename R, typename PROP>
+__device__ __forceinline__ void vacuum_columns_t(const OscTable &o, CplxT<R> z2, CplxT<R> z3, PROP &P) {
     const Herm3F A = herm_to_float(o.pr2), B = herm_to_float(o.pr3);
-#define PISAB_VAC_DIAG(C, DA, DB) \
-    P.set_right(C, C, CplxF{fmaf(z2r, DA, fmaf(z3r, DB, 1.0f)), fmaf(z2i, DA, z3i * DB)});
-#define PISAB_VAC_OFF(I, J, AR, AI, BR, BI)                                                                   \
-    {                                                                                                         \
-        const float xr = fmaf(z2r, AR, z3r * BR), xi = fmaf(z2i, AR, z3i * BR);                                 \
-        const float yr = fmaf(z2r, AI, z3r * BI), yi = fmaf(z2i, AI, z3i * BI);                                 \
-        if (J < NC) P.set_right(J, I, CplxF{xr - yi, xi + yr});                                               \
-        if (I < NC) P.set_right(I, J, CplxF{xr + yi, xi - yr});                                               \
+    const R z2r = z2.re, z2i = z2.im, z3r = z3.re, z3i = z3.im;
+#define PISAB_VAC_DIAG(C, DA, DB)                                                                            \
+    P.set_right(C, C, CplxT<R>{t_fma(z2r, t_splat<R>(DA), t_fma(z3r, t_splat<R>(DB), t_splat<R>(1.0f))),       \
+                               t_fma(z2i, t_splat<R>(DA), t_mul(z3i, t_splat<R>(DB)))});
+#define PISAB_VAC_OFF(I, J, AR, AI, BR, BI)                                                                              \
+    {                                                                                                                    \
+        const R xr = t_fma(z2r, t_splat<R>(AR), t_mul(z3r, t_splat<R>(BR))), xi = t_fma(z2i, t_splat<R>(AR), t_mul(z3i, t_splat<R>(BR))); \
+        const R yr = t_fma(z2r, t_splat<R>(AI), t_mul(z3r, t_splat<R>(BI))), yi = t_fma(z2i, t_splat<R>(AI), t_mul(z3i, t_splat<R>(BI))); \
+        if (J < NC) P.set_right(J, I, CplxT<R>{t_sub(xr, yi), t_add(xi, yr)});                                           \
+        if (I < NC) P.set_right(I, J, CplxT<R>{t_add(xr, yi), t_sub(xi, yr)});                                           \
     }
     PISAB_VAC_DIAG(0, A.d0, B.d0)
     PISAB_VAC_DIAG(1, A.d1, B.d1)
@@ -367,6 +500,17 @@ __device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, 
     PISAB_VAC_OFF(1, 2, A.r12, A.i12, B.r12, B.i12)
 #undef PISAB_VAC_DIAG
 #undef PISAB_VAC_OFF
+}
+// ts carries the nu / nubar sign: vacuum_columns uses exp(+i hdm ts) - 1 = expm1i_neg(-hdm ts)
+template <int NC, typename PROP>
+__device__ __forceinline__ void vacuum_columns_mp(const OscTable &o, double ts, PROP &P) {
+    vacuum_columns_t<NC, float>(o, expm1i_neg(-o.hdm21 * ts), expm1i_neg(-o.hdm31 * ts), P);
+}
+template <int NC, typename PROP>
+__device__ __forceinline__ void vacuum_columns_mp2(const OscTable &o, double tsa, double tsb, PROP &P) {
+    const CplxF a2 = expm1i_neg(-o.hdm21 * tsa), a3 = expm1i_neg(-o.hdm31 * tsa);
+    const CplxF b2 = expm1i_neg(-o.hdm21 * tsb), b3 = expm1i_neg(-o.hdm31 * tsb);
+    vacuum_columns_t<NC, f2>(o, Cplx2{f2{a2.re, b2.re}, f2{a2.im, b2.im}}, Cplx2{f2{a3.re, b3.re}, f2{a3.im, b3.im}}, P);
 }
 
 } // namespace pisab

@@ -125,4 +125,118 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
     }
 }
 
+// The same walk for a PAIR of events handled by one thread in the FP32 mode (prob3_mp.cuh: float part lane-packed).
+// Both events must cross the same shells (the host pairs events of equal pisab_layer_count and flags the container
+// PISAB_CONTAINER_PAIR_ALIGNED): control flow follows event 0, every decision is re-checked for event 1 and a
+// disagreement is reported through `mismatch` (the caller poisons the pair's weights rather than histogram a wrong
+// number).  Geometry, densities and segment lengths stay per event and in FP64; a segment of length <= 0 in one lane
+// only (exact tangency) becomes t = 0, i.e. the identity for that lane.
+template <int NR, int NC, bool STD, typename H0, typename PROP>
+__device__ __forceinline__ void propagate_earth_pair(const H0 &h0, const OscTable &osc, const EarthTable &E,
+                                                     const double (&cz)[2], const double (&inv_e)[2], int nubar,
+                                                     int flav, PROP &P, bool &mismatch) {
+    const Herm3 &vm = osc.vm;
+    const double T_SCALE = kTab[18];
+    enum { ACT_R = 1, ACT_L = 2 };
+    const int idx = E.idx_first_inner;
+    const bool tangent = cz[0] < E.limit[idx];
+    mismatch = (cz[1] < E.limit[idx]) != tangent;
+    bool have_r = false, have_l = false;
+    double cz2[2], base[2], l_cur[2], sq_cur[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        cz2[e] = __dmul_rn(cz[e], cz[e]);
+        base[e] = __dmul_rn(-E.r_det, cz[e]);
+        l_cur[e] = __dadd_rn(base[e], shell_root_fast(E.rd2, cz2[e], E.rj2[0]));
+        sq_cur[e] = 0.0;
+    }
+    int j = 0, phase = 0;
+#ifndef PISAB_NO_VACUUM_SHORTCUT
+    if (osc.vac_ok != 0.0 && E.rho[0] == 0.0 && idx >= 2) {
+        double seg[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const double sq_next = shell_root_fast(E.rd2, cz2[e], E.rj2[1]);
+            const double l_next = __dadd_rn(base[e], sq_next);
+            seg[e] = __dsub_rn(l_cur[e], l_next);
+            l_cur[e] = l_next;
+            sq_cur[e] = sq_next;
+        }
+        j = 1;
+        if (seg[0] > 0.0 || seg[1] > 0.0) {
+            const double sgn = nubar > 0 ? -T_SCALE : T_SCALE;
+            vacuum_columns_mp2<NC>(osc, sgn * fmax(seg[0], 0.0) * inv_e[0], sgn * fmax(seg[1], 0.0) * inv_e[1], P);
+            have_r = true;
+        }
+    }
+#endif
+    for (;;) {
+        double seg[2];
+        int act;
+        bool last = false;
+        const int shell = j;
+        if (!tangent) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const double l_next = (j + 1 < idx) ? __dadd_rn(base[e], shell_root_fast(E.rd2, cz2[e], E.rj2[j + 1])) : 0.0;
+                seg[e] = __dsub_rn(l_cur[e], l_next);
+                l_cur[e] = l_next;
+            }
+            act = (j + 1 == idx) ? ACT_L : ACT_R;
+            last = (j + 1 == idx);
+            ++j;
+        } else if (phase == 1) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) seg[e] = __dsub_rn(base[e], sq_cur[e]);
+            act = ACT_L;
+            phase = 0;
+        } else {
+            const bool more = j + 1 < E.n_radii;
+            const bool innermost = !(more && E.limit[j + 1] > cz[0]);
+            mismatch = mismatch || (!(more && E.limit[j + 1] > cz[1]) != innermost);
+            if (innermost) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) seg[e] = __dsub_rn(l_cur[e], __dsub_rn(base[e], sq_cur[e]));
+                act = ACT_R;
+                last = true;
+            } else {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const double sq_next = shell_root_fast(E.rd2, cz2[e], E.rj2[j + 1]);
+                    const double l_next = __dadd_rn(base[e], sq_next);
+                    seg[e] = __dsub_rn(l_cur[e], l_next);
+                    l_cur[e] = l_next;
+                    sq_cur[e] = sq_next;
+                }
+                act = (j >= idx) ? (ACT_R | ACT_L) : ACT_R;
+                if (j + 1 == idx) phase = 1;
+                ++j;
+            }
+        }
+        const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
+        if (seg[0] > 0.0 || seg[1] > 0.0) {
+            typename PROP::cplx T[3][3];
+            h0.layer(E.rho[rho_shell], vm, T_SCALE * fmax(seg[0], 0.0), T_SCALE * fmax(seg[1], 0.0), T);
+            if (act & ACT_R) {
+                if (have_r) P.mul_right(T);
+                else { P.init_right(T); have_r = true; }
+            }
+            if (act & ACT_L) {
+                if (have_l) P.mul_left(T);
+                else { P.init_left(T, flav); have_l = true; }
+            }
+        }
+        if (last) break;
+    }
+    if (!have_r || !have_l) {
+        typename PROP::cplx I[3][3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) I[a][b] = typename PROP::cplx{f2{a == b ? 1.0f : 0.0f, a == b ? 1.0f : 0.0f}, f2{0.0f, 0.0f}};
+        if (!have_r) P.init_right(I);
+        if (!have_l) P.init_left(I, flav);
+    }
+}
+
 } // namespace pisab

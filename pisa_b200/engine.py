@@ -21,12 +21,14 @@ EVENT_KEYS = ("true_energy", "true_coszen", "nu_flux", "weights", "index")
 
 
 class _Block:
-    __slots__ = ("name", "nubar", "flav", "n", "dev", "host", "stage", "order", "pack_index")
+    __slots__ = ("name", "nubar", "flav", "n", "n_real", "dev", "host", "stage", "order", "pack_index", "flags")
 
     def __init__(self, name, nubar, flav, n):
         self.name, self.nubar, self.flav, self.n = name, int(nubar), int(flav), int(n)
+        self.n_real = self.n                 # without the zero-weight padding of the pair-aligned layout
         self.dev, self.host, self.stage, self.order = {}, {}, None, None
         self.pack_index = False
+        self.flags = 0
 
 
 class ReweightEngine:
@@ -78,13 +80,28 @@ class ReweightEngine:
             # are physically re-ordered so that a warp's 32 events cross the same number of Earth shells
             # (no divergence) AND its loads are contiguous; a histogram does not depend on the event order
             cz = blk.dev["true_coszen"] if "true_coszen" in blk.dev else blk.host["true_coszen"].to(self.device)
-            order = ops.layer_order(self.earth, cz).long()
+            dummy = None
+            if self.tdtype == torch.float32 and n > 0:
+                # FP32 mode: the template kernel handles TWO events per thread in the lanes of the packed FP32
+                # instructions; pairs must cross the same shells, so every class is padded to an even size with a
+                # repeat of its last event carrying weight 0 and bin -1 (at most one per class)
+                order, dummy = ops.pair_aligned_order(self.earth, cz)
+                blk.flags |= _lib.CONTAINER_PAIR_ALIGNED
+                blk.n = int(order.numel())
+            else:
+                order = ops.layer_order(self.earth, cz).long()
+
+            def rearranged(t, key, idx, pad):
+                out = t[idx].contiguous()
+                if pad is not None and key in ("weights", "index"):
+                    out[pad] = 0 if key == "weights" else -1
+                return out
             for k in list(blk.dev):
-                blk.dev[k] = blk.dev[k][order].contiguous()
+                blk.dev[k] = rearranged(blk.dev[k], k, order, dummy)
             if blk.host:
-                order_h = order.cpu()
+                order_h, dummy_h = order.cpu(), None if dummy is None else dummy.cpu()
                 for k in list(blk.host):
-                    blk.host[k] = blk.host[k][order_h].contiguous().pin_memory()
+                    blk.host[k] = rearranged(blk.host[k], k, order_h, dummy_h).pin_memory()
         if blk.pack_index:
             # host mode: the static bin index (-1 .. n_bins-1) travels as index + 1 in ONE byte per event and is
             # widened on the device after the copy (41 instead of 44 bytes per event over PCIe)
@@ -102,7 +119,7 @@ class ReweightEngine:
 
     @property
     def n_events(self):
-        return sum(b.n for b in self.blocks)
+        return sum(b.n_real for b in self.blocks)
 
     def _result_buffer(self):
         if self._out is None or self._out.shape[0] != len(self.blocks):
@@ -143,7 +160,7 @@ class ReweightEngine:
                 chunk = self.blocks[lo:lo + ops.MAX_BATCH]
                 desc = [dict(nubar=b.nubar, flav=b.flav, energy=b.dev["true_energy"], coszen=b.dev["true_coszen"],
                              nu_flux=b.dev["nu_flux"], weights=b.dev["weights"], index=b.dev["index"],
-                             scale=scales[lo + j]) for j, b in enumerate(chunk)]
+                             scale=scales[lo + j], flags=b.flags) for j, b in enumerate(chunk)]
                 self._batches.append((lo, ops.TemplateBatch(desc, self.n_bins)))
         return self._batches
 
@@ -272,7 +289,7 @@ class ReweightEngine:
                 batch = ops.TemplateBatch([dict(nubar=blk.nubar, flav=blk.flav, energy=views["true_energy"],
                                                 coszen=views["true_coszen"], nu_flux=views["nu_flux"],
                                                 weights=views["weights"], index=views["index"],
-                                                scale=scales[i])], self.n_bins)
+                                                scale=scales[i], flags=blk.flags)], self.n_bins)
                 self._host_batches[(i, s, changed)] = batch
             ops.reweight_hist_batch(consts, self.earth, batch, out=out[i:i + 1])
             self._stage_free[s].record(main)

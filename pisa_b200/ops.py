@@ -232,6 +232,34 @@ def propagate_layers(consts, nubar, energy, densities, distances, out=None):
     return out
 
 
+def layer_counts(earth, coszen):
+    """Number of Earth shells every event crosses (int32; ``pisab_layer_count``): the class key of ``layer_order``."""
+    _chk(coszen, "coszen")
+    n = coszen.numel()
+    count = torch.empty(n, dtype=torch.int32, device=coszen.device)
+    f = _lib.fn("pisab_layer_count", coszen.dtype)
+    _lib.check(f(ctypes.byref(earth), _ptr(coszen), n, _ptr(count), _stream()))
+    return count
+
+
+def pair_aligned_order(earth, coszen):
+    """Setup-time helper for the two-events-per-thread FP32 kernel: (sel, dummy) with ``sel`` (int64) listing the
+    events grouped by crossed shells like ``layer_order`` and every class padded to an EVEN size by repeating its last
+    event, ``dummy`` (bool) marking the repeats (their weight must be set to 0 and their bin index to -1).  Events
+    2k and 2k+1 of ``x[sel]`` then cross the same shells (PISAB_CONTAINER_PAIR_ALIGNED)."""
+    count = layer_counts(earth, coszen)
+    order = torch.sort(count, descending=True, stable=True).indices
+    _, sizes = torch.unique_consecutive(count[order], return_counts=True)
+    ends = torch.cumsum(sizes, 0) - 1
+    extra = ends[sizes % 2 == 1]                       # position (in sorted order) of the event to repeat
+    pos = torch.cat([torch.arange(order.numel(), device=order.device), extra])
+    pos = torch.sort(pos, stable=True).values          # repeats land right behind their originals
+    dummy = torch.zeros(pos.numel(), dtype=torch.bool, device=order.device)
+    if pos.numel() > 1:
+        dummy[1:] = pos[1:] == pos[:-1]
+    return order[pos], dummy
+
+
 def layer_order(earth, coszen):
     """Setup-time helper: permutation (int32) listing the events grouped by the number of Earth
     shells they cross, deepest first, stable within a group.  Passing it as ``order`` to
@@ -546,6 +574,7 @@ class TemplateBatch:
             d.d_order = 0 if order is None else order.data_ptr()
             d.d_weights_out = 0 if wout is None else wout.data_ptr()
             d.n, d.scale, d.nubar, d.flav = n, float(c.get("scale", 1.0)), int(c["nubar"]), int(c["flav"])
+            d.flags = int(c.get("flags", 0))
             self._keep.append((e, c["coszen"], c["nu_flux"], c["weights"], c["index"], order, wout))
         self.dtype = dt
         self.device = containers[0]["energy"].device

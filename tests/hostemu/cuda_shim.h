@@ -26,6 +26,8 @@ static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x)
 struct double2 { double x, y; };
 struct float2 { float x, y; };
 static inline float2 make_float2(float x, float y) { return float2{x, y}; }
+struct float4 { float x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 #include <cstring>
 static inline int __double2loint(double v) { uint64_t b; std::memcpy(&b, &v, 8); return (int)(uint32_t)(b & 0xffffffffull); }

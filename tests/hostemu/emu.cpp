@@ -49,16 +49,44 @@ extern "C" int emu_propagate_mp(const pisab_osc_consts_t *c, const pisab_earth_t
         const Herm3 hh = herm_axpy(inv_e, ot.hv[nubar > 0 ? 0 : 1], ot.lr);
         if (probability) {
             H0MP<false> h0; h0.init(hh);
-            PropagatorF<3, 3> P;
+            float2 buf[18];
+            PropagatorSmemF<3, 3> P{buf, 1};
             propagate_earth<3, 3, false>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
             for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) probability[i * 9 + a * 3 + b] = P.prob(b, a);
         }
         if (prob_e) {
-            PropagatorF<1, 2> P;
+            float2 buf[9];
+            PropagatorSmemF<1, 2> P{buf, 1};
             if (ot.std_matter != 0.0) { H0MP<true> h0; h0.init(hh); propagate_earth<1, 2, true>(h0, ot, et, coszen[i], inv_e, nubar, flav, P); }
             else { H0MP<false> h0; h0.init(hh); propagate_earth<1, 2, false>(h0, ot, et, coszen[i], inv_e, nubar, flav, P); }
             prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
         }
+    }
+    return 0;
+}
+
+// FP32 mode, two events per thread (lane-packed float part): events (2k, 2k+1) are propagated together; the caller
+// orders the events so that pairs cross the same shells.  mismatch[k] = 1 where a pair disagreed on a decision.
+extern "C" int emu_propagate_mp_pairs(const pisab_osc_consts_t *c, const pisab_earth_t *e, int nubar, int flav,
+                                      const double *energy, const double *coszen, int64_t n, double *prob_e,
+                                      double *prob_mu, int *mismatch) {
+    OscTable ot; EarthTable et;
+    int rc = build_osc_table(c, &ot); if (rc) return rc;
+    rc = build_earth_table(e, &et); if (rc) return rc;
+    if (n % 2) return 1;
+#pragma omp parallel for
+    for (int64_t k = 0; k < n / 2; ++k) {
+        const double cz[2] = {coszen[2 * k], coszen[2 * k + 1]};
+        const double inv_e[2] = {rcp_fast(energy[2 * k]), rcp_fast(energy[2 * k + 1])};
+        const Herm3 ha = herm_axpy(inv_e[0], ot.hv[nubar > 0 ? 0 : 1], ot.lr), hb = herm_axpy(inv_e[1], ot.hv[nubar > 0 ? 0 : 1], ot.lr);
+        float4 buf[9];
+        PropagatorSmemP<1, 2> P{buf, 1};
+        bool bad = false;
+        if (ot.std_matter != 0.0) { H0MP2<true> h0; h0.init(ha, hb); propagate_earth_pair<1, 2, true>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
+        else { H0MP2<false> h0; h0.init(ha, hb); propagate_earth_pair<1, 2, false>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
+        const f2 pe = P.prob_r(0, 0), pm = P.prob_r(0, 1);
+        prob_e[2 * k] = pe.x; prob_e[2 * k + 1] = pe.y; prob_mu[2 * k] = pm.x; prob_mu[2 * k + 1] = pm.y;
+        mismatch[k] = bad ? 1 : 0;
     }
     return 0;
 }

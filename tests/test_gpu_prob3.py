@@ -349,3 +349,54 @@ def test_edge_directions_and_energies():
                                              torch.tensor(CZ, device=dev), flav=flav, want_probability=False)
             assert np.allclose(pe.cpu().numpy(), ref[:, 0, flav], rtol=1e-10, atol=1e-12)
             assert np.allclose(pmu.cpu().numpy(), ref[:, 1, flav], rtol=1e-10, atol=1e-12)
+
+
+def test_fp32_pair_kernel_equals_one_event_per_thread():
+    """FP32 mode, two events per thread in the lanes of the packed FP32 instructions (reweight_hist_pair_kernel) against
+    the one-event-per-thread kernel on the same pair-aligned containers: the per-event arithmetic is bit-identical
+    (tests/test_device_math_emulation.py), the histograms differ only by the summation order; the zero-weight padding
+    of odd classes does not change any bin; a container that breaks the pairing promise is poisoned, not mis-binned."""
+    from pisa_b200 import _lib, ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L, earth = _earth()
+    binning, _keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    ops.set_f32_math("mixed")
+    for nsi in (False, True):
+        dm, mix, mp = syn.osc_matrices(nsi=syn.STD_NSI if nsi else None)
+        consts = ops.OscConsts.from_matrices(dm, mix, mp)
+        eng = ReweightEngine(earth, 128, np.float32, dev)
+        ref = ReweightEngine(earth, 128, np.float64, dev)
+        for c, (name, nubar, flav) in enumerate(syn.CONTAINERS):
+            n = 50_001 + 37 * c                                     # odd sizes: classes need padding
+            ev = syn.make_events_torch(n, seed=90 + c, dtype=np.float32, device=dev)
+            idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
+            blk = eng.add_container(name, nubar, flav, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"], idx)
+            assert blk.flags & _lib.CONTAINER_PAIR_ALIGNED and blk.n % 2 == 0 and 0 <= blk.n - blk.n_real <= 16
+            cnt = ops.layer_counts(earth, blk.dev["true_coszen"])
+            assert bool((cnt[0::2] == cnt[1::2]).all())
+            ref.add_container(name, nubar, flav, ev["true_energy"].double(), ev["true_coszen"].double(),
+                              ev["nu_flux"].double(), ev["weights"].double(), idx)
+        pair = eng.evaluate(consts).clone()
+        assert bool(torch.isfinite(pair).all())
+        for b in eng.blocks:                                        # same arrays through the one-event kernel
+            b.flags = 0
+        eng._batches = None
+        single = eng.evaluate(consts).clone()
+        assert torch.allclose(pair, single, rtol=1e-12, atol=0)
+        full = ref.evaluate(consts)                                  # FP64 arithmetic on the same (float32-valued) events
+        nz = full[:, 0] > 0
+        assert float(((pair[:, 0] - full[:, 0]).abs()[nz] / full[:, 0][nz]).max()) < 2e-6
+        for _ in range(2):
+            for b in eng.blocks:
+                b.flags = _lib.CONTAINER_PAIR_ALIGNED
+            eng._batches = None
+            assert torch.equal(eng.evaluate(consts), pair)           # bit-reproducible
+    # broken promise: unsorted events flagged as pair-aligned
+    bad = ReweightEngine(earth, 128, np.float32, dev, sort_events=False)
+    ev = syn.make_events_torch(20_000, seed=5, dtype=np.float32, device=dev)
+    idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
+    blk = bad.add_container("numu_cc", 1, 1, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"], idx)
+    blk.flags = _lib.CONTAINER_PAIR_ALIGNED
+    assert bool(torch.isnan(bad.evaluate(consts)).any())
