@@ -55,3 +55,12 @@ def test_fp32_mode_math_on_host_within_1e5_of_fp64_oracle(emu, nsi, nubar):
 def test_fp32_mode_math_on_host_lri_and_small_earth(emu):
     assert emu.run_mp(n=20000, lri=np.diag([1e-14, -1e-14, 0.0]), seed=12, verbose=False) < 1e-5
     assert emu.run_mp(n=20000, model="PREM_4layer.dat", depth=10.0, seed=13, verbose=False) < 1e-5
+
+
+@pytest.mark.parametrize("nsi,nubar", [(False, 1), (True, -1)])
+def test_fp32_mode_pairs_are_bit_identical_to_single_events(emu, nsi, nubar):
+    """Two events per thread (float part in the two lanes of the packed FP32 instructions, emulated lane-wise on the
+    host) give bit for bit the probabilities of the one-event form; a pair whose events cross different shells is
+    flagged."""
+    identical, flagged_ok, n_unequal = emu.run_pairs(n=40000, nsi=nsi, nubar=nubar, seed=21)
+    assert identical and flagged_ok and n_unequal > 0
