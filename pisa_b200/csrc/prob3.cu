@@ -427,11 +427,18 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
 // FP32 instructions, halving its issue slots per event; FP64 eigenvalues / phases / geometry stay per event) ----------
 // Requirements, guaranteed by the host (PISAB_CONTAINER_PAIR_ALIGNED): float storage, an even number of events,
 // events 2k and 2k+1 cross the same Earth shells, no `order` indirection, no per-event outputs.
-#ifndef PISAB_PAIR_MIN_BLOCKS
-#define PISAB_PAIR_MIN_BLOCKS 2
+// Block of 128 threads, four blocks per SM (128 registers): the same 16 warps per SM as 2 x 256, but finer-grained
+// (measured +6 %, profiles/r02_pair_kernel_variants.txt); three blocks of 256 at 85 registers spill (-25 %).
+#ifndef PISAB_PAIR_BLOCK
+#define PISAB_PAIR_BLOCK 128
 #endif
+#ifndef PISAB_PAIR_MIN_BLOCKS
+#define PISAB_PAIR_MIN_BLOCKS 4
+#endif
+constexpr int kPairBlock = PISAB_PAIR_BLOCK;
 static size_t fused_pair_smem_bytes(int n_bins) {
-    return WarpHist::smem_bytes(kBlock, n_bins) + (size_t)kBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + 48);
+    return WarpHist::smem_bytes(kPairBlock, n_bins) +
+           (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48);
 }
 
 template <bool STD>
@@ -440,12 +447,14 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
                                                 double *__restrict__ partials, double *s_hist) {
     // dynamic shared memory: [histogram] [state: 9 float4 x block] [flux float4] [e, cz, w: float2 each] [bin int2]
     const int n_bins = batch.n_bins;
-    unsigned char *s_dyn = reinterpret_cast<unsigned char *>(s_hist) + WarpHist::smem_bytes(kBlock, n_bins);
-    float4(*s_state)[kBlock] = reinterpret_cast<float4(*)[kBlock]>(s_dyn);
-    s_dyn += (size_t)PropagatorSmemP<1, 2>::kSlots * kBlock * sizeof(float4);
+    unsigned char *s_dyn = reinterpret_cast<unsigned char *>(s_hist) + WarpHist::smem_bytes(kPairBlock, n_bins);
+    float4(*s_state)[kPairBlock] = reinterpret_cast<float4(*)[kPairBlock]>(s_dyn);
+    s_dyn += (size_t)PropagatorSmemP<1, 2>::kSlots * kPairBlock * sizeof(float4);
+    float2(*s_base)[kPairBlock] = reinterpret_cast<float2(*)[kPairBlock]>(s_dyn);     // packed per-pair invariants (H0MP2)
+    s_dyn += (size_t)H0MP2<true>::kSlots * kPairBlock * sizeof(float2);
     float4 *s_flux = reinterpret_cast<float4 *>(s_dyn);
-    float2 *s_e = reinterpret_cast<float2 *>(s_flux + kBlock), *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
-    int2 *s_bin = reinterpret_cast<int2 *>(s_w + kBlock);
+    float2 *s_e = reinterpret_cast<float2 *>(s_flux + kPairBlock), *s_cz = s_e + kPairBlock, *s_w = s_cz + kPairBlock;
+    int2 *s_bin = reinterpret_cast<int2 *>(s_w + kPairBlock);
     WarpHist wh(s_hist, n_bins);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)n_ranks * blockDim.x;
@@ -481,8 +490,10 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
             const double inv_e[2] = {rcp_fast((double)e2.x), rcp_fast((double)e2.y)};
             const double sg = C.nubar > 0 ? 1.0 : -1.0;
             H0MP2<STD> h0;
+            h0.col = &s_base[0][tid];
+            h0.pitch = kPairBlock;
             h0.init(herm_axpy(sg * inv_e[0], osc.hv[0], osc.lr), herm_axpy(sg * inv_e[1], osc.hv[0], osc.lr)); // hv[1] = -hv[0]
-            PropagatorSmemP<1, 2> P{&s_state[0][tid], kBlock};
+            PropagatorSmemP<1, 2> P{&s_state[0][tid], kPairBlock};
             bool mismatch;
             propagate_earth_pair<1, 2, STD>(h0, osc, s_earth, cz, inv_e, C.nubar, C.flav, P, mismatch);
             const f2 pe = P.prob_r(0, 0), pmu = P.prob_r(0, 1);
@@ -506,7 +517,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
 }
 
 template <bool STD>
-__global__ void __launch_bounds__(kBlock, PISAB_PAIR_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPairBlock, PISAB_PAIR_MIN_BLOCKS)
 reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
                           const unsigned long long *__restrict__ /* bounds: same signature as reweight_hist_kernel */) {
@@ -786,6 +797,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     const size_t smem = pairs ? fused_pair_smem_bytes(n_bins) : smem_events;
     const int64_t n_units = pairs ? (n_max + 1) / 2 : n_max;   // what a thread iterates over: events or pairs
     const int64_t unit_min = pairs ? 4 : 8;                    // >= 8 events per thread
+    const int block = pairs ? kPairBlock : kBlock;
     {
         // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
         cudaFuncAttributes fa;
@@ -809,17 +821,17 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     int ranks;
     {
         int occ = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
         const int resident = (sm_count() > 0 ? sm_count() : 148) * occ;
         const int nc = batch.n_containers;
-        const int64_t by_work = (n_units + (int64_t)kBlock * unit_min - 1) / ((int64_t)kBlock * unit_min);
-        const int64_t by_thread = (n_units + kBlock - 1) / kBlock;
+        const int64_t by_work = (n_units + (int64_t)block * unit_min - 1) / ((int64_t)block * unit_min);
+        const int64_t by_thread = (n_units + block - 1) / block;
         int64_t r = by_work;
         const int64_t cap = ((int64_t)resident * PISAB_SPREAD_WAVES + nc - 1) / nc;
         if (r > cap) r = cap;
         const int64_t fill = (resident + nc - 1) / nc; // one resident wave spread over the containers
         if (r < fill) r = by_thread < fill ? by_thread : fill;
-        const int64_t ws_cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16; // pisab_hist_workspace_bytes
+        int64_t ws_cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16; // pisab_hist_workspace_bytes
         if (r > ws_cap) r = ws_cap;
         if (r < 1) r = 1;
         ranks = (int)r;
@@ -848,7 +860,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     }
     {
         LaunchTimer t(s);
-        kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace, nullptr);
+        kernel<<<grid, block, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace, nullptr);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());

@@ -409,6 +409,103 @@ struct H0Core {
     }
 };
 
+// ---- lock-step form of the FP64 side for a PAIR --------------------------------------------------------------
+// eigen_roots_centered + layer_coefficients for the two events of a pair, written stage by stage over e = 0, 1 (and
+// over the 4 phase arguments) so that independent instructions sit next to each other: one warp then has 2-4
+// dependency chains in flight instead of one (the per-event forms above are each a single chain of ~100 dependent
+// FP64 / float instructions, and with four warps per scheduler their latency, not the issue rate, set the time).
+// Same operations in the same order per event: bit-identical to the per-event forms.
+#define PISAB_E2 _Pragma("unroll") for (int e = 0; e < 2; ++e)
+#define PISAB_E4 _Pragma("unroll") for (int e = 0; e < 4; ++e)
+__device__ __forceinline__ void eigen_roots_centered2(const double (&c1)[2], const double (&c0)[2], RootsC (&R)[2]) {
+    double p[2], q[2], disc[2], rs[2], b[2], inv[2], sq[2], zr[2], zi[2];
+    PISAB_E2 { p[e] = -3.0 * c1[e]; p[e] = p[e] > kTab[20] ? p[e] : kTab[20]; q[e] = -13.5 * c0[e]; }
+    PISAB_E2 disc[e] = 27.0 * fma(0.25 * c1[e] * c1[e], p[e] - c1[e], c0[e] * fma(6.75, c0[e], q[e]));
+    { // rsqrt_fast(p), sqrt_pos(disc): seeds first, then the refinements side by side
+        double r0[2], r1[2], t0[2], t1[2], e0[2], e1[2], xs[2];
+        PISAB_E2 { xs[e] = disc[e] > kTab[20] ? disc[e] : kTab[20]; r0[e] = rsqrt_seed(p[e]); r1[e] = rsqrt_seed(xs[e]); }
+        PISAB_E2 { t0[e] = p[e] * r0[e]; t1[e] = xs[e] * r1[e]; }
+        PISAB_E2 { e0[e] = fma(-t0[e], r0[e], 1.0); e1[e] = fma(-t1[e], r1[e], 1.0); }
+        PISAB_E2 { rs[e] = fma(r0[e] * e0[e], fma(e0[e], kTab[19], 0.5), r0[e]); sq[e] = fma(t1[e] * e1[e], fma(e1[e], kTab[19], 0.5), t1[e]); }
+    }
+    PISAB_E2 { b[e] = kTab[17] * (p[e] * rs[e]); inv[e] = rs[e] * rs[e] * rs[e]; }
+    PISAB_E2 { zr[e] = q[e] * inv[e]; zi[e] = sq[e] * inv[e]; }
+    float cf[2], sf[2];
+    { // unit_cube_root_seed, stage-wise
+        float x[2], y[2], ax[2], mx[2], mn[2], t[2], u[2], a[2], th[2], v[2];
+        PISAB_E2 { x[e] = (float)zr[e]; y[e] = (float)zi[e]; ax[e] = fabsf(x[e]); mx[e] = fmaxf(ax[e], y[e]); mn[e] = fminf(ax[e], y[e]); }
+#ifdef PISAB_HOST_EMU
+        PISAB_E2 t[e] = mn[e] / mx[e];
+#else
+        PISAB_E2 t[e] = __fdividef(mn[e], mx[e]);
+#endif
+        PISAB_E2 { u[e] = t[e] * t[e]; a[e] = fmaf(u[e], 0.00782548263669014f, -0.03689862787723541f); }
+        PISAB_E2 a[e] = fmaf(u[e], a[e], 0.08374155312776566f);
+        PISAB_E2 a[e] = fmaf(u[e], a[e], -0.13480405509471893f);
+        PISAB_E2 a[e] = fmaf(u[e], a[e], 0.19879871606826782f);
+        PISAB_E2 a[e] = fmaf(u[e], a[e], -0.3332637548446655f);
+        PISAB_E2 a[e] = fmaf(u[e], a[e], 0.9999993443489075f) * t[e];
+        PISAB_E2 { a[e] = y[e] > ax[e] ? 1.57079632679489662f - a[e] : a[e]; a[e] = x[e] < 0.0f ? 3.14159265358979324f - a[e] : a[e]; }
+        PISAB_E2 { th[e] = a[e] * (1.0f / 3.0f); v[e] = th[e] * th[e]; }
+        PISAB_E2 {
+            sf[e] = th[e] * fmaf(v[e], fmaf(v[e], fmaf(v[e], -0.00019222621631342918f, 0.008328950963914394f), -0.1666656732559204f), 0.9999999403953552f);
+            cf[e] = fmaf(v[e], fmaf(v[e], fmaf(v[e], -0.0013333901297301054f, 0.041627395898103714f), -0.4999910891056061f), 0.9999997019767761f);
+        }
+    }
+    double ct[2], st[2];
+    { // unit_cube_root_mp correction
+        double c[2], s2[2], m[2], rho[2], third[2], u2r[2], u2i[2], u3r[2], u3i[2], d[2];
+        PISAB_E2 { c[e] = (double)cf[e]; s2[e] = (double)sf[e]; }
+        PISAB_E2 { m[e] = fma(c[e], c[e], fma(s2[e], s2[e], -1.0)); u2r[e] = fma(c[e], c[e], -s2[e] * s2[e]); u2i[e] = 2.0 * c[e] * s2[e]; }
+        PISAB_E2 { rho[e] = fma(m[e], -0.5, 1.0); third[e] = fma(m[e], -0.5, kTab[16]); u3r[e] = fma(u2r[e], c[e], -u2i[e] * s2[e]); u3i[e] = fma(u2r[e], s2[e], u2i[e] * c[e]); }
+        PISAB_E2 d[e] = fma(zi[e], u3r[e], -zr[e] * u3i[e]) * third[e];
+        PISAB_E2 { ct[e] = fma(-s2[e], d[e], c[e]) * rho[e]; st[e] = fma(c[e], d[e], s2[e]) * rho[e]; }
+    }
+    const double kh = 0.5, ks = kTab[15];
+    PISAB_E2 { R[e].m0 = b[e] * (-kh * ct[e] - ks * st[e]); R[e].m1 = b[e] * (-kh * ct[e] + ks * st[e]); R[e].m2 = b[e] * ct[e]; }
+}
+
+// expm1i_neg for the four phase arguments of a pair-layer at once
+__device__ __forceinline__ void expm1i_neg4(const double (&delta)[4], CplxF (&E)[4]) {
+    double shifted[4], kd[4];
+    int k[4];
+    float r[4], z[4], ps[4], pc[4], sn[4], cm[4];
+    PISAB_E4 { shifted[e] = fma(delta[e], kTab[0], kTab[21]); k[e] = __double2loint(shifted[e]); kd[e] = shifted[e] - kTab[21]; }
+    PISAB_E4 { r[e] = (float)fma(-kd[e], kTab[1], delta[e]); z[e] = r[e] * r[e]; }
+    PISAB_E4 { ps[e] = fmaf(z[e], -1.9515295891e-4f, 8.3321608736e-3f); pc[e] = fmaf(z[e], 2.443315711809948e-5f, -1.388731625493765e-3f); }
+    PISAB_E4 { ps[e] = fmaf(z[e], ps[e], -1.6666654611e-1f); pc[e] = fmaf(z[e], pc[e], 4.166664568298827e-2f); }
+    PISAB_E4 { sn[e] = fmaf(r[e] * z[e], ps[e], r[e]); pc[e] = fmaf(z[e], pc[e], -0.5f); }
+    PISAB_E4 cm[e] = z[e] * pc[e];
+    PISAB_E4 {
+        const bool odd = k[e] & 1;
+        float c1 = odd ? sn[e] : cm[e];
+        c1 = ((k[e] + 1) & 2) ? -c1 : c1;
+        const float off = (k[e] & 3) == 0 ? 0.0f : ((k[e] & 3) == 2 ? -2.0f : -1.0f);
+        float sd = odd ? 1.0f + cm[e] : sn[e];
+        sd = (k[e] & 2) ? -sd : sd;
+        E[e] = CplxF{c1 + off, -sd};
+    }
+}
+
+// layer_coefficients of both events from their roots (t[e] = 2 * 2.534 * length of event e)
+__device__ __forceinline__ void layer_coefficients2(const float (&ea)[2][3], const RootsC (&R)[2], const double (&t)[2],
+                                                    LayerCoefF (&K)[2]) {
+    double g10d[2], g20d[2], g21d[2], delta[4];
+    PISAB_E2 { g10d[e] = R[e].m1 - R[e].m0; g20d[e] = R[e].m2 - R[e].m0; g21d[e] = R[e].m2 - R[e].m1; }
+    PISAB_E2 { delta[2 * e] = g10d[e] * t[e]; delta[2 * e + 1] = g20d[e] * t[e]; }
+    CplxF E[4];
+    expm1i_neg4(delta, E);
+    float g10[2], g20[2], g21[2], r10[2], r20[2], r21[2];
+    PISAB_E2 { g10[e] = (float)g10d[e]; g20[e] = (float)g20d[e]; g21[e] = (float)g21d[e]; }
+    PISAB_E2 { r10[e] = rcp_f32(fmaxf(g10[e], 1e-30f)); r20[e] = rcp_f32(g20[e]); r21[e] = rcp_f32(fmaxf(g21[e], 1e-30f)); }
+    PISAB_E2 {
+        K[e].n1 = CplxF{E[2 * e].re * r10[e], E[2 * e].im * r10[e]};
+        const CplxF f02{E[2 * e + 1].re * r20[e], E[2 * e + 1].im * r20[e]};
+        K[e].n2 = CplxF{(f02.re - K[e].n1.re) * r21[e], (f02.im - K[e].n1.im) * r21[e]};
+        K[e].g10 = g10[e]; K[e].g20 = g20[e]; K[e].ea0 = ea[e][0]; K[e].ea1 = ea[e][1]; K[e].ea2 = ea[e][2];
+    }
+}
+
 // One event per thread
 template <bool STD>
 struct H0MP {
@@ -439,27 +536,74 @@ __device__ __forceinline__ void pack_offdiag(const LayerMatF &a, const LayerMatF
     L.i02 = f2{a.i02, b.i02}; L.r12 = f2{a.r12, b.r12}; L.i12 = f2{a.i12, b.i12};
 }
 
-// Two events per thread (a pair that crosses the same Earth shells): FP64 cores per event, float part lane-packed
+// Two events per thread (a pair that crosses the same Earth shells): FP64 cores per event, float part lane-packed.
+// The packed per-pair invariants (15 float pairs, standard matter) live in a per-thread column of shared memory
+// (`col`, [15][pitch] float2, conflict-free 64-bit accesses): in registers they left too few for the compiler to
+// interleave the two events' FP64 eigenvalue chains, and a warp's time was the SERIAL latency of both chains
+// (ncu, round 2: issue 61 %, `wait` stalls 33 %).
 template <bool STD>
 struct H0MP2 {
     H0Core<STD> core[2];
-    LayerMatT<f2> base;
+    float2 *col; // &s_base[0][threadIdx.x]
+    int pitch;
+    static constexpr int kSlots = 15;
 
+    __device__ __forceinline__ void put(int k, f2 v) { col[k * pitch] = make_float2(v.x, v.y); }
+    __device__ __forceinline__ f2 get(int k) const {
+        const float2 v = col[k * pitch];
+        return f2{v.x, v.y};
+    }
+    __device__ __forceinline__ void store(const LayerMatT<f2> &L) {
+        put(0, L.r01); put(1, L.i01); put(2, L.r02); put(3, L.i02); put(4, L.r12); put(5, L.i12);
+        put(6, L.s0); put(7, L.s1); put(8, L.s2);
+        put(9, L.c01.re); put(10, L.c01.im); put(11, L.c02.re); put(12, L.c02.im); put(13, L.c12.re); put(14, L.c12.im);
+    }
+    __device__ __forceinline__ LayerMatT<f2> load() const {
+        LayerMatT<f2> L;
+        L.r01 = get(0); L.i01 = get(1); L.r02 = get(2); L.i02 = get(3); L.r12 = get(4); L.i12 = get(5);
+        L.s0 = get(6); L.s1 = get(7); L.s2 = get(8);
+        L.c01 = Cplx2{get(9), get(10)}; L.c02 = Cplx2{get(11), get(12)}; L.c12 = Cplx2{get(13), get(14)};
+        return L;
+    }
     __device__ __forceinline__ void init(const Herm3 &ha, const Herm3 &hb) {
         const Herm3 ca = core[0].init(ha), cb = core[1].init(hb);
         if (STD) {
             LayerMatF a, b;
             herm_offdiag_to_float(ca, a);
             herm_offdiag_to_float(cb, b);
+            LayerMatT<f2> base;
             pack_offdiag(a, b, base);
             layer_products(base);
+            store(base);
         }
     }
     // same shell for both events (same density), their own lengths
     __device__ __forceinline__ void layer(double rho, const Herm3 &vm, double ta, double tb, Cplx2 (*T)[3]) const {
         if (STD) {
+#ifdef PISAB_PAIR_NO_LOCKSTEP
             const LayerCoefF ka = core[0].layer(rho, vm, ta, nullptr), kb = core[1].layer(rho, vm, tb, nullptr);
-            assemble_matrix<f2>(base, pack_coef(ka, kb), T);
+            assemble_matrix<f2>(load(), pack_coef(ka, kb), T);
+#else
+            // H0Core<true>::layer for both events in lock-step (see eigen_roots_centered2)
+            const double x = rho * vm.d0, y = x * kTab[16];
+            double c1p[2], c0p[2];
+            PISAB_E2 {
+                const double c1 = fma(-x, core[e].d0c, core[e].c1_0), c0 = fma(-x, core[e].m00, core[e].c0_0);
+                c1p[e] = fma(-3.0 * y, y, c1);
+                c0p[e] = fma(y, fma(-2.0 * y, y, c1), c0);
+            }
+            RootsC R[2];
+            eigen_roots_centered2(c1p, c0p, R);
+            float ea[2][3];
+            PISAB_E2 {
+                const double o0 = fma(-2.0, y, R[e].m0), o12 = R[e].m0 + y;
+                ea[e][0] = (float)(core[e].d0c - o0); ea[e][1] = (float)(core[e].d1c - o12); ea[e][2] = (float)(core[e].d2c - o12);
+            }
+            const double tt[2] = {ta, tb};
+            LayerCoefF K[2];
+            layer_coefficients2(ea, R, tt, K);
+            assemble_matrix<f2>(load(), pack_coef(K[0], K[1]), T);
+#endif
         } else {
             LayerMatF a, b;
             const LayerCoefF ka = core[0].layer(rho, vm, ta, &a), kb = core[1].layer(rho, vm, tb, &b);

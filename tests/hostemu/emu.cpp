@@ -82,8 +82,9 @@ extern "C" int emu_propagate_mp_pairs(const pisab_osc_consts_t *c, const pisab_e
         float4 buf[9];
         PropagatorSmemP<1, 2> P{buf, 1};
         bool bad = false;
-        if (ot.std_matter != 0.0) { H0MP2<true> h0; h0.init(ha, hb); propagate_earth_pair<1, 2, true>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
-        else { H0MP2<false> h0; h0.init(ha, hb); propagate_earth_pair<1, 2, false>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
+        float2 hbuf[15];
+        if (ot.std_matter != 0.0) { H0MP2<true> h0; h0.col = hbuf; h0.pitch = 1; h0.init(ha, hb); propagate_earth_pair<1, 2, true>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
+        else { H0MP2<false> h0; h0.col = hbuf; h0.pitch = 1; h0.init(ha, hb); propagate_earth_pair<1, 2, false>(h0, ot, et, cz, inv_e, nubar, flav, P, bad); }
         const f2 pe = P.prob_r(0, 0), pm = P.prob_r(0, 1);
         prob_e[2 * k] = pe.x; prob_e[2 * k + 1] = pe.y; prob_mu[2 * k] = pm.x; prob_mu[2 * k + 1] = pm.y;
         mismatch[k] = bad ? 1 : 0;
