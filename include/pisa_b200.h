@@ -398,6 +398,7 @@ int pisab_exchange_create(int32_t rank, int32_t world, int64_t capacity_doubles,
 int pisab_exchange_connect(void *ctx, const unsigned char *all_handles /* [world][64] */);
 int pisab_exchange_allreduce(void *ctx, double *d_buf, int64_t count, void *stream);
 int pisab_exchange_status(void *ctx);
+int pisab_exchange_disconnect(void *ctx); /* unmap the peers; all ranks, then synchronise the ranks, then destroy */
 int pisab_exchange_destroy(void *ctx);
 int pisab_sum_slots(const double *d_gathered, int32_t world, int64_t count, double *d_out, void *stream);
 

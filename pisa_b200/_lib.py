@@ -128,6 +128,7 @@ _UNTYPED = {
     "pisab_exchange_connect": (c_i32, [c_vp, c_vp]),
     "pisab_exchange_allreduce": (c_i32, [c_vp, c_vp, c_i64, c_vp]),
     "pisab_exchange_status": (c_i32, [c_vp]),
+    "pisab_exchange_disconnect": (c_i32, [c_vp]),
     "pisab_exchange_destroy": (c_i32, [c_vp]),
     "pisab_sum_slots": (c_i32, [c_vp, c_i32, c_i64, c_vp, c_vp]),
     "pisab_joint_index": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),

@@ -193,12 +193,22 @@ int pisab_exchange_status(void *ctx) {
     return err;
 }
 
-int pisab_exchange_destroy(void *ctx) {
+/* Unmap the peers' buffers (step 1 of an orderly shutdown: every rank disconnects, the host synchronises the ranks,
+ * then every rank destroys -- an exported buffer must not be freed while a peer still maps it). */
+int pisab_exchange_disconnect(void *ctx) {
     ExchangeCtx *c = (ExchangeCtx *)ctx;
     if (!c) return PISAB_OK;
     cudaDeviceSynchronize();
     for (int q = 0; q < c->dev.world; ++q)
-        if (c->connected && q != c->dev.rank && c->peer_base[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+        if (c->connected && q != c->dev.rank && c->peer_base[q]) { cudaIpcCloseMemHandle(c->peer_base[q]); c->peer_base[q] = nullptr; }
+    c->connected = false;
+    return PISAB_OK;
+}
+
+int pisab_exchange_destroy(void *ctx) {
+    ExchangeCtx *c = (ExchangeCtx *)ctx;
+    if (!c) return PISAB_OK;
+    pisab_exchange_disconnect(ctx);
     if (c->local_base) cudaFree(c->local_base);
     delete c;
     return PISAB_OK;

@@ -121,7 +121,7 @@ class PeerExchange:
         ok = torch.tensor([1 if rc == 0 else 0], device=device if dist.get_backend() == "nccl" else "cpu")
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)       # all ranks take the same path
         if int(ok) == 0:
-            self.close()
+            self.close(collective=False)
             raise RuntimeError("peer mapping of the exchange buffers failed on at least one rank: %s"
                                % (_lib.load().pisab_last_error().decode() if rc else "another rank"))
 
@@ -134,8 +134,13 @@ class PeerExchange:
     def status(self):
         return int(self._lib.load().pisab_exchange_status(self.ctx))
 
-    def close(self):
+    def close(self, collective=True):
+        """Orderly shutdown: every rank unmaps its peers, the ranks synchronise, then every rank frees its own buffer
+        (an exported buffer must not be freed while a peer still maps it).  Collective unless ``collective=False``."""
         if self.ctx:
+            self._lib.load().pisab_exchange_disconnect(self.ctx)
+            if collective and dist.is_initialized():
+                dist.barrier()
             self._lib.load().pisab_exchange_destroy(self.ctx)
             self.ctx = None
 
@@ -157,7 +162,7 @@ def _peer_exchange(device, count):
     if ex is not None:
         ex.close()
     try:
-        _peer["exchange"] = PeerExchange(device, max(int(count), 1 << 16))
+        _peer["exchange"] = PeerExchange(device, max(int(count), 1 << 19))   # 4 MB per slot: a 100-template scan fits
     except RuntimeError as exc:
         import warnings
         warnings.warn("pisa_b200: peer-memory exchange unavailable (%s); using all_gather + sum kernel" % exc)
