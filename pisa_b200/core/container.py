@@ -371,13 +371,14 @@ class Container:
         assert src_representation in self.array_representations
         assert isinstance(dest_representation, MultiDimBinning)
         idx = self.bin_index(dest_representation)
+        plan = self.bin_plan(dest_representation)       # bin-sorted tiles + static counts (None above 256 bins)
         self.representation = "events"
         weights = self[key]
         n_bins = dest_representation.size
         cols = [weights] if weights.dim() == 1 else [weights[:, i].contiguous() for i in range(weights.shape[1])]
-        hists = [ops.hist_accumulate(idx, w, n_bins, want_w2=False)[0] for w in cols]
+        hists = [ops.hist_accumulate(idx, w, n_bins, want_w2=False, plan=plan)[0] for w in cols]
         if averaged:
-            counts, _ = ops.hist_accumulate(idx, None, n_bins, want_w2=False)
+            counts, _ = ops.hist_accumulate(idx, None, n_bins, want_w2=False, plan=plan)
             # flat_hist / counts with nan_to_num (translation.py:118-127)
             hists = [torch.nan_to_num(h / counts, nan=0.0, posinf=0.0, neginf=0.0) for h in hists]
         out = hists[0] if weights.dim() == 1 else torch.stack(hists, dim=1)

@@ -452,8 +452,16 @@ class HistPlan:
     the permutation grouping the events by bin and the group offsets.  ``hist_accumulate(..., plan=plan)`` then needs
     only the current weights.  ``None`` from ``hist_plan`` means the binning is not plannable (> 256 bins)."""
 
-    def __init__(self, buf, n, n_bins):
+    def __init__(self, buf, n, n_bins, index):
         self.buf, self.n, self.n_bins = buf, int(n), int(n_bins)
+        self._index, self._counts = index, None
+
+    @property
+    def counts(self):
+        """Event counts per bin (float64): static like the plan, computed once."""
+        if self._counts is None:
+            self._counts = hist_accumulate(self._index, None, self.n_bins, want_w2=False)[0]
+        return self._counts
 
 
 def hist_plan(index, n_bins):
@@ -464,7 +472,7 @@ def hist_plan(index, n_bins):
         return None
     buf = torch.empty(nbytes, dtype=torch.uint8, device=index.device)
     _lib.check(_lib.load().pisab_hist_plan_build(_ptr(index), n, int(n_bins), _ptr(buf), nbytes, _stream()))
-    return HistPlan(buf, n, n_bins)
+    return HistPlan(buf, n, n_bins, index)
 
 
 def hist_accumulate(index, weights, n_bins, want_w2=True, plan=None):
@@ -474,6 +482,9 @@ def hist_accumulate(index, weights, n_bins, want_w2=True, plan=None):
     n = index.numel()
     if plan is not None and (plan.n != n or plan.n_bins != int(n_bins)):
         raise ValueError("the plan was built for %d events / %d bins" % (plan.n, plan.n_bins))
+    if plan is not None and weights is None:
+        c = plan.counts                      # unweighted histogram of static indices: nothing to recompute
+        return c.clone(), (c.clone() if want_w2 else None)
     if plan is not None and weights is not None and weights.data_ptr() % 16 == 0:
         _chk(weights, "weights")
         if weights.numel() != n:

@@ -405,6 +405,9 @@ def test_planned_histogram_vs_oracle(n, n_bins, dtype):
         assert torch.equal(hb, h) and torch.equal(hb2, h2)
     h_only, none = ops.hist_accumulate(ti, tw, n_bins, want_w2=False, plan=plan)
     assert none is None and torch.equal(h_only, h)
+    cnt, cnt2 = ops.hist_accumulate(ti, None, n_bins, plan=plan)      # static counts, cached on the plan
+    want = np.bincount(idx[ok], minlength=n_bins).astype(np.float64)
+    assert np.array_equal(cnt.cpu().numpy(), want) and np.array_equal(cnt2.cpu().numpy(), want)
     if n > 1:
         with pytest.raises(ValueError):
             ops.hist_accumulate(ti[1:].contiguous(), tw[1:].contiguous(), n_bins, plan=plan)
