@@ -305,6 +305,13 @@ typedef struct pisab_container {
     int32_t nubar, flav;
     int32_t flags;            /* PISAB_CONTAINER_*                                              */
     int32_t pad;
+    /* flux.barr_simple evaluated inside the template kernel (PISAB_CONTAINER_FLUX_SYS; all three or none): */
+    const double *d_flux_terms;        /* [n][4] from pisab_flux_barr_terms_*, 32-byte aligned          */
+    const void *d_nu_flux_nominal;     /* [n][2] of the storage type                                    */
+    const void *d_nubar_flux_nominal;  /* [n][2]                                                        */
+    /* optional additive per-event term of utils.hist (hist.py:141-145: weights + astro_weights), storage type [n]:
+     * w = weights * (flux . prob) * scale + astro_weights.  Not above PISAB_DET_MAX_BINS bins or in a scan. */
+    const void *d_astro_weights;
 } pisab_container_t;
 /* The caller guarantees: n is even and events 2k and 2k+1 cross the same number of Earth shells
  * (pisab_layer_count_*), e.g. because the events are sorted by that count and every class was padded to an even size
@@ -312,15 +319,25 @@ typedef struct pisab_container {
  * handles TWO events per thread in the lanes of the packed FP32 instructions (same results, bit for bit, as one
  * event per thread).  A pair that breaks the promise poisons its weights with NaN instead of histogramming them. */
 #define PISAB_CONTAINER_PAIR_ALIGNED 1
+/* nu_flux of this container is NOT read: the kernel evaluates flux.barr_simple (barr_simple.py:139-197) per event in
+ * registers from d_flux_terms and the two nominal fluxes with the systematics of the call's pisab_flux_sys_t -- the
+ * same arithmetic, bit for bit, as pisab_flux_barr_apply_* followed by a template over its output, without the
+ * 80 B/event pass that writes nu_flux and the 16 B/event that re-read it.  Not available above PISAB_DET_MAX_BINS
+ * bins, with per-event outputs, or in pisab_reweight_hist_scan_* (PISAB_ERR_UNSUPPORTED). */
+#define PISAB_CONTAINER_FLUX_SYS 2
+typedef struct pisab_flux_sys {   /* parameters of flux.barr_simple, barr_simple.py:41-52 */
+    double nue_numu_ratio, nu_nubar_ratio, delta_index, barr_uphor_ratio, barr_nu_nubar_ratio;
+} pisab_flux_sys_t;
 int64_t pisab_reweight_batch_workspace_bytes(int32_t n_containers, int32_t n_bins);
+/* flux_sys: NULL unless a container carries PISAB_CONTAINER_FLUX_SYS. */
 int pisab_reweight_hist_batch_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                   const pisab_container_t *containers, int32_t n_containers,
-                                  int32_t n_bins, double *d_hist, void *d_workspace,
-                                  int64_t workspace_bytes, void *stream);
+                                  int32_t n_bins, const pisab_flux_sys_t *flux_sys, double *d_hist,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream);
 int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                   const pisab_container_t *containers, int32_t n_containers,
-                                  int32_t n_bins, double *d_hist, void *d_workspace,
-                                  int64_t workspace_bytes, void *stream);
+                                  int32_t n_bins, const pisab_flux_sys_t *flux_sys, double *d_hist,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* One hypothesis of a fit in ONE call and two launches: the batched template kernel, then one kernel that
  * reduces the per-block partial histograms, applies the optional per-bin detector-systematics scales of
@@ -331,11 +348,11 @@ int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_
  * NULL).  n_bins <= PISAB_DET_MAX_BINS.  Launches of one device must come from one stream at a time. */
 int pisab_reweight_hist_chi2_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                  const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
-                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 const pisab_flux_sys_t *flux_sys, const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
                                  double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream);
 int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                  const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
-                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 const pisab_flux_sys_t *flux_sys, const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
                                  double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream);
 
 /* mod_chi2 (pisa/utils/stats.py:651-695) on device for the scan driver:

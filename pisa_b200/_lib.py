@@ -17,6 +17,7 @@ DET_MAX_BINS = 1024
 DIM_LIN, DIM_LOG, DIM_EDGES = 0, 1, 2
 F32_MATH_FP64, F32_MATH_MIXED = 0, 1
 CONTAINER_PAIR_ALIGNED = 1
+CONTAINER_FLUX_SYS = 2
 
 c_i32, c_i64, c_dbl, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p
 
@@ -70,7 +71,15 @@ class ContainerDesc(ctypes.Structure):
     """pisab_container_t -- one flavour container of a batched template evaluation."""
     _fields_ = [("d_energy", c_vp), ("d_coszen", c_vp), ("d_nu_flux", c_vp), ("d_weights", c_vp),
                 ("d_index", c_vp), ("d_order", c_vp), ("d_weights_out", c_vp), ("n", c_i64),
-                ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32), ("flags", c_i32), ("pad", c_i32)]
+                ("scale", c_dbl), ("nubar", c_i32), ("flav", c_i32), ("flags", c_i32), ("pad", c_i32),
+                ("d_flux_terms", c_vp), ("d_nu_flux_nominal", c_vp), ("d_nubar_flux_nominal", c_vp),
+                ("d_astro_weights", c_vp)]
+
+
+class FluxSys(ctypes.Structure):
+    """pisab_flux_sys_t -- the five systematic parameters of flux.barr_simple (barr_simple.py:41-52)."""
+    _fields_ = [("nue_numu_ratio", c_dbl), ("nu_nubar_ratio", c_dbl), ("delta_index", c_dbl),
+                ("barr_uphor_ratio", c_dbl), ("barr_nu_nubar_ratio", c_dbl)]
 
 
 class FluxItem(ctypes.Structure):
@@ -114,10 +123,11 @@ _SIGNATURES = {
     "pisab_scale_weights": (c_i32, [c_vp, c_dbl, c_i64, c_vp, c_vp]),
     "pisab_hist_transform": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_chi2": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
-                                         ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
-                                         c_i64, c_vp]),
+                                         ctypes.POINTER(ContainerDesc), c_i32, c_i32, ctypes.POINTER(FluxSys), c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_reweight_hist_batch": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
-                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
+                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, ctypes.POINTER(FluxSys), c_vp,
+                                          c_vp, c_i64, c_vp]),
 }
 _UNTYPED = {
     "pisab_hist_workspace_bytes": (c_i64, [c_i64, c_i32]),

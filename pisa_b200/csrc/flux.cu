@@ -12,6 +12,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "flux_device.cuh"
 
 namespace pisab {
 
@@ -129,45 +130,17 @@ flux_barr_terms_kernel(const __grid_constant__ BarrTable T, const IO *__restrict
     }
 }
 
-__device__ __forceinline__ double rcp_nr(double x) { // 1/x to ~1 ulp (MUFU seed + third-order step)
-    double r;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-    const double e = fma(-x, r, 1.0);
-    return fma(r * e, 1.0 + e, r);
-}
-__device__ __forceinline__ void ratio_scale_fast(double scale, double in1, double in2, double &o0, double &o1) {
-    if (in1 == 0. && in2 == 0.) { o0 = 0.; o1 = 0.; return; }
-    const double sr = scale * (in1 * rcp_nr(in2));
-    const double nw = (in1 + in2) * rcp_nr(1. + sr);
-    o0 = sr * nw;
-    o1 = nw;
-}
-
 template <typename IO>
 __device__ __forceinline__ void flux_barr_apply_range(const BarrTable &T, const double *__restrict__ terms,
                                                       const IO *__restrict__ nu_nom, const IO *__restrict__ nubar_nom,
                                                       int nubar, int64_t n, IO *__restrict__ out, int64_t first,
                                                       int64_t stride) {
+    const BarrSys S = {T.nue_numu_ratio, T.nu_nubar_ratio, T.delta_index, T.uphor, T.nubar_sys};
     for (int64_t i = first; i < n; i += stride) {
-        const double2 ta = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i);
-        const double2 tb = __ldg(reinterpret_cast<const double2 *>(terms) + 2 * i + 1);
-        struct { double x, y, z, w; } t = {ta.x, ta.y, tb.x, tb.y};
-        const double nu0 = (double)__ldg(nu_nom + 2 * i), nu1 = (double)__ldg(nu_nom + 2 * i + 1);
-        const double nb0 = (double)__ldg(nubar_nom + 2 * i), nb1 = (double)__ldg(nubar_nom + 2 * i + 1);
-        double a0, a1, b0, b1, e_nu, e_nb, m_nu, m_nb;
-        ratio_scale_fast(T.nue_numu_ratio, nu0, nu1, a0, a1);
-        ratio_scale_fast(T.nue_numu_ratio, nb0, nb1, b0, b1);
-        ratio_scale_fast(T.nu_nubar_ratio, a0, b0, e_nu, e_nb);
-        ratio_scale_fast(T.nu_nubar_ratio, a1, b1, m_nu, m_nb);
-        double o0 = nubar < 0 ? e_nb : e_nu, o1 = nubar < 0 ? m_nb : m_nu;
-        const double h0 = 0.5 * T.nubar_sys * t.y, h1 = 0.5 * T.nubar_sys * t.z;
-        const double f0 = nubar < 0 ? rcp_nr(1. + h0) : 1. + h0, f1 = nubar < 0 ? rcp_nr(1. + h1) : 1. + h1;
-        o0 *= fmax(0., f0);
-        o1 *= fmax(0., f1);
-        o0 *= fma(-0.3 * T.uphor, t.w, 1.0);
-        const double idx_scale = exp(T.delta_index * t.x);
-        out[2 * i] = (IO)(o0 * idx_scale);
-        out[2 * i + 1] = (IO)(o1 * idx_scale);
+        double o0, o1;
+        barr_apply_event<IO>(S, terms, nu_nom, nubar_nom, nubar, i, o0, o1);
+        out[2 * i] = (IO)o0;
+        out[2 * i + 1] = (IO)o1;
     }
 }
 
@@ -235,6 +208,7 @@ static int flux_apply_impl(const double *d_terms, const IO *d_nu, const IO *d_nu
     if (n < 0 || (n > 0 && (!d_terms || !d_nu || !d_nubar || !d_out))) { set_error("bad event arrays"); return PISAB_ERR_ARG; }
     if (nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
     if ((uintptr_t)d_terms % 32 != 0) { set_error("d_terms must be 32-byte aligned"); return PISAB_ERR_ARG; }
+    if ((uintptr_t)d_nu % (2 * sizeof(IO)) != 0 || (uintptr_t)d_nubar % (2 * sizeof(IO)) != 0) { set_error("nominal flux rows must be aligned to their size"); return PISAB_ERR_ARG; }
     if (n == 0) return PISAB_OK;
     BarrTable T;
     fill_barr_table(T, nue_numu_ratio, nu_nubar_ratio, delta_index, uphor, nubar_sys);
@@ -256,6 +230,7 @@ static int flux_apply_batch_impl(const pisab_flux_item_t *items, int32_t n_items
         if (S.n < 0 || (S.n > 0 && (!S.d_terms || !S.d_nu_flux_nominal || !S.d_nubar_flux_nominal || !S.d_nu_flux))) { set_error("flux batch: container %d: bad event arrays", c); return PISAB_ERR_ARG; }
         if (S.nubar != 1 && S.nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }
         if ((uintptr_t)S.d_terms % 32 != 0) { set_error("d_terms must be 32-byte aligned"); return PISAB_ERR_ARG; }
+        if ((uintptr_t)S.d_nu_flux_nominal % (2 * sizeof(IO)) != 0 || (uintptr_t)S.d_nubar_flux_nominal % (2 * sizeof(IO)) != 0) { set_error("nominal flux rows must be aligned to their size"); return PISAB_ERR_ARG; }
         B.c[c].terms = S.d_terms; B.c[c].nu_nom = S.d_nu_flux_nominal; B.c[c].nubar_nom = S.d_nubar_flux_nominal;
         B.c[c].out = S.d_nu_flux; B.c[c].n = S.n; B.c[c].nubar = S.nubar;
         if (S.n > n_max) n_max = S.n;

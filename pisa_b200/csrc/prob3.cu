@@ -4,6 +4,7 @@
 
 #include <vector>
 
+#include "flux_device.cuh"
 #include "hist_device.cuh"
 #include "prob3_walk.cuh"
 
@@ -242,11 +243,16 @@ struct FusedContainer {
     double scale; // per-container factor folded into the weight (aeff.aeff: livetime * aeff_scale * norms)
     int32_t nubar, flav;
     int32_t flags; // PISAB_CONTAINER_*
+    // PISAB_CONTAINER_FLUX_SYS: flux.barr_simple is evaluated in the kernel from these instead of reading nu_flux
+    const double *flux_terms;
+    const IO *nu_nom, *nubar_nom;
+    const IO *astro; // optional additive per-event term (hist.py:141-145), non-PLAIN instantiations only
 };
 template <typename IO>
 struct FusedBatch {
     int32_t n_containers;
     int32_t n_bins;
+    BarrSys sys; // flux systematics of this template (FLUX instantiations)
     FusedContainer<IO> c[PISAB_MAX_BATCH];
 };
 
@@ -258,7 +264,12 @@ struct FusedBatch {
 // LARGE (n_bins > PISAB_DET_MAX_BINS): no private bins; every weight goes to the exact fixed-point accumulators in
 // global memory (hist_device.cuh), `partials` then points at FixedAcc[container][2][n_bins] and `bounds` at the
 // per-container weight bounds written by fused_bound_kernel.
-template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false>
+// FLUX: containers flagged PISAB_CONTAINER_FLUX_SYS get their nu_flux from flux.barr_simple evaluated in registers
+// (flux_device.cuh).  Its 64 bytes per event (cached terms + two nominal fluxes) do not fit the staging slots -- two
+// blocks per SM already use all of the shared memory -- so they are prefetched into L2 at the top of the event and
+// loaded after the propagation, when the registers are free; an L2 hit per ~16k-cycle event is hidden by the other
+// warps.
+template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false, bool FLUX = false>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
                                                     const FusedBatch<IO> &batch, int ci_begin, int ci_end,
                                                     int rank, int n_ranks, double *__restrict__ partials,
@@ -289,6 +300,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
         const IO *__restrict__ nu_flux = C.nu_flux, *__restrict__ weights_in = C.weights_in;
         const int32_t *__restrict__ index = C.index, *__restrict__ order = C.order;
         const int64_t n = C.n;
+        const bool fold_flux = FLUX && (C.flags & PISAB_CONTAINER_FLUX_SYS);
         FixedAcc *acc = nullptr;
         double sc1 = 1.0, sc2 = 1.0;
         if (LARGE) {
@@ -312,7 +324,13 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
             if (i_cur >= 0) {
                 const int64_t i = i_cur;
                 const double e = (double)s_e[tid], cz = (double)s_cz[tid];
-                cp_async<2 * sizeof(IO)>(&s_flux[tid][0], nu_flux + 2 * i);
+                if (fold_flux) {
+                    prefetch_l2(C.flux_terms + 4 * i);
+                    prefetch_l2(C.nu_nom + 2 * i);
+                    prefetch_l2(C.nubar_nom + 2 * i);
+                } else {
+                    cp_async<2 * sizeof(IO)>(&s_flux[tid][0], nu_flux + 2 * i);
+                }
                 cp_async<sizeof(IO)>(&s_w[tid], weights_in + i);
                 cp_async<4>(&s_bin[tid], index + i);
                 if (i_next >= 0) {
@@ -343,10 +361,19 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 }
                 cp_async_wait_all();
                 // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
-                const double fe = (double)s_flux[tid][0], fm = (double)s_flux[tid][1];
+                double fe, fm;
+                if (fold_flux) {
+                    barr_apply_event<IO>(batch.sys, C.flux_terms, C.nu_nom, C.nubar_nom, nb, i, fe, fm);
+                    fe = (double)(IO)fe; // rounded to the storage type like the nu_flux array it replaces
+                    fm = (double)(IO)fm;
+                } else {
+                    fe = (double)s_flux[tid][0];
+                    fm = (double)s_flux[tid][1];
+                }
                 w = (double)s_w[tid] * (fe * pe + fm * pmu) * C.scale;
                 bin = s_bin[tid];
                 if (!PLAIN) {
+                    if (C.astro) w += (double)__ldg(C.astro + i);
                     if (C.weights_out) C.weights_out[i] = (IO)w;
                     if (C.prob_e) C.prob_e[i] = (IO)pe;
                     if (C.prob_mu) C.prob_mu[i] = (IO)pmu;
@@ -406,7 +433,7 @@ fused_fixed_finish_kernel(const __grid_constant__ FusedBatch<IO> batch, const Fi
     out[v] = fixed_value(acc[v], sc);
 }
 
-template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false>
+template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false, bool FLUX = false>
 __global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials,
@@ -420,7 +447,7 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // never walks more than one container, so a template over analysis-size containers (1e4 events each)
     // costs one or two event latencies instead of one per container.
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, STD, PLAIN, MP, LARGE>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds);
+    fused_template_body<IO, STD, PLAIN, MP, LARGE, FLUX>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds);
 }
 
 // ---- FP32 mode, TWO events per thread (prob3_mp.cuh: the float part of a pair runs in the two lanes of the packed
@@ -441,7 +468,7 @@ static size_t fused_pair_smem_bytes(int n_bins) {
            (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48);
 }
 
-template <bool STD>
+template <bool STD, bool FLUX>
 __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const EarthTable &s_earth,
                                                 const FusedBatch<float> &batch, int ci, int rank, int n_ranks,
                                                 double *__restrict__ partials, double *s_hist) {
@@ -467,6 +494,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     const float2 *__restrict__ weights_in = reinterpret_cast<const float2 *>(C.weights_in);
     const int2 *__restrict__ index = reinterpret_cast<const int2 *>(C.index);
     const int64_t n_pairs = C.n >> 1;
+    const bool fold_flux = FLUX && (C.flags & PISAB_CONTAINER_FLUX_SYS);
     wh.clear();
     auto pair_of = [&](int64_t t) -> int { return t < n_pairs ? (int)t : -1; };
     int p_cur = pair_of(first), p_next = pair_of(first + stride);
@@ -478,7 +506,14 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
         int bin0 = -1, bin1 = -1;
         if (p_cur >= 0) {
             const float2 e2 = s_e[tid], c2 = s_cz[tid];
-            cp_async<16>(&s_flux[tid], nu_flux + p_cur);
+            if (fold_flux) {
+                prefetch_l2(C.flux_terms + 8 * (int64_t)p_cur);
+                prefetch_l2(C.flux_terms + 8 * (int64_t)p_cur + 4);
+                prefetch_l2(C.nu_nom + 4 * (int64_t)p_cur);
+                prefetch_l2(C.nubar_nom + 4 * (int64_t)p_cur);
+            } else {
+                cp_async<16>(&s_flux[tid], nu_flux + p_cur);
+            }
             cp_async<8>(&s_w[tid], weights_in + p_cur);
             cp_async<8>(&s_bin[tid], index + p_cur);
             if (p_next >= 0) {
@@ -498,7 +533,15 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
             propagate_earth_pair<1, 2, STD>(h0, osc, s_earth, cz, inv_e, C.nubar, C.flav, P, mismatch);
             const f2 pe = P.prob_r(0, 0), pmu = P.prob_r(0, 1);
             cp_async_wait_all();
-            const float4 fl = s_flux[tid]; // (flux_e, flux_mu) of event 0, then of event 1
+            float4 fl; // (flux_e, flux_mu) of event 0, then of event 1
+            if (fold_flux) {
+                double a0, a1, b0, b1;
+                barr_apply_event<float>(batch.sys, C.flux_terms, C.nu_nom, C.nubar_nom, C.nubar, 2 * (int64_t)p_cur, a0, a1);
+                barr_apply_event<float>(batch.sys, C.flux_terms, C.nu_nom, C.nubar_nom, C.nubar, 2 * (int64_t)p_cur + 1, b0, b1);
+                fl = make_float4((float)a0, (float)a1, (float)b0, (float)b1);
+            } else {
+                fl = s_flux[tid];
+            }
             const float2 ww = s_w[tid];
             const int2 bb = s_bin[tid];
             // prob3.py:622: weights *= (flux_e * prob_e) + (flux_mu * prob_mu)
@@ -516,7 +559,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
 }
 
-template <bool STD>
+template <bool STD, bool FLUX = false>
 __global__ void __launch_bounds__(kPairBlock, PISAB_PAIR_MIN_BLOCKS)
 reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
@@ -525,7 +568,7 @@ reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_con
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_pair_body<STD>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist);
+    fused_pair_body<STD, FLUX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -576,6 +619,13 @@ static auto fused_kernel(bool mp) {
         if (mp) return reweight_hist_kernel<IO, STD, PLAIN, true, false>;
     }
     return reweight_hist_kernel<IO, STD, PLAIN, false, false>;
+}
+template <typename IO, bool STD>
+static auto fused_kernel_flux(bool mp) { // flux.barr_simple folded in: fit-loop (PLAIN) form, <= PISAB_DET_MAX_BINS bins
+    if constexpr (sizeof(IO) == 4) {
+        if (mp) return reweight_hist_kernel<IO, STD, true, true, false, true>;
+    }
+    return reweight_hist_kernel<IO, STD, true, false, false, true>;
 }
 template <typename IO, bool STD>
 static auto fused_kernel_large(bool mp) { // > PISAB_DET_MAX_BINS: fixed-point accumulators, fit-loop (PLAIN) form only
@@ -738,13 +788,15 @@ template <typename IO>
 static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                     const FusedBatch<IO> &batch, int64_t n_max, double *d_batch_out,
                                     double *d_hist, double *d_hist_w2, void *d_workspace,
-                                    int64_t workspace_bytes, void *stream, const Chi2Epilogue *epi = nullptr) {
+                                    int64_t workspace_bytes, void *stream, const Chi2Epilogue *epi = nullptr,
+                                    bool has_sys = false) {
     const int n_bins = batch.n_bins;
     if (n_bins < 1) { set_error("bad histogram arguments"); return PISAB_ERR_ARG; }
     const bool large = n_bins > PISAB_DET_MAX_BINS;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
-        if (C.n < 0 || (C.n > 0 && (!C.energy || !C.coszen || !C.nu_flux || !C.weights_in || !C.index))) {
+        const bool needs_flux = !(C.flags & PISAB_CONTAINER_FLUX_SYS);
+        if (C.n < 0 || (C.n > 0 && (!C.energy || !C.coszen || (needs_flux && !C.nu_flux) || !C.weights_in || !C.index))) {
             set_error("container %d: bad event arrays", c);
             return PISAB_ERR_ARG;
         }
@@ -775,13 +827,29 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     bool plain = true;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
-        plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu;
+        plain = plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu && !C.astro;
     }
     // FP32 mode with pair-aligned containers: two events per thread (reweight_hist_pair_kernel)
     bool pairs = mp && plain && !large && sizeof(IO) == 4;
     for (int c = 0; c < batch.n_containers && pairs; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
         pairs = (C.flags & PISAB_CONTAINER_PAIR_ALIGNED) && (C.n % 2 == 0) && !C.order;
+    }
+    bool flux = false;
+    for (int c = 0; c < batch.n_containers; ++c) {
+        const FusedContainer<IO> &C = batch.c[c];
+        if (!(C.flags & PISAB_CONTAINER_FLUX_SYS)) continue;
+        flux = true;
+        if (!C.flux_terms || !C.nu_nom || !C.nubar_nom || (uintptr_t)C.flux_terms % 32 != 0 ||
+            (uintptr_t)C.nu_nom % (2 * sizeof(IO)) != 0 || (uintptr_t)C.nubar_nom % (2 * sizeof(IO)) != 0) {
+            set_error("container %d: PISAB_CONTAINER_FLUX_SYS needs d_flux_terms (32-byte aligned) and both nominal fluxes", c);
+            return PISAB_ERR_ARG;
+        }
+    }
+    if (flux && (!plain || large || !has_sys)) {
+        set_error(has_sys ? "flux.barr_simple inside the template kernel: only without per-event outputs / astro_weights and up to %d bins"
+                          : "PISAB_CONTAINER_FLUX_SYS without a pisab_flux_sys_t (up to %d bins)", PISAB_DET_MAX_BINS);
+        return has_sys ? PISAB_ERR_UNSUPPORTED : PISAB_ERR_ARG;
     }
     if (large && (!plain || !d_batch_out)) {
         set_error("more than %d bins: only the batched form without per-event outputs is fused; use propagate_earth + "
@@ -791,8 +859,12 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     auto kernel = large ? (std_matter ? fused_kernel_large<IO, true>(mp) : fused_kernel_large<IO, false>(mp))
                         : std_matter ? (plain ? fused_kernel<IO, true, true>(mp) : fused_kernel<IO, true, false>(mp))
                                      : (plain ? fused_kernel<IO, false, true>(mp) : fused_kernel<IO, false, false>(mp));
+    if (flux) kernel = std_matter ? fused_kernel_flux<IO, true>(mp) : fused_kernel_flux<IO, false>(mp);
     if (pairs) {
-        if constexpr (sizeof(IO) == 4) kernel = std_matter ? reweight_hist_pair_kernel<true> : reweight_hist_pair_kernel<false>;
+        if constexpr (sizeof(IO) == 4) {
+            kernel = flux ? (std_matter ? reweight_hist_pair_kernel<true, true> : reweight_hist_pair_kernel<false, true>)
+                          : (std_matter ? reweight_hist_pair_kernel<true, false> : reweight_hist_pair_kernel<false, false>);
+        }
     }
     const size_t smem = pairs ? fused_pair_smem_bytes(n_bins) : smem_events;
     const int64_t n_units = pairs ? (n_max + 1) / 2 : n_max;   // what a thread iterates over: events or pairs
@@ -900,8 +972,9 @@ static int reweight_hist_impl(const pisab_osc_consts_t *consts, const pisab_eart
 template <typename IO>
 static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                    const pisab_container_t *containers, int32_t n_containers,
-                                   int32_t n_bins, double *d_hist, void *d_workspace,
-                                   int64_t workspace_bytes, void *stream, const Chi2Epilogue *epi = nullptr) {
+                                   int32_t n_bins, const pisab_flux_sys_t *flux_sys, double *d_hist,
+                                   void *d_workspace, int64_t workspace_bytes, void *stream,
+                                   const Chi2Epilogue *epi = nullptr) {
     if (!containers || n_containers < 1 || n_containers > PISAB_MAX_BATCH || !d_hist) {
         set_error("n_containers must be in [1, %d] and the output non-null", PISAB_MAX_BATCH);
         return PISAB_ERR_ARG;
@@ -909,6 +982,9 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
     FusedBatch<IO> batch = {};
     batch.n_containers = n_containers;
     batch.n_bins = n_bins;
+    if (flux_sys)
+        batch.sys = BarrSys{flux_sys->nue_numu_ratio, flux_sys->nu_nubar_ratio, flux_sys->delta_index,
+                            flux_sys->barr_uphor_ratio, flux_sys->barr_nu_nubar_ratio};
     int64_t n_max = 0;
     for (int c = 0; c < n_containers; ++c) {
         const pisab_container_t &S = containers[c];
@@ -918,6 +994,9 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
         C.index = S.d_index; C.order = S.d_order; C.d_nubar = nullptr; C.d_flav = nullptr;
         C.weights_out = (IO *)S.d_weights_out; C.prob_e = nullptr; C.prob_mu = nullptr;
         C.n = S.n; C.scale = S.scale; C.nubar = S.nubar; C.flav = S.flav; C.flags = S.flags;
+        C.flux_terms = S.d_flux_terms; C.nu_nom = (const IO *)S.d_nu_flux_nominal;
+        C.nubar_nom = (const IO *)S.d_nubar_flux_nominal;
+        C.astro = (const IO *)S.d_astro_weights;
         if (S.n > n_max) n_max = S.n;
     }
     if (epi && n_bins > PISAB_DET_MAX_BINS) {
@@ -925,7 +1004,7 @@ static int reweight_hist_batch_abi(const pisab_osc_consts_t *consts, const pisab
         return PISAB_ERR_UNSUPPORTED;
     }
     return reweight_hist_batch_impl<IO>(consts, earth, batch, n_max, d_hist, nullptr, nullptr, d_workspace,
-                                        workspace_bytes, stream, epi);
+                                        workspace_bytes, stream, epi, flux_sys != nullptr);
 }
 
 // ranks (blocks) per (template, container) of a scan: every thread should see >= 8 events of the largest
@@ -959,6 +1038,8 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     for (int c = 0; c < n_containers; ++c) {
         const pisab_container_t &S = containers[c];
         FusedContainer<IO> &C = batch.c[c];
+        if (S.flags & PISAB_CONTAINER_FLUX_SYS) { set_error("scan: PISAB_CONTAINER_FLUX_SYS is not supported; apply the flux systematics first"); return PISAB_ERR_UNSUPPORTED; }
+        if (S.d_astro_weights) { set_error("scan: astro_weights are not supported"); return PISAB_ERR_UNSUPPORTED; }
         if (S.n < 0 || S.n > 2147483647LL || (S.n > 0 && (!S.d_energy || !S.d_coszen || !S.d_nu_flux || !S.d_weights || !S.d_index))) {
             set_error("container %d: bad event arrays", c);
             return PISAB_ERR_ARG;
@@ -1068,33 +1149,33 @@ int pisab_reweight_hist_f32(const pisab_osc_consts_t *consts, const pisab_earth_
 
 int pisab_reweight_hist_batch_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                   const pisab_container_t *containers, int32_t n_containers,
-                                  int32_t n_bins, double *d_hist, void *d_workspace,
-                                  int64_t workspace_bytes, void *stream) {
-    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                  int32_t n_bins, const pisab_flux_sys_t *flux_sys, double *d_hist,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream) {
+    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, flux_sys, d_hist, d_workspace,
                                            workspace_bytes, stream);
 }
 int pisab_reweight_hist_batch_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                   const pisab_container_t *containers, int32_t n_containers,
-                                  int32_t n_bins, double *d_hist, void *d_workspace,
-                                  int64_t workspace_bytes, void *stream) {
-    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+                                  int32_t n_bins, const pisab_flux_sys_t *flux_sys, double *d_hist,
+                                  void *d_workspace, int64_t workspace_bytes, void *stream) {
+    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, flux_sys, d_hist, d_workspace,
                                           workspace_bytes, stream);
 }
 
 int pisab_reweight_hist_chi2_f64(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                  const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
-                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 const pisab_flux_sys_t *flux_sys, const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
                                  double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream) {
     const Chi2Epilogue epi{d_bin_scales, d_observed, d_total, d_chi2};
-    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+    return reweight_hist_batch_abi<double>(consts, earth, containers, n_containers, n_bins, flux_sys, d_hist, d_workspace,
                                            workspace_bytes, stream, &epi);
 }
 int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_earth_t *earth,
                                  const pisab_container_t *containers, int32_t n_containers, int32_t n_bins,
-                                 const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                                 const pisab_flux_sys_t *flux_sys, const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
                                  double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream) {
     const Chi2Epilogue epi{d_bin_scales, d_observed, d_total, d_chi2};
-    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, d_hist, d_workspace,
+    return reweight_hist_batch_abi<float>(consts, earth, containers, n_containers, n_bins, flux_sys, d_hist, d_workspace,
                                           workspace_bytes, stream, &epi);
 }
 

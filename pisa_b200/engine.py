@@ -52,17 +52,23 @@ class ReweightEngine:
 
     # ------------------------------------------------------------------ containers -------
     def add_container(self, name, nubar, flav, true_energy, true_coszen, nu_flux, weights, index,
-                      nu_flux_nominal=None, nubar_flux_nominal=None):
+                      nu_flux_nominal=None, nubar_flux_nominal=None, astro_weights=None):
         """Register one container.  Tensors may live on the device (resident mode) or be pinned
         host tensors / numpy arrays (host mode, see evaluate_host).  With the nominal fluxes given (device
-        tensors [n, 2]) the Barr flux systematics can float in the fit loop: ``set_flux_params`` then rewrites
-        ``nu_flux`` from them (flux.barr_simple, one HBM-bound pass per template)."""
+        tensors [n, 2]) the Barr flux systematics can float in the fit loop (``set_flux_params``: flux.barr_simple
+        evaluated inside the template kernel, or ``nu_flux`` rewritten from them in one HBM-bound pass).
+        ``astro_weights`` (device tensor [n]): the additive per-event term of utils.hist (hist.py:141-145),
+        ``w = weights * (flux . prob) * scale + astro_weights``."""
         arrays = dict(true_energy=true_energy, true_coszen=true_coszen, nu_flux=nu_flux, weights=weights,
                       index=index)
         if (nu_flux_nominal is None) != (nubar_flux_nominal is None):
             raise ValueError("nu_flux_nominal and nubar_flux_nominal go together")
         if nu_flux_nominal is not None:
             arrays.update(nu_flux_nominal=nu_flux_nominal, nubar_flux_nominal=nubar_flux_nominal)
+        if astro_weights is not None:
+            if not torch.as_tensor(astro_weights).is_cuda:
+                raise NotImplementedError("astro_weights: resident mode only")
+            arrays.update(astro_weights=astro_weights)
         n = int(arrays["true_energy"].shape[0])
         blk = _Block(name, nubar, flav, n)
         for k, a in arrays.items():
@@ -93,8 +99,8 @@ class ReweightEngine:
 
             def rearranged(t, key, idx, pad):
                 out = t[idx].contiguous()
-                if pad is not None and key in ("weights", "index"):
-                    out[pad] = 0 if key == "weights" else -1
+                if pad is not None and key in ("weights", "index", "astro_weights"):
+                    out[pad] = -1 if key == "index" else 0
                 return out
             for k in list(blk.dev):
                 blk.dev[k] = rearranged(blk.dev[k], k, order, dummy)
@@ -114,6 +120,7 @@ class ReweightEngine:
         self.blocks.append(blk)
         self._out = None
         self._batches = None
+        self._batches_fold = None
         self._flux_batches = None
         return blk
 
@@ -128,21 +135,42 @@ class ReweightEngine:
 
     # ------------------------------------------------------------------- evaluation ------
     def set_flux_params(self, nue_numu_ratio=1.0, nu_nubar_ratio=1.0, delta_index=0.0, Barr_uphor_ratio=0.0,
-                        Barr_nu_nubar_ratio=0.0):
-        """flux.barr_simple for every container registered with nominal fluxes: rewrites ``nu_flux`` in place
-        (``pisab_flux_barr_apply``, 80 B/event at ~90 % of the HBM roofline)."""
+                        Barr_nu_nubar_ratio=0.0, materialize=None):
+        """flux.barr_simple for every container registered with nominal fluxes.  ``materialize=False``: nothing is
+        launched; the five parameters ride along with the next ``evaluate`` / ``evaluate_chi2``, whose template kernel
+        evaluates the systematics per event in registers (PISAB_CONTAINER_FLUX_SYS) -- ``nu_flux`` is neither written
+        nor read.  ``materialize=True`` (and every path that needs the array: ``evaluate_many``, ``astro_weights``,
+        more than ``DET_MAX_BINS`` bins) rewrites ``nu_flux`` in place instead (``pisab_flux_barr_apply_batch``, one
+        launch for all containers, 80 B/event at ~90 % of the HBM roofline).  Both forms give the same bits.
+        Default (None): inside the kernel for float64 (FP64-bound kernel: 11.93 instead of 12.30 ms per 1e8 events)
+        and for samples below 1e6 events (one launch less per template); as a separate pass for large float32 samples,
+        whose issue-bound kernel pays more for the FP64 flux arithmetic than the HBM-bound pass costs (8.33 vs
+        8.26 ms; scratch/bench_flux_fold.py)."""
+        for blk in self.blocks:
+            if "flux_barr_terms" not in blk.dev:
+                raise ValueError("container %s was registered without nominal fluxes" % blk.name)
+        self._flux_sys = ops.flux_sys(nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio, Barr_nu_nubar_ratio)
+        self._flux_stale = True
+        if materialize is None:
+            materialize = self.tdtype == torch.float32 and self.n_events >= 1_000_000
+        if materialize or self.n_bins > _lib.DET_MAX_BINS:
+            self._materialize_flux()
+
+    def _materialize_flux(self):
+        """Write ``nu_flux`` for the current flux systematics if it is out of date."""
+        if not getattr(self, "_flux_stale", False):
+            return
         if getattr(self, "_flux_batches", None) is None or self._flux_batches[0] != len(self.blocks):
-            for blk in self.blocks:
-                if "flux_barr_terms" not in blk.dev:
-                    raise ValueError("container %s was registered without nominal fluxes" % blk.name)
             chunks = [self.blocks[lo:lo + ops.MAX_BATCH] for lo in range(0, len(self.blocks), ops.MAX_BATCH)]
             self._flux_batches = (len(self.blocks), [ops.FluxBatch([dict(
                 terms=b.dev["flux_barr_terms"], nu_flux_nominal=b.dev["nu_flux_nominal"],
                 nubar_flux_nominal=b.dev["nubar_flux_nominal"], nu_flux=b.dev["nu_flux"], nubar=b.nubar) for b in ch])
                 for ch in chunks])
+        y = self._flux_sys
         for fb in self._flux_batches[1]:      # ONE launch for all containers of a template
-            ops.flux_barr_apply_batch(fb, nue_numu_ratio, nu_nubar_ratio, delta_index, Barr_uphor_ratio,
-                                      Barr_nu_nubar_ratio)
+            ops.flux_barr_apply_batch(fb, y.nue_numu_ratio, y.nu_nubar_ratio, y.delta_index, y.barr_uphor_ratio,
+                                      y.barr_nu_nubar_ratio)
+        self._flux_stale = False
 
     def set_scales(self, scales):
         """Per-container factor folded into the weights (aeff.aeff: livetime * aeff_scale * norms)."""
@@ -150,19 +178,38 @@ class ReweightEngine:
         if len(self.scales) != len(self.blocks):
             raise ValueError("one scale per container")
         self._batches = None
+        self._batches_fold = None
         self._host_batches = {}
 
-    def _get_batches(self):
-        if self._batches is None:
+    def _get_batches(self, fold_flux=False):
+        """Descriptor arrays of the template launches; ``fold_flux``: the variant whose containers carry the cached
+        flux terms and nominal fluxes instead of ``nu_flux`` (PISAB_CONTAINER_FLUX_SYS)."""
+        key = "_batches_fold" if fold_flux else "_batches"
+        if getattr(self, key, None) is None:
             scales = getattr(self, "scales", None) or [1.0] * len(self.blocks)
-            self._batches = []
+            batches = []
             for lo in range(0, len(self.blocks), ops.MAX_BATCH):
                 chunk = self.blocks[lo:lo + ops.MAX_BATCH]
                 desc = [dict(nubar=b.nubar, flav=b.flav, energy=b.dev["true_energy"], coszen=b.dev["true_coszen"],
                              nu_flux=b.dev["nu_flux"], weights=b.dev["weights"], index=b.dev["index"],
-                             scale=scales[lo + j], flags=b.flags) for j, b in enumerate(chunk)]
-                self._batches.append((lo, ops.TemplateBatch(desc, self.n_bins)))
-        return self._batches
+                             scale=scales[lo + j], flags=b.flags, astro_weights=b.dev.get("astro_weights"))
+                        for j, b in enumerate(chunk)]
+                if fold_flux:
+                    for d, b in zip(desc, chunk):
+                        d.update(flags=b.flags | _lib.CONTAINER_FLUX_SYS, flux_terms=b.dev["flux_barr_terms"],
+                                 nu_flux_nominal=b.dev["nu_flux_nominal"], nubar_flux_nominal=b.dev["nubar_flux_nominal"])
+                batches.append((lo, ops.TemplateBatch(desc, self.n_bins)))
+            setattr(self, key, batches)
+        return getattr(self, key)
+
+    def _flux_fold(self):
+        """(batches, flux_sys) of the next template launch: the folded form while ``nu_flux`` is out of date."""
+        if getattr(self, "_flux_stale", False):
+            if any("astro_weights" in b.dev for b in self.blocks):   # not a fit-loop (PLAIN) launch: write the array
+                self._materialize_flux()
+                return self._get_batches(), None
+            return self._get_batches(fold_flux=True), self._flux_sys
+        return self._get_batches(), None
 
     def evaluate(self, consts, allreduce=None, events=None):
         """Resident mode: all event arrays already in HBM.  ONE fused launch for all containers
@@ -173,11 +220,12 @@ class ReweightEngine:
         out = self._result_buffer()
         # (binnings beyond _lib.DET_MAX_BINS take the same launch: the library switches to exact fixed-point
         # accumulators in global memory, bit-reproducible as well)
-        for lo, batch in self._get_batches():
+        batches, sys = self._flux_fold()
+        for lo, batch in batches:
             if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            ops.reweight_hist_batch(consts, self.earth, batch, out=out[lo:lo + batch.n])
+            ops.reweight_hist_batch(consts, self.earth, batch, out=out[lo:lo + batch.n], flux_sys=sys)
             if events is not None:
                 e1.record()
                 events.append((e0, e1))
@@ -190,13 +238,13 @@ class ReweightEngine:
         nothing synchronising.  On one rank this is ONE library call and two launches (``pisab_reweight_hist_chi2``:
         template kernel, then reduce + per-bin ``bin_scales`` + container sum + chi2 in one kernel); with events sharded
         over GPUs the exchange sits between the reduction and the chi2 (three launches).  Returns (hist, chi2)."""
-        batches = self._get_batches()
+        batches, sys = self._flux_fold()
         out = self._result_buffer()
         if chi2_out is None:
             chi2_out = torch.empty(1, dtype=torch.float64, device=self.device)
         if len(batches) == 1 and not self._want_exchange(allreduce) and self.n_bins <= _lib.DET_MAX_BINS:
             ops.reweight_hist_chi2(consts, self.earth, batches[0][1], observed, out=out, chi2=chi2_out,
-                                   bin_scales=bin_scales)
+                                   bin_scales=bin_scales, flux_sys=sys)
             return out, chi2_out
         out = self.evaluate(consts, allreduce=allreduce)
         if bin_scales is not None:
@@ -209,6 +257,7 @@ class ReweightEngine:
     def evaluate_many(self, consts_list, allreduce=None):
         """P hypotheses in ONE launch (``pisab_reweight_hist_scan``): returns ``[P, n_containers, 2, n_bins]``.
         The single histogram exchange covers all P templates when sharded over GPUs."""
+        self._materialize_flux()
         batches = self._get_batches()
         if len(batches) != 1:
             raise NotImplementedError("evaluate_many supports up to %d containers" % ops.MAX_BATCH)

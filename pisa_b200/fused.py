@@ -16,8 +16,11 @@ stages before and after.  ``utils.hist``'s options (hist.py:141-145,198-209) map
   * ``apply_unc_weights``: hist = sum(unc w), sumw2 = sum((unc w)^2) come from one launch over the weights ``unc * w0``;
     ``bin_unc2 = sum(unc^2 w)`` is the "sum w" plane of a second launch over ``unc^2 * w0`` (only with sumw2 errors);
   * ``unweighted``: the weights are ones, nothing has to be propagated: one pass of the histogram kernel per container;
-  * ``astro_weights`` (an additive per-event term no stage of this package produces): not fused --
-    ``NotImplementedError``, ``DistributionMaker`` then evaluates the pipeline stage by stage.
+  * ``astro_weights`` (an additive per-event term, hist.py:141-145): handed to the kernel, which adds it to the
+    reweighted event weight before histogramming (times ``unc_weights`` / ``unc_weights^2`` like the weights).
+A ``flux.barr_simple`` stage directly in front of ``osc.prob3`` is fused as well: the engine keeps the nominal fluxes and
+the cached event terms, and a change of the five flux systematics costs no launch of its own -- the template kernel
+evaluates them per event in registers (``PISAB_CONTAINER_FLUX_SYS``), ``nu_flux`` is not rewritten.
 """
 import numpy as np
 import torch
@@ -42,6 +45,7 @@ class FusedPipeline:
             raise NotImplementedError("FusedPipeline needs exactly one osc.prob3 stage")
         k = osc[0]
         self.pre, self.osc = stages[:k], stages[k]
+        self.barr = self.pre.pop() if self.pre and _is(self.pre[-1], "flux", "barr_simple") else None
         rest = stages[k + 1:]
         self.aeff = rest.pop(0) if rest and _is(rest[0], "aeff", "aeff") else None
         if not rest or not _is(rest[0], "utils", "hist"):
@@ -59,6 +63,7 @@ class FusedPipeline:
         self._engine = None
         self._engine_unc2 = None             # second engine (weights unc^2 * w0) for bin_unc2 with unc_weights
         self._pre_hash = None
+        self._barr_hash = None
         self._scales = None
 
     # ------------------------------------------------------------------------------------------------
@@ -69,13 +74,14 @@ class FusedPipeline:
         data = self.pipeline.data
         for stage in self.pre:               # loaders reset `weights`, flux stages write `nu_flux`
             stage.run()
+        if self.barr is not None:
+            self.barr.run()                  # the containers' own nu_flux stays valid for this hypothesis
         engine = engine2 = None
         want_unc2 = self.hist.apply_unc_weights and self.hist.error_method == "sumw2"
         self._containers = list(data.containers)
         for c in self._containers:
             c.representation = "events"
-            if "astro_weights" in c.keys:
-                raise NotImplementedError("FusedPipeline: astro_weights are not supported")
+            astro = c["astro_weights"] if "astro_weights" in c.keys else None
             w = c["weights"]
             if self.aeff is not None:
                 w = w * c["weighted_aeff"]   # the per-event part of aeff.aeff; its scalar part goes in as `scale`
@@ -86,11 +92,20 @@ class FusedPipeline:
             idx = c.bin_index(self.binning, "hist")
             unc = c["unc_weights"] if self.hist.apply_unc_weights else None
             args = (c.name, int(c["nubar"]), int(c["flav"]), c["true_energy"], c["true_coszen"], c["nu_flux"])
-            engine.add_container(*args, (w if unc is None else unc * w).contiguous(), idx)
+            kw = {}
+            if self.barr is not None:
+                kw.update(nu_flux_nominal=c["nu_flux_nominal"], nubar_flux_nominal=c["nubar_flux_nominal"])
+
+            def term(x, power):              # x * unc^power (x: the weights or the additive astro term)
+                if x is None:
+                    return None
+                return (x if unc is None else x * unc ** power).contiguous()
+            engine.add_container(*args, term(w, 1), idx, astro_weights=term(astro, 1), **kw)
             if want_unc2:
-                engine2.add_container(*args, (unc * unc * w).contiguous(), idx)
+                engine2.add_container(*args, term(w, 2), idx, astro_weights=term(astro, 2), **kw)
         self._engine, self._engine_unc2 = engine, engine2
         self._pre_hash = self._inputs_hash()
+        self._barr_hash = None
 
     def _evaluate_unweighted(self):
         """``unweighted`` (hist.py:141-145): weights of one -- times ``unc_weights`` if asked for -- so the oscillation
@@ -121,6 +136,14 @@ class FusedPipeline:
             self._build_engine(earth)
             self._scales = None
         self._engine.earth = earth
+        if self.barr is not None and self.barr.params.values_hash != self._barr_hash:
+            p = self.barr.params
+            sys = {k: p[k].value.m_as("dimensionless") for k in ("nue_numu_ratio", "nu_nubar_ratio", "delta_index",
+                                                                 "Barr_uphor_ratio", "Barr_nu_nubar_ratio")}
+            for eng in (self._engine, self._engine_unc2):
+                if eng is not None:
+                    eng.set_flux_params(**sys)       # no launch: evaluated inside the next template kernel
+            self._barr_hash = self.barr.params.values_hash
         if self.aeff is not None:
             scales = [self.aeff.container_scale(c.name) for c in self._containers]
             if scales != self._scales:

@@ -558,7 +558,9 @@ class TemplateBatch:
 
     def __init__(self, containers, n_bins):
         """containers: list of dicts with nubar, flav, energy, coszen, nu_flux, weights, index and optional
-        order, weights_out, scale."""
+        order, weights_out, astro_weights (additive per-event term, hist.py:141-145), scale, flags; with ``flux_terms``, ``nu_flux_nominal`` and ``nubar_flux_nominal`` given
+        (and ``flags | _lib.CONTAINER_FLUX_SYS``) the kernel evaluates flux.barr_simple itself and never reads
+        ``nu_flux`` (which may then be None)."""
         if not 1 <= len(containers) <= MAX_BATCH:
             raise ValueError("a batch holds 1..%d containers" % MAX_BATCH)
         self.n_bins = int(n_bins)
@@ -570,23 +572,40 @@ class TemplateBatch:
             e = _chk(c["energy"], "energy")
             dt = dt or e.dtype
             n = e.numel()
-            for nm in ("coszen", "nu_flux", "weights"):
+            flags = int(c.get("flags", 0))
+            fold = bool(flags & _lib.CONTAINER_FLUX_SYS)
+            for nm in ("coszen", "weights"):
                 _chk(c[nm], nm, dt)
+            _chk(c.get("nu_flux"), "nu_flux", dt, allow_none=fold)
             _chk(c["index"], "index", torch.int32)
-            if c["nu_flux"].shape != (n, 2) or c["coszen"].numel() != n or c["weights"].numel() != n \
-                    or c["index"].numel() != n:
+            if (c.get("nu_flux") is not None and c["nu_flux"].shape != (n, 2)) or c["coszen"].numel() != n \
+                    or c["weights"].numel() != n or c["index"].numel() != n:
                 raise ValueError("inconsistent event array shapes")
-            order, wout = c.get("order"), c.get("weights_out")
+            terms, nom, nom_bar = c.get("flux_terms"), c.get("nu_flux_nominal"), c.get("nubar_flux_nominal")
+            if fold:
+                _chk(terms, "flux_terms", torch.float64)
+                _chk(nom, "nu_flux_nominal", dt)
+                _chk(nom_bar, "nubar_flux_nominal", dt)
+                if terms.shape != (n, 4) or nom.shape != (n, 2) or nom_bar.shape != (n, 2):
+                    raise ValueError("flux_terms must be [n, 4], the nominal fluxes [n, 2]")
+            order, wout, astro = c.get("order"), c.get("weights_out"), c.get("astro_weights")
             _check_order(order, n)
             _chk(wout, "weights_out", dt, allow_none=True)
+            _chk(astro, "astro_weights", dt, allow_none=True)
+            if astro is not None and astro.numel() != n:
+                raise ValueError("inconsistent event array shapes")
             d.d_energy, d.d_coszen = e.data_ptr(), c["coszen"].data_ptr()
-            d.d_nu_flux, d.d_weights = c["nu_flux"].data_ptr(), c["weights"].data_ptr()
+            d.d_nu_flux = 0 if c.get("nu_flux") is None else c["nu_flux"].data_ptr()
+            d.d_weights = c["weights"].data_ptr()
             d.d_index = c["index"].data_ptr()
+            if fold:
+                d.d_flux_terms, d.d_nu_flux_nominal, d.d_nubar_flux_nominal = terms.data_ptr(), nom.data_ptr(), nom_bar.data_ptr()
             d.d_order = 0 if order is None else order.data_ptr()
             d.d_weights_out = 0 if wout is None else wout.data_ptr()
+            d.d_astro_weights = 0 if astro is None else astro.data_ptr()
             d.n, d.scale, d.nubar, d.flav = n, float(c.get("scale", 1.0)), int(c["nubar"]), int(c["flav"])
-            d.flags = int(c.get("flags", 0))
-            self._keep.append((e, c["coszen"], c["nu_flux"], c["weights"], c["index"], order, wout))
+            d.flags = flags
+            self._keep.append((e, c["coszen"], c.get("nu_flux"), c["weights"], c["index"], order, wout, terms, nom, nom_bar, astro))
         self.dtype = dt
         self.device = containers[0]["energy"].device
 
@@ -594,8 +613,19 @@ class TemplateBatch:
         self.desc[i].scale = float(scale)
 
 
-def reweight_hist_batch(consts, earth, batch, out=None):
-    """All containers of ``batch`` in one launch; returns ``[n_containers, 2, n_bins]`` (sum w, sum w^2)."""
+def flux_sys(nue_numu_ratio=1.0, nu_nubar_ratio=1.0, delta_index=0.0, Barr_uphor_ratio=0.0, Barr_nu_nubar_ratio=0.0):
+    """pisab_flux_sys_t from the parameter names of flux.barr_simple (barr_simple.py:41-52)."""
+    return _lib.FluxSys(float(nue_numu_ratio), float(nu_nubar_ratio), float(delta_index), float(Barr_uphor_ratio),
+                        float(Barr_nu_nubar_ratio))
+
+
+def _sys_ref(sys):
+    return None if sys is None else ctypes.byref(sys)
+
+
+def reweight_hist_batch(consts, earth, batch, out=None, flux_sys=None):
+    """All containers of ``batch`` in one launch; returns ``[n_containers, 2, n_bins]`` (sum w, sum w^2).
+    ``flux_sys`` (see ``flux_sys()``): the systematics for containers flagged CONTAINER_FLUX_SYS."""
     if out is None:
         out = torch.empty((batch.n, 2, batch.n_bins), dtype=torch.float64, device=batch.device)
     _chk(out, "out", torch.float64)
@@ -603,12 +633,13 @@ def reweight_hist_batch(consts, earth, batch, out=None):
         raise ValueError("out must hold [n_containers, 2, n_bins] doubles")
     ws = _workspace(batch.device, 0, batch.n_bins, batch.n)
     f = _lib.fn("pisab_reweight_hist_batch", batch.dtype)
-    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(out), _ptr(ws),
-                 ws.numel(), _stream()))
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _sys_ref(flux_sys),
+                 _ptr(out), _ptr(ws), ws.numel(), _stream()))
     return out
 
 
-def reweight_hist_chi2(consts, earth, batch, observed, out=None, chi2=None, total=None, bin_scales=None):
+def reweight_hist_chi2(consts, earth, batch, observed, out=None, chi2=None, total=None, bin_scales=None,
+                       flux_sys=None):
     """One hypothesis of a fit in one call: all containers of ``batch`` in one launch, then ONE kernel that reduces
     the partial histograms, applies optional per-bin scales (``bin_scales`` [n_containers, n_bins], the
     discr_sys.hypersurfaces factors), sums the containers and evaluates ``mod_chi2`` against ``observed`` [n_bins]
@@ -630,8 +661,8 @@ def reweight_hist_chi2(consts, earth, batch, observed, out=None, chi2=None, tota
         raise ValueError("bin_scales must be [n_containers, n_bins]")
     ws = _workspace(batch.device, 0, batch.n_bins, batch.n)
     f = _lib.fn("pisab_reweight_hist_chi2", batch.dtype)
-    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _ptr(bin_scales),
-                 _ptr(observed), _ptr(out), _ptr(total), _ptr(chi2), _ptr(ws), ws.numel(), _stream()))
+    _lib.check(f(ctypes.byref(consts), ctypes.byref(earth), batch.desc, batch.n, batch.n_bins, _sys_ref(flux_sys),
+                 _ptr(bin_scales), _ptr(observed), _ptr(out), _ptr(total), _ptr(chi2), _ptr(ws), ws.numel(), _stream()))
     return out, chi2
 
 

@@ -29,7 +29,7 @@ for row in rows[2:]:
         except ValueError: pass
 we = n_ev / 32
 flop64 = (2 * thr["DFMA"] + thr["DMUL"] + thr["DADD"]) / n_ev
-flop32 = (2 * thr["FFMA"] + thr["FMUL"] + thr["FADD"]) / n_ev
+flop32 = (2 * thr["FFMA"] + thr["FMUL"] + thr["FADD"] + 4 * thr["FFMA2"] + 2 * thr["FMUL2"] + 2 * thr["FADD2"]) / n_ev
 L = []
 L.append("# %s: `%s`\n" % (name, val("Kernel Name").split("(")[0]))
 L.append(desc + "\n")
@@ -45,7 +45,7 @@ for k in ("gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "
 L.append("| DRAM bytes / event | %.1f |" % (dram / n_ev))
 L.append("| warp instructions / warp-event | %.0f |" % (tot / we))
 L.append("| executed FP64 FLOP / event (2 DFMA + DMUL + DADD) | %.0f |" % flop64)
-L.append("| executed FP32 FLOP / event (2 FFMA + FMUL + FADD) | %.0f |" % flop32)
+L.append("| executed FP32 FLOP / event (2 FFMA + FMUL + FADD, packed x2) | %.0f |" % flop32)
 L.append("\nSASS mix (warp instructions per warp-event):\n\n```")
 for op, n in ops.most_common(26): L.append("%-10s %8.1f %6.2f%%" % (op, n / we, 100.0 * n / tot))
 ts = sum(stalls.values()) or 1

@@ -196,6 +196,52 @@ def test_fused_pipeline_with_hist_options(tmp_path, hist_extra, loader_extra):
                 assert float(cs["weights"].sum()) == cs["weights"].sum().round().item()   # plain counts
 
 
+def test_fused_pipeline_floating_flux_systematics_and_astro_weights():
+    """flux.barr_simple in front of osc.prob3: FusedPipeline evaluates the five flux systematics inside the template
+    kernel (no engine rebuild, nu_flux not rewritten) and matches the staged pipeline; an additive ``astro_weights``
+    term (hist.py:141-145) on the containers goes through the kernel as well."""
+    _need_gpu()
+    from pisa_b200.core.pipeline import Pipeline
+    from pisa_b200.fused import FusedPipeline
+    from pisa_b200.utils.units import ureg
+    cfg = "settings/pipeline/b200_flux_events.cfg"
+    staged, fused = Pipeline(cfg), FusedPipeline(Pipeline(cfg))
+    assert fused.barr is not None and all(s.service_name != "barr_simple" for s in fused.pre)
+
+    def compare(tag):
+        staged.run()
+        fused.run()
+        for cs, cf in zip(staged.data.containers, fused.pipeline.data.containers):
+            cs.representation = cf.representation = staged.output_binning
+            for key in ("weights", "errors"):
+                a, b = cs[key].cpu().numpy(), cf[key].cpu().numpy()
+                assert np.allclose(b, a, rtol=1e-10, atol=0), (tag, cs.name, key)
+        return np.stack([c["weights"].cpu().numpy() for c in fused.pipeline.data.containers])
+
+    first = compare("nominal")
+    engine = fused._engine
+    for p in (staged, fused.pipeline):
+        p.params.delta_index = 0.08
+        p.params.Barr_uphor_ratio = -0.7
+        p.params.nu_nubar_ratio = 1.06
+        p.params.theta23 = 47.0 * ureg.deg
+    second = compare("flux systematics moved")
+    assert fused._engine is engine and engine._flux_stale     # no rebuild, nu_flux not rewritten
+    assert not np.allclose(first, second, rtol=1e-4)
+    # additive astrophysical term: both pipelines get the same per-event array
+    for p in (staged, fused.pipeline):
+        for c in p.data.containers:
+            c.representation = "events"
+            g = torch.Generator(device="cpu").manual_seed(len(c.name))
+            c["astro_weights"] = (torch.rand(c.size, generator=g, dtype=torch.float64) * 1e-3).to(c["weights"])
+    fused._engine = None                                       # event arrays changed: new engine
+    third = compare("astro_weights")
+    assert (third.sum(axis=1) > second.sum(axis=1)).all()
+    for p in (staged, fused.pipeline):
+        p.params.Barr_nu_nubar_ratio = 0.9
+    compare("astro_weights + flux systematics")
+
+
 def test_one_call_template_chi2_with_bin_scales():
     """pisab_reweight_hist_chi2: template kernel + ONE epilogue kernel (reduce, per-bin hypersurface scales, container
     sum, mod_chi2 in the last-arriving block) against the separate launches; repeated calls reuse the arrival counter."""

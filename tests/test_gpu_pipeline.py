@@ -546,8 +546,13 @@ def test_engine_with_floating_flux_systematics():
                           nu_flux_nominal=t["nu_flux"], nubar_flux_nominal=torch.tensor(nom_nb, device=dev))
         host.append((nubar, flav, ev, nom_nu, nom_nb, idx.cpu().numpy()))
     pars = dict(nue_numu_ratio=1.04, nu_nubar_ratio=0.93, delta_index=0.07, Barr_uphor_ratio=-0.8, Barr_nu_nubar_ratio=1.5)
-    eng.set_flux_params(**pars)
-    out = eng.evaluate(consts).cpu().numpy()
+    eng.set_flux_params(**pars, materialize=False)                    # folded: the template kernel evaluates barr_simple itself
+    folded = eng.evaluate(consts).clone()
+    assert eng._flux_stale
+    eng.set_flux_params(**pars, materialize=True)     # staged: nu_flux rewritten by pisab_flux_barr_apply_batch
+    assert not eng._flux_stale
+    assert torch.equal(folded, eng.evaluate(consts))  # the same bits either way
+    out = folded.cpu().numpy()
     zc, zf = np.zeros((3, 3), dtype=complex), np.zeros((3, 3))
     for c, (nubar, flav, ev, nom_nu, nom_nb, idx) in enumerate(host):
         flux = orc.flux_barr_simple(ev["true_energy"], ev["true_coszen"], nom_nu, nom_nb, nubar, *pars.values())
@@ -561,6 +566,87 @@ def test_engine_with_floating_flux_systematics():
         plain.add_container("x", 1, 0, ev["true_energy"], ev["true_coszen"], ev["nu_flux"], ev["weights"],
                             torch.zeros(100, dtype=torch.int32, device=dev))
         plain.set_flux_params()
+
+
+@pytest.mark.parametrize("dtype,math,sort", [(np.float64, None, True), (np.float64, None, False),
+                                             (np.float32, "fp64", True), (np.float32, "mixed", True),
+                                             (np.float32, "mixed", False)])
+def test_flux_systematics_folded_vs_staged(dtype, math, sort):
+    """flux.barr_simple inside the template kernel (PISAB_CONTAINER_FLUX_SYS) against the staged form (nu_flux written
+    by pisab_flux_barr_apply_batch, then the template): bit-identical histograms and chi2 in FP64, in FP32 storage with
+    FP64 arithmetic, in the FP32 mode (two events per thread when the containers are pair-aligned, one otherwise)."""
+    _need_gpu()
+    from pisa_b200 import ops
+    from pisa_b200.engine import ReweightEngine
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    dm, mix, mat_pot = syn.osc_matrices()
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    if math is not None:
+        ops.set_f32_math(math)
+    try:
+        eng = ReweightEngine(L.earth_struct(), 128, dtype, dev, sort_events=sort)
+        for i, (name, nubar, flav) in enumerate(syn.CONTAINERS[:12:3]):
+            t = syn.make_events_torch(5000 + 37 * i, 40 + i, dtype, dev)
+            idx = ops.hist_index(binning, [t["reco_energy"], t["reco_coszen"], t["pid"]])
+            eng.add_container(name, nubar, flav, t["true_energy"], t["true_coszen"], t["nu_flux"].clone(), t["weights"],
+                              idx, nu_flux_nominal=t["nu_flux"], nubar_flux_nominal=(t["nu_flux"] * 0.75).contiguous())
+        observed = torch.full((128,), 3.0, dtype=torch.float64, device=dev)
+        for pars in (dict(), dict(nue_numu_ratio=1.04, nu_nubar_ratio=0.93, delta_index=0.07, Barr_uphor_ratio=-0.8,
+                                  Barr_nu_nubar_ratio=1.5)):
+            eng.set_flux_params(**pars, materialize=False)
+            h_fold = eng.evaluate(consts).clone()
+            _, c_fold = eng.evaluate_chi2(consts, observed)
+            c_fold = c_fold.clone()
+            assert eng._flux_stale
+            eng.set_flux_params(**pars, materialize=True)
+            h_staged = eng.evaluate(consts)
+            assert torch.isfinite(h_fold).all() and float(h_fold[:, 0].sum()) > 0
+            assert torch.equal(h_fold, h_staged)
+            _, c_staged = eng.evaluate_chi2(consts, observed)
+            assert torch.equal(c_fold, c_staged)
+        # a scan needs the array: it is written on demand
+        eng.set_flux_params(delta_index=0.05)
+        many = eng.evaluate_many([consts, consts])
+        assert not eng._flux_stale
+        assert torch.equal(many[0], many[1])
+    finally:
+        ops.set_f32_math("mixed")
+
+
+def test_flux_fold_argument_checks():
+    """PISAB_CONTAINER_FLUX_SYS without the systematics struct, above DET_MAX_BINS bins, in a scan: errors, no launch."""
+    _need_gpu()
+    from pisa_b200 import ops, _lib
+    from pisa_b200.stages.osc.layers import Layers
+    from pisa_b200.utils import synthetic as syn
+    dev = torch.device("cuda:0")
+    L = Layers(PREM12, 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    dm, mix, mat_pot = syn.osc_matrices()
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    t = syn.make_events_torch(1000, 3, np.float64, dev)
+    idx = torch.zeros(1000, dtype=torch.int32, device=dev)
+    terms = ops.flux_barr_terms(t["true_energy"], t["true_coszen"])
+    desc = dict(nubar=1, flav=1, energy=t["true_energy"], coszen=t["true_coszen"], nu_flux=None, weights=t["weights"],
+                index=idx, flags=_lib.CONTAINER_FLUX_SYS, flux_terms=terms, nu_flux_nominal=t["nu_flux"],
+                nubar_flux_nominal=t["nu_flux"])
+    batch = ops.TemplateBatch([desc], 4)
+    with pytest.raises(ValueError):
+        ops.reweight_hist_batch(consts, L.earth_struct(), batch)                       # no pisab_flux_sys_t
+    out = ops.reweight_hist_batch(consts, L.earth_struct(), batch, flux_sys=ops.flux_sys())
+    assert float(out[0, 0, 0]) > 0
+    with pytest.raises(NotImplementedError):
+        ops.reweight_hist_scan([consts], L.earth_struct(), batch)
+    big = ops.TemplateBatch([desc], 3200)
+    with pytest.raises(NotImplementedError):
+        ops.reweight_hist_batch(consts, L.earth_struct(), big, flux_sys=ops.flux_sys())
+    with pytest.raises(ValueError):
+        ops.TemplateBatch([dict(desc, flux_terms=None)], 4)
 
 
 def test_fit_chi2_recovers_injected_parameters():
