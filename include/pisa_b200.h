@@ -355,6 +355,14 @@ int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_e
                                  const pisab_flux_sys_t *flux_sys, const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
                                  double *d_chi2, void *d_workspace, int64_t workspace_bytes, void *stream);
 
+/* The epilogue of pisab_reweight_hist_chi2_* as a call of its own: sums n_blocks partial histograms per container
+ * (d_partials [n_containers][n_blocks][2][n_bins], block order), applies the optional per-bin scales of
+ * discr_sys.hypersurfaces (hypersurfaces.py:219-248: weights -> clip(s w, 0), errors -> s errors, i.e. sum w^2 ->
+ * s^2 sum w^2), sums the containers and evaluates mod_chi2; outputs as in pisab_reweight_hist_chi2_*.  One launch. */
+int pisab_hist_scale_sum_chi2(const double *d_partials, int32_t n_blocks, int32_t n_containers, int32_t n_bins,
+                              const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                              double *d_chi2, void *stream);
+
 /* mod_chi2 (pisa/utils/stats.py:651-695) on device for the scan driver:
  * sum_b (obs-exp)^2 / (sigma^2 + max(exp,1e-10)); result is one double on the device. */
 int pisab_mod_chi2(const double *d_expected, const double *d_expected_w2, const double *d_observed,

@@ -144,6 +144,7 @@ _UNTYPED = {
     "pisab_joint_index": (c_i32, [c_vp, c_vp, c_i32, c_i64, c_vp, c_vp]),
     "pisab_mod_chi2": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "pisab_template_chi2": (c_i32, [c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
+    "pisab_hist_scale_sum_chi2": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pisab_template_chi2_batch": (c_i32, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     "pisab_reweight_scan_workspace_bytes": (c_i64, [c_i32, c_i32, c_i32, c_i64]),
     "pisab_fp64_peak_probe": (c_i32, [c_i32, ctypes.POINTER(c_dbl), ctypes.POINTER(c_dbl)]),

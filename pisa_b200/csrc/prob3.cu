@@ -1179,6 +1179,20 @@ int pisab_reweight_hist_chi2_f32(const pisab_osc_consts_t *consts, const pisab_e
                                           workspace_bytes, stream, &epi);
 }
 
+int pisab_hist_scale_sum_chi2(const double *d_partials, int32_t n_blocks, int32_t n_containers, int32_t n_bins,
+                              const double *d_bin_scales, const double *d_observed, double *d_hist, double *d_total,
+                              double *d_chi2, void *stream) {
+    if (!d_partials || !d_hist || n_blocks < 1 || n_containers < 1 || n_containers > PISAB_MAX_BATCH || n_bins < 1 ||
+        n_bins > PISAB_DET_MAX_BINS || (d_observed && !d_chi2)) {
+        set_error("hist_scale_sum_chi2: bad arguments (1..%d containers, 1..%d bins)", PISAB_MAX_BATCH, PISAB_DET_MAX_BINS);
+        return PISAB_ERR_ARG;
+    }
+    unsigned *d_arrive = epilogue_counter();
+    if (!d_arrive) { set_error("could not allocate the epilogue arrival counter"); return PISAB_ERR_CUDA; }
+    return hist_reduce_chi2(d_partials, n_blocks, n_bins, n_containers, d_bin_scales, d_observed, d_hist, d_total, d_chi2,
+                            d_arrive, (cudaStream_t)stream);
+}
+
 int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_containers, int32_t n_bins, int64_t n_max) {
     if (n_templates < 1) n_templates = 1;
     if (n_containers < 1) n_containers = 1;

@@ -736,6 +736,28 @@ def template_chi2(hist, observed, out=None, total=None):
     return out
 
 
+def hist_reduce_chi2(partials, n_blocks, bin_scales=None, observed=None, total=None, chi2=None):
+    """The fit-loop epilogue on its own (``pisab_hist_scale_sum_chi2``): ``partials`` [n_containers, n_blocks, 2, n_bins]
+    (or [n_containers, 2, n_bins] with ``n_blocks`` = 1) summed in block order, per-bin ``bin_scales`` [n_containers,
+    n_bins] applied like discr_sys.hypersurfaces, containers summed into ``total`` [2, n_bins], ``mod_chi2`` against
+    ``observed`` into ``chi2``.  Returns the scaled per-container histograms [n_containers, 2, n_bins]."""
+    _chk(partials, "partials", torch.float64)
+    n_c, n_bins = partials.shape[0], partials.shape[-1]
+    if partials.numel() != n_c * int(n_blocks) * 2 * n_bins:
+        raise ValueError("partials must be [n_containers, n_blocks, 2, n_bins]")
+    for t, name, numel in ((bin_scales, "bin_scales", n_c * n_bins), (observed, "observed", n_bins),
+                           (total, "total", 2 * n_bins), (chi2, "chi2", 1)):
+        _chk(t, name, torch.float64, allow_none=True)
+        if t is not None and t.numel() != numel:
+            raise ValueError("%s has the wrong size" % name)
+    if observed is not None and chi2 is None:
+        chi2 = torch.empty(1, dtype=torch.float64, device=partials.device)
+    out = torch.empty((n_c, 2, n_bins), dtype=torch.float64, device=partials.device)
+    _lib.check(_lib.load().pisab_hist_scale_sum_chi2(_ptr(partials), int(n_blocks), n_c, n_bins, _ptr(bin_scales),
+                                                     _ptr(observed), _ptr(out), _ptr(total), _ptr(chi2), _stream()))
+    return out
+
+
 def fp64_peak_probe(iters=20000):
     """Measured DFMA throughput of the device (FLOP/s): the FP64 roofline denominator."""
     flops, ms = ctypes.c_double(), ctypes.c_double()

@@ -242,6 +242,51 @@ def test_fused_pipeline_floating_flux_systematics_and_astro_weights():
     compare("astro_weights + flux systematics")
 
 
+def test_hypersurface_stage_and_epilogue_vs_reference_golden():
+    """discr_sys.hypersurfaces against the UNMODIFIED reference stage (compute_function + apply_function run on binned
+    containers by tests/golden/make_golden_hypersurfaces.py): weights (clipped at 0), errors, bin_unc2 after the stage,
+    and the same per-bin scales applied by the fit-loop epilogue kernel (pisab_reweight_hist_chi2's ``bin_scales``:
+    sum w -> max(s sum w, 0), sum w^2 -> s^2 sum w^2, i.e. errors -> |s| errors)."""
+    _need_gpu()
+    from pisa_b200 import ops
+    from pisa_b200.core.container import Container, ContainerSet
+    from pisa_b200.core.param import Param, ParamSet
+    from pisa_b200.stages.discr_sys.hypersurfaces import hypersurfaces
+    from pisa_b200.utils.config_parser import parse_pipeline_config
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_hypersurfaces_f8.npz"))
+    names, maps = list(gold["param_names"]), list(gold["map_names"])
+    binning = parse_pipeline_config("settings/pipeline/b200_icecube3y_full.cfg")[("discr_sys", "hypersurfaces")]["calc_mode"]
+    dev = torch.device("cuda:0")
+    for ci, values in enumerate(gold["param_values"]):
+        st = hypersurfaces(fit_results_file="events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2",
+        data = ContainerSet("hs")
+        for m in maps:
+            c = Container(m, representation=binning)
+            for key in ("weights", "errors", "bin_unc2"):
+                c[key] = gold["in_%s_%d_%s" % (key, ci, m)]
+            data.add_container(c)
+        st = hypersurfaces(fit_results_file="events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2",
+                           params=ParamSet([Param(name=n, value=float(v)) for n, v in zip(names, values)]),
+                           data=data, calc_mode=binning, apply_mode=binning, error_method="sumw2")
+        st.setup()
+        st.run()
+        for m, c in zip(maps, data.containers):
+            c.representation = binning
+            for key in ("weights", "errors", "bin_unc2", "hs_scales"):
+                want = gold["out_%s_%d_%s" % (key, ci, m)]
+                got = c[key].cpu().numpy() if isinstance(c[key], torch.Tensor) else np.asarray(c[key])
+                assert np.array_equal(got, want), (ci, m, key)
+        # the fit-loop epilogue with the same scales: feed the input maps as one-block "partials" of 4 containers
+        partial = torch.stack([torch.stack([torch.tensor(gold["in_weights_%d_%s" % (ci, m)], device=dev),
+                                            torch.tensor(gold["in_errors_%d_%s" % (ci, m)], device=dev) ** 2]) for m in maps])
+        scales = torch.tensor(np.stack([gold["out_hs_scales_%d_%s" % (ci, m)] for m in maps]), device=dev)
+        out = ops.hist_reduce_chi2(partial.contiguous(), 1, scales)
+        for k, m in enumerate(maps):
+            assert np.array_equal(out[k, 0].cpu().numpy(), gold["out_weights_%d_%s" % (ci, m)])
+            assert np.allclose(np.sqrt(out[k, 1].cpu().numpy()), np.abs(gold["out_errors_%d_%s" % (ci, m)]),
+                               rtol=4e-16, atol=0)
+
+
 def test_one_call_template_chi2_with_bin_scales():
     """pisab_reweight_hist_chi2: template kernel + ONE epilogue kernel (reduce, per-bin hypersurface scales, container
     sum, mod_chi2 in the last-arriving block) against the separate launches; repeated calls reuse the arrival counter."""

@@ -315,6 +315,29 @@ def test_hyperplane_loader_and_formula():
         load_hypersurfaces_data_release("events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2", other)
 
 
+def test_hyperplanes_vs_reference_golden():
+    """Loader + evaluation against outputs of the UNMODIFIED reference (``_load_hypersurfaces_data_release`` +
+    ``Hypersurface.evaluate`` run by tests/golden/make_golden_hypersurfaces.py): bit-identical scale factors for all
+    four maps and seven parameter points, and the stage's ``hs_scales`` (non-finite -> 1)."""
+    from pisa_b200.stages.discr_sys.hypersurfaces import evaluate_hyperplane, load_hypersurfaces_data_release
+    from pisa_b200.utils.config_parser import parse_pipeline_config
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "ref_hypersurfaces_f8.npz"))
+    cfg = parse_pipeline_config("settings/pipeline/b200_icecube3y_full.cfg")
+    binning = cfg[("discr_sys", "hypersurfaces")]["calc_mode"]
+    hs, names = load_hypersurfaces_data_release("events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2", binning)
+    assert names == list(gold["param_names"]) and list(hs) == list(gold["map_names"])
+    for ci, values in enumerate(gold["param_values"]):
+        vals = dict(zip(names, values))
+        for k, m in enumerate(hs):
+            got = evaluate_hyperplane(hs[m], vals)
+            assert np.array_equal(got, gold["scales_%d" % ci][k]), (ci, m)
+            want = gold["out_hs_scales_%d_%s" % (ci, m)]
+            got = got.reshape(-1).copy()
+            got[~np.isfinite(got)] = 1.0
+            assert np.array_equal(got, want)
+    assert min(gold["scales_%d" % ci].min() for ci in range(len(gold["param_values"]))) < 0   # the clip is exercised
+
+
 def test_mapset_json_interchange(tmp_path):
     """MapSet.to_json / from_json in the reference's layout (map.py:1272-1362,2206-2262; binning.py:676-694,
     1842-1859; jsons.py:196-330): state keys, nested lists, .json and .json.bz2, and a file shaped like real
