@@ -390,6 +390,28 @@ int pisab_reweight_hist_scan_f32(const pisab_osc_consts_t *consts, int32_t n_tem
 int pisab_template_chi2_batch(const double *d_hist, int32_t n_templates, int32_t n_containers, int32_t n_bins,
                               const double *d_observed, double *d_out, void *stream);
 
+/* Any number of bins, static indices: the SORTED plan.  d_perm = stable order of the events by bin index
+ * (pisab_sort_order_i32 of the index with out-of-range entries mapped to one key), d_sorted_index = index[perm], both
+ * built once.  Per template the kernel reads the plan coalesced, gathers the weights and adds every warp's run of equal
+ * bins to the exact 128-bit fixed-point accumulators with one atomic pair: bit-reproducible, independent of grid and
+ * order like pisab_hist_accumulate_* above PISAB_DET_MAX_BINS, and ~8x faster than it at 3200 bins.  Workspace:
+ * pisab_hist_workspace_bytes(n, n_bins). */
+int pisab_hist_accumulate_sorted_f64(const int32_t *d_perm, const int32_t *d_sorted_index, const double *d_weights,
+                                     int64_t n, int32_t n_bins, double *d_hist, double *d_hist_w2, void *d_workspace,
+                                     int64_t workspace_bytes, void *stream);
+int pisab_hist_accumulate_sorted_f32(const int32_t *d_perm, const int32_t *d_sorted_index, const float *d_weights,
+                                     int64_t n, int32_t n_bins, double *d_hist, double *d_hist_w2, void *d_workspace,
+                                     int64_t workspace_bytes, void *stream);
+
+/* ---- setup-time ordering (stable radix sort of small non-negative integer keys) ---------------------------------
+ * d_order[k] = index of the event with the k-th smallest (largest if `descending`) key, ties in input order;
+ * d_sorted_keys (optional) = d_keys[d_order].  key_bits: number of significant key bits (0 = 31).  Used once per event
+ * sample: grouping events by crossed Earth shells (pisab_layer_count_*; the reference computes its layer arrays once
+ * in prob3.setup_function as well, prob3.py:406-409) and the sorted plan of pisab_hist_accumulate_sorted_*. */
+int64_t pisab_sort_workspace_bytes(int64_t n);
+int pisab_sort_order_i32(const int32_t *d_keys, int64_t n, int32_t key_bits, int32_t descending, int32_t *d_order,
+                         int32_t *d_sorted_keys, void *d_workspace, int64_t workspace_bytes, void *stream);
+
 /* ---- planned histogram (the fit-loop form of utils.hist.apply_function) ------------------------------------
  * The bin index of an event is computed once at hist.setup_function (hist.py:86-127) and never changes during a fit.
  * pisab_hist_plan_build turns it, once, into a PLAN: per tile of 2048 events the permutation that groups the tile's

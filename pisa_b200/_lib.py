@@ -120,6 +120,7 @@ _SIGNATURES = {
     "pisab_reweight_hist_scan": (c_i32, [ctypes.POINTER(OscConsts), c_i32, ctypes.POINTER(Earth),
                                          ctypes.POINTER(ContainerDesc), c_i32, c_i32, c_vp, c_vp, c_i64, c_vp]),
     "pisab_hist_accumulate_planned": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "pisab_hist_accumulate_sorted": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_scale_weights": (c_i32, [c_vp, c_dbl, c_i64, c_vp, c_vp]),
     "pisab_hist_transform": (c_i32, [c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "pisab_reweight_hist_chi2": (c_i32, [ctypes.POINTER(OscConsts), ctypes.POINTER(Earth),
@@ -133,6 +134,8 @@ _UNTYPED = {
     "pisab_hist_workspace_bytes": (c_i64, [c_i64, c_i32]),
     "pisab_reweight_batch_workspace_bytes": (c_i64, [c_i32, c_i32]),
     "pisab_hist_plan_bytes": (c_i64, [c_i64, c_i32]),
+    "pisab_sort_workspace_bytes": (c_i64, [c_i64]),
+    "pisab_sort_order_i32": (c_i32, [c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "pisab_hist_plan_build": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_i64, c_vp]),
     "pisab_exchange_create": (c_i32, [c_i32, c_i32, c_i64, ctypes.POINTER(c_vp), c_vp]),
     "pisab_exchange_connect": (c_i32, [c_vp, c_vp]),

@@ -74,13 +74,15 @@ struct WarpHist {
 // ---- large binnings (> PISAB_DET_MAX_BINS): exact fixed-point accumulation ---------------------------------
 // Private copies of the bins no longer fit in shared memory, and floating-point atomics on shared bins are not
 // reproducible (the order of the additions changes from run to run).  INTEGER addition is associative, so every
-// weight is converted to a 128-bit two's-complement fixed-point number  w * 2^k = hi * 2^64 + lo  and added with two
-// 64-bit integer atomics (the carry out of the low word is detected from the returned old value and added to the
-// high word).  k is chosen from an upper bound of N * max|w| so that the sum cannot overflow; with N = 1e8 events a
-// weight keeps all 53 bits of its mantissa as long as it is within 2^47 of the largest one.  The result is the
+// weight is converted to a 128-bit two's-complement fixed-point number  w * 2^k = hi * 2^64 + lo  and added with
+// integer atomics.  k is chosen from an upper bound of N * max|w| so that the sum cannot overflow; with N = 1e8 events
+// a weight keeps all 53 bits of its mantissa as long as it is within 2^47 of the largest one.  The result is the
 // EXACT sum rounded once: bit-reproducible on any grid, any number of GPUs' worth of event order, any run.
+// The accumulator is kept in CARRY-SAVE form -- the two 32-bit halves of `lo` are summed in 64-bit words of their own
+// (room for 2^32 additions) -- so that an addition is three fire-and-forget reductions (RED) instead of an atomic whose
+// returned value decides the carry: the issuing warp never waits for the L2 round trip.
 struct FixedAcc {
-    unsigned long long lo, hi;
+    unsigned long long lo0, lo1, hi, pad; // value = hi * 2^64 + lo1 * 2^32 + lo0 (mod 2^128), 32-byte entries
 };
 // scale = 2^(62 - ex) with 2^ex > n * bound  (so |sum| * scale < 2^62); bound == 0 (all weights zero) -> 1
 __device__ __forceinline__ double fixed_scale(double bound, double n) {
@@ -90,19 +92,89 @@ __device__ __forceinline__ double fixed_scale(double bound, double n) {
     frexp(tot, &ex);
     return ldexp(1.0, 62 - ex);
 }
-__device__ __forceinline__ void fixed_add(FixedAcc *acc, double v, double scale) {
+struct Fixed128 { // one weight (or a sum of weights) as a 128-bit two's-complement fixed-point number
+    unsigned long long lo;
+    long long hi;
+};
+__device__ __forceinline__ Fixed128 to_fixed(double v, double scale) {
     const double s = v * scale;               // exact: scale is a power of two
     const double fl = floor(s);
     const double rem = s - fl;                // [0, 1), exact
-    const unsigned long long lo = (unsigned long long)(rem * 18446744073709551616.0);
-    const long long hi = (long long)fl;
-    const unsigned long long old = atomicAdd(&acc->lo, lo);
-    const unsigned long long carry = (old + lo) < old ? 1ull : 0ull;
-    const unsigned long long add_hi = (unsigned long long)hi + carry;
-    if (add_hi) atomicAdd(&acc->hi, add_hi);
+    Fixed128 r;
+    r.lo = (unsigned long long)(rem * 18446744073709551616.0);
+    r.hi = (long long)fl;
+    return r;
 }
+__device__ __forceinline__ void fixed_sum(Fixed128 &a, const Fixed128 &b) { // a += b (integer, associative)
+    const unsigned long long lo = a.lo + b.lo;
+    a.hi += b.hi + (lo < a.lo ? 1 : 0);
+    a.lo = lo;
+}
+__device__ __forceinline__ void fixed_add(FixedAcc *acc, const Fixed128 &x) {
+    atomicAdd(&acc->lo0, x.lo & 0xffffffffull); // results unused: RED, not ATOM
+    atomicAdd(&acc->lo1, x.lo >> 32);
+    if (x.hi) atomicAdd(&acc->hi, (unsigned long long)x.hi);
+}
+__device__ __forceinline__ void fixed_add(FixedAcc *acc, double v, double scale) { fixed_add(acc, to_fixed(v, scale)); }
+__device__ __forceinline__ Fixed128 warp_fixed_reduce(Fixed128 v) { // sum over the 32 lanes (xor tree), in every lane
+    for (int off = 16; off > 0; off >>= 1) {
+        Fixed128 o;
+        o.lo = __shfl_xor_sync(0xffffffffu, v.lo, off);
+        o.hi = __shfl_xor_sync(0xffffffffu, v.hi, off);
+        fixed_sum(v, o);
+    }
+    return v;
+}
+
+// Warp-collective form for events that arrive grouped by bin (the engine orders the events of a large binning by
+// bin inside every class of crossed shells).  All 32 lanes in one bin -- the usual case then: the fixed-point weights
+// are summed by a shuffle tree (integer addition: still exact and order-independent) and lane 0 issues ONE set of
+// reductions per plane instead of one per event.  Otherwise lanes that share a bin are grouped with __match_any_sync
+// and the lowest lane of each group sums its group through the warp's staging words.
+// stage: this warp's [4][32] unsigned long long.  All 32 lanes must call.
+__device__ __forceinline__ void warp_fixed_add(unsigned long long *stage, FixedAcc *acc, int n_bins, int bin, double w,
+                                               double sc1, double sc2) {
+    const int lane = threadIdx.x & 31;
+    const bool ok = (unsigned)bin < (unsigned)n_bins;
+    const int key = ok ? bin : -1;
+    const Fixed128 a = to_fixed(w, sc1), b = to_fixed(w * w, sc2);
+    const int key0 = __shfl_sync(0xffffffffu, key, 0);
+    if (__all_sync(0xffffffffu, key == key0)) {
+        if (key0 < 0) return;
+        const Fixed128 s1 = warp_fixed_reduce(a), s2 = warp_fixed_reduce(b);
+        if (lane == 0) {
+            fixed_add(acc + key0, s1);
+            fixed_add(acc + n_bins + key0, s2);
+        }
+        return;
+    }
+    __syncwarp();
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    stage[lane] = a.lo;
+    stage[32 + lane] = (unsigned long long)a.hi;
+    stage[64 + lane] = b.lo;
+    stage[96 + lane] = (unsigned long long)b.hi;
+    __syncwarp();
+    if (ok && lane == __ffs(peers) - 1) {
+        Fixed128 s1 = a, s2 = b;
+        unsigned m = peers & (peers - 1); // the other lanes of the group
+        while (m) {
+            const int l = __ffs(m) - 1;
+            m &= m - 1;
+            fixed_sum(s1, Fixed128{stage[l], (long long)stage[32 + l]});
+            fixed_sum(s2, Fixed128{stage[64 + l], (long long)stage[96 + l]});
+        }
+        fixed_add(acc + bin, s1);
+        fixed_add(acc + n_bins + bin, s2);
+    }
+    __syncwarp();
+}
+// carry-save words -> hi * 2^64 + lo, then to double
 __device__ __forceinline__ double fixed_value(const FixedAcc &a, double scale) {
-    return ((double)(long long)a.hi + (double)a.lo * 5.421010862427522e-20) / scale; // lo * 2^-64
+    const unsigned long long mid = a.lo1 << 32;
+    const unsigned long long lo = a.lo0 + mid;
+    const unsigned long long hi = a.hi + (a.lo1 >> 32) + (lo < mid ? 1ull : 0ull);
+    return ((double)(long long)hi + (double)lo * 5.421010862427522e-20) / scale; // lo * 2^-64
 }
 
 // persistent grid for the histogramming kernels (fixed by the device -> reproducible sums)

@@ -278,7 +278,9 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
-    double *s_dyn = s_hist + (LARGE ? 0 : WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double));
+    // (LARGE: no bins, only the warps' [4][32] staging words of warp_fixed_add)
+    double *s_dyn = s_hist + (LARGE ? (size_t)(kBlock / 32) * 128 : WarpHist::smem_bytes(kBlock, n_bins) / sizeof(double));
+    unsigned long long *s_fixed = reinterpret_cast<unsigned long long *>(s_hist) + (threadIdx.x >> 5) * 128;
     double2(*s_state)[kBlock] = reinterpret_cast<double2(*)[kBlock]>(s_dyn);
     float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn); // FP32 mode: float2 state columns
     s_dyn += (MP ? PropagatorSmemF<1, 2>::kSlots : PropagatorSmem<1, 2>::kDoubles) * kBlock;
@@ -380,10 +382,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 }
             }
             if (LARGE) {
-                if ((unsigned)bin < (unsigned)n_bins) {
-                    fixed_add(acc + bin, w, sc1);
-                    fixed_add(acc + n_bins + bin, w * w, sc2);
-                }
+                warp_fixed_add(s_fixed, acc, n_bins, bin, w, sc1, sc2);
             } else {
                 wh.add(bin, w);
             }
@@ -823,7 +822,9 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     const bool std_matter = ot.std_matter != 0.0;
 #endif
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
-    const size_t smem_events = fused_smem_bytes<IO>(large ? 0 : n_bins, std_matter, mp);
+    // (large binnings keep no bins in shared memory, only warp_fixed_add's [4][32] words per warp: the size of a
+    // 48-bin WarpHist)
+    const size_t smem_events = fused_smem_bytes<IO>(large ? 48 : n_bins, std_matter, mp);
     bool plain = true;
     for (int c = 0; c < batch.n_containers; ++c) {
         const FusedContainer<IO> &C = batch.c[c];
@@ -901,7 +902,9 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         int64_t r = by_work;
         const int64_t cap = ((int64_t)resident * PISAB_SPREAD_WAVES + nc - 1) / nc;
         if (r > cap) r = cap;
-        const int64_t fill = (resident + nc - 1) / nc; // one resident wave spread over the containers
+        // one resident wave spread over the containers -- rounded DOWN: a grid of 300 blocks on 296 resident slots
+        // runs as two waves and doubles the time of an analysis-size template
+        const int64_t fill = resident / nc > 0 ? resident / nc : 1;
         if (r < fill) r = by_thread < fill ? by_thread : fill;
         int64_t ws_cap = (int64_t)(sm_count() > 0 ? sm_count() : 148) * 16; // pisab_hist_workspace_bytes
         if (r > ws_cap) r = ws_cap;

@@ -87,15 +87,20 @@ class ReweightEngine:
             # (no divergence) AND its loads are contiguous; a histogram does not depend on the event order
             cz = blk.dev["true_coszen"] if "true_coszen" in blk.dev else blk.host["true_coszen"].to(self.device)
             dummy = None
+            # more bins than fit in shared memory: the events of a class are ordered by bin as well, so that a warp's
+            # 32 events share a bin and cost one exact atomic add instead of 32 (warp_fixed_add)
+            by_bin = None
+            if self.n_bins > _lib.DET_MAX_BINS:
+                by_bin = blk.dev["index"] if "index" in blk.dev else blk.host["index"].to(self.device)
             if self.tdtype == torch.float32 and n > 0:
                 # FP32 mode: the template kernel handles TWO events per thread in the lanes of the packed FP32
                 # instructions; pairs must cross the same shells, so every class is padded to an even size with a
                 # repeat of its last event carrying weight 0 and bin -1 (at most one per class)
-                order, dummy = ops.pair_aligned_order(self.earth, cz)
+                order, dummy = ops.pair_aligned_order(self.earth, cz, by_bin)
                 blk.flags |= _lib.CONTAINER_PAIR_ALIGNED
                 blk.n = int(order.numel())
             else:
-                order = ops.layer_order(self.earth, cz).long()
+                order = ops.layer_order(self.earth, cz, by_bin).long()
 
             def rearranged(t, key, idx, pad):
                 out = t[idx].contiguous()

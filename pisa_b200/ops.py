@@ -242,36 +242,62 @@ def layer_counts(earth, coszen):
     return count
 
 
-def pair_aligned_order(earth, coszen):
+def sort_order(keys, descending=False, key_bits=0, want_sorted=False):
+    """Stable order of non-negative int32 ``keys`` (``pisab_sort_order_i32``, radix sort): int32 permutation, and
+    ``keys[order]`` with ``want_sorted``.  Setup-time helper (event grouping, sorted histogram plans)."""
+    _chk(keys, "keys", torch.int32)
+    n = keys.numel()
+    order = torch.empty(n, dtype=torch.int32, device=keys.device)
+    out = torch.empty(n, dtype=torch.int32, device=keys.device) if want_sorted else None
+    if n:
+        nbytes = int(_lib.load().pisab_sort_workspace_bytes(n))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=keys.device)
+        _lib.check(_lib.load().pisab_sort_order_i32(_ptr(keys), n, int(key_bits), int(bool(descending)), _ptr(order),
+                                                    _ptr(out), _ptr(ws), nbytes, _stream()))
+    return (order, out) if want_sorted else order
+
+
+def _class_order(count, index=None):
+    """Stable permutation (int64) grouping the events by ``count`` (descending); with ``index`` the events of a class
+    are ordered by bin as well (large binnings: a warp's 32 events then share a bin, see ``warp_fixed_add``)."""
+    if index is None or count.numel() == 0:
+        return sort_order(count, descending=True, key_bits=8).long()
+    span = int(index.max()) + 2
+    key = (int(count.max()) - count) * span + torch.clamp(index + 1, min=0)
+    return sort_order(key.to(torch.int32).contiguous()).long()
+
+
+def pair_aligned_order(earth, coszen, index=None):
     """Setup-time helper for the two-events-per-thread FP32 kernel: (sel, dummy) with ``sel`` (int64) listing the
     events grouped by crossed shells like ``layer_order`` and every class padded to an EVEN size by repeating its last
     event, ``dummy`` (bool) marking the repeats (their weight must be set to 0 and their bin index to -1).  Events
     2k and 2k+1 of ``x[sel]`` then cross the same shells (PISAB_CONTAINER_PAIR_ALIGNED)."""
     count = layer_counts(earth, coszen)
-    order = torch.sort(count, descending=True, stable=True).indices
+    order = _class_order(count, index)
     _, sizes = torch.unique_consecutive(count[order], return_counts=True)
     ends = torch.cumsum(sizes, 0) - 1
     extra = ends[sizes % 2 == 1]                       # position (in sorted order) of the event to repeat
     pos = torch.cat([torch.arange(order.numel(), device=order.device), extra])
-    pos = torch.sort(pos, stable=True).values          # repeats land right behind their originals
+    pos = sort_order(pos.to(torch.int32), want_sorted=True)[1].long()   # repeats land right behind their originals
     dummy = torch.zeros(pos.numel(), dtype=torch.bool, device=order.device)
     if pos.numel() > 1:
         dummy[1:] = pos[1:] == pos[:-1]
     return order[pos], dummy
 
 
-def layer_order(earth, coszen):
+def layer_order(earth, coszen, index=None):
     """Setup-time helper: permutation (int32) listing the events grouped by the number of Earth
     shells they cross, deepest first, stable within a group.  Passing it as ``order`` to
     propagate_earth / reweight_hist makes every warp walk the same number of layers; it depends on
-    ``coszen`` only (the reference computes its layer arrays once in setup_function as well)."""
+    ``coszen`` only (the reference computes its layer arrays once in setup_function as well).
+    ``index`` (the events' bin index, optional): secondary key, events of a group ordered by bin."""
     _chk(coszen, "coszen")
     n = coszen.numel()
     count = torch.empty(n, dtype=torch.int32, device=coszen.device)
     f = _lib.fn("pisab_layer_count", coszen.dtype)
     _lib.check(f(ctypes.byref(earth), _ptr(coszen), n, _ptr(count), _stream()))
-    # torch.sort is plumbing here (stable => the permutation, hence every sum, is reproducible)
-    order = torch.sort(count, descending=True, stable=True).indices
+    # (stable sort => the permutation, hence every sum, is reproducible)
+    order = _class_order(count, index)
     return order.to(torch.int32).contiguous()
 
 
@@ -448,12 +474,15 @@ def _workspace(device, n, n_bins, n_containers=1):
 
 
 class HistPlan:
-    """Setup-time plan of a histogram over static bin indices (``pisab_hist_plan_build``): per tile of 2048 events
-    the permutation grouping the events by bin and the group offsets.  ``hist_accumulate(..., plan=plan)`` then needs
-    only the current weights.  ``None`` from ``hist_plan`` means the binning is not plannable (> 256 bins)."""
+    """Setup-time plan of a histogram over static bin indices; ``hist_accumulate(..., plan=plan)`` then needs only the
+    current weights.  Up to 256 bins (``pisab_hist_plan_build``): per tile of 2048 events the permutation grouping the
+    events by bin and the group offsets.  Above DET_MAX_BINS bins: the SORTED plan (``perm`` = stable order of all
+    events by bin, ``sorted_index`` = index[perm]; ``pisab_hist_accumulate_sorted``).  ``None`` from ``hist_plan``: the
+    binnings in between, which the replicated-slot kernel of ``pisab_hist_accumulate`` serves."""
 
-    def __init__(self, buf, n, n_bins, index):
+    def __init__(self, buf, n, n_bins, index, perm=None, sorted_index=None):
         self.buf, self.n, self.n_bins = buf, int(n), int(n_bins)
+        self.perm, self.sorted_index = perm, sorted_index
         self._index, self._counts = index, None
 
     @property
@@ -467,6 +496,11 @@ class HistPlan:
 def hist_plan(index, n_bins):
     _chk(index, "index", torch.int32)
     n = index.numel()
+    if int(n_bins) > _lib.DET_MAX_BINS:
+        # out-of-range events share the key n_bins: they sort to the end and the kernel skips them
+        key = torch.where((index >= 0) & (index < n_bins), index, torch.full_like(index, int(n_bins)))
+        perm, sorted_key = sort_order(key.contiguous(), want_sorted=True)
+        return HistPlan(None, n, n_bins, index, perm=perm, sorted_index=sorted_key)
     nbytes = int(_lib.load().pisab_hist_plan_bytes(n, int(n_bins)))
     if nbytes == 0:
         return None
@@ -485,6 +519,17 @@ def hist_accumulate(index, weights, n_bins, want_w2=True, plan=None):
     if plan is not None and weights is None:
         c = plan.counts                      # unweighted histogram of static indices: nothing to recompute
         return c.clone(), (c.clone() if want_w2 else None)
+    if plan is not None and weights is not None and plan.perm is not None:
+        _chk(weights, "weights")
+        if weights.numel() != n:
+            raise ValueError("weights and index must have the same length")
+        hist = torch.empty(n_bins, dtype=torch.float64, device=index.device)
+        w2 = torch.empty(n_bins, dtype=torch.float64, device=index.device) if want_w2 else None
+        ws = _workspace(index.device, n, n_bins)
+        f = _lib.fn("pisab_hist_accumulate_sorted", weights.dtype)
+        _lib.check(f(_ptr(plan.perm), _ptr(plan.sorted_index), _ptr(weights), n, int(n_bins), _ptr(hist), _ptr(w2),
+                     _ptr(ws), ws.numel(), _stream()))
+        return hist, w2
     if plan is not None and weights is not None and weights.data_ptr() % 16 == 0:
         _chk(weights, "weights")
         if weights.numel() != n:

@@ -258,7 +258,6 @@ def test_hypersurface_stage_and_epilogue_vs_reference_golden():
     binning = parse_pipeline_config("settings/pipeline/b200_icecube3y_full.cfg")[("discr_sys", "hypersurfaces")]["calc_mode"]
     dev = torch.device("cuda:0")
     for ci, values in enumerate(gold["param_values"]):
-        st = hypersurfaces(fit_results_file="events/IceCube_3y_oscillations/hyperplanes_*.csv.bz2",
         data = ContainerSet("hs")
         for m in maps:
             c = Container(m, representation=binning)

@@ -446,11 +446,40 @@ def test_large_binning_is_exact_and_order_independent():
     w32 = np.abs(w).astype(np.float32)
     h32, _ = ops.hist_accumulate(ti, torch.tensor(w32, device=dev), n_bins)
     assert h32.cpu().numpy()[5] == math.fsum(w32[idx == 5].astype(np.float64))
+    # the sorted plan (static indices, fit loop): the same exact sums from one atomic pair per warp and plane
+    plan = ops.hist_plan(ti, n_bins)
+    assert plan is not None and plan.perm is not None
+    sk = plan.sorted_index.cpu().numpy()
+    assert np.all(np.diff(sk) >= 0) and np.array_equal(np.where(ok, idx, n_bins)[plan.perm.cpu().numpy()], sk)
+    for weights in (tw, torch.tensor(w32, device=dev)):
+        a, a2 = ops.hist_accumulate(ti, weights, n_bins)
+        b_, b2 = ops.hist_accumulate(ti, weights, n_bins, plan=plan)
+        assert torch.equal(a, b_) and torch.equal(a2, b2)
+    cp, _ = ops.hist_accumulate(ti, None, n_bins, want_w2=False, plan=plan)
+    assert torch.equal(cp, c)
     # all-zero weights and an empty input
     z, z2 = ops.hist_accumulate(ti, torch.zeros(n, dtype=torch.float64, device=dev), n_bins)
     assert float(z.abs().sum()) == 0.0 and float(z2.abs().sum()) == 0.0
     e, _ = ops.hist_accumulate(ti[:0].contiguous(), tw[:0].contiguous(), n_bins)
     assert float(e.abs().sum()) == 0.0
+
+
+def test_sort_order_is_stable():
+    """pisab_sort_order_i32 (setup-time radix sort behind layer_order and the sorted histogram plan) against a stable
+    numpy argsort: ascending, descending, limited key bits, with the sorted keys."""
+    from pisa_b200 import ops
+    dev = _dev()
+    rng = np.random.default_rng(5)
+    for n, hi, bits in ((0, 10, 0), (1, 10, 0), (1000, 7, 3), (300_001, 60, 8), (200_000, 2_000_000, 0)):
+        k = rng.integers(0, hi, n).astype(np.int32)
+        t = torch.tensor(k, device=dev)
+        for desc in (False, True):
+            order, sk = ops.sort_order(t, descending=desc, key_bits=bits, want_sorted=True)
+            want = np.argsort(-k.astype(np.int64) if desc else k, kind="stable")
+            assert np.array_equal(order.cpu().numpy(), want), (n, hi, desc)
+            assert np.array_equal(sk.cpu().numpy(), k[want])
+    with pytest.raises(TypeError):
+        ops.sort_order(torch.zeros(4, dtype=torch.int64, device=dev))
 
 
 def test_fused_template_with_3200_bins_is_deterministic():
