@@ -527,24 +527,13 @@ hist_reduce_chi2_kernel(const double *__restrict__ partials, int n_blocks, int n
                         double *__restrict__ out, double *__restrict__ total, double *__restrict__ chi2,
                         unsigned *__restrict__ arrive) {
     const int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; // warp-uniform: (container, plane, bin)
-    const int lane = threadIdx.x & 31;
     if (v < n_containers * 2 * n_bins) {
         const int c = v / (2 * n_bins), b = v - c * 2 * n_bins;
-        const double *src = partials + (size_t)c * n_blocks * 2 * n_bins + b;
-        double s = 0.0;
-        for (int k = lane; k < n_blocks; k += 32) s += __ldg(src + (size_t)k * 2 * n_bins);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) {
-            if (bin_scales) {
-                const double sc = bin_scales[(size_t)c * n_bins + (b < n_bins ? b : b - n_bins)];
-                s = b < n_bins ? fmax(s * sc, 0.0) : s * sc * sc;
-            }
-            out[v] = s;
-        }
+        reduce_container_value(partials + (size_t)c * n_blocks * 2 * n_bins, n_blocks, n_bins, b,
+                               bin_scales ? bin_scales + (size_t)c * n_bins : nullptr, out + (size_t)c * 2 * n_bins);
     }
     __shared__ bool s_last;
-    __shared__ double s_acc[256];
+    __shared__ double s_scratch[2 * PISAB_DET_MAX_BINS + 256];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = (atomicAdd(arrive, 1u) == gridDim.x - 1);
@@ -552,35 +541,7 @@ hist_reduce_chi2_kernel(const double *__restrict__ partials, int n_blocks, int n
     if (!s_last) return;
     if (threadIdx.x == 0) *arrive = 0; // the next launch on this stream starts from zero
     __threadfence();
-    // container sums of both planes: one thread per (plane, bin), the loads of all containers issued together (one L2
-    // round trip instead of one per container: this block is the serial tail of every template)
-    __shared__ double s_tot[2 * PISAB_DET_MAX_BINS];
-    for (int v = threadIdx.x; v < 2 * n_bins; v += blockDim.x) {
-        double x[PISAB_MAX_BATCH];
-#pragma unroll
-        for (int c = 0; c < PISAB_MAX_BATCH; ++c) x[c] = c < n_containers ? __ldcg(out + (size_t)c * 2 * n_bins + v) : 0.0;
-        double t = 0.0;
-#pragma unroll
-        for (int c = 0; c < PISAB_MAX_BATCH; ++c) t += x[c]; // container order: fixed (absent containers add +0.0)
-        s_tot[v] = t;
-        if (total) total[v] = t;
-    }
-    __syncthreads();
-    double acc = 0.0;
-    if (observed) {
-        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
-            const double e = fmax(s_tot[b], 1e-10), sig2 = s_tot[n_bins + b];
-            const double d = observed[b] - e;
-            acc += d * d / (sig2 + e);
-        }
-    }
-    s_acc[threadIdx.x] = acc;
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off) s_acc[threadIdx.x] += s_acc[threadIdx.x + off];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && chi2) chi2[0] = s_acc[0];
+    template_total_chi2(out, n_containers, n_bins, observed, total, chi2, s_scratch);
 }
 
 int hist_reduce_chi2(const double *d_partials, int n_blocks, int n_bins, int n_containers, const double *d_bin_scales,

@@ -177,6 +177,128 @@ __device__ __forceinline__ double fixed_value(const FixedAcc &a, double scale) {
     return ((double)(long long)hi + (double)lo * 5.421010862427522e-20) / scale; // lo * 2^-64
 }
 
+// ---- fit-loop epilogue (reduce the per-block partial histograms, per-bin systematics scales, container sum, mod_chi2)
+// Shared by hist_reduce_chi2_kernel (a launch of its own) and the template kernels, whose last-arriving blocks run it
+// so that one hypothesis of a fit is ONE launch.
+struct FusedEpi {
+    const double *bin_scales, *observed; // optional [n_containers][n_bins] / [n_bins]
+    double *out;                         // [n_containers][2][n_bins]; nullptr: no epilogue in this launch
+    double *total, *chi2;                // optional [2][n_bins] / one double
+    unsigned *arrive;                    // zero-initialised words: [0] containers done, [1 + c] blocks of container c done
+};
+
+// value v = (plane, bin) of container c: sum of its n_blocks partials -- lane l adds blocks l, l+32, ... in ascending
+// order, the 32 lane sums are combined by a fixed xor tree (the order depends on n_blocks only) -- then the optional
+// discr_sys.hypersurfaces scale (hypersurfaces.py:219-248: weights -> clip(s w, 0), errors -> s errors).
+__device__ __forceinline__ double apply_bin_scale(double r, int v, int n_bins, const double *scales_c) {
+    if (!scales_c) return r;
+    const double sc = scales_c[v < n_bins ? v : v - n_bins];
+    return v < n_bins ? fmax(r * sc, 0.0) : r * sc * sc;
+}
+// one warp per value (the stand-alone reduction kernels: thousands of warps, every lane one strided load)
+__device__ __forceinline__ void reduce_container_value(const double *partials_c, int n_blocks, int n_bins, int v,
+                                                       const double *scales_c, double *out_c) {
+    const int lane = threadIdx.x & 31, n_values = 2 * n_bins;
+    double s = 0.0;
+    for (int k = lane; k < n_blocks; k += 32) s += __ldcg(partials_c + (size_t)k * n_values + v);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out_c[v] = apply_bin_scale(s, v, n_bins, scales_c);
+}
+// one THREAD per value, block-collective (the last block of a container inside the template kernel): consecutive
+// threads read consecutive values of one partial histogram -- coalesced, where the warp-per-value form makes one block
+// fetch 32 sectors per load instruction (10 us for 24 partials, 1 ms for 1579).  The same sums in the same order:
+// 32 register accumulators play the lanes, and since a + b == b + a the xor tree folds to t[l] += t[l + o].
+__device__ __forceinline__ void reduce_container_block(const double *partials_c, int n_blocks, int n_bins,
+                                                       const double *scales_c, double *out_c) {
+    const int n_values = 2 * n_bins;
+    for (int v = threadIdx.x; v < n_values; v += blockDim.x) {
+        double acc[32];
+#pragma unroll
+        for (int l = 0; l < 32; ++l) acc[l] = 0.0;
+        for (int k0 = 0; k0 < n_blocks; k0 += 32) {
+#pragma unroll
+            for (int h = 0; h < 32; h += 16) { // 16 loads in flight (32 would spill next to the 32 accumulators)
+                double x[16];
+#pragma unroll
+                for (int l = 0; l < 16; ++l)
+                    x[l] = k0 + h + l < n_blocks ? __ldcg(partials_c + (size_t)(k0 + h + l) * n_values + v) : 0.0;
+#pragma unroll
+                for (int l = 0; l < 16; ++l)
+                    if (k0 + h + l < n_blocks) acc[h + l] += x[l];
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+            for (int l = 0; l < o; ++l) acc[l] += acc[l + o];
+        }
+        out_c[v] = apply_bin_scale(acc[0], v, n_bins, scales_c);
+    }
+}
+
+// MapSet sum over the containers (fixed order) and mod_chi2 (stats.py:651-695).  Block-collective; scratch: at least
+// 2 * n_bins + blockDim.x doubles of shared memory.  One thread per (plane, bin) issues the loads of all containers
+// together: this is the serial tail of every template.
+__device__ __forceinline__ void template_total_chi2(const double *out, int n_containers, int n_bins, const double *observed,
+                                                    double *total, double *chi2, double *scratch) {
+    double *s_tot = scratch, *s_acc = scratch + 2 * n_bins;
+    for (int v = threadIdx.x; v < 2 * n_bins; v += blockDim.x) {
+        double x[PISAB_MAX_BATCH];
+#pragma unroll
+        for (int c = 0; c < PISAB_MAX_BATCH; ++c) x[c] = c < n_containers ? __ldcg(out + (size_t)c * 2 * n_bins + v) : 0.0;
+        double t = 0.0;
+#pragma unroll
+        for (int c = 0; c < PISAB_MAX_BATCH; ++c) t += x[c]; // (absent containers add +0.0)
+        s_tot[v] = t;
+        if (total) total[v] = t;
+    }
+    __syncthreads();
+    double acc = 0.0;
+    if (observed) {
+        for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+            const double e = fmax(s_tot[b], 1e-10), sig2 = s_tot[n_bins + b];
+            const double d = observed[b] - e;
+            acc += d * d / (sig2 + e);
+        }
+    }
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = blockDim.x >> 1; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s_acc[threadIdx.x] += s_acc[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && chi2) chi2[0] = s_acc[0];
+}
+
+// Called by every block of a template kernel after it has written its partial histogram of container ci (rank of
+// `ranks`).  The last block of a container reduces that container; the last container to finish sums the containers
+// and evaluates the chi2.  scratch: the block's (now idle) dynamic shared memory.
+__device__ __forceinline__ void fused_epilogue(const FusedEpi &E, const double *partials, int ci, int ranks, int n_containers,
+                                               int n_bins, double *scratch) {
+    __shared__ int s_role;
+    __threadfence(); // this block's partial histogram is visible device-wide before it is counted
+    __syncthreads();
+    if (threadIdx.x == 0) s_role = atomicAdd(E.arrive + 1 + ci, 1u) == (unsigned)ranks - 1 ? 1 : 0;
+    __syncthreads();
+    if (!s_role) return;
+    __threadfence();
+    const int n_values = 2 * n_bins;
+    reduce_container_block(partials + (size_t)ci * ranks * n_values, ranks, n_bins,
+                           E.bin_scales ? E.bin_scales + (size_t)ci * n_bins : nullptr, E.out + (size_t)ci * n_values);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        E.arrive[1 + ci] = 0; // the next launch on this stream starts from zero
+        s_role = atomicAdd(E.arrive, 1u) == (unsigned)n_containers - 1 ? 2 : 0;
+    }
+    __syncthreads();
+    if (s_role != 2) return;
+    if (threadIdx.x == 0) E.arrive[0] = 0;
+    __threadfence();
+    if (E.total || E.chi2) template_total_chi2(E.out, n_containers, n_bins, E.observed, E.total, E.chi2, scratch);
+}
+
 // persistent grid for the histogramming kernels (fixed by the device -> reproducible sums)
 int hist_grid(int64_t n);
 // hist[b] = sum over blocks (in block order) of partials[block][b]; w2 likewise (nullable)
@@ -189,5 +311,7 @@ int hist_reduce_batch(const double *d_partials, int n_blocks, int n_bins, int n_
 int hist_reduce_chi2(const double *d_partials, int n_blocks, int n_bins, int n_containers, const double *d_bin_scales,
                      const double *d_observed, double *d_out, double *d_total, double *d_chi2, unsigned *d_arrive,
                      cudaStream_t s);
+// zero-initialised arrival words of the epilogue for (current device, stream); nullptr when none can be had
+unsigned *epilogue_counter(cudaStream_t s);
 
 } // namespace pisab

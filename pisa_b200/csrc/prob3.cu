@@ -2,6 +2,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <mutex>
+
 #include <vector>
 
 #include "flux_device.cuh"
@@ -274,7 +276,8 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                                                     const FusedBatch<IO> &batch, int ci_begin, int ci_end,
                                                     int rank, int n_ranks, double *__restrict__ partials,
                                                     double *s_hist,
-                                                    const unsigned long long *__restrict__ bounds = nullptr) {
+                                                    const unsigned long long *__restrict__ bounds = nullptr,
+                                                    int mode = 0) {
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
@@ -292,9 +295,17 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     WarpHist wh(s_hist, n_bins);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)n_ranks * blockDim.x;
-    const int64_t first = (int64_t)rank * blockDim.x + tid;
-    // warp-uniform trip count so that the warp-collective histogram step is always converged
-    const int64_t warp_first = first - (tid & 31);
+    // Which events a thread walks: t = first + k * stride.  Default: a block takes 256 consecutive events per round --
+    // the events are sorted by crossed shells, so its warps cost the same and finish together (what a multi-wave grid
+    // wants).  `interleave` (single-wave grids, i.e. analysis-size samples): consecutive 32-event chunks go round-robin
+    // over the blocks instead, so that every SM gets the same mix of deep (expensive) and shallow (cheap) events; with
+    // consecutive chunks the SM that holds the deepest events ran 4x longer than the one with the shallowest
+    // (sm__cycles_active 13k .. 57k, profiles/r02_small_template.txt), and odd rounds walk the chunks BACKWARDS, so
+    // that the warp that drew the deepest chunk of round 0 draws the shallowest of round 1 (the critical path of a
+    // two-round template is one warp's two events).
+    const bool interleave = mode & 1;
+    const int first = interleave ? ((tid >> 5) * n_ranks + rank) * 32 + (tid & 31) : rank * (int)blockDim.x + tid;
+    const int first_odd = (mode & 2) ? (int)stride - 32 - (first - (tid & 31)) + (tid & 31) : first;
 
     for (int ci = ci_begin; ci < ci_end; ++ci) {
         const FusedContainer<IO> &C = batch.c[ci];
@@ -316,11 +327,12 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
         // `order` (optional) lists the events grouped by number of crossed shells; -1 = no event
         // (n < 2^31 is checked by the host wrapper: 32-bit event indices save registers)
         auto event_of = [&](int64_t t) -> int { return t < n ? (order ? __ldg(order + t) : (int)t) : -1; };
-        int i_cur = event_of(first), i_next = event_of(first + stride);
+        int i_cur = event_of(first), i_next = event_of(stride + first_odd);
         if (i_cur >= 0) { s_e[tid] = __ldg(energy + i_cur); s_cz[tid] = __ldg(coszen + i_cur); }
-        for (int64_t base = warp_first; base < n; base += stride) {
-            const int64_t t = base + (tid & 31);
-            const int i_nn = event_of(t + 2 * stride);
+        // block-uniform trip count (rounds of `stride` events), so that the warp-collective histogram step is converged
+        int odd = 0;
+        for (int64_t round = 0; round < n; round += stride, odd ^= 1) {
+            const int i_nn = event_of(round + 2 * stride + (odd ? first_odd : first));
             double w = 0.0;
             int bin = -1;
             if (i_cur >= 0) {
@@ -436,7 +448,7 @@ template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false
 __global__ void __launch_bounds__(kBlock, MP ? PISAB_MP_MIN_BLOCKS : PISAB_MIN_BLOCKS)
 reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                      const __grid_constant__ FusedBatch<IO> batch, int ranks, double *__restrict__ partials,
-                     const unsigned long long *__restrict__ bounds = nullptr) {
+                     const unsigned long long *__restrict__ bounds, int interleave, const __grid_constant__ FusedEpi epi) {
     extern __shared__ __align__(16) double s_hist[];
     __shared__ EarthTable s_earth;
     // the oscillation table is read straight from the kernel-parameter constant bank (fixed offsets: a
@@ -446,7 +458,10 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
     // never walks more than one container, so a template over analysis-size containers (1e4 events each)
     // costs one or two event latencies instead of one per container.
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, STD, PLAIN, MP, LARGE, FLUX>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds);
+    fused_template_body<IO, STD, PLAIN, MP, LARGE, FLUX>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials, s_hist, bounds,
+                                                         interleave);
+    // one hypothesis = one launch: the last block of every container reduces it, the last container sums and scores
+    if (!LARGE && epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
 // ---- FP32 mode, TWO events per thread (prob3_mp.cuh: the float part of a pair runs in the two lanes of the packed
@@ -470,7 +485,7 @@ static size_t fused_pair_smem_bytes(int n_bins) {
 template <bool STD, bool FLUX>
 __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const EarthTable &s_earth,
                                                 const FusedBatch<float> &batch, int ci, int rank, int n_ranks,
-                                                double *__restrict__ partials, double *s_hist) {
+                                                double *__restrict__ partials, double *s_hist, int mode) {
     // dynamic shared memory: [histogram] [state: 9 float4 x block] [flux float4] [e, cz, w: float2 each] [bin int2]
     const int n_bins = batch.n_bins;
     unsigned char *s_dyn = reinterpret_cast<unsigned char *>(s_hist) + WarpHist::smem_bytes(kPairBlock, n_bins);
@@ -484,8 +499,10 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     WarpHist wh(s_hist, n_bins);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)n_ranks * blockDim.x;
-    const int64_t first = (int64_t)rank * blockDim.x + tid;
-    const int64_t warp_first = first - (tid & 31);
+    // (interleave: see fused_template_body)
+    const bool interleave = mode & 1;
+    const int first = interleave ? ((tid >> 5) * n_ranks + rank) * 32 + (tid & 31) : rank * (int)blockDim.x + tid;
+    const int first_odd = (mode & 2) ? (int)stride - 32 - (first - (tid & 31)) + (tid & 31) : first;
     const FusedContainer<float> &C = batch.c[ci];
     const float2 *__restrict__ energy = reinterpret_cast<const float2 *>(C.energy);
     const float2 *__restrict__ coszen = reinterpret_cast<const float2 *>(C.coszen);
@@ -496,11 +513,11 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     const bool fold_flux = FLUX && (C.flags & PISAB_CONTAINER_FLUX_SYS);
     wh.clear();
     auto pair_of = [&](int64_t t) -> int { return t < n_pairs ? (int)t : -1; };
-    int p_cur = pair_of(first), p_next = pair_of(first + stride);
+    int p_cur = pair_of(first), p_next = pair_of(stride + first_odd);
     if (p_cur >= 0) { s_e[tid] = __ldg(energy + p_cur); s_cz[tid] = __ldg(coszen + p_cur); }
-    for (int64_t base = warp_first; base < n_pairs; base += stride) {
-        const int64_t t = base + (tid & 31);
-        const int p_nn = pair_of(t + 2 * stride);
+    int odd = 0;
+    for (int64_t round = 0; round < n_pairs; round += stride, odd ^= 1) {
+        const int p_nn = pair_of(round + 2 * stride + (odd ? first_odd : first));
         double w0 = 0.0, w1 = 0.0;
         int bin0 = -1, bin1 = -1;
         if (p_cur >= 0) {
@@ -562,12 +579,14 @@ template <bool STD, bool FLUX = false>
 __global__ void __launch_bounds__(kPairBlock, PISAB_PAIR_MIN_BLOCKS)
 reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
-                          const unsigned long long *__restrict__ /* bounds: same signature as reweight_hist_kernel */) {
+                          const unsigned long long *__restrict__ /* bounds: same signature as reweight_hist_kernel */,
+                          int interleave, const __grid_constant__ FusedEpi epi) {
     extern __shared__ __align__(16) double s_hist[];
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_pair_body<STD, FLUX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist);
+    fused_pair_body<STD, FLUX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist, interleave);
+    if (epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -761,20 +780,26 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
     return PISAB_OK;
 }
 
-// Arrival counter of the reduce + chi2 epilogue kernel: one zero-initialised word per device, owned by the library
-// (the kernel resets it to zero before it exits, so launches on ONE stream can reuse it; concurrent epilogues on
-// several streams of the same device are not supported).
-static unsigned *epilogue_counter() {
-    static unsigned *counters[64] = {nullptr};
+// Arrival words of the epilogue (hist_device.cuh: fused_epilogue / hist_reduce_chi2_kernel): 64 zero-initialised words
+// per (device, stream), owned by the library.  The kernels reset what they counted before they exit, so consecutive
+// launches on a stream reuse them; launches on different streams get different words.  nullptr (table full or
+// allocation failed) sends the caller to the two-launch form.
+unsigned *pisab::epilogue_counter(cudaStream_t stream) {
+    struct Slot { int dev; cudaStream_t stream; unsigned *words; };
+    static Slot slots[64];
+    static int n_slots = 0;
+    static std::mutex lock;
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!counters[dev]) {
-        unsigned *p = nullptr;
-        if (cudaMalloc(&p, 256) != cudaSuccess) return nullptr;
-        if (cudaMemset(p, 0, 256) != cudaSuccess) return nullptr;
-        counters[dev] = p;
-    }
-    return counters[dev];
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> guard(lock);
+    for (int i = 0; i < n_slots; ++i)
+        if (slots[i].dev == dev && slots[i].stream == stream) return slots[i].words;
+    if (n_slots == 64) return nullptr;
+    unsigned *p = nullptr;
+    if (cudaMalloc(&p, 256) != cudaSuccess) return nullptr;
+    if (cudaMemset(p, 0, 256) != cudaSuccess) { cudaFree(p); return nullptr; }
+    slots[n_slots++] = Slot{dev, stream, p};
+    return p;
 }
 
 // optional fit-loop epilogue of a batched template (pisab_reweight_hist_chi2_*)
@@ -892,6 +917,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
     // small containers instead get up to one block per 256 events as long as one resident wave holds them all
     // (latency of one or two events per template)
     int ranks;
+    bool single_wave = false; // the whole grid is resident at once: spread the expensive events over the SMs (interleave)
     {
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
@@ -910,6 +936,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (r > ws_cap) r = ws_cap;
         if (r < 1) r = 1;
         ranks = (int)r;
+        single_wave = (int64_t)ranks * nc <= resident;
     }
     const int grid = ranks * batch.n_containers;
     if (large) {
@@ -924,7 +951,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         note_launch();
         {
             LaunchTimer t(s);
-            kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_acc, d_bounds);
+            kernel<<<grid, kBlock, smem, s>>>(ot, et, batch, ranks, (double *)d_acc, d_bounds, single_wave ? 1 : 0, FusedEpi{});
             note_launch();
         }
         const int total = batch.n_containers * 2 * n_bins;
@@ -933,14 +960,31 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         PISAB_CUDA_CHECK(cudaGetLastError());
         return PISAB_OK;
     }
+    // Single-wave grids (analysis-size samples, where a launch is a visible fraction of a template) end inside the
+    // template kernel (fused_epilogue): reduction of the partial histograms, and for pisab_reweight_hist_chi2_* the
+    // per-bin scales, the container sum and the chi2 -- ONE launch per hypothesis.  Multi-wave grids keep the second
+    // launch: there the last block of a container would sum thousands of partial histograms alone (+0.06 ms on the
+    // 10.9 ms of 1e8 events in FP64, +0.2 ms on 7.3 ms in FP32 mode; scratch/r02_run19.sh).
+    FusedEpi fe = {};
+    if (d_batch_out && single_wave) {
+        unsigned *d_arrive = epilogue_counter(s);
+        const size_t scratch = (size_t)(2 * n_bins + block) * sizeof(double);
+        if (d_arrive && batch.n_containers < 63 && scratch <= smem) {
+            fe.out = d_batch_out;
+            fe.arrive = d_arrive;
+            if (epi) { fe.bin_scales = epi->d_bin_scales; fe.observed = epi->d_observed; fe.total = epi->d_total; fe.chi2 = epi->d_chi2; }
+        }
+    }
     {
         LaunchTimer t(s);
-        kernel<<<grid, block, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace, nullptr);
+        // bit 0: 32-event chunks round-robin over the blocks, bit 1: odd rounds backwards (fused_template_body)
+        kernel<<<grid, block, smem, s>>>(ot, et, batch, ranks, (double *)d_workspace, nullptr, single_wave ? 3 : 0, fe);
         note_launch();
     }
     PISAB_CUDA_CHECK(cudaGetLastError());
+    if (fe.out) return PISAB_OK;
     if (d_batch_out && epi) {
-        unsigned *d_arrive = epilogue_counter();
+        unsigned *d_arrive = epilogue_counter(s);
         if (!d_arrive) { set_error("could not allocate the epilogue arrival counter"); return PISAB_ERR_CUDA; }
         return hist_reduce_chi2((const double *)d_workspace, ranks, n_bins, batch.n_containers, epi->d_bin_scales,
                                 epi->d_observed, d_batch_out, epi->d_total, epi->d_chi2, d_arrive, s);
@@ -1190,7 +1234,7 @@ int pisab_hist_scale_sum_chi2(const double *d_partials, int32_t n_blocks, int32_
         set_error("hist_scale_sum_chi2: bad arguments (1..%d containers, 1..%d bins)", PISAB_MAX_BATCH, PISAB_DET_MAX_BINS);
         return PISAB_ERR_ARG;
     }
-    unsigned *d_arrive = epilogue_counter();
+    unsigned *d_arrive = epilogue_counter((cudaStream_t)stream);
     if (!d_arrive) { set_error("could not allocate the epilogue arrival counter"); return PISAB_ERR_CUDA; }
     return hist_reduce_chi2(d_partials, n_blocks, n_bins, n_containers, d_bin_scales, d_observed, d_hist, d_total, d_chi2,
                             d_arrive, (cudaStream_t)stream);
