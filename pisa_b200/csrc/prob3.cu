@@ -482,7 +482,7 @@ static size_t fused_pair_smem_bytes(int n_bins) {
            (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48);
 }
 
-template <bool STD, bool FLUX>
+template <bool STD, bool FLUX, bool MIX>
 __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const EarthTable &s_earth,
                                                 const FusedBatch<float> &batch, int ci, int rank, int n_ranks,
                                                 double *__restrict__ partials, double *s_hist, int mode) {
@@ -499,10 +499,12 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     WarpHist wh(s_hist, n_bins);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)n_ranks * blockDim.x;
-    // (interleave: see fused_template_body)
-    const bool interleave = mode & 1;
+    // MIX (single-wave grids): chunks interleaved over the blocks, odd rounds backwards -- see fused_template_body; a
+    // template parameter here because this kernel sits at the edge of its register budget (the run-time form cost
+    // 1.6 % of the multi-wave throughput)
+    const bool interleave = MIX && (mode & 1);
     const int first = interleave ? ((tid >> 5) * n_ranks + rank) * 32 + (tid & 31) : rank * (int)blockDim.x + tid;
-    const int first_odd = (mode & 2) ? (int)stride - 32 - (first - (tid & 31)) + (tid & 31) : first;
+    const int first_odd = (MIX && (mode & 2)) ? (int)stride - 32 - (first - (tid & 31)) + (tid & 31) : first;
     const FusedContainer<float> &C = batch.c[ci];
     const float2 *__restrict__ energy = reinterpret_cast<const float2 *>(C.energy);
     const float2 *__restrict__ coszen = reinterpret_cast<const float2 *>(C.coszen);
@@ -575,7 +577,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
 }
 
-template <bool STD, bool FLUX = false>
+template <bool STD, bool FLUX = false, bool MIX = false>
 __global__ void __launch_bounds__(kPairBlock, PISAB_PAIR_MIN_BLOCKS)
 reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
@@ -585,8 +587,8 @@ reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_con
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_pair_body<STD, FLUX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist, interleave);
-    if (epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
+    fused_pair_body<STD, FLUX, MIX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist, interleave);
+    if (MIX && epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
 // Parameter scan (BASELINE configs[4]): P templates in ONE launch.  Block b serves (template, container, rank)
@@ -937,6 +939,15 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (r < 1) r = 1;
         ranks = (int)r;
         single_wave = (int64_t)ranks * nc <= resident;
+    }
+    if (pairs && single_wave) {
+        // the instantiation with the interleaved chunk order and the in-kernel epilogue (same registers and shared memory)
+        if constexpr (sizeof(IO) == 4) {
+            kernel = flux ? (std_matter ? reweight_hist_pair_kernel<true, true, true> : reweight_hist_pair_kernel<false, true, true>)
+                          : (std_matter ? reweight_hist_pair_kernel<true, false, true> : reweight_hist_pair_kernel<false, false, true>);
+            if (smem > 48 * 1024)
+                PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
     }
     const int grid = ranks * batch.n_containers;
     if (large) {
