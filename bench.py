@@ -126,10 +126,16 @@ def oracle_chain(oracle, L, mats, nubar, flav, ev, den=None, dis=None, n_threads
                                   n_threads=n_threads or (os.cpu_count() or 1))
     pe, pmu = oracle.fill_probs(prob, 0, flav), oracle.fill_probs(prob, 1, flav)
     w = ev["weights"] * (ev["nu_flux"][:, 0] * pe + ev["nu_flux"][:, 1] * pmu)
-    ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
-    i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
-    idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
-    return np.stack([oracle.accumulate(idx, w, 128), oracle.accumulate(idx, w * w, 128)]), idx
+    if dims == "stress":   # STRESS_DIMS: log-E 40 x lin-coszen 40 x pid 2 (the log of sample and domain, container.py:845-850)
+        idx, _ = oracle.regular_index([np.log(ev["reco_energy"]), ev["reco_coszen"], ev["pid"]],
+                                      [np.log(5.62341325), -1.0, -0.5], [np.log(56.23413252), 1.0, 1.5], [40, 40, 2])
+        n_bins = 3200
+    else:
+        ie = oracle.digitize_irregular(ev["reco_energy"], syn.DRAGON_E_EDGES)
+        i2, _ = oracle.regular_index([ev["reco_coszen"], ev["pid"]], [-1.0, -0.5], [1.0, 1.5], [8, 2])
+        idx = np.where((ie >= 0) & (ie < 8) & (i2 >= 0), ie * 16 + i2, -1)
+        n_bins = 128
+    return np.stack([oracle.accumulate(idx, w, n_bins), oracle.accumulate(idx, w * w, n_bins)]), idx
 
 
 class CpuChain:
@@ -439,10 +445,13 @@ def run_variants(h, args):
 
     # ---- C4: standard NSI + hist, 1e9 events over 8 GPUs = 1.25e8 events per GPU (weak scaling) -------------
     n = 125_000_000 // 12 * 12
-    eng, _, _, _ = h.build(n, np.float64, seed_base=50_000)
+    keep = 0 if (args.no_parity or h.rank != 0) else 2000
+    eng, _, _, kept = h.build(n, np.float64, seed_base=50_000, keep=keep)
     c_nsi = h.consts(nsi=True)
     ms, res = h.time_steps(lambda: eng.evaluate(c_nsi), steps, warmup)
+    par = parity_check(h, kept, syn.osc_matrices(nsi=syn.STD_NSI), lambda e: e.evaluate(c_nsi, allreduce=False)) if kept else None
     out["C4_nsi"] = {"value": n * h.world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "events_per_gpu": n,
+                     "parity_check": par,
                      "global_events": n * h.world, "dtype": "f64", "n_bins": 128, "steps": steps, "warmup": warmup,
                      "what": "BASELINE configs[3]: standard-NSI matter potential (eps_emu 0.07/340deg, eps_etau "
                              "0.06/35deg, eps_mutau 0.003/175deg) + weighted hist; general-Hamiltonian kernel path"}
@@ -475,11 +484,13 @@ def run_variants(h, args):
     torch.cuda.empty_cache()
 
     # ---- stress binning 40 x 40 x 2 = 3200 bins ----------------------------------------------------
-    eng, _, _, _ = h.build(n, np.float64, dims=STRESS_DIMS, n_bins=3200)
+    eng, _, _, kept = h.build(n, np.float64, dims=STRESS_DIMS, n_bins=3200, keep=keep)
     ms, res = h.time_steps(lambda: eng.evaluate(consts), steps, warmup)
     again = eng.evaluate(consts).clone()
     again2 = eng.evaluate(consts)
+    par = parity_check(h, kept, syn.osc_matrices(), lambda e: e.evaluate(consts, allreduce=False), dims="stress") if kept else None
     out["bins_3200"] = {"value": n * h.world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "events_per_gpu": n,
+                        "parity_check": par,
                         "n_bins": 3200, "binning": "log-E 40 x lin-coszen 40 x pid 2", "dtype": "f64",
                         "bit_reproducible_run_to_run": bool(torch.equal(again, again2)), "steps": steps,
                         "warmup": warmup}
@@ -519,7 +530,7 @@ def run_variants(h, args):
     return out
 
 
-def parity_check(h, kept, consts_mats, eng_out_fn):
+def parity_check(h, kept, consts_mats, eng_out_fn, dims="dragon"):
     """Oracle chain on the kept subsample of the bench's own events vs the GPU path on the same events."""
     import oracle
     from pisa_b200.engine import ReweightEngine
@@ -527,11 +538,12 @@ def parity_check(h, kept, consts_mats, eng_out_fn):
     prem = np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat"))
     OL = oracle.OracleLayers(prem, syn.EARTH["detector_depth"], syn.EARTH["prop_height"])
     OL.setElecFrac(syn.EARTH["YeI"], syn.EARTH["YeO"], syn.EARTH["YeM"])
-    eng = ReweightEngine(h.earth, syn.DRAGON_NBINS, kept[0][3]["weights"].dtype, dev)
-    ref = np.zeros((len(kept), 2, 128))
+    n_bins = 3200 if dims == "stress" else syn.DRAGON_NBINS
+    eng = ReweightEngine(h.earth, n_bins, kept[0][3]["weights"].dtype, dev)
+    ref = np.zeros((len(kept), 2, n_bins))
     mism = 0
     for c, (name, nubar, flav, ev) in enumerate(kept):
-        ref[c], idx = oracle_chain(oracle, OL, consts_mats, nubar, flav, ev)
+        ref[c], idx = oracle_chain(oracle, OL, consts_mats, nubar, flav, ev, dims=dims)
         mism += int((idx.astype(np.int32) != ev["index"]).sum())
         t = {k: torch.tensor(ev[k], device=dev) for k in ("true_energy", "true_coszen", "nu_flux", "weights", "index")}
         eng.add_container(name, nubar, flav, **t)

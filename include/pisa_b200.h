@@ -416,10 +416,10 @@ int pisab_sort_order_i32(const int32_t *d_keys, int64_t n, int32_t key_bits, int
  * The bin index of an event is computed once at hist.setup_function (hist.py:86-127) and never changes during a fit.
  * pisab_hist_plan_build turns it, once, into a PLAN: per tile of 2048 events the permutation that groups the tile's
  * events by bin (uint16, stable) and the n_bins + 1 group offsets.  pisab_hist_accumulate_planned_* then produces
- * sum w and sum w^2 from the plan and the current weights: one thread per bin walks its group in shared memory and
- * accumulates in registers -- no private bins, no atomics, fixed summation order (bit-reproducible), 8 + 2 B/event
- * of DRAM traffic.  Supported for n_bins <= 256 (pisab_hist_plan_bytes returns 0 otherwise: use
- * pisab_hist_accumulate_*).  Events whose index is outside [0, n_bins) are dropped, as in pisab_hist_accumulate_*.
+ * sum w and sum w^2 from the plan and the current weights: one thread per bin (up to four bins per thread) walks its
+ * group in shared memory and accumulates in registers -- no private bins, no atomics, fixed summation order
+ * (bit-reproducible), 8 + 2 B/event of DRAM traffic.  Supported for n_bins <= PISAB_DET_MAX_BINS (pisab_hist_plan_bytes
+ * returns 0 otherwise: use the sorted plan of pisab_hist_accumulate_sorted_*).  Events whose index is outside [0, n_bins) are dropped, as in pisab_hist_accumulate_*.
  * d_weights must be 16-byte aligned.  Workspace: pisab_hist_workspace_bytes(n, n_bins). */
 int64_t pisab_hist_plan_bytes(int64_t n, int32_t n_bins);
 int pisab_hist_plan_build(const int32_t *d_index, int64_t n, int32_t n_bins, void *d_plan, int64_t plan_bytes,

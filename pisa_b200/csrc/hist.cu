@@ -247,7 +247,7 @@ hist_accumulate_slots_kernel(const int32_t *__restrict__ index, const IO *__rest
 // (the 16 KB of replicated bins per warp is what capped the slot kernel at 12 warps per SM), 10.1 B/event of DRAM
 // traffic instead of 12, and the summation order is fixed by the plan: bit-reproducible.
 constexpr int kPlanTile = 2048;
-constexpr int kPlanMaxBins = 256;
+constexpr int kPlanMaxBins = PISAB_DET_MAX_BINS; // 1024: up to four bins per thread
 struct PlanLayout {
     int64_t n_tiles;
     int off_stride;     // uint16 entries per tile in the offsets table (n_bins + 1 rounded up to 8: 16-byte rows)
@@ -261,8 +261,8 @@ struct PlanLayout {
     __host__ __device__ size_t bytes() const { return off_bytes + perm_bytes; }
 };
 
-// one block per tile; thread b counts, then places, the events of bin b in tile order (stable)
-__global__ void __launch_bounds__(kPlanMaxBins)
+// one block per tile; thread b counts, then places, the events of bins b, b + blockDim, ... in tile order (stable)
+__global__ void __launch_bounds__(256)
 hist_plan_kernel(const int32_t *__restrict__ index, int64_t n, int n_bins, uint16_t *__restrict__ offsets, int off_stride,
                  uint16_t *__restrict__ perm) {
     __shared__ int16_t s_bin[kPlanTile];
@@ -274,20 +274,29 @@ hist_plan_kernel(const int32_t *__restrict__ index, int64_t n, int n_bins, uint1
         s_bin[i] = (int16_t)((unsigned)b < (unsigned)n_bins ? b : -1);
     }
     __syncthreads();
-    const int b = threadIdx.x;
-    int cnt = 0;
-    if (b < n_bins)
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
+        int cnt = 0;
         for (int i = 0; i < kPlanTile; ++i) cnt += (s_bin[i] == b);
-    s_count[b] = cnt;
+        s_count[b] = cnt;
+    }
     __syncthreads();
-    if (b == 0) { // exclusive scan (<= 256 entries)
-        int acc = 0;
-        for (int k = 0; k < n_bins; ++k) { const int c = s_count[k]; s_count[k] = acc; acc += c; }
-        s_count[n_bins] = acc;
+    if (threadIdx.x < 32) { // exclusive scan by one warp: lane l owns a contiguous run of bins
+        const int per = (n_bins + 31) / 32, lo = threadIdx.x * per, hi = min(lo + per, n_bins);
+        int mine = 0;
+        for (int k = lo; k < hi; ++k) mine += s_count[k];
+        int incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
+        }
+        int acc = incl - mine;
+        for (int k = lo; k < hi; ++k) { const int c = s_count[k]; s_count[k] = acc; acc += c; }
+        if (threadIdx.x == 31) s_count[n_bins] = incl;
     }
     __syncthreads();
     uint16_t *my_perm = perm + tile * kPlanTile;
-    if (b < n_bins) {
+    for (int b = threadIdx.x; b < n_bins; b += blockDim.x) {
         int pos = s_count[b];
         for (int i = 0; i < kPlanTile; ++i)
             if (s_bin[i] == b) my_perm[pos++] = (uint16_t)i;
@@ -296,7 +305,7 @@ hist_plan_kernel(const int32_t *__restrict__ index, int64_t n, int n_bins, uint1
     // (entries of perm beyond offsets[n_bins] are never read)
 }
 
-template <typename IO, int THREADS>
+template <typename IO, int THREADS, int BPT> // thread t owns bins t, t + THREADS, ... (BPT of them)
 __global__ void __launch_bounds__(THREADS)
 hist_planned_kernel(const uint16_t *__restrict__ offsets, int off_stride, const uint16_t *__restrict__ perm,
                     const IO *__restrict__ weights, int64_t n, int n_bins, double *__restrict__ partials) {
@@ -333,7 +342,9 @@ hist_planned_kernel(const uint16_t *__restrict__ offsets, int off_stride, const 
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    double sa = 0.0, sb = 0.0, qa = 0.0, qb = 0.0; // two interleaved chains per sum: order fixed by (plan, grid)
+    double sa[BPT], sb[BPT], qa[BPT], qb[BPT]; // two interleaved chains per sum: order fixed by (plan, grid)
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) sa[j] = sb[j] = qa[j] = qb[j] = 0.0;
     int64_t tile = blockIdx.x;
     int st = 0;
     if (tile < n_tiles) issue(tile, 0);
@@ -350,25 +361,33 @@ hist_planned_kernel(const uint16_t *__restrict__ offsets, int off_stride, const 
         const IO *w = reinterpret_cast<const IO *>(base);
         const uint16_t *p = reinterpret_cast<const uint16_t *>(base + w_bytes);
         const uint16_t *o = reinterpret_cast<const uint16_t *>(base + w_bytes + p_bytes);
-        if (tid < n_bins) {
-            int k = o[tid];
-            const int end = o[tid + 1];
-            for (; k + 1 < end; k += 2) {
-                const double x = (double)w[p[k]], y = (double)w[p[k + 1]];
-                sa += x; qa = fma(x, x, qa);
-                sb += y; qb = fma(y, y, qb);
-            }
-            if (k < end) {
-                const double x = (double)w[p[k]];
-                sa += x; qa = fma(x, x, qa);
+#pragma unroll
+        for (int j = 0; j < BPT; ++j) {
+            const int b = tid + j * THREADS;
+            if (b < n_bins) {
+                int k = o[b];
+                const int end = o[b + 1];
+                for (; k + 1 < end; k += 2) {
+                    const double x = (double)w[p[k]], y = (double)w[p[k + 1]];
+                    sa[j] += x; qa[j] = fma(x, x, qa[j]);
+                    sb[j] += y; qb[j] = fma(y, y, qb[j]);
+                }
+                if (k < end) {
+                    const double x = (double)w[p[k]];
+                    sa[j] += x; qa[j] = fma(x, x, qa[j]);
+                }
             }
         }
         __syncthreads(); // the stage is refilled two iterations from now, by the issue() of the next iteration
     }
-    if (tid < n_bins) {
-        double *dst = partials + (size_t)blockIdx.x * 2 * n_bins;
-        dst[tid] = sa + sb;
-        dst[n_bins + tid] = qa + qb;
+    double *dst = partials + (size_t)blockIdx.x * 2 * n_bins;
+#pragma unroll
+    for (int j = 0; j < BPT; ++j) {
+        const int b = tid + j * THREADS;
+        if (b < n_bins) {
+            dst[b] = sa[j] + sb[j];
+            dst[n_bins + b] = qa[j] + qb[j];
+        }
     }
 }
 
@@ -974,7 +993,10 @@ static int hist_planned_impl(const void *d_plan, const IO *d_weights, int64_t n,
     const uint16_t *off = (const uint16_t *)d_plan, *perm = (const uint16_t *)((const char *)d_plan + L.off_bytes);
     const size_t stage = (size_t)kPlanTile * sizeof(IO) + (size_t)kPlanTile * 2 + (size_t)L.off_stride * 2;
     const size_t smem = 2 * stage;
-    auto kernel = n_bins <= 128 ? hist_planned_kernel<IO, 128> : hist_planned_kernel<IO, 256>;
+    auto kernel = n_bins <= 128   ? hist_planned_kernel<IO, 128, 1>
+                  : n_bins <= 256 ? hist_planned_kernel<IO, 256, 1>
+                  : n_bins <= 512 ? hist_planned_kernel<IO, 256, 2>
+                                  : hist_planned_kernel<IO, 256, 4>;
     const int threads = n_bins <= 128 ? 128 : 256;
     PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;

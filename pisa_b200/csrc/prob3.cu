@@ -945,8 +945,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if constexpr (sizeof(IO) == 4) {
             kernel = flux ? (std_matter ? reweight_hist_pair_kernel<true, true, true> : reweight_hist_pair_kernel<false, true, true>)
                           : (std_matter ? reweight_hist_pair_kernel<true, false, true> : reweight_hist_pair_kernel<false, false, true>);
-            if (smem > 48 * 1024)
-                PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
     }
     const int grid = ranks * batch.n_containers;

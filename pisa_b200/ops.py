@@ -475,10 +475,9 @@ def _workspace(device, n, n_bins, n_containers=1):
 
 class HistPlan:
     """Setup-time plan of a histogram over static bin indices; ``hist_accumulate(..., plan=plan)`` then needs only the
-    current weights.  Up to 256 bins (``pisab_hist_plan_build``): per tile of 2048 events the permutation grouping the
-    events by bin and the group offsets.  Above DET_MAX_BINS bins: the SORTED plan (``perm`` = stable order of all
-    events by bin, ``sorted_index`` = index[perm]; ``pisab_hist_accumulate_sorted``).  ``None`` from ``hist_plan``: the
-    binnings in between, which the replicated-slot kernel of ``pisab_hist_accumulate`` serves."""
+    current weights.  Up to DET_MAX_BINS (1024) bins (``pisab_hist_plan_build``): per tile of 2048 events the
+    permutation grouping the events by bin and the group offsets.  Above: the SORTED plan (``perm`` = stable order of
+    all events by bin, ``sorted_index`` = index[perm]; ``pisab_hist_accumulate_sorted``)."""
 
     def __init__(self, buf, n, n_bins, index, perm=None, sorted_index=None):
         self.buf, self.n, self.n_bins = buf, int(n), int(n_bins)

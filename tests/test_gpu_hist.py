@@ -376,12 +376,13 @@ def test_fused_kernel_other_bin_counts(n_bins):
 
 
 @pytest.mark.parametrize("n,n_bins", [(0, 128), (1, 1), (2048, 128), (2049, 7), (4095, 129), (300_001, 128),
-                                      (1_000_003, 256)])
+                                      (1_000_003, 256), (5000, 257), (400_001, 400), (300_007, 513), (700_001, 1024)])
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_planned_histogram_vs_oracle(n, n_bins, dtype):
     """pisab_hist_plan_build + pisab_hist_accumulate_planned (bin-sorted tiles, one thread per bin): empty, single,
-    tile-boundary and ragged sizes, out-of-range indices dropped, a hot bin, both storage types; identical bits run
-    to run; the plan is refused for a different index length and is not offered above 256 bins."""
+    tile-boundary and ragged sizes, out-of-range indices dropped, a hot bin, both storage types, one / two / four
+    bins per thread (up to 1024 bins); identical bits run to run; the plan is refused for a different index length;
+    above 1024 bins ``hist_plan`` returns the sorted plan instead."""
     from pisa_b200 import ops
     dev = _dev()
     rng = np.random.default_rng(n + n_bins)
@@ -411,7 +412,8 @@ def test_planned_histogram_vs_oracle(n, n_bins, dtype):
     if n > 1:
         with pytest.raises(ValueError):
             ops.hist_accumulate(ti[1:].contiguous(), tw[1:].contiguous(), n_bins, plan=plan)
-    assert ops.hist_plan(ti, 257) is None
+    big = ops.hist_plan(ti, 1025)
+    assert big is not None and big.perm is not None and big.buf is None
 
 
 def test_large_binning_is_exact_and_order_independent():
