@@ -37,9 +37,10 @@ struct WarpHist {
         for (int i = threadIdx.x; i < total; i += blockDim.x) all[i] = 0.0;
         __syncthreads();
     }
-    // Warp-collective: all 32 lanes must call (bin < 0 = nothing to add).
+    // Warp-collective: all 32 lanes must call (a bin outside [0, n_bins) = nothing to add).
     __device__ __forceinline__ void add(int bin, double w) {
         const int lane = threadIdx.x & 31;
+        if ((unsigned)bin >= (unsigned)n_bins) bin = -1;
         __syncwarp();
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
         stage[lane] = w;

@@ -19,7 +19,7 @@ n = 100_000_000
 g = torch.Generator(device=dev); g.manual_seed(1)
 for dtype, wb in ((torch.float64, 8), (torch.float32, 4)):
     w = torch.rand(n, generator=g, device=dev, dtype=torch.float64).to(dtype)
-    for n_bins in (128, 256):
+    for n_bins in (128, 256, 512, 1024):
         idx = torch.randint(-1, n_bins, (n,), generator=g, device=dev, dtype=torch.int32)
         t_slot = timeit(lambda: ops.hist_accumulate(idx, w, n_bins))
         t_plan_build = timeit(lambda: ops.hist_plan(idx, n_bins), reps=2)

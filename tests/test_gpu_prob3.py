@@ -133,6 +133,50 @@ def test_large_random_sample_vs_oracle(nubar):
     assert float((p2.sum(dim=2) - 1).abs().max()) < 5e-12
 
 
+def test_random_parameter_points_vs_oracle():
+    """40 random hypotheses -- mixing angles, both mass orderings, deltacp, standard NSI on every other point (complex
+    off-diagonal epsilons), three PREM files of the reference (the 59-layer one exceeds the reference kernel's 120-layer array), detector depth / production height, electron
+    fractions, nu and nubar -- each over 20 000 events from 0.5 GeV to 2 TeV, against the oracle: full matrix and the
+    row outputs, the reference's AC_KW on every probability."""
+    from pisa_b200 import ops
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    rng = np.random.default_rng(2026)
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    worst = 0.0
+    for point in range(40):
+        params = dict(theta12=rng.uniform(25, 40), theta13=rng.uniform(5, 12), theta23=rng.uniform(35, 55),
+                      deltacp=rng.uniform(0, 360), deltam21=rng.uniform(6e-5, 9e-5),
+                      deltam31=rng.uniform(2e-3, 3e-3) * rng.choice([1.0, -1.0]))
+        nsi = None
+        if point % 2:
+            nsi = dict(eps_ee=rng.uniform(-0.3, 0.3), eps_mumu=rng.uniform(-0.1, 0.1), eps_tautau=rng.uniform(-0.1, 0.1),
+                       eps_emu=(rng.uniform(0, 0.2), rng.uniform(0, 360)), eps_etau=(rng.uniform(0, 0.2), rng.uniform(0, 360)),
+                       eps_mutau=(rng.uniform(0, 0.05), rng.uniform(0, 360)))
+        dm, mix, mat_pot = syn.osc_matrices(params, nsi=nsi)
+        consts = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+        prem = os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_%dlayer.dat" % rng.choice([4, 10, 12]))
+        L, earth = _earth(prem, depth=rng.uniform(0.5, 2.0), height=rng.uniform(10.0, 30.0),
+                          ye=(rng.uniform(0.44, 0.48), rng.uniform(0.44, 0.48), rng.uniform(0.48, 0.51)))
+        n = 20_000
+        energy = 10 ** rng.uniform(np.log10(0.5), np.log10(2000.0), n)
+        coszen = rng.uniform(-1, 1, n)
+        nubar = int(rng.choice([1, -1]))
+        _, den, dis = L.calcLayers(coszen)
+        ref = oracle.propagate_array(dm, mix, mat_pot, -1, zero, np.zeros((3, 3)), nubar, energy, den, dis,
+                                     n_threads=os.cpu_count())
+        e, cz = torch.tensor(energy, device=dev), torch.tensor(coszen, device=dev)
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+        what = "point %d %s nsi=%s nubar=%d %s" % (point, params, nsi is not None, nubar, os.path.basename(prem))
+        _assert_prob(full.cpu().numpy(), ref, what)
+        flav = int(rng.integers(0, 3))
+        _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=flav, want_probability=False)
+        _assert_prob(pe.cpu().numpy(), ref[:, 0, flav], what + " prob_e")
+        _assert_prob(pmu.cpu().numpy(), ref[:, 1, flav], what + " prob_mu")
+        worst = max(worst, float(np.abs(full.cpu().numpy() - ref).max()))
+    assert worst < 2e-12, worst
+
+
 @pytest.mark.parametrize("nubar", [1, -1])
 def test_large_random_sample_standard_matter_vs_oracle(nubar):
     """1e6 seeded events through the standard-matter specialisation (no NSI: the path the headline benchmark takes),
