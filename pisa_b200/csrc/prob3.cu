@@ -928,7 +928,10 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         const int64_t by_work = (n_units + (int64_t)block * unit_min - 1) / ((int64_t)block * unit_min);
         const int64_t by_thread = (n_units + block - 1) / block;
         int64_t r = by_work;
-        const int64_t cap = ((int64_t)resident * PISAB_SPREAD_WAVES + nc - 1) / nc;
+        // (rounded down: 790 x 12 = 9480 blocks on 296 slots would leave 8 blocks for a 33rd wave)
+        // (measured flat between 16 and 64 waves once the count is whole: 9.29 / 9.33 / 9.31 / 9.30 / 9.27e9 events/s at
+        // 16 / 24 / 32 / 48 / 64; the rounding itself is worth 1.1 %)
+        const int64_t cap = (int64_t)resident * PISAB_SPREAD_WAVES / nc > 0 ? (int64_t)resident * PISAB_SPREAD_WAVES / nc : 1;
         if (r > cap) r = cap;
         // one resident wave spread over the containers -- rounded DOWN: a grid of 300 blocks on 296 resident slots
         // runs as two waves and doubles the time of an analysis-size template
