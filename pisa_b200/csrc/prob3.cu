@@ -479,7 +479,8 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
 constexpr int kPairBlock = PISAB_PAIR_BLOCK;
 static size_t fused_pair_smem_bytes(int n_bins) {
     return WarpHist::smem_bytes(kPairBlock, n_bins) +
-           (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48);
+           (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48) +
+           (size_t)(kPairBlock / 32) * 32 * sizeof(double); // second staging row of WarpHist::add2
 }
 
 template <bool STD, bool FLUX, bool MIX>
@@ -496,6 +497,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     float4 *s_flux = reinterpret_cast<float4 *>(s_dyn);
     float2 *s_e = reinterpret_cast<float2 *>(s_flux + kPairBlock), *s_cz = s_e + kPairBlock, *s_w = s_cz + kPairBlock;
     int2 *s_bin = reinterpret_cast<int2 *>(s_w + kPairBlock);
+    double *s_stage1 = reinterpret_cast<double *>(s_bin + kPairBlock) + (threadIdx.x >> 5) * 32;
     WarpHist wh(s_hist, n_bins);
     const int tid = threadIdx.x;
     const int64_t stride = (int64_t)n_ranks * blockDim.x;
@@ -569,8 +571,7 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
             bin0 = bb.x;
             bin1 = bb.y;
         }
-        wh.add(bin0, w0);
-        wh.add(bin1, w1);
+        wh.add2(bin0, w0, bin1, w1, s_stage1);
         p_cur = p_next;
         p_next = p_nn;
     }
