@@ -29,9 +29,15 @@
  *    on the float32-rounded inputs (tolerance 1e-5 absolute, BASELINE.json),
  *    and the distance to the reference's f4 fixtures is reported beside it.
  *
- * The decay branch (decay_flag == 1 -> numpy.linalg.eigvals,
- * numba_osc_kernels.py:656-685) is out of scope and is
- * rejected with an error code.
+ * The decay branch (decay_flag == 1, numba_osc_kernels.py:445-451,656-685) calls
+ * numpy.linalg.eigvals, i.e. LAPACK zgeev (numpy >= 1.21 bundled OpenBLAS; not
+ * under /root/reference).  It is restated here as what zgeev does for the
+ * eigenvalues of a general complex matrix: reduction to upper Hessenberg form
+ * followed by the single-shift (Wilkinson) QR iteration with deflation
+ * (eigvals3 below).  The order of the eigenvalues is not part of the contract:
+ * the Lagrange sum of get_transition_matrix_massbasis is symmetric in them.
+ * Pinned against the reference's nufit32_std_decay pickles and against
+ * outputs of the unmodified reference (tests/golden/ref_decay_f8.npz).
  */
 #include <math.h>
 #include <stddef.h>
@@ -67,6 +73,19 @@ static inline cplx c_mul(cplx a, cplx b) {
     return c_make(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
 }
 static inline cplx c_conj(cplx a) { return c_make(a.re, -a.im); }
+/* complex division as numba / CPython do it (Smith's method, _Py_c_quot); with b.im == 0 this is
+ * the per-component real division */
+static inline cplx c_div(cplx a, cplx b) {
+    real_t abs_breal = b.re < 0 ? -b.re : b.re, abs_bimag = b.im < 0 ? -b.im : b.im;
+    if (abs_breal >= abs_bimag) {
+        if (abs_breal == (real_t)0) return c_make((real_t)NAN, (real_t)NAN);
+        real_t ratio = b.im / b.re, denom = b.re + b.im * ratio;
+        return c_make((a.re + a.im * ratio) / denom, (a.im - a.re * ratio) / denom);
+    } else {
+        real_t ratio = b.re / b.im, denom = b.re * ratio + b.im;
+        return c_make((a.re * ratio + a.im) / denom, (a.im * ratio - a.re) / denom);
+    }
+}
 /* numba promotes a real factor to (x + 0j) before multiplying */
 static inline cplx c_rmul(real_t x, cplx a) { return c_mul(c_make(x, (real_t)0), a); }
 
@@ -104,6 +123,114 @@ void SUFFIX(oracle_get_H_mat)(real_t rho, const cplx mat_pot[3][3], int64_t nuba
             if (nubar == -1) H_mat[i][j] = c_rmul(-a, c_conj(mat_pot[i][j]));
             else if (nubar == 1) H_mat[i][j] = c_rmul(a, mat_pot[i][j]);
         }
+}
+
+/* numba_osc_kernels.py:571-603 get_H_decay */
+void SUFFIX(oracle_get_H_decay)(const cplx mix[3][3], const cplx mix_ct[3][3],
+                                const cplx mat_decay[3][3], cplx H_decay[3][3]) {
+    cplx tmp[3][3];
+    mat_mul(mat_decay, mix_ct, tmp);
+    mat_mul(mix, tmp, H_decay);
+}
+
+/* numpy.linalg.eigvals of a general complex 3x3 (LAPACK zgeev: zgehrd + zhseqr, eigenvalues only):
+ * one Givens similarity brings A to upper Hessenberg form, then shifted QR steps on the active block
+ * [lo..hi] with the Wilkinson shift (the eigenvalue of the trailing 2x2 closer to its last diagonal
+ * entry) until the last subdiagonal entry is negligible, deflate, repeat. */
+static real_t c_abs1(cplx z) { return R_FABS(z.re) + R_FABS(z.im); }
+static real_t c_abs(cplx z) { return (real_t)hypot((double)z.re, (double)z.im); }
+static cplx c_sqrt(cplx z) {
+    real_t m = c_abs(z);
+    if (m == 0) return c_make(0, 0);
+    real_t a = R_SQRT((real_t)0.5 * (m + R_FABS(z.re)));
+    real_t b = (real_t)0.5 * z.im / a;
+    if (z.re >= 0) return c_make(a, b);
+    return c_make(R_FABS(b), z.im < 0 ? -a : a);
+}
+/* Givens rotation G = [[c, s], [-conj(s), c]] (c real) with G (f, g)^T = (r, 0)^T */
+static void givens(cplx f, cplx g, real_t *c, cplx *s) {
+    real_t ng = c_abs(g), nf = c_abs(f);
+    if (ng == 0) { *c = 1; *s = c_make(0, 0); return; }
+    if (nf == 0) { *c = 0; *s = c_make(1, 0); return; } /* any unit s; r = g up to phase is not needed */
+    real_t nrm = (real_t)hypot((double)nf, (double)ng);
+    *c = nf / nrm;
+    /* s = (f / |f|) conj(g) / nrm */
+    cplx fu = c_make(f.re / nf, f.im / nf);
+    cplx t = c_mul(fu, c_conj(g));
+    *s = c_make(t.re / nrm, t.im / nrm);
+}
+/* rows p, q of H <- G rows ; columns p, q of H <- columns G^H   (similarity) */
+static void rot_rows(cplx H[3][3], int p, int q, real_t c, cplx s, int c0, int c1) {
+    for (int j = c0; j <= c1; ++j) {
+        cplx a = H[p][j], b = H[q][j];
+        H[p][j] = c_add(c_rmul(c, a), c_mul(s, b));
+        H[q][j] = c_sub(c_rmul(c, b), c_mul(c_conj(s), a));
+    }
+}
+static void rot_cols(cplx H[3][3], int p, int q, real_t c, cplx s, int r0, int r1) {
+    for (int i = r0; i <= r1; ++i) {
+        cplx a = H[i][p], b = H[i][q];
+        H[i][p] = c_add(c_rmul(c, a), c_mul(c_conj(s), b));
+        H[i][q] = c_sub(c_rmul(c, b), c_mul(s, a));
+    }
+}
+int SUFFIX(oracle_eigvals3)(const cplx A[3][3], cplx w[3]) {
+    cplx H[3][3];
+    mat_copy(A, H);
+    const real_t eps = sizeof(real_t) == 8 ? (real_t)2.220446049250313e-16 : (real_t)1.1920929e-07;
+    /* Hessenberg: annihilate H[2][0] against H[1][0] */
+    {
+        real_t c; cplx s;
+        givens(H[1][0], H[2][0], &c, &s);
+        rot_rows(H, 1, 2, c, s, 0, 2);
+        rot_cols(H, 1, 2, c, s, 0, 2);
+        H[2][0] = c_make(0, 0);
+    }
+    int hi = 2, iter = 0;
+    while (hi >= 0) {
+        int lo = hi;
+        while (lo > 0) {
+            real_t sd = c_abs1(H[lo][lo - 1]);
+            real_t dd = c_abs1(H[lo][lo]) + c_abs1(H[lo - 1][lo - 1]);
+            if (sd <= eps * dd || sd == 0) { H[lo][lo - 1] = c_make(0, 0); break; }
+            --lo;
+        }
+        if (lo == hi) { w[hi] = H[hi][hi]; --hi; iter = 0; continue; }
+        if (++iter > 300) return -1;
+        /* Wilkinson shift from [[a, b], [c, d]] = H[hi-1..hi][hi-1..hi] */
+        cplx a = H[hi - 1][hi - 1], b = H[hi - 1][hi], c_ = H[hi][hi - 1], d = H[hi][hi];
+        cplx half_diff = c_rmul((real_t)0.5, c_sub(a, d));
+        cplx disc = c_sqrt(c_add(c_mul(half_diff, half_diff), c_mul(b, c_)));
+        cplx mean = c_rmul((real_t)0.5, c_add(a, d));
+        cplx e1 = c_add(mean, disc), e2 = c_sub(mean, disc);
+        cplx mu = c_abs(c_sub(e1, d)) <= c_abs(c_sub(e2, d)) ? e1 : e2;
+        if (iter % 10 == 0) mu = c_add(mu, c_make(c_abs1(c_), 0)); /* exceptional shift */
+        /* QR step on the active block: H - mu = QR, H <- RQ + mu */
+        for (int i = lo; i <= hi; ++i) H[i][i] = c_sub(H[i][i], mu);
+        real_t cs[2]; cplx ss[2];
+        for (int k = lo; k < hi; ++k) {
+            givens(H[k][k], H[k + 1][k], &cs[k - lo], &ss[k - lo]);
+            rot_rows(H, k, k + 1, cs[k - lo], ss[k - lo], k, hi);
+            H[k + 1][k] = c_make(0, 0);
+        }
+        for (int k = lo; k < hi; ++k) rot_cols(H, k, k + 1, cs[k - lo], ss[k - lo], lo, k + 1 < hi ? k + 2 : hi);
+        for (int i = lo; i <= hi; ++i) H[i][i] = c_add(H[i][i], mu);
+    }
+    return 0;
+}
+
+/* numba_osc_kernels.py:656-685 get_dms_numerical */
+int SUFFIX(oracle_get_dms_numerical)(real_t energy, const cplx H[3][3], cplx dm_mat_mat[3][3],
+                                     cplx dm_mat[3][3]) {
+    cplx w[3], m[3];
+    if (SUFFIX(oracle_eigvals3)(H, w)) return -1;
+    for (int i = 0; i < 3; ++i) m[i] = c_rmul((real_t)2.0 * energy, w[i]);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            dm_mat_mat[i][j] = c_sub(m[i], m[j]);
+            dm_mat[i][j] = m[i];
+        }
+    return 0;
 }
 
 /* numba_osc_kernels.py:687-831 get_dms */
@@ -191,7 +318,7 @@ void SUFFIX(oracle_get_product)(real_t energy, const cplx dm_mat[3][3], const cp
                 if (i == j) HmM[i][j][k] = c_sub(HmM[i][j][k], dm_mat[k][j]);
                 product[i][j][k] = c_make(0, 0);
             }
-    /* denominators are complex products of real-valued complex numbers */
+    /* denominators: complex products (real-valued without decay, where c_div is the per-component division) */
     cplx d0 = c_mul(dm_mat_mat[0][1], dm_mat_mat[0][2]);
     cplx d1 = c_mul(dm_mat_mat[1][2], dm_mat_mat[1][0]);
     cplx d2 = c_mul(dm_mat_mat[2][0], dm_mat_mat[2][1]);
@@ -202,10 +329,9 @@ void SUFFIX(oracle_get_product)(real_t energy, const cplx dm_mat[3][3], const cp
                 product[i][j][1] = c_add(product[i][j][1], c_mul(HmM[i][k][2], HmM[k][j][0]));
                 product[i][j][2] = c_add(product[i][j][2], c_mul(HmM[i][k][0], HmM[k][j][1]));
             }
-            /* CPython/numba complex division with a zero imaginary divisor */
-            product[i][j][0] = c_make(product[i][j][0].re / d0.re, product[i][j][0].im / d0.re);
-            product[i][j][1] = c_make(product[i][j][1].re / d1.re, product[i][j][1].im / d1.re);
-            product[i][j][2] = c_make(product[i][j][2].re / d2.re, product[i][j][2].im / d2.re);
+            product[i][j][0] = c_div(product[i][j][0], d0);
+            product[i][j][1] = c_div(product[i][j][1], d1);
+            product[i][j][2] = c_div(product[i][j][2], d2);
         }
 }
 
@@ -219,23 +345,25 @@ void SUFFIX(oracle_get_transition_matrix_massbasis)(real_t baseline, real_t ener
     SUFFIX(oracle_get_product)(energy, dm_mat, dm_mat_mat, Hm, product);
     const real_t hbar_c_factor = (real_t)2.534;
     for (int k = 0; k < 3; ++k) {
-        /* -dm_mat[k,0] is complex; (z * real) * real keeps the imaginary part 0 */
-        real_t arg = -dm_mat[k][0].re * (baseline / energy) * hbar_c_factor;
-        cplx c = c_make(R_COS(arg), R_SIN(arg)); /* cmath.exp(arg*1j) */
+        /* arg = -dm_mat[k,0] * (baseline / energy) * hbar_c_factor is complex (imaginary part 0 without decay);
+         * c = cmath.exp(arg * 1j) = exp(-Im arg) (cos(Re arg) + i sin(Re arg)) */
+        real_t boe = baseline / energy;
+        real_t arg = -dm_mat[k][0].re * boe * hbar_c_factor;
+        real_t arg_im = -dm_mat[k][0].im * boe * hbar_c_factor;
+        cplx c = c_make(R_COS(arg), R_SIN(arg));
+        if (arg_im != 0) { real_t damp = (real_t)exp((double)-arg_im); c = c_make(damp * c.re, damp * c.im); }
         for (int i = 0; i < 3; ++i)
             for (int j = 0; j < 3; ++j) T[i][j] = c_add(T[i][j], c_mul(c, product[i][j][k]));
     }
 }
 
-/* numba_osc_kernels.py:348-478 get_transition_matrix (decay_flag != 1 branch) */
+/* numba_osc_kernels.py:348-478 get_transition_matrix */
 int SUFFIX(oracle_get_transition_matrix)(int64_t nubar, real_t energy, real_t rho, real_t baseline,
                                          const cplx mix_nubar[3][3], const cplx mix_nubar_ct[3][3],
                                          const cplx mat_pot[3][3], const cplx H_vac[3][3],
                                          int64_t decay_flag, const cplx H_decay[3][3],
                                          const real_t lri_pot[3][3], const real_t dm[3][3],
                                          cplx T[3][3]) {
-    (void)H_decay;
-    if (decay_flag == 1) return -2; /* eigvals branch: out of scope */
     cplx H_mat[3][3], dm_mat[3][3], dm_mat_mat[3][3], H_full[3][3], tmp[3][3], Hm[3][3];
     SUFFIX(oracle_get_H_mat)(rho, mat_pot, nubar, H_mat);
     for (int i = 0; i < 3; ++i)
@@ -244,10 +372,17 @@ int SUFFIX(oracle_get_transition_matrix)(int64_t nubar, real_t energy, real_t rh
             else if (nubar < 0) H_mat[i][j].re = H_mat[i][j].re - lri_pot[i][j] * (real_t)1e9;
         }
     real_t one_over_two_e = (real_t)0.5 / energy;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j)
-            H_full[i][j] = c_add(c_mul(H_vac[i][j], c_make(one_over_two_e, 0)), H_mat[i][j]);
-    SUFFIX(oracle_get_dms)(energy, H_full, dm, dm_mat_mat, dm_mat);
+    if (decay_flag == 1) { /* :445-451 */
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                H_full[i][j] = c_add(c_mul(c_add(H_vac[i][j], H_decay[i][j]), c_make(one_over_two_e, 0)), H_mat[i][j]);
+        if (SUFFIX(oracle_get_dms_numerical)(energy, H_full, dm_mat_mat, dm_mat)) return -4;
+    } else {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                H_full[i][j] = c_add(c_mul(H_vac[i][j], c_make(one_over_two_e, 0)), H_mat[i][j]);
+        SUFFIX(oracle_get_dms)(energy, H_full, dm, dm_mat_mat, dm_mat);
+    }
     mat_mul(H_full, mix_nubar, tmp);
     mat_mul(mix_nubar_ct, tmp, Hm);
     SUFFIX(oracle_get_transition_matrix_massbasis)(baseline, energy, dm_mat, dm_mat_mat, Hm, T);
@@ -261,11 +396,7 @@ int SUFFIX(oracle_osc_probs_layers)(const real_t dm[3][3], const cplx mix[3][3],
                                     int64_t nubar, real_t energy, const real_t *density,
                                     const real_t *distance, int n_layers, real_t osc_probs[3][3]) {
     cplx H_vac[3][3], H_decay[3][3], mixn[3][3], mixn_ct[3][3], prod[3][3], T[3][3], tmp[3][3];
-    static const cplx zero9[3][3];
-    (void)mat_decay;
     if (n_layers > MAX_LAYERS) return -3;
-    if (decay_flag == 1) return -2;
-    mat_copy(zero9, H_decay); /* get_H_decay of a matrix that is only used when decay_flag==1 */
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             mixn[i][j] = nubar > 0 ? mix[i][j] : c_conj(mix[i][j]);
@@ -274,6 +405,7 @@ int SUFFIX(oracle_osc_probs_layers)(const real_t dm[3][3], const cplx mix[3][3],
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) mixn_ct[j][i] = c_conj(mixn[i][j]);
     SUFFIX(oracle_get_H_vac)(mixn, mixn_ct, dm, H_vac);
+    SUFFIX(oracle_get_H_decay)(mixn, mixn_ct, mat_decay, H_decay); /* :220 (only read when decay_flag == 1) */
 
     cplx Ts[MAX_LAYERS][3][3];
     for (int i = 0; i < n_layers; ++i) {

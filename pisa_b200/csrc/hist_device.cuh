@@ -41,7 +41,7 @@ struct WarpHist {
     __device__ __forceinline__ void add(int bin, double w) {
         const int lane = threadIdx.x & 31;
         if ((unsigned)bin >= (unsigned)n_bins) bin = -1;
-        __syncwarp();
+        // (no barrier here: every add ends with one, and clear() ends with a block barrier)
         const unsigned peers = __match_any_sync(0xffffffffu, bin);
         stage[lane] = w;
         __syncwarp();
@@ -68,7 +68,6 @@ struct WarpHist {
         const int lane = threadIdx.x & 31;
         if ((unsigned)bin0 >= (unsigned)n_bins) bin0 = -1;
         if ((unsigned)bin1 >= (unsigned)n_bins) bin1 = -1;
-        __syncwarp();
         const unsigned p0 = __match_any_sync(0xffffffffu, bin0), p1 = __match_any_sync(0xffffffffu, bin1);
         stage[lane] = w0;
         stage1[lane] = w1;
