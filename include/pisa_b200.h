@@ -39,9 +39,10 @@ enum {
     PISAB_OK = 0,
     PISAB_ERR_ARG = 1,         /* bad argument (null pointer, negative size, ...)             */
     PISAB_ERR_CUDA = 2,        /* CUDA runtime error; text in pisab_last_error()              */
-    PISAB_ERR_UNSUPPORTED = 3, /* branch of the reference that is out of scope (decay_flag=1, */
-                               /* non-Hermitian potential, Earth geometry the reference       */
-                               /* itself cannot process)                                      */
+    PISAB_ERR_UNSUPPORTED = 3, /* branch of the reference that is out of scope (non-Hermitian */
+                               /* matter potential, Earth geometry the reference itself       */
+                               /* cannot process) or a combination an entry point does not    */
+                               /* fuse (text in pisab_last_error())                           */
     PISAB_ERR_WORKSPACE = 4    /* caller-provided workspace too small                         */
 };
 
@@ -51,9 +52,14 @@ typedef struct pisab_osc_consts {
     double dm[9];         /* dm[i][j] = m_i^2 - m_j^2 (eV^2), OscParams.dm_matrix            */
     double mix[18];       /* PMNS matrix (un-conjugated; nubar handling is internal)         */
     double mat_pot[18];   /* generalised matter potential / a, diag(1|1.02,0,0) + eps        */
-    double mat_decay[18]; /* accepted for signature parity; only read when decay_flag == 1    */
+    double mat_decay[18]; /* decay matrix in the mass basis (eV^2), DecayParams.decay_matrix =  */
+                          /* diag(0, 0, -i alpha3); read when decay_flag == 1                 */
     double lri_pot[9];    /* long-range-interaction potential (eV), real symmetric            */
-    int64_t decay_flag;   /* -1 = standard oscillations (supported); +1 = decay (rejected)    */
+    int64_t decay_flag;   /* +1 = oscillations + neutrino decay (numba_osc_kernels.py:445-451, */
+                          /* the numpy.linalg.eigvals branch: general-matrix kernels, FP64     */
+                          /* arithmetic whatever the storage type; one template per launch,    */
+                          /* so the multi-template scan entry points reject it);               */
+                          /* any other value (-1 in the reference) = standard oscillations     */
 } pisab_osc_consts_t;
 
 /* What `Layers` holds after __init__/setElecFrac (layers.py:216-289,308-335):

@@ -74,6 +74,13 @@ struct OscTable {
 
 static_assert(sizeof(OscTable) == 464, "OscTable feeds the static shared memory of the scan kernel: see the note above");
 
+// Neutrino decay (decay_flag == 1): 0.5 * U G U^dagger as a full complex 3x3 (row-major, re/im), [0] with
+// G = mat_decay (neutrinos), [1] with G = -conj(mat_decay) (antineutrinos through the neutrino code, see tables.cu).
+// Passed to the decay kernels only (prob3_decay.cuh); the standard kernels never see it.
+struct DecayTable {
+    double hd[2][3][3][2];
+};
+
 struct EarthTable {
     int n_radii;
     int idx_first_inner; // first shell with radius < r_detector (layers.py:91)
@@ -86,5 +93,6 @@ struct EarthTable {
 
 int build_osc_table(const pisab_osc_consts_t *c, OscTable *out);
 int build_earth_table(const pisab_earth_t *e, EarthTable *out);
+int build_decay_table(const pisab_osc_consts_t *c, DecayTable *out);
 
 } // namespace pisab

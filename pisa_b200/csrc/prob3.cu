@@ -8,6 +8,7 @@
 
 #include "flux_device.cuh"
 #include "hist_device.cuh"
+#include "prob3_decay.cuh"
 #include "prob3_walk.cuh"
 
 namespace pisab {
@@ -208,6 +209,102 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
     }
 }
 
+// ---- neutrino decay (decay_flag == 1, prob3_decay.cuh): the same two entry points with the general-matrix layer ----
+// One thread per event, state in registers / local memory, plain loads: this branch is an analysis option outside the
+// fit-loop default and is not tuned (one block per SM-quarter is plenty to hide its latencies).
+constexpr int kDecayBlock = 128;
+
+template <typename IO, bool FULL>
+__global__ void __launch_bounds__(kDecayBlock)
+prob3_earth_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec,
+                         const __grid_constant__ EarthTable earth, int nubar, const int32_t *__restrict__ d_nubar,
+                         int flav, const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
+                         const IO *__restrict__ coszen, int64_t n, IO *__restrict__ probability,
+                         IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
+    constexpr int NR = FULL ? 3 : 1, NC = FULL ? 3 : 2;
+    __shared__ EarthTable s_earth;
+    copy_earth(earth, &s_earth);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = ld(energy, i), cz = ld(coszen, i);
+        const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
+        const int fl = d_flav ? __ldg(d_flav + i) : flav;
+        const double inv_e = 1.0 / e;
+        H0Decay h0;
+        h0.init(herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr), dec, nb, inv_e);
+        Propagator<NR, NC> P;
+        propagate_earth<NR, NC, false>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
+        if (FULL) {
+            IO *o = probability + i * 9;
+#pragma unroll
+            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) o[a * 3 + b] = (IO)P.prob(b, a);
+        } else {
+            prob_e[i] = (IO)P.prob(0, 0);
+            prob_mu[i] = (IO)P.prob(0, 1);
+        }
+    }
+}
+
+// propagate_array with decay_flag == 1 on explicit layers; same layer-cache rule as prob3_layers_kernel
+template <typename IO>
+__global__ void __launch_bounds__(kDecayBlock)
+prob3_layers_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec, int nubar,
+                          const int32_t *__restrict__ d_nubar, const IO *__restrict__ energy,
+                          const IO *__restrict__ densities, const IO *__restrict__ distances, int64_t n,
+                          int n_layers, IO *__restrict__ probability) {
+    const double T_SCALE = kTab[18];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double e = ld(energy, i);
+        const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
+        const double inv_e = 1.0 / e;
+        H0Decay h0;
+        h0.init(herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr), dec, nb, inv_e);
+        const IO *rho = densities + i * n_layers;
+        const IO *dist = distances + i * n_layers;
+        Cplx M[3][3];
+        bool first = true;
+        for (int l = 0; l < n_layers; ++l) {
+            IO d = __ldg(dist + l);
+            if (!(d > (IO)0)) continue;
+            IO r = __ldg(rho + l);
+            int src = l;
+            for (;;) {
+                int hit = -1;
+                const IO rs = __ldg(rho + src), ds = __ldg(dist + src);
+                for (int j = 0; j < src; ++j)
+                    if (fabs((double)(__ldg(rho + j) - rs)) < 1e-5 && fabs((double)(__ldg(dist + j) - ds)) < 1e-5 &&
+                        __ldg(dist + j) > (IO)0)
+                        hit = j;
+                if (hit < 0) break;
+                src = hit;
+            }
+            if (src != l) { r = __ldg(rho + src); d = __ldg(dist + src); }
+            Mat3 T;
+            h0.layer((double)r, osc.vm, T_SCALE * (double)d, T);
+            if (first) {
+#pragma unroll
+                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                    for (int b = 0; b < 3; ++b) M[b][a] = T[a][b];
+                first = false;
+            } else {
+                times_right<3>(T, M);
+            }
+        }
+        IO *o = probability + i * 9;
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) {
+                const Cplx z = first ? Cplx{0.0, 0.0} : M[a][b];
+                o[a * 3 + b] = (IO)fma(z.re, z.re, z.im * z.im);
+            }
+    }
+}
+
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
 static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false) {
@@ -271,13 +368,15 @@ struct FusedBatch {
 // blocks per SM already use all of the shared memory -- so they are prefetched into L2 at the top of the event and
 // loaded after the propagation, when the registers are free; an L2 hit per ~16k-cycle event is hidden by the other
 // warps.
-template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false, bool FLUX = false>
+// DECAY (decay_flag == 1): the general-matrix layers of prob3_decay.cuh with the state in registers; `dec` is the
+// launch's DecayTable.  Everything around the propagation (staging, weights, histogram) is the common code.
+template <typename IO, bool STD, bool PLAIN, bool MP = false, bool LARGE = false, bool FLUX = false, bool DECAY = false>
 __device__ __forceinline__ void fused_template_body(const OscTable &osc, const EarthTable &s_earth,
                                                     const FusedBatch<IO> &batch, int ci_begin, int ci_end,
                                                     int rank, int n_ranks, double *__restrict__ partials,
                                                     double *s_hist,
                                                     const unsigned long long *__restrict__ bounds = nullptr,
-                                                    int mode = 0) {
+                                                    int mode = 0, const DecayTable *dec = nullptr) {
     // dynamic shared memory: [histogram: warps x (2 n_bins + 32)] [per-thread state 9 x double2 x block]
     // [per-thread h0 (+ invariants + h0^2) x block] [flux 2 x block] [e, cz, w: block each] (IO) [bin: block]
     const int n_bins = batch.n_bins;
@@ -357,7 +456,14 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 const double inv_e = rcp_fast(e);
                 const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
                 double pe, pmu;
-                if constexpr (MP) {
+                if constexpr (DECAY) {
+                    H0Decay h0;
+                    h0.init(hh, *dec, nb, inv_e);
+                    Propagator<1, 2> P;
+                    propagate_earth<1, 2, false>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
+                    pe = P.prob(0, 0);
+                    pmu = P.prob(0, 1);
+                } else if constexpr (MP) {
                     H0MP<STD> h0;
                     h0.init(hh);
                     PropagatorSmemF<1, 2> P{&s_statef[0][tid], kBlock};
@@ -462,6 +568,23 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
                                                          interleave);
     // one hypothesis = one launch: the last block of every container reduces it, the last container sums and scores
     if (!LARGE && epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
+}
+
+// The template kernel of the decay branch: same grid / partials / epilogue contract as reweight_hist_kernel (so the
+// host code after the launch is shared), per-event outputs and in-kernel flux.barr_simple included; one instantiation
+// per storage type, one block of 256 threads per SM (the general-matrix layer wants ~200 registers).
+template <typename IO>
+__global__ void __launch_bounds__(kBlock, 1)
+reweight_hist_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec,
+                           const __grid_constant__ EarthTable earth, const __grid_constant__ FusedBatch<IO> batch,
+                           int ranks, double *__restrict__ partials, const __grid_constant__ FusedEpi epi) {
+    extern __shared__ __align__(16) double s_hist[];
+    __shared__ EarthTable s_earth;
+    copy_earth(earth, &s_earth);
+    const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
+    fused_template_body<IO, false, false, false, false, true, true>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials,
+                                                                    s_hist, nullptr, 0, &dec);
+    if (epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
 // ---- FP32 mode, TWO events per thread (prob3_mp.cuh: the float part of a pair runs in the two lanes of the packed
@@ -718,6 +841,27 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
     if (rc) return rc;
     if (n == 0) return PISAB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    if (consts->decay_flag == 1) {
+        // neutrino decay (numba_osc_kernels.py:445-451): general-matrix layers, FP64 arithmetic whatever the storage
+        DecayTable dt;
+        rc = build_decay_table(consts, &dt);
+        if (rc) return rc;
+        if (d_prob_e && d_probability && d_flav) { set_error("per-event flav with full probability output: call fill_probs per flavour"); return PISAB_ERR_ARG; }
+        const int grid = grid_for(n, 8) * (kBlock / kDecayBlock);
+        LaunchTimer t(s);
+        if (d_probability) {
+            prob3_earth_decay_kernel<IO, true><<<grid, kDecayBlock, 0, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy,
+                                                                          d_coszen, n, d_probability, nullptr, nullptr);
+            note_launch();
+        }
+        if (d_prob_e) {
+            prob3_earth_decay_kernel<IO, false><<<grid, kDecayBlock, 0, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy,
+                                                                           d_coszen, n, nullptr, d_prob_e, d_prob_mu);
+            note_launch();
+        }
+        PISAB_CUDA_CHECK(cudaGetLastError());
+        return PISAB_OK;
+    }
     const bool std_matter = ot.std_matter != 0.0;
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
     if (d_probability) {
@@ -773,7 +917,15 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
     if (rc) return rc;
     if (n == 0) return PISAB_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    {
+    if (consts->decay_flag == 1) {
+        DecayTable dt;
+        rc = build_decay_table(consts, &dt);
+        if (rc) return rc;
+        LaunchTimer t(s);
+        prob3_layers_decay_kernel<IO><<<grid_for(n, 8) * (kBlock / kDecayBlock), kDecayBlock, 0, s>>>(
+            ot, dt, nubar, d_nubar, d_energy, d_densities, d_distances, n, n_layers, d_probability);
+        note_launch();
+    } else {
         LaunchTimer t(s);
         prob3_layers_kernel<IO><<<grid_for(n, 4), kBlock, 0, s>>>(ot, nubar, d_nubar, d_energy, d_densities,
                                                                   d_distances, n, n_layers, d_probability);
@@ -849,6 +1001,60 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
 #else
     const bool std_matter = ot.std_matter != 0.0;
 #endif
+    if (consts->decay_flag == 1) {
+        // Neutrino decay: reweight_hist_decay_kernel, then the common reduction launches.  One block per SM; ranks per
+        // container as in the standard path's multi-wave rule, capped by the partials' workspace.
+        if (large) {
+            set_error("neutrino decay with more than %d bins: use propagate_earth + hist_accumulate", PISAB_DET_MAX_BINS);
+            return PISAB_ERR_UNSUPPORTED;
+        }
+        bool any_flux = false, all_plain = true;
+        for (int c = 0; c < batch.n_containers; ++c) {
+            const FusedContainer<IO> &C = batch.c[c];
+            all_plain = all_plain && !C.d_nubar && !C.d_flav && !C.weights_out && !C.prob_e && !C.prob_mu && !C.astro;
+            if (!(C.flags & PISAB_CONTAINER_FLUX_SYS)) continue;
+            any_flux = true;
+            if (!C.flux_terms || !C.nu_nom || !C.nubar_nom || (uintptr_t)C.flux_terms % 32 != 0 ||
+                (uintptr_t)C.nu_nom % (2 * sizeof(IO)) != 0 || (uintptr_t)C.nubar_nom % (2 * sizeof(IO)) != 0) {
+                set_error("container %d: PISAB_CONTAINER_FLUX_SYS needs d_flux_terms (32-byte aligned) and both nominal fluxes", c);
+                return PISAB_ERR_ARG;
+            }
+        }
+        if (any_flux && (!all_plain || !has_sys)) {
+            set_error(has_sys ? "flux.barr_simple inside the template kernel: only without per-event outputs / astro_weights"
+                              : "PISAB_CONTAINER_FLUX_SYS without a pisab_flux_sys_t");
+            return has_sys ? PISAB_ERR_UNSUPPORTED : PISAB_ERR_ARG;
+        }
+        DecayTable dt;
+        rc = build_decay_table(consts, &dt);
+        if (rc) return rc;
+        auto kernel = reweight_hist_decay_kernel<IO>;
+        const size_t smem = fused_smem_bytes<IO>(n_bins, false, false);
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int sms = sm_count() > 0 ? sm_count() : 148;
+        const int nc = batch.n_containers;
+        int64_t r = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
+        const int64_t cap = (int64_t)sms * 8 / nc > 0 ? (int64_t)sms * 8 / nc : 1;
+        if (r > cap) r = cap;
+        const int64_t fill = sms / nc > 0 ? sms / nc : 1, by_thread = (n_max + kBlock - 1) / kBlock;
+        if (r < fill) r = by_thread < fill ? by_thread : fill;
+        if (r < 1) r = 1;
+        const int ranks = (int)r;
+        {
+            LaunchTimer t(s);
+            kernel<<<ranks * nc, kBlock, smem, s>>>(ot, dt, et, batch, ranks, (double *)d_workspace, FusedEpi{});
+            note_launch();
+        }
+        PISAB_CUDA_CHECK(cudaGetLastError());
+        if (d_batch_out && epi) {
+            unsigned *d_arrive = epilogue_counter(s);
+            if (!d_arrive) { set_error("could not allocate the epilogue arrival counter"); return PISAB_ERR_CUDA; }
+            return hist_reduce_chi2((const double *)d_workspace, ranks, n_bins, nc, epi->d_bin_scales, epi->d_observed,
+                                    d_batch_out, epi->d_total, epi->d_chi2, d_arrive, s);
+        }
+        if (d_batch_out) return hist_reduce_batch((const double *)d_workspace, ranks, n_bins, nc, d_batch_out, s);
+        return hist_reduce_partials((const double *)d_workspace, ranks, n_bins, d_hist, d_hist_w2, s);
+    }
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
     // (large binnings keep no bins in shared memory, only warp_fixed_add's [4][32] words per warp: the size of a
     // 48-bin WarpHist)
@@ -1115,6 +1321,10 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     std::vector<OscTable> tables((size_t)n_templates);
     bool all_std = true;
     for (int t = 0; t < n_templates; ++t) {
+        if (consts[t].decay_flag == 1) {
+            set_error("scan: neutrino decay (decay_flag == 1) is evaluated one template per launch; call pisab_reweight_hist_batch_*");
+            return PISAB_ERR_UNSUPPORTED;
+        }
         const int rc = build_osc_table(consts + t, &tables[t]);
         if (rc) return rc;
         all_std = all_std && tables[t].std_matter != 0.0;

@@ -42,6 +42,13 @@ __device__ __forceinline__ Cplx cfma(Cplx a, Cplx b, Cplx c) { // a*b + c
 
 typedef Cplx Mat3[3][3];
 
+// Per-event Hamiltonian providers whose layers are general (non-Hermitian) matrices specialise this (prob3_decay.cuh);
+// propagate_earth then asks the provider itself for the layer's transition matrix.
+template <typename H0>
+struct is_general_h0 {
+    static constexpr bool value = false;
+};
+
 // ---- numeric building blocks ------------------------------------------------------------------
 // Non-trivial double constants live in __constant__ memory: a DFMA can take a constant-bank
 // operand directly, whereas a 64-bit literal costs two extra MOV/UMOV issue slots per use (ncu on

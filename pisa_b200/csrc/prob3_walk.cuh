@@ -94,7 +94,10 @@ __device__ __forceinline__ void propagate_earth(const H0 &h0, const OscTable &os
         const int rho_shell = (tangent && act == ACT_L) ? idx - 1 : shell;
         if (seg > 0.0) {
             typename PROP::cplx T[3][3];
-            if constexpr (PROP::kF32) {
+            if constexpr (is_general_h0<H0>::value) {
+                // neutrino decay: non-Hermitian layer Hamiltonian, complex eigenvalues (prob3_decay.cuh)
+                h0.layer(E.rho[rho_shell], vm, T_SCALE * seg, T);
+            } else if constexpr (PROP::kF32) {
                 // FP32 mode: eigenvalues and phase arguments in FP64, everything else in float (prob3_mp.cuh)
                 h0.layer(E.rho[rho_shell], vm, T_SCALE * seg, T);
             } else if constexpr (STD) {

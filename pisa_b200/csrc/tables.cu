@@ -38,11 +38,8 @@ static bool is_hermitian(const double m[3][3][2]) {
 
 int build_osc_table(const pisab_osc_consts_t *c, OscTable *out) {
     if (!c || !out) { set_error("null osc consts"); return PISAB_ERR_ARG; }
-    if (c->decay_flag == 1) {
-        // numba_osc_kernels.py:445-451 -> get_dms_numerical (numpy.linalg.eigvals): out of scope
-        set_error("decay_flag == 1 (neutrino decay) is not supported by the B200 path");
-        return PISAB_ERR_UNSUPPORTED;
-    }
+    // decay_flag == 1 selects the decay branch (build_decay_table, prob3_decay.cuh); like the reference
+    // (numba_osc_kernels.py:445-457) every other value means standard oscillations
     double U[3][3][2], V[3][3][2], Lr[3][3][2], Hv[3][3][2];
     memcpy(U, c->mix, sizeof U);
     memcpy(V, c->mat_pot, sizeof V);
@@ -83,12 +80,41 @@ int build_osc_table(const pisab_osc_consts_t *c, OscTable *out) {
     out->hdm31 = 0.5 * d[2];
     bool lr_zero = true;
     for (int i = 0; i < 9; ++i) lr_zero = lr_zero && c->lri_pot[i] == 0.0;
-    out->vac_ok = lr_zero ? 1.0 : 0.0;
+    // (with decay the atmosphere is not a pure phase rotation of the mass states: no shortcut; see build_decay_table)
+    out->vac_ok = (lr_zero && c->decay_flag != 1) ? 1.0 : 0.0;
     {
         const Herm3 &v = out->vm;
         out->std_matter = (v.d1 == 0.0 && v.d2 == 0.0 && v.r01 == 0.0 && v.i01 == 0.0 && v.r02 == 0.0 &&
                            v.i02 == 0.0 && v.r12 == 0.0 && v.i12 == 0.0) ? 1.0 : 0.0;
     }
+    return PISAB_OK;
+}
+
+// H_decay = U mat_decay U^dagger (get_H_decay, numba_osc_kernels.py:571-603), halved like H_vac (one_over_two_e, :443-448).
+// Antineutrinos: the reference propagates conj(U) mat_decay conj(U)^dagger with conj(U), -a conj(V), -lri; as for the
+// standard tables (common.cuh) the same probabilities come from the neutrino code with -hv/E + rho vm + lr and the decay
+// term U (-conj(mat_decay)) U^dagger / 2E.
+int build_decay_table(const pisab_osc_consts_t *c, DecayTable *out) {
+    if (!c || !out) { set_error("null osc consts"); return PISAB_ERR_ARG; }
+    double U[3][3][2], G[3][3][2];
+    memcpy(U, c->mix, sizeof U);
+    memcpy(G, c->mat_decay, sizeof G);
+    for (int which = 0; which < 2; ++which)
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double re = 0, im = 0;
+                for (int k = 0; k < 3; ++k)
+                    for (int l = 0; l < 3; ++l) {
+                        // U[i][k] * g[k][l] * conj(U[j][l]),  g = mat_decay or -conj(mat_decay)
+                        const double gr = which ? -G[k][l][0] : G[k][l][0], gi = G[k][l][1];
+                        const double ar = U[i][k][0], ai = U[i][k][1], br = U[j][l][0], bi = -U[j][l][1];
+                        const double tr = ar * gr - ai * gi, ti = ar * gi + ai * gr;
+                        re += tr * br - ti * bi;
+                        im += tr * bi + ti * br;
+                    }
+                out->hd[which][i][j][0] = 0.5 * re;
+                out->hd[which][i][j][1] = 0.5 * im;
+            }
     return PISAB_OK;
 }
 

@@ -17,13 +17,15 @@ at setup, :406-409) and the propagation (``propagate_array`` :439-450) in one ke
 
 Both NSI parameterisations (:232-254,341-346), the long-range-interaction potential (:272-275,519-520,567-575)
 and the Earth-tomography density scalings (:278-297,368-395,521-537) are host-side parameter -> matrix / density
-work and follow the reference's sequence of calls.  Out of scope (raises at construction): neutrino decay
-(numpy eigvals branch).
+work and follow the reference's sequence of calls.  ``neutrino_decay=True`` (:224-230,256-259,349-351,516-517,561-563) adds
+the ``decay_alpha3`` parameter and sends ``decay_flag = 1`` with ``diag(0, 0, -i alpha3)`` to the library, whose decay
+kernels (csrc/prob3_decay.cuh) evaluate the non-Hermitian layers that the reference hands to ``numpy.linalg.eigvals``.
 """
 import numpy as np
 
 from pisa_b200 import ops
 from pisa_b200.core.stage import Stage
+from pisa_b200.stages.osc.decay_params import DecayParams
 from pisa_b200.stages.osc.layers import Layers
 from pisa_b200.stages.osc.lri_params import LRI_TYPES, LRIParams
 from pisa_b200.stages.osc.nsi_params import StdNSIParams, VacuumLikeNSIParams
@@ -54,9 +56,9 @@ class prob3(Stage):  # pylint: disable=invalid-name
                 raise ValueError('Chosen NSI type "%s" not available! Choose one of %s.' % (nsi_type, NSI_TYPES))
         self.nsi_type = nsi_type
         self.reparam_mix_matrix = reparam_mix_matrix
-        if neutrino_decay:
-            raise NotImplementedError("neutrino decay (numpy.linalg.eigvals branch) is outside the scope of pisa_b200")
-        self.neutrino_decay, self.decay_flag = False, -1
+        self.neutrino_decay = bool(neutrino_decay)
+        self.decay_flag = 1 if neutrino_decay else -1   # :227-230
+        decay_params = ("decay_alpha3",) if neutrino_decay else ()
         lri_params = ()
         if lri_type is not None:
             lri_type = lri_type.strip().lower()
@@ -81,13 +83,14 @@ class prob3(Stage):  # pylint: disable=invalid-name
                           "eps_mumu", "eps_mutau_magn", "eps_mutau_phase", "eps_tautau")
         elif nsi_type == "vacuum-like":
             nsi_params = ("eps_scale", "eps_prime", "phi12", "phi13", "phi23", "alpha1", "alpha2", "deltansi")
-        super().__init__(expected_params=expected_params + nsi_params + lri_params + tomography_params,
+        super().__init__(expected_params=expected_params + nsi_params + decay_params + lri_params + tomography_params,
                          expected_container_keys=expected_container_keys, **std_kwargs)
         self.store_layers = store_layers
         self.layers = None
         self.osc_params = None
         self.nsi_params = None
         self.lri_params = None
+        self.decay_params = None
         self.tomography_params = None
         self.gen_mat_pot_matrix_complex = None
         self.decay_matrix = np.zeros((3, 3), dtype=np.complex128)
@@ -118,6 +121,8 @@ class prob3(Stage):  # pylint: disable=invalid-name
             self.nsi_params = VacuumLikeNSIParams()
         if self.lri_type is not None:
             self.lri_params = LRIParams()
+        if self.neutrino_decay:
+            self.decay_params = DecayParams()
         earth_model = find_resource(self.params.earth_model.value)
         self.YeI = self.params.YeI.value.m_as("dimensionless")
         self.YeO = self.params.YeO.value.m_as("dimensionless")
@@ -199,6 +204,9 @@ class prob3(Stage):  # pylint: disable=invalid-name
         if self.lri_type is not None:                        # :519-520,567-575
             self.lri_params.v_lri = p.v_lri.value.m_as("eV")
             self.lri_pot = self.lri_params.potential_matrix(self.lri_type)
+        if self.neutrino_decay:                              # :516-517,561-563
+            self.decay_params.decay_alpha3 = p.decay_alpha3.value.m_as("eV**2")
+            self.decay_matrix = self.decay_params.decay_matrix
         mix = o.mix_matrix_reparam_complex if self.reparam_mix_matrix else o.mix_matrix_complex
         return ops.OscConsts.from_matrices(o.dm_matrix, mix, self.gen_mat_pot_matrix_complex, self.decay_flag,
                                            self.decay_matrix, self.lri_pot)

@@ -82,6 +82,38 @@ def run_mp(n=200000, nsi=False, nubar=1, lri=None, model="PREM_12layer.dat", see
         print("MP n=%d nsi=%s nubar=%+d lri=%s %s: max|dP| = %.3e" % (n, nsi, nubar, lri is not None, model, worst))
     return worst
 
+def run_decay(n=50000, nsi=False, nubar=1, lri=None, alpha3=1e-4, mat_decay=None, model="PREM_12layer.dat", seed=0, depth=2.0,
+              e_max=3.0):
+    """Decay branch (emu_propagate_decay: prob3_decay.cuh through the Earth walk) against the oracle's restatement of
+    the reference's eigvals branch: max |dP| over the full matrix and the row outputs."""
+    rng = np.random.default_rng(seed)
+    e = 10 ** rng.uniform(0, e_max, n); cz = rng.uniform(-1, 1, n)
+    L = layers_obj(model, depth)
+    dm, mix, mp = syn.osc_matrices(nsi=syn.STD_NSI if nsi else None)
+    md = np.zeros((3, 3), complex)
+    md[2, 2] = -1j * alpha3
+    if mat_decay is not None:
+        md = np.asarray(mat_decay, complex)
+    lr = np.zeros((3, 3)) if lri is None else lri
+    c = OscConsts.from_matrices(dm, mix, mp, 1, md, lr)
+    E = earth_struct(L)
+    prob = np.empty((n, 3, 3)); pe = np.empty(n); pm = np.empty(n)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _, den, dis = L.calcLayers(cz)
+    ref = oracle.propagate_array(dm, mix, mp, 1, md, lr, nubar, e, den, dis, n_threads=8)
+    worst = 0
+    for flav in (0, 1, 2):
+        rc = emu.emu_propagate_decay(ctypes.byref(c), ctypes.byref(E), nubar, flav, vp(e), vp(cz), ctypes.c_int64(n),
+                                     vp(prob) if flav == 0 else None, vp(pe), vp(pm))
+        assert rc == 0
+        if flav == 0:
+            worst = max(worst, np.abs(prob - ref).max())
+        worst = max(worst, np.abs(pe - ref[:, 0, flav]).max(), np.abs(pm - ref[:, 1, flav]).max())
+    print("decay n=%d nsi=%s nubar=%+d lri=%s alpha3=%g %s: max|dP| = %.3e (min row sum %.3f)" % (
+        n, nsi, nubar, lri is not None, alpha3, model, worst, ref.sum(axis=2).min()))
+    return worst
+
+
 def run_pairs(n=100000, nsi=False, nubar=1, seed=0):
     """Two-events-per-thread form of the FP32 mode (emu_propagate_mp_pairs, lane-packed float part) against the
     one-event form on events sorted by the number of crossed shells: returns (all equal-class pairs bit-identical,

@@ -9,6 +9,7 @@
 #define __host__
 #define __global__
 #define __forceinline__ inline
+#define __noinline__
 #define __constant__ static const
 #define __restrict__
 #define __launch_bounds__(...)
@@ -21,6 +22,7 @@ static inline double __dsub_rn(double a, double b) { volatile double r = a - b; 
 static inline double __dsqrt_rn(double a) { return std::sqrt(a); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 using std::fma; using std::fmax; using std::fmin; using std::rint; using std::sqrt;
+// (sincos, exp, cbrt, hypot, atan2 of prob3_decay.cuh: glibc's, declared by <cmath> under _GNU_SOURCE)
 static inline void pisab_emu_sincosf(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 #define __sincosf pisab_emu_sincosf
 struct double2 { double x, y; };

@@ -2,6 +2,7 @@
 #ifndef PISAB_HOST_EMU
 #define PISAB_HOST_EMU
 #endif
+#include "../../pisa_b200/csrc/prob3_decay.cuh"
 #include "../../pisa_b200/csrc/prob3_walk.cuh"
 #include "../../pisa_b200/csrc/tables.cu"
 #include <stdarg.h>
@@ -88,6 +89,33 @@ extern "C" int emu_propagate_mp_pairs(const pisab_osc_consts_t *c, const pisab_e
         const f2 pe = P.prob_r(0, 0), pm = P.prob_r(0, 1);
         prob_e[2 * k] = pe.x; prob_e[2 * k + 1] = pe.y; prob_mu[2 * k] = pm.x; prob_mu[2 * k + 1] = pm.y;
         mismatch[k] = bad ? 1 : 0;
+    }
+    return 0;
+}
+
+// Neutrino decay (prob3_decay.cuh): general-matrix layers through the same Earth walk
+extern "C" int emu_propagate_decay(const pisab_osc_consts_t *c, const pisab_earth_t *e, int nubar, int flav,
+                                   const double *energy, const double *coszen, int64_t n, double *probability,
+                                   double *prob_e, double *prob_mu) {
+    OscTable ot; EarthTable et; DecayTable dt;
+    int rc = build_osc_table(c, &ot); if (rc) return rc;
+    rc = build_earth_table(e, &et); if (rc) return rc;
+    rc = build_decay_table(c, &dt); if (rc) return rc;
+#pragma omp parallel for
+    for (int64_t i = 0; i < n; ++i) {
+        const double inv_e = 1.0 / energy[i];
+        H0Decay h0;
+        h0.init(herm_axpy(nubar > 0 ? inv_e : -inv_e, ot.hv[0], ot.lr), dt, nubar, inv_e);
+        if (probability) {
+            Propagator<3, 3> P;
+            propagate_earth<3, 3, false>(h0, ot, et, coszen[i], inv_e, nubar, 0, P);
+            for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) probability[i * 9 + a * 3 + b] = P.prob(b, a);
+        }
+        if (prob_e) {
+            Propagator<1, 2> P;
+            propagate_earth<1, 2, false>(h0, ot, et, coszen[i], inv_e, nubar, flav, P);
+            prob_e[i] = P.prob(0, 0); prob_mu[i] = P.prob(0, 1);
+        }
     }
     return 0;
 }

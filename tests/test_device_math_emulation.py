@@ -64,3 +64,20 @@ def test_fp32_mode_pairs_are_bit_identical_to_single_events(emu, nsi, nubar):
     flagged."""
     identical, flagged_ok, n_unequal = emu.run_pairs(n=40000, nsi=nsi, nubar=nubar, seed=21)
     assert identical and flagged_ok and n_unequal > 0
+
+
+@pytest.mark.parametrize("nsi,nubar", [(False, 1), (True, -1)])
+def test_decay_math_on_host_matches_oracle(emu, nsi, nubar):
+    """The decay branch (prob3_decay.cuh: complex Cardano + Newton eigenvalues of the non-Hermitian layer, complex
+    Cayley-Hamilton coefficients, damped amplitudes) through the Earth walk against the oracle's restatement of the
+    reference's numpy.linalg.eigvals branch.  Measured 2e-13."""
+    assert emu.run_decay(n=20000, nsi=nsi, nubar=nubar, seed=31) < 1e-11
+
+
+def test_decay_math_on_host_edge_parameters(emu):
+    assert emu.run_decay(n=10000, alpha3=0.0, seed=32) < 1e-11                    # Hermitian input to the general solver
+    assert emu.run_decay(n=10000, alpha3=5e-4, lri=np.diag([1e-14, -1e-14, 0.0]), seed=33) < 1e-11
+    assert emu.run_decay(n=10000, alpha3=1e-3, e_max=4.0, seed=34) < 1e-10         # up to 10 TeV (measured 1.8e-12)
+    general = [[0, 0, 0], [0, -2e-5j, 1e-5 - 1e-5j], [0, 1e-5 + 1e-5j, -1e-4j]]    # a full complex decay matrix
+    assert emu.run_decay(n=10000, mat_decay=general, nubar=-1, seed=35) < 1e-11
+    assert emu.run_decay(n=10000, model="PREM_4layer.dat", depth=10.0, seed=36) < 1e-11

@@ -776,10 +776,42 @@ def _oracle_probs(st, container):
     c = container
     c.representation = "events"
     _, den, dis = L.calcLayers(c["true_coszen"].cpu().numpy())
-    zc = np.zeros((3, 3), dtype=complex)
-    return oracle.propagate_array(o.dm_matrix, o.mix_matrix_complex, st.gen_mat_pot_matrix_complex, -1, zc,
+    return oracle.propagate_array(o.dm_matrix, o.mix_matrix_complex, st.gen_mat_pot_matrix_complex, st.decay_flag,
+                                  np.asarray(st.decay_matrix, dtype=complex),
                                   np.asarray(st.lri_pot, dtype=np.float64), int(c["nubar"]),
                                   c["true_energy"].cpu().numpy(), den, dis)
+
+
+def test_prob3_stage_with_neutrino_decay():
+    """prob3(neutrino_decay=True) (prob3.py:224-230,256-259,516-517,561-563): decay_alpha3 reaches the kernels as
+    diag(0, 0, -i alpha3) with decay_flag = 1; probabilities against the oracle's eigvals branch; apply_function
+    reweights with the damped probabilities; alpha3 = 0 reproduces the standard stage; the parameter can be updated."""
+    _need_gpu()
+    from pisa_b200.core.param import Param
+    from pisa_b200.utils.units import ureg
+    st = _prob3_stage([Param(name="decay_alpha3", value=2.0e-4 * ureg.eV ** 2)], neutrino_decay=True)
+    assert st.decay_flag == 1 and st.decay_matrix[2, 2] == -2.0e-4j
+    plain = _prob3_stage()
+    for c, c0 in zip(st.data, plain.data):
+        prob = _oracle_probs(st, c)
+        flav = int(c["flav"])
+        assert np.allclose(c["probability"].cpu().numpy(), prob, rtol=1e-10, atol=1e-13)
+        assert np.allclose(c["prob_e"].cpu().numpy(), prob[:, 0, flav], rtol=1e-10, atol=1e-13)
+        assert np.allclose(c["prob_mu"].cpu().numpy(), prob[:, 1, flav], rtol=1e-10, atol=1e-13)
+        assert np.abs(c["prob_mu"].cpu().numpy() - c0["prob_mu"].cpu().numpy()).max() > 1e-2
+        nf = c["nu_flux"].cpu().numpy()
+        assert np.allclose(c["weights"].cpu().numpy(), nf[:, 0] * prob[:, 0, flav] + nf[:, 1] * prob[:, 1, flav],
+                           rtol=1e-10, atol=1e-13)
+    zero = _prob3_stage([Param(name="decay_alpha3", value=0.0 * ureg.eV ** 2)], neutrino_decay=True)
+    for c, c0 in zip(zero.data, plain.data):
+        assert np.abs(c["probability"].cpu().numpy() - c0["probability"].cpu().numpy()).max() < 2e-12
+    # a parameter update re-runs compute_function
+    zero.params.decay_alpha3.value = 2.0e-4 * ureg.eV ** 2
+    for c in zero.data:
+        c["weights"] = np.ones(c.size)
+    zero.run()
+    for c, c1 in zip(zero.data, st.data):
+        assert np.array_equal(c["prob_mu"].cpu().numpy(), c1["prob_mu"].cpu().numpy())
 
 
 def test_prob3_stage_vacuum_like_nsi_lri_and_tomography():

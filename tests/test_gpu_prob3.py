@@ -51,8 +51,7 @@ def test_golden_pickles_through_abi():
     dev = _dev()
     g = load_golden("ref_pickles_f8.npz")
     cases = sorted({k.split("/")[1] for k in g.files if k.startswith("propagate_scalar/")})
-    cases = [c for c in cases if c != "nufit32_std_decay"]
-    assert len(cases) == 12
+    assert len(cases) == 13   # incl. nufit32_std_decay: decay_flag = 1, the reference's numpy.linalg.eigvals branch
     for case in cases:
         p = "propagate_scalar/%s/" % case
         consts = ops.OscConsts.from_matrices(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], int(g[p + "decay_flag"]),
@@ -65,17 +64,79 @@ def test_golden_pickles_through_abi():
         assert np.allclose(out, ref, rtol=1e-10, atol=1e-13), (case, np.abs(out - ref).max())
 
 
-def test_decay_branch_is_rejected():
+def test_decay_reference_fixture_events_earth_and_layers():
+    """Neutrino decay (decay_flag = 1): 600 reference events x 12 parameter sets (nu / nubar, deltacp, inverted ordering,
+    NSI + LRI, alpha3 = 0, a general complex decay matrix; tests/golden/make_golden_decay.py) through the in-kernel-layers
+    and the explicit-layers entry points, full matrix and row outputs, at the reference's AC_KW on every entry."""
     from pisa_b200 import ops
-    from pisa_b200._lib import PisabError
     dev = _dev()
-    g = load_golden("ref_pickles_f8.npz")
-    p = "propagate_scalar/nufit32_std_decay/"
-    consts = ops.OscConsts.from_matrices(g[p + "dm"], g[p + "mix"], g[p + "mat_pot"], 1, g[p + "mat_decay"], g[p + "lri_pot"])
-    e = torch.ones(1, dtype=torch.float64, device=dev)
-    with pytest.raises(PisabError):
-        ops.propagate_layers(consts, 1, e, torch.ones((1, 3), dtype=torch.float64, device=dev),
-                             torch.ones((1, 3), dtype=torch.float64, device=dev))
+    g = load_golden("ref_decay_f8.npz")
+    L, earth = _earth()
+    _, den, dis = L.calcLayers(g["coszen"])
+    e = torch.tensor(g["energy"], device=dev)
+    cz = torch.tensor(g["coszen"], device=dev)
+    rho_t, dis_t = torch.tensor(den, device=dev), torch.tensor(dis, device=dev)
+    keys = sorted({k.rsplit("/", 1)[0] for k in g.files if k.endswith("/probability")})
+    assert len(keys) == 12
+    for key in keys:
+        consts = ops.OscConsts.from_matrices(g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], 1, g[key + "/mat_decay"],
+                                             g[key + "/lri_pot"])
+        nubar = int(g[key + "/nubar"])
+        ref = g[key + "/probability"]
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+        _assert_prob(full.cpu().numpy(), ref, key + " earth")
+        lay = ops.propagate_layers(consts, nubar, e, rho_t, dis_t)
+        _assert_prob(lay.cpu().numpy(), ref, key + " layers")
+        for flav in (0, 1, 2):
+            _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=flav, want_probability=False)
+            _assert_prob(pe.cpu().numpy(), ref[:, 0, flav], key + " prob_e")
+            _assert_prob(pmu.cpu().numpy(), ref[:, 1, flav], key + " prob_mu")
+        if "_a0" not in key:
+            assert float(full.sum(dim=2).min()) < 0.9   # the third mass state decays: probability is lost
+
+
+@pytest.mark.parametrize("nubar", [1, -1])
+def test_decay_large_random_sample_vs_oracle(nubar):
+    """2e5 seeded events with decay + NSI + deltacp against the oracle's eigvals branch (pinned to the reference by
+    tests/test_oracle_golden.py), the per-event nubar form, float storage, and two size-independent properties on
+    1e6 events: alpha3 = 0 through the decay kernels equals the standard kernels, and decay only removes probability."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_decay_f8.npz")
+    key = "nufit20_nh_dcp306_stdnsi_a2e-4/nu"
+    dm, mix, mat_pot, md = g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"], g[key + "/mat_decay"]
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, md)
+    L, earth = _earth()
+    rng = np.random.default_rng(3)
+    n = 200_000
+    energy = 10 ** rng.uniform(0, 3, n)
+    coszen = rng.uniform(-1, 1, n)
+    _, den, dis = L.calcLayers(coszen)
+    ref = oracle.propagate_array(dm, mix, mat_pot, 1, md, np.zeros((3, 3)), nubar, energy, den, dis,
+                                 n_threads=os.cpu_count())
+    e_t, c_t = torch.tensor(energy, device=dev), torch.tensor(coszen, device=dev)
+    full, _, _ = ops.propagate_earth(consts, earth, nubar, e_t, c_t)
+    _assert_prob(full.cpu().numpy(), ref, "decay random %d" % nubar)
+    # float storage: FP64 arithmetic on float32-rounded inputs, results rounded to float
+    e32, c32 = e_t.float(), c_t.float()
+    _, den32, dis32 = L.calcLayers(c32.cpu().numpy().astype(np.float64))
+    ref32 = oracle.propagate_array(dm, mix, mat_pot, 1, md, np.zeros((3, 3)), nubar, e32.cpu().numpy().astype(np.float64),
+                                   den32, dis32, n_threads=os.cpu_count())
+    full32, _, _ = ops.propagate_earth(consts, earth, nubar, e32, c32)
+    assert full32.dtype == torch.float32
+    assert np.abs(full32.cpu().numpy() - ref32).max() < 1e-6
+    # alpha3 = 0: the general-matrix kernels on a Hermitian problem == the standard kernels
+    n2 = 1_000_000
+    e2 = torch.tensor(10 ** rng.uniform(0, 3, n2), device=dev)
+    c2 = torch.tensor(rng.uniform(-1, 1, n2), device=dev)
+    zero = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, np.zeros((3, 3), dtype=complex))
+    std = ops.OscConsts.from_matrices(dm, mix, mat_pot)
+    p0, _, _ = ops.propagate_earth(zero, earth, nubar, e2, c2)
+    ps, _, _ = ops.propagate_earth(std, earth, nubar, e2, c2)
+    assert float((p0 - ps).abs().max()) < 2e-12
+    pd, _, _ = ops.propagate_earth(consts, earth, nubar, e2, c2)
+    assert float(pd.sum(dim=2).max()) < 1 + 1e-12 and float(pd.sum(dim=1).max()) < 1 + 1e-12
+    assert float(pd.min()) >= 0.0
 
 
 def test_reference_fixture_events_earth_and_layers():

@@ -234,8 +234,12 @@ def test_stage_contract_errors():
         prob3(params=ParamSet(list(good) + [Param("bogus", 1.0)]))
     with pytest.raises(ValueError):
         prob3(params=good, nsi_type="quantum")
-    with pytest.raises(NotImplementedError):
+    # neutrino_decay=True adds decay_alpha3 (prob3.py:256-259) and selects the decay branch (:227-230)
+    with pytest.raises(ValueError, match="decay_alpha3"):
         prob3(params=good, neutrino_decay=True)
+    from pisa_b200.utils.units import ureg
+    d = prob3(params=ParamSet(list(good) + [Param("decay_alpha3", 1e-4 * ureg.eV ** 2)]), neutrino_decay=True)
+    assert d.decay_flag == 1 and d.neutrino_decay
     with pytest.raises(ValueError, match="not supported"):
         hist(calc_mode="log_events").setup()
     h = hist(calc_mode="events")
