@@ -210,29 +210,43 @@ prob3_layers_kernel(const __grid_constant__ OscTable osc, int nubar,
 }
 
 // ---- neutrino decay (decay_flag == 1, prob3_decay.cuh): the same two entry points with the general-matrix layer ----
-// One thread per event, state in registers / local memory, plain loads: this branch is an analysis option outside the
-// fit-loop default and is not tuned (one block per SM-quarter is plenty to hide its latencies).
+// One thread per event, state and per-event Hamiltonian in per-thread shared-memory columns like the standard kernels,
+// plain loads (a ~50k-cycle event hides them).
 constexpr int kDecayBlock = 128;
+#ifndef PISAB_DECAY_EARTH_MIN_BLOCKS
+#define PISAB_DECAY_EARTH_MIN_BLOCKS 3 // 168 registers; 2 / 3 / 4 blocks: 2.86 / 2.56 / 2.59 ms per 4e6 events (3x3 output, ordered)
+#endif
 
+template <bool FULL>
+static size_t earth_decay_smem_bytes() {
+    return (size_t)((FULL ? PropagatorSmem<3, 3>::kDoubles : PropagatorSmem<1, 2>::kDoubles) + H0DecaySmem::kDoubles) *
+           kDecayBlock * sizeof(double);
+}
 template <typename IO, bool FULL>
-__global__ void __launch_bounds__(kDecayBlock)
+__global__ void __launch_bounds__(kDecayBlock, PISAB_DECAY_EARTH_MIN_BLOCKS)
 prob3_earth_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec,
                          const __grid_constant__ EarthTable earth, int nubar, const int32_t *__restrict__ d_nubar,
                          int flav, const int32_t *__restrict__ d_flav, const IO *__restrict__ energy,
-                         const IO *__restrict__ coszen, int64_t n, IO *__restrict__ probability,
-                         IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
+                         const IO *__restrict__ coszen, const int32_t *__restrict__ order, int64_t n,
+                         IO *__restrict__ probability, IO *__restrict__ prob_e, IO *__restrict__ prob_mu) {
     constexpr int NR = FULL ? 3 : 1, NC = FULL ? 3 : 2;
+    extern __shared__ __align__(16) double s_dyn_decay[];
     __shared__ EarthTable s_earth;
+    double2(*s_state)[kDecayBlock] = reinterpret_cast<double2(*)[kDecayBlock]>(s_dyn_decay);
+    double(*s_h0)[kDecayBlock] = reinterpret_cast<double(*)[kDecayBlock]>(s_dyn_decay + PropagatorSmem<NR, NC>::kDoubles * kDecayBlock);
     copy_earth(earth, &s_earth);
+    const int tid = threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    // `order` (optional): events grouped by crossed shells, so that a warp's lanes walk the same number of layers
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + tid; t < n; t += stride) {
+        const int64_t i = order ? (int64_t)__ldg(order + t) : t;
         const double e = ld(energy, i), cz = ld(coszen, i);
         const int nb = d_nubar ? __ldg(d_nubar + i) : nubar;
         const int fl = d_flav ? __ldg(d_flav + i) : flav;
-        const double inv_e = 1.0 / e;
-        H0Decay h0;
+        const double inv_e = rcp_fast(e);
+        H0DecaySmem h0{&s_h0[0][tid], kDecayBlock};
         h0.init(herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr), dec, nb, inv_e);
-        Propagator<NR, NC> P;
+        PropagatorSmem<NR, NC> P{&s_state[0][tid], kDecayBlock};
         propagate_earth<NR, NC, false>(h0, osc, s_earth, cz, inv_e, nb, FULL ? 0 : fl, P);
         if (FULL) {
             IO *o = probability + i * 9;
@@ -249,7 +263,7 @@ prob3_earth_decay_kernel(const __grid_constant__ OscTable osc, const __grid_cons
 
 // propagate_array with decay_flag == 1 on explicit layers; same layer-cache rule as prob3_layers_kernel
 template <typename IO>
-__global__ void __launch_bounds__(kDecayBlock)
+__global__ void __launch_bounds__(kDecayBlock, PISAB_DECAY_EARTH_MIN_BLOCKS)
 prob3_layers_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec, int nubar,
                           const int32_t *__restrict__ d_nubar, const IO *__restrict__ energy,
                           const IO *__restrict__ densities, const IO *__restrict__ distances, int64_t n,
@@ -457,9 +471,11 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
                 double pe, pmu;
                 if constexpr (DECAY) {
-                    H0Decay h0;
+                    // (STD = true here only sizes the per-thread h0 column: 23 doubles, of which M0 takes 18)
+                    static_assert(STD && H0Smem<true>::kDoubles >= H0DecaySmem::kDoubles, "decay: h0 column too small");
+                    H0DecaySmem h0{&s_h0[0][tid], kBlock};
                     h0.init(hh, *dec, nb, inv_e);
-                    Propagator<1, 2> P;
+                    PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
                     propagate_earth<1, 2, false>(h0, osc, s_earth, cz, inv_e, nb, fl, P);
                     pe = P.prob(0, 0);
                     pmu = P.prob(0, 1);
@@ -572,9 +588,12 @@ reweight_hist_kernel(const __grid_constant__ OscTable osc, const __grid_constant
 
 // The template kernel of the decay branch: same grid / partials / epilogue contract as reweight_hist_kernel (so the
 // host code after the launch is shared), per-event outputs and in-kernel flux.barr_simple included; one instantiation
-// per storage type, one block of 256 threads per SM (the general-matrix layer wants ~200 registers).
+// per storage type; state and per-event Hamiltonian in the per-thread shared-memory columns of the standard kernel.
+#ifndef PISAB_DECAY_MIN_BLOCKS
+#define PISAB_DECAY_MIN_BLOCKS 2 // 128 registers (some spills) beat one block at 255: 15.6 vs 16.9 ms per 4.8e7 events
+#endif
 template <typename IO>
-__global__ void __launch_bounds__(kBlock, 1)
+__global__ void __launch_bounds__(kBlock, PISAB_DECAY_MIN_BLOCKS)
 reweight_hist_decay_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ DecayTable dec,
                            const __grid_constant__ EarthTable earth, const __grid_constant__ FusedBatch<IO> batch,
                            int ranks, double *__restrict__ partials, const __grid_constant__ FusedEpi epi) {
@@ -582,8 +601,8 @@ reweight_hist_decay_kernel(const __grid_constant__ OscTable osc, const __grid_co
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, false, false, false, false, true, true>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials,
-                                                                    s_hist, nullptr, 0, &dec);
+    fused_template_body<IO, true, false, false, false, true, true>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials,
+                                                                   s_hist, nullptr, 0, &dec);
     if (epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
@@ -847,16 +866,22 @@ static int propagate_earth_impl(const pisab_osc_consts_t *consts, const pisab_ea
         rc = build_decay_table(consts, &dt);
         if (rc) return rc;
         if (d_prob_e && d_probability && d_flav) { set_error("per-event flav with full probability output: call fill_probs per flavour"); return PISAB_ERR_ARG; }
-        const int grid = grid_for(n, 8) * (kBlock / kDecayBlock);
+        const int grid = grid_for(n, 2 * PISAB_DECAY_EARTH_MIN_BLOCKS) * (kBlock / kDecayBlock);
         LaunchTimer t(s);
         if (d_probability) {
-            prob3_earth_decay_kernel<IO, true><<<grid, kDecayBlock, 0, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy,
-                                                                          d_coszen, n, d_probability, nullptr, nullptr);
+            auto kernel = prob3_earth_decay_kernel<IO, true>;
+            const size_t smem = earth_decay_smem_bytes<true>();
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, kDecayBlock, smem, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n,
+                                                   d_probability, nullptr, nullptr);
             note_launch();
         }
         if (d_prob_e) {
-            prob3_earth_decay_kernel<IO, false><<<grid, kDecayBlock, 0, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy,
-                                                                           d_coszen, n, nullptr, d_prob_e, d_prob_mu);
+            auto kernel = prob3_earth_decay_kernel<IO, false>;
+            const size_t smem = earth_decay_smem_bytes<false>();
+            PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kernel<<<grid, kDecayBlock, smem, s>>>(ot, dt, et, nubar, d_nubar, flav, d_flav, d_energy, d_coszen, d_order, n,
+                                                   nullptr, d_prob_e, d_prob_mu);
             note_launch();
         }
         PISAB_CUDA_CHECK(cudaGetLastError());
@@ -922,7 +947,7 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
         rc = build_decay_table(consts, &dt);
         if (rc) return rc;
         LaunchTimer t(s);
-        prob3_layers_decay_kernel<IO><<<grid_for(n, 8) * (kBlock / kDecayBlock), kDecayBlock, 0, s>>>(
+        prob3_layers_decay_kernel<IO><<<grid_for(n, 2 * PISAB_DECAY_EARTH_MIN_BLOCKS) * (kBlock / kDecayBlock), kDecayBlock, 0, s>>>(
             ot, dt, nubar, d_nubar, d_energy, d_densities, d_distances, n, n_layers, d_probability);
         note_launch();
     } else {
@@ -1029,9 +1054,11 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         rc = build_decay_table(consts, &dt);
         if (rc) return rc;
         auto kernel = reweight_hist_decay_kernel<IO>;
-        const size_t smem = fused_smem_bytes<IO>(n_bins, false, false);
+        const size_t smem = fused_smem_bytes<IO>(n_bins, true, false); // (the standard-matter layout: see fused_template_body)
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int sms = sm_count() > 0 ? sm_count() : 148;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
+        const int sms = (sm_count() > 0 ? sm_count() : 148) * occ;
         const int nc = batch.n_containers;
         int64_t r = (n_max + (int64_t)kBlock * 8 - 1) / ((int64_t)kBlock * 8);
         const int64_t cap = (int64_t)sms * 8 / nc > 0 ? (int64_t)sms * 8 / nc : 1;

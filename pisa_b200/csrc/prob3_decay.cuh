@@ -10,44 +10,54 @@
 //     DecayTable; antineutrinos reuse the neutrino code exactly like the standard path (common.cuh): the probabilities
 //     of conj(X) equal those of -X, and -X = -hv/E + rho vm + lr + U (-conj(mat_decay)) U^dagger / 2E;
 //   * eigenvalues: the trace is removed (A = M - tr/3), the depressed cubic x^3 + p x + q of A is solved in complex
-//     arithmetic (Cardano with the cancellation-free choice of the cube root) and polished by two Newton steps;
+//     arithmetic (Cardano with the cancellation-free choice of the cube root; optional Newton polish, not needed);
 //   * exp(-i M t) = a0 + a1 A + a2 A^2 (Cayley-Hamilton form of the same Lagrange sum) times exp(Im(tr/3) t); only a
 //     unit-modulus phase is dropped.
-// Nothing here is tuned: decay is a per-analysis option, not the fit-loop default, and the path is ~3x the FP64 work
-// of the Hermitian one.  Everything is FP64 whatever the storage type.
+// Decay is a per-analysis option, not the fit-loop default: the path shares the fast primitives, the Earth walk and the
+// shared-memory state of the Hermitian one but is ~2.8x its FP64 work (27 complex products for A^2, three complex
+// exponentials, complex cube / square roots).  Everything is FP64 whatever the storage type.
 #pragma once
 #include "prob3_device.cuh"
 
 namespace pisab {
 
 // (DecayTable: common.cuh; built by build_decay_table, tables.cu)
+// (inlined: as separate functions the 3x3 complex arguments travel through local memory -- 19.3 instead of 15.6 ms per
+// 4.8e7 events, profiles/r02_decay.txt)
+#define PISAB_DECAY_FN __device__ __forceinline__
 
 __device__ __forceinline__ Cplx cadd(Cplx a, Cplx b) { return Cplx{a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return Cplx{a.re - b.re, a.im - b.im}; }
 __device__ __forceinline__ Cplx cscale(double s, Cplx a) { return Cplx{s * a.re, s * a.im}; }
 __device__ __forceinline__ double cnorm2(Cplx a) { return fma(a.re, a.re, a.im * a.im); }
+// (1 / |b|^2 from the MUFU-seeded reciprocal of prob3_device.cuh: ~1 ulp, no IEEE slow path)
 __device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
-    const double inv = 1.0 / cnorm2(b);
+    const double inv = rcp_fast(cnorm2(b));
     return Cplx{fma(a.re, b.re, a.im * b.im) * inv, fma(a.im, b.re, -a.re * b.im) * inv};
 }
+// principal square root; |z| from the fast square root (z == 0 gives 0)
 __device__ __forceinline__ Cplx csqrt_principal(Cplx z) {
-    const double m = hypot(z.re, z.im);
-    if (m == 0.0) return Cplx{0.0, 0.0};
-    const double a = sqrt(0.5 * (m + fabs(z.re)));
-    const double b = 0.5 * z.im / a;
+    const double m = sqrt_fast(cnorm2(z));
+    const double a2 = 0.5 * (m + fabs(z.re));
+    if (!(a2 > 0.0)) return Cplx{0.0, 0.0};
+    const double ia = rsqrt_fast(a2);
+    const double a = a2 * ia, b = 0.5 * z.im * ia;
     return z.re >= 0.0 ? Cplx{a, b} : Cplx{fabs(b), z.im < 0.0 ? -a : a};
 }
+// a cube root of z (the principal one): modulus by cbrt, direction by unit_cube_root (float seed + one third-order
+// correction, ~1e-18; it wants Im >= 0, the lower half plane goes through the conjugate)
 __device__ __forceinline__ Cplx ccbrt_principal(Cplx z) {
-    const double m = hypot(z.re, z.im);
-    if (m == 0.0) return Cplx{0.0, 0.0};
-    const double r = cbrt(m), th = atan2(z.im, z.re) * (1.0 / 3.0);
-    double s, c;
-    sincos(th, &s, &c);
-    return Cplx{r * c, r * s};
+    const double m2 = cnorm2(z);
+    if (!(m2 > 0.0)) return Cplx{0.0, 0.0};
+    const double im = rsqrt_fast(m2);
+    const double r = cbrt(m2 * im);
+    double c, s;
+    unit_cube_root(z.re * im, fabs(z.im) * im, &c, &s);
+    return Cplx{r * c, z.im < 0.0 ? -r * s : r * s};
 }
 
 // Roots of x^3 + p x + q (complex p, q).
-__device__ __noinline__ void depressed_cubic_roots(Cplx p, Cplx q, Cplx x[3]) {
+PISAB_DECAY_FN void depressed_cubic_roots(Cplx p, Cplx q, Cplx x[3]) {
     const Cplx hq = cscale(0.5, q), tp = cscale(1.0 / 3.0, p);
     const Cplx disc = cadd(cmul(hq, hq), cmul(cmul(tp, tp), tp));
     const Cplx s = csqrt_principal(disc);
@@ -62,8 +72,11 @@ __device__ __noinline__ void depressed_cubic_roots(Cplx p, Cplx q, Cplx x[3]) {
     x[0] = cadd(u, v);
     x[1] = cadd(cmul(u, w), cmul(v, wc));
     x[2] = cadd(cmul(u, wc), cmul(v, w));
+#ifndef PISAB_DECAY_NEWTON
+#define PISAB_DECAY_NEWTON 0 // Cardano alone matches the oracle to 2e-13, with one or two steps likewise (tests/hostemu)
+#endif
 #pragma unroll 1
-    for (int it = 0; it < 2; ++it)
+    for (int it = 0; it < PISAB_DECAY_NEWTON; ++it)
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const Cplx x2 = cmul(x[k], x[k]);
@@ -74,7 +87,7 @@ __device__ __noinline__ void depressed_cubic_roots(Cplx p, Cplx q, Cplx x[3]) {
 }
 
 // T = exp(-i M t) up to a unit-modulus phase, M a general complex 3x3 (eV^2/GeV), t = 2 * 2.534 * distance[km].
-__device__ __noinline__ void transition_matrix_general(const Cplx M[3][3], double t, Mat3 T) {
+PISAB_DECAY_FN void transition_matrix_general(const Cplx M[3][3], double t, Mat3 T) {
     const Cplx tr{(M[0][0].re + M[1][1].re + M[2][2].re) * (1.0 / 3.0), (M[0][0].im + M[1][1].im + M[2][2].im) * (1.0 / 3.0)};
     Cplx A[3][3];
 #pragma unroll
@@ -98,7 +111,7 @@ __device__ __noinline__ void transition_matrix_general(const Cplx M[3][3], doubl
     for (int k = 0; k < 3; ++k) {
         const Cplx xj = x[(k + 1) % 3], xl = x[(k + 2) % 3];
         double sn, cs;
-        sincos(x[k].re * t, &sn, &cs);
+        sincos_small(x[k].re * t, &sn, &cs);   // |phase| < 1e5 rad, as in the Hermitian path
         const double mag = exp((x[k].im + tr.im) * t);
         const Cplx e{mag * cs, -mag * sn};
         const Cplx w = cdiv(e, cmul(csub(x[k], xj), csub(x[k], xl)));
@@ -152,6 +165,37 @@ struct H0Decay {
 };
 template <>
 struct is_general_h0<H0Decay> {
+    static constexpr bool value = true;
+};
+
+// The same provider with M0 in a per-thread column of shared memory ([18][pitch] doubles, conflict free): frees 36
+// registers across the Earth walk of the template kernel.
+struct H0DecaySmem {
+    double *col; // &s[0][threadIdx.x]
+    int pitch;
+    static constexpr int kDoubles = 18;
+    __device__ __forceinline__ void init(const Herm3 &h, const DecayTable &d, int nubar, double inv_e) {
+        H0Decay r;
+        r.init(h, d, nubar, inv_e);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                col[((i * 3 + j) * 2) * pitch] = r.m0[i][j].re;
+                col[((i * 3 + j) * 2 + 1) * pitch] = r.m0[i][j].im;
+            }
+    }
+    __device__ __forceinline__ void layer(double rho, const Herm3 &vm, double t, Mat3 T) const {
+        H0Decay r;
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) r.m0[i][j] = Cplx{col[((i * 3 + j) * 2) * pitch], col[((i * 3 + j) * 2 + 1) * pitch]};
+        r.layer(rho, vm, t, T);
+    }
+};
+template <>
+struct is_general_h0<H0DecaySmem> {
     static constexpr bool value = true;
 };
 
