@@ -57,8 +57,8 @@ typedef struct pisab_osc_consts {
     double lri_pot[9];    /* long-range-interaction potential (eV), real symmetric            */
     int64_t decay_flag;   /* +1 = oscillations + neutrino decay (numba_osc_kernels.py:445-451, */
                           /* the numpy.linalg.eigvals branch: general-matrix kernels, FP64     */
-                          /* arithmetic whatever the storage type; one template per launch,    */
-                          /* so the multi-template scan entry points reject it);               */
+                          /* arithmetic whatever the storage type; a scan with at least one    */
+                          /* such template runs ALL its templates through these kernels);      */
                           /* any other value (-1 in the reference) = standard oscillations     */
 } pisab_osc_consts_t;
 

@@ -321,11 +321,12 @@ prob3_layers_decay_kernel(const __grid_constant__ OscTable osc, const __grid_con
 
 // dynamic shared memory of reweight_hist_kernel (layout documented in the kernel)
 template <typename IO>
-static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false) {
+static size_t fused_smem_bytes(int n_bins, bool std_matter, bool mp = false, bool decay = false) {
     // (FP32 mode: 9 float2 of state per thread = 9 doubles' worth; the Hamiltonian lives in registers)
+    // (decay: the 18 doubles of the general per-event matrix take the place of the packed Hermitian one)
+    const size_t h0_doubles = decay ? H0DecaySmem::kDoubles : (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles);
     const size_t doubles = mp ? (size_t)PropagatorSmemF<1, 2>::kSlots * kBlock
-                              : (size_t)(PropagatorSmem<1, 2>::kDoubles +
-                                         (std_matter ? H0Smem<true>::kDoubles : H0Smem<false>::kDoubles)) * kBlock;
+                              : (size_t)(PropagatorSmem<1, 2>::kDoubles + h0_doubles) * kBlock;
     return WarpHist::smem_bytes(kBlock, n_bins) + doubles * sizeof(double) + (size_t)kBlock * (5 * sizeof(IO) + 4);
 }
 
@@ -401,7 +402,7 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
     float2(*s_statef)[kBlock] = reinterpret_cast<float2(*)[kBlock]>(s_dyn); // FP32 mode: float2 state columns
     s_dyn += (MP ? PropagatorSmemF<1, 2>::kSlots : PropagatorSmem<1, 2>::kDoubles) * kBlock;
     double(*s_h0)[kBlock] = reinterpret_cast<double(*)[kBlock]>(s_dyn); // 16-byte aligned: see H0Smem
-    if (!MP) s_dyn += H0Smem<STD>::kDoubles * kBlock;   // (FP32 mode: the per-event Hamiltonian lives in registers)
+    if (!MP) s_dyn += (DECAY ? H0DecaySmem::kDoubles : H0Smem<STD>::kDoubles) * kBlock;   // (FP32 mode: the per-event Hamiltonian lives in registers)
     IO(*s_flux)[2] = reinterpret_cast<IO(*)[2]>(s_dyn);
     IO *s_e = &s_flux[kBlock][0], *s_cz = s_e + kBlock, *s_w = s_cz + kBlock;
     int32_t *s_bin = reinterpret_cast<int32_t *>(s_w + kBlock);
@@ -471,8 +472,6 @@ __device__ __forceinline__ void fused_template_body(const OscTable &osc, const E
                 const Herm3 hh = herm_axpy(nb > 0 ? inv_e : -inv_e, osc.hv[0], osc.lr); // hv[1] = -hv[0]
                 double pe, pmu;
                 if constexpr (DECAY) {
-                    // (STD = true here only sizes the per-thread h0 column: 23 doubles, of which M0 takes 18)
-                    static_assert(STD && H0Smem<true>::kDoubles >= H0DecaySmem::kDoubles, "decay: h0 column too small");
                     H0DecaySmem h0{&s_h0[0][tid], kBlock};
                     h0.init(hh, *dec, nb, inv_e);
                     PropagatorSmem<1, 2> P{&s_state[0][tid], kBlock};
@@ -601,8 +600,8 @@ reweight_hist_decay_kernel(const __grid_constant__ OscTable osc, const __grid_co
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_template_body<IO, true, false, false, false, true, true>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials,
-                                                                   s_hist, nullptr, 0, &dec);
+    fused_template_body<IO, false, false, false, false, true, true>(osc, s_earth, batch, ci, ci + 1, rank, ranks, partials,
+                                                                    s_hist, nullptr, 0, &dec);
     if (epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
@@ -759,6 +758,34 @@ reweight_hist_scan_kernel(const OscTable *__restrict__ tables, const __grid_cons
     copy_earth(earth, &s_earth); // ends with __syncthreads()
     double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
     fused_template_body<IO, STD, true, MP>(s_osc, s_earth, batch, ci, ci + 1, rank, ranks_per_template, mine, s_hist);
+}
+
+// The scan with neutrino decay: every template carries a DecayTable next to its OscTable (a template without decay
+// has a zero table and goes through the same general-matrix layers: equal to the standard kernels within 2e-12).
+template <typename IO>
+__global__ void __launch_bounds__(kBlock, PISAB_DECAY_MIN_BLOCKS)
+reweight_hist_scan_decay_kernel(const OscTable *__restrict__ tables, const DecayTable *__restrict__ dtables,
+                                const __grid_constant__ EarthTable earth, const __grid_constant__ FusedBatch<IO> batch,
+                                int ranks_per_template, double *__restrict__ partials) {
+    extern __shared__ __align__(16) double s_hist[];
+    __shared__ EarthTable s_earth;
+    __shared__ OscTable s_osc;
+    __shared__ DecayTable s_dec;
+    const int per_template = batch.n_containers * ranks_per_template;
+    const int tmpl = blockIdx.x / per_template, rem = blockIdx.x - tmpl * per_template;
+    const int ci = rem / ranks_per_template, rank = rem - ci * ranks_per_template;
+    {
+        const double *src = reinterpret_cast<const double *>(tables + tmpl);
+        double *dst = reinterpret_cast<double *>(&s_osc);
+        for (int i = threadIdx.x; i < (int)(sizeof(OscTable) / 8); i += blockDim.x) dst[i] = __ldg(src + i);
+        const double *srcd = reinterpret_cast<const double *>(dtables + tmpl);
+        double *dstd = reinterpret_cast<double *>(&s_dec);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecayTable) / 8); i += blockDim.x) dstd[i] = __ldg(srcd + i);
+    }
+    copy_earth(earth, &s_earth); // ends with __syncthreads()
+    double *mine = partials + (size_t)tmpl * batch.n_containers * ranks_per_template * 2 * batch.n_bins;
+    fused_template_body<IO, false, true, false, false, false, true>(s_osc, s_earth, batch, ci, ci + 1, rank, ranks_per_template,
+                                                                    mine, s_hist, nullptr, 0, &s_dec);
 }
 
 } // namespace pisab
@@ -1054,7 +1081,7 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         rc = build_decay_table(consts, &dt);
         if (rc) return rc;
         auto kernel = reweight_hist_decay_kernel<IO>;
-        const size_t smem = fused_smem_bytes<IO>(n_bins, true, false); // (the standard-matter layout: see fused_template_body)
+        const size_t smem = fused_smem_bytes<IO>(n_bins, false, false, true);
         PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kBlock, smem) != cudaSuccess || occ < 1) occ = 1;
@@ -1347,13 +1374,21 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     }
     std::vector<OscTable> tables((size_t)n_templates);
     bool all_std = true;
+    bool any_decay = false;
+    for (int t = 0; t < n_templates; ++t) any_decay = any_decay || consts[t].decay_flag == 1;
+    std::vector<DecayTable> dtables(any_decay ? (size_t)n_templates : 0);
     for (int t = 0; t < n_templates; ++t) {
-        if (consts[t].decay_flag == 1) {
-            set_error("scan: neutrino decay (decay_flag == 1) is evaluated one template per launch; call pisab_reweight_hist_batch_*");
-            return PISAB_ERR_UNSUPPORTED;
-        }
         const int rc = build_osc_table(consts + t, &tables[t]);
         if (rc) return rc;
+        if (any_decay) {
+            // one kernel for the whole scan: templates without decay get a zero table (and no vacuum shortcut)
+            tables[t].vac_ok = 0.0;
+            memset(&dtables[t], 0, sizeof(DecayTable));
+            if (consts[t].decay_flag == 1) {
+                const int rd = build_decay_table(consts + t, &dtables[t]);
+                if (rd) return rd;
+            }
+        }
         all_std = all_std && tables[t].std_matter != 0.0;
     }
     EarthTable et;
@@ -1363,10 +1398,31 @@ static int reweight_hist_scan_abi(const pisab_osc_consts_t *consts, int32_t n_te
     const int64_t need = pisab_reweight_scan_workspace_bytes(n_templates, n_containers, n_bins, n_max);
     if (!d_workspace || workspace_bytes < need) { set_error("workspace too small: need %lld bytes", (long long)need); return PISAB_ERR_WORKSPACE; }
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t table_bytes = ((size_t)n_templates * sizeof(OscTable) + 255) / 256 * 256;
+    const size_t osc_bytes = ((size_t)n_templates * sizeof(OscTable) + 255) / 256 * 256;
+    const size_t table_bytes = ((size_t)n_templates * (sizeof(OscTable) + sizeof(DecayTable)) + 511) / 256 * 256;
     OscTable *d_tables = (OscTable *)d_workspace;
+    DecayTable *d_dtables = (DecayTable *)((char *)d_workspace + osc_bytes);
     double *d_partials = (double *)((char *)d_workspace + table_bytes);
     PISAB_CUDA_CHECK(cudaMemcpyAsync(d_tables, tables.data(), (size_t)n_templates * sizeof(OscTable), cudaMemcpyHostToDevice, s));
+    if (any_decay) {
+        PISAB_CUDA_CHECK(cudaMemcpyAsync(d_dtables, dtables.data(), (size_t)n_templates * sizeof(DecayTable), cudaMemcpyHostToDevice, s));
+        auto kernel = reweight_hist_scan_decay_kernel<IO>;
+        const size_t smem = fused_smem_bytes<IO>(n_bins, false, false, true);
+        cudaFuncAttributes fa;
+        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+        int dev = 0, optin = 0;
+        PISAB_CUDA_CHECK(cudaGetDevice(&dev));
+        PISAB_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (fa.sharedSizeBytes + smem > (size_t)optin) { set_error("scan: %d bins exceed the shared-memory budget", n_bins); return PISAB_ERR_UNSUPPORTED; }
+        PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            LaunchTimer t(s);
+            kernel<<<n_templates * n_containers * ranks, kBlock, smem, s>>>(d_tables, d_dtables, et, batch, ranks, d_partials);
+            note_launch();
+        }
+        PISAB_CUDA_CHECK(cudaGetLastError());
+        return hist_reduce_batch(d_partials, ranks, n_bins, n_templates * n_containers, d_hist, s);
+    }
     const bool mp = sizeof(IO) == 4 && f32_math_mixed();
     const size_t smem = fused_smem_bytes<IO>(n_bins, all_std, mp);
     auto kernel = all_std ? scan_kernel<IO, true>(mp) : scan_kernel<IO, false>(mp);
@@ -1495,7 +1551,8 @@ int64_t pisab_reweight_scan_workspace_bytes(int32_t n_templates, int32_t n_conta
     if (n_templates < 1) n_templates = 1;
     if (n_containers < 1) n_containers = 1;
     const int ranks = scan_ranks(n_max, n_templates, n_containers);
-    const int64_t table_bytes = ((int64_t)n_templates * (int64_t)sizeof(OscTable) + 255) / 256 * 256;
+    // (per template: OscTable + DecayTable, each block rounded to 256 bytes -- see reweight_hist_scan_abi)
+    const int64_t table_bytes = ((int64_t)n_templates * (int64_t)(sizeof(OscTable) + sizeof(DecayTable)) + 511) / 256 * 256;
     return table_bytes + (int64_t)n_templates * n_containers * ranks * 2 * (int64_t)n_bins * (int64_t)sizeof(double);
 }
 int pisab_reweight_hist_scan_f64(const pisab_osc_consts_t *consts, int32_t n_templates, const pisab_earth_t *earth,

@@ -262,9 +262,6 @@ class ReweightEngine:
     def evaluate_many(self, consts_list, allreduce=None):
         """P hypotheses in ONE launch (``pisab_reweight_hist_scan``): returns ``[P, n_containers, 2, n_bins]``.
         The single histogram exchange covers all P templates when sharded over GPUs."""
-        if any(int(c.decay_flag) == 1 for c in consts_list):
-            # neutrino decay: the library evaluates one template per launch (pisab_reweight_hist_scan rejects it)
-            return torch.stack([self.evaluate(c, allreduce=allreduce).clone() for c in consts_list])
         self._materialize_flux()
         batches = self._get_batches()
         if len(batches) != 1:

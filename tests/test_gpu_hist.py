@@ -255,6 +255,14 @@ def test_fused_reweight_hist_with_neutrino_decay(dtype):
         std = ops.OscConsts.from_matrices(dm, mix, mat_pot)
         a, b = eng.evaluate(zero).cpu().numpy(), eng.evaluate(std).cpu().numpy()
         assert np.allclose(a, b, rtol=1e-10 if dtype == np.float64 else 1e-5)
+        # the multi-template scan: decay tables travel per template; a template without decay in the same scan goes
+        # through the general-matrix kernel too
+        dec2 = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, 3.0 * md)
+        many = eng.evaluate_many([consts, std, dec2]).cpu().numpy()
+        assert np.allclose(many[0], out, rtol=1e-12 if dtype == np.float64 else 1e-6)
+        assert np.allclose(many[1], b, rtol=1e-10 if dtype == np.float64 else 1e-5)
+        assert np.allclose(many[2], eng.evaluate(dec2).cpu().numpy(), rtol=1e-12 if dtype == np.float64 else 1e-6)
+        assert many[2][:, 0].sum() < many[0][:, 0].sum() < many[1][:, 0].sum()
         # the fit-loop form: template + container sum + mod_chi2 in the library call
         observed = torch.tensor(refs[0][0] + refs[1][0], device=dev)
         hist, chi2 = eng.evaluate_chi2(consts, observed)
