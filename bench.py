@@ -30,7 +30,7 @@ parity_check : the oracle chain (oracle/*.c) on a 1e5-event subsample of the ben
            path: bin indices bit-exact, binned weights relative.
 cpu_baseline : the reference's own numba kernels (baseline/_ref, `parallel` target, all host cores) on a bounded
            sample; the C/OpenMP oracle port is timed beside it (`cpu_baseline_port`).
-variants : measured in the same run at the current world size -- C4 (standard NSI, 1.25e8 events/GPU), the FP32
+variants : measured in the same run at the current world size -- neutrino decay, C4 (standard NSI, 1.25e8 events/GPU), the FP32
            mode, the 40x40x2 stress binning, and C5 (100-point theta23 x dm31 scan with device-side mod_chi2).
 """
 import argparse
@@ -118,11 +118,14 @@ def oracle_chain(oracle, L, mats, nubar, flav, ev, den=None, dis=None, n_threads
     weights *= flux.prob -> bin index -> histogram (w, w^2) (prob3.py:581-622; hist.py:198-209).
     Returns (hist[2, 128], index)."""
     from pisa_b200.utils import synthetic as syn
-    dm, mix, mat_pot = mats
+    dm, mix, mat_pot = mats[:3]
     zc, zf = np.zeros((3, 3), dtype=np.complex128), np.zeros((3, 3))
+    decay_flag = -1
+    if len(mats) > 3:   # neutrino decay: (dm, mix, mat_pot, mat_decay)
+        decay_flag, zc = 1, np.asarray(mats[3], dtype=np.complex128)
     if den is None:
         _, den, dis = L.calcLayers(ev["true_coszen"].astype(np.float64))
-    prob = oracle.propagate_array(dm, mix, mat_pot, -1, zc, zf, nubar, ev["true_energy"].astype(np.float64), den, dis,
+    prob = oracle.propagate_array(dm, mix, mat_pot, decay_flag, zc, zf, nubar, ev["true_energy"].astype(np.float64), den, dis,
                                   n_threads=n_threads or (os.cpu_count() or 1))
     pe, pmu = oracle.fill_probs(prob, 0, flav), oracle.fill_probs(prob, 1, flav)
     w = ev["weights"] * (ev["nu_flux"][:, 0] * pe + ev["nu_flux"][:, 1] * pmu)
@@ -495,6 +498,22 @@ def run_variants(h, args):
                         "bit_reproducible_run_to_run": bool(torch.equal(again, again2)), "steps": steps,
                         "warmup": warmup}
     del eng, res, again, again2
+    torch.cuda.empty_cache()
+
+    # ---- neutrino decay (prob3 neutrino_decay=True: the reference's numpy.linalg.eigvals branch) -------------------
+    eng, _, _, kept = h.build(n, np.float64, seed_base=90_000, keep=keep)
+    dm_, mix_, mp_ = syn.osc_matrices()
+    mat_decay = np.zeros((3, 3), dtype=np.complex128)
+    mat_decay[2, 2] = -1.0e-4j   # decay_params.py:47-55 with alpha3 = 1e-4 eV^2
+    c_dec = ops.OscConsts.from_matrices(dm_, mix_, mp_, 1, mat_decay)
+    ms, res = h.time_steps(lambda: eng.evaluate(c_dec), steps, warmup)
+    par = parity_check(h, kept, (dm_, mix_, mp_, mat_decay), lambda e: e.evaluate(c_dec, allreduce=False)) if kept else None
+    out["decay"] = {"value": n * h.world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "events_per_gpu": n,
+                    "parity_check": par, "dtype": "f64", "n_bins": 128, "steps": steps, "warmup": warmup,
+                    "what": "osc.prob3 with neutrino_decay=True (decay_flag = 1, alpha3 = 1e-4 eV^2): non-Hermitian layer "
+                            "Hamiltonian, general-matrix kernels (csrc/prob3_decay.cuh); the reference solves it with "
+                            "numpy.linalg.eigvals per layer on the CPU"}
+    del eng, res
     torch.cuda.empty_cache()
 
     # ---- C5: theta23 x dm31 scan, mod_chi2 on device, every point a full template --------------------------

@@ -876,7 +876,8 @@ def test_pipeline_in_fp32_process_mode(tmp_path):
         assert np.allclose(a, b, rtol=2e-2, atol=2e-3 * b.max()), (m.name, np.abs(a - b).max() / b.max())
 
 
-@pytest.mark.parametrize("cfg", ["settings/pipeline/b200_events.cfg", "settings/pipeline/b200_icecube3y_full.cfg"])
+@pytest.mark.parametrize("cfg", ["settings/pipeline/b200_events.cfg", "settings/pipeline/b200_icecube3y_full.cfg",
+                                 "settings/pipeline/b200_events_decay.cfg"])
 def test_fused_pipeline_equals_staged_pipeline(cfg):
     """FusedPipeline replaces osc.prob3 -> aeff.aeff -> utils.hist by one fused launch and must return the MapSet of
     Pipeline.get_outputs(): maps and sumw2 errors within 1e-10, also after oscillation, aeff, flux and detector
@@ -907,6 +908,13 @@ def test_fused_pipeline_equals_staged_pipeline(cfg):
             p.params.delta_index = 0.04 * ureg.dimensionless
             p.params.nue_numu_ratio = 1.03 * ureg.dimensionless
         compare()
+    if "decay_alpha3" in names:                      # osc.prob3 with neutrino_decay = True: the decay kernels in both forms
+        before = fused.get_outputs()
+        for p in (staged, fused.pipeline):
+            p.params.decay_alpha3 = 4.0e-4 * ureg.eV ** 2
+        compare()
+        after = fused.get_outputs()
+        assert sum(m.hist.sum() for m in after) < 0.99 * sum(m.hist.sum() for m in before)
     if "opt_eff_overall" in names:                   # discr_sys.hypersurfaces downstream of the histogram stage
         for p in (staged, fused.pipeline):
             p.params.opt_eff_overall = 1.08 * ureg.dimensionless
