@@ -176,7 +176,7 @@ class PisabArgError(PisabError, ValueError):
 
 
 class PisabUnsupportedError(PisabError, NotImplementedError):
-    """PISAB_ERR_UNSUPPORTED: a branch of the reference that is outside the hot path (e.g. neutrino decay)."""
+    """PISAB_ERR_UNSUPPORTED: a branch of the reference that is outside the hot path (e.g. a non-Hermitian matter potential) or a combination an entry point does not fuse."""
 
 
 _ERR_CLASSES = {1: PisabArgError, 3: PisabUnsupportedError}
