@@ -32,7 +32,8 @@ extern "C" {
 #endif
 
 #define PISAB_MAX_RADII 64   /* PREM_59layer + atmosphere = 61 shells                     */
-#define PISAB_MAX_LAYERS 120 /* hard cap of the reference, numba_osc_kernels.py:173-177,227 */
+#define PISAB_MAX_LAYERS 120 /* layer-matrix cache of the reference, numba_osc_kernels.py:173-177,227; explicit   */
+                             /* layer arrays may be up to 2 * PISAB_MAX_RADII wide (PREM_59layer: 122)         */
 #define PISAB_MAX_DIMS 4
 
 enum {

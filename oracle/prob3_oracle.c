@@ -396,7 +396,11 @@ int SUFFIX(oracle_osc_probs_layers)(const real_t dm[3][3], const cplx mix[3][3],
                                     int64_t nubar, real_t energy, const real_t *density,
                                     const real_t *distance, int n_layers, real_t osc_probs[3][3]) {
     cplx H_vac[3][3], H_decay[3][3], mixn[3][3], mixn_ct[3][3], prod[3][3], T[3][3], tmp[3][3];
-    if (n_layers > MAX_LAYERS) return -3;
+    /* transition_matrices has 120 slots (:227) but the loops run over the array's width (:230,282): PREM_59layer
+     * arrives 122 wide with at most 118 active slots and works; an ACTIVE slot >= 120 would be written out of bounds */
+    for (int i = MAX_LAYERS; i < n_layers; ++i)
+        if (distance[i] > 0) return -3;
+    if (n_layers > MAX_LAYERS) n_layers = MAX_LAYERS;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
             mixn[i][j] = nubar > 0 ? mix[i][j] : c_conj(mix[i][j]);

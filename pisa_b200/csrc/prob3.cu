@@ -959,8 +959,11 @@ static int propagate_layers_impl(const pisab_osc_consts_t *consts, int32_t nubar
         set_error("bad event arrays");
         return PISAB_ERR_ARG;
     }
-    if (n_layers < 1 || n_layers > PISAB_MAX_LAYERS) {
-        set_error("n_layers = %d outside [1, %d] (numba_osc_kernels.py:227)", n_layers, PISAB_MAX_LAYERS);
+    // The reference caches at most 120 layer matrices (numba_osc_kernels.py:173-177,227) but loops over the arrays' width:
+    // PREM_59layer arrives 122 wide (2 * 61 shells, at most 118 active) and works there.  The kernels here keep no
+    // per-layer array, so the width is only bounded by the shell table.
+    if (n_layers < 1 || n_layers > 2 * PISAB_MAX_RADII) {
+        set_error("n_layers = %d outside [1, %d]", n_layers, 2 * PISAB_MAX_RADII);
         return PISAB_ERR_ARG;
     }
     if (!d_nubar && nubar != 1 && nubar != -1) { set_error("nubar must be +1 or -1"); return PISAB_ERR_ARG; }

@@ -44,6 +44,14 @@ def test_device_math_on_host_lri_and_other_earth_models(emu):
     assert emu.run(n=20000, model="PREM_4layer.dat", depth=10.0, seed=8) < 1e-10
 
 
+def test_device_math_on_host_prem59_maximum_depth(emu):
+    """PREM_59layer: 61 shells, layer arrays 122 wide with up to 118 active slots -- the largest Earth model the reference
+    ships and the limit of its 120-slot layer cache (numba_osc_kernels.py:173-177,227)."""
+    assert emu.run(n=6000, model="PREM_59layer.dat", seed=9) < 1e-10
+    assert emu.run(n=4000, nsi=True, nubar=-1, model="PREM_59layer.dat", seed=10) < 1e-10
+    assert emu.run_decay(n=3000, model="PREM_59layer.dat", seed=11) < 1e-10
+
+
 @pytest.mark.parametrize("nsi,nubar", [(False, 1), (True, -1)])
 def test_fp32_mode_math_on_host_within_1e5_of_fp64_oracle(emu, nsi, nubar):
     """The mixed-precision FP32 mode (prob3_mp.cuh: FP64 eigenvalues / phases, float matrices and state) against the

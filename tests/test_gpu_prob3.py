@@ -238,6 +238,53 @@ def test_random_parameter_points_vs_oracle():
     assert worst < 2e-12, worst
 
 
+def test_prem59_maximum_depth_vs_oracle():
+    """The largest Earth model of the reference (PREM_59layer: 61 shells, 122-wide layer arrays, up to 118 active slots,
+    the limit of the reference's 120-slot layer cache): in-kernel layers and explicit layers, standard matter, NSI and
+    decay, nu and nubar, vertical / core-tangent directions included, AC_KW on every probability; the fused template over
+    the same events against the oracle chain."""
+    from pisa_b200 import ops
+    dev = _dev()
+    g = load_golden("ref_prob3_f8.npz")
+    L, earth = _earth(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_59layer.dat"))
+    assert L.max_layers == 122
+    rng = np.random.default_rng(59)
+    n = 30_000
+    energy = 10 ** rng.uniform(0, 3, n)
+    coszen = rng.uniform(-1, 1, n)
+    coszen[:6] = [-1.0, -0.9999, -0.8376, -0.9815, 0.0, 1.0]
+    nl, den, dis = L.calcLayers(coszen)
+    assert (dis[:, 120:] == 0).all() and int((dis > 0).sum(axis=1).max()) >= 110
+    e, cz = torch.tensor(energy, device=dev), torch.tensor(coszen, device=dev)
+    zero = np.zeros((3, 3), dtype=np.complex128)
+    gd = load_golden("ref_decay_f8.npz")
+    cases = [("nufit20_nh_dcp306/nu", 1, -1, zero), ("nufit20_nh_dcp306_stdnsi/nu", -1, -1, zero),
+             ("nufit20_nh_dcp306_stdnsi/nu", 1, 1, gd["nufit20_nh_dcp306_stdnsi_a2e-4/nu/mat_decay"])]
+    for key, nubar, decay_flag, md in cases:
+        dm, mix, mat_pot = g[key + "/dm"], g[key + "/mix"], g[key + "/mat_pot"]
+        consts = ops.OscConsts.from_matrices(dm, mix, mat_pot, decay_flag, md)
+        ref = oracle.propagate_array(dm, mix, mat_pot, decay_flag, md, np.zeros((3, 3)), nubar, energy, den, dis,
+                                     n_threads=os.cpu_count())
+        what = "PREM_59 %s nubar=%d decay=%d" % (key, nubar, decay_flag)
+        full, _, _ = ops.propagate_earth(consts, earth, nubar, e, cz)
+        _assert_prob(full.cpu().numpy(), ref, what + " earth")
+        lay = ops.propagate_layers(consts, nubar, e, torch.tensor(den, device=dev), torch.tensor(dis, device=dev))
+        _assert_prob(lay.cpu().numpy(), ref, what + " layers")
+        order = ops.layer_order(earth, cz)
+        _, pe, pmu = ops.propagate_earth(consts, earth, nubar, e, cz, flav=1, want_probability=False, order=order)
+        _assert_prob(pe.cpu().numpy(), ref[:, 0, 1], what + " prob_e")
+        _assert_prob(pmu.cpu().numpy(), ref[:, 1, 1], what + " prob_mu")
+        # fused template
+        flux = rng.uniform(0.5, 1.5, (n, 2))
+        w0 = rng.uniform(0, 1, n)
+        idx = rng.integers(-1, 128, n).astype(np.int32)
+        w = w0 * (flux[:, 0] * ref[:, 0, 1] + flux[:, 1] * ref[:, 1, 1])
+        h, h2 = ops.reweight_hist(consts, earth, nubar, 1, e, cz, torch.tensor(flux, device=dev), torch.tensor(w0, device=dev),
+                                  torch.tensor(idx, device=dev), 128, order=order)
+        assert np.allclose(h.cpu().numpy(), oracle.accumulate(idx, w, 128), rtol=1e-10)
+        assert np.allclose(h2.cpu().numpy(), oracle.accumulate(idx, w * w, 128), rtol=2e-10)
+
+
 def test_decay_random_parameter_points_vs_oracle():
     """24 random decay hypotheses -- mixing parameters and mass ordering, alpha3 from 1e-6 to 2e-3 eV^2 (log-uniform;
     every third point a general complex decay matrix instead of diag(0, 0, -i alpha3)), standard NSI and a long-range
