@@ -16,12 +16,15 @@ import torch
 
 from . import ops
 
-__all__ = ["osc_consts", "osc_consts_array", "scan_chi2", "asimov", "fit_chi2", "OSC_PARAM_NAMES"]
+__all__ = ["osc_consts", "osc_consts_array", "scan_chi2", "asimov", "fit_chi2", "OSC_PARAM_NAMES", "DECAY_PARAM_NAME"]
 
 OSC_PARAM_NAMES = ("theta12", "theta13", "theta23", "deltacp", "dm21", "dm31")
+# optional seventh parameter of the drivers below: invisible decay of the third mass state (prob3 neutrino_decay=True,
+# prob3.py:76-88; decay_params.py:47-55: mat_decay = diag(0, 0, -i alpha3), decay_flag = 1)
+DECAY_PARAM_NAME = "decay_alpha3"
 
 
-def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
+def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None, decay_alpha3=None):
     """OscConsts from mixing angles (rad) and mass splittings (eV^2), like prob3.compute_function builds
     them (prob3.py:485-559); ``mat_pot`` defaults to the standard matter potential diag(1, 0, 0).
     Scalar arithmetic with the formulas of ``OscParams`` (sines via numpy like its setters, cosines as
@@ -50,17 +53,21 @@ def osc_consts(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
         mp = np.asarray(mat_pot, dtype=np.complex128).reshape(3, 3)
         c.mat_pot[:] = np.stack([mp.real, mp.imag], axis=-1).ravel()
     c.decay_flag = -1
+    if decay_alpha3 is not None:
+        c.decay_flag = 1
+        c.mat_decay[17] = -float(decay_alpha3)   # Im of element [2][2]
     return c
 
 
-def osc_consts_array(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None):
+def osc_consts_array(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=None, decay_alpha3=None):
     """Vectorised ``osc_consts``: any of the six parameters may be an array of P values (the others
     broadcast); returns a ctypes array ``OscConsts[P]`` for ``ops.reweight_hist_scan``.  Same arithmetic as
     ``OscParams`` (sines stored, cosines as sqrt(1 - s^2), osc_params.py:175-211,266-292); building the
     hypotheses one by one costs ~50 us each in Python, which would dominate a scan over an analysis-size
-    sample."""
-    t12, t13, t23, dcp, m21, m31 = np.broadcast_arrays(*[np.atleast_1d(np.asarray(x, dtype=np.float64))
-                                                         for x in (theta12, theta13, theta23, deltacp, dm21, dm31)])
+    sample.  ``decay_alpha3`` (scalar or array, eV^2; None = no decay) selects the decay branch for every hypothesis."""
+    cols = [theta12, theta13, theta23, deltacp, dm21, dm31] + ([decay_alpha3] if decay_alpha3 is not None else [])
+    cols = np.broadcast_arrays(*[np.atleast_1d(np.asarray(x, dtype=np.float64)) for x in cols])
+    t12, t13, t23, dcp, m21, m31 = cols[:6]
     n = t12.shape[0]
     if not np.all((dcp >= 0.0) & (dcp <= 2 * np.pi)):
         raise AssertionError("deltacp must be within [0, 2pi]")
@@ -93,6 +100,9 @@ def osc_consts_array(theta12, theta13, theta23, deltacp, dm21, dm31, mat_pot=Non
         mp = np.asarray(mat_pot, dtype=np.complex128).reshape(3, 3)
         rec[:, 27:45] = np.stack([mp.real, mp.imag], axis=-1).ravel()
     rec[:, 72] = np.array([-1], dtype=np.int64).view(np.float64)[0]   # decay_flag = -1
+    if decay_alpha3 is not None:
+        rec[:, 45 + 17] = -cols[6]                                     # mat_decay[2][2] = -i alpha3
+        rec[:, 72] = np.array([1], dtype=np.int64).view(np.float64)[0]
     arr = (ops.OscConsts * n).from_buffer_copy(np.ascontiguousarray(rec).tobytes())
     return arr
 
@@ -112,21 +122,23 @@ def scan_chi2(engine, observed, points, fixed, mat_pot=None, batch=64):
     engine   : ReweightEngine with resident containers (scales set through ``set_scales``)
     observed : float64 device tensor [n_bins]
     points   : iterable of (theta23 [rad], dm31 [eV^2])
-    fixed    : dict theta12, theta13, deltacp [rad], dm21 [eV^2]
+    fixed    : dict theta12, theta13, deltacp [rad], dm21 [eV^2]; optionally decay_alpha3 [eV^2] (neutrino decay)
     Returns a float64 device tensor [n_points] (no host synchronisation happens here).
     """
     points = list(points)
     out = torch.empty(len(points), dtype=torch.float64, device=engine.device)
+    alpha3 = fixed.get(DECAY_PARAM_NAME)
     if batch <= 1:
         for i, (t23, dm31) in enumerate(points):
-            consts = osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot)
+            consts = osc_consts(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mat_pot,
+                                decay_alpha3=alpha3)
             engine.evaluate_chi2(consts, observed, chi2_out=out[i:i + 1])   # one call, two launches per hypothesis
         return out
     pts = np.asarray(points, dtype=np.float64).reshape(-1, 2)
     for lo in range(0, len(points), batch):
         chunk = pts[lo:lo + batch]
         consts = osc_consts_array(fixed["theta12"], fixed["theta13"], chunk[:, 0], fixed["deltacp"], fixed["dm21"],
-                                  chunk[:, 1], mat_pot)
+                                  chunk[:, 1], mat_pot, decay_alpha3=alpha3)
         hist = engine.evaluate_many(consts)
         ops.template_chi2_batch(hist, observed, out=out[lo:lo + len(chunk)])
     return out
@@ -141,8 +153,9 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
     parameters -- in ONE launch (``ReweightEngine.evaluate_many`` + ``template_chi2_batch``) and reads 2k + 1
     doubles back: for an analysis-size sample a launch is latency-bound, so the gradient costs nothing extra.
 
-    start  : dict name -> start value for the free parameters (names from ``OSC_PARAM_NAMES``; rad / eV^2)
-    fixed  : dict with the remaining parameters
+    start  : dict name -> start value for the free parameters (names from ``OSC_PARAM_NAMES``; rad / eV^2; and
+             optionally ``decay_alpha3`` [eV^2]: neutrino decay, every hypothesis then runs the decay kernels)
+    fixed  : dict with the remaining parameters (``decay_alpha3`` only when decay is wanted)
     bounds : optional dict name -> (lo, hi)
     steps  : optional dict name -> finite-difference half step (default 1e-4 of the start value's magnitude)
     Returns ``scipy.optimize.OptimizeResult`` with ``x`` as a dict, plus ``n_templates`` evaluated.
@@ -150,8 +163,10 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
     from scipy import optimize
     names = list(start)
     for nm in names + list(fixed):
-        if nm not in OSC_PARAM_NAMES:
-            raise ValueError("unknown oscillation parameter %r (known: %s)" % (nm, ", ".join(OSC_PARAM_NAMES)))
+        if nm not in OSC_PARAM_NAMES and nm != DECAY_PARAM_NAME:
+            raise ValueError("unknown oscillation parameter %r (known: %s, %s)"
+                             % (nm, ", ".join(OSC_PARAM_NAMES), DECAY_PARAM_NAME))
+    with_decay = DECAY_PARAM_NAME in start or DECAY_PARAM_NAME in fixed
     missing = [nm for nm in OSC_PARAM_NAMES if nm not in start and nm not in fixed]
     if missing or set(start) & set(fixed):
         raise ValueError("every oscillation parameter must be either free or fixed (missing: %s)" % missing)
@@ -162,7 +177,7 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
     h = np.array([float((steps or {}).get(nm, 1e-4 * s)) for nm, s in zip(names, scale)])
     # physical domains the host-side parameter code enforces (osc_params.py: deltacp in [0, 2 pi]): a stencil point or a
     # minimiser step outside would abort the fit with an AssertionError, so they act as default bounds
-    domain = {"deltacp": (0.0, 2 * np.pi)}
+    domain = {"deltacp": (0.0, 2 * np.pi), DECAY_PARAM_NAME: (0.0, np.inf)}
     def _bound(nm, k):
         user = (bounds or {}).get(nm, (-np.inf, np.inf))[k]
         dom = domain.get(nm, (-np.inf, np.inf))[k]
@@ -182,7 +197,7 @@ def fit_chi2(engine, observed, start, fixed, bounds=None, steps=None, mat_pot=No
         args = {nm: pts[:, i] for i, nm in enumerate(names)}
         args.update(fixed)
         consts = osc_consts_array(args["theta12"], args["theta13"], args["theta23"], args["deltacp"], args["dm21"],
-                                  args["dm31"], mat_pot)
+                                  args["dm31"], mat_pot, decay_alpha3=args[DECAY_PARAM_NAME] if with_decay else None)
         ops.template_chi2_batch(engine.evaluate_many(consts), observed, out=out)
         counter[0] += 2 * k + 1
         c = out.cpu().numpy()

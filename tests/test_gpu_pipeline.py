@@ -686,6 +686,22 @@ def test_fit_chi2_recovers_injected_parameters():
         scan.fit_chi2(eng, observed, dict(theta24=0.1), fixed)
     with pytest.raises(ValueError):
         scan.fit_chi2(eng, observed, dict(theta23=0.7), fixed)          # dm31 neither free nor fixed
+    # neutrino decay as a seventh parameter: pseudo-data made with alpha3 = 2e-4 eV^2, fit over (theta23, alpha3); every
+    # objective call is ONE launch of the decay scan kernel over 5 hypotheses
+    truth_d = dict(theta23=truth["theta23"], decay_alpha3=2.0e-4)
+    fixed_d = dict(fixed, dm31=truth["dm31"])
+    observed_d = scan.asimov(eng, scan.osc_consts(**truth_d, **fixed_d))
+    assert float(observed_d.sum()) < 0.999 * float(observed.sum())
+    res = scan.fit_chi2(eng, observed_d, dict(theta23=np.deg2rad(40.0), decay_alpha3=5.0e-5), fixed_d,
+                        bounds=dict(theta23=(np.deg2rad(30.0), np.deg2rad(45.0)), decay_alpha3=(0.0, 1.0e-3)))
+    assert res.fun < 1e-6, res
+    assert abs(res.x["theta23"] - truth_d["theta23"]) < 5e-4 and abs(res.x["decay_alpha3"] / 2.0e-4 - 1) < 5e-3, res.x
+    # the scan driver with a fixed alpha3: batched and one-launch-per-template forms agree, minimum at the truth
+    pts = [(t, truth["dm31"]) for t in np.deg2rad(np.linspace(38.0, 47.0, 7))] + [(truth["theta23"], truth["dm31"])]
+    fx = dict(fixed, decay_alpha3=2.0e-4)
+    c_many = scan.scan_chi2(eng, observed_d, pts, fx, batch=8).cpu().numpy()
+    c_one = scan.scan_chi2(eng, observed_d, pts, fx, batch=1).cpu().numpy()
+    assert np.allclose(c_many, c_one, rtol=1e-9, atol=1e-12) and int(c_many.argmin()) == len(pts) - 1 and c_many.min() < 1e-12
 
 
 def test_hist_stage_with_binned_calc_mode_uses_a_transform():
