@@ -384,6 +384,61 @@ def test_full_size_properties_of_the_fused_path():
     assert float((p.sum(dim=1) - 1).abs().max()) < 5e-12 and float((p.sum(dim=2) - 1).abs().max()) < 5e-12
 
 
+def test_full_size_properties_of_the_decay_path():
+    """The decay template kernel at a BASELINE-size launch (1.2e7 events per container): checksum of checksums, exact
+    linearity under a power-of-two weight scale, bit-reproducibility, permutation invariance, monotonic loss of
+    probability in alpha3, and agreement of the template's per-event weights with the stand-alone decay kernel."""
+    from pisa_b200 import ops
+    from pisa_b200.utils import synthetic as syn
+    dev = _dev()
+    L = oracle.OracleLayers(np.loadtxt(os.path.join(ROOT, "pisa_b200", "resources", "osc", "PREM_12layer.dat")), 2.0, 20.0)
+    L.setElecFrac(0.4656, 0.4656, 0.4957)
+    earth = ops.Earth.from_arrays(L.radii, L.rhos, L.coszen_limit, L.r_detector, L.max_layers)
+    dm, mix, mat_pot = syn.osc_matrices(nsi=syn.STD_NSI)
+    md = np.zeros((3, 3), dtype=complex)
+    md[2, 2] = -2.0e-4j
+    consts = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, md)
+    binning, keep = ops.make_binning(syn.DRAGON_DIMS, dev)
+    n = 12_000_000
+    ev = syn.make_events_torch(n, seed=6, dtype=np.float64, device=dev)
+    ev["reco_coszen"][::89] = 1.5
+    idx = ops.hist_index(binning, [ev["reco_energy"], ev["reco_coszen"], ev["pid"]])
+    inside = idx >= 0
+    wout = torch.empty(n, dtype=torch.float64, device=dev)
+    args = (consts, earth, 1, 1, ev["true_energy"], ev["true_coszen"], ev["nu_flux"])
+    h, h2 = ops.reweight_hist(*args, ev["weights"], idx, 128, weights_out=wout)
+    assert abs(float(h.sum()) / float(wout[inside].sum()) - 1) < 1e-12
+    assert abs(float(h2.sum()) / float((wout[inside] ** 2).sum()) - 1) < 1e-12
+    assert float(wout.min()) >= 0.0 and torch.isfinite(wout).all()
+    ref = torch.zeros(128, dtype=torch.float64, device=dev).index_add_(0, idx[inside].long(), wout[inside])
+    assert torch.allclose(h, ref, rtol=1e-11, atol=0)
+    hb, _ = ops.reweight_hist(*args, ev["weights"], idx, 128)
+    assert torch.equal(h, hb)
+    h4, h42 = ops.reweight_hist(*args, (ev["weights"] * 4.0).contiguous(), idx, 128)
+    assert torch.equal(h4, 4.0 * h) and torch.equal(h42, 16.0 * h2)
+    perm = torch.randperm(n, device=dev)
+    hp, _ = ops.reweight_hist(consts, earth, 1, 1, ev["true_energy"][perm].contiguous(),
+                              ev["true_coszen"][perm].contiguous(), ev["nu_flux"][perm].contiguous(),
+                              ev["weights"][perm].contiguous(), idx[perm].contiguous(), 128)
+    assert torch.allclose(hp, h, rtol=1e-11, atol=0)
+    # the stand-alone decay kernel gives the template's per-event weights
+    _, pe, pmu = ops.propagate_earth(consts, earth, 1, ev["true_energy"], ev["true_coszen"], flav=1, want_probability=False)
+    w_ref = ev["weights"] * (ev["nu_flux"][:, 0] * pe + ev["nu_flux"][:, 1] * pmu)
+    assert torch.allclose(wout, w_ref, rtol=1e-12, atol=1e-15)
+    # more decay, fewer events -- in every bin (numu appearance + survival both lose the nu3 component)
+    totals = []
+    for alpha in (0.0, 1.0e-4, 2.0e-4, 8.0e-4):
+        md[2, 2] = -1j * alpha
+        c = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, md)
+        totals.append(float(ops.reweight_hist(c, earth, 1, 1, ev["true_energy"], ev["true_coszen"], ev["nu_flux"],
+                                              ev["weights"], idx, 128)[0].sum()))
+    assert totals[0] > totals[1] > totals[2] > totals[3]
+    # no probability is created: rows and columns of the full matrix sum to at most one
+    p, _, _ = ops.propagate_earth(consts, earth, 1, ev["true_energy"][:4_000_000].contiguous(),
+                                  ev["true_coszen"][:4_000_000].contiguous())
+    assert float(p.sum(dim=1).max()) < 1 + 1e-12 and float(p.sum(dim=2).max()) < 1 + 1e-12 and float(p.min()) >= 0.0
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32, None])
 def test_large_input_histogram(dtype):
     """3e6 events through the stand-alone histogram kernel: ragged tail, invalid and out-of-range indices,
