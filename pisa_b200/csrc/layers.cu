@@ -17,9 +17,9 @@ __host__ __device__ inline int layers_row_bytes(int max_layers) { return 4 * (((
 constexpr int kLayersWarps = 8;
 constexpr unsigned char kNoShell = 255;
 
-template <typename IO>
+template <typename IO, bool FULL_ROWS>
 __global__ void __launch_bounds__(32 * kLayersWarps)
-layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO *__restrict__ coszen,
+layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, int rows_arg, const IO *__restrict__ coszen,
               int64_t n, IO *__restrict__ densities, IO *__restrict__ distances,
               int32_t *__restrict__ n_layers) {
     extern __shared__ __align__(16) unsigned char s_raw[];
@@ -32,24 +32,32 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int row = layers_row_stride(max_layers), row_b = layers_row_bytes(max_layers);
-    // [warps][32][row] distances (IO), then [warps][32][row_b] shell indices (bytes)
-    IO *tile_dis = reinterpret_cast<IO *>(s_raw) + (size_t)warp * 32 * row;
-    unsigned char *tile_sh = s_raw + (size_t)(blockDim.x >> 5) * 32 * row * sizeof(IO) + (size_t)warp * 32 * row_b;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int rows = FULL_ROWS ? 32 : rows_arg; // (a compile-time 32 for the usual models: no predicates, no idle lanes)
+    // [warps][rows][row] distances (IO), then [warps][rows][row_b] shell indices (bytes); `rows` (<= 32) directions per
+    // warp and pass: 32 for the usual Earth models, fewer for very deep ones (PREM_59layer: 122 slots) so that the tile
+    // does not cost the occupancy -- the lanes beyond `rows` only help with the copy-out
+    const int n_warps = blockDim.x >> 5;
+    IO *tile_dis = reinterpret_cast<IO *>(s_raw) + (size_t)warp * rows * row;
+    unsigned char *tile_sh = s_raw + (size_t)n_warps * rows * row * sizeof(IO) + (size_t)warp * rows * row_b;
+    const int64_t stride = (int64_t)gridDim.x * n_warps * rows;
     // warp-uniform trip count: every lane takes part in the copy-out of its warp's tile
-    for (int64_t first = (int64_t)blockIdx.x * blockDim.x + warp * 32; first < n; first += stride) {
+    for (int64_t first = ((int64_t)blockIdx.x * n_warps + warp) * rows; first < n; first += stride) {
         const int64_t i = first + lane;
-        const bool live = i < n;
+        const bool live = lane < rows && i < n;
         const IO czs = live ? __ldg(coszen + i) : (IO)1;
         const double cz = (double)czs;
-        unsigned char *sh = tile_sh + lane * row_b;
-        IO *dis = tile_dis + lane * row;
+        // (idle lanes compute the trivial down-going case into row 0's shadow: they write nothing, see `put`)
+        unsigned char *sh = tile_sh + (lane < rows ? lane : 0) * row_b;
+        IO *dis = tile_dis + (lane < rows ? lane : 0) * row;
+        const bool writer = FULL_ROWS || lane < rows;
         const int idx = E.idx_first_inner;
         const double base = __dmul_rn(-E.r_det, cz);
         int count = 0, slot = 0;
         auto put = [&](int shell, double seg) {
-            sh[slot] = seg > 0.0 ? (unsigned char)shell : kNoShell;
-            dis[slot] = (IO)seg;
+            if (writer) {
+                sh[slot] = seg > 0.0 ? (unsigned char)shell : kNoShell;
+                dis[slot] = (IO)seg;
+            }
             count += seg > 0.0;
             ++slot;
         };
@@ -62,7 +70,8 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
                 put(j, __dsub_rn(l_cur, l_next));
                 l_cur = l_next;
             }
-            for (; slot < E.n_radii && slot < max_layers; ++slot) { sh[slot] = kNoShell; dis[slot] = (IO)0; }
+            if (writer)
+                for (; slot < E.n_radii && slot < max_layers; ++slot) { sh[slot] = kNoShell; dis[slot] = (IO)0; }
         } else {
             // layers.py:105-159; `coszen**2` (int exponent) stays in FTYPE under numba's typing
             const double cz2 = sizeof(IO) == 4 ? (double)__fmul_rn((float)czs, (float)czs) : __dmul_rn(cz, cz);
@@ -86,8 +95,10 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
                         const double s_lo = j >= idx ? __dsub_rn(base, sq_j) : 0.0;
                         const double out = __dsub_rn(s_hi, s_lo);
                         const int o = 2 * K - 2 - j;
-                        sh[o] = out > 0.0 ? (unsigned char)j : kNoShell;
-                        dis[o] = (IO)out;
+                        if (writer) {
+                            sh[o] = out > 0.0 ? (unsigned char)j : kNoShell;
+                            dis[o] = (IO)out;
+                        }
                         count += out > 0.0;
                     }
                     sq_j = sq_next;
@@ -98,11 +109,12 @@ layers_kernel(const __grid_constant__ EarthTable earth, int max_layers, const IO
             }
             slot = 2 * K - 2 > slot ? 2 * K - 2 : slot;
         }
-        for (; slot < max_layers; ++slot) { sh[slot] = kNoShell; dis[slot] = (IO)0; }
+        if (writer)
+            for (; slot < max_layers; ++slot) { sh[slot] = kNoShell; dis[slot] = (IO)0; }
         if (n_layers && live) n_layers[i] = count;
         __syncwarp();
         const int64_t rows_left = n - first;
-        const int total = (int)(rows_left < 32 ? rows_left : 32) * max_layers;
+        const int total = (int)(rows_left < rows ? rows_left : rows) * max_layers;
         IO *out_den = densities + first * max_layers, *out_dis = distances + first * max_layers;
         // element k = r * max_layers + c of the warp's contiguous output block; (r, c) advanced by 32 per step
         int r = lane / max_layers, c = lane - r * max_layers;
@@ -161,19 +173,22 @@ static int layers_impl(const pisab_earth_t *earth, const IO *d_coszen, int64_t n
     const int sms = sm_count() > 0 ? sm_count() : 148;
     // 32 rows per warp: distances as IO + one byte of shell index per slot; as many warps per block (<= kLayersWarps)
     // as ~200 KB of shared memory hold (PREM_59layer: 122 slots)
-    const size_t per_warp = (size_t)32 * (layers_row_stride(earth->max_layers) * sizeof(IO) + layers_row_bytes(earth->max_layers));
-    int warps = (int)((200 * 1024) / per_warp);
-    warps = warps > kLayersWarps ? kLayersWarps : warps;
-    if (warps < 1) { set_error("max_layers too large"); return PISAB_ERR_UNSUPPORTED; }
+    // rows per warp and pass: 32, halved until a block of kLayersWarps warps stays below ~72 KB (three blocks per SM)
+    const size_t per_row = layers_row_stride(earth->max_layers) * sizeof(IO) + layers_row_bytes(earth->max_layers);
+    int rows = 32;
+    while (rows > 4 && (size_t)rows * per_row * kLayersWarps > 72 * 1024) rows /= 2;
+    const size_t per_warp = (size_t)rows * per_row;
+    const int warps = kLayersWarps;
     if (et.n_radii >= (int)kNoShell) { set_error("too many shells"); return PISAB_ERR_UNSUPPORTED; }
     const size_t smem = per_warp * warps;
-    int64_t want = (n + 32 * warps - 1) / (32 * warps);
+    int64_t want = (n + rows * warps - 1) / (rows * warps);
     int occ = 0;
-    PISAB_CUDA_CHECK(cudaFuncSetAttribute(layers_kernel<IO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, layers_kernel<IO>, 32 * warps, smem) != cudaSuccess || occ < 1) occ = 1;
+    auto kernel = rows == 32 ? layers_kernel<IO, true> : layers_kernel<IO, false>;
+    PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * warps, smem) != cudaSuccess || occ < 1) occ = 1;
     const int grid = (int)(want < (int64_t)sms * occ * 4 ? want : (int64_t)sms * occ * 4);
-    layers_kernel<IO><<<grid, 32 * warps, smem, (cudaStream_t)stream>>>(et, earth->max_layers, d_coszen, n, d_densities,
-                                                                       d_distances, d_n_layers);
+    kernel<<<grid, 32 * warps, smem, (cudaStream_t)stream>>>(et, earth->max_layers, rows, d_coszen, n, d_densities,
+                                                             d_distances, d_n_layers);
     note_launch();
     PISAB_CUDA_CHECK(cudaGetLastError());
     return PISAB_OK;
