@@ -97,7 +97,7 @@ def test_decay_reference_fixture_events_earth_and_layers():
 
 @pytest.mark.parametrize("nubar", [1, -1])
 def test_decay_large_random_sample_vs_oracle(nubar):
-    """2e5 seeded events with decay + NSI + deltacp against the oracle's eigvals branch (pinned to the reference by
+    """1e6 seeded events with decay + NSI + deltacp against the oracle's eigvals branch (pinned to the reference by
     tests/test_oracle_golden.py), the per-event nubar form, float storage, and two size-independent properties on
     1e6 events: alpha3 = 0 through the decay kernels equals the standard kernels, and decay only removes probability."""
     from pisa_b200 import ops
@@ -108,7 +108,7 @@ def test_decay_large_random_sample_vs_oracle(nubar):
     consts = ops.OscConsts.from_matrices(dm, mix, mat_pot, 1, md)
     L, earth = _earth()
     rng = np.random.default_rng(3)
-    n = 200_000
+    n = 1_000_000
     energy = 10 ** rng.uniform(0, 3, n)
     coszen = rng.uniform(-1, 1, n)
     _, den, dis = L.calcLayers(coszen)
