@@ -611,20 +611,22 @@ reweight_hist_decay_kernel(const __grid_constant__ OscTable osc, const __grid_co
 // events 2k and 2k+1 cross the same Earth shells, no `order` indirection, no per-event outputs.
 // Block of 128 threads, four blocks per SM (128 registers): the same 16 warps per SM as 2 x 256, but finer-grained
 // (measured +6 %, profiles/r02_pair_kernel_variants.txt); three blocks of 256 at 85 registers spill (-25 %).
+// The block size is a template parameter: multi-wave grids of the standard-matter instantiation run 2.2 % faster
+// still with 64 threads x 8 blocks (6.79 instead of 6.94 ms per 9.6e7 events; NSI: level), while analysis-size
+// single-wave templates want the 128-thread blocks (64: 66 instead of 35 us per 1.2e5-event template, 32 x 16: 101 us;
+// profiles/r02_pair_kernel_variants.txt) -- the host picks (reweight_hist_batch_impl).
 #ifndef PISAB_PAIR_BLOCK
 #define PISAB_PAIR_BLOCK 128
 #endif
-#ifndef PISAB_PAIR_MIN_BLOCKS
-#define PISAB_PAIR_MIN_BLOCKS 4
-#endif
 constexpr int kPairBlock = PISAB_PAIR_BLOCK;
-static size_t fused_pair_smem_bytes(int n_bins) {
-    return WarpHist::smem_bytes(kPairBlock, n_bins) +
-           (size_t)kPairBlock * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48) +
-           (size_t)(kPairBlock / 32) * 32 * sizeof(double); // second staging row of WarpHist::add2
+constexpr int kPairBlockSmall = 64; // multi-wave grids, standard matter
+static size_t fused_pair_smem_bytes(int n_bins, int block = kPairBlock) {
+    return WarpHist::smem_bytes(block, n_bins) +
+           (size_t)block * (PropagatorSmemP<1, 2>::kSlots * sizeof(float4) + H0MP2<true>::kSlots * sizeof(float2) + 48) +
+           (size_t)(block / 32) * 32 * sizeof(double); // second staging row of WarpHist::add2
 }
 
-template <bool STD, bool FLUX, bool MIX>
+template <bool STD, bool FLUX, bool MIX, int kPairBlock>
 __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const EarthTable &s_earth,
                                                 const FusedBatch<float> &batch, int ci, int rank, int n_ranks,
                                                 double *__restrict__ partials, double *s_hist, int mode) {
@@ -719,8 +721,8 @@ __device__ __forceinline__ void fused_pair_body(const OscTable &osc, const Earth
     wh.flush(partials + ((size_t)ci * n_ranks + rank) * 2 * n_bins);
 }
 
-template <bool STD, bool FLUX = false, bool MIX = false>
-__global__ void __launch_bounds__(kPairBlock, PISAB_PAIR_MIN_BLOCKS)
+template <bool STD, bool FLUX = false, bool MIX = false, int BLOCK = kPairBlock>
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
 reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_constant__ EarthTable earth,
                           const __grid_constant__ FusedBatch<float> batch, int ranks, double *__restrict__ partials,
                           const unsigned long long *__restrict__ /* bounds: same signature as reweight_hist_kernel */,
@@ -729,7 +731,7 @@ reweight_hist_pair_kernel(const __grid_constant__ OscTable osc, const __grid_con
     __shared__ EarthTable s_earth;
     copy_earth(earth, &s_earth);
     const int ci = blockIdx.x / ranks, rank = blockIdx.x - ci * ranks;
-    fused_pair_body<STD, FLUX, MIX>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist, interleave);
+    fused_pair_body<STD, FLUX, MIX, BLOCK>(osc, s_earth, batch, ci, rank, ranks, partials, s_hist, interleave);
     if (MIX && epi.out) fused_epilogue(epi, partials, ci, ranks, batch.n_containers, batch.n_bins, s_hist);
 }
 
@@ -1158,33 +1160,33 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
                           : (std_matter ? reweight_hist_pair_kernel<true, false> : reweight_hist_pair_kernel<false, false>);
         }
     }
-    const size_t smem = pairs ? fused_pair_smem_bytes(n_bins) : smem_events;
+    size_t smem = pairs ? fused_pair_smem_bytes(n_bins) : smem_events;
     const int64_t n_units = pairs ? (n_max + 1) / 2 : n_max;   // what a thread iterates over: events or pairs
     const int64_t unit_min = pairs ? 4 : 8;                    // >= 8 events per thread
-    const int block = pairs ? kPairBlock : kBlock;
-    {
-        // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
-        cudaFuncAttributes fa;
-        PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
-        int dev = 0, optin = 0;
-        PISAB_CUDA_CHECK(cudaGetDevice(&dev));
-        PISAB_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        if (fa.sharedSizeBytes + smem > (size_t)optin) {
-            set_error("fused reweight+hist: %d bins need %zu bytes of shared memory per block (limit %d); "
-                      "use propagate_earth + hist_accumulate", n_bins, fa.sharedSizeBytes + smem, optin);
-            return PISAB_ERR_UNSUPPORTED;
-        }
-        if (fa.sharedSizeBytes + smem > 48 * 1024)
-            PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+    int block = pairs ? kPairBlock : kBlock;
     // ranks (blocks) per container: at most PISAB_SPREAD_WAVES waves of resident blocks in total (blocks of
     // different containers differ in cost, so they are kept short: 1/32 of the run each; 4 waves cost 12 %, 8
     // waves 5 %, 32 and 64 are level -- profiles/r01_fused_kernel_variants.txt) with >= 8 events per thread;
     // small containers instead get up to one block per 256 events as long as one resident wave holds them all
     // (latency of one or two events per template)
-    int ranks;
+    int ranks = 1, resident_blocks = 1;
     bool single_wave = false; // the whole grid is resident at once: spread the expensive events over the SMs (interleave)
-    {
+    auto plan = [&]() -> int {
+        {
+            // static (tables) + dynamic (histogram, per-thread state and staging) exceed the 48 KB default
+            cudaFuncAttributes fa;
+            PISAB_CUDA_CHECK(cudaFuncGetAttributes(&fa, kernel));
+            int dev = 0, optin = 0;
+            PISAB_CUDA_CHECK(cudaGetDevice(&dev));
+            PISAB_CUDA_CHECK(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            if (fa.sharedSizeBytes + smem > (size_t)optin) {
+                set_error("fused reweight+hist: %d bins need %zu bytes of shared memory per block (limit %d); "
+                          "use propagate_earth + hist_accumulate", n_bins, fa.sharedSizeBytes + smem, optin);
+                return PISAB_ERR_UNSUPPORTED;
+            }
+            if (fa.sharedSizeBytes + smem > 48 * 1024)
+                PISAB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
         int occ = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, smem) != cudaSuccess || occ < 1) occ = 1;
         const int resident = (sm_count() > 0 ? sm_count() : 148) * occ;
@@ -1205,7 +1207,29 @@ static int reweight_hist_batch_impl(const pisab_osc_consts_t *consts, const pisa
         if (r > ws_cap) r = ws_cap;
         if (r < 1) r = 1;
         ranks = (int)r;
+        resident_blocks = resident;
         single_wave = (int64_t)ranks * nc <= resident;
+        return PISAB_OK;
+    };
+    rc = plan();
+    if (rc) return rc;
+    if (pairs && std_matter && (int64_t)ranks * batch.n_containers >= 8 * (int64_t)resident_blocks) {
+        // long multi-wave grid of the standard-matter pair kernel: 64 threads x 8 blocks per SM (see kPairBlockSmall;
+        // a two-wave grid -- 1.2e6 events -- is 2 % faster with the 128-thread blocks)
+        if constexpr (sizeof(IO) == 4) {
+            const auto kernel0 = kernel;
+            const int block0 = block, ranks0 = ranks;
+            const size_t smem0 = smem;
+            kernel = flux ? reweight_hist_pair_kernel<true, true, false, kPairBlockSmall>
+                          : reweight_hist_pair_kernel<true, false, false, kPairBlockSmall>;
+            block = kPairBlockSmall;
+            smem = fused_pair_smem_bytes(n_bins, block);
+            rc = plan();
+            if (rc) return rc;
+            if (single_wave) { // (twice the resident blocks could hold it after all: stay with the 128-thread form)
+                kernel = kernel0; block = block0; smem = smem0; ranks = ranks0; single_wave = false;
+            }
+        }
     }
     if (pairs && single_wave) {
         // the instantiation with the interleaved chunk order and the in-kernel epilogue (same registers and shared memory)

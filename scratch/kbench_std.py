@@ -46,11 +46,12 @@ def run(path, n_total=48_000_000, dtype=np.float64):
 
 if __name__ == "__main__":
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 48_000_000
+    dtype = np.float32 if (len(sys.argv) > 2 and sys.argv[2] == "f32") else np.float64
     libs = [("base", BASE)] + [(os.path.basename(p)[8:-3], p) for p in sorted(glob.glob(os.path.join(ROOT, "scratch", "variants", "libpisa_*.so")))]
     for rep in range(2):
         for tag, path in libs:
             try:
-                (t0, c0, _), (t1, c1, _) = run(path, n)
+                (t0, c0, _), (t1, c1, _) = run(path, n, dtype)
                 print("%-12s std %8.3f ms %.3e ev/s chk %.15e | nsi %8.3f ms %.3e ev/s chk %.15e" % (
                     tag, t0, n / t0 * 1e3, c0, t1, n / t1 * 1e3, c1), flush=True)
             except Exception as e:

@@ -5,6 +5,10 @@ import os, sys, time
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+if os.environ.get("PISAB_LIB"):   # A/B of prebuilt library variants (scratch/variants/)
+    from pisa_b200 import _lib, build as _B
+    _B.LIB = os.path.abspath(os.environ["PISAB_LIB"])
+    _lib._build.LIB = _B.LIB
 from pisa_b200 import ops, scan
 from pisa_b200.engine import ReweightEngine
 from pisa_b200.stages.osc.layers import Layers
