@@ -85,6 +85,26 @@ def test_vectorised_osc_consts_equal_the_scalar_builder():
             assert bytes(one) == bytes(arr[k]), k
     with pytest.raises(AssertionError):
         scan.osc_consts_array(0.5, 0.1, 0.7, 7.0, 7e-5, 2e-3)
+    # the optional seventh parameter (neutrino decay): decay_flag = 1 and mat_decay = diag(0, 0, -i alpha3), the record
+    # DecayParams + OscConsts.from_matrices give; per-hypothesis values and a broadcast scalar
+    from pisa_b200 import ops
+    from pisa_b200.stages.osc.decay_params import DecayParams
+    alpha = rng.uniform(0, 1e-3, n)
+    arr = scan.osc_consts_array(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mp,
+                                decay_alpha3=alpha)
+    arr_s = scan.osc_consts_array(fixed["theta12"], fixed["theta13"], t23, fixed["deltacp"], fixed["dm21"], dm31, mp,
+                                  decay_alpha3=2.0e-4)
+    for k in range(n):
+        one = scan.osc_consts(fixed["theta12"], fixed["theta13"], t23[k], fixed["deltacp"], fixed["dm21"], dm31[k], mp,
+                              decay_alpha3=alpha[k])
+        assert bytes(one) == bytes(arr[k]) and int(arr[k].decay_flag) == 1 and int(arr_s[k].decay_flag) == 1
+        d = DecayParams()
+        d.decay_alpha3 = alpha[k]
+        op = OscParams()
+        op.theta12, op.theta13, op.theta23, op.deltacp, op.dm21, op.dm31 = 0.58, 0.148, t23[k], 4.1, 7.5e-5, dm31[k]
+        ref = ops.OscConsts.from_matrices(op.dm_matrix, op.mix_matrix_complex, mp, 1, d.decay_matrix)
+        assert bytes(ref) == bytes(one), k
+        assert list(arr_s[k].mat_decay)[16:18] == [0.0, -2.0e-4]
 
 
 def test_scalar_osc_consts_equal_oscparams_matrices():
