@@ -179,3 +179,19 @@ def test_lri_and_tomography_parameter_classes():
     w = Core_scaling_wo_constrain()
     w.core_density_scale, w.innermantle_density_scale, w.middlemantle_density_scale = 1.1, 0.9, 1.05
     assert w.scaling_factor_array.tolist() == [1.0, 1.05, 0.9, 1.1, 1.1, 1.1]
+
+
+def test_fit_driver_argument_checks_need_no_device():
+    """scan.fit_chi2 validates its parameter names before it touches the engine: the six oscillation parameters must
+    each be free or fixed exactly once, decay_alpha3 is the only optional seventh name."""
+    from pisa_b200 import scan
+    fixed = dict(theta12=0.58, theta13=0.148, deltacp=4.1, dm21=7.5e-5)
+    with pytest.raises(ValueError, match="unknown oscillation parameter"):
+        scan.fit_chi2(None, None, dict(theta24=0.1), fixed)
+    with pytest.raises(ValueError, match="free or fixed"):
+        scan.fit_chi2(None, None, dict(theta23=0.7), fixed)                      # dm31 missing
+    with pytest.raises(ValueError, match="free or fixed"):
+        scan.fit_chi2(None, None, dict(theta23=0.7, dm31=2.5e-3, decay_alpha3=1e-4), dict(fixed, decay_alpha3=2e-4))
+    with pytest.raises(ValueError, match="unknown oscillation parameter"):
+        scan.fit_chi2(None, None, dict(theta23=0.7, dm31=2.5e-3), dict(fixed, decay_alpha4=1e-4))
+    assert scan.DECAY_PARAM_NAME == "decay_alpha3" and scan.DECAY_PARAM_NAME not in scan.OSC_PARAM_NAMES
